@@ -1,0 +1,796 @@
+// gf_capi.cu -- extern "C" entry points declared in include/gofeature_b200.h.
+//
+// Thin: argument validation, string unpacking, exception containment.  All behaviour
+// lives in gf_runtime.cu (host logic) and the kernels.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "gf_device.cuh"
+#include "gf_runtime.h"
+
+namespace gf {
+const std::string &error_detail();
+}
+
+using namespace gf;
+
+namespace {
+
+struct Msg {
+    int code;
+    const char *name;
+    const char *text;
+};
+// texts are the errors.New strings of error.go:9-49
+const Msg kMsgs[] = {
+    {GF_OK, "", "ok"},
+    {GF_ERR_BUFFER_WRITE_OUT_OF_RANGE, "ErrBufferWriteOutofRange", "try to write too much data into buffer"},
+    {GF_ERR_BUFFER_COPY_OUT_OF_RANGE, "ErrBufferCopyOutofRange", "try to copy too much data from source buffer"},
+    {GF_ERR_BUFFER_SLICE_OUT_OF_RANGE, "ErrBufferSliceOutofRange", "slice buffer out of range"},
+    {GF_ERR_INVALID_BUFFER_DATA, "ErrInvalidBufferData", "invalid buffer data"},
+    {GF_ERR_ALLOCATE_GPU_BUFFER, "ErrAllocateGPUBuffer", "failed to allocate gpu buffer"},
+    {GF_ERR_INVALID_DEVICE_ID, "ErrInvalidDeviceID", "invalid device id"},
+    {GF_ERR_INVALID_FEATURES, "ErrInvalidFeautres", "invalid features in request"},
+    {GF_ERR_FEATURE_SET_NOT_FOUND, "ErrFeatureSetNotFound", "feature set not found"},
+    {GF_ERR_INVALID_SET_STATE, "ErrInvalidSetState", "invalid set state"},
+    {GF_ERR_FEATURE_SET_EXIST, "ErrFeatureSetExist", "feature set is already exist"},
+    {GF_ERR_TOO_MUCH_GPU_MEMORY, "ErrTooMuchGPUMemory", "use too much gpu memory"},
+    {GF_ERR_ALLOCAT_GPU_MEMORY, "ErrAllocatGPUMemory", "fail to allocate gpu memory"},
+    {GF_ERR_SLICE_GPU_BUFFER, "ErrSliceGPUBuffer", "fail to slice gpu buffer"},
+    {GF_ERR_NOT_ENOUGH_BLOCKS, "ErrNotEnoughBlocks", "cache does not have enough blocks"},
+    {GF_ERR_OUT_OF_BATCH, "ErrOutOfBatch", "requests out of batch limit"},
+    {GF_ERR_MISMATCH_DIMENSION, "ErrMismatchDimension", "feature with mismatch dimension"},
+    {GF_ERR_WRITE_INPUT_BUFFER, "ErrWriteInputBuffer", "failed to write input buffer"},
+    {GF_ERR_WRITE_OUTPUT_BUFFER, "ErrWriteOutputBuffer", "failed to write output buffer"},
+    {GF_ERR_BLOCK_IS_FULL, "ErrBlockIsFull", "block is full"},
+    {GF_ERR_BLOCK_USED, "ErrBlockUsed", "block is used"},
+    {GF_ERR_WRITE_CUDA_BUFFER, "ErrWriteCudaBuffer", "write to cuda buffer error"},
+    {GF_ERR_SLICE_BUFFER, "ErrSliceBuffer", "fail to slice cuda buffer"},
+    {GF_ERR_CLEAR_CUDA_BUFFER, "ErrClearCudaBuffer", "clear cuda buffer failed"},
+    {GF_ERR_ALL_DEVICE, "ErrAllDevice", "fail to list all cuda device"},
+    {GF_ERR_CREATE_CONTEXT, "ErrCreateContext", "fail to create cuda context"},
+    {GF_ERR_BAD_TRANSPOSE_VALUE, "ErrBadTransposeValue", "invalid transpose value to transpose"},
+    {GF_ERR_INVALID_ARGUMENT, "", "invalid argument"},
+    {GF_ERR_CUDA, "", "cuda runtime error"},
+    {GF_ERR_READ_CUDA_BUFFER, "", "fail to read buffer vec3"},
+    {GF_ERR_UNSUPPORTED, "", "unsupported on the search path"},
+};
+
+const Msg *find_msg(int status)
+{
+    for (const Msg &m : kMsgs)
+        if (m.code == status) return &m;
+    return nullptr;
+}
+
+// concatenated ids + n+1 offsets -> strings; empty ids are invalid (an empty FeatureID marks a
+// free slot, block.go:159,239)
+int unpack_ids(int64_t n, const char *ids, const uint64_t *off, std::vector<std::string> &out)
+{
+    if (n < 0 || (n > 0 && (!ids || !off))) return GF_ERR_INVALID_ARGUMENT;
+    out.clear();
+    out.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (off[i + 1] <= off[i]) return GF_ERR_INVALID_FEATURES;
+        out.emplace_back(ids + off[i], (size_t)(off[i + 1] - off[i]));
+    }
+    return GF_OK;
+}
+
+template <typename F>
+int guarded(F &&f)
+{
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        set_error_detail("out of host memory");
+        return GF_ERR_INVALID_ARGUMENT;
+    } catch (const std::exception &e) {
+        set_error_detail(e.what());
+        return GF_ERR_INVALID_ARGUMENT;
+    } catch (...) {
+        set_error_detail("unknown exception");
+        return GF_ERR_INVALID_ARGUMENT;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gf_strerror(int status)
+{
+    const Msg *m = find_msg(status);
+    return m ? m->text : "unknown status";
+}
+const char *gf_status_name(int status)
+{
+    const Msg *m = find_msg(status);
+    return m ? m->name : "";
+}
+const char *gf_last_error_detail(void) { return error_detail().c_str(); }
+const char *gf_version(void) { return "gofeature_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ host utilities (util.go)
+int gf_util_normalize_float32(const float *in, float *out, int64_t n)
+{
+    if (n < 0 || (n > 0 && (!in || !out))) return GF_ERR_INVALID_ARGUMENT;
+    volatile float mode = 0.0f;  // volatile: keep the float32 rounding of every step (util.go:126-129)
+    for (int64_t i = 0; i < n; ++i) {
+        volatile float sq = in[i] * in[i];
+        mode = mode + sq;
+    }
+    float m = (float)pow((double)mode, 0.5);  // util.go:130
+    if (m == 0.0f) {
+        for (int64_t i = 0; i < n; ++i) out[i] = 0.0f;  // util.go:131-133
+        return GF_OK;
+    }
+    for (int64_t i = 0; i < n; ++i) out[i] = in[i] / m;  // util.go:135-137
+    return GF_OK;
+}
+
+int gf_util_transpose_1d(int precision, const void *features, int64_t row, int64_t len0, void *ret)
+{
+    if (row == 0) return GF_OK;  // util.go:23-25
+    if (precision <= 0 || row < 0 || len0 < 0 || !features || !ret) return GF_ERR_INVALID_ARGUMENT;
+    if (len0 % precision != 0) return GF_ERR_BAD_TRANSPOSE_VALUE;  // util.go:26-28
+    const int64_t col = len0 / precision;
+    const uint8_t *src = (const uint8_t *)features;
+    uint8_t *dst = (uint8_t *)ret;
+    for (int64_t i = 0; i < col; ++i)
+        for (int64_t j = 0; j < row; ++j)
+            memcpy(dst + (i * row + j) * precision, src + j * len0 + i * precision, (size_t)precision);
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------ device / context
+int gf_device_count(int *out_count)
+{
+    if (!out_count) return GF_ERR_INVALID_ARGUMENT;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out_count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount", GF_ERR_ALL_DEVICE);
+    }
+    *out_count = n;
+    return GF_OK;
+}
+
+int gf_device_total_mem(int device, uint64_t *out_bytes)
+{
+    if (!out_bytes) return GF_ERR_INVALID_ARGUMENT;
+    cudaDeviceProp p;
+    GF_CUDA(cudaGetDeviceProperties(&p, device), GF_ERR_INVALID_DEVICE_ID);
+    *out_bytes = (uint64_t)p.totalGlobalMem;
+    return GF_OK;
+}
+
+int gf_context_create(int device, gf_context **out_ctx)
+{
+    if (!out_ctx) return GF_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    return guarded([&]() -> int {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", GF_ERR_CREATE_CONTEXT);
+        if (device < 0 || device >= n) return GF_ERR_INVALID_DEVICE_ID;
+        GF_CUDA(cudaSetDevice(device), GF_ERR_CREATE_CONTEXT);
+        cudaDeviceProp p;
+        GF_CUDA(cudaGetDeviceProperties(&p, device), GF_ERR_CREATE_CONTEXT);
+        if (p.major < 10) {
+            set_error_detail("gofeature_b200 kernels are built for sm_100a only");
+            return GF_ERR_CREATE_CONTEXT;
+        }
+        std::unique_ptr<gf_context> c(new gf_context());
+        c->device = device;
+        c->sms = p.multiProcessorCount;
+        GF_CUDA(cudaStreamCreateWithFlags(&c->mut_stream, cudaStreamNonBlocking), GF_ERR_CREATE_CONTEXT);
+        c->stage_bytes = (size_t)8 << 20;
+        for (int i = 0; i < 2; ++i) {
+            GF_CUDA(cudaMallocHost((void **)&c->stage[i], c->stage_bytes), GF_ERR_CREATE_CONTEXT);
+            GF_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming), GF_ERR_CREATE_CONTEXT);
+        }
+        *out_ctx = c.release();
+        return GF_OK;
+    });
+}
+
+int gf_context_destroy(gf_context *ctx)
+{
+    if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    delete ctx;
+    return GF_OK;
+}
+
+int gf_context_device(const gf_context *ctx) { return ctx ? ctx->device : -1; }
+
+int gf_context_synchronize(gf_context *ctx)
+{
+    if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
+    return GF_OK;
+}
+
+int gf_context_stats(const gf_context *ctx, gf_stats *out)
+{
+    if (!ctx || !out) return GF_ERR_INVALID_ARGUMENT;
+    const_cast<gf_context *>(ctx)->prof_collect();
+    const Stats &s = ctx->stats;
+    out->scan_kernel_ns = s.scan_kernel_ns;
+    out->scan_kernel_timed = s.scan_kernel_timed;
+    out->searches = s.searches;
+    out->scan_launches = s.scan_launches;
+    out->gemm_launches = s.gemm_launches;
+    out->merge_launches = s.merge_launches;
+    out->other_launches = s.other_launches;
+    out->rows_scanned = s.rows_scanned;
+    out->quirk_fallbacks = s.quirk_fallbacks;
+    out->coalesced_batches = s.coalesced_batches;
+    out->h2d_bytes = s.h2d_bytes;
+    out->d2h_bytes = s.d2h_bytes;
+    return GF_OK;
+}
+
+int gf_context_reset_stats(gf_context *ctx)
+{
+    if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    Stats &s = ctx->stats;
+    s.searches = s.scan_launches = s.gemm_launches = s.merge_launches = s.other_launches = 0;
+    s.rows_scanned = s.quirk_fallbacks = s.coalesced_batches = s.h2d_bytes = s.d2h_bytes = 0;
+    ctx->prof_collect();
+    s.scan_kernel_ns = s.scan_kernel_timed = 0;
+    return GF_OK;
+}
+
+int gf_context_set_profiling(gf_context *ctx, int on)
+{
+    if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    ctx->profiling = on ? 1 : 0;
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------ Buffer (buffer.go)
+int gf_buffer_create(gf_context *ctx, uint64_t size, gf_buffer **out_buf)
+{
+    if (!ctx || !out_buf) return GF_ERR_INVALID_ARGUMENT;
+    *out_buf = nullptr;
+    return guarded([&]() -> int {
+        int rc = ctx->bind();
+        if (rc) return rc;
+        void *p = nullptr;
+        GF_CUDA(cudaMalloc(&p, size ? size : 1), GF_ERR_ALLOCATE_GPU_BUFFER);  // buffer.go:20-23
+        cudaError_t e = cudaMemset(p, 0, size);                                 // buffer.go:24
+        if (e != cudaSuccess) {
+            cudaFree(p);
+            return cuda_fail(e, "cudaMemset", GF_ERR_CLEAR_CUDA_BUFFER);
+        }
+        auto root = std::make_shared<DeviceAlloc>(DeviceAlloc{ctx, p, size, true});
+        gf_buffer *b = new gf_buffer();
+        b->ctx = ctx;
+        b->root = root;
+        b->ptr = (uint8_t *)p;
+        b->size = size;
+        *out_buf = b;
+        return GF_OK;
+    });
+}
+
+int gf_buffer_wrap(gf_context *ctx, void *device_ptr, uint64_t size, gf_buffer **out_buf)
+{
+    if (!ctx || !out_buf || (!device_ptr && size)) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        auto root = std::make_shared<DeviceAlloc>(DeviceAlloc{ctx, device_ptr, size, false});
+        gf_buffer *b = new gf_buffer();
+        b->ctx = ctx;
+        b->root = root;
+        b->ptr = (uint8_t *)device_ptr;
+        b->size = size;
+        *out_buf = b;
+        return GF_OK;
+    });
+}
+
+int gf_buffer_write(gf_buffer *buf, const void *value, uint64_t len)
+{
+    if (!buf || (!value && len)) return GF_ERR_INVALID_ARGUMENT;
+    if (len > buf->size) return GF_ERR_BUFFER_WRITE_OUT_OF_RANGE;  // buffer.go:35-37
+    int rc = buf->ctx->bind();
+    if (rc) return rc;
+    return buf->ctx->upload(buf->ptr, value, len);
+}
+
+int gf_buffer_read(gf_buffer *buf, void *out, uint64_t cap)
+{
+    if (!buf || (!out && buf->size)) return GF_ERR_INVALID_ARGUMENT;
+    if (cap < buf->size) return GF_ERR_INVALID_ARGUMENT;
+    int rc = buf->ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaMemcpy(out, buf->ptr, buf->size, cudaMemcpyDeviceToHost), GF_ERR_READ_CUDA_BUFFER);
+    buf->ctx->stats.d2h_bytes += buf->size;
+    return GF_OK;
+}
+
+int gf_buffer_copy(gf_buffer *dst, const gf_buffer *src)
+{
+    if (!dst || !src) return GF_ERR_INVALID_ARGUMENT;
+    if (src->size > dst->size) return GF_ERR_BUFFER_COPY_OUT_OF_RANGE;  // buffer.go:55-57
+    int rc = dst->ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaMemcpy(dst->ptr, src->ptr, src->size, cudaMemcpyDeviceToDevice), GF_ERR_WRITE_CUDA_BUFFER);
+    return GF_OK;
+}
+
+int gf_buffer_reset(gf_buffer *buf)
+{
+    if (!buf) return GF_ERR_INVALID_ARGUMENT;
+    int rc = buf->ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaMemset(buf->ptr, 0, buf->size), GF_ERR_CLEAR_CUDA_BUFFER);
+    return GF_OK;
+}
+
+int gf_buffer_slice(gf_buffer *buf, int64_t start, int64_t end, gf_buffer **out_buf)
+{
+    if (!buf || !out_buf) return GF_ERR_INVALID_ARGUMENT;
+    *out_buf = nullptr;
+    // buffer.go:74-79
+    if (start < 0 || (uint64_t)start > buf->size) return GF_ERR_BUFFER_SLICE_OUT_OF_RANGE;
+    if (end < 0 || (uint64_t)end > buf->size || end < start) return GF_ERR_BUFFER_SLICE_OUT_OF_RANGE;
+    return guarded([&]() -> int {
+        gf_buffer *b = new gf_buffer();
+        b->ctx = buf->ctx;
+        b->root = buf->root;
+        b->ptr = buf->ptr + start;
+        b->size = (uint64_t)(end - start);
+        *out_buf = b;
+        return GF_OK;
+    });
+}
+
+uint64_t gf_buffer_size(const gf_buffer *buf) { return buf ? buf->size : 0; }
+void *gf_buffer_device_ptr(const gf_buffer *buf) { return buf ? buf->ptr : nullptr; }
+int gf_buffer_free(gf_buffer *buf)
+{
+    delete buf;
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------ Cache (cache.go)
+int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache **out_cache)
+{
+    if (!ctx || !out_cache || block_num < 0 || block_size <= 0) return GF_ERR_INVALID_ARGUMENT;
+    *out_cache = nullptr;
+    return guarded([&]() -> int {
+        int rc = ctx->bind();
+        if (rc) return rc;
+        std::unique_ptr<gf_cache> c(new gf_cache());
+        c->ctx = ctx;
+        c->block_size = block_size;
+        uint64_t total = (uint64_t)block_num * (uint64_t)block_size;
+        void *p = nullptr;
+        // one slab (cache.go:31) + a tail pad so a 16-byte bulk copy never runs off the allocation
+        GF_CUDA(cudaMalloc(&p, total + 256), GF_ERR_ALLOCATE_GPU_BUFFER);
+        cudaError_t e = cudaMemset(p, 0, total + 256);
+        if (e != cudaSuccess) {
+            cudaFree(p);
+            return cuda_fail(e, "cudaMemset", GF_ERR_CLEAR_CUDA_BUFFER);
+        }
+        c->slab = std::make_shared<DeviceAlloc>(DeviceAlloc{ctx, p, total, true});
+        for (int i = 0; i < block_num; ++i) {  // cache.go:33-41
+            std::unique_ptr<Block> b(new gf_block());
+            b->cache = c.get();
+            b->index = i;
+            b->block_size = block_size;
+            b->dev = (uint8_t *)p + (uint64_t)i * (uint64_t)block_size;
+            c->all_blocks.push_back(std::move(b));
+        }
+        *out_cache = c.release();
+        return GF_OK;
+    });
+}
+
+int gf_cache_destroy(gf_cache *cache)
+{
+    if (!cache) return GF_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(cache->ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &s : cache->owned_sets) {
+        if (s->d_segs) cudaFree(s->d_segs);
+        s->d_segs = nullptr;
+        if (s->dev_ws) cache->ctx->release_ws(s->dev_ws);
+        s->dev_ws = nullptr;
+    }
+    delete cache;
+    return GF_OK;
+}
+
+int gf_cache_new_set(gf_cache *cache, const char *name, int dims, int precision, int batch)
+{
+    if (!cache || !name || dims <= 0 || precision <= 0 || batch <= 0) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        std::lock_guard<std::mutex> g(cache->mu);
+        if (cache->sets.count(name)) return GF_ERR_FEATURE_SET_EXIST;  // cache.go:47-50
+        std::unique_ptr<Set> s(new gf_set());
+        s->cache = cache;
+        s->ctx = cache->ctx;
+        s->name = name;
+        s->dims = dims;
+        s->precision = precision;
+        s->batch = batch;
+        s->cap = (int)(cache->block_size / ((int64_t)dims * precision));  // cache.go:59
+        cache->sets[name] = s.get();
+        cache->owned_sets.push_back(std::move(s));
+        return GF_OK;
+    });
+}
+
+int gf_cache_destroy_set(gf_cache *cache, const char *name)
+{
+    if (!cache || !name) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        Set *s;
+        {
+            std::lock_guard<std::mutex> g(cache->mu);
+            auto it = cache->sets.find(name);
+            if (it == cache->sets.end()) return GF_ERR_FEATURE_SET_NOT_FOUND;  // cache.go:76-80
+            s = it->second;
+        }
+        int rc = s->destroy();
+        if (rc) return rc;
+        std::lock_guard<std::mutex> g(cache->mu);
+        cache->sets.erase(name);
+        return GF_OK;
+    });
+}
+
+int gf_cache_get_set(gf_cache *cache, const char *name, gf_set **out_set)
+{
+    if (!cache || !name || !out_set) return GF_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(cache->mu);
+    auto it = cache->sets.find(name);
+    if (it == cache->sets.end()) {
+        *out_set = nullptr;
+        return GF_ERR_FEATURE_SET_NOT_FOUND;
+    }
+    *out_set = it->second;
+    return GF_OK;
+}
+
+int64_t gf_cache_get_block_size(const gf_cache *cache) { return cache ? cache->block_size : 0; }
+
+int gf_cache_get_empty_block(gf_cache *cache, int block_num, gf_block **out_blocks)
+{
+    if (!cache || block_num < 0 || (block_num > 0 && !out_blocks)) return GF_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(cache->mu);
+    int n = 0;
+    for (auto &b : cache->all_blocks)
+        if (!b->is_owned()) ++n;
+    if (n < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
+    int k = 0;
+    for (auto &b : cache->all_blocks) {
+        if (k == block_num) break;
+        if (!b->is_owned()) out_blocks[k++] = b.get();
+    }
+    return GF_OK;
+}
+
+int gf_cache_block_count(const gf_cache *cache) { return cache ? (int)cache->all_blocks.size() : 0; }
+
+int gf_cache_block_at(gf_cache *cache, int index, gf_block **out_block)
+{
+    if (!cache || !out_block || index < 0 || index >= (int)cache->all_blocks.size()) return GF_ERR_INVALID_ARGUMENT;
+    *out_block = cache->all_blocks[index].get();
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------ Block (block.go)
+int gf_block_capacity(const gf_block *block) { return block ? block->capacity() : 0; }
+int gf_block_margin(const gf_block *block) { return (block && block->is_owned()) ? block->margin() : 0; }
+int gf_block_is_owned(const gf_block *block) { return block ? (block->is_owned() ? 1 : 0) : 0; }
+int gf_block_next_index(const gf_block *block) { return block ? block->next_index : 0; }
+
+int gf_block_acquire(gf_block *block, const char *owner, int dims, int precision, int batch)
+{
+    if (!block || !owner) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        std::lock_guard<std::mutex> g(block->cache->mu);
+        return block->acquire(owner, dims, precision, batch);
+    });
+}
+
+int gf_block_release(gf_block *block)
+{
+    if (!block) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int { return block->release(); });
+}
+
+int gf_block_insert(gf_block *block, int64_t n, const void *values, uint64_t values_len, const char *ids,
+                    const uint64_t *id_offsets)
+{
+    if (!block || n < 0 || (n > 0 && !values)) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        if (!block->is_owned()) return GF_ERR_INVALID_ARGUMENT;
+        if (values_len != (uint64_t)n * block->dims * block->precision) return GF_ERR_MISMATCH_DIMENSION;
+        std::vector<std::string> v;
+        int rc = unpack_ids(n, ids, id_offsets, v);
+        if (rc) return rc;
+        if (block->set) return GF_ERR_BLOCK_USED;  // blocks of a live set are filled through Set.Add
+        return block->insert(n, (const uint8_t *)values, v);
+    });
+}
+
+int gf_block_delete(gf_block *block, int64_t n, const char *ids, const uint64_t *id_offsets, uint8_t *out_deleted,
+                    int64_t *out_ndeleted)
+{
+    if (!block || n < 0) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        std::vector<std::string> v;
+        int rc = unpack_ids(n, ids, id_offsets, v);
+        if (rc) return rc;
+        if (block->set) return GF_ERR_BLOCK_USED;
+        std::vector<uint8_t> found((size_t)n, 0);
+        rc = block->remove(v, found);
+        if (rc) return rc;
+        int64_t c = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (out_deleted) out_deleted[i] = found[i];
+            c += found[i];
+        }
+        if (out_ndeleted) *out_ndeleted = c;
+        return GF_OK;
+    });
+}
+
+int gf_block_search(gf_block *block, const gf_buffer *input, gf_buffer *output, int batch, int limit,
+                    gf_result **out_result)
+{
+    (void)output;  // the reference's score matrix scratch (block.go:71); scores never leave the SM here
+    if (!block || !input || !out_result) return GF_ERR_INVALID_ARGUMENT;
+    *out_result = nullptr;
+    return guarded([&]() -> int {
+        Result *r = nullptr;
+        int rc = block_search(block, input, batch, limit, &r);
+        if (rc) return rc;
+        *out_result = r;
+        return GF_OK;
+    });
+}
+
+// ------------------------------------------------------------------ Set (set.go)
+int gf_set_add(gf_set *set, int64_t n, const void *values, uint64_t values_len, const char *ids,
+               const uint64_t *id_offsets)
+{
+    if (!set || n < 0 || (n > 0 && !values)) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        if (values_len != (uint64_t)n * set->dims * set->precision) return GF_ERR_MISMATCH_DIMENSION;
+        std::vector<std::string> v;
+        int rc = unpack_ids(n, ids, id_offsets, v);
+        if (rc) return rc;
+        return set->add(n, (const uint8_t *)values, v);
+    });
+}
+
+int gf_set_delete(gf_set *set, int64_t n, const char *ids, const uint64_t *id_offsets, uint8_t *out_deleted,
+                  int64_t *out_ndeleted)
+{
+    if (!set || n < 0) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        std::vector<std::string> v;
+        int rc = unpack_ids(n, ids, id_offsets, v);
+        if (rc) return rc;
+        std::vector<uint8_t> found;
+        rc = set->remove(v, found);
+        if (rc) return rc;
+        int64_t c = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (out_deleted) out_deleted[i] = found[i];
+            c += found[i];
+        }
+        if (out_ndeleted) *out_ndeleted = c;
+        return GF_OK;
+    });
+}
+
+int gf_set_update(gf_set *set, int64_t n, const void *values, uint64_t values_len, const char *ids,
+                  const uint64_t *id_offsets, uint8_t *out_updated, int64_t *out_nupdated)
+{
+    if (!set || n < 0 || (n > 0 && !values)) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        if (values_len != (uint64_t)n * set->dims * set->precision) return GF_ERR_MISMATCH_DIMENSION;
+        std::vector<std::string> v;
+        int rc = unpack_ids(n, ids, id_offsets, v);
+        if (rc) return rc;
+        std::vector<uint8_t> found;
+        rc = set->update(n, (const uint8_t *)values, v, found);
+        if (rc) return rc;
+        int64_t c = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (out_updated) out_updated[i] = found[i];
+            c += found[i];
+        }
+        if (out_nupdated) *out_nupdated = c;
+        return GF_OK;
+    });
+}
+
+int gf_set_read(gf_set *set, int64_t n, const char *ids, const uint64_t *id_offsets, void *out_values,
+                uint64_t out_values_cap, uint8_t *out_found, int64_t *out_nfound)
+{
+    if (!set || n < 0 || (n > 0 && !out_values)) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        if (out_values_cap < (uint64_t)n * set->dims * set->precision) return GF_ERR_INVALID_ARGUMENT;
+        std::vector<std::string> v;
+        int rc = unpack_ids(n, ids, id_offsets, v);
+        if (rc) return rc;
+        std::vector<uint8_t> found;
+        rc = set->read(v, (uint8_t *)out_values, found);
+        if (rc) return rc;
+        int64_t c = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (out_found) out_found[i] = found[i];
+            c += found[i];
+        }
+        if (out_nfound) *out_nfound = c;
+        return GF_OK;
+    });
+}
+
+int gf_set_search(gf_set *set, float threshold, int limit, int q, const void *queries, uint64_t queries_len,
+                  gf_result **out_result)
+{
+    if (!set || !out_result || q < 0 || (q > 0 && !queries)) return GF_ERR_INVALID_ARGUMENT;
+    *out_result = nullptr;
+    return guarded([&]() -> int {
+        if (q > set->batch) return GF_ERR_OUT_OF_BATCH;  // set.go:119-122 comes first
+        if (queries_len != (uint64_t)q * set->dims * set->precision) return GF_ERR_MISMATCH_DIMENSION;
+        Result *r = nullptr;
+        int rc = set->search(threshold, limit, q, (const uint8_t *)queries, &r);
+        if (rc) return rc;
+        *out_result = r;
+        return GF_OK;
+    });
+}
+
+int gf_set_destroy(gf_set *set)
+{
+    if (!set) return GF_ERR_INVALID_ARGUMENT;
+    return gf_cache_destroy_set(set->cache, set->name.c_str());
+}
+
+int gf_set_dims(const gf_set *set) { return set ? set->dims : 0; }
+int gf_set_precision(const gf_set *set) { return set ? set->precision : 0; }
+int gf_set_batch(const gf_set *set) { return set ? set->batch : 0; }
+int gf_set_block_count(const gf_set *set) { return set ? (int)set->blocks.size() : 0; }
+int64_t gf_set_scanned_rows(const gf_set *set) { return set ? set->scanned_rows : 0; }
+int64_t gf_set_live_rows(const gf_set *set)
+{
+    if (!set) return 0;
+    int64_t n = 0;
+    for (const Block *b : set->blocks) n += b->live_count;
+    return n;
+}
+
+// ------------------------------------------------------------------ results
+int gf_result_batch(const gf_result *r) { return r ? r->batch : 0; }
+int gf_result_count(const gf_result *r, int q)
+{
+    if (!r || q < 0 || q >= r->batch) return 0;
+    return (int)(r->offsets[q + 1] - r->offsets[q]);
+}
+float gf_result_score(const gf_result *r, int q, int i)
+{
+    if (!r || q < 0 || q >= r->batch || i < 0 || i >= gf_result_count(r, q)) return 0.0f;
+    return r->scores[(size_t)r->offsets[q] + i];
+}
+const char *gf_result_id(const gf_result *r, int q, int i, uint32_t *out_len)
+{
+    if (out_len) *out_len = 0;
+    if (!r || q < 0 || q >= r->batch || i < 0 || i >= gf_result_count(r, q)) return nullptr;
+    size_t k = (size_t)r->offsets[q] + i;
+    if (out_len) *out_len = (uint32_t)(r->id_off[k + 1] - r->id_off[k]);
+    return r->id_bytes.data() + r->id_off[k];
+}
+uint64_t gf_result_slot(const gf_result *r, int q, int i)
+{
+    if (!r || q < 0 || q >= r->batch || i < 0 || i >= gf_result_count(r, q)) return 0;
+    return r->slots[(size_t)r->offsets[q] + i];
+}
+int64_t gf_result_total(const gf_result *r) { return r ? (int64_t)r->scores.size() : 0; }
+int64_t gf_result_id_bytes(const gf_result *r) { return r ? (int64_t)r->id_bytes.size() : 0; }
+int gf_result_export(const gf_result *r, int32_t *out_counts, float *out_scores, uint64_t *out_slots, char *out_ids,
+                     uint64_t *out_id_offsets)
+{
+    if (!r) return GF_ERR_INVALID_ARGUMENT;
+    if (out_counts)
+        for (int q = 0; q < r->batch; ++q) out_counts[q] = (int32_t)(r->offsets[q + 1] - r->offsets[q]);
+    size_t t = r->scores.size();
+    if (out_scores && t) memcpy(out_scores, r->scores.data(), t * sizeof(float));
+    if (out_slots && t) memcpy(out_slots, r->slots.data(), t * sizeof(uint64_t));
+    if (out_ids && !r->id_bytes.empty()) memcpy(out_ids, r->id_bytes.data(), r->id_bytes.size());
+    if (out_id_offsets) memcpy(out_id_offsets, r->id_off.data(), (t + 1) * sizeof(uint64_t));
+    return GF_OK;
+}
+int gf_result_free(gf_result *r)
+{
+    delete r;
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------ device-resident entry points
+uint64_t gf_key_make(float score, uint32_t slot) { return make_key(score, slot); }
+float gf_key_score(uint64_t key) { return key_score(key); }
+uint32_t gf_key_slot(uint64_t key) { return key_slot(key); }
+
+int gf_set_set_shard(gf_set *set, int rank, int world)
+{
+    if (!set || world < 1 || rank < 0 || rank >= world) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        set->lock.lock();
+        set->shard_rank = rank;
+        set->shard_world = world;
+        int rc = set->rebuild_segments();
+        set->lock.unlock();
+        return rc;
+    });
+}
+
+int gf_set_search_device(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys, int path,
+                         void *stream)
+{
+    if (!set || !d_queries || !d_out_keys) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        return set->search_device(limit, q, d_queries, (unsigned long long *)d_out_keys, path, (cudaStream_t)stream);
+    });
+}
+
+int gf_merge_keys_device(gf_context *ctx, int lists, int q, int limit, const uint64_t *d_in, uint64_t *d_out,
+                         void *stream)
+{
+    if (!ctx || !d_in || !d_out || lists < 1 || q < 1 || limit < 1) return GF_ERR_INVALID_ARGUMENT;
+    if (limit > kMaxK) return GF_ERR_UNSUPPORTED;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(merge_launch((const unsigned long long *)d_in, 1, lists, q, limit, (unsigned long long *)d_out,
+                         (cudaStream_t)stream),
+            GF_ERR_CUDA);
+    ctx->stats.merge_launches++;
+    return GF_OK;
+}
+
+int gf_set_resolve_keys(gf_set *set, float threshold, int limit, int q, const uint64_t *h_keys, gf_result **out_result)
+{
+    if (!set || !h_keys || !out_result || q < 0 || limit < 0) return GF_ERR_INVALID_ARGUMENT;
+    *out_result = nullptr;
+    return guarded([&]() -> int {
+        Result *r = nullptr;
+        int rc = set->resolve_keys(threshold, limit, q, (const unsigned long long *)h_keys, &r);
+        if (rc) return rc;
+        *out_result = r;
+        return GF_OK;
+    });
+}
+
+int gf_set_add_synthetic(gf_set *set, int64_t n, uint64_t seed, int64_t first_ordinal, int normalize,
+                         const char *id_prefix)
+{
+    if (!set || n < 0 || first_ordinal < 0) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        return set->add_synthetic(n, seed, first_ordinal, normalize, id_prefix ? id_prefix : "f");
+    });
+}
+
+int gf_set_set_coalescing(gf_set *set, int max_wait_us)
+{
+    if (!set || max_wait_us < 0) return GF_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(set->co_mu);
+    set->coalesce_wait_us = max_wait_us;
+    return GF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// gf_device.cuh -- device-side helpers shared by the sm_100a kernels.
+//
+// Candidate keys, the canonical float32 dot-product order, mbarrier / bulk-copy (TMA)
+// PTX wrappers and the per-CTA candidate lists.  The canonical order is restated
+// on the CPU in oracle/gf_oracle.c (gf_dot_canonical_scalar); the two must stay
+// bit-identical.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gf {
+
+// ------------------------------------------------------------------ keys
+// (orderable image of the score) << 32 | (0xFFFFFFFF - slot).  Larger = better:
+// score descending, then slot ascending.  NaN -> image 0 (worst), -0.0 -> +0.0.
+// The reference's own tie order is unspecified (unstable sort.Slice, util.go:85).
+__host__ __device__ __forceinline__ uint32_t score_image(float s)
+{
+    if (s != s) return 0u;
+    s = s + 0.0f;
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(s);
+#else
+    union { float f; uint32_t u; } c; c.f = s; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float image_score(uint32_t im)
+{
+    uint32_t u = (im & 0x80000000u) ? (im & 0x7FFFFFFFu) : ~im;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float s, uint32_t slot)
+{
+    return ((uint64_t)score_image(s) << 32) | (uint64_t)(0xFFFFFFFFu - slot);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return image_score((uint32_t)(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_slot(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu); }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP); completion is
+// signalled as `bytes` transaction bytes on `bar`.  src/dst 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// same, with an L2 eviction-priority policy (createpolicy) for stream-once data
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                              uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------ canonical reduction
+// Thread l of a warp holds P[4l..4l+3] in (p0,p1,p2,p3); returns the full sum in every lane:
+//   T[l] = (P[4l]+P[4l+1]) + (P[4l+2]+P[4l+3]); then xor-butterfly 16,8,4,2,1; then +0.0f.
+__device__ __forceinline__ float canonical_reduce(float p0, float p1, float p2, float p3)
+{
+    float t = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, off));
+    return __fadd_rn(t, 0.0f);
+}
+
+// ------------------------------------------------------------------ per-CTA candidate lists
+// One list per query lives in shared memory: an unsorted append buffer of `cap` keys
+// (a power of two, >= 2*K) plus the gate tau = K-th best key seen at the last compaction
+// (0 while fewer than `cap` keys have ever been appended).  A warp that finds key > tau
+// takes the list's lock, appends, and when the buffer is full sorts it and keeps K.
+struct ListCtl {
+    unsigned long long tau;  // gate; keys <= tau are rejected without taking the lock
+    int cnt;                 // keys in the buffer
+    int lock;                // 0 free, 1 held
+};
+
+// bitonic sort (descending) of n (power of two) keys in shared memory by ONE warp
+__device__ __forceinline__ void warp_sort_desc(unsigned long long *buf, int n, int lane)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = buf[i], b = buf[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) {
+                        buf[i] = b;
+                        buf[ixj] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Whole warp calls this with a warp-uniform key.  K <= cap/2.
+__device__ __forceinline__ void list_insert(ListCtl *ctl, unsigned long long *buf, int cap, int K,
+                                            unsigned long long key, int lane)
+{
+    if (lane == 0) {
+        while (atomicCAS(&ctl->lock, 0, 1) != 0) {
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+    unsigned long long tau = *(volatile unsigned long long *)&ctl->tau;
+    if (key > tau) {
+        int n = *(volatile int *)&ctl->cnt;
+        if (lane == 0) buf[n] = key;
+        n += 1;
+        __syncwarp();
+        if (n == cap) {
+            warp_sort_desc(buf, cap, lane);
+            n = K;
+            if (lane == 0) *(volatile unsigned long long *)&ctl->tau = buf[K - 1];
+        }
+        if (lane == 0) *(volatile int *)&ctl->cnt = n;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicExch(&ctl->lock, 0);
+    }
+    __syncwarp();
+}
+
+// Sort the list and write its best K keys (zero padded) to out[0..K).  One warp, no contention.
+__device__ __forceinline__ void list_flush(ListCtl *ctl, unsigned long long *buf, int cap, int K,
+                                           unsigned long long *out, int lane)
+{
+    int n = ctl->cnt;
+    for (int i = n + lane; i < cap; i += 32) buf[i] = 0ull;
+    __syncwarp();
+    warp_sort_desc(buf, cap, lane);
+    for (int i = lane; i < K; i += 32) out[i] = buf[i];
+}
+#endif  // __CUDACC__
+
+}  // namespace gf

@@ -1,0 +1,193 @@
+// gf_merge.cu -- candidate-list merge and the synthetic row generator, sm_100a.
+//
+// merge_kernel folds `lists` per-CTA (or per-rank) candidate lists of K keys into the
+// top-K per query: the device-side counterpart of MaxNFeatureResult (util.go:95-112)
+// as used at set.go:154-157, on (score,slot) keys instead of Go structs.
+#include "gf_device.cuh"
+#include "gf_kernels.h"
+
+namespace gf {
+
+namespace {
+
+constexpr int kMergeThreads = 256;
+constexpr int kMergeBuf = 2048;  // keys held in shared memory; kMaxK <= kMergeBuf/2
+
+// bitonic sort (descending) of n (power of two, <= kMergeBuf) keys in shared memory by the CTA
+__device__ void block_sort_desc(unsigned long long *buf, int n)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = buf[i], b = buf[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) {
+                        buf[i] = b;
+                        buf[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int pow2_at_least(int v)
+{
+    int p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// grid (q, groups); d_in [groups][lists][q][K]; d_out [groups][q][K]
+__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const unsigned long long *__restrict__ d_in, int lists,
+                                                             int q, int K, unsigned long long *__restrict__ d_out)
+{
+    __shared__ unsigned long long buf[kMergeBuf];
+    __shared__ unsigned long long red[kMergeThreads / 32];
+    __shared__ unsigned long long s_tau;
+    __shared__ int s_n;
+
+    const int qi = blockIdx.x, group = blockIdx.y;
+    const unsigned long long *base = d_in + ((size_t)group * lists * q + qi) * (size_t)K;
+    const size_t list_stride = (size_t)q * K;
+
+    // tau = best K-th key of any single list: that list alone holds K keys >= tau
+    unsigned long long m = 0ull;
+    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
+        unsigned long long v = base[(size_t)l * list_stride + (K - 1)];
+        m = v > m ? v : m;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0ull;
+        for (int w = 0; w < kMergeThreads / 32; ++w) t = red[w] > t ? red[w] : t;
+        s_tau = t;
+    }
+    __syncthreads();
+
+    const long long total = (long long)lists * K;
+    const int chunk = kMergeBuf - K;  // with <= K keys kept, one chunk can never overflow buf
+    for (long long c0 = 0; c0 < total; c0 += chunk) {
+        const unsigned long long tau = s_tau;
+        long long c1 = c0 + chunk < total ? c0 + chunk : total;
+        for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            long long l = i / K;
+            int j = (int)(i - l * K);
+            unsigned long long key = base[(size_t)l * list_stride + j];
+            if (key != 0ull && key >= tau) {
+                int pos = atomicAdd(&s_n, 1);
+                buf[pos] = key;
+            }
+        }
+        __syncthreads();
+        int n = s_n;
+        if (c1 < total && n > K) {
+            int np = pow2_at_least(n);
+            for (int i = n + threadIdx.x; i < np; i += blockDim.x) buf[i] = 0ull;
+            __syncthreads();
+            block_sort_desc(buf, np);
+            if (threadIdx.x == 0) {
+                s_n = K;
+                if (buf[K - 1] > s_tau) s_tau = buf[K - 1];
+            }
+            __syncthreads();
+        }
+    }
+    int n = s_n;
+    int np = pow2_at_least(n > K ? n : K);
+    for (int i = n + threadIdx.x; i < np; i += blockDim.x) buf[i] = 0ull;
+    __syncthreads();
+    block_sort_desc(buf, np);
+    unsigned long long *out = d_out + ((size_t)group * q + qi) * (size_t)K;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) out[i] = buf[i];
+}
+
+// ------------------------------------------------------------------ synthetic rows
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ float uniform_pm1(unsigned long long seed, unsigned long long counter)
+{
+    unsigned long long h = splitmix64(seed ^ splitmix64(counter));
+    unsigned int m = (unsigned int)(h >> 40);
+    return __fadd_rn(__fmul_rn((float)m, 1.0f / 8388608.0f), -1.0f);
+}
+
+// one warp per row; element e handled by lane (e%128)/4, partial sum e%4 (canonical order)
+__global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ rows, long long nrows, int dims,
+                                                         unsigned long long seed, long long first_row, int normalize)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < nrows; r += nwarps) {
+        const unsigned long long c0 = (unsigned long long)(first_row + r) * (unsigned long long)dims;
+        float inv_ok = 1.0f, nrm = 1.0f;
+        if (normalize) {
+            float p[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < dims; j += 128) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int e = j + 4 * lane + c;
+                    if (e < dims) {
+                        float v = uniform_pm1(seed, c0 + e);
+                        p[c] = __fmaf_rn(v, v, p[c]);
+                    }
+                }
+            }
+            float ss = canonical_reduce(p[0], p[1], p[2], p[3]);
+            nrm = __fsqrt_rn(ss);
+            inv_ok = (nrm == 0.0f) ? 0.0f : 1.0f;
+        }
+        float *out = rows + (size_t)r * dims;
+        for (int j = 0; j < dims; j += 128) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int e = j + 4 * lane + c;
+                if (e < dims) {
+                    float v = uniform_pm1(seed, c0 + e);
+                    if (normalize) v = (inv_ok == 0.0f) ? 0.0f : __fdiv_rn(v, nrm);
+                    out[e] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
+                         unsigned long long *d_out, cudaStream_t stream)
+{
+    if (K < 1 || K > kMaxK || q < 1 || lists < 1 || groups < 1) return cudaErrorInvalidValue;
+    dim3 grid(q, groups);
+    merge_kernel<<<grid, kMergeThreads, 0, stream>>>(d_in, lists, q, K, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, uint64_t seed, int64_t first_row, int normalize,
+                              cudaStream_t stream)
+{
+    if (nrows <= 0) return cudaSuccess;
+    long long warps = nrows;
+    long long blocks = (warps + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    synth_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, nrows, dims, seed, first_row, normalize);
+    return cudaGetLastError();
+}
+
+}  // namespace gf

@@ -1,0 +1,1166 @@
+// gf_runtime.cu -- host object model: Context / Buffer / Block / Set / Cache.
+//
+// Restates the reference's Go host code (block.go, buffer.go, cache.go, set.go, util.go)
+// in C++ behind the C ABI; citations are /root/reference/<file>:<line>.  The GPU work is
+// in gf_scan.cu / gf_merge.cu.  There is no CPU scoring path in this file or anywhere in
+// the library: every score comes out of a CUDA kernel.
+#include "gf_runtime.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "gf_device.cuh"
+
+namespace gf {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_detail;
+void set_error_detail(const std::string &s) { g_detail = s; }
+const std::string &error_detail() { return g_detail; }
+
+int cuda_fail(cudaError_t e, const char *what, int status)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_detail = buf;
+    cudaGetLastError();  // clear the sticky-free error state
+    return status;
+}
+
+// ------------------------------------------------------------------ RWLock
+void RWLock::lock_shared()
+{
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return !writer_ && writers_waiting_ == 0; });
+    ++readers_;
+}
+void RWLock::unlock_shared()
+{
+    std::unique_lock<std::mutex> l(m_);
+    if (--readers_ == 0) cv_.notify_all();
+}
+void RWLock::lock()
+{
+    std::unique_lock<std::mutex> l(m_);
+    ++writers_waiting_;
+    cv_.wait(l, [&] { return !writer_ && readers_ == 0; });
+    --writers_waiting_;
+    writer_ = true;
+}
+void RWLock::unlock()
+{
+    std::unique_lock<std::mutex> l(m_);
+    writer_ = false;
+    cv_.notify_all();
+}
+
+struct SharedGuard {
+    RWLock &l;
+    explicit SharedGuard(RWLock &l_) : l(l_) { l.lock_shared(); }
+    ~SharedGuard() { l.unlock_shared(); }
+};
+struct ExclusiveGuard {
+    RWLock &l;
+    explicit ExclusiveGuard(RWLock &l_) : l(l_) { l.lock(); }
+    ~ExclusiveGuard() { l.unlock(); }
+};
+
+// ------------------------------------------------------------------ Workspace / Context
+int Workspace::reserve(size_t d_bytes, size_t h_bytes)
+{
+    if (d_bytes > d_cap) {
+        if (d_buf) {
+            GF_CUDA(cudaStreamSynchronize(stream), GF_ERR_CUDA);
+            cudaFree(d_buf);
+            d_buf = nullptr;
+            d_cap = 0;
+        }
+        size_t want = std::max(d_bytes, (size_t)1 << 20);
+        GF_CUDA(cudaMalloc((void **)&d_buf, want), GF_ERR_ALLOCATE_GPU_BUFFER);
+        d_cap = want;
+    }
+    if (h_bytes > h_cap) {
+        if (h_buf) {
+            GF_CUDA(cudaStreamSynchronize(stream), GF_ERR_CUDA);
+            cudaFreeHost(h_buf);
+            h_buf = nullptr;
+            h_cap = 0;
+        }
+        size_t want = std::max(h_bytes, (size_t)1 << 16);
+        GF_CUDA(cudaMallocHost((void **)&h_buf, want), GF_ERR_ALLOCATE_GPU_BUFFER);
+        h_cap = want;
+    }
+    return GF_OK;
+}
+
+Workspace::~Workspace()
+{
+    if (d_buf) cudaFree(d_buf);
+    if (h_buf) cudaFreeHost(h_buf);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+int Context::bind() const
+{
+    GF_CUDA(cudaSetDevice(device), GF_ERR_INVALID_DEVICE_ID);
+    return GF_OK;
+}
+
+Workspace *Context::acquire_ws()
+{
+    {
+        std::lock_guard<std::mutex> g(ws_mu);
+        if (!ws_free.empty()) {
+            Workspace *w = ws_free.back();
+            ws_free.pop_back();
+            return w;
+        }
+    }
+    Workspace *w = new Workspace();
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete w;
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(ws_mu);
+    ws_all.push_back(w);
+    return w;
+}
+
+void Context::release_ws(Workspace *w)
+{
+    std::lock_guard<std::mutex> g(ws_mu);
+    ws_free.push_back(w);
+}
+
+int Context::upload(void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return GF_OK;
+    std::lock_guard<std::mutex> g(stage_mu);
+    size_t off = 0;
+    int k = 0;
+    while (off < bytes) {
+        size_t n = std::min(stage_bytes, bytes - off);
+        int i = k & 1;
+        GF_CUDA(cudaEventSynchronize(stage_ev[i]), GF_ERR_WRITE_CUDA_BUFFER);
+        memcpy(stage[i], (const uint8_t *)src + off, n);
+        GF_CUDA(cudaMemcpyAsync((uint8_t *)dst + off, stage[i], n, cudaMemcpyHostToDevice, mut_stream),
+                GF_ERR_WRITE_CUDA_BUFFER);
+        GF_CUDA(cudaEventRecord(stage_ev[i], mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+        off += n;
+        ++k;
+    }
+    GF_CUDA(cudaStreamSynchronize(mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+    stats.h2d_bytes += bytes;
+    return GF_OK;
+}
+
+void Context::prof_begin(cudaStream_t st, std::pair<cudaEvent_t, cudaEvent_t> *ev)
+{
+    ev->first = ev->second = nullptr;
+    if (!profiling.load()) return;
+    {
+        std::lock_guard<std::mutex> g(prof_mu);
+        if (!prof_free.empty()) {
+            *ev = prof_free.back();
+            prof_free.pop_back();
+        }
+    }
+    if (!ev->first) {
+        if (cudaEventCreate(&ev->first) != cudaSuccess || cudaEventCreate(&ev->second) != cudaSuccess) {
+            ev->first = ev->second = nullptr;
+            return;
+        }
+    }
+    cudaEventRecord(ev->first, st);
+}
+
+void Context::prof_end(cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t> &ev)
+{
+    if (!ev.first) return;
+    cudaEventRecord(ev.second, st);
+    std::lock_guard<std::mutex> g(prof_mu);
+    prof_pending.push_back(ev);
+}
+
+void Context::prof_collect()
+{
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> todo;
+    {
+        std::lock_guard<std::mutex> g(prof_mu);
+        todo.swap(prof_pending);
+    }
+    for (auto &ev : todo) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+            stats.scan_kernel_ns += (uint64_t)((double)ms * 1e6);
+            stats.scan_kernel_timed++;
+        }
+    }
+    std::lock_guard<std::mutex> g(prof_mu);
+    prof_free.insert(prof_free.end(), todo.begin(), todo.end());
+}
+
+Context::~gf_context()
+{
+    cudaSetDevice(device);
+    for (auto &ev : prof_pending) prof_free.push_back(ev);
+    for (auto &ev : prof_free) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    for (Workspace *w : ws_all) delete w;
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
+    }
+    if (mut_stream) cudaStreamDestroy(mut_stream);
+}
+
+gf::DeviceAlloc::~DeviceAlloc()
+{
+    if (owned && ptr) {
+        cudaSetDevice(ctx->device);
+        cudaFree(ptr);
+    }
+}
+
+// ------------------------------------------------------------------ Result
+void Result::begin(int q)
+{
+    batch = q;
+    offsets.assign(1, 0);
+    id_off.assign(1, 0);
+}
+void Result::push(float score, uint64_t slot, const std::string &id)
+{
+    scores.push_back(score);
+    slots.push_back(slot);
+    id_bytes.append(id);
+    id_off.push_back(id_bytes.size());
+}
+void Result::end_query() { offsets.push_back((int64_t)scores.size()); }
+
+// ------------------------------------------------------------------ Block
+std::string Block::id_at(int row) const
+{
+    if (row < 0 || row >= (int)live.size() || !live[row]) return std::string();
+    if (implicit_ids) {
+        char buf[32];
+        snprintf(buf, sizeof buf, "%011lld", (long long)(id_first + row));
+        return id_prefix + buf;
+    }
+    return ids[row];
+}
+
+void Block::index_add(const std::string &id, int row) { id_index[id].push_back(row); }
+
+void Block::index_del(const std::string &id, int row)
+{
+    auto it = id_index.find(id);
+    if (it == id_index.end()) return;
+    auto &v = it->second;
+    v.erase(std::remove(v.begin(), v.end(), row), v.end());
+    if (v.empty()) id_index.erase(it);
+}
+
+int Block::find_last(const std::string &id) const
+{
+    if (implicit_ids) {
+        if (id.size() != id_prefix.size() + 11 || id.compare(0, id_prefix.size(), id_prefix) != 0) return -1;
+        long long ord = 0;
+        for (size_t i = id_prefix.size(); i < id.size(); ++i) {
+            if (id[i] < '0' || id[i] > '9') return -1;
+            ord = ord * 10 + (id[i] - '0');
+        }
+        long long row = ord - id_first;
+        if (row < 0 || row >= next_index || !live[row]) return -1;
+        return (int)row;
+    }
+    auto it = id_index.find(id);
+    if (it == id_index.end() || it->second.empty()) return -1;
+    return *std::max_element(it->second.begin(), it->second.end());
+}
+
+void Block::materialize_ids()
+{
+    if (!implicit_ids) return;
+    std::vector<std::string> v((size_t)capacity());
+    for (int r = 0; r < next_index; ++r)
+        if (live[r]) v[r] = id_at(r);
+    implicit_ids = false;
+    ids.swap(v);
+    id_index.clear();
+    for (int r = 0; r < next_index; ++r)
+        if (live[r]) index_add(ids[r], r);
+}
+
+// block.go:59-78
+int Block::acquire(const std::string &owner_, int dims_, int precision_, int batch_)
+{
+    if (!owner.empty()) return GF_ERR_BLOCK_USED;
+    if (owner_.empty() || dims_ <= 0 || precision_ <= 0 || batch_ <= 0) return GF_ERR_INVALID_ARGUMENT;
+    if ((int64_t)dims_ * precision_ > block_size) return GF_ERR_INVALID_ARGUMENT;
+    dims = dims_;
+    precision = precision_;
+    batch = batch_;
+    owner = owner_;
+    ids.assign((size_t)capacity(), std::string());
+    live.assign((size_t)capacity(), 0);
+    live_count = 0;
+    implicit_ids = false;
+    id_index.clear();
+    empty.clear();
+    next_index = 0;
+    return GF_OK;
+}
+
+// block.go:253-270
+int Block::release()
+{
+    std::lock_guard<std::mutex> g(mu);
+    int rc = cache->ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaMemsetAsync(dev, 0, (size_t)block_size, cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    GF_CUDA(cudaStreamSynchronize(cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    dims = precision = batch = 0;
+    owner.clear();
+    std::vector<std::string>().swap(ids);
+    std::vector<uint8_t>().swap(live);
+    id_index.clear();
+    empty.clear();
+    next_index = 0;
+    live_count = 0;
+    implicit_ids = false;
+    set = nullptr;
+    return GF_OK;
+}
+
+// block.go:80-131, with the evident intent of lines 103/115 (whole rows, byte offsets)
+int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_)
+{
+    if (owner.empty()) return GF_ERR_INVALID_ARGUMENT;
+    if (n > margin()) return GF_ERR_BLOCK_IS_FULL;
+    if (n == 0) return GF_OK;
+    std::lock_guard<std::mutex> g(mu);
+    Context *ctx = cache->ctx;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    materialize_ids();
+    const size_t rowb = (size_t)dims * precision;
+    const size_t nempty = empty.size();
+    const size_t refill = std::min(nempty, (size_t)n);
+    for (size_t i = 0; i < refill; ++i) {
+        int slot = empty[i];
+        rc = ctx->upload(dev + (size_t)slot * rowb, values + i * rowb, rowb);
+        if (rc) return GF_ERR_WRITE_CUDA_BUFFER;
+        ids[slot] = ids_[i];
+        live[slot] = 1;
+        ++live_count;
+        index_add(ids_[i], slot);
+    }
+    if ((size_t)n > nempty) {
+        size_t tail = (size_t)n - nempty;
+        rc = ctx->upload(dev + (size_t)next_index * rowb, values + nempty * rowb, tail * rowb);
+        if (rc) return rc;
+        for (size_t i = 0; i < tail; ++i) {
+            int slot = next_index + (int)i;
+            ids[slot] = ids_[nempty + i];
+            live[slot] = 1;
+            index_add(ids_[nempty + i], slot);
+        }
+        live_count += (int)tail;
+        next_index += (int)tail;
+        empty.clear();
+    } else {
+        empty.erase(empty.begin(), empty.begin() + n);
+    }
+    return GF_OK;
+}
+
+int Block::insert_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix)
+{
+    if (owner.empty() || precision != 4) return GF_ERR_INVALID_ARGUMENT;
+    if (n > capacity() - next_index) return GF_ERR_BLOCK_IS_FULL;
+    if (n == 0) return GF_OK;
+    std::lock_guard<std::mutex> g(mu);
+    Context *ctx = cache->ctx;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    bool can_implicit = (next_index == 0 && empty.empty()) ||
+                        (implicit_ids && id_prefix == prefix && id_first + next_index == first_ordinal);
+    if (!can_implicit) materialize_ids();
+    GF_CUDA(synth_fill_launch((float *)dev + (size_t)next_index * dims, n, dims, seed, first_ordinal, normalize,
+                              ctx->mut_stream),
+            GF_ERR_WRITE_CUDA_BUFFER);
+    ctx->stats.other_launches++;
+    if (can_implicit) {
+        if (next_index == 0) {
+            implicit_ids = true;
+            id_prefix = prefix;
+            id_first = first_ordinal;
+            std::vector<std::string>().swap(ids);
+        }
+        for (int64_t i = 0; i < n; ++i) live[next_index + i] = 1;
+    } else {
+        char buf[32];
+        for (int64_t i = 0; i < n; ++i) {
+            snprintf(buf, sizeof buf, "%011lld", (long long)(first_ordinal + i));
+            int slot = next_index + (int)i;
+            ids[slot] = prefix + buf;
+            live[slot] = 1;
+            index_add(ids[slot], slot);
+        }
+    }
+    live_count += (int)n;
+    next_index += (int)n;
+    return GF_OK;
+}
+
+// block.go:135-165.  `found[i]` is set for every request id removed here; ids already
+// flagged by an earlier block are skipped (set.go:176-190 forwards only the remainder).
+int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found)
+{
+    if (owner.empty()) return GF_OK;
+    std::lock_guard<std::mutex> g(mu);
+    Context *ctx = cache->ctx;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    const size_t rowb = (size_t)dims * precision;
+    bool any = false;
+    for (size_t i = 0; i < ids_.size(); ++i) {
+        if (found[i]) continue;
+        bool dup = false;  // targets is a map: a repeated id is looked up once (block.go:136-139)
+        for (size_t j = 0; j < i && !dup; ++j) dup = (ids_[j] == ids_[i]);
+        if (dup) continue;
+        int row = find_last(ids_[i]);
+        if (row < 0) continue;
+        GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+        if (!implicit_ids) {
+            index_del(ids_[i], row);
+            ids[row].clear();
+        }
+        live[row] = 0;
+        --live_count;
+        empty.push_back(row);
+        found[i] = 1;
+        any = true;
+    }
+    if (any) GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------ Set
+bool Set::slot_to_block(uint32_t slot, int *block_pos, int *row) const
+{
+    if (cap <= 0) return false;
+    uint64_t gb = slot / (uint32_t)cap;
+    if ((int)(gb % (uint64_t)shard_world) != shard_rank) return false;
+    uint64_t pos = gb / (uint64_t)shard_world;
+    if (pos >= blocks.size()) return false;
+    *block_pos = (int)pos;
+    *row = (int)(slot % (uint32_t)cap);
+    return true;
+}
+
+int Set::rebuild_segments()
+{
+    h_segs.clear();
+    seg_block.clear();
+    int tr = scan_tile_rows(dims);
+    aligned16 = (dims % 4 == 0) && (cache->block_size % 16 == 0) && precision == 4;
+    tile_rows = (aligned16 && tr > 0) ? tr : 64;
+    uint64_t gblocks = (uint64_t)blocks.size() * shard_world;
+    if (gblocks * (uint64_t)cap >= 0xFFFFFFFFull) {
+        set_error_detail("set too large for 32-bit slots");
+        return GF_ERR_INVALID_ARGUMENT;
+    }
+    uint32_t tiles = 0;
+    scanned_rows = 0;
+    for (size_t p = 0; p < blocks.size(); ++p) {
+        Block *b = blocks[p];
+        if (b->next_index == 0) continue;  // block.go:186-189
+        Segment s;
+        s.base = (const float *)b->dev;
+        s.rows = (uint32_t)b->next_index;
+        s.slot_base = slot_base_of((int)p);
+        s.tile_start = tiles;
+        s.pad = 0;
+        tiles += (s.rows + tile_rows - 1) / tile_rows;
+        scanned_rows += b->next_index;
+        h_segs.push_back(s);
+        seg_block.push_back((int)p);
+    }
+    total_tiles = tiles;
+    if (h_segs.empty()) return GF_OK;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    if ((int)h_segs.size() > d_segs_cap) {
+        if (d_segs) cudaFree(d_segs);
+        d_segs = nullptr;
+        int want = std::max((int)h_segs.size() * 2, 64);
+        GF_CUDA(cudaMalloc((void **)&d_segs, (size_t)want * sizeof(Segment)), GF_ERR_ALLOCATE_GPU_BUFFER);
+        d_segs_cap = want;
+    }
+    GF_CUDA(cudaMemcpyAsync(d_segs, h_segs.data(), h_segs.size() * sizeof(Segment), cudaMemcpyHostToDevice,
+                            ctx->mut_stream),
+            GF_ERR_WRITE_CUDA_BUFFER);
+    GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+    return GF_OK;
+}
+
+// Mutations wait for every search already enqueued on the device (device-resident
+// searches return before their kernels finish).
+static int quiesce(Context *ctx)
+{
+    int rc = ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
+    return GF_OK;
+}
+
+// set.go:77-116
+int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (n == 0) return GF_OK;
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    int64_t empty = 0;
+    for (Block *b : blocks) empty += b->margin();
+    if (n > empty) {
+        int64_t remain = n - empty;
+        int64_t block_length = cache->block_size / ((int64_t)dims * precision);
+        if (block_length <= 0) return GF_ERR_NOT_ENOUGH_BLOCKS;
+        int64_t block_num = (remain + block_length - 1) / block_length;
+        std::vector<Block *> got;
+        {
+            std::lock_guard<std::mutex> cg(cache->mu);
+            for (auto &ub : cache->all_blocks) {  // cache.go:104-115
+                if ((int64_t)got.size() == block_num) break;
+                if (!ub->is_owned()) got.push_back(ub.get());
+            }
+            if ((int64_t)got.size() < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
+            for (Block *b : got) {
+                rc = b->acquire(name, dims, precision, batch);
+                if (rc) return rc;
+                b->set = this;
+            }
+        }
+        blocks.insert(blocks.end(), got.begin(), got.end());
+    }
+    const size_t rowb = (size_t)dims * precision;
+    int64_t offset = 0, remain = n;
+    for (Block *b : blocks) {
+        int64_t length = std::min<int64_t>(b->margin(), remain);
+        if (length > 0) {
+            std::vector<std::string> sub(ids_.begin() + offset, ids_.begin() + offset + length);
+            rc = b->insert(length, values + (size_t)offset * rowb, sub);
+            if (rc) {
+                rebuild_segments();
+                return rc;
+            }
+            offset += length;
+            remain -= length;
+        }
+        if (remain <= 0) break;
+    }
+    return rebuild_segments();
+}
+
+int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (precision != 4) return GF_ERR_UNSUPPORTED;
+    if (n == 0) return GF_OK;
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    // synthetic rows only append (never refill tombstones): count tail room
+    int64_t room = 0;
+    for (Block *b : blocks) room += b->capacity() - b->next_index;
+    if (n > room) {
+        int64_t remain = n - room;
+        int64_t block_length = cache->block_size / ((int64_t)dims * precision);
+        int64_t block_num = (remain + block_length - 1) / block_length;
+        std::vector<Block *> got;
+        std::lock_guard<std::mutex> cg(cache->mu);
+        for (auto &ub : cache->all_blocks) {
+            if ((int64_t)got.size() == block_num) break;
+            if (!ub->is_owned()) got.push_back(ub.get());
+        }
+        if ((int64_t)got.size() < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
+        for (Block *b : got) {
+            rc = b->acquire(name, dims, precision, batch);
+            if (rc) return rc;
+            b->set = this;
+            // implicit ids: do not keep capacity() empty strings per block
+            std::vector<std::string>().swap(b->ids);
+            b->implicit_ids = true;
+            b->id_prefix = prefix;
+            b->id_first = 0;
+        }
+        blocks.insert(blocks.end(), got.begin(), got.end());
+    }
+    int64_t done = 0;
+    for (Block *b : blocks) {
+        int64_t length = std::min<int64_t>(b->capacity() - b->next_index, n - done);
+        if (length > 0) {
+            if (b->implicit_ids && b->next_index == 0) b->id_first = first_ordinal + done;
+            rc = b->insert_synthetic(length, seed, first_ordinal + done, normalize, prefix);
+            if (rc) return rc;
+            done += length;
+        }
+        if (done >= n) break;
+    }
+    GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+    return rebuild_segments();
+}
+
+// set.go:163-193
+int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    found.assign(ids_.size(), 0);
+    if (ids_.empty()) return GF_OK;
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    size_t nfound = 0;
+    for (Block *b : blocks) {
+        if (nfound == ids_.size()) break;
+        rc = b->remove(ids_, found);
+        if (rc) return rc;
+        nfound = (size_t)std::count(found.begin(), found.end(), (uint8_t)1);
+    }
+    return GF_OK;  // NextIndex never shrinks (block.go:159-160): the segment table is unchanged
+}
+
+// interface.go:47-50 (TODO in the reference, set.go:195-198): overwrite in place
+int Set::update(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_, std::vector<uint8_t> &found)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    found.assign(ids_.size(), 0);
+    if (n == 0) return GF_OK;
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    const size_t rowb = (size_t)dims * precision;
+    for (int64_t i = 0; i < n; ++i) {
+        for (Block *b : blocks) {
+            int row = b->find_last(ids_[i]);
+            if (row < 0) continue;
+            rc = ctx->upload(b->dev + (size_t)row * rowb, values + (size_t)i * rowb, rowb);
+            if (rc) return rc;
+            found[i] = 1;
+            break;
+        }
+    }
+    return GF_OK;
+}
+
+// interface.go:52-55 (TODO in the reference, set.go:216-219)
+int Set::read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<uint8_t> &found)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    found.assign(ids_.size(), 0);
+    SharedGuard g(lock);
+    int rc = ctx->bind();
+    if (rc) return rc;
+    const size_t rowb = (size_t)dims * precision;
+    for (size_t i = 0; i < ids_.size(); ++i) {
+        memset(out + i * rowb, 0, rowb);
+        for (Block *b : blocks) {
+            int row = b->find_last(ids_[i]);
+            if (row < 0) continue;
+            GF_CUDA(cudaMemcpy(out + i * rowb, b->dev + (size_t)row * rowb, rowb, cudaMemcpyDeviceToHost),
+                    GF_ERR_READ_CUDA_BUFFER);
+            ctx->stats.d2h_bytes += rowb;
+            found[i] = 1;
+            break;
+        }
+    }
+    return GF_OK;
+}
+
+// set.go:202-214
+int Set::destroy()
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    destroyed = true;
+    for (Block *b : blocks) {
+        rc = b->release();
+        if (rc) return rc;
+    }
+    blocks.clear();
+    h_segs.clear();
+    seg_block.clear();
+    total_tiles = 0;
+    scanned_rows = 0;
+    if (d_segs) {
+        cudaFree(d_segs);
+        d_segs = nullptr;
+        d_segs_cap = 0;
+    }
+    if (dev_ws) {
+        ctx->release_ws(dev_ws);
+        dev_ws = nullptr;
+    }
+    return GF_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// partial-list bytes one scan pass of qp queries needs
+static size_t partial_bytes(const ScanPlan &p, int qp, int K)
+{
+    return (size_t)p.groups * p.grid_x * qp * K * sizeof(unsigned long long);
+}
+
+int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                     int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
+                     unsigned long long *d_out)
+{
+    const int nseg = (int)h_segs.size();
+    const int maxq = scan_max_q(dims);
+    if (maxq < 1) return GF_ERR_UNSUPPORTED;
+    size_t out_off = 0;
+    for (int p0 = 0; p0 < q; p0 += maxq) {
+        const int qp = std::min(maxq, q - p0);
+        ScanPlan plan;
+        GF_CUDA(scan_make_plan(ctx->sms, dims, qp, K, total_tiles, nseg, per_segment, aligned16, &plan), GF_ERR_CUDA);
+        // the scratch for the per-CTA lists lives at the tail of the workspace arena
+        size_t need = partial_bytes(plan, qp, K);
+        if (need > ws->d_cap) return GF_ERR_ALLOCATE_GPU_BUFFER;  // reserved by the caller
+        unsigned long long *d_partial = (unsigned long long *)(ws->d_buf + ws->d_cap - align_up(need, 256));
+        const unsigned long long *up = nullptr;  // global: [q]; per segment: [pass][segment][qp]
+        if (d_upper) up = per_segment ? d_upper + out_off / K : d_upper + p0;
+        std::pair<cudaEvent_t, cudaEvent_t> ev;
+        ctx->prof_begin(stream, &ev);
+        cudaError_t le = scan_launch(plan, d_segs, nseg, total_tiles, d_queries + (size_t)p0 * q_stride, qp, q_stride,
+                                     l_stride, K, up, d_partial, stream);
+        ctx->prof_end(stream, ev);
+        if (le != cudaSuccess) return cuda_fail(le, "scan_launch", GF_ERR_CUDA);
+        ctx->stats.scan_launches++;
+        ctx->stats.rows_scanned += (uint64_t)scanned_rows;
+        GF_CUDA(merge_launch(d_partial, plan.groups, plan.grid_x, qp, K, d_out + out_off, stream), GF_ERR_CUDA);
+        ctx->stats.merge_launches++;
+        out_off += (size_t)plan.groups * qp * K;
+    }
+    return GF_OK;
+}
+
+// worst-case scratch for topk_device with K <= kMaxK
+static size_t scratch_bytes(const Set *s, int q, int K, bool per_segment)
+{
+    const int nseg = (int)s->h_segs.size();
+    const int maxq = std::max(1, scan_max_q(s->dims));
+    const int qp = std::min(q, maxq);
+    size_t lists = per_segment ? (size_t)std::max(nseg, s->ctx->sms * 2 + nseg) : (size_t)s->ctx->sms;
+    return align_up(lists * qp * K * sizeof(unsigned long long), 256) + 256;
+}
+
+struct KeyList {
+    std::vector<unsigned long long> keys;
+    bool exhausted = false;
+};
+
+// set.go:118-159 + block.go:184-249
+int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out)
+{
+    std::unique_ptr<Result> res(new Result());
+    res->begin(q);
+    SharedGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    ctx->stats.searches++;
+    if (q == 0) {
+        *out = res.release();
+        return GF_OK;
+    }
+    if (scanned_rows == 0 || limit <= 0) {
+        for (int i = 0; i < q; ++i) res->end_query();
+        *out = res.release();
+        return GF_OK;
+    }
+    if (precision != 4) return GF_ERR_UNSUPPORTED;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    const int nseg = (int)h_segs.size();
+    const int64_t k_total = std::min<int64_t>(limit, scanned_rows);
+    const int kb_max = (int)std::min<int64_t>(k_total, kMaxK);
+
+    Workspace *ws = ctx->acquire_ws();
+    if (!ws) return GF_ERR_CUDA;
+    struct Release {
+        Context *c;
+        Workspace *w;
+        ~Release() { c->release_ws(w); }
+    } rel{ctx, ws};
+
+    const size_t qbytes = (size_t)q * dims * 4;
+    const size_t out_keys = (size_t)q * kb_max;
+    size_t d_need = align_up(qbytes, 256) + align_up((size_t)q * 8, 256) + align_up(out_keys * 8, 256) +
+                    scratch_bytes(this, q, kb_max, false);
+    size_t h_need = align_up(qbytes, 256) + align_up((size_t)q * 8, 256) + align_up(out_keys * 8, 256);
+    rc = ws->reserve(d_need, h_need);
+    if (rc) return rc;
+    float *d_q = (float *)ws->d_buf;
+    unsigned long long *d_upper = (unsigned long long *)(ws->d_buf + align_up(qbytes, 256));
+    unsigned long long *d_out = (unsigned long long *)((uint8_t *)d_upper + align_up((size_t)q * 8, 256));
+    float *h_q = (float *)ws->h_buf;
+    unsigned long long *h_upper = (unsigned long long *)(ws->h_buf + align_up(qbytes, 256));
+    unsigned long long *h_out = (unsigned long long *)((uint8_t *)h_upper + align_up((size_t)q * 8, 256));
+
+    memcpy(h_q, queries, qbytes);
+    GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
+    ctx->stats.h2d_bytes += qbytes;
+
+    // ---- set-wide top-k_total, in bands of <= kMaxK keys
+    std::vector<KeyList> lists((size_t)q);
+    int64_t got = 0;
+    bool first_band = true;
+    while (got < k_total) {
+        const int kb = (int)std::min<int64_t>(kMaxK, k_total - got);
+        if (!first_band) {
+            for (int i = 0; i < q; ++i) h_upper[i] = lists[i].exhausted ? 0ull : lists[i].keys.back();
+            GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)q * 8, cudaMemcpyHostToDevice, ws->stream),
+                    GF_ERR_WRITE_INPUT_BUFFER);
+        }
+        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out);
+        if (rc) return rc;
+        GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
+                GF_ERR_READ_CUDA_BUFFER);
+        GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+        ctx->stats.d2h_bytes += (size_t)q * kb * 8;
+        bool all_done = true;
+        for (int i = 0; i < q; ++i) {
+            if (lists[i].exhausted) continue;
+            int n = 0;
+            while (n < kb && h_out[(size_t)i * kb + n] != 0ull) ++n;
+            lists[i].keys.insert(lists[i].keys.end(), h_out + (size_t)i * kb, h_out + (size_t)i * kb + n);
+            if (n < kb) lists[i].exhausted = true;
+            if (!lists[i].exhausted) all_done = false;
+        }
+        got += kb;
+        first_band = false;
+        if (all_done) break;
+    }
+
+    // ---- tombstones among the winners?  (block.go:236-243 selects before it drops them)
+    bool quirk = false;
+    for (int i = 0; i < q && !quirk; ++i) {
+        for (unsigned long long k : lists[i].keys) {
+            int bp, row;
+            if (!slot_to_block(key_slot(k), &bp, &row) || !blocks[bp]->live[row]) {
+                quirk = true;
+                break;
+            }
+        }
+    }
+
+    if (!quirk) {
+        for (int i = 0; i < q; ++i) {
+            for (unsigned long long k : lists[i].keys) {
+                float sc = key_score(k);
+                if (!(sc >= threshold)) continue;  // set.go:145
+                int bp, row;
+                slot_to_block(key_slot(k), &bp, &row);
+                res->push(sc, key_slot(k), blocks[bp]->id_at(row));
+            }
+            res->end_query();
+        }
+        *out = res.release();
+        return GF_OK;
+    }
+
+    // ---- exact per-block path: top-limit per block INCLUDING tombstones, drop them, threshold,
+    // merge, top-limit (block.go:237-243, set.go:138-157)
+    ctx->stats.quirk_fallbacks++;
+    const int maxq = std::max(1, scan_max_q(dims));
+    int64_t max_rows = 0;
+    for (const Segment &s : h_segs) max_rows = std::max<int64_t>(max_rows, s.rows);
+    const int64_t kseg_total = std::min<int64_t>(limit, max_rows);
+    const int kseg = (int)std::min<int64_t>(kseg_total, kMaxK);
+    const size_t seg_keys = (size_t)nseg * q * kseg;
+    d_need = align_up(qbytes, 256) + align_up((size_t)nseg * q * 8, 256) + align_up(seg_keys * 8, 256) +
+             scratch_bytes(this, q, kseg, true);
+    h_need = align_up(qbytes, 256) + align_up((size_t)nseg * q * 8, 256) + align_up(seg_keys * 8, 256);
+    rc = ws->reserve(d_need, h_need);
+    if (rc) return rc;
+    d_q = (float *)ws->d_buf;
+    d_upper = (unsigned long long *)(ws->d_buf + align_up(qbytes, 256));
+    d_out = (unsigned long long *)((uint8_t *)d_upper + align_up((size_t)nseg * q * 8, 256));
+    h_q = (float *)ws->h_buf;
+    h_upper = (unsigned long long *)(ws->h_buf + align_up(qbytes, 256));
+    h_out = (unsigned long long *)((uint8_t *)h_upper + align_up((size_t)nseg * q * 8, 256));
+    memcpy(h_q, queries, qbytes);
+    GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
+
+    // lists per (query, segment); layout of every band on the device: [pass][segment][qp][kb]
+    std::vector<KeyList> seg_lists((size_t)q * nseg);
+    got = 0;
+    first_band = true;
+    while (got < kseg_total) {
+        const int kb = (int)std::min<int64_t>(kMaxK, kseg_total - got);
+        if (!first_band) {
+            size_t off = 0;
+            for (int p0 = 0; p0 < q; p0 += maxq) {
+                int qp = std::min(maxq, q - p0);
+                for (int sgi = 0; sgi < nseg; ++sgi)
+                    for (int j = 0; j < qp; ++j) {
+                        KeyList &kl = seg_lists[(size_t)(p0 + j) * nseg + sgi];
+                        h_upper[off++] = kl.exhausted ? 0ull : kl.keys.back();
+                    }
+            }
+            GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)nseg * q * 8, cudaMemcpyHostToDevice, ws->stream),
+                    GF_ERR_WRITE_INPUT_BUFFER);
+        }
+        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, true, first_band ? nullptr : d_upper, d_out);
+        if (rc) return rc;
+        GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)nseg * q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
+                GF_ERR_READ_CUDA_BUFFER);
+        GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+        ctx->stats.d2h_bytes += (size_t)nseg * q * kb * 8;
+        bool all_done = true;
+        size_t off = 0;
+        for (int p0 = 0; p0 < q; p0 += maxq) {
+            int qp = std::min(maxq, q - p0);
+            for (int sgi = 0; sgi < nseg; ++sgi)
+                for (int j = 0; j < qp; ++j) {
+                    KeyList &kl = seg_lists[(size_t)(p0 + j) * nseg + sgi];
+                    const unsigned long long *src = h_out + off;
+                    off += kb;
+                    if (kl.exhausted) continue;
+                    int n = 0;
+                    while (n < kb && src[n] != 0ull) ++n;
+                    kl.keys.insert(kl.keys.end(), src, src + n);
+                    if (n < kb) kl.exhausted = true;
+                    if (!kl.exhausted) all_done = false;
+                }
+        }
+        got += kb;
+        first_band = false;
+        if (all_done) break;
+    }
+    for (int i = 0; i < q; ++i) {
+        std::vector<unsigned long long> merged;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+            const KeyList &kl = seg_lists[(size_t)i * nseg + sgi];
+            size_t take = std::min<size_t>(kl.keys.size(), (size_t)limit);  // MaxNFloat32(vec, limit)
+            for (size_t j = 0; j < take; ++j) {
+                unsigned long long k = kl.keys[j];
+                int bp, row;
+                if (!slot_to_block(key_slot(k), &bp, &row) || !blocks[bp]->live[row]) continue;  // block.go:239
+                if (!(key_score(k) >= threshold)) continue;                                        // set.go:145
+                merged.push_back(k);
+            }
+        }
+        std::sort(merged.begin(), merged.end(), std::greater<unsigned long long>());  // set.go:155
+        if (merged.size() > (size_t)limit) merged.resize((size_t)limit);
+        for (unsigned long long k : merged) {
+            int bp, row;
+            slot_to_block(key_slot(k), &bp, &row);
+            res->push(key_score(k), key_slot(k), blocks[bp]->id_at(row));
+        }
+        res->end_query();
+    }
+    *out = res.release();
+    return GF_OK;
+}
+
+int Set::search(float threshold, int limit, int q, const uint8_t *queries, Result **out)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (q > batch) return GF_ERR_OUT_OF_BATCH;  // set.go:119-122
+    return search_now(threshold, limit, q, queries, out);
+}
+
+int Set::search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
+                       cudaStream_t stream)
+{
+    (void)path;
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (q > batch) return GF_ERR_OUT_OF_BATCH;
+    if (q <= 0 || limit <= 0) return GF_ERR_INVALID_ARGUMENT;
+    if (limit > kMaxK) return GF_ERR_UNSUPPORTED;
+    if (precision != 4) return GF_ERR_UNSUPPORTED;
+    SharedGuard g(lock);
+    int rc = ctx->bind();
+    if (rc) return rc;
+    ctx->stats.searches++;
+    // one dedicated workspace per set for device-resident searches (calls must be stream ordered)
+    Workspace *ws;
+    {
+        std::lock_guard<std::mutex> lg(co_mu);
+        if (!dev_ws) dev_ws = ctx->acquire_ws();
+        ws = dev_ws;
+    }
+    if (!ws) return GF_ERR_CUDA;
+    cudaStream_t st = stream ? stream : ws->stream;
+    if (scanned_rows == 0) {
+        GF_CUDA(cudaMemsetAsync(d_out, 0, (size_t)q * limit * 8, st), GF_ERR_CUDA);
+        return GF_OK;
+    }
+    size_t need = scratch_bytes(this, q, limit, false);
+    if (need > ws->d_cap) {
+        GF_CUDA(cudaStreamSynchronize(st), GF_ERR_CUDA);
+        rc = ws->reserve(need, 0);
+        if (rc) return rc;
+    }
+    return topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out);
+}
+
+int Set::resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    std::unique_ptr<Result> res(new Result());
+    res->begin(q);
+    SharedGuard g(lock);
+    for (int i = 0; i < q; ++i) {
+        for (int j = 0; j < limit; ++j) {
+            unsigned long long k = h_keys[(size_t)i * limit + j];
+            if (k == 0ull) break;
+            float sc = key_score(k);
+            if (!(sc >= threshold)) continue;
+            int bp, row;
+            if (slot_to_block(key_slot(k), &bp, &row)) {
+                if (!blocks[bp]->live[row]) continue;
+                res->push(sc, key_slot(k), blocks[bp]->id_at(row));
+            } else {
+                res->push(sc, key_slot(k), std::string());  // another shard owns this slot
+            }
+        }
+        res->end_query();
+    }
+    *out = res.release();
+    return GF_OK;
+}
+
+// block.go:184-249 on one bare block; `input` holds the dims-major transposed queries
+int gf::block_search(Block *b, const Buffer *input, int batch, int limit, Result **out)
+{
+    std::unique_ptr<Result> res(new Result());
+    if (!b->is_owned()) return GF_ERR_INVALID_ARGUMENT;
+    if (b->next_index == 0) {  // block.go:186-189: `return` with ret == nil
+        res->begin(0);
+        *out = res.release();
+        return GF_OK;
+    }
+    if (b->precision != 4) return GF_ERR_UNSUPPORTED;
+    if (batch <= 0 || (uint64_t)batch * b->dims * 4 > input->size) return GF_ERR_INVALID_ARGUMENT;
+    res->begin(batch);
+    if (limit <= 0) {
+        for (int i = 0; i < batch; ++i) res->end_query();
+        *out = res.release();
+        return GF_OK;
+    }
+    Context *ctx = b->cache->ctx;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(b->mu);
+    ctx->stats.searches++;
+
+    // a one-segment, un-sharded view of the block
+    Set view;
+    view.cache = b->cache;
+    view.ctx = ctx;
+    view.dims = b->dims;
+    view.precision = 4;
+    view.batch = batch;
+    view.cap = b->capacity();
+    view.blocks.push_back(b);
+    Workspace *ws = ctx->acquire_ws();
+    if (!ws) return GF_ERR_CUDA;
+    struct Release {
+        Context *c;
+        Workspace *w;
+        ~Release() { c->release_ws(w); }
+    } rel{ctx, ws};
+    {
+        // build the segment table in the workspace instead of Set::rebuild_segments' own buffer
+        int tr = scan_tile_rows(b->dims);
+        view.aligned16 = (b->dims % 4 == 0) && (((uintptr_t)b->dev) % 16 == 0);
+        view.tile_rows = (view.aligned16 && tr > 0) ? tr : 64;
+        Segment s;
+        s.base = (const float *)b->dev;
+        s.rows = (uint32_t)b->next_index;
+        s.slot_base = 0;
+        s.tile_start = 0;
+        s.pad = 0;
+        view.h_segs.push_back(s);
+        view.total_tiles = (s.rows + view.tile_rows - 1) / view.tile_rows;
+        view.scanned_rows = b->next_index;
+    }
+    const int64_t k_total = std::min<int64_t>(limit, b->next_index);
+    const int kb_max = (int)std::min<int64_t>(k_total, kMaxK);
+    const size_t out_keys = (size_t)batch * kb_max;
+    size_t d_need = 256 + align_up((size_t)batch * 8, 256) + align_up(out_keys * 8, 256) +
+                    scratch_bytes(&view, batch, kb_max, false);
+    size_t h_need = 256 + align_up((size_t)batch * 8, 256) + align_up(out_keys * 8, 256);
+    rc = ws->reserve(d_need, h_need);
+    if (rc) return rc;
+    Segment *d_seg = (Segment *)ws->d_buf;
+    unsigned long long *d_upper = (unsigned long long *)(ws->d_buf + 256);
+    unsigned long long *d_out = (unsigned long long *)((uint8_t *)d_upper + align_up((size_t)batch * 8, 256));
+    Segment *h_seg = (Segment *)ws->h_buf;
+    unsigned long long *h_upper = (unsigned long long *)(ws->h_buf + 256);
+    unsigned long long *h_out = (unsigned long long *)((uint8_t *)h_upper + align_up((size_t)batch * 8, 256));
+    *h_seg = view.h_segs[0];
+    GF_CUDA(cudaMemcpyAsync(d_seg, h_seg, sizeof(Segment), cudaMemcpyHostToDevice, ws->stream), GF_ERR_CUDA);
+    view.d_segs = d_seg;
+
+    std::vector<KeyList> lists((size_t)batch);
+    int64_t got = 0;
+    bool first_band = true;
+    while (got < k_total) {
+        const int kb = (int)std::min<int64_t>(kMaxK, k_total - got);
+        if (!first_band) {
+            for (int i = 0; i < batch; ++i) h_upper[i] = lists[i].exhausted ? 0ull : lists[i].keys.back();
+            GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)batch * 8, cudaMemcpyHostToDevice, ws->stream),
+                    GF_ERR_CUDA);
+        }
+        // dims-major queries: element l of query i at input[l*batch + i] (util.go:33-36)
+        rc = view.topk_device(ws, ws->stream, (const float *)input->ptr, batch, 1, batch, kb, false,
+                              first_band ? nullptr : d_upper, d_out);
+        if (rc) break;
+        cudaError_t e = cudaMemcpyAsync(h_out, d_out, (size_t)batch * kb * 8, cudaMemcpyDeviceToHost, ws->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ws->stream);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "block search readback", GF_ERR_READ_CUDA_BUFFER);
+            break;
+        }
+        bool all_done = true;
+        for (int i = 0; i < batch; ++i) {
+            if (lists[i].exhausted) continue;
+            int n = 0;
+            while (n < kb && h_out[(size_t)i * kb + n] != 0ull) ++n;
+            lists[i].keys.insert(lists[i].keys.end(), h_out + (size_t)i * kb, h_out + (size_t)i * kb + n);
+            if (n < kb) lists[i].exhausted = true;
+            if (!lists[i].exhausted) all_done = false;
+        }
+        got += kb;
+        first_band = false;
+        if (all_done) break;
+    }
+    view.d_segs = nullptr;  // owned by the workspace
+    view.blocks.clear();
+    if (rc) return rc;
+    for (int i = 0; i < batch; ++i) {
+        for (unsigned long long k : lists[i].keys) {
+            int row = (int)key_slot(k);
+            if (!b->live[row]) continue;  // block.go:239
+            res->push(key_score(k), (uint64_t)row, b->id_at(row));
+        }
+        res->end_query();
+    }
+    *out = res.release();
+    return GF_OK;
+}

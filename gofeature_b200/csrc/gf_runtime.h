@@ -1,0 +1,253 @@
+// gf_runtime.h -- host object model behind the C ABI (internal, C++17).
+//
+// Mirrors the reference's layers: Context (unixpickle/cuda Context), Buffer
+// (buffer.go), Block (block.go), Set (set.go), Cache (cache.go).  Citations are
+// /root/reference/<file>:<line>.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gofeature_b200.h"
+#include "gf_kernels.h"
+
+// The opaque handle types of the C header ARE these structs.
+struct gf_context;
+struct gf_buffer;
+struct gf_cache;
+struct gf_block;
+struct gf_set;
+struct gf_result;
+
+namespace gf {
+
+using Context = ::gf_context;
+using Buffer = ::gf_buffer;
+using Cache = ::gf_cache;
+using Block = ::gf_block;
+using Set = ::gf_set;
+using Result = ::gf_result;
+
+void set_error_detail(const std::string &s);
+int cuda_fail(cudaError_t e, const char *what, int status = GF_ERR_CUDA);
+
+#define GF_CUDA(call, status)                                   \
+    do {                                                        \
+        cudaError_t _e = (call);                                \
+        if (_e != cudaSuccess) return gf::cuda_fail(_e, #call, status); \
+    } while (0)
+
+// writer-preferring reader/writer lock: searches share, Add/Delete/Update exclude
+class RWLock {
+   public:
+    void lock_shared();
+    void unlock_shared();
+    void lock();
+    void unlock();
+
+   private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int readers_ = 0;
+    int writers_waiting_ = 0;
+    bool writer_ = false;
+};
+
+struct Stats {
+    std::atomic<uint64_t> searches{0}, scan_launches{0}, gemm_launches{0}, merge_launches{0}, other_launches{0},
+        rows_scanned{0}, quirk_fallbacks{0}, coalesced_batches{0}, h2d_bytes{0}, d2h_bytes{0}, scan_kernel_ns{0},
+        scan_kernel_timed{0};
+};
+
+// per-search scratch: a stream, device and pinned arenas
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_buf = nullptr;
+    size_t d_cap = 0;
+    uint8_t *h_buf = nullptr;
+    size_t h_cap = 0;
+    int reserve(size_t d_bytes, size_t h_bytes);
+    ~Workspace();
+};
+
+}  // namespace gf
+
+struct gf_context {
+    using Workspace = gf::Workspace;
+    using Stats = gf::Stats;
+    int device = 0;
+    int sms = 0;
+    cudaStream_t mut_stream = nullptr;  // Add / Delete / Update traffic
+    uint8_t *stage[2] = {nullptr, nullptr};  // pinned upload ring
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    std::mutex stage_mu;
+    Stats stats;
+    // optional CUDA-event timing of the scan launches
+    std::atomic<int> profiling{0};
+    std::mutex prof_mu;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending, prof_free;
+    void prof_begin(cudaStream_t st, std::pair<cudaEvent_t, cudaEvent_t> *ev);
+    void prof_end(cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t> &ev);
+    void prof_collect();  // waits for the pending events and folds them into stats
+    std::mutex ws_mu;
+    std::vector<Workspace *> ws_free;
+    std::vector<Workspace *> ws_all;
+
+    int bind() const;  // cudaSetDevice
+    Workspace *acquire_ws();
+    void release_ws(Workspace *w);
+    // pageable host -> device through the pinned ring, on mut_stream; returns after the copy finished
+    int upload(void *dst, const void *src, size_t bytes);
+    ~gf_context();
+};
+
+namespace gf {
+struct DeviceAlloc {
+    Context *ctx;
+    void *ptr;
+    uint64_t size;
+    bool owned;
+    ~DeviceAlloc();
+};
+
+}  // namespace gf
+
+struct gf_buffer {
+    gf::Context *ctx;
+    std::shared_ptr<gf::DeviceAlloc> root;
+    uint8_t *ptr;
+    uint64_t size;
+};
+
+struct gf_result {
+    int batch = 0;
+    std::vector<int64_t> offsets;  // batch + 1
+    std::vector<float> scores;
+    std::vector<uint64_t> slots;
+    std::vector<uint64_t> id_off;  // total + 1
+    std::string id_bytes;
+    void begin(int q);
+    void push(float score, uint64_t slot, const std::string &id);
+    void end_query();
+};
+
+struct gf_block {
+    gf::Cache *cache = nullptr;
+    int index = 0;
+    int64_t block_size = 0;
+    uint8_t *dev = nullptr;
+    std::mutex mu;  // block.go:19
+    // feature info (block.go:24-31)
+    int dims = 0, precision = 0, batch = 0;
+    std::string owner;
+    std::vector<int> empty;
+    int next_index = 0;
+    std::vector<std::string> ids;  // explicit IDs[]; unused while implicit
+    std::vector<uint8_t> live;     // live[j] = (IDs[j] != "")
+    int live_count = 0;
+    // implicit ids "<prefix>%011d" of id_first + slot (synthetic fill); dropped on first refill
+    bool implicit_ids = false;
+    std::string id_prefix;
+    int64_t id_first = 0;
+    std::unordered_map<std::string, std::vector<int>> id_index;  // id -> rows holding it
+    gf::Set *set = nullptr;
+
+    int capacity() const { return (dims > 0 && precision > 0) ? (int)(block_size / ((int64_t)precision * dims)) : 0; }
+    int margin() const { return (int)empty.size() + (capacity() - next_index); }
+    bool is_owned() const { return !owner.empty(); }
+    std::string id_at(int row) const;
+    int find_last(const std::string &id) const;  // largest row holding id, -1 if none (block.go:140-144)
+    void materialize_ids();
+    int acquire(const std::string &owner_, int dims_, int precision_, int batch_);
+    int release();
+    // values: n rows of dims*precision bytes; ids[i] non-empty
+    int insert(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
+    int insert_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
+    int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
+    void index_add(const std::string &id, int row);
+    void index_del(const std::string &id, int row);
+};
+
+namespace gf {
+struct PendingSearch;
+}
+
+struct gf_set {
+    using Segment = gf::Segment;
+    using Workspace = gf::Workspace;
+    using Block = gf::Block;
+    using Result = gf::Result;
+    gf::Cache *cache = nullptr;
+    gf::Context *ctx = nullptr;
+    std::string name;
+    int dims = 0, precision = 0, batch = 0;
+    int cap = 0;  // BlockFeatureNum (cache.go:59)
+    std::vector<Block *> blocks;
+    gf::RWLock lock;
+    bool destroyed = false;
+    int shard_rank = 0, shard_world = 1;
+    // device segment table of the scanned rows, rebuilt after every mutation that moves NextIndex
+    std::vector<Segment> h_segs;
+    std::vector<int> seg_block;  // segment -> position in blocks
+    Segment *d_segs = nullptr;
+    int d_segs_cap = 0;
+    uint32_t total_tiles = 0;
+    int64_t scanned_rows = 0;
+    int tile_rows = 0;
+    bool aligned16 = false;
+    Workspace *dev_ws = nullptr;  // scratch of gf_set_search_device (stream-ordered calls)
+    // coalescer
+    int coalesce_wait_us = 0;
+    std::mutex co_mu;
+    std::condition_variable co_cv;
+    std::vector<gf::PendingSearch *> co_queue;
+    bool co_leader_active = false;
+
+    uint32_t slot_base_of(int block_pos) const
+    {
+        return (uint32_t)(((uint64_t)block_pos * shard_world + shard_rank) * (uint64_t)cap);
+    }
+    int rebuild_segments();  // caller holds the exclusive lock
+    int add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
+    int add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
+    int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
+    int update(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
+    int read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<uint8_t> &found);
+    int search(float threshold, int limit, int q, const uint8_t *queries, Result **out);
+    int search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out);
+    int search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
+                      cudaStream_t stream);
+    int resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out);
+    int destroy();
+    // top-K over the scanned rows into d_out; read lock held by the caller.
+    //   per_segment: d_out is [pass][segment][qp][K] (qp = queries of that pass), else [q][K]
+    int topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                    int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
+                    unsigned long long *d_out);
+    bool slot_to_block(uint32_t slot, int *block_pos, int *row) const;
+};
+
+struct gf_cache {
+    gf::Context *ctx = nullptr;
+    int64_t block_size = 0;
+    std::shared_ptr<gf::DeviceAlloc> slab;
+    std::vector<std::unique_ptr<gf::Block>> all_blocks;
+    std::mutex mu;  // cache.go:17
+    std::unordered_map<std::string, gf::Set *> sets;
+    std::vector<std::unique_ptr<gf::Set>> owned_sets;  // live and destroyed (handles stay valid)
+};
+
+namespace gf {
+
+// searches on one bare block (Block.Search through the C ABI)
+int block_search(Block *b, const Buffer *input, int batch, int limit, Result **out);
+
+}  // namespace gf

@@ -1,0 +1,446 @@
+// gf_scan.cu -- fused dot-product + streaming top-K scan (small query batches), sm_100a.
+//
+// Replaces, for one whole set in ONE launch, what the reference does per block:
+// cublasSgemm (block.go:196-209) + D2H of the full score matrix (block.go:214) +
+// strided gather and full sort on the CPU (block.go:231-237, util.go:76-93).
+//
+// Shape of the work: every feature row (dims float32, contiguous, block.go:99) is read
+// exactly once from HBM; Q <= 8 queries sit in registers; scores never leave the SM.
+// The kernel is HBM-bound: algorithmic bytes per pass = rows*dims*4 (+ Q*dims*4 + lists).
+//
+//   producer warp (1 elected thread): walks this CTA's tiles, one 1-D bulk copy
+//       (cp.async.bulk -> SASS UBLKCP, the TMA engine) of tile_rows*dims*4 = 28 KB per tile
+//       into a `stages`-deep shared-memory ring, completion on an mbarrier (complete_tx).
+//   7 consumer warps: wait on the tile's "full" barrier, each takes tile_rows/7 rows:
+//       128-bit conflict-free LDS, FFMA into the canonical 4 partial sums per thread,
+//       xor-butterfly, then a gate against the CTA's current K-th best key.  The rare
+//       survivor is appended to a per-(CTA,query) list under a shared-memory lock; a
+//       full list is bitonic-sorted by the inserting warp and cut back to K.
+//   end: each list is sorted and its K best keys written to d_partial; merge_kernel
+//       (gf_merge.cu) folds the per-CTA lists into the final K.
+//
+// Grid: persistent, one CTA per SM (148 on B200), tiles strided over CTAs; in per-segment
+// mode (tombstone parity path, block.go:236-243) gridDim.y = blocks and every CTA stays
+// inside one block.
+#include "gf_device.cuh"
+#include "gf_kernels.h"
+
+namespace gf {
+
+namespace {
+
+struct ScanArgs {
+    const Segment *segs;
+    int nseg;
+    uint32_t total_tiles;
+    const float *queries;
+    int q;
+    long long q_stride;
+    long long l_stride;
+    int K;
+    int list_cap;
+    int stages;
+    int tile_rows;
+    int dims;
+    int per_segment;
+    const unsigned long long *upper;
+    unsigned long long *partial;
+};
+
+struct TileMeta {
+    uint32_t rows;
+    uint32_t slot0;
+};
+
+constexpr int kConsumerWarps = kScanConsumerWarps;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+
+__device__ __forceinline__ void tile_range(const ScanArgs &a, uint32_t &first, uint32_t &end, uint32_t &stride,
+                                           uint32_t &group)
+{
+    if (a.per_segment) {
+        group = blockIdx.y;
+        uint32_t b = a.segs[group].tile_start;
+        end = (group + 1 < (uint32_t)a.nseg) ? a.segs[group + 1].tile_start : a.total_tiles;
+        first = b + blockIdx.x;
+    } else {
+        group = 0;
+        first = blockIdx.x;
+        end = a.total_tiles;
+    }
+    stride = gridDim.x;
+}
+
+// gate + insert for one (row, query) score; warp-uniform arguments
+__device__ __forceinline__ void offer(ListCtl *ctl, unsigned long long *buf, int cap, int K, float score,
+                                      uint32_t slot, unsigned long long upper, int lane)
+{
+    unsigned long long key = make_key(score, slot);
+    unsigned long long tau = *(volatile unsigned long long *)&ctl->tau;
+    if (key > tau && key < upper) list_insert(ctl, buf, cap, K, key, lane);
+}
+
+// --------------------------------------------------------------------------------------
+// Bulk-copy (TMA) pipeline kernel.  D in {128,256,512,1024}; CH = D/128 chunks per lane.
+// --------------------------------------------------------------------------------------
+template <int D, int QT>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArgs a)
+{
+    constexpr int CH = D / 128;
+    constexpr int TILE_ROWS = kScanTileBytes / (D * 4);
+    constexpr int RPW = TILE_ROWS / kConsumerWarps;  // rows per warp per tile
+    constexpr int RB = (RPW >= 2 && QT * CH <= 32) ? 2 : 1;  // rows in flight per warp
+    static_assert(RPW >= 1 && RPW % RB == 0, "tile split");
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int stages = a.stages;
+    float *tiles = reinterpret_cast<float *>(smem);
+    uint8_t *p = smem + (size_t)stages * kScanTileBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(p);
+    uint64_t *empty = full + stages;
+    TileMeta *meta = reinterpret_cast<TileMeta *>(empty + stages);
+    ListCtl *ctl = reinterpret_cast<ListCtl *>(meta + stages);
+    unsigned long long *lists = reinterpret_cast<unsigned long long *>(ctl + QT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < QT) {
+        ctl[threadIdx.x].tau = 0ull;
+        ctl[threadIdx.x].cnt = 0;
+        ctl[threadIdx.x].lock = 0;
+    }
+    __syncthreads();
+
+    uint32_t first, end, stride, group;
+    tile_range(a, first, end, stride, group);
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer: one thread feeds the ring =====================
+        if (lane == 0 && first < end) {
+            const uint64_t policy = l2_policy_evict_first();
+            uint32_t segi = a.per_segment ? group : 0;
+            Segment cur = a.segs[segi];
+            uint32_t next_start = (segi + 1 < (uint32_t)a.nseg) ? a.segs[segi + 1].tile_start : a.total_tiles;
+            int s = 0;
+            uint32_t ph = 0;
+            for (uint32_t t = first; t < end; t += stride) {
+                mbar_wait(&empty[s], ph ^ 1);
+                while (t >= next_start) {
+                    ++segi;
+                    cur = a.segs[segi];
+                    next_start = (segi + 1 < (uint32_t)a.nseg) ? a.segs[segi + 1].tile_start : a.total_tiles;
+                }
+                uint32_t row0 = (t - cur.tile_start) * TILE_ROWS;
+                uint32_t rows = min((uint32_t)TILE_ROWS, cur.rows - row0);
+                uint32_t bytes = rows * (uint32_t)(D * 4);
+                meta[s].rows = rows;
+                meta[s].slot0 = cur.slot_base + row0;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s_hint(tiles + (size_t)s * (kScanTileBytes / 4), cur.base + (size_t)row0 * D, bytes, &full[s],
+                              policy);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    float4 qreg[QT][CH];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            float v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int e = 128 * j + 4 * lane + c;
+                v[c] = (qi < a.q) ? a.queries[(long long)qi * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+            }
+            qreg[qi][j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    unsigned long long upper[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi)
+        upper[qi] = (a.upper != nullptr && qi < a.q) ? a.upper[(size_t)group * a.q + qi] : ~0ull;
+
+    const int cap = a.list_cap, K = a.K;
+    int s = 0;
+    uint32_t ph = 0;
+    for (uint32_t t = first; t < end; t += stride) {
+        mbar_wait(&full[s], ph);
+        const uint32_t vrows = meta[s].rows;
+        const uint32_t slot0 = meta[s].slot0;
+        const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * (kScanTileBytes / 4));
+#pragma unroll
+        for (int rb = 0; rb < RPW; rb += RB) {
+            const int r0 = warp * RPW + rb;
+            float4 x[RB][CH];
+#pragma unroll
+            for (int b = 0; b < RB; ++b)
+#pragma unroll
+                for (int j = 0; j < CH; ++j) x[b][j] = tile[(size_t)(r0 + b) * (D / 4) + j * 32 + lane];
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                float sc[RB];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        p0 = __fmaf_rn(x[b][j].x, qreg[qi][j].x, p0);
+                        p1 = __fmaf_rn(x[b][j].y, qreg[qi][j].y, p1);
+                        p2 = __fmaf_rn(x[b][j].z, qreg[qi][j].z, p2);
+                        p3 = __fmaf_rn(x[b][j].w, qreg[qi][j].w, p3);
+                    }
+                    sc[b] = canonical_reduce(p0, p1, p2, p3);
+                }
+                if (qi < a.q) {
+#pragma unroll
+                    for (int b = 0; b < RB; ++b)
+                        if ((uint32_t)(r0 + b) < vrows)
+                            offer(&ctl[qi], lists + (size_t)qi * cap, cap, K, sc[b], slot0 + r0 + b, upper[qi], lane);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+        }
+    }
+
+    named_bar_sync(1, kConsumerThreads);
+    if (warp < a.q && warp < QT) {
+        unsigned long long *out =
+            a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)warp) * (size_t)K;
+        list_flush(&ctl[warp], lists + (size_t)warp * cap, cap, K, out, lane);
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// Generic kernel: any dims, any alignment, plain global loads.  Correct, not tuned --
+// it serves the odd geometries (the reference's own unit test uses dims = 5).
+// --------------------------------------------------------------------------------------
+template <int QT>
+__global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const ScanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int dims = a.dims;
+    float *qs = reinterpret_cast<float *>(smem);  // QT x dims
+    size_t qbytes = ((size_t)QT * dims * 4 + 15) & ~(size_t)15;
+    ListCtl *ctl = reinterpret_cast<ListCtl *>(smem + qbytes);
+    unsigned long long *lists = reinterpret_cast<unsigned long long *>(ctl + QT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < QT * dims; i += blockDim.x) {
+        int qi = i / dims, e = i - qi * dims;
+        qs[i] = (qi < a.q) ? a.queries[(long long)qi * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+    }
+    if (threadIdx.x < QT) {
+        ctl[threadIdx.x].tau = 0ull;
+        ctl[threadIdx.x].cnt = 0;
+        ctl[threadIdx.x].lock = 0;
+    }
+    __syncthreads();
+
+    uint32_t first, end, stride, group;
+    tile_range(a, first, end, stride, group);
+    const int cap = a.list_cap, K = a.K, TR = a.tile_rows;
+    uint32_t segi = a.per_segment ? group : 0;
+
+    for (uint32_t t = first; t < end; t += stride) {
+        while (segi + 1 < (uint32_t)a.nseg && t >= a.segs[segi + 1].tile_start) ++segi;
+        const Segment cur = a.segs[segi];
+        const uint32_t row0 = (t - cur.tile_start) * TR;
+        const uint32_t vrows = min((uint32_t)TR, cur.rows - row0);
+        for (uint32_t r = warp; r < vrows; r += kConsumerWarps) {
+            const float *x = cur.base + (size_t)(row0 + r) * dims;
+            float P[QT][4];
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) P[qi][0] = P[qi][1] = P[qi][2] = P[qi][3] = 0.f;
+            for (int j = 0; j < dims; j += 128) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int e = j + 4 * lane + c;
+                    if (e < dims) {
+                        float xv = __ldg(x + e);
+#pragma unroll
+                        for (int qi = 0; qi < QT; ++qi) P[qi][c] = __fmaf_rn(xv, qs[qi * dims + e], P[qi][c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                float sc = canonical_reduce(P[qi][0], P[qi][1], P[qi][2], P[qi][3]);
+                if (qi < a.q) {
+                    unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + qi] : ~0ull;
+                    offer(&ctl[qi], lists + (size_t)qi * cap, cap, K, sc, cur.slot_base + row0 + r, up, lane);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < a.q && warp < QT) {
+        unsigned long long *out =
+            a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)warp) * (size_t)K;
+        list_flush(&ctl[warp], lists + (size_t)warp * cap, cap, K, out, lane);
+    }
+}
+
+constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in per CTA on sm_100
+
+int next_pow2(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <typename Kern>
+cudaError_t set_smem_attr(Kern kern, size_t bytes)
+{
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int D, int QT>
+cudaError_t launch_tma(const ScanPlan &plan, const ScanArgs &args, cudaStream_t stream)
+{
+    if constexpr (QT * D > 4096) {
+        return cudaErrorInvalidValue;
+    } else {
+        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT>, plan.smem_bytes);
+        if (e != cudaSuccess) return e;
+        dim3 grid(plan.grid_x, plan.groups);
+        scan_tma_kernel<D, QT><<<grid, kScanThreads, plan.smem_bytes, stream>>>(args);
+        return cudaGetLastError();
+    }
+}
+
+template <int D>
+cudaError_t launch_tma_q(const ScanPlan &plan, const ScanArgs &args, cudaStream_t stream)
+{
+    switch (plan.qt) {
+        case 1: return launch_tma<D, 1>(plan, args, stream);
+        case 2: return launch_tma<D, 2>(plan, args, stream);
+        case 4: return launch_tma<D, 4>(plan, args, stream);
+        case 8: return launch_tma<D, 8>(plan, args, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int QT>
+cudaError_t launch_generic(const ScanPlan &plan, const ScanArgs &args, cudaStream_t stream)
+{
+    cudaError_t e = set_smem_attr(scan_generic_kernel<QT>, plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid(plan.grid_x, plan.groups);
+    scan_generic_kernel<QT><<<grid, kConsumerThreads, plan.smem_bytes, stream>>>(args);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int scan_tile_rows(int dims)
+{
+    if (dims == 128 || dims == 256 || dims == 512 || dims == 1024) return kScanTileBytes / (dims * 4);
+    return 0;
+}
+
+int scan_max_q(int dims)
+{
+    if (scan_tile_rows(dims)) return dims <= 512 ? 8 : 4;
+    // generic path: queries live in shared memory
+    int byq = (int)(96 * 1024 / ((size_t)dims * 4));
+    if (byq >= 8) return 8;
+    if (byq >= 4) return 4;
+    if (byq >= 2) return 2;
+    return byq >= 1 ? 1 : 0;
+}
+
+cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t total_tiles, int nseg, bool per_segment,
+                           bool aligned16, ScanPlan *plan)
+{
+    if (q < 1 || q > kScanMaxQ || K < 1 || K > kMaxK || dims < 1) return cudaErrorInvalidValue;
+    ScanPlan p{};
+    p.dims = dims;
+    p.qt = q <= 1 ? 1 : q <= 2 ? 2 : q <= 4 ? 4 : 8;
+    p.list_cap = next_pow2(2 * K < 64 ? 64 : 2 * K);
+    size_t lists_bytes = (size_t)p.qt * p.list_cap * 8;
+    int tr = scan_tile_rows(dims);
+    p.tma = aligned16 && tr > 0 && p.qt * dims <= 4096;
+    if (p.tma) {
+        p.tile_rows = tr;
+        size_t fixed = 1024;
+        if (lists_bytes + fixed + 2 * (size_t)kScanTileBytes > kSmemLimit) return cudaErrorInvalidValue;
+        int st = (int)((kSmemLimit - fixed - lists_bytes) / kScanTileBytes);
+        p.stages = st > 7 ? 7 : st;
+        p.smem_bytes = (size_t)p.stages * kScanTileBytes + fixed + lists_bytes;
+    } else {
+        p.tile_rows = 64;
+        p.stages = 0;
+        size_t qbytes = ((size_t)p.qt * dims * 4 + 15) & ~(size_t)15;
+        p.smem_bytes = qbytes + 256 + lists_bytes;
+        if (p.smem_bytes > kSmemLimit) return cudaErrorInvalidValue;
+    }
+    p.groups = per_segment ? nseg : 1;
+    uint32_t per_group_tiles = per_segment ? (total_tiles + nseg - 1) / (nseg > 0 ? nseg : 1) : total_tiles;
+    int want = per_segment ? (device_sms * 2 + nseg - 1) / (nseg > 0 ? nseg : 1) : device_sms;
+    if (want < 1) want = 1;
+    if ((uint32_t)want > per_group_tiles) want = (int)per_group_tiles;
+    if (want < 1) want = 1;
+    p.grid_x = want;
+    *plan = p;
+    return cudaSuccess;
+}
+
+cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, uint32_t total_tiles,
+                        const float *d_queries, int q, int64_t q_stride, int64_t l_stride, int K,
+                        const unsigned long long *d_upper, unsigned long long *d_partial, cudaStream_t stream)
+{
+    ScanArgs a{};
+    a.segs = d_segs;
+    a.nseg = nseg;
+    a.total_tiles = total_tiles;
+    a.queries = d_queries;
+    a.q = q;
+    a.q_stride = q_stride;
+    a.l_stride = l_stride;
+    a.K = K;
+    a.list_cap = plan.list_cap;
+    a.stages = plan.stages;
+    a.tile_rows = plan.tile_rows;
+    a.dims = plan.dims;
+    a.per_segment = (plan.groups != 1) ? 1 : 0;
+    a.upper = d_upper;
+    a.partial = d_partial;
+    if (plan.tma) {
+        switch (plan.dims) {
+            case 128: return launch_tma_q<128>(plan, a, stream);
+            case 256: return launch_tma_q<256>(plan, a, stream);
+            case 512: return launch_tma_q<512>(plan, a, stream);
+            case 1024: return launch_tma_q<1024>(plan, a, stream);
+        }
+        return cudaErrorInvalidValue;
+    }
+    switch (plan.qt) {
+        case 1: return launch_generic<1>(plan, a, stream);
+        case 2: return launch_generic<2>(plan, a, stream);
+        case 4: return launch_generic<4>(plan, a, stream);
+        case 8: return launch_generic<8>(plan, a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace gf

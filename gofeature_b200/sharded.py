@@ -1,0 +1,186 @@
+"""Row-sharded feature set over the ranks of one torch.distributed job (one process per GPU).
+
+The reference is single-device (`devices[0]`, search_test.go:40); what it already does across
+*blocks* -- independent per-block top-limit, then a merge (set.go:129-157) -- is done here
+across *ranks*: global block g lives on rank g % world as that rank's block g // world
+(SURVEY 8e), every rank scans only its own rows, and the only exchange is one all-gather of
+`limit` candidate keys per query per rank (12.5 M rows/GPU -> 80 bytes per query per rank at
+limit 10), followed by the same merge kernel that folds the per-CTA lists.
+
+torch is plumbing here: device tensors for the keys, `torch.distributed` (NCCL over
+NVLink/NVSwitch on GPUs, gloo for the CPU tests of the host logic) for the gather.
+"""
+import numpy as np
+
+from . import api
+
+
+def owner_of(global_block, world):
+    """(rank, local block position) of a global block (block striping)."""
+    return global_block % world, global_block // world
+
+
+def split_rows(n_existing, n_new, cap, world):
+    """Which rank receives which of `n_new` appended rows when the sharded set already holds
+    `n_existing` rows: rows fill global blocks of `cap` rows in order (set.go:97-114), block g on
+    rank g % world.  Returns a list of (rank, start, stop) slices of the new rows, in order."""
+    out = []
+    pos, end = n_existing, n_existing + n_new
+    while pos < end:
+        g = pos // cap
+        stop = min(end, (g + 1) * cap)
+        out.append((g % world, pos - n_existing, stop - n_existing))
+        pos = stop
+    return out
+
+
+def merge_keys_host(gathered, limit):
+    """Reference merge of per-rank key lists on the host: gathered [world, q, limit] uint64
+    (descending, zero padded) -> [q, limit].  Same total order as the device merge kernel; used
+    by the gloo tests of the host logic and as a cross-check of gf_merge_keys_device."""
+    g = np.asarray(gathered, dtype=np.uint64)
+    world, q, k = g.shape
+    out = np.zeros((q, limit), dtype=np.uint64)
+    for i in range(q):
+        allk = np.sort(g[:, i, :].reshape(-1))[::-1]
+        allk = allk[allk != 0][:limit]
+        out[i, :len(allk)] = allk
+    return out
+
+
+class ShardedSet:
+    """One logical set, row-sharded over `world` ranks.  Every rank constructs it collectively.
+
+    Append-only through this wrapper (Add / AddSynthetic); Delete is forwarded to every rank and
+    each removes the ids it owns.  Search is collective and returns the same result on every rank.
+    """
+
+    def __init__(self, ctx, cache, name, dims, batch, rank, world, group=None):
+        self.ctx, self.cache, self.name = ctx, cache, name
+        self.dims, self.batch, self.rank, self.world, self.group = dims, batch, rank, world, group
+        cache.NewSet(name, dims, 4, batch)
+        self.local = cache.GetSet(name)
+        self.local.SetShard(rank, world)
+        self.cap = cache.GetBlockSize() // (dims * 4)
+        self.total_rows = 0
+        self._bufs = {}
+
+    # ---- mutation (collective: every rank passes the same arguments)
+    def Add(self, values, ids):
+        values = np.ascontiguousarray(values, dtype=np.float32).reshape(len(ids), self.dims)
+        for r, a, b in split_rows(self.total_rows, len(ids), self.cap, self.world):
+            if r == self.rank:
+                self.local.AddArray(values[a:b], ids[a:b])
+        self.total_rows += len(ids)
+
+    def AddSynthetic(self, n, seed, normalize=True, id_prefix="f"):
+        for r, a, b in split_rows(self.total_rows, n, self.cap, self.world):
+            if r == self.rank:
+                self.local.AddSynthetic(b - a, seed, self.total_rows + a, normalize, id_prefix)
+        self.total_rows += n
+
+    def Delete(self, *ids):
+        import torch
+        import torch.distributed as dist
+        mine = self.local.Delete(*ids) or []
+        flags = torch.tensor([1 if i in set(mine) else 0 for i in ids], dtype=torch.int32)
+        if self.world > 1:
+            dev = flags.cuda() if dist.get_backend(self.group) == "nccl" else flags
+            dist.all_reduce(dev, op=dist.ReduceOp.MAX, group=self.group)
+            flags = dev.cpu()
+        return [i for i, f in zip(ids, flags.tolist()) if f] or None
+
+    # ---- search
+    def _tensors(self, q, limit):
+        import torch
+        key = (q, limit)
+        if key not in self._bufs:
+            dev = "cuda:%d" % self.ctx.device
+            self._bufs[key] = dict(
+                dq=torch.empty((q, self.dims), dtype=torch.float32, device=dev),
+                local=torch.zeros((q, limit), dtype=torch.int64, device=dev),
+                gathered=torch.zeros((self.world, q, limit), dtype=torch.int64, device=dev),
+                merged=torch.zeros((q, limit), dtype=torch.int64, device=dev),
+                hq=torch.empty((q, self.dims), dtype=torch.float32).pin_memory(),
+                hk=torch.empty((q, limit), dtype=torch.int64).pin_memory(),
+            )
+        return self._bufs[key]
+
+    def search_device(self, limit, q, dq, out=None):
+        """Collective device-resident search: dq [q, dims] float32 on this rank's GPU (same on all
+        ranks) -> merged keys [q, limit] int64 tensor, identical on every rank.  Enqueues on the
+        current torch stream; no host synchronisation."""
+        import torch
+        import torch.distributed as dist
+        t = self._tensors(q, limit)
+        stream = torch.cuda.current_stream().cuda_stream
+        self.local.SearchDevice(limit, q, dq.data_ptr(), t["local"].data_ptr(), 0, stream)
+        if self.world == 1:
+            return t["local"]
+        dist.all_gather_into_tensor(t["gathered"], t["local"], group=self.group)
+        merged = out if out is not None else t["merged"]
+        api._check(api.lib().gf_merge_keys_device(self.ctx._h, self.world, q, limit, t["gathered"].data_ptr(),
+                                                  merged.data_ptr(), stream))
+        return merged
+
+    def search_keys(self, limit, queries):
+        """Host queries [q, dims] -> merged keys [q, limit] uint64 on the host (H2D, scan, gather,
+        merge, D2H all inside)."""
+        import torch
+        queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dims)
+        q = queries.shape[0]
+        if q > self.batch:
+            raise api.GoFeatureError(api.ErrOutOfBatch)  # set.go:119-122
+        t = self._tensors(q, limit)
+        t["hq"].numpy()[:] = queries
+        t["dq"].copy_(t["hq"], non_blocking=True)
+        merged = self.search_device(limit, q, t["dq"])
+        t["hk"].copy_(merged, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return t["hk"].numpy().view(np.uint64).copy()
+
+    def Search(self, threshold, limit, queries):
+        """Collective Set.Search (set.go:118-159) over the sharded rows.  IDs are resolved by the
+        rank that owns each winning slot and exchanged as fixed-width bytes."""
+        import torch
+        import torch.distributed as dist
+        keys = self.search_keys(limit, queries)
+        mine = self.local.ResolveKeys(threshold, limit, keys)
+        if self.world == 1:
+            return mine
+        # every rank fills the ids (and tombstone flags) of the slots it owns
+        q = keys.shape[0]
+        width = 64
+        table = np.zeros((q, limit, width + 2), dtype=np.uint8)   # [..., 0]=owned+live, [..., 1]=len
+        for i in range(q):
+            own = {r.Slot: r for r in mine[i] if r.ID != ""}
+            for j in range(limit):
+                k = int(keys[i, j])
+                if k == 0:
+                    break
+                r = own.get(api.key_slot(k))
+                if r is not None:
+                    b = r.ID.encode() if isinstance(r.ID, str) else r.ID
+                    table[i, j, 0], table[i, j, 1] = 1, len(b)
+                    table[i, j, 2:2 + len(b)] = np.frombuffer(b[:width], dtype=np.uint8)
+        tt = torch.from_numpy(table).to("cuda:%d" % self.ctx.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=self.group)
+        table = tt.cpu().numpy()
+        out = []
+        for i in range(q):
+            row = []
+            for j in range(limit):
+                k = int(keys[i, j])
+                if k == 0:
+                    break
+                if not table[i, j, 0]:
+                    continue                                   # tombstone on its owner rank
+                sc = api.key_score(k)
+                if not (sc >= np.float32(threshold)):
+                    continue
+                n = int(table[i, j, 1])
+                row.append(api.FeatureSearchResult(sc, bytes(table[i, j, 2:2 + n]).decode(errors="replace"),
+                                                   api.key_slot(k)))
+            out.append(row)
+        return out
+

@@ -1,0 +1,450 @@
+/*
+ * gf_oracle.c -- CPU restatement of goFeature's brute-force search path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under gofeature_b200/ may include, link or
+ * call this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and only as the checker or the
+ * reported CPU baseline.
+ *
+ * What it restates (all citations are /root/reference/<file>:<line>):
+ *   - NoramlizeFloat32            util.go:125-139
+ *   - FeatureValueTranspose1D     util.go:21-39
+ *   - MaxNFloat32 / MaxNFeatureResult   util.go:76-93, 95-112
+ *   - _Block.Search               block.go:184-249  (scores for all NextIndex rows,
+ *                                 per-query top-limit INCLUDING zeroed tombstones,
+ *                                 tombstones dropped AFTER selection)
+ *   - FeatureSet.Search           set.go:118-159    (per-block fan-out, Score >= threshold,
+ *                                 final top-limit over the merged block winners)
+ *   - the arithmetic of the one GPU call, cublasSgemm(N,N,Q,height,dims,1,A,Q,B,dims,0,C,Q)
+ *     (block.go:196-209): score[q][j] = sum_l query[q][l] * row[j][l] in float32.
+ *
+ * The arithmetic lives in a third-party dependency that is NOT under /root/reference:
+ * github.com/unixpickle/cuda/cublas (unpinned, `go get` at HEAD, docker/Dockerfile:23),
+ * a cgo pass-through to cublasSgemm_v2 of CUDA 8.0.  cuBLAS does not publish its fp32
+ * summation order, so three orders are offered here:
+ *   mode 0  CANONICAL  the order the sm_100a kernels use, bit-for-bit (see gf_dot_canonical)
+ *   mode 1  SEQ32      plain left-to-right float32 multiply-add, what a Go `for` loop gives
+ *   mode 2  F64        double accumulation of the stored float32 values (ground truth)
+ *
+ * Parity pin status: IDs / result counts are pinned by the five known-answer assertions
+ * of the reference's only test, TestBasicSearch (search_test.go:77-145; fixtures in
+ * tests/golden/basic_search.json).  Numeric scores are pinned by that test only through
+ * its inequalities (>= 0.999999, <= 0.999999); no golden score file exists in the
+ * reference and the reference cannot be built here (no Go toolchain, un-vendored deps).
+ * Tie order is unspecified in the reference (sort.Slice is unstable, util.go:85,104);
+ * this oracle fixes it to: score descending, then (block position in Set.Blocks, row)
+ * ascending; NaN sorts below -Inf; -0.0 is folded into +0.0.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#define GF_HAVE_AVX2 1
+#else
+#define GF_HAVE_AVX2 0
+#endif
+
+#define GF_EXPORT __attribute__((visibility("default")))
+
+enum { GF_MODE_CANONICAL = 0, GF_MODE_SEQ32 = 1, GF_MODE_F64 = 2 };
+
+/* ------------------------------------------------------------------ ordering */
+
+/* Orderable image of a score: larger image = better.  NaN -> 0 (worst),
+ * -0.0 folded to +0.0 so that 0.0 == -0.0 tie on the slot like Go's `>` does. */
+static inline uint32_t gf_score_image(float s)
+{
+    uint32_t u;
+    if (s != s) return 0u;
+    s = s + 0.0f;
+    memcpy(&u, &s, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+GF_EXPORT uint32_t gf_oracle_score_image(float s) { return gf_score_image(s); }
+
+/* ---------------------------------------------------------------- arithmetic */
+
+/*
+ * CANONICAL float32 dot product.  128 partial sums P[v], element e feeds
+ * P[e % 128] with one fused multiply-add, e ascending.  Then the fixed tree
+ *   T[l] = (P[4l] + P[4l+1]) + (P[4l+2] + P[4l+3])          l = 0..31
+ *   for off in 16, 8, 4, 2, 1:  T[l] = T[l] + T[l ^ off]
+ * and the score is T[0] + 0.0f.  On the GPU, thread l of a warp owns
+ * P[4l..4l+3] (one 128-bit load per 128 elements) and the tree is the
+ * xor-butterfly of five warp shuffles.
+ */
+static float gf_dot_canonical_scalar(const float *x, const float *q, int dims)
+{
+    float P[128];
+    float T[32];
+    int e, l, off;
+    for (e = 0; e < 128; ++e) P[e] = 0.0f;
+    for (e = 0; e < dims; ++e) P[e & 127] = fmaf(x[e], q[e], P[e & 127]);
+    for (l = 0; l < 32; ++l) T[l] = (P[4 * l] + P[4 * l + 1]) + (P[4 * l + 2] + P[4 * l + 3]);
+    for (off = 16; off >= 1; off >>= 1)
+        for (l = 0; l < off; ++l) T[l] = T[l] + T[l + off];
+    return T[0] + 0.0f;
+}
+
+#if GF_HAVE_AVX2
+/* Same value as gf_dot_canonical_scalar, bit for bit, for dims % 128 == 0.
+ * Register r holds P[8r..8r+7] = threads 2r (low half) and 2r+1 (high half). */
+static float gf_dot_canonical_avx2(const float *x, const float *q, int dims)
+{
+    __m256 a[16];
+    int r, j;
+    for (r = 0; r < 16; ++r) a[r] = _mm256_setzero_ps();
+    for (j = 0; j < dims; j += 128)
+        for (r = 0; r < 16; ++r)
+            a[r] = _mm256_fmadd_ps(_mm256_loadu_ps(x + j + 8 * r), _mm256_loadu_ps(q + j + 8 * r), a[r]);
+    /* hadd(A,B) = [A0+A1, A2+A3, B0+B1, B2+B3 | A4+A5, A6+A7, B4+B5, B6+B7]
+     * two levels give per-thread sums T: R[k] = [T(8k),T(8k+2),T(8k+4),T(8k+6) | T(8k+1),T(8k+3),T(8k+5),T(8k+7)] */
+    __m256 R[4];
+    for (r = 0; r < 4; ++r) {
+        __m256 h0 = _mm256_hadd_ps(a[4 * r + 0], a[4 * r + 1]);
+        __m256 h1 = _mm256_hadd_ps(a[4 * r + 2], a[4 * r + 3]);
+        R[r] = _mm256_hadd_ps(h0, h1);
+    }
+    /* xor 16: T(l)+T(l+16) -> R0+R2, R1+R3 ; xor 8: T(l)+T(l+8) */
+    __m256 s16a = _mm256_add_ps(R[0], R[2]);
+    __m256 s16b = _mm256_add_ps(R[1], R[3]);
+    __m256 s8 = _mm256_add_ps(s16a, s16b); /* [t0,t2,t4,t6 | t1,t3,t5,t7] */
+    /* xor 4: t0+t4, t2+t6 | t1+t5, t3+t7 */
+    __m256 s4 = _mm256_add_ps(s8, _mm256_permute_ps(s8, 0x4E)); /* swap pairs (0,1)<->(2,3) */
+    /* xor 2: (t0+t4)+(t2+t6) */
+    __m256 s2 = _mm256_add_ps(s4, _mm256_permute_ps(s4, 0xB1)); /* swap adjacent */
+    /* xor 1: low half + high half */
+    __m128 lo = _mm256_castps256_ps128(s2);
+    __m128 hi = _mm256_extractf128_ps(s2, 1);
+    float out = _mm_cvtss_f32(_mm_add_ss(lo, hi));
+    return out + 0.0f;
+}
+#endif
+
+static inline float gf_dot_canonical(const float *x, const float *q, int dims)
+{
+#if GF_HAVE_AVX2
+    if ((dims & 127) == 0) return gf_dot_canonical_avx2(x, q, dims);
+#endif
+    return gf_dot_canonical_scalar(x, q, dims);
+}
+
+/* SEQ32: what `for l { acc += a[l]*b[l] }` in Go float32 gives (separate mul and add). */
+static float gf_dot_seq32(const float *x, const float *q, int dims)
+{
+    volatile float acc = 0.0f; /* volatile: forbid reassociation / contraction */
+    int e;
+    for (e = 0; e < dims; ++e) {
+        volatile float p = x[e] * q[e];
+        acc = acc + p;
+    }
+    return acc;
+}
+
+static double gf_dot_f64(const float *x, const float *q, int dims)
+{
+    double acc = 0.0;
+    int e;
+    for (e = 0; e < dims; ++e) acc += (double)x[e] * (double)q[e];
+    return acc;
+}
+
+GF_EXPORT double gf_oracle_dot(const float *x, const float *q, int dims, int mode)
+{
+    if (mode == GF_MODE_CANONICAL) return (double)gf_dot_canonical(x, q, dims);
+    if (mode == GF_MODE_SEQ32) return (double)gf_dot_seq32(x, q, dims);
+    return gf_dot_f64(x, q, dims);
+}
+
+/* scalar twin of the AVX2 kernel, exported so tests can prove they agree */
+GF_EXPORT float gf_oracle_dot_canonical_scalar(const float *x, const float *q, int dims)
+{
+    return gf_dot_canonical_scalar(x, q, dims);
+}
+
+GF_EXPORT int gf_oracle_have_avx2(void) { return GF_HAVE_AVX2; }
+
+/* util.go:125-139 NoramlizeFloat32: sequential float32 sum of squares, sqrt through
+ * float64 pow(.,0.5), per-element float32 divide, all-zero input -> zeros. */
+GF_EXPORT void gf_oracle_normalize(const float *in, float *out, int n)
+{
+    volatile float mode = 0.0f;
+    int i;
+    for (i = 0; i < n; ++i) {
+        volatile float sq = in[i] * in[i];
+        mode = mode + sq;
+    }
+    float m = (float)pow((double)mode, 0.5);
+    if (m == 0.0f) {
+        for (i = 0; i < n; ++i) out[i] = 0.0f;
+        return;
+    }
+    for (i = 0; i < n; ++i) out[i] = in[i] / m;
+}
+
+/* util.go:21-39 FeatureValueTranspose1D: ret[(i*row + j)] = features[j][i] on
+ * `precision`-byte elements; returns -1 for ErrBadTransposeValue. */
+GF_EXPORT int gf_oracle_transpose1d(int precision, const uint8_t *const *features, int row, int len0, uint8_t *ret)
+{
+    int i, j;
+    if (row == 0) return 0;
+    if (precision <= 0 || len0 % precision != 0) return -1;
+    int col = len0 / precision;
+    for (i = 0; i < col; ++i)
+        for (j = 0; j < row; ++j)
+            memcpy(ret + (size_t)(i * row + j) * precision, features[j] + (size_t)i * precision, (size_t)precision);
+    return 0;
+}
+
+/* ------------------------------------------------------------------- top-N */
+
+typedef struct {
+    double score;   /* float32-exact in modes 0/1 */
+    uint32_t image; /* ordering image of (float)score */
+    int64_t slot;   /* tie-break: ascending */
+} gf_cand;
+
+static inline int gf_better(const gf_cand *a, const gf_cand *b)
+{
+    if (a->image != b->image) return a->image > b->image;
+    if (a->score != b->score && a->score == a->score && b->score == b->score) return a->score > b->score; /* F64 mode */
+    return a->slot < b->slot;
+}
+
+static int gf_cand_cmp(const void *pa, const void *pb)
+{
+    const gf_cand *a = (const gf_cand *)pa, *b = (const gf_cand *)pb;
+    if (gf_better(a, b)) return -1;
+    if (gf_better(b, a)) return 1;
+    return 0;
+}
+
+/* util.go:76-93 MaxNFloat32: full descending sort, first `limit` (limit > n -> all).
+ * Canonical tie order: index ascending. */
+GF_EXPORT int gf_oracle_maxn_float32(const float *vector, int n, int limit, int *out_index, float *out_value)
+{
+    int i;
+    if (limit < 0) limit = 0;
+    gf_cand *c = (gf_cand *)malloc(sizeof(gf_cand) * (size_t)(n > 0 ? n : 1));
+    for (i = 0; i < n; ++i) {
+        c[i].score = vector[i];
+        c[i].image = gf_score_image(vector[i]);
+        c[i].slot = i;
+    }
+    qsort(c, (size_t)n, sizeof(gf_cand), gf_cand_cmp);
+    int m = limit < n ? limit : n;
+    for (i = 0; i < m; ++i) {
+        out_index[i] = (int)c[i].slot;
+        out_value[i] = (float)c[i].score;
+    }
+    free(c);
+    return m;
+}
+
+/* ------------------------------------------------------ block / set search */
+
+static double gf_score(const float *x, const float *q, int dims, int mode)
+{
+    return gf_oracle_dot(x, q, dims, mode);
+}
+
+/*
+ * FeatureSet.Search (set.go:118-159) over nblocks blocks.
+ *   rows[b]    : heights[b] x dims float32, row-major (block.go:99,111 layout); tombstoned rows
+ *                are whatever the device holds (the runtime zeroes them, block.go:152-158)
+ *   live[b][j] : 1 if IDs[j] != "" (block.go:239)
+ *   queries    : Q x dims row-major
+ * out_*        : Q x limit, entries beyond out_counts[q] untouched.
+ * Returns 0.
+ */
+GF_EXPORT int gf_oracle_set_search(const float *const *rows, const int *heights, const uint8_t *const *live,
+                                   int nblocks, int dims, const float *queries, int Q, int limit, float threshold,
+                                   int mode, int *out_counts, double *out_scores, int *out_block, int *out_row)
+{
+    int q, b, j;
+    if (limit < 0) limit = 0;
+    for (q = 0; q < Q; ++q) {
+        const float *qv = queries + (size_t)q * dims;
+        size_t cap = 0, n = 0;
+        gf_cand *merged = NULL;
+        for (b = 0; b < nblocks; ++b) {
+            int h = heights[b];
+            if (h == 0) continue; /* block.go:186-189 */
+            gf_cand *c = (gf_cand *)malloc(sizeof(gf_cand) * (size_t)h);
+            for (j = 0; j < h; ++j) {
+                double s = gf_score(rows[b] + (size_t)j * dims, qv, dims, mode);
+                c[j].score = s;
+                c[j].image = gf_score_image((float)s);
+                c[j].slot = j;
+            }
+            qsort(c, (size_t)h, sizeof(gf_cand), gf_cand_cmp); /* MaxNFloat32, block.go:237 */
+            int m = limit < h ? limit : h;
+            for (j = 0; j < m; ++j) {
+                if (!live[b][c[j].slot]) continue;                /* block.go:239 */
+                if (!((float)c[j].score >= threshold)) continue;  /* set.go:145 */
+                if (n == cap) {
+                    cap = cap ? cap * 2 : 64;
+                    merged = (gf_cand *)realloc(merged, cap * sizeof(gf_cand));
+                }
+                merged[n] = c[j];
+                merged[n].slot = ((int64_t)b << 32) | (int64_t)c[j].slot;
+                ++n;
+            }
+            free(c);
+        }
+        if (n) qsort(merged, n, sizeof(gf_cand), gf_cand_cmp); /* MaxNFeatureResult, set.go:155 */
+        int m = (size_t)limit < n ? limit : (int)n;
+        out_counts[q] = m;
+        for (j = 0; j < m; ++j) {
+            out_scores[(size_t)q * limit + j] = merged[j].score;
+            out_block[(size_t)q * limit + j] = (int)(merged[j].slot >> 32);
+            out_row[(size_t)q * limit + j] = (int)(merged[j].slot & 0xffffffff);
+        }
+        free(merged);
+    }
+    return 0;
+}
+
+/* -------------------------------------------- multi-threaded plain scan (CPU baseline) */
+
+/*
+ * Brute-force scan of one contiguous n x dims matrix: Q queries, top-`limit` each,
+ * canonical arithmetic, bounded insertion list instead of the reference's full sort
+ * (same answer: a total order has one top-N).  Row ranges per thread mirror the
+ * reference's one-goroutine-per-block post-processing (block.go:76).
+ */
+typedef struct {
+    const float *rows;
+    int64_t lo, hi;
+    int dims, Q, limit, mode;
+    const float *queries;
+    gf_cand *best; /* Q x limit */
+    int *cnt;      /* Q */
+} gf_scan_job;
+
+static void gf_insert(gf_cand *best, int *cnt, int limit, const gf_cand *c)
+{
+    int n = *cnt, i;
+    if (n == limit) {
+        if (limit == 0 || !gf_better(c, &best[n - 1])) return;
+        n = n - 1;
+    }
+    i = n;
+    while (i > 0 && gf_better(c, &best[i - 1])) {
+        best[i] = best[i - 1];
+        --i;
+    }
+    best[i] = *c;
+    *cnt = n + 1;
+}
+
+static void *gf_scan_worker(void *arg)
+{
+    gf_scan_job *jb = (gf_scan_job *)arg;
+    int64_t j;
+    int q;
+    for (j = jb->lo; j < jb->hi; ++j) {
+        const float *x = jb->rows + (size_t)j * jb->dims;
+        for (q = 0; q < jb->Q; ++q) {
+            gf_cand c;
+            c.score = gf_score(x, jb->queries + (size_t)q * jb->dims, jb->dims, jb->mode);
+            c.image = gf_score_image((float)c.score);
+            c.slot = j;
+            gf_insert(jb->best + (size_t)q * jb->limit, jb->cnt + q, jb->limit, &c);
+        }
+    }
+    return NULL;
+}
+
+GF_EXPORT int gf_oracle_scan_topk(const float *rows, int64_t n, int dims, const float *queries, int Q, int limit,
+                                  int mode, int nthreads, int *out_counts, double *out_scores, int64_t *out_index)
+{
+    int t, q, i;
+    if (nthreads < 1) nthreads = 1;
+    if (limit < 0) limit = 0;
+    if ((int64_t)nthreads > n && n > 0) nthreads = (int)n;
+    gf_scan_job *jobs = (gf_scan_job *)calloc((size_t)nthreads, sizeof(gf_scan_job));
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    for (t = 0; t < nthreads; ++t) {
+        jobs[t].rows = rows;
+        jobs[t].lo = n * t / nthreads;
+        jobs[t].hi = n * (t + 1) / nthreads;
+        jobs[t].dims = dims;
+        jobs[t].Q = Q;
+        jobs[t].limit = limit;
+        jobs[t].mode = mode;
+        jobs[t].queries = queries;
+        jobs[t].best = (gf_cand *)calloc((size_t)Q * (size_t)(limit ? limit : 1), sizeof(gf_cand));
+        jobs[t].cnt = (int *)calloc((size_t)Q, sizeof(int));
+        if (t > 0) pthread_create(&th[t], NULL, gf_scan_worker, &jobs[t]);
+    }
+    gf_scan_worker(&jobs[0]);
+    for (t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    for (q = 0; q < Q; ++q) {
+        gf_cand *fin = jobs[0].best + (size_t)q * limit;
+        int *fc = jobs[0].cnt + q;
+        for (t = 1; t < nthreads; ++t)
+            for (i = 0; i < jobs[t].cnt[q]; ++i) gf_insert(fin, fc, limit, &jobs[t].best[(size_t)q * limit + i]);
+        out_counts[q] = *fc;
+        for (i = 0; i < *fc; ++i) {
+            out_scores[(size_t)q * limit + i] = fin[i].score;
+            out_index[(size_t)q * limit + i] = fin[i].slot;
+        }
+    }
+    for (t = 0; t < nthreads; ++t) {
+        free(jobs[t].best);
+        free(jobs[t].cnt);
+    }
+    free(jobs);
+    free(th);
+    return 0;
+}
+
+/* ------------------------------------------------------- synthetic data generator */
+
+/*
+ * Counter-based generator shared with the CUDA fill kernel (bit-identical):
+ * u = splitmix64(seed, row*dims + col) -> U(-1,1) float32 as in search_test.go:65
+ * (`r.Float32()*2-1`), then per-row normalisation.  The normalisation here is
+ * NOT util.go's sequential one: sum of squares uses the canonical dot (x.x), the
+ * scale is 1/sqrtf via correctly rounded sqrtf and division, so the device can
+ * reproduce it exactly.
+ */
+static inline uint64_t gf_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+static inline float gf_uniform_pm1(uint64_t seed, uint64_t counter)
+{
+    uint64_t h = gf_splitmix64(seed ^ gf_splitmix64(counter));
+    uint32_t m = (uint32_t)(h >> 40); /* 24 random bits */
+    return (float)m * (1.0f / 8388608.0f) - 1.0f; /* exact in float32: [-1, 1) */
+}
+
+GF_EXPORT void gf_oracle_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, int dims, int normalize, float *out)
+{
+    int64_t r;
+    int c;
+    for (r = 0; r < nrows; ++r) {
+        float *x = out + (size_t)r * dims;
+        for (c = 0; c < dims; ++c) x[c] = gf_uniform_pm1(seed, (uint64_t)(row0 + r) * (uint64_t)dims + (uint64_t)c);
+        if (normalize) {
+            float ss = gf_dot_canonical(x, x, dims);
+            float nrm = sqrtf(ss);
+            if (nrm == 0.0f) {
+                for (c = 0; c < dims; ++c) x[c] = 0.0f;
+            } else {
+                for (c = 0; c < dims; ++c) x[c] = x[c] / nrm;
+            }
+        }
+    }
+}
