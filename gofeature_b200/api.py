@@ -26,7 +26,7 @@ class GoFeatureError(Exception):
         self.message = L.gf_strerror(status).decode()
         detail = L.gf_last_error_detail().decode(errors="replace")
         super().__init__("%s (%d): %s%s" % (self.name or "gf_status", status, self.message,
-                                            (" [" + detail + "]") if detail and status >= 100 else ""))
+                                            (" [" + detail + "]") if detail else ""))
 
 
 _SENTINELS = ["ErrBufferWriteOutofRange", "ErrBufferCopyOutofRange", "ErrBufferSliceOutofRange",

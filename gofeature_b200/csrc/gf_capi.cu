@@ -68,13 +68,13 @@ const Msg *find_msg(int status)
 // free slot, block.go:159,239)
 int unpack_ids(int64_t n, const char *ids, const uint64_t *off, std::vector<std::string> &out)
 {
-    if (n < 0 || (n > 0 && (!ids || !off))) return GF_ERR_INVALID_ARGUMENT;
+    if (n < 0 || (n > 0 && !off)) return GF_ERR_INVALID_ARGUMENT;
     out.clear();
     out.reserve((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
+    for (int64_t i = 0; i < n; ++i)
         if (off[i + 1] <= off[i]) return GF_ERR_INVALID_FEATURES;
-        out.emplace_back(ids + off[i], (size_t)(off[i + 1] - off[i]));
-    }
+    if (n > 0 && !ids) return GF_ERR_INVALID_ARGUMENT;
+    for (int64_t i = 0; i < n; ++i) out.emplace_back(ids + off[i], (size_t)(off[i + 1] - off[i]));
     return GF_OK;
 }
 
@@ -270,7 +270,7 @@ int gf_buffer_create(gf_context *ctx, uint64_t size, gf_buffer **out_buf)
             cudaFree(p);
             return cuda_fail(e, "cudaMemset", GF_ERR_CLEAR_CUDA_BUFFER);
         }
-        auto root = std::make_shared<DeviceAlloc>(DeviceAlloc{ctx, p, size, true});
+        auto root = std::make_shared<DeviceAlloc>(ctx, p, size, true);
         gf_buffer *b = new gf_buffer();
         b->ctx = ctx;
         b->root = root;
@@ -285,7 +285,7 @@ int gf_buffer_wrap(gf_context *ctx, void *device_ptr, uint64_t size, gf_buffer *
 {
     if (!ctx || !out_buf || (!device_ptr && size)) return GF_ERR_INVALID_ARGUMENT;
     return guarded([&]() -> int {
-        auto root = std::make_shared<DeviceAlloc>(DeviceAlloc{ctx, device_ptr, size, false});
+        auto root = std::make_shared<DeviceAlloc>(ctx, device_ptr, size, false);
         gf_buffer *b = new gf_buffer();
         b->ctx = ctx;
         b->root = root;
@@ -381,7 +381,7 @@ int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache
             cudaFree(p);
             return cuda_fail(e, "cudaMemset", GF_ERR_CLEAR_CUDA_BUFFER);
         }
-        c->slab = std::make_shared<DeviceAlloc>(DeviceAlloc{ctx, p, total, true});
+        c->slab = std::make_shared<DeviceAlloc>(ctx, p, total, true);
         for (int i = 0; i < block_num; ++i) {  // cache.go:33-41
             std::unique_ptr<Block> b(new gf_block());
             b->cache = c.get();

@@ -115,6 +115,9 @@ struct DeviceAlloc {
     void *ptr;
     uint64_t size;
     bool owned;
+    DeviceAlloc(Context *c, void *p, uint64_t s, bool o) : ctx(c), ptr(p), size(s), owned(o) {}
+    DeviceAlloc(const DeviceAlloc &) = delete;
+    DeviceAlloc &operator=(const DeviceAlloc &) = delete;
     ~DeviceAlloc();
 };
 

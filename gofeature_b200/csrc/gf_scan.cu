@@ -222,10 +222,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     }
 
     named_bar_sync(1, kConsumerThreads);
-    if (warp < a.q && warp < QT) {
+    for (int qi = warp; qi < a.q && qi < QT; qi += kConsumerWarps) {
         unsigned long long *out =
-            a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)warp) * (size_t)K;
-        list_flush(&ctl[warp], lists + (size_t)warp * cap, cap, K, out, lane);
+            a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
+        list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
     }
 }
 
@@ -292,10 +292,10 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
         }
     }
     __syncthreads();
-    if (warp < a.q && warp < QT) {
+    for (int qi = warp; qi < a.q && qi < QT; qi += kConsumerWarps) {
         unsigned long long *out =
-            a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)warp) * (size_t)K;
-        list_flush(&ctl[warp], lists + (size_t)warp * cap, cap, K, out, lane);
+            a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
+        list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
     }
 }
 
