@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- search QPS of the brute-force cosine top-K hot path on B200.
+
+Workload (BASELINE.json configs[1]): 1 000 000 x 512-d L2-normalised float32 features per GPU
+(2.048 GB, 62 blocks of 32 MiB = demo geometry, demo/main.go:19-23), top-10, 10 concurrent
+single-query searchers.  One "step" serves one query from each of the 10 searchers.
+
+  value     queries/s with the 10 queries already resident in HBM (gf_set_search_device: fused
+            scan kernel passes + merge kernel; at N > 1 also the NCCL all-gather of 10 keys per
+            query per rank and the cross-rank merge kernel), CUDA-event timed, max over ranks.
+            Weak scaling: every rank holds its own 1 M-row shard of an N-million-row set, and a
+            query is counted once per 1 M-row shard it scans (N per query), so value is the
+            1 M-row-equivalent QPS of the whole job; `qps_user` is the plain end-user QPS.
+  e2e       the same through the public host-buffer call (gf_set_search at N = 1, the collective
+            ShardedSet.search_keys at N > 1): H2D of the queries and D2H of the winners inside
+            the timed region, wall clock bracketed by device synchronisation.
+  roofline  the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference
+            the oracle's plain multi-threaded CPU scan ("port": the reference has no CPU build and
+            there is no Go toolchain) on a bounded row sample, scaled to 1 M rows.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = 512
+BLOCK_SIZE = 1024 * 1024 * 32      # demo/main.go:19
+SEED = 20260101
+QUERY_SEED = 20260102
+UNIT = "queries/s"
+METRIC = "search_qps_1Mx512_top10_parallel10"
+
+
+def make_queries(n, dims, seed):
+    """U(-1,1) rows (search_test.go:65) normalised like util.go:125-139, float32."""
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-1.0, 1.0, (n, dims)).astype(np.float32)
+    q /= np.sqrt((q.astype(np.float64) ** 2).sum(axis=1, keepdims=True)).astype(np.float32)
+    return np.ascontiguousarray(q)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or \
+               [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_from_profile():
+    """dram bytes per scan launch from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
+# --------------------------------------------------------------------------- CPU arms
+def cpu_scan_qps(sample_rows, nq, limit, min_seconds, rows_full):
+    """The oracle's multi-threaded plain scan on `sample_rows` rows; QPS scaled to rows_full rows."""
+    from oracle import lib as ol
+    cores = os.cpu_count() or 1
+    X = ol.synth_rows(SEED, 0, sample_rows, DIMS)
+    Q = make_queries(nq, DIMS, QUERY_SEED)
+    ol.scan_topk(X[:1000], Q, limit, ol.MODE_CANONICAL, cores)  # warm
+    t0 = time.perf_counter()
+    reps, times = 0, []
+    while True:
+        a = time.perf_counter()
+        ol.scan_topk(X, Q, limit, ol.MODE_CANONICAL, cores)
+        times.append(time.perf_counter() - a)
+        reps += 1
+        if time.perf_counter() - t0 >= min_seconds and reps >= 2:
+            break
+    per_pass = float(np.median(times))
+    qps_sample = nq / per_pass
+    return {"value": qps_sample * sample_rows / rows_full, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d rows x %d-d, %d queries top-%d per pass, %d passes, median %.1f ms/pass, "
+                      "oracle canonical-order AVX2 scan, pthreads; QPS scaled by rows ratio"
+                      % (sample_rows, rows_full, DIMS, nq, limit, reps, per_pass * 1e3)}, per_pass
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  goFeature has no non-cublas build and this image
+    has no Go toolchain, so this is the oracle port (plain brute-force scan, all host threads)."""
+    if rank != 0:
+        return
+    from oracle import lib as ol
+    cores = os.cpu_count() or 1
+    rows_full = args.rows_per_gpu
+    sample = min(args.cpu_sample_rows, rows_full)
+    X = ol.synth_rows(SEED, 0, sample, DIMS)
+    Q = make_queries(args.queries, DIMS, QUERY_SEED)
+    for _ in range(max(args.warmup, 1)):
+        ol.scan_topk(X, Q, args.limit, ol.MODE_CANONICAL, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ol.scan_topk(X, Q, args.limit, ol.MODE_CANONICAL, cores)
+    dt = time.perf_counter() - t0
+    ms_step_sample = dt / args.steps * 1e3
+    ms_step = ms_step_sample * rows_full / sample
+    # same unit as the GPU arm (1 M-row shard scans per second): the host cores are one pool, so it does not grow with N
+    value = args.queries / (ms_step / 1e3)
+    sample_txt = ("each step scans %d of %d rows (%d queries top-%d, all %d host threads) and is scaled by the "
+                  "rows ratio" % (sample, rows_full, args.queries, args.limit, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bench_config(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(args, world):
+    return {"workload": "BASELINE configs[1]: %d x %d-d normalised float32 rows per GPU (%d blocks of 32 MiB), "
+                        "top-%d, %d concurrent single-query searchers per step"
+                        % (args.rows_per_gpu, DIMS, (args.rows_per_gpu + 16383) // 16384, args.limit, args.queries),
+            "rows_per_gpu": args.rows_per_gpu, "rows_total": args.rows_per_gpu * world, "dims": DIMS,
+            "limit": args.limit, "queries_per_step": args.queries, "sharding": "row-sharded x%d" % world,
+            "l2": "inputs exceed L2 (2.05 GB per GPU streamed per pass vs 126 MB L2)"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from gofeature_b200 import _capi, api
+    from gofeature_b200.sharded import ShardedSet
+
+    _capi.lib()  # raises if the CUDA library is missing: no fallback
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    Q, K, rows_total = args.queries, args.limit, args.rows_per_gpu * world
+    ctx = api.NewContext(local_rank)
+    cap = BLOCK_SIZE // (DIMS * 4)
+    gblocks = (rows_total + cap - 1) // cap
+    cache = api.NewCache(ctx, (gblocks + world - 1) // world + 1, BLOCK_SIZE)
+    sset = ShardedSet(ctx, cache, "bench", DIMS, max(Q, 16), rank, world)
+    sset.AddSynthetic(rows_total, SEED)
+    rows_local = sset.local.ScannedRows()
+
+    npool = 32
+    pool = make_queries(npool * Q, DIMS, QUERY_SEED).reshape(npool, Q, DIMS)
+    dpool = torch.from_numpy(pool).cuda()
+    hpool = torch.from_numpy(pool).pin_memory()
+
+    def step_device(i):
+        return sset.search_device(K, Q, dpool[i % npool])
+
+    lean = api.lib()
+    import ctypes
+    handle = ctypes.c_void_p()
+
+    def step_e2e(i):
+        if world == 1:
+            hq = hpool[i % npool]
+            rc = lean.gf_set_search(sset.local._h, -2.0, K, Q, hq.data_ptr(), Q * DIMS * 4, ctypes.byref(handle))
+            if rc != 0:
+                raise api.GoFeatureError(rc)
+            n = lean.gf_result_total(handle)
+            lean.gf_result_free(handle)
+            return n
+        return sset.search_keys(K, pool[i % npool])
+
+    # ---- warm-up (>= 3), then the device-resident timed region
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step_device(i)
+        step_e2e(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if rank == 0 else 0.0)
+    ctx.ResetStats()
+    ctx.SetProfiling(True)
+    barrier()
+    t_mark0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_device(i)
+    ev1.record()
+    barrier()
+    t_mark1 = time.time()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    stats = ctx.Stats()
+    ctx.SetProfiling(False)
+    launches = stats["scan_launches"] + stats["merge_launches"] + stats["other_launches"] + stats["gemm_launches"]
+    scan_ms = stats["scan_kernel_ns"] / 1e6 / max(stats["scan_kernel_timed"], 1)
+    scans_per_step = stats["scan_launches"] / args.steps
+
+    # ---- e2e timed region (host buffers, H2D + D2H inside)
+    barrier()
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        a = time.perf_counter()
+        step_e2e(i)
+        lat.append(time.perf_counter() - a)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    # ---- single-query latency through the host call (north_star: sub-0.5 ms p50)
+    lat1 = []
+    if world == 1:
+        for i in range(max(30, min(args.steps, 200))):
+            hq = hpool[i % npool][:1]
+            a = time.perf_counter()
+            lean.gf_set_search(sset.local._h, -2.0, K, 1, hq.data_ptr(), DIMS * 4, ctypes.byref(handle))
+            lat1.append(time.perf_counter() - a)
+            lean.gf_result_free(handle)
+        ctx.ResetStats()
+        ctx.SetProfiling(True)
+        for i in range(20):
+            sset.local.SearchDevice(K, 1, dpool[i % npool].data_ptr(), sset._tensors(Q, K)["local"].data_ptr(), 0,
+                                    torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        s1 = ctx.Stats()
+        ctx.SetProfiling(False)
+        q1_ms = s1["scan_kernel_ns"] / 1e6 / max(s1["scan_kernel_timed"], 1)
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    avg_q = Q / scans_per_step if scans_per_step else Q
+    alg_bytes = rows_local * DIMS * 4 + avg_q * DIMS * 4 + avg_q * K * 8
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    qps_user = Q * args.steps / (dev_ms * 1e-3)
+    e2e_user = Q * args.steps / (e2e_ms * 1e-3)
+    lat_ms = sorted(x * 1e3 for x in lat)
+    line = {
+        "metric": METRIC, "value": qps_user * world, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(args, world),
+        "qps_user": qps_user, "rows_local_rank0": rows_local,
+        "e2e": {"value": e2e_user * world, "unit": UNIT, "h2d_bytes_per_step": Q * DIMS * 4,
+                "d2h_bytes_per_step": Q * K * 8, "qps_user": e2e_user, "ms_per_step": e2e_ms / args.steps,
+                "p50_ms": lat_ms[len(lat_ms) // 2], "p99_ms": lat_ms[min(len(lat_ms) - 1, int(len(lat_ms) * 0.99))],
+                "call": "gf_set_search(q=%d)" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic_from_profile(),
+                     "kernel": "scan_tma_kernel<512,QT>", "launches_per_step": scans_per_step,
+                     "avg_launch_ms": scan_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "frac_of_nominal_8000": achieved / 8000.0},
+        "clocks": sampler.summary(t_mark0, t_mark1) if sampler else None,
+    }
+    if world == 1:
+        l1 = sorted(x * 1e3 for x in lat1)
+        b1 = rows_local * DIMS * 4 + DIMS * 4 + K * 8
+        line["single_query"] = {"p50_ms": l1[len(l1) // 2], "p99_ms": l1[min(len(l1) - 1, int(len(l1) * 0.99))],
+                                "qps": 1e3 / (sum(l1) / len(l1)), "scan_kernel_ms": q1_ms,
+                                "roofline_frac": (b1 / (q1_ms * 1e-3) / 1e9 / peak) if q1_ms > 0 else None,
+                                "achieved_gbs": (b1 / (q1_ms * 1e-3) / 1e9) if q1_ms > 0 else None}
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_scan_qps(min(args.cpu_sample_rows, args.rows_per_gpu), Q, K, args.cpu_seconds,
+                                 args.rows_per_gpu)
+            line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    cache.Close()
+    ctx.Close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--queries", type=int, default=10)
+    ap.add_argument("--limit", type=int, default=10)
+    ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

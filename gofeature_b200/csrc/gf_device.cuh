@@ -119,6 +119,33 @@ __device__ __forceinline__ float canonical_reduce(float p0, float p1, float p2, 
     return __fadd_rn(t, 0.0f);
 }
 
+// Same sum for V independent values at once (V a power of two <= 32): at each of the first
+// log2(V) butterfly levels a lane keeps half of its values and trades the other half, so the
+// pairs added are exactly those of canonical_reduce (T[l] + T[l ^ off]) but V values cost
+// V-1 + (5 - log2 V) shuffles instead of 5 V.  On return lane l holds the finished sum of value
+// index  l >> (5 - log2 V)  (input t[] holds the per-thread sums T of every value).
+template <int V>
+__device__ __forceinline__ float canonical_reduce_many(float (&t)[V], int lane)
+{
+    static_assert(V >= 1 && V <= 32 && (V & (V - 1)) == 0, "V must be a power of two");
+    int off = 16;
+#pragma unroll
+    for (int n = V; n > 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? t[i] : t[i + n / 2];
+            const float keep = up ? t[i + n / 2] : t[i];
+            t[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, off));
+        }
+        off >>= 1;
+    }
+    float s = t[0];
+#pragma unroll
+    for (; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, off));
+    return __fadd_rn(s, 0.0f);
+}
+
 // ------------------------------------------------------------------ per-CTA candidate lists
 // One list per query lives in shared memory: an unsorted append buffer of `cap` keys
 // (a power of two, >= 2*K) plus the gate tau = K-th best key seen at the last compaction
@@ -128,7 +155,18 @@ struct ListCtl {
     unsigned long long tau;  // gate; keys <= tau are rejected without taking the lock
     int cnt;                 // keys in the buffer
     int lock;                // 0 free, 1 held
+    float tauf;              // score of tau (-inf while tau == 0): the one-compare pre-gate
+    int pad;
 };
+
+__device__ __forceinline__ void list_init(ListCtl *ctl)
+{
+    ctl->tau = 0ull;
+    ctl->cnt = 0;
+    ctl->lock = 0;
+    ctl->tauf = __int_as_float(0xff800000);  // -inf
+    ctl->pad = 0;
+}
 
 // bitonic sort (descending) of n (power of two) keys in shared memory by ONE warp
 __device__ __forceinline__ void warp_sort_desc(unsigned long long *buf, int n, int lane)
@@ -170,7 +208,11 @@ __device__ __forceinline__ void list_insert(ListCtl *ctl, unsigned long long *bu
         if (n == cap) {
             warp_sort_desc(buf, cap, lane);
             n = K;
-            if (lane == 0) *(volatile unsigned long long *)&ctl->tau = buf[K - 1];
+            if (lane == 0) {
+                unsigned long long kth = buf[K - 1];
+                *(volatile unsigned long long *)&ctl->tau = kth;
+                *(volatile float *)&ctl->tauf = key_score(kth);
+            }
         }
         if (lane == 0) *(volatile int *)&ctl->cnt = n;
     }

@@ -1004,7 +1004,7 @@ int Set::search_device(int limit, int q, const float *d_queries, unsigned long l
         ws = dev_ws;
     }
     if (!ws) return GF_ERR_CUDA;
-    cudaStream_t st = stream ? stream : ws->stream;
+    cudaStream_t st = stream;  // NULL is the CUDA legacy default stream, as everywhere in CUDA
     if (scanned_rows == 0) {
         GF_CUDA(cudaMemsetAsync(d_out, 0, (size_t)q * limit * 8, st), GF_ERR_CUDA);
         return GF_OK;

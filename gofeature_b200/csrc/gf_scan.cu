@@ -111,11 +111,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         }
         mbar_fence_init();
     }
-    if (threadIdx.x < QT) {
-        ctl[threadIdx.x].tau = 0ull;
-        ctl[threadIdx.x].cnt = 0;
-        ctl[threadIdx.x].lock = 0;
-    }
+    if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
     __syncthreads();
 
     uint32_t first, end, stride, group;
@@ -169,10 +165,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
             qreg[qi][j] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    unsigned long long upper[QT];
-#pragma unroll
-    for (int qi = 0; qi < QT; ++qi)
-        upper[qi] = (a.upper != nullptr && qi < a.q) ? a.upper[(size_t)group * a.q + qi] : ~0ull;
+    // V = RB*QT scores are reduced together; afterwards this lane holds score index vi = b*QT + qi
+    constexpr int V = RB * QT;
+    constexpr int LOG2V = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : 4;
+    constexpr int GROUP = 32 >> LOG2V;  // lanes that end up with the same score
+    const int vi = lane >> (5 - LOG2V);
+    const int my_b = vi / QT, my_q = vi % QT;
+    const bool my_live = my_q < a.q;
 
     const int cap = a.list_cap, K = a.K;
     int s = 0;
@@ -181,6 +180,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         mbar_wait(&full[s], ph);
         const uint32_t vrows = meta[s].rows;
         const uint32_t slot0 = meta[s].slot0;
+        // one-compare pre-gate, refreshed per tile; a stale (lower) value only lets extra keys through
+        const float tau_l = *(volatile float *)&ctl[my_q].tauf;
         const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * (kScanTileBytes / 4));
 #pragma unroll
         for (int rb = 0; rb < RPW; rb += RB) {
@@ -190,27 +191,35 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
             for (int b = 0; b < RB; ++b)
 #pragma unroll
                 for (int j = 0; j < CH; ++j) x[b][j] = tile[(size_t)(r0 + b) * (D / 4) + j * 32 + lane];
+            float tsum[V];
 #pragma unroll
-            for (int qi = 0; qi < QT; ++qi) {
-                float sc[RB];
+            for (int b = 0; b < RB; ++b) {
 #pragma unroll
-                for (int b = 0; b < RB; ++b) {
-                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                for (int qi = 0; qi < QT; ++qi) {
+                    // P[4l..4l+3] as two packed pairs: fma.rn.f32x2 (FFMA2) is two independent IEEE fmas
+                    float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
-                        p0 = __fmaf_rn(x[b][j].x, qreg[qi][j].x, p0);
-                        p1 = __fmaf_rn(x[b][j].y, qreg[qi][j].y, p1);
-                        p2 = __fmaf_rn(x[b][j].z, qreg[qi][j].z, p2);
-                        p3 = __fmaf_rn(x[b][j].w, qreg[qi][j].w, p3);
+                        p01 = __ffma2_rn(make_float2(x[b][j].x, x[b][j].y),
+                                         make_float2(qreg[qi][j].x, qreg[qi][j].y), p01);
+                        p23 = __ffma2_rn(make_float2(x[b][j].z, x[b][j].w),
+                                         make_float2(qreg[qi][j].z, qreg[qi][j].w), p23);
                     }
-                    sc[b] = canonical_reduce(p0, p1, p2, p3);
+                    tsum[b * QT + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
                 }
-                if (qi < a.q) {
-#pragma unroll
-                    for (int b = 0; b < RB; ++b)
-                        if ((uint32_t)(r0 + b) < vrows)
-                            offer(&ctl[qi], lists + (size_t)qi * cap, cap, K, sc[b], slot0 + r0 + b, upper[qi], lane);
-                }
+            }
+            const float sc = canonical_reduce_many<V>(tsum, lane);
+            const bool pass = my_live && ((uint32_t)(r0 + my_b) < vrows) && !(sc < tau_l);
+            unsigned bal = __ballot_sync(0xffffffffu, pass);
+            while (bal) {  // rare: a score reached this CTA's current K-th best
+                const int leader = __ffs(bal) - 1;
+                const int lvi = leader >> (5 - LOG2V);
+                const float ls = __shfl_sync(0xffffffffu, sc, leader);
+                const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lvi * GROUP));
+                bal &= ~gmask;
+                const int lb = lvi / QT, lq = lvi % QT;
+                const unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + lq] : ~0ull;
+                offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
             }
         }
         __syncwarp();
@@ -248,11 +257,7 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
         int qi = i / dims, e = i - qi * dims;
         qs[i] = (qi < a.q) ? a.queries[(long long)qi * a.q_stride + (long long)e * a.l_stride] : 0.0f;
     }
-    if (threadIdx.x < QT) {
-        ctl[threadIdx.x].tau = 0ull;
-        ctl[threadIdx.x].cnt = 0;
-        ctl[threadIdx.x].lock = 0;
-    }
+    if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
     __syncthreads();
 
     uint32_t first, end, stride, group;

@@ -227,8 +227,9 @@ GF_API int gf_result_free(gf_result *r);
 
 /* ------------------------------------------------- device-resident entry points
  * Used by bench.py (`value`: inputs already in HBM), by the multi-GPU shard merge and by
- * callers that keep queries on the device.  `stream` is a cudaStream_t (NULL = the set's
- * own search stream).  Nothing here synchronises with the host. */
+ * callers that keep queries on the device.  `stream` is a cudaStream_t (NULL = the CUDA legacy
+ * default stream, which is also torch's default).  Nothing here synchronises with the host;
+ * calls on one set must be stream-ordered (they share one scratch arena). */
 
 /* A candidate is one u64 key: (orderable image of the float32 score) << 32 | (0xFFFFFFFF - slot),
  * larger key = better hit (score descending, slot ascending); 0 = no candidate. */
