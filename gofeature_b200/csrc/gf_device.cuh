@@ -189,32 +189,85 @@ __device__ __forceinline__ void warp_sort_desc(unsigned long long *buf, int n, i
     }
 }
 
-// Whole warp calls this with a warp-uniform key.  K <= cap/2.
+// K <= kSortedMaxK: the list is kept SORTED (descending, zero padded) in cap = 32*E slots, lane l
+// owning slots [l*E, l*E+E), so tau is exact after every insert and the number of inserts per
+// list is the minimum a streaming top-K can have, K*(1 + ln(rows/K)).  Larger K: unsorted append
+// buffer of cap >= 2K keys, sorted and cut back to K whenever it fills (amortised O(log^2) per key).
+constexpr int kSortedMaxK = 128;
+
+__host__ __device__ __forceinline__ bool list_is_sorted_mode(int K) { return K <= kSortedMaxK; }
+
+__device__ __forceinline__ float tau_score(unsigned long long tau)
+{
+    return tau == 0ull ? __int_as_float(0xff800000) : key_score(tau);
+}
+
+// lock held by this warp, key > tau already checked
+template <int E>
+__device__ __forceinline__ void sorted_insert(ListCtl *ctl, unsigned long long *buf, int K, unsigned long long key,
+                                              int lane)
+{
+    unsigned long long my[E];
+    unsigned p = 0;  // slots holding a key greater than `key`: the insert position (the list is a sorted prefix)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        my[e] = *(volatile unsigned long long *)&buf[lane * E + e];
+        p += __popc(__ballot_sync(0xffffffffu, my[e] > key));
+    }
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, my[E - 1], 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const unsigned i = (unsigned)(lane * E + e);
+        const unsigned long long prev = (e > 0) ? my[e > 0 ? e - 1 : 0] : up;
+        const unsigned long long nv = (i < p) ? my[e] : ((i == p) ? key : prev);
+        if (i >= p) *(volatile unsigned long long *)&buf[i] = nv;
+        if (i == (unsigned)(K - 1)) {
+            *(volatile unsigned long long *)&ctl->tau = nv;
+            *(volatile float *)&ctl->tauf = tau_score(nv);
+        }
+    }
+}
+
+// Whole warp calls this with a warp-uniform key.
 __device__ __forceinline__ void list_insert(ListCtl *ctl, unsigned long long *buf, int cap, int K,
                                             unsigned long long key, int lane)
 {
     if (lane == 0) {
+        // back off while another warp holds the list: spinning ATOMS on one bank would starve the
+        // holder's own shared-memory traffic
+        unsigned ns = 32;
         while (atomicCAS(&ctl->lock, 0, 1) != 0) {
+            __nanosleep(ns);
+            if (ns < 512) ns <<= 1;
         }
     }
     __syncwarp();
     __threadfence_block();
     unsigned long long tau = *(volatile unsigned long long *)&ctl->tau;
     if (key > tau) {
-        int n = *(volatile int *)&ctl->cnt;
-        if (lane == 0) buf[n] = key;
-        n += 1;
-        __syncwarp();
-        if (n == cap) {
-            warp_sort_desc(buf, cap, lane);
-            n = K;
-            if (lane == 0) {
-                unsigned long long kth = buf[K - 1];
-                *(volatile unsigned long long *)&ctl->tau = kth;
-                *(volatile float *)&ctl->tauf = key_score(kth);
+        if (list_is_sorted_mode(K)) {
+            switch (cap >> 5) {
+                case 1: sorted_insert<1>(ctl, buf, K, key, lane); break;
+                case 2: sorted_insert<2>(ctl, buf, K, key, lane); break;
+                case 3: sorted_insert<3>(ctl, buf, K, key, lane); break;
+                default: sorted_insert<4>(ctl, buf, K, key, lane); break;
             }
+        } else {
+            int n = *(volatile int *)&ctl->cnt;
+            if (lane == 0) buf[n] = key;
+            n += 1;
+            __syncwarp();
+            if (n == cap) {
+                warp_sort_desc(buf, cap, lane);
+                n = K;
+                if (lane == 0) {
+                    unsigned long long kth = buf[K - 1];
+                    *(volatile unsigned long long *)&ctl->tau = kth;
+                    *(volatile float *)&ctl->tauf = tau_score(kth);
+                }
+            }
+            if (lane == 0) *(volatile int *)&ctl->cnt = n;
         }
-        if (lane == 0) *(volatile int *)&ctl->cnt = n;
     }
     __syncwarp();
     if (lane == 0) {
@@ -224,14 +277,16 @@ __device__ __forceinline__ void list_insert(ListCtl *ctl, unsigned long long *bu
     __syncwarp();
 }
 
-// Sort the list and write its best K keys (zero padded) to out[0..K).  One warp, no contention.
+// Write the list's best K keys (descending, zero padded) to out[0..K).  One warp, no contention.
 __device__ __forceinline__ void list_flush(ListCtl *ctl, unsigned long long *buf, int cap, int K,
                                            unsigned long long *out, int lane)
 {
-    int n = ctl->cnt;
-    for (int i = n + lane; i < cap; i += 32) buf[i] = 0ull;
-    __syncwarp();
-    warp_sort_desc(buf, cap, lane);
+    if (!list_is_sorted_mode(K)) {
+        int n = ctl->cnt;
+        for (int i = n + lane; i < cap; i += 32) buf[i] = 0ull;
+        __syncwarp();
+        warp_sort_desc(buf, cap, lane);
+    }
     for (int i = lane; i < K; i += 32) out[i] = buf[i];
 }
 #endif  // __CUDACC__

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         mbar_fence_init();
     }
     if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
+    for (int i = threadIdx.x; i < QT * a.list_cap; i += blockDim.x) lists[i] = 0ull;
     __syncthreads();
 
     uint32_t first, end, stride, group;
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
         qs[i] = (qi < a.q) ? a.queries[(long long)qi * a.q_stride + (long long)e * a.l_stride] : 0.0f;
     }
     if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
+    for (int i = threadIdx.x; i < QT * a.list_cap; i += blockDim.x) lists[i] = 0ull;
     __syncthreads();
 
     uint32_t first, end, stride, group;
@@ -381,7 +383,7 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
     ScanPlan p{};
     p.dims = dims;
     p.qt = q <= 1 ? 1 : q <= 2 ? 2 : q <= 4 ? 4 : 8;
-    p.list_cap = next_pow2(2 * K < 64 ? 64 : 2 * K);
+    p.list_cap = list_is_sorted_mode(K) ? ((K + 31) / 32) * 32 : next_pow2(2 * K);
     size_t lists_bytes = (size_t)p.qt * p.list_cap * 8;
     int tr = scan_tile_rows(dims);
     p.tma = aligned16 && tr > 0 && p.qt * dims <= 4096;

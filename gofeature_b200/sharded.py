@@ -4,15 +4,21 @@ The reference is single-device (`devices[0]`, search_test.go:40); what it alread
 *blocks* -- independent per-block top-limit, then a merge (set.go:129-157) -- is done here
 across *ranks*: global block g lives on rank g % world as that rank's block g // world
 (SURVEY 8e), every rank scans only its own rows, and the only exchange is one all-gather of
-`limit` candidate keys per query per rank (12.5 M rows/GPU -> 80 bytes per query per rank at
-limit 10), followed by the same merge kernel that folds the per-CTA lists.
+`limit` candidate keys per query per rank (80 bytes per query per rank at limit 10), followed
+by the same merge kernel that folds the per-CTA lists.
 
 torch is plumbing here: device tensors for the keys, `torch.distributed` (NCCL over
-NVLink/NVSwitch on GPUs, gloo for the CPU tests of the host logic) for the gather.
+NVLink/NVSwitch on GPUs, gloo for the CPU tests of this host logic) for the gather.
+
+The collective steps are free functions on tensors of any device so that the host logic
+(striping, key merge, id exchange) is testable with gloo at world_size 2 without a GPU;
+`ShardedSet` binds them to the CUDA library.
 """
 import numpy as np
 
 from . import api
+
+ID_WIDTH = 64  # bytes of a feature id carried through the id exchange
 
 
 def owner_of(global_block, world):
@@ -34,10 +40,14 @@ def split_rows(n_existing, n_new, cap, world):
     return out
 
 
+def slot_owner(slot, cap, world):
+    """rank that owns a global slot (= global block * cap + row)."""
+    return (slot // cap) % world
+
+
 def merge_keys_host(gathered, limit):
-    """Reference merge of per-rank key lists on the host: gathered [world, q, limit] uint64
-    (descending, zero padded) -> [q, limit].  Same total order as the device merge kernel; used
-    by the gloo tests of the host logic and as a cross-check of gf_merge_keys_device."""
+    """Merge of per-rank key lists on the host: gathered [world, q, limit] uint64 (descending,
+    zero padded) -> [q, limit].  Same total order as the device merge kernel (gf_merge.cu)."""
     g = np.asarray(gathered, dtype=np.uint64)
     world, q, k = g.shape
     out = np.zeros((q, limit), dtype=np.uint64)
@@ -46,6 +56,82 @@ def merge_keys_host(gathered, limit):
         allk = allk[allk != 0][:limit]
         out[i, :len(allk)] = allk
     return out
+
+
+def gather_keys(local_keys, world, group=None, out=None):
+    """all-gather of the per-rank winners: local_keys [q, limit] int64 tensor (any device) ->
+    [world, q, limit].  The only data-path collective of a sharded search."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local_keys.unsqueeze(0)
+    q, limit = local_keys.shape
+    if out is None:
+        out = torch.empty((world, q, limit), dtype=local_keys.dtype, device=local_keys.device)
+    # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+    dist.all_gather_into_tensor(out.view(world * q, limit), local_keys.contiguous(), group=group)
+    return out
+
+
+def exchange_ids(keys, mine, rank, world, group=None, device=None):
+    """Every rank knows ids / tombstones only for the slots it owns.  `mine[i]` maps slot ->
+    id (str) for this rank's LIVE winners of query i.  One all-reduce(MAX) of a byte table makes
+    the table complete on every rank.  Returns table uint8 [q, limit, 2 + ID_WIDTH]:
+    [...,0] = 1 if the owner reported the slot live, [...,1] = id length, then the id bytes."""
+    import torch
+    import torch.distributed as dist
+    q, limit = keys.shape
+    table = np.zeros((q, limit, ID_WIDTH + 2), dtype=np.uint8)
+    for i in range(q):
+        for j in range(limit):
+            k = int(keys[i, j])
+            if k == 0:
+                break
+            slot = 0xFFFFFFFF - (k & 0xFFFFFFFF)
+            ident = mine[i].get(slot)
+            if ident is not None:
+                b = ident.encode() if isinstance(ident, str) else bytes(ident)
+                b = b[:ID_WIDTH]
+                table[i, j, 0], table[i, j, 1] = 1, len(b)
+                table[i, j, 2:2 + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    if world > 1:
+        tt = torch.from_numpy(table)
+        if device is not None:
+            tt = tt.to(device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=group)
+        table = tt.cpu().numpy()
+    return table
+
+
+def results_from_table(keys, table, threshold):
+    """[][]FeatureSearchResult from merged keys + the exchanged id table: tombstones (not reported
+    live by their owner) and scores below the threshold (set.go:145) are dropped."""
+    q, limit = keys.shape
+    thr = np.float32(threshold)
+    out = []
+    for i in range(q):
+        row = []
+        for j in range(limit):
+            k = int(keys[i, j])
+            if k == 0:
+                break
+            if not table[i, j, 0]:
+                continue
+            sc = _key_score(k)
+            if not (sc >= thr):
+                continue
+            n = int(table[i, j, 1])
+            row.append(api.FeatureSearchResult(sc, bytes(table[i, j, 2:2 + n]).decode(errors="replace"),
+                                               0xFFFFFFFF - (k & 0xFFFFFFFF)))
+        out.append(row)
+    return out
+
+
+def _key_score(k):
+    """score of a key without calling into the library (same mapping as gf_key_score)."""
+    im = (k >> 32) & 0xFFFFFFFF
+    u = (im & 0x7FFFFFFF) if (im & 0x80000000) else (~im & 0xFFFFFFFF)
+    return np.frombuffer(np.uint32(u).tobytes(), dtype=np.float32)[0]
 
 
 class ShardedSet:
@@ -82,13 +168,12 @@ class ShardedSet:
     def Delete(self, *ids):
         import torch
         import torch.distributed as dist
-        mine = self.local.Delete(*ids) or []
-        flags = torch.tensor([1 if i in set(mine) else 0 for i in ids], dtype=torch.int32)
+        mine = set(self.local.Delete(*ids) or [])
+        flags = torch.tensor([1 if i in mine else 0 for i in ids], dtype=torch.int32,
+                             device="cuda:%d" % self.ctx.device)
         if self.world > 1:
-            dev = flags.cuda() if dist.get_backend(self.group) == "nccl" else flags
-            dist.all_reduce(dev, op=dist.ReduceOp.MAX, group=self.group)
-            flags = dev.cpu()
-        return [i for i, f in zip(ids, flags.tolist()) if f] or None
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+        return [i for i, f in zip(ids, flags.cpu().tolist()) if f] or None
 
     # ---- search
     def _tensors(self, q, limit):
@@ -106,22 +191,20 @@ class ShardedSet:
             )
         return self._bufs[key]
 
-    def search_device(self, limit, q, dq, out=None):
+    def search_device(self, limit, q, dq):
         """Collective device-resident search: dq [q, dims] float32 on this rank's GPU (same on all
         ranks) -> merged keys [q, limit] int64 tensor, identical on every rank.  Enqueues on the
         current torch stream; no host synchronisation."""
         import torch
-        import torch.distributed as dist
         t = self._tensors(q, limit)
         stream = torch.cuda.current_stream().cuda_stream
         self.local.SearchDevice(limit, q, dq.data_ptr(), t["local"].data_ptr(), 0, stream)
         if self.world == 1:
             return t["local"]
-        dist.all_gather_into_tensor(t["gathered"], t["local"], group=self.group)
-        merged = out if out is not None else t["merged"]
-        api._check(api.lib().gf_merge_keys_device(self.ctx._h, self.world, q, limit, t["gathered"].data_ptr(),
-                                                  merged.data_ptr(), stream))
-        return merged
+        gathered = gather_keys(t["local"], self.world, self.group, out=t["gathered"])
+        api._check(api.lib().gf_merge_keys_device(self.ctx._h, self.world, q, limit, gathered.data_ptr(),
+                                                  t["merged"].data_ptr(), stream))
+        return t["merged"]
 
     def search_keys(self, limit, queries):
         """Host queries [q, dims] -> merged keys [q, limit] uint64 on the host (H2D, scan, gather,
@@ -141,46 +224,10 @@ class ShardedSet:
 
     def Search(self, threshold, limit, queries):
         """Collective Set.Search (set.go:118-159) over the sharded rows.  IDs are resolved by the
-        rank that owns each winning slot and exchanged as fixed-width bytes."""
-        import torch
-        import torch.distributed as dist
+        rank that owns each winning slot and exchanged as fixed-width bytes.  Tombstones that reach
+        the merged top-limit are dropped after selection, as block.go:236-243 does per block."""
         keys = self.search_keys(limit, queries)
-        mine = self.local.ResolveKeys(threshold, limit, keys)
-        if self.world == 1:
-            return mine
-        # every rank fills the ids (and tombstone flags) of the slots it owns
-        q = keys.shape[0]
-        width = 64
-        table = np.zeros((q, limit, width + 2), dtype=np.uint8)   # [..., 0]=owned+live, [..., 1]=len
-        for i in range(q):
-            own = {r.Slot: r for r in mine[i] if r.ID != ""}
-            for j in range(limit):
-                k = int(keys[i, j])
-                if k == 0:
-                    break
-                r = own.get(api.key_slot(k))
-                if r is not None:
-                    b = r.ID.encode() if isinstance(r.ID, str) else r.ID
-                    table[i, j, 0], table[i, j, 1] = 1, len(b)
-                    table[i, j, 2:2 + len(b)] = np.frombuffer(b[:width], dtype=np.uint8)
-        tt = torch.from_numpy(table).to("cuda:%d" % self.ctx.device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=self.group)
-        table = tt.cpu().numpy()
-        out = []
-        for i in range(q):
-            row = []
-            for j in range(limit):
-                k = int(keys[i, j])
-                if k == 0:
-                    break
-                if not table[i, j, 0]:
-                    continue                                   # tombstone on its owner rank
-                sc = api.key_score(k)
-                if not (sc >= np.float32(threshold)):
-                    continue
-                n = int(table[i, j, 1])
-                row.append(api.FeatureSearchResult(sc, bytes(table[i, j, 2:2 + n]).decode(errors="replace"),
-                                                   api.key_slot(k)))
-            out.append(row)
-        return out
-
+        local = self.local.ResolveKeys(float("-inf"), limit, keys)     # live winners this rank owns
+        mine = [{r.Slot: r.ID for r in row if r.ID != ""} for row in local]
+        table = exchange_ids(keys, mine, self.rank, self.world, self.group, "cuda:%d" % self.ctx.device)
+        return results_from_table(keys, table, threshold)
