@@ -23,7 +23,8 @@ P = ctypes.POINTER
 class gf_stats(ctypes.Structure):
     _fields_ = [(n, c_u64) for n in ("searches", "scan_launches", "gemm_launches", "merge_launches",
                                      "other_launches", "rows_scanned", "quirk_fallbacks", "coalesced_batches",
-                                     "h2d_bytes", "d2h_bytes", "scan_kernel_ns", "scan_kernel_timed")]
+                                     "h2d_bytes", "d2h_bytes", "scan_kernel_ns", "scan_kernel_timed",
+                                     "tensor_passes", "uncertified_queries")]
 
 
 # name -> (restype, argtypes); every symbol include/gofeature_b200.h declares

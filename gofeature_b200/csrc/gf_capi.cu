@@ -224,6 +224,8 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
     const Stats &s = ctx->stats;
     out->scan_kernel_ns = s.scan_kernel_ns;
     out->scan_kernel_timed = s.scan_kernel_timed;
+    out->tensor_passes = s.tensor_passes;
+    out->uncertified_queries = s.uncertified_queries;
     out->searches = s.searches;
     out->scan_launches = s.scan_launches;
     out->gemm_launches = s.gemm_launches;
@@ -245,6 +247,7 @@ int gf_context_reset_stats(gf_context *ctx)
     s.rows_scanned = s.quirk_fallbacks = s.coalesced_batches = s.h2d_bytes = s.d2h_bytes = 0;
     ctx->prof_collect();
     s.scan_kernel_ns = s.scan_kernel_timed = 0;
+    s.tensor_passes = s.uncertified_queries = 0;
     return GF_OK;
 }
 
@@ -403,6 +406,8 @@ int gf_cache_destroy(gf_cache *cache)
     for (auto &s : cache->owned_sets) {
         if (s->d_segs) cudaFree(s->d_segs);
         s->d_segs = nullptr;
+        if (s->d_small) cudaFree(s->d_small);
+        s->d_small = nullptr;
         if (s->dev_ws) cache->ctx->release_ws(s->dev_ws);
         s->dev_ws = nullptr;
     }

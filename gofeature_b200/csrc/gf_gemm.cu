@@ -1,0 +1,676 @@
+// gf_gemm.cu -- tcgen05 / TMEM contraction for large query batches (Q >= 9), sm_100a.
+//
+// score[row][q] = <feature row, query q> for 128 feature rows x NQ queries per tile:
+//   A operand = feature rows   (M = 128 rows, K-major: the row-major block exactly as it sits in
+//               HBM, block.go:99), TMA 2-D box 32 floats x 128 rows, SWIZZLE_128B
+//   B operand = queries        (N = NQ, K-major), TMA box 32 floats x NQ rows from the padded batch
+//   D         = fp32 accumulators in TMEM, [128 lanes = rows][NQ columns = queries], double buffered
+// Rows on M / queries on N makes the tensor time scale with the real batch (N/2 cycles per K = 8
+// step) instead of a batch padded to 128, so the kernel stays HBM-bound up to ~256 queries per pass.
+//
+// kind::tf32 reads the fp32 bits and keeps 10 mantissa bits: these scores only SELECT candidates.
+// Every candidate is re-scored in the canonical float32 order (rescore_kernel) and a certificate
+// proves that no row outside the candidate set can be in the top-K (gf_runtime.cu); the Q x N score
+// matrix never leaves the SM except in DUMP mode (small sets / diagnostics).
+//
+// Warp roles (192 threads): warp 0 TMA producer (one thread), warp 1 TMEM allocator + MMA issuer
+// (one thread), warps 2..5 epilogue (tcgen05.ld, one feature row per thread).
+#include <cuda.h>
+
+#include "gf_device.cuh"
+#include "gf_kernels.h"
+
+namespace gf {
+
+namespace {
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileRows = 128;
+constexpr int kBK = 32;  // floats per K block = one 128-byte swizzle row
+constexpr int kABytes = kTileRows * kBK * 4;
+
+struct GemmArgs {
+    const Segment *segs;
+    const uint32_t *gtile_start;  // nseg + 1, in 128-row tiles
+    int nseg;
+    int dims;
+    const float *slab_base;  // row 0 of tensor map A
+    int mode;
+    uint32_t tile_first, tile_stride, tile_count;
+    int q;
+    const float *thr;
+    unsigned long long *cand;
+    unsigned int *cnt;
+    unsigned int cap;
+    float *tilemax;
+    float *dump;
+    unsigned long long dump_ld;
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, one K = 8 step of kind::tf32
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups,
+// version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t smem_desc_sw128(const void *p)
+{
+    uint64_t d = (uint64_t)((smem_u32(p) >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// which segment holds 128-row tile t; `segi` only moves forward (tiles of a CTA ascend)
+__device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint32_t &segi, uint32_t &row0,
+                                            uint32_t &valid)
+{
+    while (segi + 1 < (uint32_t)a.nseg && t >= a.gtile_start[segi + 1]) ++segi;
+    row0 = (t - a.gtile_start[segi]) * kTileRows;
+    uint32_t rows = a.segs[segi].rows;
+    valid = rows - row0 < (uint32_t)kTileRows ? rows - row0 : (uint32_t)kTileRows;
+}
+
+template <int NQ>
+struct GemmCfg {
+    static constexpr int kBBytes = NQ * kBK * 4;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (NQ <= 64) ? 6 : (NQ <= 128 ? 5 : 4);
+    static constexpr int kTmemCols = (2 * NQ < 32) ? 32 : 2 * NQ;
+    static constexpr int kChunk = (NQ >= 32) ? 32 : 16;
+    static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 8;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
+{
+    using Cfg = GemmCfg<NQ>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *tail = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);
+    uint64_t *empty = full + Cfg::kStages;
+    uint64_t *tfull = empty + Cfg::kStages;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float *thr_s = reinterpret_cast<float *>(tail + 256);
+    unsigned int *tmax_s = reinterpret_cast<unsigned int *>(thr_s + NQ);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = a.dims / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+        thr_s[i] = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
+        tmax_s[i] = 0u;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, segi = 0;
+            for (uint32_t i = blockIdx.x; i < a.tile_count; i += gridDim.x) {
+                const uint32_t t = a.tile_first + i * a.tile_stride;
+                uint32_t row0, valid;
+                locate_tile(a, t, segi, row0, valid);
+                const int slab_row = (int)((a.segs[segi].base - a.slab_base) / a.dims) + (int)row0;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                    tma_load_2d(sa, &tmA, kb * kBK, slab_row, &full[s]);
+                    tma_load_2d(sa + kABytes, &tmB, kb * kBK, 0, &full[s]);
+                    if (++s == Cfg::kStages) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(kTileRows, NQ);
+            int s = 0;
+            uint32_t ph = 0, it = 0;
+            for (uint32_t i = blockIdx.x; i < a.tile_count; i += gridDim.x, ++it) {
+                const uint32_t acc = it & 1;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + acc * NQ;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
+                    const uint64_t adesc = smem_desc_sw128(sa);
+                    const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
+                        tc_mma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    tc_commit(&empty[s]);  // frees the stage when these MMAs have read it
+                    if (++s == Cfg::kStages) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                tc_commit(&tfull[acc]);  // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue: one feature row per thread =====================
+        const int quarter = warp & 3;  // TMEM lanes this warp may read
+        const uint32_t row = quarter * 32 + lane;
+        uint32_t it = 0, segi = 0;
+        for (uint32_t i = blockIdx.x; i < a.tile_count; i += gridDim.x, ++it) {
+            const uint32_t t = a.tile_first + i * a.tile_stride;
+            uint32_t row0, valid;
+            locate_tile(a, t, segi, row0, valid);
+            const bool live = row < valid;
+            const uint32_t slot = a.segs[segi].slot_base + row0 + row;
+            const uint32_t acc = it & 1;
+            mbar_wait(&tfull[acc], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < NQ; c0 += Cfg::kChunk) {
+                uint32_t r[Cfg::kChunk];
+                tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NQ + c0, r);
+                tmem_ld_wait();
+                if (a.mode == 0) {
+                    // COLLECT: fixed per-query threshold, atomic append of the rare survivor
+                    unsigned pass = 0;
+#pragma unroll
+                    for (int j = 0; j < Cfg::kChunk; ++j)
+                        pass |= (__uint_as_float(r[j]) > thr_s[c0 + j]) ? (1u << j) : 0u;
+                    if (!live) pass = 0;
+                    while (pass) {
+                        const int j = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        float sc = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < Cfg::kChunk; ++jj)
+                            if (jj == j) sc = __uint_as_float(r[jj]);
+                        const int qi = c0 + j;
+                        const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
+                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
+                    }
+                } else if (a.mode == 1) {
+                    // TILEMAX: per query the best score of this tile (threshold estimation sample)
+                    float v[Cfg::kChunk];
+#pragma unroll
+                    for (int j = 0; j < Cfg::kChunk; ++j)
+                        v[j] = live ? __uint_as_float(r[j]) : __int_as_float(0xff800000);
+                    // transposed max-reduce: lane j ends with the max of column c0 + j over 32 rows
+                    int off = 16;
+#pragma unroll
+                    for (int n = Cfg::kChunk; n > 1; n >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int k = 0; k < n / 2; ++k) {
+                            const float send = up ? v[k] : v[k + n / 2];
+                            const float keep = up ? v[k + n / 2] : v[k];
+                            v[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+                        }
+                        off >>= 1;
+                    }
+                    float m = v[0];
+                    for (; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                    const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
+                    if (Cfg::kChunk == 32 || (lane & 1) == 0) atomicMax(&tmax_s[col], score_image(m));
+                } else {
+                    // DUMP: every score, coalesced over rows (small sets and diagnostics)
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < Cfg::kChunk; ++j)
+                            if (c0 + j < a.q)
+                                a.dump[(size_t)(c0 + j) * a.dump_ld + (size_t)i * kTileRows + row] =
+                                    __uint_as_float(r[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (a.mode == 1) {
+                named_bar_sync(2, 128);
+                for (int c = threadIdx.x - 64; c < NQ; c += 128) {
+                    a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
+                    tmax_s[c] = 0u;
+                }
+                named_bar_sync(2, 128);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ helper kernels
+// queries [q][dims] (any stride) -> padded row-major batch [nq][dims] (rows >= q zeroed) + |q|^2
+__global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
+                                    int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2)
+{
+    const int qi = blockIdx.x;
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < dims; e += blockDim.x) {
+        float v = qi < q ? src[(long long)qi * q_stride + (long long)e * l_stride] : 0.f;
+        dst[(size_t)qi * dims + e] = v;
+        acc += v * v;
+    }
+    __shared__ float red[32];
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+        qnorm2[qi] = t * 1.0001f;  // upper bound is what the certificate needs
+    }
+}
+
+// max over rows of |row|^2 (upper-bounded): one warp per row, atomicMax on the float bits (>= 0)
+__global__ void rownorm_max_kernel(const Segment *__restrict__ segs, int nseg, int dims, unsigned int *out_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (int s = 0; s < nseg; ++s) {
+        const Segment sg = segs[s];
+        for (long long r = warp; r < sg.rows; r += nwarps) {
+            const float *x = sg.base + (size_t)r * dims;
+            float acc = 0.f;
+            for (int e = lane; e < dims; e += 32) {
+                float v = x[e];
+                acc += v * v;
+            }
+            for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (acc == acc) best = fmaxf(best, acc);
+        }
+    }
+    if (lane == 0 && best > 0.f) atomicMax(out_bits, __float_as_uint(best * 1.0001f));
+}
+
+// per query: threshold = m-th largest of `ntiles` tile maxima (descending), minus nothing; also
+// resets the candidate counters.  One warp per query; ntiles <= 1024.
+__global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, int nq, int q, int m,
+                                 float *__restrict__ thr, unsigned int *__restrict__ cnt)
+{
+    __shared__ unsigned int v[1024];
+    const int qi = blockIdx.x;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+        v[i] = i < ntiles ? score_image(tilemax[(size_t)i * nq + qi]) : 0u;
+    __syncthreads();
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned a = v[i], b = v[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) {
+                        v[i] = b;
+                        v[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        int idx = m - 1 < ntiles ? m - 1 : ntiles - 1;
+        thr[qi] = qi < q ? image_score(v[idx]) : __int_as_float(0x7f800000);
+        cnt[qi] = 0u;
+    }
+}
+
+// candidates (approx keys) -> for the best `kp` of each query: exact canonical score of the row.
+// d_sel [q][kp] approx keys (descending, zero padded) in; d_exact [q][kp] exact keys out.
+__global__ void __launch_bounds__(256)
+    rescore_kernel(const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_slot_base, int nseg, int dims,
+                   uint32_t cap_rows, const float *__restrict__ queries, int kp,
+                   const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int qi = blockIdx.y;
+    if (w >= kp) return;
+    const unsigned long long key = d_sel[(size_t)qi * kp + w];
+    if (key == 0ull) {
+        if (lane == 0) d_exact[(size_t)qi * kp + w] = 0ull;
+        return;
+    }
+    const uint32_t slot = key_slot(key);
+    // segment whose slot range holds this slot: slot_base values ascend with the segment index
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (seg_slot_base[mid] <= slot) lo = mid; else hi = mid - 1;
+    }
+    (void)cap_rows;
+    const float *x = segs[lo].base + (size_t)(slot - seg_slot_base[lo]) * dims;
+    const float *qv = queries + (size_t)qi * dims;
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < dims; j += 128) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int e = j + 4 * lane + c;
+            if (e < dims) p[c] = __fmaf_rn(x[e], qv[e], p[c]);
+        }
+    }
+    const float sc = canonical_reduce(p[0], p[1], p[2], p[3]);
+    if (lane == 0) d_exact[(size_t)qi * kp + w] = make_key(sc, slot);
+}
+
+// per query: sort the kp exact keys, emit the best K, and certify: the K-th exact score must beat
+// everything a non-candidate row could reach (bound = approx ceiling of the non-candidates + error).
+__global__ void __launch_bounds__(256)
+    finalize_kernel(const unsigned long long *__restrict__ d_exact, const unsigned long long *__restrict__ d_sel,
+                    const unsigned int *__restrict__ cnt, const float *__restrict__ thr, unsigned int cap, int kp,
+                    int K, long long rows_total, const float *__restrict__ qnorm2,
+                    const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
+                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags)
+{
+    __shared__ unsigned long long buf[1024];
+    const int qi = blockIdx.x;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) buf[i] = i < kp ? d_exact[(size_t)qi * kp + i] : 0ull;
+    __syncthreads();
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = buf[i], y = buf[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (x < y) : (x > y)) {
+                        buf[i] = y;
+                        buf[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) d_out[(size_t)qi * K + i] = buf[i];
+    if (threadIdx.x == 0) {
+        const unsigned int n = cnt[qi];
+        const long long keff = rows_total < K ? rows_total : K;
+        bool ok = true;
+        if (n > cap) ok = false;                       // candidate buffer overflowed: the selection saw a subset
+        if ((long long)n < keff) ok = false;           // threshold too high: not even K candidates
+        if (ok && (long long)n < rows_total) {         // some rows were never candidates
+            // approx ceiling of every row outside the re-scored set
+            float ceil_approx = thr[qi];
+            if (n > (unsigned)kp) {
+                const unsigned long long last = d_sel[(size_t)qi * kp + kp - 1];
+                ceil_approx = fmaxf(ceil_approx, key_score(last));
+            }
+            const float delta = err_coeff * sqrtf(__uint_as_float(*maxnorm2_bits)) * sqrtf(qnorm2[qi]);
+            const unsigned long long kth = buf[keff - 1];
+            if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
+        }
+        d_flags[qi] = ok ? 0u : 1u;  // flagged queries are re-run by the exact scan
+    }
+}
+
+// best kp keys of an unsorted candidate buffer: one CTA per query, bitonic sort in shared memory
+__global__ void __launch_bounds__(512)
+    select_kernel(const unsigned long long *__restrict__ d_cand, const unsigned int *__restrict__ d_cnt,
+                  unsigned int cap, int kp, unsigned long long *__restrict__ d_sel)
+{
+    __shared__ unsigned long long buf[kGemmCandCap];
+    const int qi = blockIdx.x;
+    unsigned int n = d_cnt[qi];
+    if (n > cap) n = cap;
+    int np = 2;
+    while ((unsigned)np < n) np <<= 1;
+    if (np < kp) {
+        np = 2;
+        while (np < kp) np <<= 1;
+    }
+    for (int i = threadIdx.x; i < np; i += blockDim.x) buf[i] = (unsigned)i < n ? d_cand[(size_t)qi * cap + i] : 0ull;
+    __syncthreads();
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = buf[i], y = buf[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (x < y) : (x > y)) {
+                        buf[i] = y;
+                        buf[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) d_sel[(size_t)qi * kp + i] = buf[i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+cudaError_t make_map(CUtensorMap *map, const float *base, uint64_t rows, int dims, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {(cuuint64_t)dims, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dims * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int NQ>
+cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int grid,
+                        cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)GemmCfg<NQ>::kSmem);
+    if (e != cudaSuccess) return e;
+    gemm_tf32_kernel<NQ><<<grid, kGemmThreads, GemmCfg<NQ>::kSmem, stream>>>(tmA, tmB, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int gemm_pad_queries(int q)
+{
+    if (q <= 16) return 16;
+    if (q <= 32) return 32;
+    if (q <= 64) return 64;
+    if (q <= 128) return 128;
+    return 256;
+}
+
+cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
+{
+    if (g.dims % kBK != 0 || g.q < 1 || g.q > g.nq) return cudaErrorInvalidValue;
+    CUtensorMap tmA, tmB;
+    cudaError_t e = make_map(&tmA, g.slab_base, g.slab_rows, g.dims, kTileRows);
+    if (e != cudaSuccess) return e;
+    e = make_map(&tmB, g.d_queries_padded, (uint64_t)g.nq, g.dims, (uint32_t)g.nq);
+    if (e != cudaSuccess) return e;
+    GemmArgs a{};
+    a.segs = g.d_segs;
+    a.gtile_start = g.d_gtile_start;
+    a.nseg = g.nseg;
+    a.dims = g.dims;
+    a.slab_base = g.slab_base;
+    a.mode = g.mode;
+    a.tile_first = g.tile_first;
+    a.tile_stride = g.tile_stride;
+    a.tile_count = g.tile_count;
+    a.q = g.q;
+    a.thr = g.d_thr;
+    a.cand = g.d_cand;
+    a.cnt = g.d_cnt;
+    a.cap = g.cap;
+    a.tilemax = g.d_tilemax;
+    a.dump = g.d_dump;
+    a.dump_ld = g.dump_ld;
+    int grid = g.sms < (int)g.tile_count ? g.sms : (int)g.tile_count;
+    if (grid < 1) return cudaSuccess;
+    switch (g.nq) {
+        case 16: return launch_gemm<16>(tmA, tmB, a, grid, stream);
+        case 32: return launch_gemm<32>(tmA, tmB, a, grid, stream);
+        case 64: return launch_gemm<64>(tmA, tmB, a, grid, stream);
+        case 128: return launch_gemm<128>(tmA, tmB, a, grid, stream);
+        case 256: return launch_gemm<256>(tmA, tmB, a, grid, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
+                                float *dst, float *qnorm2, cudaStream_t stream)
+{
+    prep_queries_kernel<<<nq, 128, 0, stream>>>(src, q_stride, l_stride, q, nq, dims, dst, qnorm2);
+    return cudaGetLastError();
+}
+
+cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
+                               cudaStream_t stream)
+{
+    rownorm_max_kernel<<<sms * 8, 256, 0, stream>>>(d_segs, nseg, dims, d_out_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
+                             unsigned int *d_cnt, cudaStream_t stream)
+{
+    if (ntiles > 1024 || ntiles < 1) return cudaErrorInvalidValue;
+    threshold_kernel<<<nq, 256, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *d_cnt, unsigned int cap, int q, int kp,
+                          unsigned long long *d_sel, cudaStream_t stream)
+{
+    if (cap > (unsigned)kGemmCandCap || kp > kGemmCandCap) return cudaErrorInvalidValue;
+    select_kernel<<<q, 512, 0, stream>>>(d_cand, d_cnt, cap, kp, d_sel);
+    return cudaGetLastError();
+}
+
+cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
+                           const float *d_queries_padded, int kp, const unsigned long long *d_sel,
+                           unsigned long long *d_exact, cudaStream_t stream)
+{
+    dim3 grid((kp * 32 + 255) / 256, q);
+    rescore_kernel<<<grid, 256, 0, stream>>>(d_segs, d_seg_slot_base, nseg, dims, 0, d_queries_padded, kp, d_sel,
+                                             d_exact);
+    return cudaGetLastError();
+}
+
+cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
+                            const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
+                            long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
+                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, cudaStream_t stream)
+{
+    if (kp > 1024 || K > kp) return cudaErrorInvalidValue;
+    finalize_kernel<<<q, 256, 0, stream>>>(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, rows_total, d_qnorm2,
+                                           d_maxnorm2_bits, err_coeff, d_out, d_flags);
+    return cudaGetLastError();
+}
+
+}  // namespace gf

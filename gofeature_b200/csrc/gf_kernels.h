@@ -46,15 +46,73 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
 // Fused dot-product + streaming top-K over the segments.
 //   d_queries : q queries; element l of query i at d_queries[i*q_stride + l*l_stride]
 //   d_upper   : optional q exclusive upper-bound keys (band passes for limit > kMaxK), may be null
+//   d_q_map / d_q_count : optional device-side indirection (fix-up of uncertified tensor-path queries):
+//               query i is row d_q_map[i] of d_queries, only *d_q_count (<= q) queries are live
 //   d_partial : [groups][grid_x][q][K] keys out
 cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, uint32_t total_tiles,
                         const float *d_queries, int q, int64_t q_stride, int64_t l_stride, int K,
-                        const unsigned long long *d_upper, unsigned long long *d_partial, cudaStream_t stream);
+                        const unsigned long long *d_upper, unsigned long long *d_partial, cudaStream_t stream,
+                        const int *d_q_map = nullptr, const unsigned int *d_q_count = nullptr);
 
 // Merge `lists` lists of K keys per (group, query): d_in [groups][lists][q][K] -> d_out [groups][q][K]
 // (descending, zero padded).
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
                          unsigned long long *d_out, cudaStream_t stream);
+
+// ---- tcgen05 contraction path (gf_gemm.cu) ----
+constexpr int kGemmMaxQ = 256;       // queries per pass (N of the MMA)
+constexpr int kGemmCandCap = 4096;   // candidate keys kept per query
+constexpr int kGemmMaxSampleTiles = 1024;
+constexpr float kTf32ErrCoeff = 2.2e-3f;  // |tf32 score - exact| <= coeff * |row| * |query| (two 10-bit truncations)
+enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2 };
+
+struct GemmLaunch {
+    const Segment *d_segs;
+    const uint32_t *d_gtile_start;  // nseg + 1 prefix of 128-row tiles
+    int nseg;
+    int dims;
+    const float *slab_base;   // first row of the cache slab (tensor map A covers the whole slab)
+    uint64_t slab_rows;
+    const float *d_queries_padded;  // [nq][dims]
+    int nq, q;
+    int mode;
+    uint32_t tile_first, tile_stride, tile_count;
+    const float *d_thr;
+    unsigned long long *d_cand;
+    unsigned int *d_cnt;
+    unsigned int cap;
+    float *d_tilemax;
+    float *d_dump;
+    unsigned long long dump_ld;
+    int sms;
+};
+int gemm_pad_queries(int q);
+cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
+cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
+                                float *dst, float *qnorm2, cudaStream_t stream);
+cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
+                               cudaStream_t stream);
+cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
+                             unsigned int *d_cnt, cudaStream_t stream);
+// best kp of each query's candidate buffer (unsorted, cnt valid entries) -> d_sel [q][kp] descending
+cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *d_cnt, unsigned int cap, int q, int kp,
+                          unsigned long long *d_sel, cudaStream_t stream);
+cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
+                           const float *d_queries_padded, int kp, const unsigned long long *d_sel,
+                           unsigned long long *d_exact, cudaStream_t stream);
+// d_flags[qi] = 1 when query qi could not be certified (it must be re-run by the exact scan)
+cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
+                            const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
+                            long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
+                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, cudaStream_t stream);
+
+constexpr int kFixupMaxQ = 8;  // uncertified queries one device-side fix-up scan pass can take
+cudaError_t compact_failed_launch(unsigned int *d_flags, int q, int maxn, int *d_map, unsigned int *d_count,
+                                  unsigned int *d_uncertified, cudaStream_t stream);
+cudaError_t scatter_fix_launch(const unsigned long long *d_fix, const int *d_map, const unsigned int *d_count,
+                               int maxn, int K, unsigned long long *d_out, cudaStream_t stream);
+cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, unsigned int *d_out_bits,
+                                 cudaStream_t stream);
 
 // Synthetic rows, bit-identical to oracle/gf_oracle.c gf_oracle_synth_rows.
 cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, uint64_t seed, int64_t first_row, int normalize,

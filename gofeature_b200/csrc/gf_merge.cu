@@ -168,7 +168,83 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ row
     }
 }
 
+// ---- device-side fix-up of tensor-path queries that failed their certificate ----
+// flags[q] (1 = uncertified) -> map[0..n) of their indices, *count = min(n, maxn); what does not
+// fit in one fix-up pass stays flagged and is added to *uncertified (the host API re-runs those).
+__global__ void compact_failed_kernel(unsigned int *flags, int q, int maxn, int *map, unsigned int *count,
+                                      unsigned int *uncertified)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    for (int i = 0; i < q; ++i) {
+        if (flags[i]) {
+            if (n < maxn) {
+                map[n] = i;
+                flags[i] = 0u;
+            }
+            ++n;
+        }
+    }
+    *count = (unsigned)(n < maxn ? n : maxn);
+    if (n > maxn) atomicAdd(uncertified, (unsigned)(n - maxn));
+}
+
+// fix [maxn][K] exact keys of the re-scanned queries -> rows map[i] of out [q][K]
+__global__ void scatter_fix_kernel(const unsigned long long *__restrict__ fix, const int *__restrict__ map,
+                                   const unsigned int *__restrict__ count, int K, unsigned long long *__restrict__ out)
+{
+    const unsigned i = blockIdx.x;
+    if (i >= *count) return;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) out[(size_t)map[i] * K + j] = fix[(size_t)i * K + j];
+}
+
 }  // namespace
+
+cudaError_t compact_failed_launch(unsigned int *d_flags, int q, int maxn, int *d_map, unsigned int *d_count,
+                                  unsigned int *d_uncertified, cudaStream_t stream)
+{
+    compact_failed_kernel<<<1, 32, 0, stream>>>(d_flags, q, maxn, d_map, d_count, d_uncertified);
+    return cudaGetLastError();
+}
+
+cudaError_t scatter_fix_launch(const unsigned long long *d_fix, const int *d_map, const unsigned int *d_count,
+                               int maxn, int K, unsigned long long *d_out, cudaStream_t stream)
+{
+    scatter_fix_kernel<<<maxn, 128, 0, stream>>>(d_fix, d_map, d_count, K, d_out);
+    return cudaGetLastError();
+}
+
+// max |row|^2 over a contiguous range of rows (incremental upkeep of the certificate's norm bound)
+namespace {
+__global__ void rownorm_range_kernel(const float *__restrict__ base, long long rows, int dims, unsigned int *out_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float *x = base + (size_t)r * dims;
+        float acc = 0.f;
+        for (int e = lane; e < dims; e += 32) {
+            float v = x[e];
+            acc += v * v;
+        }
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (acc == acc) best = fmaxf(best, acc);
+    }
+    if (lane == 0 && best > 0.f) atomicMax(out_bits, __float_as_uint(best * 1.0001f));
+}
+}  // namespace
+
+cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, unsigned int *d_out_bits,
+                                 cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rownorm_range_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, rows, dims, d_out_bits);
+    return cudaGetLastError();
+}
 
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
                          unsigned long long *d_out, cudaStream_t stream)

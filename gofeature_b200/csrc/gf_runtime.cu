@@ -7,6 +7,7 @@
 #include "gf_runtime.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -94,8 +95,23 @@ int Workspace::reserve(size_t d_bytes, size_t h_bytes)
     return GF_OK;
 }
 
+int Workspace::reserve_tensor(size_t bytes)
+{
+    if (bytes <= d_tensor_cap) return GF_OK;
+    if (d_tensor) {
+        GF_CUDA(cudaStreamSynchronize(stream), GF_ERR_CUDA);
+        cudaFree(d_tensor);
+        d_tensor = nullptr;
+        d_tensor_cap = 0;
+    }
+    GF_CUDA(cudaMalloc((void **)&d_tensor, bytes), GF_ERR_ALLOCATE_GPU_BUFFER);
+    d_tensor_cap = bytes;
+    return GF_OK;
+}
+
 Workspace::~Workspace()
 {
+    if (d_tensor) cudaFree(d_tensor);
     if (d_buf) cudaFree(d_buf);
     if (h_buf) cudaFreeHost(h_buf);
     if (stream) cudaStreamDestroy(stream);
@@ -503,13 +519,49 @@ int Set::rebuild_segments()
         if (d_segs) cudaFree(d_segs);
         d_segs = nullptr;
         int want = std::max((int)h_segs.size() * 2, 64);
-        GF_CUDA(cudaMalloc((void **)&d_segs, (size_t)want * sizeof(Segment)), GF_ERR_ALLOCATE_GPU_BUFFER);
+        // one allocation: Segment[want] | gtile_start[want + 1] | slot_base[want]
+        size_t bytes = (size_t)want * sizeof(Segment) + (size_t)(2 * want + 2) * sizeof(uint32_t);
+        GF_CUDA(cudaMalloc((void **)&d_segs, bytes), GF_ERR_ALLOCATE_GPU_BUFFER);
         d_segs_cap = want;
+        d_gtile_start = reinterpret_cast<uint32_t *>(d_segs + want);
+        d_seg_slot_base = d_gtile_start + want + 1;
     }
-    GF_CUDA(cudaMemcpyAsync(d_segs, h_segs.data(), h_segs.size() * sizeof(Segment), cudaMemcpyHostToDevice,
+    // host image of the three arrays, one upload
+    const size_t n = h_segs.size();
+    std::vector<uint32_t> aux(2 * n + 1);
+    uint32_t gt = 0;
+    for (size_t i = 0; i < n; ++i) {
+        aux[i] = gt;
+        gt += (h_segs[i].rows + 127) / 128;
+        aux[n + 1 + i] = h_segs[i].slot_base;
+    }
+    aux[n] = gt;
+    total_gtiles = gt;
+    tensor_ok = precision == 4 && dims % 32 == 0 && dims >= 32 && (cache->block_size % ((int64_t)dims * 4)) == 0 &&
+                ((uintptr_t)cache->slab->ptr % 128) == 0;
+    GF_CUDA(cudaMemcpyAsync(d_segs, h_segs.data(), n * sizeof(Segment), cudaMemcpyHostToDevice, ctx->mut_stream),
+            GF_ERR_WRITE_CUDA_BUFFER);
+    GF_CUDA(cudaMemcpyAsync(d_gtile_start, aux.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            ctx->mut_stream),
+            GF_ERR_WRITE_CUDA_BUFFER);
+    GF_CUDA(cudaMemcpyAsync(d_seg_slot_base, aux.data() + n + 1, n * sizeof(uint32_t), cudaMemcpyHostToDevice,
                             ctx->mut_stream),
             GF_ERR_WRITE_CUDA_BUFFER);
     GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+    return GF_OK;
+}
+
+// The tensor path's certificate needs an upper bound of |row| over the set: an atomicMax over the
+// rows that were just written (deletes never lower it: the bound stays conservative).
+int Set::note_rows(const float *d_rows, int64_t rows)
+{
+    if (precision != 4 || rows <= 0) return GF_OK;
+    if (!d_small) {
+        GF_CUDA(cudaMalloc((void **)&d_small, 64), GF_ERR_ALLOCATE_GPU_BUFFER);
+        GF_CUDA(cudaMemsetAsync(d_small, 0, 64, ctx->mut_stream), GF_ERR_CUDA);
+    }
+    GF_CUDA(rownorm_range_launch(d_rows, rows, dims, d_small, ctx->mut_stream), GF_ERR_CUDA);
+    ctx->stats.other_launches++;
     return GF_OK;
 }
 
@@ -560,11 +612,16 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
         int64_t length = std::min<int64_t>(b->margin(), remain);
         if (length > 0) {
             std::vector<std::string> sub(ids_.begin() + offset, ids_.begin() + offset + length);
+            const std::vector<int> refilled(b->empty.begin(),
+                                            b->empty.begin() + std::min<size_t>(b->empty.size(), (size_t)length));
+            const int tail0 = b->next_index;
             rc = b->insert(length, values + (size_t)offset * rowb, sub);
             if (rc) {
                 rebuild_segments();
                 return rc;
             }
+            for (int slot : refilled) note_rows((const float *)b->dev + (size_t)slot * dims, 1);
+            if (b->next_index > tail0) note_rows((const float *)b->dev + (size_t)tail0 * dims, b->next_index - tail0);
             offset += length;
             remain -= length;
         }
@@ -612,8 +669,10 @@ int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int norm
         int64_t length = std::min<int64_t>(b->capacity() - b->next_index, n - done);
         if (length > 0) {
             if (b->implicit_ids && b->next_index == 0) b->id_first = first_ordinal + done;
+            const int tail0 = b->next_index;
             rc = b->insert_synthetic(length, seed, first_ordinal + done, normalize, prefix);
             if (rc) return rc;
+            note_rows((const float *)b->dev + (size_t)tail0 * dims, length);
             done += length;
         }
         if (done >= n) break;
@@ -657,10 +716,12 @@ int Set::update(int64_t n, const uint8_t *values, const std::vector<std::string>
             if (row < 0) continue;
             rc = ctx->upload(b->dev + (size_t)row * rowb, values + (size_t)i * rowb, rowb);
             if (rc) return rc;
+            note_rows((const float *)b->dev + (size_t)row * dims, 1);
             found[i] = 1;
             break;
         }
     }
+    GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
     return GF_OK;
 }
 
@@ -714,6 +775,13 @@ int Set::destroy()
         ctx->release_ws(dev_ws);
         dev_ws = nullptr;
     }
+    if (d_small) {
+        cudaFree(d_small);
+        d_small = nullptr;
+    }
+    d_gtile_start = d_seg_slot_base = nullptr;
+    total_gtiles = 0;
+    tensor_ok = false;
     return GF_OK;
 }
 
@@ -725,9 +793,145 @@ static size_t partial_bytes(const ScanPlan &p, int qp, int K)
     return (size_t)p.groups * p.grid_x * qp * K * sizeof(unsigned long long);
 }
 
+bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long long *d_upper, int path) const
+{
+    if (path == 1 || per_segment || d_upper != nullptr || !tensor_ok || d_small == nullptr) return false;
+    if (K > 512) return false;                               // K' = K + slack must fit the 1024-key re-score
+    if (total_gtiles < 2 * 256) return false;                // small sets: the sample would be the set
+    if (path == 2) return true;
+    return q > scan_max_q(dims);                             // one scan pass cannot hold the batch
+}
+
 int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                      int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
-                     unsigned long long *d_out)
+                     unsigned long long *d_out, int path, unsigned int *d_flags)
+{
+    if (tensor_eligible(q, K, per_segment, d_upper, path))
+        return topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, d_out, d_flags);
+    if (d_flags) GF_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)q * sizeof(unsigned int), stream), GF_ERR_CUDA);
+    return topk_scan(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out);
+}
+
+// Tensor-core candidate pass + exact re-score + certificate, in passes of <= 256 queries:
+//   prep (pad + |q|^2) -> TILEMAX over a strided sample of tiles -> per-query threshold ->
+//   COLLECT over all tiles (threshold + atomic append) -> best K' candidates -> canonical re-score
+//   -> sort, emit K, certify.  Uncertified queries are re-run by one fix-up scan pass on the device
+//   (up to kFixupMaxQ per call); what is still flagged is reported through d_flags.
+int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags)
+{
+    const int nseg = (int)h_segs.size();
+    const int kp = std::min(1024, std::max(K + 32, K + K / 2));
+    const unsigned cap = kGemmCandCap;
+    // sample: G strided tiles; threshold = m-th largest tile maximum so that ~target rows pass
+    int G = (int)std::min<uint32_t>(kGemmMaxSampleTiles, std::max<uint32_t>(256, total_gtiles / 32));
+    G = (int)std::min<uint32_t>((uint32_t)G, total_gtiles);
+    const uint32_t stride = total_gtiles / (uint32_t)G;
+    const double target = std::max(1024.0, 4.0 * kp);
+    int m = (int)std::ceil(target * G / (double)total_gtiles);
+    m = std::max(2, std::min(m, G / 2));
+
+    const int nq_max = gemm_pad_queries(std::min(q, kGemmMaxQ));
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_qpad = carve((size_t)nq_max * dims * 4);
+    const size_t o_qn = carve((size_t)nq_max * 4);
+    const size_t o_tmax = carve((size_t)kGemmMaxSampleTiles * nq_max * 4);
+    const size_t o_thr = carve((size_t)nq_max * 4);
+    const size_t o_cnt = carve((size_t)nq_max * 4);
+    const size_t o_cand = carve((size_t)nq_max * cap * 8);
+    const size_t o_sel = carve((size_t)nq_max * kp * 8);
+    const size_t o_exact = carve((size_t)nq_max * kp * 8);
+    const size_t o_flags = carve((size_t)q * 4);
+    const size_t o_map = carve((size_t)kFixupMaxQ * 4);
+    const size_t o_count = carve(4);
+    const size_t o_fix = carve((size_t)kFixupMaxQ * K * 8);
+    const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
+    int rc = ws->reserve_tensor(off);
+    if (rc) return rc;
+    uint8_t *T = ws->d_tensor;
+    float *d_qpad = (float *)(T + o_qpad);
+    float *d_qn = (float *)(T + o_qn);
+    float *d_tmax = (float *)(T + o_tmax);
+    float *d_thr = (float *)(T + o_thr);
+    unsigned int *d_cnt = (unsigned int *)(T + o_cnt);
+    unsigned long long *d_cand = (unsigned long long *)(T + o_cand);
+    unsigned long long *d_sel = (unsigned long long *)(T + o_sel);
+    unsigned long long *d_exact = (unsigned long long *)(T + o_exact);
+    unsigned int *d_fl = (unsigned int *)(T + o_flags);
+    int *d_map = (int *)(T + o_map);
+    unsigned int *d_count = (unsigned int *)(T + o_count);
+    unsigned long long *d_fix = (unsigned long long *)(T + o_fix);
+    float *d_qall = (float *)(T + o_qall);
+
+    GemmLaunch g{};
+    g.d_segs = d_segs;
+    g.d_gtile_start = d_gtile_start;
+    g.nseg = nseg;
+    g.dims = dims;
+    g.slab_base = (const float *)cache->slab->ptr;
+    g.slab_rows = (uint64_t)(cache->slab->size / ((uint64_t)dims * 4));
+    g.d_queries_padded = d_qpad;
+    g.d_thr = d_thr;
+    g.d_cand = d_cand;
+    g.d_cnt = d_cnt;
+    g.cap = cap;
+    g.d_tilemax = d_tmax;
+    g.sms = ctx->sms;
+
+    for (int p0 = 0; p0 < q; p0 += kGemmMaxQ) {
+        const int qp = std::min(kGemmMaxQ, q - p0);
+        const int nq = gemm_pad_queries(qp);
+        g.nq = nq;
+        g.q = qp;
+        GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad, d_qn,
+                                    stream),
+                GF_ERR_CUDA);
+        GF_CUDA(cudaMemcpyAsync(d_qall + (size_t)p0 * dims, d_qpad, (size_t)qp * dims * 4, cudaMemcpyDeviceToDevice,
+                                stream),
+                GF_ERR_CUDA);
+        g.mode = kGemmTileMax;
+        g.tile_first = 0;
+        g.tile_stride = stride;
+        g.tile_count = (uint32_t)G;
+        GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
+        GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
+        g.mode = kGemmCollect;
+        g.tile_stride = 1;
+        g.tile_count = total_gtiles;
+        GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
+        GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
+        GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp, d_sel, d_exact, stream),
+                GF_ERR_CUDA);
+        GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, qp, scanned_rows, d_qn, d_small,
+                                kTf32ErrCoeff, d_out + (size_t)p0 * K, d_fl + p0, stream),
+                GF_ERR_CUDA);
+        ctx->stats.gemm_launches += 2;
+        ctx->stats.other_launches += 5;
+        ctx->stats.tensor_passes++;
+        ctx->stats.rows_scanned += (uint64_t)scanned_rows;
+    }
+    // device-side fix-up: one exact scan pass over up to kFixupMaxQ flagged queries (a no-op launch
+    // when everything was certified)
+    const int fixq = std::min(kFixupMaxQ, scan_max_q(dims));
+    GF_CUDA(compact_failed_launch(d_fl, q, fixq, d_map, d_count, d_small + 1, stream), GF_ERR_CUDA);
+    rc = topk_scan(ws, stream, d_qall, fixq, dims, 1, K, false, nullptr, d_fix, d_map, d_count);
+    if (rc) return rc;
+    GF_CUDA(scatter_fix_launch(d_fix, d_map, d_count, fixq, K, d_out, stream), GF_ERR_CUDA);
+    ctx->stats.other_launches += 2;
+    if (d_flags)
+        GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream),
+                GF_ERR_CUDA);
+    return GF_OK;
+}
+
+int Set::topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                   int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
+                   unsigned long long *d_out, const int *d_q_map, const unsigned int *d_q_count)
 {
     const int nseg = (int)h_segs.size();
     const int maxq = scan_max_q(dims);
@@ -746,7 +950,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         std::pair<cudaEvent_t, cudaEvent_t> ev;
         ctx->prof_begin(stream, &ev);
         cudaError_t le = scan_launch(plan, d_segs, nseg, total_tiles, d_queries + (size_t)p0 * q_stride, qp, q_stride,
-                                     l_stride, K, up, d_partial, stream);
+                                     l_stride, K, up, d_partial, stream, d_q_map, d_q_count);
         ctx->prof_end(stream, ev);
         if (le != cudaSuccess) return cuda_fail(le, "scan_launch", GF_ERR_CUDA);
         ctx->stats.scan_launches++;
@@ -808,16 +1012,19 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
     const size_t qbytes = (size_t)q * dims * 4;
     const size_t out_keys = (size_t)q * kb_max;
     size_t d_need = align_up(qbytes, 256) + align_up((size_t)q * 8, 256) + align_up(out_keys * 8, 256) +
-                    scratch_bytes(this, q, kb_max, false);
-    size_t h_need = align_up(qbytes, 256) + align_up((size_t)q * 8, 256) + align_up(out_keys * 8, 256);
+                    align_up((size_t)q * 4, 256) + scratch_bytes(this, q, kb_max, false);
+    size_t h_need = align_up(qbytes, 256) + align_up((size_t)q * 8, 256) + align_up(out_keys * 8, 256) +
+                    align_up((size_t)q * 4, 256);
     rc = ws->reserve(d_need, h_need);
     if (rc) return rc;
     float *d_q = (float *)ws->d_buf;
     unsigned long long *d_upper = (unsigned long long *)(ws->d_buf + align_up(qbytes, 256));
     unsigned long long *d_out = (unsigned long long *)((uint8_t *)d_upper + align_up((size_t)q * 8, 256));
+    unsigned int *d_flags = (unsigned int *)((uint8_t *)d_out + align_up(out_keys * 8, 256));
     float *h_q = (float *)ws->h_buf;
     unsigned long long *h_upper = (unsigned long long *)(ws->h_buf + align_up(qbytes, 256));
     unsigned long long *h_out = (unsigned long long *)((uint8_t *)h_upper + align_up((size_t)q * 8, 256));
+    unsigned int *h_flags = (unsigned int *)((uint8_t *)h_out + align_up(out_keys * 8, 256));
 
     memcpy(h_q, queries, qbytes);
     GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
@@ -834,12 +1041,27 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
             GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)q * 8, cudaMemcpyHostToDevice, ws->stream),
                     GF_ERR_WRITE_INPUT_BUFFER);
         }
-        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out);
+        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out, 0,
+                         d_flags);
         if (rc) return rc;
         GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
                 GF_ERR_READ_CUDA_BUFFER);
+        GF_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)q * 4, cudaMemcpyDeviceToHost, ws->stream),
+                GF_ERR_READ_CUDA_BUFFER);
         GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
-        ctx->stats.d2h_bytes += (size_t)q * kb * 8;
+        ctx->stats.d2h_bytes += (size_t)q * kb * 8 + (size_t)q * 4;
+        // tensor-path queries that could neither be certified nor fixed on the device: exact scan, one by one
+        for (int i = 0; i < q; ++i) {
+            if (!h_flags[i]) continue;
+            ctx->stats.uncertified_queries++;
+            rc = topk_scan(ws, ws->stream, d_q + (size_t)i * dims, 1, dims, 1, kb, false, nullptr,
+                           d_out + (size_t)i * kb);
+            if (rc) return rc;
+            GF_CUDA(cudaMemcpyAsync(h_out + (size_t)i * kb, d_out + (size_t)i * kb, (size_t)kb * 8,
+                                    cudaMemcpyDeviceToHost, ws->stream),
+                    GF_ERR_READ_CUDA_BUFFER);
+            GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+        }
         bool all_done = true;
         for (int i = 0; i < q; ++i) {
             if (lists[i].exhausted) continue;
@@ -986,7 +1208,6 @@ int Set::search(float threshold, int limit, int q, const uint8_t *queries, Resul
 int Set::search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
                        cudaStream_t stream)
 {
-    (void)path;
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (q > batch) return GF_ERR_OUT_OF_BATCH;
     if (q <= 0 || limit <= 0) return GF_ERR_INVALID_ARGUMENT;
@@ -1015,7 +1236,7 @@ int Set::search_device(int limit, int q, const float *d_queries, unsigned long l
         rc = ws->reserve(need, 0);
         if (rc) return rc;
     }
-    return topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out);
+    return topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out, path == 0 ? 0 : path, nullptr);
 }
 
 int Set::resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out)

@@ -63,7 +63,7 @@ class RWLock {
 struct Stats {
     std::atomic<uint64_t> searches{0}, scan_launches{0}, gemm_launches{0}, merge_launches{0}, other_launches{0},
         rows_scanned{0}, quirk_fallbacks{0}, coalesced_batches{0}, h2d_bytes{0}, d2h_bytes{0}, scan_kernel_ns{0},
-        scan_kernel_timed{0};
+        scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0};
 };
 
 // per-search scratch: a stream, device and pinned arenas
@@ -73,7 +73,10 @@ struct Workspace {
     size_t d_cap = 0;
     uint8_t *h_buf = nullptr;
     size_t h_cap = 0;
+    uint8_t *d_tensor = nullptr;  // scratch of the tcgen05 path (queries, tile maxima, candidates ...)
+    size_t d_tensor_cap = 0;
     int reserve(size_t d_bytes, size_t h_bytes);
+    int reserve_tensor(size_t bytes);
     ~Workspace();
 };
 
@@ -202,6 +205,12 @@ struct gf_set {
     std::vector<int> seg_block;  // segment -> position in blocks
     Segment *d_segs = nullptr;
     int d_segs_cap = 0;
+    // tcgen05 path: 128-row tile prefix per segment, slot base per segment, |row|^2 bound, counters
+    uint32_t *d_gtile_start = nullptr;
+    uint32_t *d_seg_slot_base = nullptr;
+    uint32_t total_gtiles = 0;
+    unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter
+    bool tensor_ok = false;
     uint32_t total_tiles = 0;
     int64_t scanned_rows = 0;
     int tile_rows = 0;
@@ -232,9 +241,18 @@ struct gf_set {
     int destroy();
     // top-K over the scanned rows into d_out; read lock held by the caller.
     //   per_segment: d_out is [pass][segment][qp][K] (qp = queries of that pass), else [q][K]
+    //   path: 0 = choose (tensor cores for q >= 9 on large sets), 1 = fused scan only, 2 = tensor path
+    //   d_flags (optional, [q]): 1 where a tensor-path query could not be certified nor fixed on the device
     int topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                     int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
-                    unsigned long long *d_out);
+                    unsigned long long *d_out, int path = 1, unsigned int *d_flags = nullptr);
+    int topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                  int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
+                  unsigned long long *d_out, const int *d_q_map = nullptr, const unsigned int *d_q_count = nullptr);
+    int topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                    int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags);
+    bool tensor_eligible(int q, int K, bool per_segment, const unsigned long long *d_upper, int path) const;
+    int note_rows(const float *d_rows, int64_t rows);  // keep the |row|^2 bound current (mutation stream)
     bool slot_to_block(uint32_t slot, int *block_pos, int *row) const;
 };
 

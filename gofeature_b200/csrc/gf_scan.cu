@@ -43,6 +43,8 @@ struct ScanArgs {
     int tile_rows;
     int dims;
     int per_segment;
+    const int *q_map;             // optional: query i of this launch is row q_map[i] of `queries`
+    const unsigned int *q_count;  // optional: live query count lives on the device (0 -> nothing to do)
     const unsigned long long *upper;
     unsigned long long *partial;
 };
@@ -103,6 +105,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     unsigned long long *lists = reinterpret_cast<unsigned long long *>(ctl + QT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int q_live = a.q;
+    if (a.q_count != nullptr) {
+        const unsigned int c = *a.q_count;
+        if (c == 0u) return;  // fix-up launch with nothing to fix
+        q_live = c < (unsigned)a.q ? (int)c : a.q;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -161,7 +169,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 int e = 128 * j + 4 * lane + c;
-                v[c] = (qi < a.q) ? a.queries[(long long)qi * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+                const int qsrc = (qi < q_live && a.q_map != nullptr) ? a.q_map[qi] : qi;
+                v[c] = (qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
             }
             qreg[qi][j] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     constexpr int GROUP = 32 >> LOG2V;  // lanes that end up with the same score
     const int vi = lane >> (5 - LOG2V);
     const int my_b = vi / QT, my_q = vi % QT;
-    const bool my_live = my_q < a.q;
+    const bool my_live = my_q < q_live;
 
     const int cap = a.list_cap, K = a.K;
     int s = 0;
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     }
 
     named_bar_sync(1, kConsumerThreads);
-    for (int qi = warp; qi < a.q && qi < QT; qi += kConsumerWarps) {
+    for (int qi = warp; qi < q_live && qi < QT; qi += kConsumerWarps) {
         unsigned long long *out =
             a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
         list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
@@ -254,9 +263,16 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
     unsigned long long *lists = reinterpret_cast<unsigned long long *>(ctl + QT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int q_live = a.q;
+    if (a.q_count != nullptr) {
+        const unsigned int c = *a.q_count;
+        if (c == 0u) return;
+        q_live = c < (unsigned)a.q ? (int)c : a.q;
+    }
     for (int i = threadIdx.x; i < QT * dims; i += blockDim.x) {
         int qi = i / dims, e = i - qi * dims;
-        qs[i] = (qi < a.q) ? a.queries[(long long)qi * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+        const int qsrc = (qi < q_live && a.q_map != nullptr) ? a.q_map[qi] : qi;
+        qs[i] = (qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
     }
     if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
     for (int i = threadIdx.x; i < QT * a.list_cap; i += blockDim.x) lists[i] = 0ull;
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
 #pragma unroll
             for (int qi = 0; qi < QT; ++qi) {
                 float sc = canonical_reduce(P[qi][0], P[qi][1], P[qi][2], P[qi][3]);
-                if (qi < a.q) {
+                if (qi < q_live) {
                     unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + qi] : ~0ull;
                     offer(&ctl[qi], lists + (size_t)qi * cap, cap, K, sc, cur.slot_base + row0 + r, up, lane);
                 }
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
         }
     }
     __syncthreads();
-    for (int qi = warp; qi < a.q && qi < QT; qi += kConsumerWarps) {
+    for (int qi = warp; qi < q_live && qi < QT; qi += kConsumerWarps) {
         unsigned long long *out =
             a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
         list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
@@ -414,9 +430,12 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
 
 cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, uint32_t total_tiles,
                         const float *d_queries, int q, int64_t q_stride, int64_t l_stride, int K,
-                        const unsigned long long *d_upper, unsigned long long *d_partial, cudaStream_t stream)
+                        const unsigned long long *d_upper, unsigned long long *d_partial, cudaStream_t stream,
+                        const int *d_q_map, const unsigned int *d_q_count)
 {
     ScanArgs a{};
+    a.q_map = d_q_map;
+    a.q_count = d_q_count;
     a.segs = d_segs;
     a.nseg = nseg;
     a.total_tiles = total_tiles;

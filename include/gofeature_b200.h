@@ -276,6 +276,8 @@ typedef struct gf_stats {
     uint64_t d2h_bytes;
     uint64_t scan_kernel_ns;    /* CUDA-event time of the timed scan launches (profiling on) */
     uint64_t scan_kernel_timed; /* how many scan launches were timed */
+    uint64_t tensor_passes;     /* tcgen05 candidate passes (each serves up to 256 queries) */
+    uint64_t uncertified_queries; /* tensor-path queries the host API re-ran through the exact scan */
 } gf_stats;
 GF_API int gf_context_stats(const gf_context *ctx, gf_stats *out);
 GF_API int gf_context_reset_stats(gf_context *ctx);
