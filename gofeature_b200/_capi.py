@@ -24,7 +24,7 @@ class gf_stats(ctypes.Structure):
     _fields_ = [(n, c_u64) for n in ("searches", "scan_launches", "gemm_launches", "merge_launches",
                                      "other_launches", "rows_scanned", "quirk_fallbacks", "coalesced_batches",
                                      "h2d_bytes", "d2h_bytes", "scan_kernel_ns", "scan_kernel_timed",
-                                     "tensor_passes", "uncertified_queries")]
+                                     "tensor_passes", "uncertified_queries", "gemm_kernel_ns", "gemm_kernel_timed")]
 
 
 # name -> (restype, argtypes); every symbol include/gofeature_b200.h declares

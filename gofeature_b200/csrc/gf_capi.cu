@@ -226,6 +226,8 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
     out->scan_kernel_timed = s.scan_kernel_timed;
     out->tensor_passes = s.tensor_passes;
     out->uncertified_queries = s.uncertified_queries;
+    out->gemm_kernel_ns = s.gemm_kernel_ns;
+    out->gemm_kernel_timed = s.gemm_kernel_timed;
     out->searches = s.searches;
     out->scan_launches = s.scan_launches;
     out->gemm_launches = s.gemm_launches;
@@ -248,6 +250,7 @@ int gf_context_reset_stats(gf_context *ctx)
     ctx->prof_collect();
     s.scan_kernel_ns = s.scan_kernel_timed = 0;
     s.tensor_passes = s.uncertified_queries = 0;
+    s.gemm_kernel_ns = s.gemm_kernel_timed = 0;
     return GF_OK;
 }
 

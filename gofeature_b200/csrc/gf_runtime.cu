@@ -195,12 +195,12 @@ void Context::prof_begin(cudaStream_t st, std::pair<cudaEvent_t, cudaEvent_t> *e
     cudaEventRecord(ev->first, st);
 }
 
-void Context::prof_end(cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t> &ev)
+void Context::prof_end(cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t> &ev, bool gemm)
 {
     if (!ev.first) return;
     cudaEventRecord(ev.second, st);
     std::lock_guard<std::mutex> g(prof_mu);
-    prof_pending.push_back(ev);
+    (gemm ? prof_pending_gemm : prof_pending).push_back(ev);
 }
 
 void Context::prof_collect()
@@ -217,14 +217,28 @@ void Context::prof_collect()
             stats.scan_kernel_timed++;
         }
     }
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> todo2;
+    {
+        std::lock_guard<std::mutex> g(prof_mu);
+        todo2.swap(prof_pending_gemm);
+    }
+    for (auto &ev : todo2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+            stats.gemm_kernel_ns += (uint64_t)((double)ms * 1e6);
+            stats.gemm_kernel_timed++;
+        }
+    }
     std::lock_guard<std::mutex> g(prof_mu);
     prof_free.insert(prof_free.end(), todo.begin(), todo.end());
+    prof_free.insert(prof_free.end(), todo2.begin(), todo2.end());
 }
 
 Context::~gf_context()
 {
     cudaSetDevice(device);
     for (auto &ev : prof_pending) prof_free.push_back(ev);
+    for (auto &ev : prof_pending_gemm) prof_free.push_back(ev);
     for (auto &ev : prof_free) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -903,7 +917,13 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         g.mode = kGemmCollect;
         g.tile_stride = 1;
         g.tile_count = total_gtiles;
-        GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
+        {
+            std::pair<cudaEvent_t, cudaEvent_t> ev;
+            ctx->prof_begin(stream, &ev);
+            cudaError_t le = gemm_launch(g, stream);
+            ctx->prof_end(stream, ev, true);
+            if (le != cudaSuccess) return cuda_fail(le, "gemm_launch", GF_ERR_CUDA);
+        }
         GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
         GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp, d_sel, d_exact, stream),
                 GF_ERR_CUDA);

@@ -63,7 +63,7 @@ class RWLock {
 struct Stats {
     std::atomic<uint64_t> searches{0}, scan_launches{0}, gemm_launches{0}, merge_launches{0}, other_launches{0},
         rows_scanned{0}, quirk_fallbacks{0}, coalesced_batches{0}, h2d_bytes{0}, d2h_bytes{0}, scan_kernel_ns{0},
-        scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0};
+        scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0}, gemm_kernel_ns{0}, gemm_kernel_timed{0};
 };
 
 // per-search scratch: a stream, device and pinned arenas
@@ -96,9 +96,9 @@ struct gf_context {
     // optional CUDA-event timing of the scan launches
     std::atomic<int> profiling{0};
     std::mutex prof_mu;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending, prof_free;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending, prof_pending_gemm, prof_free;
     void prof_begin(cudaStream_t st, std::pair<cudaEvent_t, cudaEvent_t> *ev);
-    void prof_end(cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t> &ev);
+    void prof_end(cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t> &ev, bool gemm = false);
     void prof_collect();  // waits for the pending events and folds them into stats
     std::mutex ws_mu;
     std::vector<Workspace *> ws_free;

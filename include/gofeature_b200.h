@@ -278,6 +278,8 @@ typedef struct gf_stats {
     uint64_t scan_kernel_timed; /* how many scan launches were timed */
     uint64_t tensor_passes;     /* tcgen05 candidate passes (each serves up to 256 queries) */
     uint64_t uncertified_queries; /* tensor-path queries the host API re-ran through the exact scan */
+    uint64_t gemm_kernel_ns;    /* CUDA-event time of the timed tcgen05 COLLECT launches (profiling on) */
+    uint64_t gemm_kernel_timed;
 } gf_stats;
 GF_API int gf_context_stats(const gf_context *ctx, gf_stats *out);
 GF_API int gf_context_reset_stats(gf_context *ctx);

@@ -482,3 +482,62 @@ def test_full_size_needles_1m(gpu_ctx):
     for s_, i_ in zip(sc, idx):
         assert s_ <= tenth or ("f%011d" % i_) in ids
     cache.Close()
+
+
+# ------------------------------------------------------------------ large batches: tcgen05 candidate pass
+@pytest.mark.parametrize("dims,n,q,limit", [
+    (512, 70000, 9, 10),        # smallest batch the tensor path takes
+    (512, 70000, 33, 1),
+    (512, 90000, 100, 100),     # K' = 150 re-scored per query
+    (512, 70000, 300, 10),      # two passes of <= 256 queries
+    (128, 140000, 20, 10),
+    (256, 80000, 17, 50),
+])
+def test_tensor_path_parity(gpu_ctx, dims, n, q, limit):
+    """q >= 9 on a large set runs TF32 tensor-core candidate selection + canonical re-score + certificate;
+    the answer must still be bit-identical to the oracle (and therefore to the fused scan)."""
+    block_rows = 16384
+    cache, st, ost = _pair(gpu_ctx, "tensor", dims, q, block_rows, (n + block_rows - 1) // block_rows + 1)
+    st.AddSynthetic(n, 4242 + dims)
+    rows = ol.synth_rows(4242 + dims, 0, n, dims)
+    ost.add(rows, ["f%011d" % i for i in range(n)])
+    queries = ol.synth_rows(99 + q, 0, q, dims)
+    queries[0] = rows[n // 2]                                          # a needle: score 1 at a known slot
+    gpu_ctx.ResetStats()
+    got = st.SearchArray(-1.0, limit, queries)
+    stats = gpu_ctx.Stats()
+    assert stats["tensor_passes"] == (q + 255) // 256, stats           # the tcgen05 path really ran
+    assert got[0][0].ID == "f%011d" % (n // 2)
+    _assert_same(got, ost.search(-1.0, limit, queries), "tensor")
+    assert stats["uncertified_queries"] == 0
+    kill = ["f%011d" % i for i in range(0, n, 997)]
+    assert sorted(st.Delete(*kill)) == sorted(ost.delete(kill))        # tombstones compete as zero rows
+    _assert_same(st.SearchArray(0.05, limit, queries), ost.search(0.05, limit, queries), "tensor+tombstones")
+    cache.Close()
+
+
+def test_tensor_path_certificate_fallback(gpu_ctx):
+    """Thousands of rows whose scores differ by less than the TF32 error bound: the certificate cannot
+    hold, the flagged queries are re-run by the exact scan (on the device, then by the host call), and
+    the answer is still exact.  Un-normalised rows exercise the |row|.|query| scaling of the bound."""
+    dims, n, q, limit = 512, 70000, 24, 10
+    cache, st, ost = _pair(gpu_ctx, "cert", dims, q, 16384, 6)
+    rng = np.random.default_rng(17)
+    rows = ol.synth_rows(808, 0, n, dims)
+    rows[::3] *= np.float32(2.5)                                       # norms up to 2.5
+    centre = rows[1].copy()
+    near = centre[None, :] + rng.normal(0, 2e-6, (6000, dims)).astype(np.float32)
+    rows[10000:16000] = near                                           # 6000 near-duplicates
+    ids = ["c%06d" % i for i in range(n)]
+    st.AddArray(rows, ids)
+    ost.add(rows, ids)
+    queries = ol.synth_rows(809, 0, q, dims)
+    for i in range(12):                                                # half the batch looks at the cluster
+        queries[i] = centre / np.linalg.norm(centre) + rng.normal(0, 1e-3, dims).astype(np.float32)
+    gpu_ctx.ResetStats()
+    got = st.SearchArray(-10.0, limit, queries)
+    stats = gpu_ctx.Stats()
+    assert stats["tensor_passes"] == 1
+    assert stats["uncertified_queries"] > 0 or stats["scan_launches"] >= 1
+    _assert_same(got, ost.search(-10.0, limit, queries), "certificate fallback")
+    cache.Close()
