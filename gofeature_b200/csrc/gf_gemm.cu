@@ -330,13 +330,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 // ------------------------------------------------------------------ helper kernels
 // queries [q][dims] (any stride) -> padded row-major batch [nq][dims] (rows >= q zeroed) + |q|^2
 __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
-                                    int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2)
+                                    int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2,
+                                    float *__restrict__ copy)
 {
     const int qi = blockIdx.x;
     float acc = 0.f;
     for (int e = threadIdx.x; e < dims; e += blockDim.x) {
         float v = qi < q ? src[(long long)qi * q_stride + (long long)e * l_stride] : 0.f;
         dst[(size_t)qi * dims + e] = v;
+        if (copy != nullptr && qi < q) copy[(size_t)qi * dims + e] = v;
         acc += v * v;
     }
     __shared__ float red[32];
@@ -373,35 +375,32 @@ __global__ void rownorm_max_kernel(const Segment *__restrict__ segs, int nseg, i
     if (lane == 0 && best > 0.f) atomicMax(out_bits, __float_as_uint(best * 1.0001f));
 }
 
-// per query: threshold = m-th largest of `ntiles` tile maxima (descending), minus nothing; also
-// resets the candidate counters.  One warp per query; ntiles <= 1024.
+// per query: threshold = m-th largest of `ntiles` tile maxima; also resets the candidate counter.
+// One warp per query: MSB-first radix select on the orderable score images (32 count steps).
 __global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, int nq, int q, int m,
                                  float *__restrict__ thr, unsigned int *__restrict__ cnt)
 {
-    __shared__ unsigned int v[1024];
-    const int qi = blockIdx.x;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
-        v[i] = i < ntiles ? score_image(tilemax[(size_t)i * nq + qi]) : 0u;
-    __syncthreads();
-    for (int k = 2; k <= 1024; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned a = v[i], b = v[ixj];
-                    bool desc = ((i & k) == 0);
-                    if (desc ? (a < b) : (a > b)) {
-                        v[i] = b;
-                        v[ixj] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    unsigned int v[kGemmMaxSampleTiles / 32];
+#pragma unroll
+    for (int i = 0; i < kGemmMaxSampleTiles / 32; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < ntiles ? score_image(tilemax[(size_t)t * nq + qi]) : 0u;
     }
-    if (threadIdx.x == 0) {
-        int idx = m - 1 < ntiles ? m - 1 : ntiles - 1;
-        thr[qi] = qi < q ? image_score(v[idx]) : __int_as_float(0x7f800000);
+    // largest x such that count(v >= x) >= m
+    unsigned int prefix = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned int cand = prefix | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < kGemmMaxSampleTiles / 32; ++i) c += (v[i] >= cand) ? 1 : 0;
+        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (c >= m) prefix = cand;
+    }
+    if (lane == 0) {
+        thr[qi] = qi < q ? image_score(prefix) : __int_as_float(0x7f800000);
         cnt[qi] = 0u;
     }
 }
@@ -410,13 +409,14 @@ __global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, 
 // d_sel [q][kp] approx keys (descending, zero padded) in; d_exact [q][kp] exact keys out.
 __global__ void __launch_bounds__(256)
     rescore_kernel(const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_slot_base, int nseg, int dims,
-                   uint32_t cap_rows, const float *__restrict__ queries, int kp,
+                   const unsigned int *__restrict__ d_cnt, const float *__restrict__ queries, int kp,
                    const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact)
 {
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int qi = blockIdx.y;
     if (w >= kp) return;
+    if (d_cnt != nullptr && (unsigned)w >= d_cnt[qi]) return;  // unsorted candidate buffer: only cnt entries are valid
     const unsigned long long key = d_sel[(size_t)qi * kp + w];
     if (key == 0ull) {
         if (lane == 0) d_exact[(size_t)qi * kp + w] = 0ull;
@@ -429,7 +429,6 @@ __global__ void __launch_bounds__(256)
         int mid = (lo + hi + 1) >> 1;
         if (seg_slot_base[mid] <= slot) lo = mid; else hi = mid - 1;
     }
-    (void)cap_rows;
     const float *x = segs[lo].base + (size_t)(slot - seg_slot_base[lo]) * dims;
     const float *qv = queries + (size_t)qi * dims;
     float p[4] = {0.f, 0.f, 0.f, 0.f};
@@ -444,49 +443,92 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) d_exact[(size_t)qi * kp + w] = make_key(sc, slot);
 }
 
-// per query: sort the kp exact keys, emit the best K, and certify: the K-th exact score must beat
-// everything a non-candidate row could reach (bound = approx ceiling of the non-candidates + error).
-__global__ void __launch_bounds__(256)
-    finalize_kernel(const unsigned long long *__restrict__ d_exact, const unsigned long long *__restrict__ d_sel,
-                    const unsigned int *__restrict__ cnt, const float *__restrict__ thr, unsigned int cap, int kp,
-                    int K, long long rows_total, const float *__restrict__ qnorm2,
-                    const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
-                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags)
+// Best K of up to kGemmCandCap keys held 16 per thread (256 threads), written sorted (descending,
+// zero padded to a power of two) to `out` in shared memory; returns how many keys were kept (>= min(K, n);
+// more only when scores tie at the cut).  MSB-first radix select on the 32-bit score image finds the
+// cut in 32 counting steps, then only the survivors are bitonic-sorted -- a full sort of ~1000
+// candidates per query was the slowest small kernel of the tensor path.
+__device__ int block_topk_256(const unsigned long long (&mine)[kGemmCandCap / 256], int K, unsigned long long *out,
+                              int *s_cnt)
 {
-    __shared__ unsigned long long buf[1024];
-    const int qi = blockIdx.x;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) buf[i] = i < kp ? d_exact[(size_t)qi * kp + i] : 0ull;
+    constexpr int R = kGemmCandCap / 256;
+    unsigned int prefix = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned int cand = prefix | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) c += (mine[i] != 0ull && (unsigned int)(mine[i] >> 32) >= cand) ? 1 : 0;
+        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (threadIdx.x == 0) *s_cnt = 0;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(s_cnt, c);
+        __syncthreads();
+        if (*s_cnt >= K) prefix = cand;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *s_cnt = 0;
     __syncthreads();
-    for (int k = 2; k <= 1024; k <<= 1) {
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if (mine[i] != 0ull && (unsigned int)(mine[i] >> 32) >= prefix) out[atomicAdd(s_cnt, 1)] = mine[i];
+    __syncthreads();
+    const int m = *s_cnt;
+    int np = 2;
+    while (np < m || np < K) np <<= 1;
+    for (int i = m + threadIdx.x; i < np; i += blockDim.x) out[i] = 0ull;
+    __syncthreads();
+    for (int k = 2; k <= np; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            for (int i = threadIdx.x; i < np; i += blockDim.x) {
                 int ixj = i ^ j;
                 if (ixj > i) {
-                    unsigned long long x = buf[i], y = buf[ixj];
+                    unsigned long long x = out[i], y = out[ixj];
                     bool desc = ((i & k) == 0);
                     if (desc ? (x < y) : (x > y)) {
-                        buf[i] = y;
-                        buf[ixj] = x;
+                        out[i] = y;
+                        out[ixj] = x;
                     }
                 }
             }
             __syncthreads();
         }
     }
+    return m;
+}
+
+// per query: sort the re-scored keys, emit the best K, and certify: the K-th exact score must beat
+// everything a row outside the re-scored set could reach (its approx ceiling + the TF32 error bound).
+//   all == 0: d_exact [q][kp] holds the best kp candidates by approx score (select_kernel)
+//   all == 1: d_exact [q][kp = cap] holds ALL min(cnt, cap) collected candidates
+__global__ void __launch_bounds__(256)
+    finalize_kernel(const unsigned long long *__restrict__ d_exact, const unsigned long long *__restrict__ d_sel,
+                    const unsigned int *__restrict__ cnt, const float *__restrict__ thr, unsigned int cap, int kp,
+                    int all, int K, long long rows_total, const float *__restrict__ qnorm2,
+                    const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
+                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags)
+{
+    __shared__ unsigned long long buf[kGemmCandCap];
+    __shared__ int s_cnt;
+    const int qi = blockIdx.x;
+    const unsigned int n = cnt[qi];
+    const int valid = all ? (int)(n < cap ? n : cap) : (int)((unsigned)kp < n ? (unsigned)kp : n);
+    unsigned long long mine[kGemmCandCap / 256];
+#pragma unroll
+    for (int i = 0; i < kGemmCandCap / 256; ++i) {
+        const int idx = threadIdx.x + 256 * i;
+        mine[i] = idx < valid ? d_exact[(size_t)qi * kp + idx] : 0ull;
+    }
+    block_topk_256(mine, K, buf, &s_cnt);
     for (int i = threadIdx.x; i < K; i += blockDim.x) d_out[(size_t)qi * K + i] = buf[i];
     if (threadIdx.x == 0) {
-        const unsigned int n = cnt[qi];
         const long long keff = rows_total < K ? rows_total : K;
         bool ok = true;
-        if (n > cap) ok = false;                       // candidate buffer overflowed: the selection saw a subset
-        if ((long long)n < keff) ok = false;           // threshold too high: not even K candidates
-        if (ok && (long long)n < rows_total) {         // some rows were never candidates
-            // approx ceiling of every row outside the re-scored set
-            float ceil_approx = thr[qi];
-            if (n > (unsigned)kp) {
-                const unsigned long long last = d_sel[(size_t)qi * kp + kp - 1];
-                ceil_approx = fmaxf(ceil_approx, key_score(last));
-            }
+        if (n > cap) ok = false;               // candidate buffer overflowed: the selection saw a subset
+        if ((long long)n < keff) ok = false;   // threshold too high: not even K candidates
+        if (ok && (long long)n < rows_total) { // some rows were never re-scored
+            float ceil_approx = thr[qi];       // rows that were never collected have approx <= thr
+            if (!all && n > (unsigned)kp)      // collected but not among the best kp by approx score
+                ceil_approx = fmaxf(ceil_approx, key_score(d_sel[(size_t)qi * kp + kp - 1]));
             const float delta = err_coeff * sqrtf(__uint_as_float(*maxnorm2_bits)) * sqrtf(qnorm2[qi]);
             const unsigned long long kth = buf[keff - 1];
             if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
@@ -495,39 +537,23 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// best kp keys of an unsorted candidate buffer: one CTA per query, bitonic sort in shared memory
-__global__ void __launch_bounds__(512)
+// best kp keys of an unsorted candidate buffer: one CTA per query
+__global__ void __launch_bounds__(256)
     select_kernel(const unsigned long long *__restrict__ d_cand, const unsigned int *__restrict__ d_cnt,
                   unsigned int cap, int kp, unsigned long long *__restrict__ d_sel)
 {
     __shared__ unsigned long long buf[kGemmCandCap];
+    __shared__ int s_cnt;
     const int qi = blockIdx.x;
     unsigned int n = d_cnt[qi];
     if (n > cap) n = cap;
-    int np = 2;
-    while ((unsigned)np < n) np <<= 1;
-    if (np < kp) {
-        np = 2;
-        while (np < kp) np <<= 1;
+    unsigned long long mine[kGemmCandCap / 256];
+#pragma unroll
+    for (int i = 0; i < kGemmCandCap / 256; ++i) {
+        const unsigned idx = threadIdx.x + 256 * i;
+        mine[i] = idx < n ? d_cand[(size_t)qi * cap + idx] : 0ull;
     }
-    for (int i = threadIdx.x; i < np; i += blockDim.x) buf[i] = (unsigned)i < n ? d_cand[(size_t)qi * cap + i] : 0ull;
-    __syncthreads();
-    for (int k = 2; k <= np; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long x = buf[i], y = buf[ixj];
-                    bool desc = ((i & k) == 0);
-                    if (desc ? (x < y) : (x > y)) {
-                        buf[i] = y;
-                        buf[ixj] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    block_topk_256(mine, kp, buf, &s_cnt);
     for (int i = threadIdx.x; i < kp; i += blockDim.x) d_sel[(size_t)qi * kp + i] = buf[i];
 }
 
@@ -623,9 +649,9 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
 }
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
-                                float *dst, float *qnorm2, cudaStream_t stream)
+                                float *dst, float *qnorm2, float *copy, cudaStream_t stream)
 {
-    prep_queries_kernel<<<nq, 128, 0, stream>>>(src, q_stride, l_stride, q, nq, dims, dst, qnorm2);
+    prep_queries_kernel<<<nq, 128, 0, stream>>>(src, q_stride, l_stride, q, nq, dims, dst, qnorm2, copy);
     return cudaGetLastError();
 }
 
@@ -639,8 +665,8 @@ cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsign
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
                              unsigned int *d_cnt, cudaStream_t stream)
 {
-    if (ntiles > 1024 || ntiles < 1) return cudaErrorInvalidValue;
-    threshold_kernel<<<nq, 256, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+    if (ntiles > kGemmMaxSampleTiles || ntiles < 1) return cudaErrorInvalidValue;
+    threshold_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
     return cudaGetLastError();
 }
 
@@ -648,16 +674,16 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
                           unsigned long long *d_sel, cudaStream_t stream)
 {
     if (cap > (unsigned)kGemmCandCap || kp > kGemmCandCap) return cudaErrorInvalidValue;
-    select_kernel<<<q, 512, 0, stream>>>(d_cand, d_cnt, cap, kp, d_sel);
+    select_kernel<<<q, 256, 0, stream>>>(d_cand, d_cnt, cap, kp, d_sel);
     return cudaGetLastError();
 }
 
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
                            const float *d_queries_padded, int kp, const unsigned long long *d_sel,
-                           unsigned long long *d_exact, cudaStream_t stream)
+                           const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream)
 {
     dim3 grid((kp * 32 + 255) / 256, q);
-    rescore_kernel<<<grid, 256, 0, stream>>>(d_segs, d_seg_slot_base, nseg, dims, 0, d_queries_padded, kp, d_sel,
+    rescore_kernel<<<grid, 256, 0, stream>>>(d_segs, d_seg_slot_base, nseg, dims, d_cnt, d_queries_padded, kp, d_sel,
                                              d_exact);
     return cudaGetLastError();
 }
@@ -665,10 +691,11 @@ cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_bas
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
                             const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
-                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, cudaStream_t stream)
+                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, int all,
+                            cudaStream_t stream)
 {
-    if (kp > 1024 || K > kp) return cudaErrorInvalidValue;
-    finalize_kernel<<<q, 256, 0, stream>>>(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, rows_total, d_qnorm2,
+    if (kp > kGemmCandCap || K > kp) return cudaErrorInvalidValue;
+    finalize_kernel<<<q, 256, 0, stream>>>(d_exact, d_sel, d_cnt, d_thr, cap, kp, all, K, rows_total, d_qnorm2,
                                            d_maxnorm2_bits, err_coeff, d_out, d_flags);
     return cudaGetLastError();
 }

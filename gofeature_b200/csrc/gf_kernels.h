@@ -57,7 +57,7 @@ cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, u
 // Merge `lists` lists of K keys per (group, query): d_in [groups][lists][q][K] -> d_out [groups][q][K]
 // (descending, zero padded).
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
-                         unsigned long long *d_out, cudaStream_t stream);
+                         unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count = nullptr);
 
 // ---- tcgen05 contraction path (gf_gemm.cu) ----
 constexpr int kGemmMaxQ = 256;       // queries per pass (N of the MMA)
@@ -89,7 +89,7 @@ struct GemmLaunch {
 int gemm_pad_queries(int q);
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
-                                float *dst, float *qnorm2, cudaStream_t stream);
+                                float *dst, float *qnorm2, float *copy, cudaStream_t stream);
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
@@ -99,12 +99,13 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
                           unsigned long long *d_sel, cudaStream_t stream);
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
                            const float *d_queries_padded, int kp, const unsigned long long *d_sel,
-                           unsigned long long *d_exact, cudaStream_t stream);
+                           const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream);
 // d_flags[qi] = 1 when query qi could not be certified (it must be re-run by the exact scan)
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
                             const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
-                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, cudaStream_t stream);
+                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, int all,
+                            cudaStream_t stream);
 
 constexpr int kFixupMaxQ = 8;  // uncertified queries one device-side fix-up scan pass can take
 cudaError_t compact_failed_launch(unsigned int *d_flags, int q, int maxn, int *d_map, unsigned int *d_count,

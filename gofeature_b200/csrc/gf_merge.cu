@@ -43,8 +43,10 @@ __device__ __forceinline__ int pow2_at_least(int v)
 
 // grid (q, groups); d_in [groups][lists][q][K]; d_out [groups][q][K]
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const unsigned long long *__restrict__ d_in, int lists,
-                                                             int q, int K, unsigned long long *__restrict__ d_out)
+                                                             int q, int K, unsigned long long *__restrict__ d_out,
+                                                             const unsigned int *__restrict__ d_q_count)
 {
+    if (d_q_count != nullptr && (unsigned)blockIdx.x >= *d_q_count) return;  // fix-up pass with fewer live queries
     __shared__ unsigned long long buf[kMergeBuf];
     __shared__ unsigned long long red[kMergeThreads / 32];
     __shared__ unsigned long long s_tau;
@@ -247,11 +249,11 @@ cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, un
 }
 
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
-                         unsigned long long *d_out, cudaStream_t stream)
+                         unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count)
 {
     if (K < 1 || K > kMaxK || q < 1 || lists < 1 || groups < 1) return cudaErrorInvalidValue;
     dim3 grid(q, groups);
-    merge_kernel<<<grid, kMergeThreads, 0, stream>>>(d_in, lists, q, K, d_out);
+    merge_kernel<<<grid, kMergeThreads, 0, stream>>>(d_in, lists, q, K, d_out, d_q_count);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gf_device.cuh"
@@ -813,7 +814,8 @@ bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long lo
     if (K > 512) return false;                               // K' = K + slack must fit the 1024-key re-score
     if (total_gtiles < 2 * 256) return false;                // small sets: the sample would be the set
     if (path == 2) return true;
-    return q > scan_max_q(dims);                             // one scan pass cannot hold the batch
+    // one scan pass cannot hold the batch, or K is beyond what the per-CTA sorted lists do cheaply
+    return q > scan_max_q(dims) || K > 32;
 }
 
 int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
@@ -838,7 +840,9 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const int kp = std::min(1024, std::max(K + 32, K + K / 2));
     const unsigned cap = kGemmCandCap;
     // sample: G strided tiles; threshold = m-th largest tile maximum so that ~target rows pass
-    int G = (int)std::min<uint32_t>(kGemmMaxSampleTiles, std::max<uint32_t>(256, total_gtiles / 32));
+    // whole waves of the grid: one tile per SM on a 1 M-row set, up to 6 on the largest
+    int waves = (int)std::max<uint32_t>(1, std::min<uint32_t>(6, total_gtiles / (48u * (uint32_t)ctx->sms)));
+    int G = std::min(kGemmMaxSampleTiles, waves * ctx->sms);
     G = (int)std::min<uint32_t>((uint32_t)G, total_gtiles);
     const uint32_t stride = total_gtiles / (uint32_t)G;
     const double target = std::max(1024.0, 4.0 * kp);
@@ -859,7 +863,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_cnt = carve((size_t)nq_max * 4);
     const size_t o_cand = carve((size_t)nq_max * cap * 8);
     const size_t o_sel = carve((size_t)nq_max * kp * 8);
-    const size_t o_exact = carve((size_t)nq_max * kp * 8);
+    const size_t o_exact = carve((size_t)nq_max * std::max<size_t>((size_t)kp, nq_max <= 32 ? (size_t)cap : 0) * 8);
     const size_t o_flags = carve((size_t)q * 4);
     const size_t o_map = carve((size_t)kFixupMaxQ * 4);
     const size_t o_count = carve(4);
@@ -897,23 +901,35 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     g.d_tilemax = d_tmax;
     g.sms = ctx->sms;
 
+    static const bool stage_timing = getenv("GF_STAGE_TIMING") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() {
+        if (!stage_timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        evs.push_back(e);
+    };
     for (int p0 = 0; p0 < q; p0 += kGemmMaxQ) {
         const int qp = std::min(kGemmMaxQ, q - p0);
         const int nq = gemm_pad_queries(qp);
         g.nq = nq;
         g.q = qp;
+        mark();
         GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad, d_qn,
-                                    stream),
+                                    d_qall + (size_t)p0 * dims, stream),
                 GF_ERR_CUDA);
-        GF_CUDA(cudaMemcpyAsync(d_qall + (size_t)p0 * dims, d_qpad, (size_t)qp * dims * 4, cudaMemcpyDeviceToDevice,
-                                stream),
-                GF_ERR_CUDA);
+        // small batches: re-score EVERY collected candidate (~1000 rows per query) and skip the selection
+        const bool all = (size_t)qp * (size_t)target * (size_t)dims * 4 <= ((size_t)64 << 20);
+        mark();
         g.mode = kGemmTileMax;
         g.tile_first = 0;
         g.tile_stride = stride;
         g.tile_count = (uint32_t)G;
         GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
+        mark();
         GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
+        mark();
         g.mode = kGemmCollect;
         g.tile_stride = 1;
         g.tile_count = total_gtiles;
@@ -924,12 +940,28 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             ctx->prof_end(stream, ev, true);
             if (le != cudaSuccess) return cuda_fail(le, "gemm_launch", GF_ERR_CUDA);
         }
-        GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
-        GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp, d_sel, d_exact, stream),
-                GF_ERR_CUDA);
-        GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, qp, scanned_rows, d_qn, d_small,
-                                kTf32ErrCoeff, d_out + (size_t)p0 * K, d_fl + p0, stream),
-                GF_ERR_CUDA);
+        mark();
+        if (all) {
+            mark();
+            GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, (int)cap, d_cand, d_cnt, d_exact,
+                                   stream),
+                    GF_ERR_CUDA);
+            mark();
+            GF_CUDA(finalize_launch(d_exact, d_cand, d_cnt, d_thr, cap, (int)cap, K, qp, scanned_rows, d_qn, d_small,
+                                    kTf32ErrCoeff, d_out + (size_t)p0 * K, d_fl + p0, 1, stream),
+                    GF_ERR_CUDA);
+        } else {
+            GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
+            mark();
+            GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp, d_sel, nullptr, d_exact,
+                                   stream),
+                    GF_ERR_CUDA);
+            mark();
+            GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, qp, scanned_rows, d_qn, d_small,
+                                    kTf32ErrCoeff, d_out + (size_t)p0 * K, d_fl + p0, 0, stream),
+                    GF_ERR_CUDA);
+        }
+        mark();
         ctx->stats.gemm_launches += 2;
         ctx->stats.other_launches += 5;
         ctx->stats.tensor_passes++;
@@ -943,6 +975,19 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     if (rc) return rc;
     GF_CUDA(scatter_fix_launch(d_fix, d_map, d_count, fixq, K, d_out, stream), GF_ERR_CUDA);
     ctx->stats.other_launches += 2;
+    mark();
+    if (stage_timing && !evs.empty()) {
+        cudaEventSynchronize(evs.back());
+        static const char *names[] = {"prep+copy", "tilemax", "threshold", "collect", "select", "rescore", "finalize", "fixup"};
+        fprintf(stderr, "[stage us]");
+        for (size_t i = 0; i + 1 < evs.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+            fprintf(stderr, " %s=%.1f", names[i % 8], ms * 1e3);
+        }
+        fprintf(stderr, "\n");
+        for (auto e : evs) cudaEventDestroy(e);
+    }
     if (d_flags)
         GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream),
                 GF_ERR_CUDA);
@@ -975,7 +1020,8 @@ int Set::topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, i
         if (le != cudaSuccess) return cuda_fail(le, "scan_launch", GF_ERR_CUDA);
         ctx->stats.scan_launches++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
-        GF_CUDA(merge_launch(d_partial, plan.groups, plan.grid_x, qp, K, d_out + out_off, stream), GF_ERR_CUDA);
+        GF_CUDA(merge_launch(d_partial, plan.groups, plan.grid_x, qp, K, d_out + out_off, stream, d_q_count),
+                GF_ERR_CUDA);
         ctx->stats.merge_launches++;
         out_off += (size_t)plan.groups * qp * K;
     }
