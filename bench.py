@@ -295,6 +295,22 @@ def run_ours(args, rank, world, local_rank):
         s1 = ctx.Stats()
         ctx.SetProfiling(False)
         q1_ms = s1["scan_kernel_ns"] / 1e6 / max(s1["scan_kernel_timed"], 1)
+    # ---- config[1] exactly as written: 10 concurrent host threads, one query each, through the C ABI
+    # (tools/gf_demo, the counterpart of the reference's demo/main.go), request coalescing on
+    demo = None
+    if world == 1 and rank == 0:
+        exe = os.path.join(ROOT, "tools", "gf_demo")
+        if os.path.exists(exe):
+            cache.Close()      # give the memory back: the tool builds its own 1 M-row set
+            cache = None
+            try:
+                out = subprocess.run([exe, "--rows", str(args.rows_per_gpu), "--threads", str(Q), "--rounds",
+                                      str(max(args.steps, 50)), "--limit", str(K), "--coalesce-us", "100",
+                                      "--device", str(local_rank)], capture_output=True, text=True, timeout=300)
+                if out.returncode == 0:
+                    demo = json.loads(out.stdout.strip().splitlines()[-1])
+            except Exception as exc:  # the bench line must still come out
+                demo = {"error": str(exc)}
     if sampler:
         sampler.stop()
 
@@ -318,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_user * world, "unit": UNIT, "h2d_bytes_per_step": Q * DIMS * 4,
                 "d2h_bytes_per_step": Q * K * 8, "qps_user": e2e_user, "ms_per_step": e2e_ms / args.steps,
                 "p50_ms": lat_ms[len(lat_ms) // 2], "p99_ms": lat_ms[min(len(lat_ms) - 1, int(len(lat_ms) * 0.99))],
-                "call": "gf_set_search(q=%d)" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q},
+                "call": "one gf_set_search(q=%d) per step" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q},
         "gpu_launches": int(launches), "tensor_passes": stats["tensor_passes"],
         "uncertified_queries": stats["uncertified_queries"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -329,6 +345,19 @@ def run_ours(args, rank, world, local_rank):
                      "frac_of_nominal_8000": achieved / 8000.0},
         "clocks": sampler.summary(t_mark0, t_mark1) if sampler else None,
     }
+    if demo and "qps" in demo:
+        # the headline end-to-end number: 10 real concurrent callers, host buffers, coalesced by the library
+        line["e2e_batched_call"] = line["e2e"]
+        line["e2e"] = {"value": demo["qps"], "unit": UNIT,
+                       "h2d_bytes_per_step": int(demo["h2d_bytes"] / max(demo["searches"], 1) * Q),
+                       "d2h_bytes_per_step": int(demo["d2h_bytes"] / max(demo["searches"], 1) * Q),
+                       "qps_user": demo["qps"], "ms_per_step": demo["wall_ms"] / demo["rounds"],
+                       "p50_ms": demo["p50_ms"], "p99_ms": demo["p99_ms"],
+                       "call": "%d host threads x gf_set_search(q=1), coalescing 100 us (tools/gf_demo)" % Q,
+                       "coalesced_batches": demo["coalesced_batches"], "tensor_passes": demo["tensor_passes"],
+                       "self_check": demo["self_check"]}
+    elif demo:
+        line["e2e_parallel_error"] = demo
     if world == 1:
         l1 = sorted(x * 1e3 for x in lat1)
         b1 = rows_local * DIMS * 4 + DIMS * 4 + K * 8
@@ -341,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
                                  args.rows_per_gpu)
             line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
-    cache.Close()
+    if cache is not None:
+        cache.Close()
     ctx.Close()
     if world > 1:
         dist.destroy_process_group()

@@ -7,6 +7,7 @@
 #include "gf_runtime.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1268,7 +1269,102 @@ int Set::search(float threshold, int limit, int q, const uint8_t *queries, Resul
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (q > batch) return GF_ERR_OUT_OF_BATCH;  // set.go:119-122
+    if (coalesce_wait_us > 0 && q > 0 && limit > 0) return search_coalesced(threshold, limit, q, queries, out);
     return search_now(threshold, limit, q, queries, out);
+}
+
+// The analogue of the reference's SearchQueue (set.go:36, cache.go:61: every Search of a set feeds
+// one channel).  Concurrent callers are folded into ONE pass over the rows: the first caller to
+// arrive leads, waits at most coalesce_wait_us for company, runs the concatenated batch (same limit)
+// with no threshold, and hands every follower its slice with its own threshold applied
+// (set.go:145 filters after selection, so filtering a shared top-limit is exact).  While a batch
+// runs, new callers queue up and form the next batch.
+int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *queries, Result **out)
+{
+    PendingSearch me;
+    me.queries = queries;
+    me.q = q;
+    me.limit = limit;
+    me.threshold = threshold;
+    const size_t qbytes = (size_t)dims * precision;
+    static thread_local const Set *tl_set = nullptr;
+    static thread_local uint64_t tl_batch = 0;
+    std::unique_lock<std::mutex> lk(co_mu);
+    me.returnee = (tl_set == this && tl_batch == co_batch_id && co_batch_id != 0);
+    co_queue.push_back(&me);
+    co_cv.notify_all();  // a waiting leader re-counts its company
+    while (!me.done) {
+        if (co_leader_active) {  // someone else is leading: wait to be served (or to take over)
+            co_cv.wait(lk);
+            continue;
+        }
+        co_leader_active = true;
+        // How many callers to expect: everybody served by the previous batch is about to come back,
+        // plus whoever queued up meanwhile and was not in it.  Wait for them, but never longer than
+        // coalesce_wait_us: two half-size batches alternating cost twice the HBM traffic of one.
+        {
+            int fresh = 0;
+            for (PendingSearch *p : co_queue) fresh += p->returnee ? 0 : 1;
+            const size_t target = (size_t)co_last_group + (size_t)fresh;
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(coalesce_wait_us);
+            while (co_queue.size() < target && co_cv.wait_until(lk, deadline) != std::cv_status::timeout) {
+            }
+        }
+        // take every queued request with my limit, up to 256 queries
+        std::vector<PendingSearch *> group;
+        int total = 0;
+        for (auto it = co_queue.begin(); it != co_queue.end();) {
+            PendingSearch *p = *it;
+            if (p->limit == me.limit && (p == &me || total + p->q <= kGemmMaxQ)) {
+                group.push_back(p);
+                total += p->q;
+                it = co_queue.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        std::vector<uint8_t> flat((size_t)total * qbytes);
+        size_t off = 0;
+        for (PendingSearch *p : group) {
+            memcpy(flat.data() + off, p->queries, (size_t)p->q * qbytes);
+            off += (size_t)p->q * qbytes;
+        }
+        Result *all = nullptr;
+        int rc = search_now(-INFINITY, limit, total, flat.data(), &all);
+        if (group.size() > 1) ctx->stats.coalesced_batches++;
+        int q0 = 0;
+        for (PendingSearch *p : group) {
+            p->rc = rc;
+            if (rc == GF_OK) {
+                Result *r = new Result();
+                r->begin(p->q);
+                for (int i = 0; i < p->q; ++i) {
+                    for (int64_t k = all->offsets[q0 + i]; k < all->offsets[q0 + i + 1]; ++k) {
+                        if (!(all->scores[k] >= p->threshold)) continue;  // set.go:145
+                        r->push(all->scores[k], all->slots[k],
+                                all->id_bytes.substr(all->id_off[k], all->id_off[k + 1] - all->id_off[k]));
+                    }
+                    r->end_query();
+                }
+                p->result = r;
+            }
+            q0 += p->q;
+        }
+        delete all;
+        lk.lock();
+        ++co_batch_id;
+        co_last_group = (int)group.size();
+        for (PendingSearch *p : group) p->done = true;
+        co_leader_active = false;
+        co_cv.notify_all();
+    }
+    tl_set = this;
+    tl_batch = co_batch_id;  // approximately: the batch that served me is the latest or close to it
+    lk.unlock();
+    if (me.rc) return me.rc;
+    *out = me.result;
+    return GF_OK;
 }
 
 int Set::search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,

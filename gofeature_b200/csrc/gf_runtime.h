@@ -183,7 +183,17 @@ struct gf_block {
 };
 
 namespace gf {
-struct PendingSearch;
+// one caller of gf_set_search waiting to be served by a coalesced scan pass
+struct PendingSearch {
+    const uint8_t *queries;
+    int q;
+    int limit;
+    float threshold;
+    gf::Result *result = nullptr;
+    int rc = 0;
+    bool done = false;
+    bool returnee = false;  // this thread was served by the immediately preceding batch
+};
 }
 
 struct gf_set {
@@ -222,6 +232,8 @@ struct gf_set {
     std::condition_variable co_cv;
     std::vector<gf::PendingSearch *> co_queue;
     bool co_leader_active = false;
+    uint64_t co_batch_id = 0;   // batches served so far
+    int co_last_group = 0;      // requests in the last batch
 
     uint32_t slot_base_of(int block_pos) const
     {
@@ -235,6 +247,7 @@ struct gf_set {
     int read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<uint8_t> &found);
     int search(float threshold, int limit, int q, const uint8_t *queries, Result **out);
     int search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out);
+    int search_coalesced(float threshold, int limit, int q, const uint8_t *queries, Result **out);
     int search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
                       cudaStream_t stream);
     int resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out);
