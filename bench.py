@@ -300,6 +300,9 @@ def run_ours(args, rank, world, local_rank):
     demo = None
     if world == 1 and rank == 0:
         exe = os.path.join(ROOT, "tools", "gf_demo")
+        if not os.path.exists(exe):
+            subprocess.call(["make", "-C", os.path.join(ROOT, "tools")], stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL)
         if os.path.exists(exe):
             cache.Close()      # give the memory back: the tool builds its own 1 M-row set
             cache = None

@@ -111,6 +111,12 @@ def lib():
     """The loaded C-ABI library.  Raises if it has not been built (no fallback)."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and os.environ.get("GF_NO_AUTOBUILD") is None:
+            # a fresh checkout has sources only: compile the CUDA library in-tree (nvcc, sm_100a).  This is a
+            # build step, not a fallback -- if it fails the import fails.
+            import subprocess
+            subprocess.call(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL)
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 "gofeature_b200: %s is missing -- build it with __graft_entry__.build() "

@@ -236,6 +236,28 @@ void Context::prof_collect()
     prof_free.insert(prof_free.end(), todo2.begin(), todo2.end());
 }
 
+int Context::upload_scatter(uint8_t *base, const int *slots, size_t n, size_t rowb, const uint8_t *src)
+{
+    if (n == 0) return GF_OK;
+    std::lock_guard<std::mutex> g(stage_mu);
+    const size_t per = std::max<size_t>(1, stage_bytes / rowb);
+    int k = 0;
+    for (size_t r0 = 0; r0 < n; r0 += per, ++k) {
+        const size_t cnt = std::min(per, n - r0);
+        const int i = k & 1;
+        GF_CUDA(cudaEventSynchronize(stage_ev[i]), GF_ERR_WRITE_CUDA_BUFFER);
+        memcpy(stage[i], src + r0 * rowb, cnt * rowb);
+        for (size_t j = 0; j < cnt; ++j)
+            GF_CUDA(cudaMemcpyAsync(base + (size_t)slots[r0 + j] * rowb, stage[i] + j * rowb, rowb,
+                                    cudaMemcpyHostToDevice, mut_stream),
+                    GF_ERR_WRITE_CUDA_BUFFER);
+        GF_CUDA(cudaEventRecord(stage_ev[i], mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+    }
+    GF_CUDA(cudaStreamSynchronize(mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+    stats.h2d_bytes += n * rowb;
+    return GF_OK;
+}
+
 Context::~gf_context()
 {
     cudaSetDevice(device);
@@ -289,10 +311,23 @@ std::string Block::id_at(int row) const
     return ids[row];
 }
 
-void Block::index_add(const std::string &id, int row) { id_index[id].push_back(row); }
+void Block::index_add(const std::string &id, int row)
+{
+    if (use_index) id_index[id].push_back(row);
+}
+
+void Block::rebuild_index()
+{
+    id_index.clear();
+    use_index = true;
+    if (implicit_ids) return;
+    for (int r = 0; r < next_index; ++r)
+        if (live[r]) id_index[ids[r]].push_back(r);
+}
 
 void Block::index_del(const std::string &id, int row)
 {
+    if (!use_index) return;
     auto it = id_index.find(id);
     if (it == id_index.end()) return;
     auto &v = it->second;
@@ -312,6 +347,11 @@ int Block::find_last(const std::string &id) const
         long long row = ord - id_first;
         if (row < 0 || row >= next_index || !live[row]) return -1;
         return (int)row;
+    }
+    if (!use_index) {  // no per-block index: the reference's own linear scan, last match wins (block.go:140-144)
+        for (int r = next_index - 1; r >= 0; --r)
+            if (live[r] && ids[r] == id) return r;
+        return -1;
     }
     auto it = id_index.find(id);
     if (it == id_index.end() || it->second.empty()) return -1;
@@ -345,6 +385,7 @@ int Block::acquire(const std::string &owner_, int dims_, int precision_, int bat
     live.assign((size_t)capacity(), 0);
     live_count = 0;
     implicit_ids = false;
+    use_index = true;
     id_index.clear();
     empty.clear();
     next_index = 0;
@@ -386,10 +427,12 @@ int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::strin
     const size_t rowb = (size_t)dims * precision;
     const size_t nempty = empty.size();
     const size_t refill = std::min(nempty, (size_t)n);
+    if (refill > 0) {
+        rc = ctx->upload_scatter(dev, empty.data(), refill, rowb, values);
+        if (rc) return GF_ERR_WRITE_CUDA_BUFFER;
+    }
     for (size_t i = 0; i < refill; ++i) {
         int slot = empty[i];
-        rc = ctx->upload(dev + (size_t)slot * rowb, values + i * rowb, rowb);
-        if (rc) return GF_ERR_WRITE_CUDA_BUFFER;
         ids[slot] = ids_[i];
         live[slot] = 1;
         ++live_count;
@@ -464,11 +507,13 @@ int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &fo
     if (rc) return rc;
     const size_t rowb = (size_t)dims * precision;
     bool any = false;
+    // targets is a map: a repeated id is looked up once (block.go:136-139)
+    std::unordered_map<std::string, size_t> first;
+    first.reserve(ids_.size() * 2);
+    for (size_t i = 0; i < ids_.size(); ++i) first.emplace(ids_[i], i);
     for (size_t i = 0; i < ids_.size(); ++i) {
         if (found[i]) continue;
-        bool dup = false;  // targets is a map: a repeated id is looked up once (block.go:136-139)
-        for (size_t j = 0; j < i && !dup; ++j) dup = (ids_[j] == ids_[i]);
-        if (dup) continue;
+        if (first[ids_[i]] != i) continue;
         int row = find_last(ids_[i]);
         if (row < 0) continue;
         GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
@@ -486,7 +531,112 @@ int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &fo
     return GF_OK;
 }
 
+int Block::remove_rows(const std::vector<int> &rows)
+{
+    if (rows.empty()) return GF_OK;
+    std::lock_guard<std::mutex> g(mu);
+    Context *ctx = cache->ctx;
+    const size_t rowb = (size_t)dims * precision;
+    for (int row : rows) {
+        if (row < 0 || row >= next_index || !live[row]) continue;
+        GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+        if (!implicit_ids) {
+            index_del(ids[row], row);
+            ids[row].clear();
+        }
+        live[row] = 0;
+        --live_count;
+        empty.push_back(row);
+    }
+    return GF_OK;
+}
+
 // ------------------------------------------------------------------ Set
+bool Set::find_implicit(const std::string &id, int *pos, int *row) const
+{
+    if (implicit_ranges.empty()) return false;
+    const size_t pl = implicit_prefix.size();
+    if (id.size() != pl + 11 || id.compare(0, pl, implicit_prefix) != 0) return false;
+    int64_t ord = 0;
+    for (size_t i = pl; i < id.size(); ++i) {
+        if (id[i] < '0' || id[i] > '9') return false;
+        ord = ord * 10 + (id[i] - '0');
+    }
+    size_t lo = 0, hi = implicit_ranges.size();
+    while (lo < hi) {  // last range with first <= ord
+        size_t mid = (lo + hi) / 2;
+        if (implicit_ranges[mid].first <= ord) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return false;
+    const ImplicitRange &r = implicit_ranges[lo - 1];
+    if (ord >= r.first + r.count) return false;
+    const Block *b = blocks[r.pos];
+    const int rr = (int)(ord - r.first);
+    if (!b->implicit_ids || rr >= b->next_index || !b->live[rr]) return false;
+    *pos = r.pos;
+    *row = rr;
+    return true;
+}
+
+// First block (Set.Blocks order) holding the id, last row inside it (set.go:167-170, block.go:140-144).
+bool Set::find(const std::string &id, int *pos, int *row) const
+{
+    if (has_dups) {
+        for (size_t p = 0; p < blocks.size(); ++p) {
+            int r = blocks[p]->find_last(id);
+            if (r >= 0) {
+                *pos = (int)p;
+                *row = r;
+                return true;
+            }
+        }
+        return false;
+    }
+    if (find_implicit(id, pos, row)) return true;
+    auto it = loc.find(id);
+    if (it == loc.end()) return false;
+    *pos = (int)(it->second >> 32);
+    *row = (int)(it->second & 0xffffffffu);
+    return true;
+}
+
+void Set::enter_dup_mode()
+{
+    if (has_dups) return;
+    has_dups = true;  // ids are not unique: fall back to the reference's block-by-block walk
+    loc.clear();
+    for (Block *b : blocks) b->rebuild_index();
+}
+
+void Set::note_id(const std::string &id, int pos, int row)
+{
+    if (has_dups) return;
+    int p, r;
+    if (find_implicit(id, &p, &r) || !loc.emplace(id, ((uint64_t)pos << 32) | (uint32_t)row).second) enter_dup_mode();
+}
+
+// an implicit-id block is about to take arbitrary ids: give it explicit ids and move them to the locator
+void Set::materialize_block(int pos)
+{
+    Block *b = blocks[pos];
+    if (!b->implicit_ids) return;
+    b->materialize_ids();
+    for (size_t i = 0; i < implicit_ranges.size(); ++i)
+        if (implicit_ranges[i].pos == pos) {
+            implicit_ranges.erase(implicit_ranges.begin() + i);
+            break;
+        }
+    if (has_dups) {
+        b->rebuild_index();
+        return;
+    }
+    for (int r = 0; r < b->next_index; ++r)
+        if (b->live[r] && !loc.emplace(b->ids[r], ((uint64_t)pos << 32) | (uint32_t)r).second) {
+            enter_dup_mode();
+            return;
+        }
+}
+
 bool Set::slot_to_block(uint32_t slot, int *block_pos, int *row) const
 {
     if (cap <= 0) return false;
@@ -618,15 +768,18 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
                 rc = b->acquire(name, dims, precision, batch);
                 if (rc) return rc;
                 b->set = this;
+                b->use_index = has_dups;
             }
         }
         blocks.insert(blocks.end(), got.begin(), got.end());
     }
     const size_t rowb = (size_t)dims * precision;
     int64_t offset = 0, remain = n;
-    for (Block *b : blocks) {
+    for (size_t bp = 0; bp < blocks.size(); ++bp) {
+        Block *b = blocks[bp];
         int64_t length = std::min<int64_t>(b->margin(), remain);
         if (length > 0) {
+            materialize_block((int)bp);
             std::vector<std::string> sub(ids_.begin() + offset, ids_.begin() + offset + length);
             const std::vector<int> refilled(b->empty.begin(),
                                             b->empty.begin() + std::min<size_t>(b->empty.size(), (size_t)length));
@@ -636,8 +789,16 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
                 rebuild_segments();
                 return rc;
             }
-            for (int slot : refilled) note_rows((const float *)b->dev + (size_t)slot * dims, 1);
-            if (b->next_index > tail0) note_rows((const float *)b->dev + (size_t)tail0 * dims, b->next_index - tail0);
+            if (refilled.size() > 8) {
+                note_rows((const float *)b->dev, b->next_index);  // one pass over the block beats a launch per slot
+            } else {
+                for (int slot : refilled) note_rows((const float *)b->dev + (size_t)slot * dims, 1);
+                if (b->next_index > tail0)
+                    note_rows((const float *)b->dev + (size_t)tail0 * dims, b->next_index - tail0);
+            }
+            for (size_t i = 0; i < refilled.size(); ++i) note_id(sub[i], (int)bp, refilled[i]);
+            for (int64_t i = (int64_t)refilled.size(); i < length; ++i)
+                note_id(sub[i], (int)bp, tail0 + (int)(i - (int64_t)refilled.size()));
             offset += length;
             remain -= length;
         }
@@ -672,6 +833,7 @@ int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int norm
             rc = b->acquire(name, dims, precision, batch);
             if (rc) return rc;
             b->set = this;
+            b->use_index = has_dups;
             // implicit ids: do not keep capacity() empty strings per block
             std::vector<std::string>().swap(b->ids);
             b->implicit_ids = true;
@@ -680,15 +842,46 @@ int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int norm
         }
         blocks.insert(blocks.end(), got.begin(), got.end());
     }
+    if (!implicit_ranges.empty() && implicit_prefix != prefix) enter_dup_mode();  // two id families: walk the blocks
+    implicit_prefix = prefix;
     int64_t done = 0;
-    for (Block *b : blocks) {
+    for (size_t bp = 0; bp < blocks.size(); ++bp) {
+        Block *b = blocks[bp];
         int64_t length = std::min<int64_t>(b->capacity() - b->next_index, n - done);
         if (length > 0) {
             if (b->implicit_ids && b->next_index == 0) b->id_first = first_ordinal + done;
             const int tail0 = b->next_index;
+            const bool was_implicit = b->implicit_ids;
             rc = b->insert_synthetic(length, seed, first_ordinal + done, normalize, prefix);
             if (rc) return rc;
             note_rows((const float *)b->dev + (size_t)tail0 * dims, length);
+            if (b->implicit_ids) {
+                bool merged = false;
+                for (ImplicitRange &r : implicit_ranges)
+                    if (r.pos == (int)bp) {
+                        r.count = b->next_index;
+                        merged = true;
+                    }
+                if (!merged) {
+                    ImplicitRange r{b->id_first, b->next_index, (int)bp};
+                    auto it = std::lower_bound(implicit_ranges.begin(), implicit_ranges.end(), r,
+                                               [](const ImplicitRange &x, const ImplicitRange &y) { return x.first < y.first; });
+                    if ((it != implicit_ranges.end() && it->first < r.first + r.count) ||
+                        (it != implicit_ranges.begin() && (it - 1)->first + (it - 1)->count > r.first))
+                        enter_dup_mode();  // overlapping ordinal ranges
+                    implicit_ranges.insert(it, r);
+                }
+                if (!loc.empty() && !has_dups) {  // an explicit id may collide with a generated one
+                    char buf[32];
+                    for (int64_t i = 0; i < length && !has_dups; ++i) {
+                        snprintf(buf, sizeof buf, "%011lld", (long long)(first_ordinal + done + i));
+                        if (loc.count(prefix + buf)) enter_dup_mode();
+                    }
+                }
+            } else {
+                if (was_implicit) materialize_block((int)bp);
+                for (int64_t i = 0; i < length; ++i) note_id(b->ids[tail0 + i], (int)bp, tail0 + (int)i);
+            }
             done += length;
         }
         if (done >= n) break;
@@ -706,13 +899,25 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
     ExclusiveGuard g(lock);
     int rc = quiesce(ctx);
     if (rc) return rc;
-    size_t nfound = 0;
-    for (Block *b : blocks) {
-        if (nfound == ids_.size()) break;
-        rc = b->remove(ids_, found);
-        if (rc) return rc;
-        nfound = (size_t)std::count(found.begin(), found.end(), (uint8_t)1);
+    // set.go:163-193 walks the blocks and block.go:136-147 scans every IDs[]; the locator answers the same
+    // question (first block holding the id, last row in it) in O(1) per id
+    std::unordered_map<std::string, size_t> first;
+    first.reserve(ids_.size() * 2);
+    for (size_t i = 0; i < ids_.size(); ++i) first.emplace(ids_[i], i);  // a repeated id is looked up once
+    std::unordered_map<int, std::vector<int>> per_block;
+    for (size_t i = 0; i < ids_.size(); ++i) {
+        if (first[ids_[i]] != i) continue;
+        int pos, row;
+        if (!find(ids_[i], &pos, &row)) continue;
+        per_block[pos].push_back(row);
+        found[i] = 1;
+        if (!has_dups && !blocks[pos]->implicit_ids) loc.erase(ids_[i]);
     }
+    for (auto &kv : per_block) {
+        rc = blocks[kv.first]->remove_rows(kv.second);
+        if (rc) return rc;
+    }
+    if (!per_block.empty()) GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     return GF_OK;  // NextIndex never shrinks (block.go:159-160): the segment table is unchanged
 }
 
@@ -727,15 +932,13 @@ int Set::update(int64_t n, const uint8_t *values, const std::vector<std::string>
     if (rc) return rc;
     const size_t rowb = (size_t)dims * precision;
     for (int64_t i = 0; i < n; ++i) {
-        for (Block *b : blocks) {
-            int row = b->find_last(ids_[i]);
-            if (row < 0) continue;
-            rc = ctx->upload(b->dev + (size_t)row * rowb, values + (size_t)i * rowb, rowb);
-            if (rc) return rc;
-            note_rows((const float *)b->dev + (size_t)row * dims, 1);
-            found[i] = 1;
-            break;
-        }
+        int pos, row;
+        if (!find(ids_[i], &pos, &row)) continue;
+        Block *b = blocks[pos];
+        rc = ctx->upload(b->dev + (size_t)row * rowb, values + (size_t)i * rowb, rowb);
+        if (rc) return rc;
+        note_rows((const float *)b->dev + (size_t)row * dims, 1);
+        found[i] = 1;
     }
     GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
     return GF_OK;
@@ -752,15 +955,12 @@ int Set::read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<ui
     const size_t rowb = (size_t)dims * precision;
     for (size_t i = 0; i < ids_.size(); ++i) {
         memset(out + i * rowb, 0, rowb);
-        for (Block *b : blocks) {
-            int row = b->find_last(ids_[i]);
-            if (row < 0) continue;
-            GF_CUDA(cudaMemcpy(out + i * rowb, b->dev + (size_t)row * rowb, rowb, cudaMemcpyDeviceToHost),
-                    GF_ERR_READ_CUDA_BUFFER);
-            ctx->stats.d2h_bytes += rowb;
-            found[i] = 1;
-            break;
-        }
+        int pos, row;
+        if (!find(ids_[i], &pos, &row)) continue;
+        GF_CUDA(cudaMemcpy(out + i * rowb, blocks[pos]->dev + (size_t)row * rowb, rowb, cudaMemcpyDeviceToHost),
+                GF_ERR_READ_CUDA_BUFFER);
+        ctx->stats.d2h_bytes += rowb;
+        found[i] = 1;
     }
     return GF_OK;
 }
@@ -778,6 +978,9 @@ int Set::destroy()
         if (rc) return rc;
     }
     blocks.clear();
+    loc.clear();
+    implicit_ranges.clear();
+    has_dups = false;
     h_segs.clear();
     seg_block.clear();
     total_tiles = 0;

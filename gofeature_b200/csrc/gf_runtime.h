@@ -109,6 +109,8 @@ struct gf_context {
     void release_ws(Workspace *w);
     // pageable host -> device through the pinned ring, on mut_stream; returns after the copy finished
     int upload(void *dst, const void *src, size_t bytes);
+    // n rows of `rowb` bytes, row i to base + slots[i]*rowb: staged through the ring, one sync at the end
+    int upload_scatter(uint8_t *base, const int *slots, size_t n, size_t rowb, const uint8_t *src);
     ~gf_context();
 };
 
@@ -163,7 +165,8 @@ struct gf_block {
     bool implicit_ids = false;
     std::string id_prefix;
     int64_t id_first = 0;
-    std::unordered_map<std::string, std::vector<int>> id_index;  // id -> rows holding it
+    std::unordered_map<std::string, std::vector<int>> id_index;  // id -> rows holding it (when use_index)
+    bool use_index = true;  // false while a set keeps the set-wide locator for this block
     gf::Set *set = nullptr;
 
     int capacity() const { return (dims > 0 && precision > 0) ? (int)(block_size / ((int64_t)precision * dims)) : 0; }
@@ -178,6 +181,8 @@ struct gf_block {
     int insert(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
     int insert_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
+    int remove_rows(const std::vector<int> &rows);  // zero + tombstone the rows (no stream sync)
+    void rebuild_index();
     void index_add(const std::string &id, int row);
     void index_del(const std::string &id, int row);
 };
@@ -226,6 +231,22 @@ struct gf_set {
     int tile_rows = 0;
     bool aligned16 = false;
     Workspace *dev_ws = nullptr;  // scratch of gf_set_search_device (stream-ordered calls)
+    // set-wide id locator: O(1) Delete / Update / Read instead of block.go:140-144's scan of every block.
+    // Exact while ids are unique; the first duplicate id switches to the reference's block walk.
+    struct ImplicitRange {
+        int64_t first;
+        int count;
+        int pos;
+    };
+    std::unordered_map<std::string, uint64_t> loc;  // explicit id -> (block position << 32 | row)
+    std::vector<ImplicitRange> implicit_ranges;     // sorted by first; ids "<implicit_prefix>%011d"
+    std::string implicit_prefix;
+    bool has_dups = false;
+    bool find(const std::string &id, int *pos, int *row) const;
+    bool find_implicit(const std::string &id, int *pos, int *row) const;
+    void note_id(const std::string &id, int pos, int row);
+    void enter_dup_mode();
+    void materialize_block(int pos);
     // coalescer
     int coalesce_wait_us = 0;
     std::mutex co_mu;

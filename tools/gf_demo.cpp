@@ -49,6 +49,8 @@ int main(int argc, char **argv)
     const int adds = (int)arg(argc, argv, "--adds", 0);         // 50 in the demo
     const int dels = (int)arg(argc, argv, "--deletes", 0);      // 200 in the demo
     const int add_gap_us = (int)arg(argc, argv, "--add-gap-us", 2000);
+    const int add_size = (int)arg(argc, argv, "--add-size", 0);      // rows per Add call (0 = 1..10 like the demo)
+    const int del_size = (int)arg(argc, argv, "--delete-size", 1);   // ids per Delete call
     const int device = (int)arg(argc, argv, "--device", 0);
     const long block_size = 1024L * 1024 * 32;                  // BlockSize demo/main.go:19
     const long cap = block_size / (dims * 4L);
@@ -90,6 +92,7 @@ int main(int argc, char **argv)
     std::atomic<long> hits{0};
     std::atomic<bool> stop{false};
     std::atomic<int> n_adds{0}, n_dels{0}, n_deleted{0};
+    std::atomic<long> rows_added{0}, add_us{0}, del_us{0};
     auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> th;
     for (int p = 0; p < threads; ++p) {
@@ -112,7 +115,7 @@ int main(int argc, char **argv)
         std::uniform_real_distribution<float> u(-1.f, 1.f);
         long next = 0;
         for (int i = 0; i < adds && !stop; ++i) {
-            int size = 1 + (int)(rng() % 10);
+            int size = add_size > 0 ? add_size : 1 + (int)(rng() % 10);
             std::vector<float> v((size_t)size * dims), raw(dims);
             std::string ids;
             std::vector<uint64_t> off(size + 1, 0);
@@ -124,8 +127,11 @@ int main(int argc, char **argv)
                 ids += buf;
                 off[k + 1] = ids.size();
             }
+            auto a0 = std::chrono::steady_clock::now();
             int rc = gf_set_add(set, size, v.data(), (uint64_t)size * dims * 4, ids.data(), off.data());
             if (rc) die("gf_set_add", rc);
+            add_us += (long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a0).count();
+            rows_added += size;
             ++n_adds;
             std::this_thread::sleep_for(std::chrono::microseconds(add_gap_us));
         }
@@ -133,13 +139,20 @@ int main(int argc, char **argv)
     std::thread deleter([&]() {  // demo/main.go:184-201
         std::mt19937_64 rng(13);
         for (int i = 0; i < dels && !stop; ++i) {
-            char buf[32];
-            snprintf(buf, sizeof buf, "f%011ld", (long)(rng() % (uint64_t)rows));
-            uint64_t off[2] = {0, strlen(buf)};
-            uint8_t flag = 0;
+            std::string ids;
+            std::vector<uint64_t> off(del_size + 1, 0);
+            for (int k = 0; k < del_size; ++k) {
+                char buf[32];
+                snprintf(buf, sizeof buf, "f%011ld", (long)(rng() % (uint64_t)rows));
+                ids += buf;
+                off[k + 1] = ids.size();
+            }
+            std::vector<uint8_t> flags(del_size);
             int64_t n = 0;
-            int rc = gf_set_delete(set, 1, buf, off, &flag, &n);
+            auto a0 = std::chrono::steady_clock::now();
+            int rc = gf_set_delete(set, del_size, ids.data(), off.data(), flags.data(), &n);
             if (rc) die("gf_set_delete", rc);
+            del_us += (long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a0).count();
             ++n_dels;
             n_deleted += (int)n;
             std::this_thread::sleep_for(std::chrono::microseconds(add_gap_us / 4 + 1));
@@ -178,13 +191,18 @@ int main(int argc, char **argv)
     const double nsearch = (double)all.size();
     printf("{\"rows\": %ld, \"dims\": %d, \"threads\": %d, \"rounds\": %d, \"batch\": %d, \"limit\": %d, \"coalesce_us\": %d, "
            "\"fill_ms\": %.1f, \"wall_ms\": %.3f, \"searches\": %.0f, \"queries\": %.0f, \"qps\": %.1f, \"avg_ms\": %.4f, "
-           "\"p50_ms\": %.4f, \"p99_ms\": %.4f, \"hits\": %ld, \"adds\": %d, \"deletes\": %d, \"deleted\": %d, "
-           "\"scan_launches\": %llu, \"tensor_passes\": %llu, \"coalesced_batches\": %llu, \"quirk_fallbacks\": %llu, "
-           "\"uncertified_queries\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"self_check\": \"%s\"}\n",
+           "\"p50_ms\": %.4f, \"p99_ms\": %.4f, \"hits\": %ld, ",
            rows, dims, threads, rounds, batch, limit, coalesce, fill_ms, wall_ms, nsearch, nsearch * batch,
            nsearch * batch / (wall_ms / 1e3), sum / nsearch, all[all.size() / 2],
-           all[std::min(all.size() - 1, (size_t)(all.size() * 0.99))], hits.load(), n_adds.load(), n_dels.load(),
-           n_deleted.load(), (unsigned long long)st.scan_launches, (unsigned long long)st.tensor_passes,
+           all[std::min(all.size() - 1, (size_t)(all.size() * 0.99))], hits.load());
+    printf("\"adds\": %d, \"rows_added\": %ld, \"add_rows_per_s\": %.0f, \"deletes\": %d, \"deleted\": %d, "
+           "\"delete_ids_per_s\": %.0f, ",
+           n_adds.load(), rows_added.load(), add_us.load() ? rows_added.load() / (add_us.load() / 1e6) : 0.0,
+           n_dels.load(), n_deleted.load(),
+           del_us.load() ? (double)n_dels.load() * del_size / (del_us.load() / 1e6) : 0.0);
+    printf("\"scan_launches\": %llu, \"tensor_passes\": %llu, \"coalesced_batches\": %llu, \"quirk_fallbacks\": %llu, "
+           "\"uncertified_queries\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"self_check\": \"%s\"}\n",
+           (unsigned long long)st.scan_launches, (unsigned long long)st.tensor_passes,
            (unsigned long long)st.coalesced_batches, (unsigned long long)st.quirk_fallbacks,
            (unsigned long long)st.uncertified_queries, (unsigned long long)st.h2d_bytes,
            (unsigned long long)st.d2h_bytes, ok ? "ok" : "FAILED");
