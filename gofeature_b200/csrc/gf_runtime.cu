@@ -72,6 +72,7 @@ struct ExclusiveGuard {
 // ------------------------------------------------------------------ Workspace / Context
 int Workspace::reserve(size_t d_bytes, size_t h_bytes)
 {
+    if (d_bytes > d_cap || h_bytes > h_cap) drop_graphs();  // cached graphs point into the old arenas
     if (d_bytes > d_cap) {
         if (d_buf) {
             GF_CUDA(cudaStreamSynchronize(stream), GF_ERR_CUDA);
@@ -97,9 +98,16 @@ int Workspace::reserve(size_t d_bytes, size_t h_bytes)
     return GF_OK;
 }
 
+void Workspace::drop_graphs()
+{
+    for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+}
+
 int Workspace::reserve_tensor(size_t bytes)
 {
     if (bytes <= d_tensor_cap) return GF_OK;
+    drop_graphs();  // cached graphs point into the old arena
     if (d_tensor) {
         GF_CUDA(cudaStreamSynchronize(stream), GF_ERR_CUDA);
         cudaFree(d_tensor);
@@ -113,6 +121,7 @@ int Workspace::reserve_tensor(size_t bytes)
 
 Workspace::~Workspace()
 {
+    drop_graphs();
     if (d_tensor) cudaFree(d_tensor);
     if (d_buf) cudaFree(d_buf);
     if (h_buf) cudaFreeHost(h_buf);
@@ -649,8 +658,11 @@ bool Set::slot_to_block(uint32_t slot, int *block_pos, int *row) const
     return true;
 }
 
+static std::atomic<uint64_t> g_set_version{0};
+
 int Set::rebuild_segments()
 {
+    version = ++g_set_version;  // process-wide unique: a cached graph can never match a different table
     h_segs.clear();
     seg_block.clear();
     int tr = scan_tile_rows(dims);
@@ -1022,9 +1034,96 @@ bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long lo
     return q > scan_max_q(dims) || K > 32;
 }
 
+// The tensor path is ~12 small launches around one big kernel, and the gaps between them were 20 % of
+// a 10-query step: everything after the query preparation is recorded once per (set state, q, K) as a
+// CUDA graph and replayed.  The graph only touches workspace-owned buffers (the caller's query and
+// result pointers stay outside: one eager prep kernel before, two small copies after), recording
+// happens on the workspace's own stream (the caller's may be the legacy default stream, which cannot
+// be captured), replay goes into the caller's stream.
 int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                      int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
                      unsigned long long *d_out, int path, unsigned int *d_flags)
+{
+    static const bool no_graphs = getenv("GF_NO_GRAPHS") != nullptr || getenv("GF_STAGE_TIMING") != nullptr;
+    const bool tensor = tensor_eligible(q, K, per_segment, d_upper, path);
+    if (!tensor || q > kGemmMaxQ || no_graphs || ws->graphs_broken || ctx->profiling.load())
+        return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
+    Stats &st = ctx->stats;
+    for (auto &g : ws->graphs) {
+        if (g.set == this && g.version == version && g.q == q && g.K == K) {
+            int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1);
+            if (rc) return rc;
+            GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
+            GF_CUDA(cudaMemcpyAsync(d_out, ws->t_res, (size_t)q * K * 8, cudaMemcpyDeviceToDevice, stream), GF_ERR_CUDA);
+            if (d_flags)
+                GF_CUDA(cudaMemcpyAsync(d_flags, ws->t_flags, (size_t)q * 4, cudaMemcpyDeviceToDevice, stream),
+                        GF_ERR_CUDA);
+            g.stamp = ++ws->graph_clock;
+            st.scan_launches += g.d_scan;
+            st.gemm_launches += g.d_gemm;
+            st.merge_launches += g.d_merge;
+            st.other_launches += g.d_other + 1;
+            st.tensor_passes += g.d_tensor_passes;
+            st.rows_scanned += g.d_rows;
+            return GF_OK;
+        }
+    }
+    // first call of this shape: run it eagerly (sizes the scratch arenas, sets kernel attributes) ...
+    int rc = topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
+    if (rc) return rc;
+    // ... then record the part after the query preparation for the next calls
+    GF_CUDA(cudaStreamSynchronize(stream), GF_ERR_CUDA);
+    const uint64_t s0 = st.scan_launches, g0 = st.gemm_launches, m0 = st.merge_launches, o0 = st.other_launches,
+                   t0 = st.tensor_passes, r0 = st.rows_scanned;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ws->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        ws->graphs_broken = true;
+        return GF_OK;
+    }
+    int crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2);
+    cudaError_t ce = cudaStreamEndCapture(ws->stream, &graph);
+    Workspace::CachedGraph cg{};  // what the recording pass "launched" did not run: take its counters back
+    cg.d_scan = st.scan_launches - s0;
+    cg.d_gemm = st.gemm_launches - g0;
+    cg.d_merge = st.merge_launches - m0;
+    cg.d_other = st.other_launches - o0;
+    cg.d_tensor_passes = st.tensor_passes - t0;
+    cg.d_rows = st.rows_scanned - r0;
+    st.scan_launches -= cg.d_scan;
+    st.gemm_launches -= cg.d_gemm;
+    st.merge_launches -= cg.d_merge;
+    st.other_launches -= cg.d_other;
+    st.tensor_passes -= cg.d_tensor_passes;
+    st.rows_scanned -= cg.d_rows;
+    cudaGraphExec_t exec = nullptr;
+    if (crc == GF_OK && ce == cudaSuccess && graph != nullptr) ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (crc != GF_OK || ce != cudaSuccess || exec == nullptr) {
+        cudaGetLastError();
+        ws->graphs_broken = true;
+        return GF_OK;  // the eager result above stands
+    }
+    if (ws->graphs.size() >= 16) {  // evict the least recently used shape
+        size_t victim = 0;
+        for (size_t i = 1; i < ws->graphs.size(); ++i)
+            if (ws->graphs[i].stamp < ws->graphs[victim].stamp) victim = i;
+        cudaGraphExecDestroy(ws->graphs[victim].exec);
+        ws->graphs.erase(ws->graphs.begin() + victim);
+    }
+    cg.set = this;
+    cg.version = version;
+    cg.q = q;
+    cg.K = K;
+    cg.exec = exec;
+    cg.stamp = ++ws->graph_clock;
+    ws->graphs.push_back(cg);
+    return GF_OK;
+}
+
+int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                    int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
+                    unsigned long long *d_out, int path, unsigned int *d_flags)
 {
     if (tensor_eligible(q, K, per_segment, d_upper, path))
         return topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, d_out, d_flags);
@@ -1038,7 +1137,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
 //   -> sort, emit K, certify.  Uncertified queries are re-run by one fix-up scan pass on the device
 //   (up to kFixupMaxQ per call); what is still flagged is reported through d_flags.
 int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
-                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags)
+                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase)
 {
     const int nseg = (int)h_segs.size();
     const int kp = std::min(1024, std::max(K + 32, K + K / 2));
@@ -1073,6 +1172,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_count = carve(4);
     const size_t o_fix = carve((size_t)kFixupMaxQ * K * 8);
     const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
+    const size_t o_res = carve((size_t)q * K * 8);     // result keys when the caller's buffer must stay outside (phase 2)
     int rc = ws->reserve_tensor(off);
     if (rc) return rc;
     uint8_t *T = ws->d_tensor;
@@ -1089,6 +1189,9 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     unsigned int *d_count = (unsigned int *)(T + o_count);
     unsigned long long *d_fix = (unsigned long long *)(T + o_fix);
     float *d_qall = (float *)(T + o_qall);
+    ws->t_res = (unsigned long long *)(T + o_res);
+    ws->t_flags = d_fl;
+    if (phase == 2) d_out = ws->t_res;
 
     GemmLaunch g{};
     g.d_segs = d_segs;
@@ -1120,9 +1223,11 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         g.nq = nq;
         g.q = qp;
         mark();
-        GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad, d_qn,
-                                    d_qall + (size_t)p0 * dims, stream),
-                GF_ERR_CUDA);
+        if (phase != 2)
+            GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
+                                        d_qn, d_qall + (size_t)p0 * dims, stream),
+                    GF_ERR_CUDA);
+        if (phase == 1) continue;
         // small batches: re-score EVERY collected candidate (~1000 rows per query) and skip the selection
         const bool all = (size_t)qp * (size_t)target * (size_t)dims * 4 <= ((size_t)64 << 20);
         mark();
@@ -1171,6 +1276,10 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         ctx->stats.tensor_passes++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
     }
+    if (phase == 1) {
+        ctx->stats.other_launches++;
+        return GF_OK;
+    }
     // device-side fix-up: one exact scan pass over up to kFixupMaxQ flagged queries (a no-op launch
     // when everything was certified)
     const int fixq = std::min(kFixupMaxQ, scan_max_q(dims));
@@ -1192,7 +1301,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         fprintf(stderr, "\n");
         for (auto e : evs) cudaEventDestroy(e);
     }
-    if (d_flags)
+    if (d_flags && phase == 0)
         GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream),
                 GF_ERR_CUDA);
     return GF_OK;

@@ -75,6 +75,21 @@ struct Workspace {
     size_t h_cap = 0;
     uint8_t *d_tensor = nullptr;  // scratch of the tcgen05 path (queries, tile maxima, candidates ...)
     size_t d_tensor_cap = 0;
+    // CUDA graphs of whole search pipelines (one per distinct call shape), replayed to shed launch gaps
+    struct CachedGraph {
+        const void *set;
+        uint64_t version;
+        int q, K;
+        cudaGraphExec_t exec;
+        uint64_t d_scan, d_gemm, d_merge, d_other, d_tensor_passes, d_rows;  // counters one replay adds
+        uint64_t stamp;
+    };
+    std::vector<CachedGraph> graphs;
+    uint64_t graph_clock = 0;
+    bool graphs_broken = false;
+    unsigned long long *t_res = nullptr;  // tensor path: internal result keys / flags of the last carve
+    unsigned int *t_flags = nullptr;
+    void drop_graphs();
     int reserve(size_t d_bytes, size_t h_bytes);
     int reserve_tensor(size_t bytes);
     ~Workspace();
@@ -226,6 +241,7 @@ struct gf_set {
     uint32_t total_gtiles = 0;
     unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter
     bool tensor_ok = false;
+    uint64_t version = 0;  // bumped whenever the segment table or the shard identity changes
     uint32_t total_tiles = 0;
     int64_t scanned_rows = 0;
     int tile_rows = 0;
@@ -280,11 +296,16 @@ struct gf_set {
     int topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                     int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
                     unsigned long long *d_out, int path = 1, unsigned int *d_flags = nullptr);
+    int topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
+                   int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
+                   unsigned long long *d_out, int path, unsigned int *d_flags);
     int topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                   int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
                   unsigned long long *d_out, const int *d_q_map = nullptr, const unsigned int *d_q_count = nullptr);
+    //   phase 0: everything, results to d_out / d_flags;  1: query preparation only;
+    //   2: everything after the preparation, results to the workspace (ws->t_res / ws->t_flags)
     int topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
-                    int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags);
+                    int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase = 0);
     bool tensor_eligible(int q, int K, bool per_segment, const unsigned long long *d_upper, int path) const;
     int note_rows(const float *d_rows, int64_t rows);  // keep the |row|^2 bound current (mutation stream)
     bool slot_to_block(uint32_t slot, int *block_pos, int *row) const;
