@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
 
 #include "gf_device.cuh"
 
@@ -1601,13 +1603,36 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
     const size_t qbytes = (size_t)dims * precision;
     static thread_local const Set *tl_set = nullptr;
     static thread_local uint64_t tl_batch = 0;
+    static const int hw = (int)std::max(2u, std::thread::hardware_concurrency());
+    struct Inside {
+        std::atomic<int> &c;
+        explicit Inside(std::atomic<int> &c_) : c(c_) { ++c; }
+        ~Inside() { --c; }
+    } inside(co_inside);
     std::unique_lock<std::mutex> lk(co_mu);
     me.returnee = (tl_set == this && tl_batch == co_batch_id && co_batch_id != 0);
     co_queue.push_back(&me);
-    co_cv.notify_all();  // a waiting leader re-counts its company
-    while (!me.done) {
-        if (co_leader_active) {  // someone else is leading: wait to be served (or to take over)
-            co_cv.wait(lk);
+    co_queued.store((int)co_queue.size(), std::memory_order_release);
+    co_cv.notify_all();  // a parked leader re-counts its company
+    auto spin_until = [](const std::function<bool()> &ready, int us) {
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(us);
+        for (int i = 0;; ++i) {
+            if (ready()) return true;
+            if ((i & 63) == 63 && std::chrono::steady_clock::now() >= deadline) return false;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    };
+    while (!me.done.load(std::memory_order_acquire)) {
+        if (co_leader_active.load()) {  // someone else is leading: wait to be served (or to take over)
+            // a batch takes a few hundred microseconds: spin through it before paying a futex sleep + wake-up
+            if (co_inside.load() <= hw - 4) {  // more waiters than spare cores: spinning would starve the leader
+                lk.unlock();
+                spin_until([&] { return me.done.load(std::memory_order_acquire) || !co_leader_active.load(); }, 600);
+                lk.lock();
+            }
+            if (!me.done.load(std::memory_order_acquire) && co_leader_active.load()) co_cv.wait(lk);
             continue;
         }
         co_leader_active = true;
@@ -1617,9 +1642,11 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         {
             int fresh = 0;
             for (PendingSearch *p : co_queue) fresh += p->returnee ? 0 : 1;
-            const size_t target = (size_t)co_last_group + (size_t)fresh;
-            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(coalesce_wait_us);
-            while (co_queue.size() < target && co_cv.wait_until(lk, deadline) != std::cv_status::timeout) {
+            const int target = co_last_group + fresh;
+            if ((int)co_queue.size() < target) {
+                lk.unlock();
+                spin_until([&] { return co_queued.load(std::memory_order_acquire) >= target; }, coalesce_wait_us);
+                lk.lock();
             }
         }
         // take every queued request with my limit, up to 256 queries
@@ -1635,6 +1662,7 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
                 ++it;
             }
         }
+        co_queued.store((int)co_queue.size(), std::memory_order_release);
         lk.unlock();
         std::vector<uint8_t> flat((size_t)total * qbytes);
         size_t off = 0;
@@ -1667,7 +1695,9 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         lk.lock();
         ++co_batch_id;
         co_last_group = (int)group.size();
-        for (PendingSearch *p : group) p->done = true;
+        for (PendingSearch *p : group)
+            if (p != &me) p->done.store(true, std::memory_order_release);  // p may be gone right after this
+        me.done.store(true, std::memory_order_release);
         co_leader_active = false;
         co_cv.notify_all();
     }

@@ -211,7 +211,7 @@ struct PendingSearch {
     float threshold;
     gf::Result *result = nullptr;
     int rc = 0;
-    bool done = false;
+    std::atomic<bool> done{false};
     bool returnee = false;  // this thread was served by the immediately preceding batch
 };
 }
@@ -268,7 +268,9 @@ struct gf_set {
     std::mutex co_mu;
     std::condition_variable co_cv;
     std::vector<gf::PendingSearch *> co_queue;
-    bool co_leader_active = false;
+    std::atomic<bool> co_leader_active{false};
+    std::atomic<int> co_queued{0};  // co_queue.size(), readable without the lock
+    std::atomic<int> co_inside{0};  // callers currently inside search_coalesced (spin only when cores are spare)
     uint64_t co_batch_id = 0;   // batches served so far
     int co_last_group = 0;      // requests in the last batch
 
