@@ -22,6 +22,8 @@
 // Grid: persistent, one CTA per SM (148 on B200), tiles strided over CTAs; in per-segment
 // mode (tombstone parity path, block.go:236-243) gridDim.y = blocks and every CTA stays
 // inside one block.
+#include <cstdlib>
+
 #include "gf_device.cuh"
 #include "gf_kernels.h"
 
@@ -409,6 +411,10 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
         if (lists_bytes + fixed + 2 * (size_t)kScanTileBytes > kSmemLimit) return cudaErrorInvalidValue;
         int st = (int)((kSmemLimit - fixed - lists_bytes) / kScanTileBytes);
         p.stages = st > 7 ? 7 : st;
+        if (const char *e = getenv("GF_SCAN_STAGES")) {  // tuning knob
+            int v = atoi(e);
+            if (v >= 2 && v <= p.stages) p.stages = v;
+        }
         p.smem_bytes = (size_t)p.stages * kScanTileBytes + fixed + lists_bytes;
     } else {
         p.tile_rows = 64;

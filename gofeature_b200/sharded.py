@@ -127,6 +127,29 @@ def results_from_table(keys, table, threshold):
     return out
 
 
+def tombstone_among_winners(keys, table):
+    """True if a merged winner was not reported live by its owner (a zeroed, deleted row scored its way in)."""
+    q, limit = keys.shape
+    for i in range(q):
+        for j in range(limit):
+            if int(keys[i, j]) == 0:
+                break
+            if not table[i, j, 0]:
+                return True
+    return False
+
+
+def merge_hit_lists(gathered, limit):
+    """gathered[rank][query] = [(key, id)] already filtered per block / threshold -> MaxNFeatureResult
+    (set.go:154-157) over the union, in canonical key order."""
+    nq = len(gathered[0])
+    out = []
+    for i in range(nq):
+        allh = sorted((h for per_rank in gathered for h in per_rank[i]), key=lambda t: -t[0])[:limit]
+        out.append([api.FeatureSearchResult(_key_score(k), ident, 0xFFFFFFFF - (k & 0xFFFFFFFF)) for k, ident in allh])
+    return out
+
+
 def _key_score(k):
     """score of a key without calling into the library (same mapping as gf_key_score)."""
     im = (k >> 32) & 0xFFFFFFFF
@@ -230,4 +253,21 @@ class ShardedSet:
         local = self.local.ResolveKeys(float("-inf"), limit, keys)     # live winners this rank owns
         mine = [{r.Slot: r.ID for r in row if r.ID != ""} for row in local]
         table = exchange_ids(keys, mine, self.rank, self.world, self.group, "cuda:%d" % self.ctx.device)
-        return results_from_table(keys, table, threshold)
+        if not tombstone_among_winners(keys, table):
+            return results_from_table(keys, table, threshold)
+        # A deleted row made it into the merged top-limit.  The reference selects per BLOCK before it drops
+        # tombstones (block.go:236-243), so the exact answer is the merge of the per-block lists: every rank
+        # runs its own Set.Search (which applies that rule to its blocks) and the hit lists are merged.
+        return self._search_exact_lists(threshold, limit, queries)
+
+    def _search_exact_lists(self, threshold, limit, queries):
+        import torch.distributed as dist
+        queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dims)
+        local = self.local.SearchArray(threshold, limit, queries)
+        mine = [[(api.key_make(r.Score, r.Slot), r.ID) for r in row] for row in local]
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=self.group)
+        else:
+            gathered = [mine]
+        return merge_hit_lists(gathered, limit)

@@ -72,6 +72,18 @@ def _free_port():
     return p
 
 
+def _negative_set():
+    rows = ol.synth_rows(63, 0, 3000, 512).copy()
+    rows[:, 0] = np.abs(rows[:, 0]) + np.float32(0.5)
+    ids = ["n%05d" % i for i in range(3000)]
+    q = np.zeros((2, 512), dtype=np.float32)
+    q[0, 0] = -1.0
+    q[1, 0] = -1.0
+    q[1, 1] = 0.25
+    dead = [ids[i] for i in (3, 1025, 1030, 2500, 2999)]
+    return rows, ids, q, dead
+
+
 def _nccl_worker(rank, world, port, q_out):
     import torch
     import torch.distributed as dist
@@ -89,7 +101,15 @@ def _nccl_worker(rank, world, port, q_out):
         dead = ["f%011d" % i for i in (5, 1030, 4444)]
         assert sorted(s.Delete(*dead)) == sorted(dead)
         res = s.Search(-1.0, 10, ol.synth_rows(62, 0, 3, 512))
-        q_out.put((rank, [[(float(r.Score), r.ID) for r in row] for row in res]))
+        # second set: every live score is negative, so the zeroed tombstones win the merged top-10 and the
+        # exact per-block path (block.go:236-243) has to run across the ranks
+        rows2, ids2, q2, dead2 = _negative_set()
+        s2 = ShardedSet(ctx, cache, "neg", 512, 8, rank, world)
+        s2.Add(rows2, ids2)
+        s2.Delete(*dead2)
+        res2 = s2.Search(-10.0, 10, q2)
+        q_out.put((rank, [[(float(r.Score), r.ID) for r in row] for row in res],
+                   [[(float(r.Score), r.ID) for r in row] for row in res2]))
         cache.Close()
         ctx.Close()
     finally:
@@ -107,11 +127,13 @@ def test_nccl_sharded_search_two_gpus():
     procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q_out)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q_out.get(timeout=300) for _ in range(world))
+    outs = [q_out.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert got[0] == got[1]
+    got = {r: a for r, a, _ in outs}
+    got2 = {r: b for r, _, b in outs}
+    assert got[0] == got[1] and got2[0] == got2[1]
     oc = model.Cache(12, 1024 * 512 * 4)
     oc.new_set("one", 512, 4, 8)
     o = oc.get_set("one")
@@ -119,5 +141,15 @@ def test_nccl_sharded_search_two_gpus():
     o.delete(["f%011d" % i for i in (5, 1030, 4444)])
     want = o.search(-1.0, 10, ol.synth_rows(62, 0, 3, 512))
     for g, w in zip(got[0], want):
+        assert [i for _, i in g] == [i for _, i in w]
+        assert [s_ for s_, _ in g] == [float(np.float32(s_)) for s_, _ in w]
+    rows2, ids2, q2, dead2 = _negative_set()
+    o2c = model.Cache(12, 1024 * 512 * 4)
+    o2c.new_set("neg", 512, 4, 8)
+    o2 = o2c.get_set("neg")
+    o2.add(rows2, ids2)
+    o2.delete(dead2)
+    want2 = o2.search(-10.0, 10, q2)
+    for g, w in zip(got2[0], want2):
         assert [i for _, i in g] == [i for _, i in w]
         assert [s_ for s_, _ in g] == [float(np.float32(s_)) for s_, _ in w]
