@@ -400,6 +400,12 @@ class Set:
                                          ctypes.byref(h)))
         return _take_result(h)
 
+    def Compact(self):
+        """Pack live rows, shrink NextIndex (not in the reference).  Returns rows reclaimed."""
+        n = c_i64(0)
+        _check(lib().gf_set_compact(self._h, ctypes.byref(n)))
+        return n.value
+
     def SetShard(self, rank, world):
         _check(lib().gf_set_set_shard(self._h, rank, world))
 

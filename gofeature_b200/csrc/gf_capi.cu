@@ -671,6 +671,12 @@ int gf_set_destroy(gf_set *set)
     return gf_cache_destroy_set(set->cache, set->name.c_str());
 }
 
+int gf_set_compact(gf_set *set, int64_t *out_reclaimed_rows)
+{
+    if (!set) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int { return set->compact(out_reclaimed_rows); });
+}
+
 int gf_set_dims(const gf_set *set) { return set ? set->dims : 0; }
 int gf_set_precision(const gf_set *set) { return set ? set->precision : 0; }
 int gf_set_batch(const gf_set *set) { return set ? set->batch : 0; }

@@ -115,6 +115,9 @@ cudaError_t scatter_fix_launch(const unsigned long long *d_fix, const int *d_map
 cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, unsigned int *d_out_bits,
                                  cudaStream_t stream);
 
+cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int dims, float *d_dst,
+                               cudaStream_t stream);
+
 // Synthetic rows, bit-identical to oracle/gf_oracle.c gf_oracle_synth_rows.
 cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, uint64_t seed, int64_t first_row, int normalize,
                               cudaStream_t stream);

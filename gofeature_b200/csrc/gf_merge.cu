@@ -248,6 +248,32 @@ cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, un
     return cudaGetLastError();
 }
 
+// dst row j = src row idx[j]: packs the live rows of a block (tombstone compaction)
+namespace {
+__global__ void gather_rows_kernel(const float *__restrict__ src, const int *__restrict__ idx, int n, int dims,
+                                   float *__restrict__ dst)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < n; j += nwarps) {
+        const float *s = src + (size_t)idx[j] * dims;
+        float *d = dst + (size_t)j * dims;
+        for (int e = lane; e < dims; e += 32) d[e] = s[e];
+    }
+}
+}  // namespace
+
+cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int dims, float *d_dst,
+                               cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    int blocks = (n + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gather_rows_kernel<<<blocks, 256, 0, stream>>>(d_src, d_idx, n, dims, d_dst);
+    return cudaGetLastError();
+}
+
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
                          unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count)
 {

@@ -979,6 +979,68 @@ int Set::read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<ui
     return GF_OK;
 }
 
+// Not in the reference (NextIndex never shrinks, block.go:159-160, so deleted rows are scanned for
+// ever): pack the live rows of every block to its front, in order, and shrink NextIndex.  The
+// relative slot order of live rows is kept, so results change only where tombstones used to take
+// places in a block's top-limit (block.go:236-243).
+int Set::compact(int64_t *reclaimed)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (precision != 4) return GF_ERR_UNSUPPORTED;
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    int64_t freed = 0;
+    float *d_tmp = nullptr;
+    int *d_idx = nullptr;
+    for (size_t bp = 0; bp < blocks.size(); ++bp) {
+        Block *b = blocks[bp];
+        if (b->next_index == 0 || b->live_count == b->next_index) continue;
+        materialize_block((int)bp);
+        std::vector<int> rows;
+        rows.reserve((size_t)b->live_count);
+        for (int r = 0; r < b->next_index; ++r)
+            if (b->live[r]) rows.push_back(r);
+        const int n_live = (int)rows.size();
+        if (!d_tmp) {
+            GF_CUDA(cudaMalloc((void **)&d_tmp, (size_t)cache->block_size), GF_ERR_ALLOCATE_GPU_BUFFER);
+            GF_CUDA(cudaMalloc((void **)&d_idx, (size_t)cap * sizeof(int) + 16), GF_ERR_ALLOCATE_GPU_BUFFER);
+        }
+        std::lock_guard<std::mutex> bg(b->mu);
+        if (n_live > 0) {
+            GF_CUDA(cudaMemcpyAsync(d_idx, rows.data(), (size_t)n_live * sizeof(int), cudaMemcpyHostToDevice,
+                                    ctx->mut_stream),
+                    GF_ERR_WRITE_CUDA_BUFFER);
+            GF_CUDA(gather_rows_launch((const float *)b->dev, d_idx, n_live, dims, d_tmp, ctx->mut_stream),
+                    GF_ERR_CUDA);
+            GF_CUDA(cudaMemcpyAsync(b->dev, d_tmp, (size_t)n_live * dims * 4, cudaMemcpyDeviceToDevice,
+                                    ctx->mut_stream),
+                    GF_ERR_WRITE_CUDA_BUFFER);
+            ctx->stats.other_launches++;
+        }
+        GF_CUDA(cudaMemsetAsync(b->dev + (size_t)n_live * dims * 4, 0, (size_t)(b->next_index - n_live) * dims * 4,
+                                ctx->mut_stream),
+                GF_ERR_CLEAR_CUDA_BUFFER);
+        GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CUDA);  // rows[] is reused by the next block
+        for (int j = 0; j < n_live; ++j) {
+            if (rows[j] != j) b->ids[j] = std::move(b->ids[rows[j]]);
+            if (!has_dups) loc[b->ids[j]] = ((uint64_t)bp << 32) | (uint32_t)j;
+        }
+        for (int r = n_live; r < b->next_index; ++r) b->ids[r].clear();
+        std::fill(b->live.begin(), b->live.begin() + n_live, (uint8_t)1);
+        std::fill(b->live.begin() + n_live, b->live.end(), (uint8_t)0);
+        freed += b->next_index - n_live;
+        b->next_index = n_live;
+        b->live_count = n_live;
+        b->empty.clear();
+        if (b->use_index) b->rebuild_index();
+    }
+    if (d_tmp) cudaFree(d_tmp);
+    if (d_idx) cudaFree(d_idx);
+    if (reclaimed) *reclaimed = freed;
+    return rebuild_segments();
+}
+
 // set.go:202-214
 int Set::destroy()
 {

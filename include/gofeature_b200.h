@@ -201,6 +201,11 @@ GF_API int gf_set_search(gf_set *set, float threshold, int limit, int q, const v
 /* Set.Destroy (set.go:202-214); normally reached through gf_cache_destroy_set. */
 GF_API int gf_set_destroy(gf_set *set);
 
+/* Not in the reference: NextIndex never shrinks there (block.go:159-160), so deleted rows are
+ * scanned for ever.  Packs the live rows of every block to its front, in order, and shrinks NextIndex;
+ * out_reclaimed_rows = rows a search no longer scans.  Slot order of live rows is preserved. */
+GF_API int gf_set_compact(gf_set *set, int64_t *out_reclaimed_rows);
+
 GF_API int gf_set_dims(const gf_set *set);
 GF_API int gf_set_precision(const gf_set *set);
 GF_API int gf_set_batch(const gf_set *set);

@@ -158,6 +158,21 @@ class Set:
         raw = olib.set_search(rows, heights, live, queries, limit, threshold, mode)
         return [[(s, self.blocks[bi].ids[ri]) for (s, bi, ri) in per_q] for per_q in raw]
 
+    def compact(self):
+        """Extension (no reference counterpart): per block, live rows move to the front in
+        order, NextIndex shrinks to the live count, the free list empties."""
+        freed = 0
+        for b in self.blocks:
+            keep = [r for r in range(b.next_index) if b.ids[r] != ""]
+            if len(keep) == b.next_index:
+                continue
+            new_rows = np.zeros_like(b.rows)
+            new_rows[:len(keep)] = b.rows[keep]
+            new_ids = [b.ids[r] for r in keep] + [""] * (len(b.ids) - len(keep))
+            freed += b.next_index - len(keep)
+            b.rows, b.ids, b.next_index, b.empty = new_rows, new_ids, len(keep), []
+        return freed
+
     def destroy(self):                                  # set.go:202-214
         for b in self.blocks:
             b.release()

@@ -541,3 +541,38 @@ def test_tensor_path_certificate_fallback(gpu_ctx):
     assert stats["uncertified_queries"] > 0 or stats["scan_launches"] >= 1
     _assert_same(got, ost.search(-10.0, limit, queries), "certificate fallback")
     cache.Close()
+
+
+# ------------------------------------------------------------------ compaction (not in the reference)
+def test_compact_reclaims_tombstones(gpu_ctx):
+    """gf_set_compact packs live rows per block and shrinks NextIndex: the scan gets shorter, live rows keep
+    their order, Delete / Add / Search keep agreeing with the oracle's model of the same operation."""
+    cache, st, ost = _pair(gpu_ctx, "compact", 512, 4, 1000, 8)
+    rows = ol.synth_rows(71, 0, 4500, 512)
+    ids = ["z%05d" % i for i in range(4500)]
+    st.AddArray(rows, ids)
+    ost.add(rows, ids)
+    rng = np.random.default_rng(2)
+    kill = [ids[i] for i in sorted(set(rng.integers(0, 4500, 1800).tolist()))]
+    kill += ids[2000:3000]                                              # one block loses every row
+    assert sorted(st.Delete(*kill)) == sorted(ost.delete(kill))
+    q = ol.synth_rows(72, 0, 4, 512)
+    before = st.SearchArray(0.0, 20, q)
+    assert st.ScannedRows() == 4500
+    freed = st.Compact()
+    assert freed == ost.compact() == 4500 - st.LiveRows()
+    assert st.ScannedRows() == st.LiveRows() == sum(b.next_index for b in ost.blocks)
+    after = st.SearchArray(0.0, 20, q)
+    _assert_same(after, ost.search(0.0, 20, q), "after compact")
+    assert [[r.ID for r in row] for row in after] == [[r.ID for r in row] for row in before]   # positive scores: same hits
+    assert st.Compact() == 0                                            # idempotent
+    more = ol.synth_rows(73, 0, 1200, 512)
+    mids = ["y%05d" % i for i in range(1200)]
+    st.AddArray(more, mids)                                             # fills the reclaimed tails first
+    ost.add(more, mids)
+    assert st.BlockCount() == len(ost.blocks)
+    assert sorted(st.Delete(ids[1], mids[7], "nope") or []) == sorted(ost.delete([ids[1], mids[7], "nope"]))
+    _assert_same(st.SearchArray(-1.0, 50, q), ost.search(-1.0, 50, q), "after refill")
+    got = st.Read(mids[0], ids[4499] if ids[4499] not in kill else mids[1])
+    assert got and got[0].Value == more[0].tobytes()
+    cache.Close()
