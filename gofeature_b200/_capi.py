@@ -76,6 +76,7 @@ SIGNATURES = {
     "gf_set_search": (c_int, [c_vp, c_f32, c_int, c_int, c_vp, c_u64, P(c_vp)]),
     "gf_set_destroy": (c_int, [c_vp]),
     "gf_set_compact": (c_int, [c_vp, P(c_i64)]),
+    "gf_set_export": (c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, c_vp, P(c_i64), P(c_u64)]),
     "gf_set_dims": (c_int, [c_vp]),
     "gf_set_precision": (c_int, [c_vp]),
     "gf_set_batch": (c_int, [c_vp]),

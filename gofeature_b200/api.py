@@ -406,6 +406,18 @@ class Set:
         _check(lib().gf_set_compact(self._h, ctypes.byref(n)))
         return n.value
 
+    def Export(self):
+        """All live rows in slot order: (float32 array [rows, dims], list of ids).  SURVEY 8f N3."""
+        n, nb = c_i64(0), c_u64(0)
+        _check(lib().gf_set_export(self._h, None, 0, None, 0, None, ctypes.byref(n), ctypes.byref(nb)))
+        vals = np.zeros((max(n.value, 1), self.Dims()), dtype=np.float32)
+        idb = ctypes.create_string_buffer(max(1, nb.value))
+        off = np.zeros(n.value + 1, dtype=np.uint64)
+        _check(lib().gf_set_export(self._h, vals.ctypes.data, vals.nbytes, idb, nb.value, off.ctypes.data,
+                                   ctypes.byref(n), ctypes.byref(nb)))
+        raw = idb.raw
+        return vals[:n.value], [_decode_id(raw[int(off[i]):int(off[i + 1])]) for i in range(n.value)]
+
     def SetShard(self, rank, world):
         _check(lib().gf_set_set_shard(self._h, rank, world))
 

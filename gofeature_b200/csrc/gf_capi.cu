@@ -677,6 +677,16 @@ int gf_set_compact(gf_set *set, int64_t *out_reclaimed_rows)
     return guarded([&]() -> int { return set->compact(out_reclaimed_rows); });
 }
 
+int gf_set_export(gf_set *set, void *out_values, uint64_t values_cap, char *out_ids, uint64_t ids_cap,
+                  uint64_t *out_id_offsets, int64_t *out_rows, uint64_t *out_id_bytes)
+{
+    if (!set) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        return set->export_rows((uint8_t *)out_values, values_cap, out_ids, ids_cap, out_id_offsets, out_rows,
+                                out_id_bytes);
+    });
+}
+
 int gf_set_dims(const gf_set *set) { return set ? set->dims : 0; }
 int gf_set_precision(const gf_set *set) { return set ? set->precision : 0; }
 int gf_set_batch(const gf_set *set) { return set ? set->batch : 0; }

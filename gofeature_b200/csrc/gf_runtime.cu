@@ -1041,6 +1041,48 @@ int Set::compact(int64_t *reclaimed)
     return rebuild_segments();
 }
 
+int Set::export_rows(uint8_t *out_values, uint64_t values_cap, char *out_ids, uint64_t ids_cap, uint64_t *out_off,
+                     int64_t *out_rows, uint64_t *out_id_bytes)
+{
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    SharedGuard g(lock);
+    int rc = ctx->bind();
+    if (rc) return rc;
+    const size_t rowb = (size_t)dims * precision;
+    int64_t rows = 0;
+    uint64_t idb = 0;
+    for (const Block *b : blocks)
+        for (int r = 0; r < b->next_index; ++r)
+            if (b->live[r]) {
+                ++rows;
+                idb += b->id_at(r).size();
+            }
+    if (out_rows) *out_rows = rows;
+    if (out_id_bytes) *out_id_bytes = idb;
+    if (!out_values && !out_ids && !out_off) return GF_OK;  // size query
+    if (!out_values || !out_ids || !out_off) return GF_ERR_INVALID_ARGUMENT;
+    if (values_cap < (uint64_t)rows * rowb || ids_cap < idb) return GF_ERR_BUFFER_WRITE_OUT_OF_RANGE;
+    std::vector<uint8_t> tmp;
+    int64_t k = 0;
+    uint64_t io = 0;
+    out_off[0] = 0;
+    for (const Block *b : blocks) {
+        if (b->next_index == 0) continue;
+        tmp.resize((size_t)b->next_index * rowb);
+        GF_CUDA(cudaMemcpy(tmp.data(), b->dev, tmp.size(), cudaMemcpyDeviceToHost), GF_ERR_READ_CUDA_BUFFER);
+        ctx->stats.d2h_bytes += tmp.size();
+        for (int r = 0; r < b->next_index; ++r) {
+            if (!b->live[r]) continue;
+            memcpy(out_values + (size_t)k * rowb, tmp.data() + (size_t)r * rowb, rowb);
+            const std::string id = b->id_at(r);
+            memcpy(out_ids + io, id.data(), id.size());
+            io += id.size();
+            out_off[++k] = io;
+        }
+    }
+    return GF_OK;
+}
+
 // set.go:202-214
 int Set::destroy()
 {

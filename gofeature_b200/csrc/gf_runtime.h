@@ -291,7 +291,9 @@ struct gf_set {
                       cudaStream_t stream);
     int resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out);
     int destroy();
-    int compact(int64_t *reclaimed);  // pack live rows, shrink NextIndex
+    int compact(int64_t *reclaimed);
+    int export_rows(uint8_t *out_values, uint64_t values_cap, char *out_ids, uint64_t ids_cap, uint64_t *out_off,
+                    int64_t *out_rows, uint64_t *out_id_bytes);  // SURVEY 8f N3  // pack live rows, shrink NextIndex
     // top-K over the scanned rows into d_out; read lock held by the caller.
     //   per_segment: d_out is [pass][segment][qp][K] (qp = queries of that pass), else [q][K]
     //   path: 0 = choose (tensor cores for q >= 9 on large sets), 1 = fused scan only, 2 = tensor path

@@ -206,6 +206,12 @@ GF_API int gf_set_destroy(gf_set *set);
  * out_reclaimed_rows = rows a search no longer scans.  Slot order of live rows is preserved. */
 GF_API int gf_set_compact(gf_set *set, int64_t *out_reclaimed_rows);
 
+/* Bulk export (the reference has no persistence): every live row in slot order, with its id.
+ * Call once with NULL buffers to learn out_rows / out_id_bytes, then with buffers of rows*dims*precision
+ * bytes, out_id_bytes bytes and rows+1 offsets.  Re-import with gf_set_add. */
+GF_API int gf_set_export(gf_set *set, void *out_values, uint64_t values_cap, char *out_ids, uint64_t ids_cap,
+                         uint64_t *out_id_offsets, int64_t *out_rows, uint64_t *out_id_bytes);
+
 GF_API int gf_set_dims(const gf_set *set);
 GF_API int gf_set_precision(const gf_set *set);
 GF_API int gf_set_batch(const gf_set *set);

@@ -576,3 +576,27 @@ def test_compact_reclaims_tombstones(gpu_ctx):
     got = st.Read(mids[0], ids[4499] if ids[4499] not in kill else mids[1])
     assert got and got[0].Value == more[0].tobytes()
     cache.Close()
+
+
+def test_export_and_reimport_round_trip(gpu_ctx):
+    """gf_set_export: live rows + ids in slot order; a set rebuilt from them answers alike."""
+    cache, st, ost = _pair(gpu_ctx, "export", 256, 3, 600, 12)
+    rows = ol.synth_rows(81, 0, 2000, 256)
+    ids = ["e%04d" % i for i in range(2000)]
+    st.AddArray(rows, ids)
+    st.AddSynthetic(500, 82, first_ordinal=7)                          # implicit ids export too
+    kill = ids[5:900:7] + ["f%011d" % 9]
+    st.Delete(*kill)
+    vals, out_ids = st.Export()
+    dead = set(kill)
+    want_ids = [i for i in ids if i not in dead] + ["f%011d" % (7 + i) for i in range(500) if 7 + i != 9]
+    assert out_ids == want_ids and vals.shape == (len(want_ids), 256) and st.LiveRows() == len(want_ids)
+    assert vals[0].tobytes() == rows[0].tobytes()
+    assert vals[len(want_ids) - 1].tobytes() == ol.synth_rows(82, 7 + 499, 1, 256)[0].tobytes()
+    cache.NewSet("reimport", 256, 4, 3)
+    st2 = cache.GetSet("reimport")
+    st2.AddArray(vals, out_ids)
+    q = ol.synth_rows(83, 0, 3, 256)
+    a, b = st.SearchArray(0.0, 15, q), st2.SearchArray(0.0, 15, q)
+    assert [[(r.ID, r.Score) for r in row] for row in a] == [[(r.ID, r.Score) for r in row] for row in b]
+    cache.Close()
