@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
             for (int b = 0; b < RB; ++b)
 #pragma unroll
                 for (int j = 0; j < CH; ++j) x[b][j] = tile[(size_t)(r0 + b) * (D / 4) + j * 32 + lane];
+            if (rb + RB >= RPW) {
+                // this warp's last rows of the tile are in registers: hand the stage back to the producer now,
+                // the arithmetic, the butterfly and the gate no longer need shared memory
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
             float tsum[V];
 #pragma unroll
             for (int b = 0; b < RB; ++b) {
@@ -234,8 +240,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
                 offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == stages) {
             s = 0;
             ph ^= 1;
