@@ -600,3 +600,52 @@ def test_export_and_reimport_round_trip(gpu_ctx):
     a, b = st.SearchArray(0.0, 15, q), st2.SearchArray(0.0, 15, q)
     assert [[(r.ID, r.Score) for r in row] for row in a] == [[(r.ID, r.Score) for r in row] for row in b]
     cache.Close()
+
+
+# ------------------------------------------------------------------ random operation sequences
+@pytest.mark.parametrize("dims,block_rows,seed", [(8, 37, 1), (128, 300, 2), (512, 256, 3), (100, 64, 4)])
+def test_random_operation_sequences(gpu_ctx, dims, block_rows, seed):
+    """Interleaved Add / Delete / Update / Compact / Search with random sizes, thresholds and limits; after
+    every step the CUDA path and the oracle's model must agree on everything observable."""
+    from gofeature_b200 import api
+    cache, st, ost = _pair(gpu_ctx, "seq%d" % seed, dims, 6, block_rows, 40)
+    rng = np.random.default_rng(seed)
+    alive, nid = [], 0
+    for step in range(40):
+        op = rng.choice(["add", "add", "delete", "update", "compact", "search", "search"])
+        if op == "add" or not alive:
+            n = int(rng.integers(1, 3 * block_rows))
+            if len(alive) + n > 30 * block_rows:
+                continue
+            rows = ol.synth_rows(1000 * seed + step, 0, n, dims, normalize=bool(rng.integers(0, 2)))
+            ids = ["i%06d" % (nid + i) for i in range(n)]
+            nid += n
+            st.AddArray(rows, ids)
+            ost.add(rows, ids)
+            alive += ids
+        elif op == "delete":
+            k = int(rng.integers(1, max(2, len(alive) // 3)))
+            kill = [alive[i] for i in sorted(set(rng.integers(0, len(alive), k).tolist()))] + ["ghost%d" % step]
+            assert sorted(st.Delete(*kill) or []) == sorted(ost.delete(kill))
+            dead = set(kill)
+            alive = [a for a in alive if a not in dead]
+        elif op == "update":
+            pick = [alive[int(i)] for i in rng.integers(0, len(alive), 3)] + ["ghost"]
+            new = ol.synth_rows(77 * seed + step, 0, len(pick), dims)
+            got = st.Update(*[api.Feature(new[i].tobytes(), pick[i]) for i in range(len(pick))])
+            assert set(got or []) == set(pick[:-1])
+            for i, ident in enumerate(pick[:-1]):      # the model has no Update (a TODO stub in the reference):
+                for b in ost.blocks:                   # overwrite the row the id lives in
+                    if ident in b.ids:
+                        b.rows[len(b.ids) - 1 - b.ids[::-1].index(ident)] = new[i]
+                        break
+        elif op == "compact":
+            assert st.Compact() == ost.compact()
+        assert st.LiveRows() == len(alive) and st.ScannedRows() == sum(b.next_index for b in ost.blocks)
+        q = ol.synth_rows(5000 * seed + step, 0, int(rng.integers(1, 7)), dims)
+        limit = int(rng.choice([1, 3, 10, 40, 200, 1500]))
+        thr = float(rng.choice([-10.0, -0.1, 0.0, 0.05]))
+        _assert_same(st.SearchArray(thr, limit, q), ost.search(thr, limit, q), "step %d %s" % (step, op))
+    vals, out_ids = st.Export()
+    assert out_ids == [i for b in ost.blocks for i in b.ids[:b.next_index] if i != ""]
+    cache.Close()
