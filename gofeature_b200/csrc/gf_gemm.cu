@@ -17,6 +17,8 @@
 // (one thread), warps 2..5 epilogue (tcgen05.ld, one feature row per thread).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "gf_device.cuh"
 #include "gf_kernels.h"
 
@@ -127,21 +129,31 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
     valid = rows - row0 < (uint32_t)kTileRows ? rows - row0 : (uint32_t)kTileRows;
 }
 
-template <int NQ>
+// TM = feature-row tiles that share one load of the query operand.  The ring can only hold ~190 KB of
+// loads in flight; at NQ = 256 one K block is 16 KB of rows + 32 KB of queries per 512 MMA cycles, more
+// than the L2 latency lets 4 stages cover (measured: 53 % tensor utilisation, and sharing B across a CTA
+// pair by multicast did not help because the footprint per stage stayed).  With TM = 2 a stage feeds
+// 1024 MMA cycles with 64 KB, and the kernel goes back to being HBM-bound.
+template <int NQ, int TM>
 struct GemmCfg {
     static constexpr int kBBytes = NQ * kBK * 4;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (NQ <= 64) ? 6 : (NQ <= 128 ? 5 : 4);
-    static constexpr int kTmemCols = (2 * NQ < 32) ? 32 : 2 * NQ;
+    static constexpr int kStageBytes = TM * kABytes + kBBytes;
+    static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 8 - 1024) / kStageBytes);
+    static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+    static constexpr int kBuf = (2 * TM * NQ <= 512) ? 2 : 1;  // accumulator sets (double buffering when TMEM allows)
+    static constexpr int kTmemColsRaw = kBuf * TM * NQ;
+    static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
     static constexpr int kChunk = (NQ >= 32) ? 32 : 16;
     static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 8;
+    static_assert(kStages >= 2, "pipeline too shallow");
+    static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
 
-template <int NQ>
+template <int NQ, int TM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
 {
-    using Cfg = GemmCfg<NQ>;
+    using Cfg = GemmCfg<NQ, TM>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *tail = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
@@ -155,6 +167,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = a.dims / kBK;
+    const uint32_t ngroups = (a.tile_count + TM - 1) / TM;  // a group = TM consecutive tiles of this launch
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
@@ -187,17 +200,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0, segi = 0;
-            for (uint32_t i = blockIdx.x; i < a.tile_count; i += gridDim.x) {
-                const uint32_t t = a.tile_first + i * a.tile_stride;
-                uint32_t row0, valid;
-                locate_tile(a, t, segi, row0, valid);
-                const int slab_row = (int)((a.segs[segi].base - a.slab_base) / a.dims) + (int)row0;
+            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+                int slab_row[TM];
+#pragma unroll
+                for (int j = 0; j < TM; ++j) {
+                    uint32_t i = g * TM + j;
+                    if (i >= a.tile_count) i = a.tile_count - 1;  // odd tail: shadow the last tile
+                    const uint32_t t = a.tile_first + i * a.tile_stride;
+                    uint32_t row0, valid;
+                    locate_tile(a, t, segi, row0, valid);
+                    slab_row[j] = (int)((a.segs[segi].base - a.slab_base) / a.dims) + (int)row0;
+                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-                    tma_load_2d(sa, &tmA, kb * kBK, slab_row, &full[s]);
-                    tma_load_2d(sa + kABytes, &tmB, kb * kBK, 0, &full[s]);
+#pragma unroll
+                    for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
+                    tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
@@ -211,27 +231,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             constexpr uint32_t idesc = instr_desc_tf32(kTileRows, NQ);
             int s = 0;
             uint32_t ph = 0, it = 0;
-            for (uint32_t i = blockIdx.x; i < a.tile_count; i += gridDim.x, ++it) {
-                const uint32_t acc = it & 1;
-                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+                const uint32_t buf = it % Cfg::kBuf;
+                mbar_wait(&tempty[buf], ((it / Cfg::kBuf) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + acc * NQ;
+                const uint32_t d_addr = tmem_base + buf * (TM * NQ);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
-                    const uint64_t adesc = smem_desc_sw128(sa);
-                    const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+                    const uint64_t bdesc = smem_desc_sw128(sa + TM * kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
-                        tc_mma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    for (int j = 0; j < TM; ++j) {
+                        const uint64_t adesc = smem_desc_sw128(sa + j * kABytes);
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
+                            tc_mma_tf32(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                        (uint32_t)((kb | k) != 0));
+                    }
                     tc_commit(&empty[s]);  // frees the stage when these MMAs have read it
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
                     }
                 }
-                tc_commit(&tfull[acc]);  // accumulator complete
+                tc_commit(&tfull[buf]);  // accumulators of the group complete
             }
         }
     } else {
@@ -239,83 +263,95 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const int quarter = warp & 3;  // TMEM lanes this warp may read
         const uint32_t row = quarter * 32 + lane;
         uint32_t it = 0, segi = 0;
-        for (uint32_t i = blockIdx.x; i < a.tile_count; i += gridDim.x, ++it) {
-            const uint32_t t = a.tile_first + i * a.tile_stride;
-            uint32_t row0, valid;
-            locate_tile(a, t, segi, row0, valid);
-            const bool live = row < valid;
-            const uint32_t slot = a.segs[segi].slot_base + row0 + row;
-            const uint32_t acc = it & 1;
-            mbar_wait(&tfull[acc], (it >> 1) & 1);
+        for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+            const uint32_t buf = it % Cfg::kBuf;
+            mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < NQ; c0 += Cfg::kChunk) {
-                uint32_t r[Cfg::kChunk];
-                tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NQ + c0, r);
-                tmem_ld_wait();
-                if (a.mode == 0) {
-                    // COLLECT: fixed per-query threshold, atomic append of the rare survivor
-                    unsigned pass = 0;
+            for (int j = 0; j < TM; ++j) {
+                const uint32_t i = g * TM + j;
+                if (i >= a.tile_count) break;  // shadow tile of an odd tail: nothing to report
+                const uint32_t t = a.tile_first + i * a.tile_stride;
+                uint32_t row0, valid;
+                locate_tile(a, t, segi, row0, valid);
+                const bool live = row < valid;
+                const uint32_t slot = a.segs[segi].slot_base + row0 + row;
+                const uint32_t acc_col = buf * (TM * NQ) + j * NQ;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NQ; c0 += Cfg::kChunk) {
+                    uint32_t r[Cfg::kChunk];
+                    tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + c0, r);
+                    tmem_ld_wait();
+                    if (a.mode == 0) {
+                        // COLLECT: fixed per-query threshold, atomic append of the rare survivor
+                        unsigned pass = 0;
+                        const float4 *thr4 = reinterpret_cast<const float4 *>(thr_s + c0);  // 16-byte aligned
 #pragma unroll
-                    for (int j = 0; j < Cfg::kChunk; ++j)
-                        pass |= (__uint_as_float(r[j]) > thr_s[c0 + j]) ? (1u << j) : 0u;
-                    if (!live) pass = 0;
-                    while (pass) {
-                        const int j = __ffs(pass) - 1;
-                        pass &= pass - 1;
-                        float sc = 0.f;
+                        for (int jj = 0; jj < Cfg::kChunk; jj += 4) {
+                            const float4 th = thr4[jj >> 2];
+                            pass |= (__uint_as_float(r[jj + 0]) > th.x) ? (1u << (jj + 0)) : 0u;
+                            pass |= (__uint_as_float(r[jj + 1]) > th.y) ? (1u << (jj + 1)) : 0u;
+                            pass |= (__uint_as_float(r[jj + 2]) > th.z) ? (1u << (jj + 2)) : 0u;
+                            pass |= (__uint_as_float(r[jj + 3]) > th.w) ? (1u << (jj + 3)) : 0u;
+                        }
+                        if (!live) pass = 0;
+                        while (pass) {
+                            const int b = __ffs(pass) - 1;
+                            pass &= pass - 1;
+                            float sc = 0.f;
+#pragma unroll
+                            for (int jj = 0; jj < Cfg::kChunk; ++jj)
+                                if (jj == b) sc = __uint_as_float(r[jj]);
+                            const int qi = c0 + b;
+                            const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
+                            if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
+                        }
+                    } else if (a.mode == 1) {
+                        // TILEMAX: per query the best score of this tile (threshold estimation sample)
+                        float v[Cfg::kChunk];
 #pragma unroll
                         for (int jj = 0; jj < Cfg::kChunk; ++jj)
-                            if (jj == j) sc = __uint_as_float(r[jj]);
-                        const int qi = c0 + j;
-                        const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
-                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
-                    }
-                } else if (a.mode == 1) {
-                    // TILEMAX: per query the best score of this tile (threshold estimation sample)
-                    float v[Cfg::kChunk];
+                            v[jj] = live ? __uint_as_float(r[jj]) : __int_as_float(0xff800000);
+                        // transposed max-reduce: lane jj ends with the max of column c0 + jj over 32 rows
+                        int off = 16;
 #pragma unroll
-                    for (int j = 0; j < Cfg::kChunk; ++j)
-                        v[j] = live ? __uint_as_float(r[j]) : __int_as_float(0xff800000);
-                    // transposed max-reduce: lane j ends with the max of column c0 + j over 32 rows
-                    int off = 16;
+                        for (int n = Cfg::kChunk; n > 1; n >>= 1) {
+                            const bool up = (lane & off) != 0;
 #pragma unroll
-                    for (int n = Cfg::kChunk; n > 1; n >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int k = 0; k < n / 2; ++k) {
-                            const float send = up ? v[k] : v[k + n / 2];
-                            const float keep = up ? v[k + n / 2] : v[k];
-                            v[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+                            for (int k = 0; k < n / 2; ++k) {
+                                const float send = up ? v[k] : v[k + n / 2];
+                                const float keep = up ? v[k + n / 2] : v[k];
+                                v[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+                            }
+                            off >>= 1;
                         }
-                        off >>= 1;
-                    }
-                    float m = v[0];
-                    for (; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                    const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
-                    if (Cfg::kChunk == 32 || (lane & 1) == 0) atomicMax(&tmax_s[col], score_image(m));
-                } else {
-                    // DUMP: every score, coalesced over rows (small sets and diagnostics)
-                    if (live) {
+                        float m = v[0];
+                        for (; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                        const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
+                        if (Cfg::kChunk == 32 || (lane & 1) == 0) atomicMax(&tmax_s[col], score_image(m));
+                    } else {
+                        // DUMP: every score, coalesced over rows (small sets and diagnostics)
+                        if (live) {
 #pragma unroll
-                        for (int j = 0; j < Cfg::kChunk; ++j)
-                            if (c0 + j < a.q)
-                                a.dump[(size_t)(c0 + j) * a.dump_ld + (size_t)i * kTileRows + row] =
-                                    __uint_as_float(r[j]);
+                            for (int jj = 0; jj < Cfg::kChunk; ++jj)
+                                if (c0 + jj < a.q)
+                                    a.dump[(size_t)(c0 + jj) * a.dump_ld + (size_t)i * kTileRows + row] =
+                                        __uint_as_float(r[jj]);
+                        }
                     }
+                }
+                if (a.mode == 1) {
+                    named_bar_sync(2, 128);
+                    for (int c = threadIdx.x - 64; c < NQ; c += 128) {
+                        a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
+                        tmax_s[c] = 0u;
+                    }
+                    named_bar_sync(2, 128);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (a.mode == 1) {
-                named_bar_sync(2, 128);
-                for (int c = threadIdx.x - 64; c < NQ; c += 128) {
-                    a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
-                    tmax_s[c] = 0u;
-                }
-                named_bar_sync(2, 128);
-            }
+            if (lane == 0) mbar_arrive(&tempty[buf]);
         }
     }
     tc_fence_before();
@@ -588,14 +624,18 @@ cudaError_t make_map(CUtensorMap *map, const float *base, uint64_t rows, int dim
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int NQ>
-cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int grid,
+template <int NQ, int TM>
+cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms,
                         cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)GemmCfg<NQ>::kSmem);
+    using Cfg = GemmCfg<NQ, TM>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<NQ, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmem);
     if (e != cudaSuccess) return e;
-    gemm_tf32_kernel<NQ><<<grid, kGemmThreads, GemmCfg<NQ>::kSmem, stream>>>(tmA, tmB, a);
+    const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
+    const int grid = sms < (int)ngroups ? sms : (int)ngroups;
+    if (grid < 1) return cudaSuccess;
+    gemm_tf32_kernel<NQ, TM><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, a);
     return cudaGetLastError();
 }
 
@@ -636,14 +676,18 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.tilemax = g.d_tilemax;
     a.dump = g.d_dump;
     a.dump_ld = g.dump_ld;
-    int grid = g.sms < (int)g.tile_count ? g.sms : (int)g.tile_count;
-    if (grid < 1) return cudaSuccess;
+    if (g.tile_count < 1) return cudaSuccess;
+    static const int tm_big = getenv("GF_GEMM_TM2") ? 2 : 1;  // tuning knob (TM = 2 measured slower: 0.58 vs 0.40 ms at NQ = 256)
     switch (g.nq) {
-        case 16: return launch_gemm<16>(tmA, tmB, a, grid, stream);
-        case 32: return launch_gemm<32>(tmA, tmB, a, grid, stream);
-        case 64: return launch_gemm<64>(tmA, tmB, a, grid, stream);
-        case 128: return launch_gemm<128>(tmA, tmB, a, grid, stream);
-        case 256: return launch_gemm<256>(tmA, tmB, a, grid, stream);
+        case 16: return launch_gemm<16, 1>(tmA, tmB, a, g.sms, stream);
+        case 32: return launch_gemm<32, 1>(tmA, tmB, a, g.sms, stream);
+        case 64: return launch_gemm<64, 1>(tmA, tmB, a, g.sms, stream);
+        case 128:
+            return tm_big == 2 ? launch_gemm<128, 2>(tmA, tmB, a, g.sms, stream)
+                               : launch_gemm<128, 1>(tmA, tmB, a, g.sms, stream);
+        case 256:
+            return tm_big == 2 ? launch_gemm<256, 2>(tmA, tmB, a, g.sms, stream)
+                               : launch_gemm<256, 1>(tmA, tmB, a, g.sms, stream);
     }
     return cudaErrorInvalidValue;
 }
