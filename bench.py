@@ -14,7 +14,10 @@ single-query searchers.  One "step" serves one query from each of the 10 searche
   e2e       the same through the public host-buffer call (gf_set_search at N = 1, the collective
             ShardedSet.search_keys at N > 1): H2D of the queries and D2H of the winners inside
             the timed region, wall clock bracketed by device synchronisation.
-  roofline  the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  roofline  the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  With the
+            bf16 shadow slab (default) that kernel is the tcgen05 kind::f16 candidate pass and its algorithmic
+            bytes are the SHADOW bytes it must stream (rows x dims x 2), not the float32 bytes: the
+            fraction says how well the kernel uses HBM, the halved traffic shows up in `value`.
   cpu_baseline / --impl reference
             the oracle's plain multi-threaded CPU scan ("port": the reference has no CPU build and
             there is no Go toolchain) on a bounded row sample, scaled to 1 M rows.
@@ -101,9 +104,10 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_from_profile():
-    """dram bytes per scan launch from the committed ncu --set full capture, if any."""
-    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+def traffic_from_profile(eb):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture of the same
+    kernel (eb = bytes per element it streams: 4 float32 rows, 2 bf16 shadow), if any."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json" if eb == 4 else "shadow_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f).get("dram_bytes_per_launch")
@@ -169,7 +173,10 @@ def run_reference(args, rank, world):
 
 
 def bench_config(args, world):
-    return {"workload": "BASELINE configs[1]: %d x %d-d normalised float32 rows per GPU (%d blocks of 32 MiB), "
+    shadow = not getattr(args, "no_shadow", False)
+    return {"shadow": "bf16 shadow slab (+50% HBM per row), candidates re-scored from the float32 rows" if shadow
+            else "none (float32 rows only)",
+            "workload": "BASELINE configs[1]: %d x %d-d normalised float32 rows per GPU (%d blocks of 32 MiB), "
                         "top-%d, %d concurrent single-query searchers per step"
                         % (args.rows_per_gpu, DIMS, (args.rows_per_gpu + 16383) // 16384, args.limit, args.queries),
             "rows_per_gpu": args.rows_per_gpu, "rows_total": args.rows_per_gpu * world, "dims": DIMS,
@@ -206,7 +213,8 @@ def run_ours(args, rank, world, local_rank):
     ctx = api.NewContext(local_rank)
     cap = BLOCK_SIZE // (DIMS * 4)
     gblocks = (rows_total + cap - 1) // cap
-    cache = api.NewCache(ctx, (gblocks + world - 1) // world + 1, BLOCK_SIZE)
+    cache = api.NewCache(ctx, (gblocks + world - 1) // world + 1, BLOCK_SIZE, shadow=not args.no_shadow)
+    shadow = cache.HasShadow()
     sset = ShardedSet(ctx, cache, "bench", DIMS, max(Q, 16), rank, world)
     sset.AddSynthetic(rows_total, SEED)
     rows_local = sset.local.ScannedRows()
@@ -303,7 +311,11 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         s1 = ctx.Stats()
         ctx.SetProfiling(False)
-        q1_ms = s1["scan_kernel_ns"] / 1e6 / max(s1["scan_kernel_timed"], 1)
+        q1_tensor = s1["tensor_passes"] > 0
+        if q1_tensor:
+            q1_ms = s1["gemm_kernel_ns"] / 1e6 / max(s1["gemm_kernel_timed"], 1)
+        else:
+            q1_ms = s1["scan_kernel_ns"] / 1e6 / max(s1["scan_kernel_timed"], 1)
     # ---- config[1] exactly as written: 10 concurrent host threads, one query each, through the C ABI
     # (tools/gf_demo, the counterpart of the reference's demo/main.go), request coalescing on
     demo = None
@@ -333,7 +345,8 @@ def run_ours(args, rank, world, local_rank):
 
     peak, peak_src = hbm_peak()
     avg_q = Q / scans_per_step if scans_per_step else Q
-    alg_bytes = rows_local * DIMS * 4 + avg_q * DIMS * 4 + avg_q * K * 8
+    eb = 2 if (tensor and shadow) else 4   # bytes per element the dominant kernel streams
+    alg_bytes = rows_local * DIMS * eb + avg_q * DIMS * eb + avg_q * K * 8
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     qps_user = Q * args.steps / (dev_ms * 1e-3)
     e2e_user = Q * args.steps / (e2e_ms * 1e-3)
@@ -350,8 +363,13 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches), "tensor_passes": stats["tensor_passes"],
         "uncertified_queries": stats["uncertified_queries"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic_from_profile(),
-                     "kernel": "gemm_tf32_kernel<16> (tcgen05 COLLECT pass)" if tensor else "scan_tma_kernel<512,QT>",
+                     "frac": achieved / peak if peak else None, "traffic": traffic_from_profile(eb),
+                     "kernel": ("gemm_kernel<16,1,%d> (tcgen05 %s COLLECT pass over the %s)"
+                                % (eb, "kind::f16 bf16" if eb == 2 else "kind::tf32",
+                                   "bf16 shadow slab" if eb == 2 else "float32 rows")) if tensor
+                     else "scan_tma_kernel<512,QT>",
+                     "bytes_per_element": eb,
+                     "frac_if_counted_as_f32_bytes": (achieved * 4 / eb) / peak if peak else None,
                      "launches_per_step": scans_per_step,
                      "avg_launch_ms": scan_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "timed": "CUDA events around each launch, second pass of the same %d steps" % args.steps,
@@ -373,9 +391,12 @@ def run_ours(args, rank, world, local_rank):
         line["e2e_parallel_error"] = demo
     if world == 1:
         l1 = sorted(x * 1e3 for x in lat1)
-        b1 = rows_local * DIMS * 4 + DIMS * 4 + K * 8
+        eb1 = 2 if (q1_tensor and shadow) else 4
+        b1 = rows_local * DIMS * eb1 + DIMS * eb1 + K * 8
         line["single_query"] = {"p50_ms": l1[len(l1) // 2], "p99_ms": l1[min(len(l1) - 1, int(len(l1) * 0.99))],
                                 "qps": 1e3 / (sum(l1) / len(l1)), "scan_kernel_ms": q1_ms,
+                                "kernel": "tcgen05 COLLECT pass" if q1_tensor else "scan_tma_kernel<512,1>",
+                                "bytes_per_element": eb1,
                                 "roofline_frac": (b1 / (q1_ms * 1e-3) / 1e9 / peak) if q1_ms > 0 else None,
                                 "achieved_gbs": (b1 / (q1_ms * 1e-3) / 1e9) if q1_ms > 0 else None}
         if not args.no_cpu_baseline:
@@ -402,6 +423,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shadow", action="store_true", help="float32 rows only (no bf16 shadow slab)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -52,6 +52,8 @@ SIGNATURES = {
     "gf_buffer_device_ptr": (c_vp, [c_vp]),
     "gf_buffer_free": (c_int, [c_vp]),
     "gf_cache_create": (c_int, [c_vp, c_int, c_i64, P(c_vp)]),
+    "gf_cache_create_ex": (c_int, [c_vp, c_int, c_i64, ctypes.c_uint, P(c_vp)]),
+    "gf_cache_has_shadow": (c_int, [c_vp]),
     "gf_cache_destroy": (c_int, [c_vp]),
     "gf_cache_new_set": (c_int, [c_vp, c_cp, c_int, c_int, c_int]),
     "gf_cache_destroy_set": (c_int, [c_vp, c_cp]),
@@ -104,6 +106,7 @@ SIGNATURES = {
     "gf_context_reset_stats": (c_int, [c_vp]),
     "gf_context_set_profiling": (c_int, [c_vp, c_int]),
     "gf_set_set_coalescing": (c_int, [c_vp, c_int]),
+    "gf_set_set_search_path": (c_int, [c_vp, c_int]),
 }
 
 _lib = None

@@ -424,6 +424,10 @@ class Set:
     def SetCoalescing(self, max_wait_us):
         _check(lib().gf_set_set_coalescing(self._h, max_wait_us))
 
+    def SetSearchPath(self, path):
+        """0 choose, 1 fused scan, 2 tensor path, 3 tensor path on the float32 rows (kind::tf32)."""
+        _check(lib().gf_set_set_search_path(self._h, path))
+
     def Dims(self):
         return lib().gf_set_dims(self._h)
 
@@ -463,6 +467,9 @@ class Cache:
     def GetBlockSize(self):
         return int(lib().gf_cache_get_block_size(self._h))
 
+    def HasShadow(self):
+        return bool(lib().gf_cache_has_shadow(self._h))
+
     def GetEmptyBlock(self, blocknum):
         arr = (c_vp * max(blocknum, 1))()
         _check(lib().gf_cache_get_empty_block(self._h, blocknum, arr))
@@ -482,10 +489,19 @@ class Cache:
             self._h = None
 
 
-def NewCache(ctx, blockNum, blockSize):
-    """cache.go:21-43."""
+CACHE_NO_SHADOW = 1
+CACHE_REQUIRE_SHADOW = 2
+
+
+def NewCache(ctx, blockNum, blockSize, shadow=None):
+    """cache.go:21-43.  shadow: None = library default (a bf16 shadow slab unless GF_SHADOW=0),
+    False = none, True = required."""
     h = c_vp()
-    _check(lib().gf_cache_create(ctx._h, blockNum, blockSize, ctypes.byref(h)))
+    if shadow is None:
+        _check(lib().gf_cache_create(ctx._h, blockNum, blockSize, ctypes.byref(h)))
+    else:
+        flags = CACHE_REQUIRE_SHADOW if shadow else CACHE_NO_SHADOW
+        _check(lib().gf_cache_create_ex(ctx._h, blockNum, blockSize, flags, ctypes.byref(h)))
     return Cache(h, ctx)
 
 

@@ -370,6 +370,14 @@ int gf_buffer_free(gf_buffer *buf)
 // ------------------------------------------------------------------ Cache (cache.go)
 int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache **out_cache)
 {
+    const char *env = getenv("GF_SHADOW");  // "0" = no bf16 shadow slab
+    return gf_cache_create_ex(ctx, block_num, block_size, (env && env[0] == '0') ? GF_CACHE_NO_SHADOW : 0, out_cache);
+}
+
+int gf_cache_has_shadow(const gf_cache *cache) { return (cache && cache->shadow) ? 1 : 0; }
+
+int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsigned flags, gf_cache **out_cache)
+{
     if (!ctx || !out_cache || block_num < 0 || block_size <= 0) return GF_ERR_INVALID_ARGUMENT;
     *out_cache = nullptr;
     return guarded([&]() -> int {
@@ -388,12 +396,30 @@ int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache
             return cuda_fail(e, "cudaMemset", GF_ERR_CLEAR_CUDA_BUFFER);
         }
         c->slab = std::make_shared<DeviceAlloc>(ctx, p, total, true);
+        // bf16 shadow of the slab for the tensor path (half the bytes per scanned row).  It needs block_size / 2
+        // bytes per block; when the device cannot hold it the cache works without (GF_CACHE_REQUIRE_SHADOW: fail).
+        const bool want_shadow = !(flags & GF_CACHE_NO_SHADOW) && block_size % 2 == 0 && total > 0;
+        if (want_shadow) {
+            void *sp = nullptr;
+            cudaError_t se = cudaMalloc(&sp, total / 2 + 256);
+            if (se == cudaSuccess) se = cudaMemset(sp, 0, total / 2 + 256);
+            if (se != cudaSuccess) {
+                if (sp) cudaFree(sp);
+                cudaGetLastError();
+                if (flags & GF_CACHE_REQUIRE_SHADOW) return cuda_fail(se, "cudaMalloc(shadow)", GF_ERR_ALLOCATE_GPU_BUFFER);
+            } else {
+                c->shadow = std::make_shared<DeviceAlloc>(ctx, sp, total / 2, true);
+            }
+        } else if (flags & GF_CACHE_REQUIRE_SHADOW) {
+            return GF_ERR_INVALID_ARGUMENT;
+        }
         for (int i = 0; i < block_num; ++i) {  // cache.go:33-41
             std::unique_ptr<Block> b(new gf_block());
             b->cache = c.get();
             b->index = i;
             b->block_size = block_size;
             b->dev = (uint8_t *)p + (uint64_t)i * (uint64_t)block_size;
+            if (c->shadow) b->shadow = (uint8_t *)c->shadow->ptr + (uint64_t)i * (uint64_t)(block_size / 2);
             c->all_blocks.push_back(std::move(b));
         }
         *out_cache = c.release();
@@ -807,6 +833,13 @@ int gf_set_add_synthetic(gf_set *set, int64_t n, uint64_t seed, int64_t first_or
     return guarded([&]() -> int {
         return set->add_synthetic(n, seed, first_ordinal, normalize, id_prefix ? id_prefix : "f");
     });
+}
+
+int gf_set_set_search_path(gf_set *set, int path)
+{
+    if (!set || path < 0 || path > 3) return GF_ERR_INVALID_ARGUMENT;
+    set->search_path = path;
+    return GF_OK;
 }
 
 int gf_set_set_coalescing(gf_set *set, int max_wait_us)

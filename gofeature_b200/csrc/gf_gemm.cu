@@ -16,6 +16,7 @@
 // Warp roles (192 threads): warp 0 TMA producer (one thread), warp 1 TMEM allocator + MMA issuer
 // (one thread), warps 2..5 epilogue (tcgen05.ld, one feature row per thread).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <cstdlib>
 
@@ -28,15 +29,19 @@ namespace {
 
 constexpr int kGemmThreads = 192;
 constexpr int kTileRows = 128;
-constexpr int kBK = 32;  // floats per K block = one 128-byte swizzle row
-constexpr int kABytes = kTileRows * kBK * 4;
+constexpr int kABytes = kTileRows * 128;  // one K block = one 128-byte swizzle row per feature row
+// elements per K block: 32 floats (kind::tf32 on the fp32 slab) or 64 bf16 (kind::f16 on the bf16 shadow)
+template <int EB>
+struct KBlock {
+    static constexpr int kElems = 128 / EB;
+};
 
 struct GemmArgs {
     const Segment *segs;
     const uint32_t *gtile_start;  // nseg + 1, in 128-row tiles
     int nseg;
     int dims;
-    const float *slab_base;  // row 0 of tensor map A
+    const float *slab_base;  // row 0 of tensor map A (the shadow slab has the same row geometry)
     int mode;
     uint32_t tile_first, tile_stride, tile_count;
     int q;
@@ -64,16 +69,27 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, one K = 8 step of kind::tf32
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate)
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T over 32 bytes of K: one K = 8 step of kind::tf32 (EB = 4)
+// or one K = 16 step of kind::f16 with bf16 operands (EB = 2)
+template <int EB>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (EB == 4) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups,
@@ -87,10 +103,13 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(const void *p)
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
-__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A and B formats in bits
+// 7-9 / 10-12 (kind::tf32: TF32 = 2; kind::f16: BF16 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+template <int EB>
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((EB == 4 ? 2u : 1u) << 7) | ((EB == 4 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 template <int N>
@@ -136,7 +155,7 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
 // 1024 MMA cycles with 64 KB, and the kernel goes back to being HBM-bound.
 template <int NQ, int TM>
 struct GemmCfg {
-    static constexpr int kBBytes = NQ * kBK * 4;
+    static constexpr int kBBytes = NQ * 128;
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
     static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 8 - 1024) / kStageBytes);
     static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
@@ -149,9 +168,9 @@ struct GemmCfg {
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
 
-template <int NQ, int TM>
+template <int NQ, int TM, int EB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
 {
     using Cfg = GemmCfg<NQ, TM>;
     extern __shared__ uint8_t smem_raw[];
@@ -166,6 +185,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     unsigned int *tmax_s = reinterpret_cast<unsigned int *>(thr_s + NQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kBK = KBlock<EB>::kElems;
     const int kblocks = a.dims / kBK;
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;  // a group = TM consecutive tiles of this launch
 
@@ -228,7 +248,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc_tf32(kTileRows, NQ);
+            constexpr uint32_t idesc = instr_desc<EB>(kTileRows, NQ);
             int s = 0;
             uint32_t ph = 0, it = 0;
             for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
@@ -245,8 +265,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                     for (int j = 0; j < TM; ++j) {
                         const uint64_t adesc = smem_desc_sw128(sa + j * kABytes);
 #pragma unroll
-                        for (int k = 0; k < kBK / 8; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
-                            tc_mma_tf32(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
+                        for (int k = 0; k < 4; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
+                            tc_mma<EB>(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
                                         (uint32_t)((kb | k) != 0));
                     }
                     tc_commit(&empty[s]);  // frees the stage when these MMAs have read it
@@ -365,26 +385,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
 // ------------------------------------------------------------------ helper kernels
 // queries [q][dims] (any stride) -> padded row-major batch [nq][dims] (rows >= q zeroed) + |q|^2
+// With a bf16 shadow: dst_bf [nq][dims] = round-to-nearest bf16 of the batch, qres2 = |q - bf16(q)|^2.
 __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
                                     int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2,
-                                    float *__restrict__ copy)
+                                    float *__restrict__ copy, __nv_bfloat16 *__restrict__ dst_bf,
+                                    float *__restrict__ qres2)
 {
     const int qi = blockIdx.x;
-    float acc = 0.f;
+    float acc = 0.f, res = 0.f;
     for (int e = threadIdx.x; e < dims; e += blockDim.x) {
         float v = qi < q ? src[(long long)qi * q_stride + (long long)e * l_stride] : 0.f;
         dst[(size_t)qi * dims + e] = v;
         if (copy != nullptr && qi < q) copy[(size_t)qi * dims + e] = v;
         acc += v * v;
+        if (dst_bf != nullptr) {
+            const __nv_bfloat16 b = __float2bfloat16_rn(v);
+            dst_bf[(size_t)qi * dims + e] = b;
+            const float d = __bfloat162float(b) - v;
+            res += d * d;
+        }
     }
-    __shared__ float red[32];
-    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __shared__ float red[32], red2[32];
+    for (int off = 16; off >= 1; off >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        res += __shfl_xor_sync(0xffffffffu, res, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = acc;
+        red2[threadIdx.x >> 5] = res;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
-        qnorm2[qi] = t * 1.0001f;  // upper bound is what the certificate needs
+        float t = 0.f, t2 = 0.f;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) {
+            t += red[w];
+            t2 += red2[w];
+        }
+        qnorm2[qi] = t * 1.0001f;  // upper bounds are what the certificate needs
+        if (qres2 != nullptr) qres2[qi] = t2 * 1.0001f;
     }
 }
 
@@ -541,6 +579,7 @@ __global__ void __launch_bounds__(256)
                     const unsigned int *__restrict__ cnt, const float *__restrict__ thr, unsigned int cap, int kp,
                     int all, int K, long long rows_total, const float *__restrict__ qnorm2,
                     const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
+                    const float *__restrict__ qres2, const unsigned int *__restrict__ maxres2_bits,
                     unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags)
 {
     __shared__ unsigned long long buf[kGemmCandCap];
@@ -565,7 +604,15 @@ __global__ void __launch_bounds__(256)
             float ceil_approx = thr[qi];       // rows that were never collected have approx <= thr
             if (!all && n > (unsigned)kp)      // collected but not among the best kp by approx score
                 ceil_approx = fmaxf(ceil_approx, key_score(d_sel[(size_t)qi * kp + kp - 1]));
-            const float delta = err_coeff * sqrtf(__uint_as_float(*maxnorm2_bits)) * sqrtf(qnorm2[qi]);
+            // tf32: |approx - exact| <= coeff |row| |q| (operand truncation + accumulation).
+            // bf16 shadow (qres2 != null): approx - exact = <r^ - r, q^> + <r, q^ - q>, bounded by the MEASURED
+            // residual norms max|r^ - r| (kept current by shadow_rows_kernel) and |q^ - q|, with |q^| <=
+            // |q| (1 + 2^-9); coeff |row| |q| covers the fp32 accumulation inside the tensor core.
+            const float mn = sqrtf(__uint_as_float(*maxnorm2_bits)), qn = sqrtf(qnorm2[qi]);
+            float delta = err_coeff * mn * qn;
+            if (qres2 != nullptr)
+                delta += sqrtf(__uint_as_float(*maxres2_bits)) * qn * 1.002f + mn * sqrtf(qres2[qi]) +
+                         1e-30f * (1.f + qn);
             const unsigned long long kth = buf[keff - 1];
             if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
         }
@@ -610,32 +657,33 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
-cudaError_t make_map(CUtensorMap *map, const float *base, uint64_t rows, int dims, uint32_t box_rows)
+cudaError_t make_map(CUtensorMap *map, const void *base, uint64_t rows, int dims, uint32_t box_rows, int eb)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return cudaErrorNotSupported;
     cuuint64_t gdim[2] = {(cuuint64_t)dims, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dims * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dims * (cuuint64_t)eb};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / eb), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
+    CUresult r = fn(map, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base,
+                    gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int NQ, int TM>
+template <int NQ, int TM, int EB>
 cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms,
                         cudaStream_t stream)
 {
     using Cfg = GemmCfg<NQ, TM>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<NQ, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmem);
     if (e != cudaSuccess) return e;
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
     const int grid = sms < (int)ngroups ? sms : (int)ngroups;
     if (grid < 1) return cudaSuccess;
-    gemm_tf32_kernel<NQ, TM><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, a);
+    gemm_kernel<NQ, TM, EB><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, a);
     return cudaGetLastError();
 }
 
@@ -650,13 +698,36 @@ int gemm_pad_queries(int q)
     return 256;
 }
 
+template <int EB>
+static cudaError_t gemm_dispatch(const GemmLaunch &g, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a,
+                                 cudaStream_t stream)
+{
+    static const int tm_big = getenv("GF_GEMM_TM2") ? 2 : 1;  // tuning knob (TM = 2 measured slower: 0.58 vs 0.40 ms at NQ = 256)
+    switch (g.nq) {
+        case 16: return launch_gemm<16, 1, EB>(tmA, tmB, a, g.sms, stream);
+        case 32: return launch_gemm<32, 1, EB>(tmA, tmB, a, g.sms, stream);
+        case 64: return launch_gemm<64, 1, EB>(tmA, tmB, a, g.sms, stream);
+        case 128:
+            return tm_big == 2 ? launch_gemm<128, 2, EB>(tmA, tmB, a, g.sms, stream)
+                               : launch_gemm<128, 1, EB>(tmA, tmB, a, g.sms, stream);
+        case 256:
+            return tm_big == 2 ? launch_gemm<256, 2, EB>(tmA, tmB, a, g.sms, stream)
+                               : launch_gemm<256, 1, EB>(tmA, tmB, a, g.sms, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
 {
-    if (g.dims % kBK != 0 || g.q < 1 || g.q > g.nq) return cudaErrorInvalidValue;
+    const bool bf16 = g.shadow_base != nullptr;
+    const int eb = bf16 ? 2 : 4;
+    if (g.dims % (128 / eb) != 0 || g.q < 1 || g.q > g.nq) return cudaErrorInvalidValue;
+    if (bf16 && g.d_queries_bf16 == nullptr) return cudaErrorInvalidValue;
     CUtensorMap tmA, tmB;
-    cudaError_t e = make_map(&tmA, g.slab_base, g.slab_rows, g.dims, kTileRows);
+    cudaError_t e = make_map(&tmA, bf16 ? g.shadow_base : (const void *)g.slab_base, g.slab_rows, g.dims, kTileRows, eb);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, g.d_queries_padded, (uint64_t)g.nq, g.dims, (uint32_t)g.nq);
+    e = make_map(&tmB, bf16 ? g.d_queries_bf16 : (const void *)g.d_queries_padded, (uint64_t)g.nq, g.dims,
+                 (uint32_t)g.nq, eb);
     if (e != cudaSuccess) return e;
     GemmArgs a{};
     a.segs = g.d_segs;
@@ -677,25 +748,15 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.dump = g.d_dump;
     a.dump_ld = g.dump_ld;
     if (g.tile_count < 1) return cudaSuccess;
-    static const int tm_big = getenv("GF_GEMM_TM2") ? 2 : 1;  // tuning knob (TM = 2 measured slower: 0.58 vs 0.40 ms at NQ = 256)
-    switch (g.nq) {
-        case 16: return launch_gemm<16, 1>(tmA, tmB, a, g.sms, stream);
-        case 32: return launch_gemm<32, 1>(tmA, tmB, a, g.sms, stream);
-        case 64: return launch_gemm<64, 1>(tmA, tmB, a, g.sms, stream);
-        case 128:
-            return tm_big == 2 ? launch_gemm<128, 2>(tmA, tmB, a, g.sms, stream)
-                               : launch_gemm<128, 1>(tmA, tmB, a, g.sms, stream);
-        case 256:
-            return tm_big == 2 ? launch_gemm<256, 2>(tmA, tmB, a, g.sms, stream)
-                               : launch_gemm<256, 1>(tmA, tmB, a, g.sms, stream);
-    }
-    return cudaErrorInvalidValue;
+    return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, stream) : gemm_dispatch<4>(g, tmA, tmB, a, stream);
 }
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
-                                float *dst, float *qnorm2, float *copy, cudaStream_t stream)
+                                float *dst, float *qnorm2, float *copy, void *dst_bf16, float *qres2,
+                                cudaStream_t stream)
 {
-    prep_queries_kernel<<<nq, 128, 0, stream>>>(src, q_stride, l_stride, q, nq, dims, dst, qnorm2, copy);
+    prep_queries_kernel<<<nq, 128, 0, stream>>>(src, q_stride, l_stride, q, nq, dims, dst, qnorm2, copy,
+                                                (__nv_bfloat16 *)dst_bf16, qres2);
     return cudaGetLastError();
 }
 
@@ -735,12 +796,12 @@ cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_bas
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
                             const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
-                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, int all,
-                            cudaStream_t stream)
+                            float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
+                            unsigned long long *d_out, unsigned int *d_flags, int all, cudaStream_t stream)
 {
     if (kp > kGemmCandCap || K > kp) return cudaErrorInvalidValue;
     finalize_kernel<<<q, 256, 0, stream>>>(d_exact, d_sel, d_cnt, d_thr, cap, kp, all, K, rows_total, d_qnorm2,
-                                           d_maxnorm2_bits, err_coeff, d_out, d_flags);
+                                           d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags);
     return cudaGetLastError();
 }
 

@@ -64,6 +64,7 @@ constexpr int kGemmMaxQ = 256;       // queries per pass (N of the MMA)
 constexpr int kGemmCandCap = 4096;   // candidate keys kept per query
 constexpr int kGemmMaxSampleTiles = 1024;
 constexpr float kTf32ErrCoeff = 2.2e-3f;  // |tf32 score - exact| <= coeff * |row| * |query| (two 10-bit truncations)
+constexpr float kAccErrCoeff = 2.5e-4f;   // fp32 accumulation inside the tensor core (the slack kTf32ErrCoeff holds too)
 enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2 };
 
 struct GemmLaunch {
@@ -74,6 +75,8 @@ struct GemmLaunch {
     const float *slab_base;   // first row of the cache slab (tensor map A covers the whole slab)
     uint64_t slab_rows;
     const float *d_queries_padded;  // [nq][dims]
+    const void *shadow_base;        // bf16 shadow of the slab (same row geometry); null = kind::tf32 on the fp32 rows
+    const void *d_queries_bf16;     // [nq][dims] bf16, used with the shadow
     int nq, q;
     int mode;
     uint32_t tile_first, tile_stride, tile_count;
@@ -89,7 +92,8 @@ struct GemmLaunch {
 int gemm_pad_queries(int q);
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
-                                float *dst, float *qnorm2, float *copy, cudaStream_t stream);
+                                float *dst, float *qnorm2, float *copy, void *dst_bf16, float *qres2,
+                                cudaStream_t stream);
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
@@ -104,8 +108,8 @@ cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_bas
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
                             const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
-                            float err_coeff, unsigned long long *d_out, unsigned int *d_flags, int all,
-                            cudaStream_t stream);
+                            float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
+                            unsigned long long *d_out, unsigned int *d_flags, int all, cudaStream_t stream);
 
 constexpr int kFixupMaxQ = 8;  // uncertified queries one device-side fix-up scan pass can take
 cudaError_t compact_failed_launch(unsigned int *d_flags, int q, int maxn, int *d_map, unsigned int *d_count,
@@ -114,6 +118,10 @@ cudaError_t scatter_fix_launch(const unsigned long long *d_fix, const int *d_map
                                int maxn, int K, unsigned long long *d_out, cudaStream_t stream);
 cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, unsigned int *d_out_bits,
                                  cudaStream_t stream);
+// rows -> bf16 shadow rows (round to nearest), and the certificate's bounds of the set:
+// d_small[0] = max |row|^2 bits, d_small[2] = max |bf16(row) - row|^2 bits (atomicMax, upper-bounded)
+cudaError_t shadow_rows_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, unsigned int *d_small,
+                               cudaStream_t stream);
 
 cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int dims, float *d_dst,
                                cudaStream_t stream);

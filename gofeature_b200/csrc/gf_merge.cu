@@ -3,6 +3,7 @@
 // merge_kernel folds `lists` per-CTA (or per-rank) candidate lists of K keys into the
 // top-K per query: the device-side counterpart of MaxNFeatureResult (util.go:95-112)
 // as used at set.go:154-157, on (score,slot) keys instead of Go structs.
+#include <cuda_bf16.h>
 #include "gf_device.cuh"
 #include "gf_kernels.h"
 
@@ -245,6 +246,58 @@ cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, un
     long long blocks = (rows + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     rownorm_range_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, rows, dims, d_out_bits);
+    return cudaGetLastError();
+}
+
+// fp32 rows -> bf16 shadow rows (round to nearest even) + the two bounds the bf16 certificate uses.
+// One warp per row, 8 bytes of bf16 per lane per step (dims % 4 == 0 on the shadow path).
+namespace {
+__global__ void shadow_rows_kernel(const float *__restrict__ base, long long rows, int dims,
+                                   __nv_bfloat16 *__restrict__ out, unsigned int *small)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f, best_res = 0.f;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float4 *x = reinterpret_cast<const float4 *>(base + (size_t)r * dims);
+        uint2 *o = reinterpret_cast<uint2 *>(out + (size_t)r * dims);
+        float acc = 0.f, res = 0.f;
+        for (int e = lane; e < dims / 4; e += 32) {
+            const float4 v = x[e];
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 w;
+            w.x = *reinterpret_cast<const unsigned int *>(&lo);
+            w.y = *reinterpret_cast<const unsigned int *>(&hi);
+            o[e] = w;
+            acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            const float d0 = __low2float(lo) - v.x, d1 = __high2float(lo) - v.y, d2 = __low2float(hi) - v.z,
+                        d3 = __high2float(hi) - v.w;
+            res += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            res += __shfl_xor_sync(0xffffffffu, res, off);
+        }
+        if (acc == acc) best = fmaxf(best, acc);
+        // a residual that is not finite (row element beyond the bf16 range, Inf, NaN) must fail every certificate
+        best_res = (res == res) ? fmaxf(best_res, res) : __int_as_float(0x7f800000);
+    }
+    if (lane == 0) {
+        if (best > 0.f) atomicMax(small + 0, __float_as_uint(best * 1.0001f));
+        if (best_res > 0.f) atomicMax(small + 2, __float_as_uint(best_res * 1.0001f));
+    }
+}
+}  // namespace
+
+cudaError_t shadow_rows_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, unsigned int *d_small,
+                               cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    if (dims % 4 != 0) return cudaErrorInvalidValue;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    shadow_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, rows, dims, (__nv_bfloat16 *)d_shadow_rows, d_small);
     return cudaGetLastError();
 }
 

@@ -410,6 +410,8 @@ int Block::release()
     int rc = cache->ctx->bind();
     if (rc) return rc;
     GF_CUDA(cudaMemsetAsync(dev, 0, (size_t)block_size, cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    if (shadow)
+        GF_CUDA(cudaMemsetAsync(shadow, 0, (size_t)block_size / 2, cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     GF_CUDA(cudaStreamSynchronize(cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     dims = precision = batch = 0;
     owner.clear();
@@ -528,6 +530,9 @@ int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &fo
         int row = find_last(ids_[i]);
         if (row < 0) continue;
         GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+        if (shadow && precision == 4)
+            GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * (rowb / 2), 0, rowb / 2, ctx->mut_stream),
+                    GF_ERR_CLEAR_CUDA_BUFFER);
         if (!implicit_ids) {
             index_del(ids_[i], row);
             ids[row].clear();
@@ -551,6 +556,9 @@ int Block::remove_rows(const std::vector<int> &rows)
     for (int row : rows) {
         if (row < 0 || row >= next_index || !live[row]) continue;
         GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+        if (shadow && precision == 4)
+            GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * (rowb / 2), 0, rowb / 2, ctx->mut_stream),
+                    GF_ERR_CLEAR_CUDA_BUFFER);
         if (!implicit_ids) {
             index_del(ids[row], row);
             ids[row].clear();
@@ -719,6 +727,7 @@ int Set::rebuild_segments()
     total_gtiles = gt;
     tensor_ok = precision == 4 && dims % 32 == 0 && dims >= 32 && (cache->block_size % ((int64_t)dims * 4)) == 0 &&
                 ((uintptr_t)cache->slab->ptr % 128) == 0;
+    shadow_ok = tensor_ok && cache->shadow != nullptr && dims % 64 == 0 && ((uintptr_t)cache->shadow->ptr % 128) == 0;
     GF_CUDA(cudaMemcpyAsync(d_segs, h_segs.data(), n * sizeof(Segment), cudaMemcpyHostToDevice, ctx->mut_stream),
             GF_ERR_WRITE_CUDA_BUFFER);
     GF_CUDA(cudaMemcpyAsync(d_gtile_start, aux.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
@@ -740,7 +749,14 @@ int Set::note_rows(const float *d_rows, int64_t rows)
         GF_CUDA(cudaMalloc((void **)&d_small, 64), GF_ERR_ALLOCATE_GPU_BUFFER);
         GF_CUDA(cudaMemsetAsync(d_small, 0, 64, ctx->mut_stream), GF_ERR_CUDA);
     }
-    GF_CUDA(rownorm_range_launch(d_rows, rows, dims, d_small, ctx->mut_stream), GF_ERR_CUDA);
+    if (cache->shadow != nullptr && dims % 4 == 0) {
+        // same element index in both slabs: row j of block i sits at the same (i, j) in the shadow
+        const size_t elem = (size_t)(d_rows - (const float *)cache->slab->ptr);
+        GF_CUDA(shadow_rows_launch(d_rows, rows, dims, (uint16_t *)cache->shadow->ptr + elem, d_small, ctx->mut_stream),
+                GF_ERR_CUDA);
+    } else {
+        GF_CUDA(rownorm_range_launch(d_rows, rows, dims, d_small, ctx->mut_stream), GF_ERR_CUDA);
+    }
     ctx->stats.other_launches++;
     return GF_OK;
 }
@@ -1021,6 +1037,15 @@ int Set::compact(int64_t *reclaimed)
         GF_CUDA(cudaMemsetAsync(b->dev + (size_t)n_live * dims * 4, 0, (size_t)(b->next_index - n_live) * dims * 4,
                                 ctx->mut_stream),
                 GF_ERR_CLEAR_CUDA_BUFFER);
+        if (b->shadow) {  // the packed rows moved: convert them again, clear the freed tail
+            if (n_live > 0) {
+                rc = note_rows((const float *)b->dev, n_live);
+                if (rc) return rc;
+            }
+            GF_CUDA(cudaMemsetAsync(b->shadow + (size_t)n_live * dims * 2, 0,
+                                    (size_t)(b->next_index - n_live) * dims * 2, ctx->mut_stream),
+                    GF_ERR_CLEAR_CUDA_BUFFER);
+        }
         GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CUDA);  // rows[] is reused by the next block
         for (int j = 0; j < n_live; ++j) {
             if (rows[j] != j) b->ids[j] = std::move(b->ids[rows[j]]);
@@ -1135,7 +1160,9 @@ bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long lo
     if (path == 1 || per_segment || d_upper != nullptr || !tensor_ok || d_small == nullptr) return false;
     if (K > 512) return false;                               // K' = K + slack must fit the 1024-key re-score
     if (total_gtiles < 2 * 256) return false;                // small sets: the sample would be the set
-    if (path == 2) return true;
+    if (path == 2 || path == 3) return true;
+    // the bf16 shadow halves the bytes of a pass: it wins for every batch size
+    if (shadow_ok) return true;
     // one scan pass cannot hold the batch, or K is beyond what the per-CTA sorted lists do cheaply
     return q > scan_max_q(dims) || K > 32;
 }
@@ -1155,9 +1182,10 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     if (!tensor || q > kGemmMaxQ || no_graphs || ws->graphs_broken || ctx->profiling.load())
         return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     Stats &st = ctx->stats;
+    const int mode = use_shadow(path) ? 1 : 0;
     for (auto &g : ws->graphs) {
-        if (g.set == this && g.version == version && g.q == q && g.K == K) {
-            int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1);
+        if (g.set == this && g.version == version && g.q == q && g.K == K && g.mode == mode) {
+            int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path);
             if (rc) return rc;
             GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
             GF_CUDA(cudaMemcpyAsync(d_out, ws->t_res, (size_t)q * K * 8, cudaMemcpyDeviceToDevice, stream), GF_ERR_CUDA);
@@ -1187,7 +1215,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         ws->graphs_broken = true;
         return GF_OK;
     }
-    int crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2);
+    int crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path);
     cudaError_t ce = cudaStreamEndCapture(ws->stream, &graph);
     Workspace::CachedGraph cg{};  // what the recording pass "launched" did not run: take its counters back
     cg.d_scan = st.scan_launches - s0;
@@ -1221,6 +1249,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     cg.version = version;
     cg.q = q;
     cg.K = K;
+    cg.mode = mode;
     cg.exec = exec;
     cg.stamp = ++ws->graph_clock;
     ws->graphs.push_back(cg);
@@ -1232,7 +1261,7 @@ int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, 
                     unsigned long long *d_out, int path, unsigned int *d_flags)
 {
     if (tensor_eligible(q, K, per_segment, d_upper, path))
-        return topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, d_out, d_flags);
+        return topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, d_out, d_flags, 0, path);
     if (d_flags) GF_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)q * sizeof(unsigned int), stream), GF_ERR_CUDA);
     return topk_scan(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out);
 }
@@ -1243,10 +1272,13 @@ int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, 
 //   -> sort, emit K, certify.  Uncertified queries are re-run by one fix-up scan pass on the device
 //   (up to kFixupMaxQ per call); what is still flagged is reported through d_flags.
 int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
-                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase)
+                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase, int path)
 {
     const int nseg = (int)h_segs.size();
-    const int kp = std::min(1024, std::max(K + 32, K + K / 2));
+    const bool bf16 = use_shadow(path);
+    // K' re-scored per query when the batch is too large to re-score everything collected: the certificate
+    // needs exact[K] > approx[K'] + delta, and delta is ~3.5e-3 with bf16 operands (2.2e-3 with tf32)
+    const int kp = bf16 ? std::min(1024, std::max(K + 64, 2 * K + 32)) : std::min(1024, std::max(K + 32, K + K / 2));
     const unsigned cap = kGemmCandCap;
     // sample: G strided tiles; threshold = m-th largest tile maximum so that ~target rows pass
     // whole waves of the grid: one tile per SM on a 1 M-row set, up to 6 on the largest
@@ -1267,6 +1299,8 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     };
     const size_t o_qpad = carve((size_t)nq_max * dims * 4);
     const size_t o_qn = carve((size_t)nq_max * 4);
+    const size_t o_qbf = carve(bf16 ? (size_t)nq_max * dims * 2 : 0);
+    const size_t o_qres = carve((size_t)nq_max * 4);
     const size_t o_tmax = carve((size_t)kGemmMaxSampleTiles * nq_max * 4);
     const size_t o_thr = carve((size_t)nq_max * 4);
     const size_t o_cnt = carve((size_t)nq_max * 4);
@@ -1284,6 +1318,9 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     uint8_t *T = ws->d_tensor;
     float *d_qpad = (float *)(T + o_qpad);
     float *d_qn = (float *)(T + o_qn);
+    void *d_qbf = bf16 ? (void *)(T + o_qbf) : nullptr;
+    float *d_qres = bf16 ? (float *)(T + o_qres) : nullptr;
+    const float err_coeff = bf16 ? kAccErrCoeff : kTf32ErrCoeff;
     float *d_tmax = (float *)(T + o_tmax);
     float *d_thr = (float *)(T + o_thr);
     unsigned int *d_cnt = (unsigned int *)(T + o_cnt);
@@ -1307,6 +1344,8 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     g.slab_base = (const float *)cache->slab->ptr;
     g.slab_rows = (uint64_t)(cache->slab->size / ((uint64_t)dims * 4));
     g.d_queries_padded = d_qpad;
+    g.shadow_base = bf16 ? cache->shadow->ptr : nullptr;
+    g.d_queries_bf16 = d_qbf;
     g.d_thr = d_thr;
     g.d_cand = d_cand;
     g.d_cnt = d_cnt;
@@ -1331,7 +1370,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
-                                        d_qn, d_qall + (size_t)p0 * dims, stream),
+                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, d_qres, stream),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
         // small batches: re-score EVERY collected candidate (~1000 rows per query) and skip the selection
@@ -1363,7 +1402,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                     GF_ERR_CUDA);
             mark();
             GF_CUDA(finalize_launch(d_exact, d_cand, d_cnt, d_thr, cap, (int)cap, K, qp, scanned_rows, d_qn, d_small,
-                                    kTf32ErrCoeff, d_out + (size_t)p0 * K, d_fl + p0, 1, stream),
+                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 1, stream),
                     GF_ERR_CUDA);
         } else {
             GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
@@ -1373,7 +1412,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                     GF_ERR_CUDA);
             mark();
             GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, qp, scanned_rows, d_qn, d_small,
-                                    kTf32ErrCoeff, d_out + (size_t)p0 * K, d_fl + p0, 0, stream),
+                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, stream),
                     GF_ERR_CUDA);
         }
         mark();
@@ -1526,8 +1565,8 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
             GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)q * 8, cudaMemcpyHostToDevice, ws->stream),
                     GF_ERR_WRITE_INPUT_BUFFER);
         }
-        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out, 0,
-                         d_flags);
+        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out,
+                         search_path, d_flags);
         if (rc) return rc;
         GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
                 GF_ERR_READ_CUDA_BUFFER);

@@ -79,7 +79,7 @@ struct Workspace {
     struct CachedGraph {
         const void *set;
         uint64_t version;
-        int q, K;
+        int q, K, mode;
         cudaGraphExec_t exec;
         uint64_t d_scan, d_gemm, d_merge, d_other, d_tensor_passes, d_rows;  // counters one replay adds
         uint64_t stamp;
@@ -167,6 +167,7 @@ struct gf_block {
     int index = 0;
     int64_t block_size = 0;
     uint8_t *dev = nullptr;
+    uint8_t *shadow = nullptr;  // this block's rows in the cache's bf16 shadow slab (null: no shadow)
     std::mutex mu;  // block.go:19
     // feature info (block.go:24-31)
     int dims = 0, precision = 0, batch = 0;
@@ -239,8 +240,10 @@ struct gf_set {
     uint32_t *d_gtile_start = nullptr;
     uint32_t *d_seg_slot_base = nullptr;
     uint32_t total_gtiles = 0;
-    unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter
+    unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter, [2] max |bf16(row) - row|^2 bits
     bool tensor_ok = false;
+    bool shadow_ok = false;   // the bf16 shadow of this set's rows is maintained and usable by the tensor path
+    int search_path = 0;      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32
     uint64_t version = 0;  // bumped whenever the segment table or the shard identity changes
     uint32_t total_tiles = 0;
     int64_t scanned_rows = 0;
@@ -296,7 +299,8 @@ struct gf_set {
                     int64_t *out_rows, uint64_t *out_id_bytes);  // SURVEY 8f N3  // pack live rows, shrink NextIndex
     // top-K over the scanned rows into d_out; read lock held by the caller.
     //   per_segment: d_out is [pass][segment][qp][K] (qp = queries of that pass), else [q][K]
-    //   path: 0 = choose (tensor cores for q >= 9 on large sets), 1 = fused scan only, 2 = tensor path
+    //   path: 0 = choose (tensor cores on large sets: any q with the bf16 shadow, q >= 9 without),
+    //         1 = fused scan only, 2 = tensor path, 3 = tensor path on the fp32 rows (kind::tf32) even with a shadow
     //   d_flags (optional, [q]): 1 where a tensor-path query could not be certified nor fixed on the device
     int topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                     int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
@@ -310,9 +314,12 @@ struct gf_set {
     //   phase 0: everything, results to d_out / d_flags;  1: query preparation only;
     //   2: everything after the preparation, results to the workspace (ws->t_res / ws->t_flags)
     int topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
-                    int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase = 0);
+                    int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase = 0,
+                    int path = 0);
     bool tensor_eligible(int q, int K, bool per_segment, const unsigned long long *d_upper, int path) const;
-    int note_rows(const float *d_rows, int64_t rows);  // keep the |row|^2 bound current (mutation stream)
+    // rows were written on the device: refresh their bf16 shadow and the certificate's bounds (mutation stream)
+    int note_rows(const float *d_rows, int64_t rows);
+    bool use_shadow(int path) const { return shadow_ok && path != 3; }
     bool slot_to_block(uint32_t slot, int *block_pos, int *row) const;
 };
 
@@ -320,6 +327,7 @@ struct gf_cache {
     gf::Context *ctx = nullptr;
     int64_t block_size = 0;
     std::shared_ptr<gf::DeviceAlloc> slab;
+    std::shared_ptr<gf::DeviceAlloc> shadow;  // bf16 copy of the slab, same row geometry at half the bytes (optional)
     std::vector<std::unique_ptr<gf::Block>> all_blocks;
     std::mutex mu;  // cache.go:17
     std::unordered_map<std::string, gf::Set *> sets;

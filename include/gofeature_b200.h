@@ -138,6 +138,18 @@ GF_API int gf_buffer_free(gf_buffer *buf);
 /* ------------------------------------------------- L4: Cache (interface.go:12-34) */
 /* NewCache(ctx, blockNum, blockSize) (cache.go:21-43): one zeroed slab cut into blocks. */
 GF_API int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache **out_cache);
+/* gf_cache_create with options.  By default the cache also keeps a bf16 SHADOW of the slab
+ * (block_size / 2 more bytes per block, rows converted on the device whenever Add / Update /
+ * Delete / Compact writes them): the tensor-core candidate pass then streams 2 bytes per
+ * element instead of 4, and every candidate is still re-scored from the float32 rows, so
+ * results are identical with and without it.  GF_CACHE_NO_SHADOW (or the environment variable
+ * GF_SHADOW=0 for gf_cache_create) turns it off; GF_CACHE_REQUIRE_SHADOW fails instead of
+ * continuing without when the device cannot hold it. */
+#define GF_CACHE_NO_SHADOW 1u
+#define GF_CACHE_REQUIRE_SHADOW 2u
+GF_API int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsigned flags,
+                              gf_cache **out_cache);
+GF_API int gf_cache_has_shadow(const gf_cache *cache);
 /* Releases every set, the slab and all handles obtained from this cache. */
 GF_API int gf_cache_destroy(gf_cache *cache);
 /* Cache.NewSet (cache.go:45-72). */
@@ -254,8 +266,9 @@ GF_API int gf_set_set_shard(gf_set *set, int rank, int world);
 
 /* Top-`limit` over all scanned rows (tombstones compete with score 0.0 exactly like
  * block.go:236-243 lets them) for q row-major float32 queries resident on the device.
- * d_out_keys: q*limit keys, descending, zero padded.  path: 0 = choose by q, 1 = fused
- * scan kernel, 2 = tcgen05 contraction + exact rescoring. */
+ * d_out_keys: q*limit keys, descending, zero padded.  path: 0 = choose, 1 = fused
+ * scan kernel, 2 = tcgen05 contraction + exact rescoring (bf16 shadow when the cache has one),
+ * 3 = the same on the float32 rows (kind::tf32). */
 GF_API int gf_set_search_device(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys,
                                 int path, void *stream);
 /* Merge `lists` candidate lists (each [q][limit], e.g. the all-gathered per-rank winners)
@@ -297,6 +310,11 @@ GF_API int gf_context_reset_stats(gf_context *ctx);
 /* Bracket every scan kernel launch with CUDA events on its own stream (bench.py's roofline
  * figure); the durations are folded into gf_stats by gf_context_stats.  Off by default. */
 GF_API int gf_context_set_profiling(gf_context *ctx, int on);
+
+/* Kernel path the host-side Search of this set takes: 0 = choose (default), 1 = fused scan,
+ * 2 = tensor path, 3 = tensor path on the float32 rows (kind::tf32) even when a shadow exists.
+ * Results do not depend on it; tests and benchmarks use it to pin one path. */
+GF_API int gf_set_set_search_path(gf_set *set, int path);
 
 /* Allow concurrent single callers of gf_set_search to be served by one scan pass
  * (the analogue of the reference's SearchQueue, set.go:36, cache.go:61). 0 = off. */

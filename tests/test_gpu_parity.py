@@ -20,11 +20,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-5  # north_star: scores within 1e-5 absolute
 
 
-def _pair(gpu_ctx, name, dims, batch, block_rows, block_num):
+def _pair(gpu_ctx, name, dims, batch, block_rows, block_num, shadow=None):
     """The same empty set twice: on the GPU and in the oracle's model."""
     from gofeature_b200 import api
     bs = block_rows * dims * 4
-    cache = api.NewCache(gpu_ctx, block_num, bs)
+    cache = api.NewCache(gpu_ctx, block_num, bs, shadow=shadow)
     cache.NewSet(name, dims, 4, batch)
     oc = model.Cache(block_num, bs)
     oc.new_set(name, dims, 4, batch)
@@ -497,7 +497,8 @@ def test_tensor_path_parity(gpu_ctx, dims, n, q, limit):
     """q >= 9 on a large set runs TF32 tensor-core candidate selection + canonical re-score + certificate;
     the answer must still be bit-identical to the oracle (and therefore to the fused scan)."""
     block_rows = 16384
-    cache, st, ost = _pair(gpu_ctx, "tensor", dims, q, block_rows, (n + block_rows - 1) // block_rows + 1)
+    cache, st, ost = _pair(gpu_ctx, "tensor", dims, q, block_rows, (n + block_rows - 1) // block_rows + 1,
+                           shadow=False)                               # the bf16 shadow path: tests/test_gpu_shadow.py
     st.AddSynthetic(n, 4242 + dims)
     rows = ol.synth_rows(4242 + dims, 0, n, dims)
     ost.add(rows, ["f%011d" % i for i in range(n)])
@@ -521,7 +522,7 @@ def test_tensor_path_certificate_fallback(gpu_ctx):
     hold, the flagged queries are re-run by the exact scan (on the device, then by the host call), and
     the answer is still exact.  Un-normalised rows exercise the |row|.|query| scaling of the bound."""
     dims, n, q, limit = 512, 70000, 24, 10
-    cache, st, ost = _pair(gpu_ctx, "cert", dims, q, 16384, 6)
+    cache, st, ost = _pair(gpu_ctx, "cert", dims, q, 16384, 6, shadow=False)
     rng = np.random.default_rng(17)
     rows = ol.synth_rows(808, 0, n, dims)
     rows[::3] *= np.float32(2.5)                                       # norms up to 2.5
