@@ -451,15 +451,16 @@ __global__ void rownorm_max_kernel(const Segment *__restrict__ segs, int nseg, i
 
 // per query: threshold = m-th largest of `ntiles` tile maxima; also resets the candidate counter.
 // One warp per query: MSB-first radix select on the orderable score images (32 count steps).
+template <int NV>
 __global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, int nq, int q, int m,
                                  float *__restrict__ thr, unsigned int *__restrict__ cnt)
 {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
-    unsigned int v[kGemmMaxSampleTiles / 32];
+    unsigned int v[NV];  // NV = values per lane: 5 for one wave of 148 sample tiles
 #pragma unroll
-    for (int i = 0; i < kGemmMaxSampleTiles / 32; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int t = lane + 32 * i;
         v[i] = t < ntiles ? score_image(tilemax[(size_t)t * nq + qi]) : 0u;
     }
@@ -469,8 +470,8 @@ __global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, 
         const unsigned int cand = prefix | (1u << bit);
         int c = 0;
 #pragma unroll
-        for (int i = 0; i < kGemmMaxSampleTiles / 32; ++i) c += (v[i] >= cand) ? 1 : 0;
-        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        for (int i = 0; i < NV; ++i) c += (v[i] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
         if (c >= m) prefix = cand;
     }
     if (lane == 0) {
@@ -506,11 +507,30 @@ __global__ void __launch_bounds__(256)
     const float *x = segs[lo].base + (size_t)(slot - seg_slot_base[lo]) * dims;
     const float *qv = queries + (size_t)qi * dims;
     float p[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < dims; j += 128) {
+    if ((dims & 511) == 0) {
+        // the tensor path's rows are 16-byte aligned: four 128-bit loads per operand in flight at once
+        for (int j = 0; j < dims; j += 512) {
+            float4 xv[4], qq[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int e = j + 4 * lane + c;
-            if (e < dims) p[c] = __fmaf_rn(x[e], qv[e], p[c]);
+            for (int u = 0; u < 4; ++u) {
+                xv[u] = __ldg(reinterpret_cast<const float4 *>(x + j + 128 * u) + lane);
+                qq[u] = __ldg(reinterpret_cast<const float4 *>(qv + j + 128 * u) + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // same element order as the scalar loop below
+                p[0] = __fmaf_rn(xv[u].x, qq[u].x, p[0]);
+                p[1] = __fmaf_rn(xv[u].y, qq[u].y, p[1]);
+                p[2] = __fmaf_rn(xv[u].z, qq[u].z, p[2]);
+                p[3] = __fmaf_rn(xv[u].w, qq[u].w, p[3]);
+            }
+        }
+    } else {
+        for (int j = 0; j < dims; j += 128) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int e = j + 4 * lane + c;
+                if (e < dims) p[c] = __fmaf_rn(x[e], qv[e], p[c]);
+            }
         }
     }
     const float sc = canonical_reduce(p[0], p[1], p[2], p[3]);
@@ -519,27 +539,72 @@ __global__ void __launch_bounds__(256)
 
 // Best K of up to kGemmCandCap keys held 16 per thread (256 threads), written sorted (descending,
 // zero padded to a power of two) to `out` in shared memory; returns how many keys were kept (>= min(K, n);
-// more only when scores tie at the cut).  MSB-first radix select on the 32-bit score image finds the
-// cut in 32 counting steps, then only the survivors are bitonic-sorted -- a full sort of ~1000
-// candidates per query was the slowest small kernel of the tensor path.
+// more only when scores tie at the cut).  A radix select on the 32-bit score image finds the cut, then
+// only the survivors are bitonic-sorted -- a full sort of ~1000 candidates per query was the slowest
+// small kernel of the tensor path.
 __device__ int block_topk_256(const unsigned long long (&mine)[kGemmCandCap / 256], int K, unsigned long long *out,
                               int *s_cnt)
 {
     constexpr int R = kGemmCandCap / 256;
-    unsigned int prefix = 0u;
-    for (int bit = 31; bit >= 0; --bit) {
-        const unsigned int cand = prefix | (1u << bit);
-        int c = 0;
+    // the cut = K-th largest score image, found 8 bits at a time (MSB first) with a 256-bin histogram:
+    // 4 passes of 3 barriers (the bit-by-bit version took 96 barriers and was the slowest small kernel)
+    __shared__ int hist[256];
+    __shared__ unsigned int s_prefix;
+    __shared__ int s_krem;
+    unsigned int prefix = 0u, mask = 0u;
+    int krem = K;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;  // blockDim.x == 256
+        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < R; ++i) c += (mine[i] != 0ull && (unsigned int)(mine[i] >> 32) >= cand) ? 1 : 0;
-        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-        if (threadIdx.x == 0) *s_cnt = 0;
+        for (int i = 0; i < R; ++i) {
+            const unsigned int img = (unsigned int)(mine[i] >> 32);
+            if (mine[i] != 0ull && (img & mask) == prefix) atomicAdd(&hist[(img >> shift) & 255u], 1);
+        }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0 && c) atomicAdd(s_cnt, c);
+        if (threadIdx.x < 32) {
+            // lane l owns bins 255 - 8l .. 248 - 8l (descending); find the bin holding the krem-th key
+            const int lane = threadIdx.x;
+            int h[8], local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                h[j] = hist[255 - 8 * lane - j];
+                local += h[j];
+            }
+            int incl = local;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            const int excl = incl - local;  // keys in bins above this lane's
+            const bool here = excl < krem && incl >= krem;
+            const unsigned ball = __ballot_sync(0xffffffffu, here);
+            if (ball == 0u) {
+                if (lane == 0) {  // fewer than krem keys left: keep them all
+                    s_prefix = prefix;
+                    s_krem = -1;
+                }
+            } else if (lane == __ffs(ball) - 1) {
+                int run = excl, bin = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (run < krem && run + h[j] >= krem) {
+                        bin = 255 - 8 * lane - j;
+                        break;
+                    }
+                    run += h[j];
+                }
+                s_prefix = prefix | ((unsigned int)bin << shift);
+                s_krem = krem - run;
+            }
+        }
         __syncthreads();
-        if (*s_cnt >= K) prefix = cand;
-        __syncthreads();
+        if (s_krem < 0) break;  // (uniform) every remaining key with this prefix is kept
+        prefix = s_prefix;
+        krem = s_krem;
+        mask |= 255u << shift;
     }
+    // a partial prefix (early exit) has zero low bits: `>= prefix` keeps everything at or above it
     if (threadIdx.x == 0) *s_cnt = 0;
     __syncthreads();
 #pragma unroll
@@ -580,7 +645,7 @@ __global__ void __launch_bounds__(256)
                     int all, int K, long long rows_total, const float *__restrict__ qnorm2,
                     const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
                     const float *__restrict__ qres2, const unsigned int *__restrict__ maxres2_bits,
-                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags)
+                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags, const FixupPlan fix)
 {
     __shared__ unsigned long long buf[kGemmCandCap];
     __shared__ int s_cnt;
@@ -617,6 +682,36 @@ __global__ void __launch_bounds__(256)
             if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
         }
         d_flags[qi] = ok ? 0u : 1u;  // flagged queries are re-run by the exact scan
+    }
+    if (fix.flags_all == nullptr) return;
+    // the last CTA of the call's last finalize launch lists the flagged queries for the fix-up scan
+    __shared__ unsigned int s_ticket;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_ticket = atomicAdd(fix.ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    if (threadIdx.x < 32) {
+        __threadfence();
+        const int lane = threadIdx.x;
+        int n = 0;
+        for (int base = 0; base < fix.q_total; base += 32) {
+            const int i = base + lane;
+            const bool f = i < fix.q_total && __ldcg(fix.flags_all + i) != 0u;
+            const unsigned ball = __ballot_sync(0xffffffffu, f);
+            const int pos = n + __popc(ball & ((1u << lane) - 1u));
+            if (f && pos < fix.maxn) {
+                fix.map[pos] = i;
+                fix.flags_all[i] = 0u;
+            }
+            n += __popc(ball);
+        }
+        if (lane == 0) {
+            *fix.count = (unsigned)(n < fix.maxn ? n : fix.maxn);
+            if (n > fix.maxn) atomicAdd(fix.uncertified, (unsigned)(n - fix.maxn));
+            *fix.ticket = 0u;
+        }
     }
 }
 
@@ -771,7 +866,16 @@ cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, 
                              unsigned int *d_cnt, cudaStream_t stream)
 {
     if (ntiles > kGemmMaxSampleTiles || ntiles < 1) return cudaErrorInvalidValue;
-    threshold_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+    const int nv = (ntiles + 31) / 32;
+    const int grid = (nq + 3) / 4;
+    if (nv <= 5)
+        threshold_kernel<5><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+    else if (nv <= 10)
+        threshold_kernel<10><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+    else if (nv <= 19)
+        threshold_kernel<19><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+    else
+        threshold_kernel<kGemmMaxSampleTiles / 32><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
     return cudaGetLastError();
 }
 
@@ -797,11 +901,12 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
                             float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
-                            unsigned long long *d_out, unsigned int *d_flags, int all, cudaStream_t stream)
+                            unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
+                            cudaStream_t stream)
 {
     if (kp > kGemmCandCap || K > kp) return cudaErrorInvalidValue;
     finalize_kernel<<<q, 256, 0, stream>>>(d_exact, d_sel, d_cnt, d_thr, cap, kp, all, K, rows_total, d_qnorm2,
-                                           d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags);
+                                           d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags, fix);
     return cudaGetLastError();
 }
 

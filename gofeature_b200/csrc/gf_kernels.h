@@ -56,8 +56,10 @@ cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, u
 
 // Merge `lists` lists of K keys per (group, query): d_in [groups][lists][q][K] -> d_out [groups][q][K]
 // (descending, zero padded).
+// d_out_map (optional, groups == 1): query i of this launch is written to row d_out_map[i] of d_out.
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
-                         unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count = nullptr);
+                         unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count = nullptr,
+                         const int *d_out_map = nullptr);
 
 // ---- tcgen05 contraction path (gf_gemm.cu) ----
 constexpr int kGemmMaxQ = 256;       // queries per pass (N of the MMA)
@@ -104,18 +106,27 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
                            const float *d_queries_padded, int kp, const unsigned long long *d_sel,
                            const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream);
+constexpr int kFixupMaxQ = 8;  // uncertified queries one device-side fix-up scan pass can take
+// What the LAST finalize launch of a call also does, in the last CTA to finish: flags[0..q_total) (1 =
+// uncertified) -> map[0..n) of their indices, *count = min(n, maxn), those flags cleared; what does not fit
+// in one fix-up pass stays flagged and is added to *uncertified (the host API re-runs those).
+struct FixupPlan {
+    unsigned int *flags_all;  // null: this launch does not compact
+    int q_total;
+    int maxn;
+    int *map;
+    unsigned int *count;
+    unsigned int *uncertified;
+    unsigned int *ticket;  // zero between calls
+};
 // d_flags[qi] = 1 when query qi could not be certified (it must be re-run by the exact scan)
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
                             const unsigned int *d_cnt, const float *d_thr, unsigned int cap, int kp, int K, int q,
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
                             float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
-                            unsigned long long *d_out, unsigned int *d_flags, int all, cudaStream_t stream);
+                            unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
+                            cudaStream_t stream);
 
-constexpr int kFixupMaxQ = 8;  // uncertified queries one device-side fix-up scan pass can take
-cudaError_t compact_failed_launch(unsigned int *d_flags, int q, int maxn, int *d_map, unsigned int *d_count,
-                                  unsigned int *d_uncertified, cudaStream_t stream);
-cudaError_t scatter_fix_launch(const unsigned long long *d_fix, const int *d_map, const unsigned int *d_count,
-                               int maxn, int K, unsigned long long *d_out, cudaStream_t stream);
 cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, unsigned int *d_out_bits,
                                  cudaStream_t stream);
 // rows -> bf16 shadow rows (round to nearest), and the certificate's bounds of the set:

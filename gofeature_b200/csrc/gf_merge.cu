@@ -45,7 +45,8 @@ __device__ __forceinline__ int pow2_at_least(int v)
 // grid (q, groups); d_in [groups][lists][q][K]; d_out [groups][q][K]
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const unsigned long long *__restrict__ d_in, int lists,
                                                              int q, int K, unsigned long long *__restrict__ d_out,
-                                                             const unsigned int *__restrict__ d_q_count)
+                                                             const unsigned int *__restrict__ d_q_count,
+                                                             const int *__restrict__ d_out_map)
 {
     if (d_q_count != nullptr && (unsigned)blockIdx.x >= *d_q_count) return;  // fix-up pass with fewer live queries
     __shared__ unsigned long long buf[kMergeBuf];
@@ -111,7 +112,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const unsigned lon
     for (int i = n + threadIdx.x; i < np; i += blockDim.x) buf[i] = 0ull;
     __syncthreads();
     block_sort_desc(buf, np);
-    unsigned long long *out = d_out + ((size_t)group * q + qi) * (size_t)K;
+    // fix-up pass: query qi of this launch is row d_out_map[qi] of the caller's result
+    unsigned long long *out = d_out + ((size_t)group * q + (d_out_map != nullptr ? d_out_map[qi] : qi)) * (size_t)K;
     for (int i = threadIdx.x; i < K; i += blockDim.x) out[i] = buf[i];
 }
 
@@ -171,51 +173,7 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ row
     }
 }
 
-// ---- device-side fix-up of tensor-path queries that failed their certificate ----
-// flags[q] (1 = uncertified) -> map[0..n) of their indices, *count = min(n, maxn); what does not
-// fit in one fix-up pass stays flagged and is added to *uncertified (the host API re-runs those).
-__global__ void compact_failed_kernel(unsigned int *flags, int q, int maxn, int *map, unsigned int *count,
-                                      unsigned int *uncertified)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int n = 0;
-    for (int i = 0; i < q; ++i) {
-        if (flags[i]) {
-            if (n < maxn) {
-                map[n] = i;
-                flags[i] = 0u;
-            }
-            ++n;
-        }
-    }
-    *count = (unsigned)(n < maxn ? n : maxn);
-    if (n > maxn) atomicAdd(uncertified, (unsigned)(n - maxn));
-}
-
-// fix [maxn][K] exact keys of the re-scanned queries -> rows map[i] of out [q][K]
-__global__ void scatter_fix_kernel(const unsigned long long *__restrict__ fix, const int *__restrict__ map,
-                                   const unsigned int *__restrict__ count, int K, unsigned long long *__restrict__ out)
-{
-    const unsigned i = blockIdx.x;
-    if (i >= *count) return;
-    for (int j = threadIdx.x; j < K; j += blockDim.x) out[(size_t)map[i] * K + j] = fix[(size_t)i * K + j];
-}
-
 }  // namespace
-
-cudaError_t compact_failed_launch(unsigned int *d_flags, int q, int maxn, int *d_map, unsigned int *d_count,
-                                  unsigned int *d_uncertified, cudaStream_t stream)
-{
-    compact_failed_kernel<<<1, 32, 0, stream>>>(d_flags, q, maxn, d_map, d_count, d_uncertified);
-    return cudaGetLastError();
-}
-
-cudaError_t scatter_fix_launch(const unsigned long long *d_fix, const int *d_map, const unsigned int *d_count,
-                               int maxn, int K, unsigned long long *d_out, cudaStream_t stream)
-{
-    scatter_fix_kernel<<<maxn, 128, 0, stream>>>(d_fix, d_map, d_count, K, d_out);
-    return cudaGetLastError();
-}
 
 // max |row|^2 over a contiguous range of rows (incremental upkeep of the certificate's norm bound)
 namespace {
@@ -328,11 +286,13 @@ cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int 
 }
 
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
-                         unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count)
+                         unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count,
+                         const int *d_out_map)
 {
+    if (d_out_map != nullptr && groups != 1) return cudaErrorInvalidValue;
     if (K < 1 || K > kMaxK || q < 1 || lists < 1 || groups < 1) return cudaErrorInvalidValue;
     dim3 grid(q, groups);
-    merge_kernel<<<grid, kMergeThreads, 0, stream>>>(d_in, lists, q, K, d_out, d_q_count);
+    merge_kernel<<<grid, kMergeThreads, 0, stream>>>(d_in, lists, q, K, d_out, d_q_count, d_out_map);
     return cudaGetLastError();
 }
 

@@ -117,6 +117,7 @@ int Workspace::reserve_tensor(size_t bytes)
         d_tensor_cap = 0;
     }
     GF_CUDA(cudaMalloc((void **)&d_tensor, bytes), GF_ERR_ALLOCATE_GPU_BUFFER);
+    GF_CUDA(cudaMemset(d_tensor, 0, 256), GF_ERR_CUDA);  // the finalize ticket lives at offset 0
     d_tensor_cap = bytes;
     return GF_OK;
 }
@@ -1286,7 +1287,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     int G = std::min(kGemmMaxSampleTiles, waves * ctx->sms);
     G = (int)std::min<uint32_t>((uint32_t)G, total_gtiles);
     const uint32_t stride = total_gtiles / (uint32_t)G;
-    const double target = std::max(1024.0, 4.0 * kp);
+    const double target = std::max(512.0, 4.0 * kp);
     int m = (int)std::ceil(target * G / (double)total_gtiles);
     m = std::max(2, std::min(m, G / 2));
 
@@ -1297,6 +1298,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         off += (bytes + 255) / 256 * 256;
         return o;
     };
+    const size_t o_ticket = carve(4);  // always offset 0: zeroed when the arena is allocated, left zero by every call
     const size_t o_qpad = carve((size_t)nq_max * dims * 4);
     const size_t o_qn = carve((size_t)nq_max * 4);
     const size_t o_qbf = carve(bf16 ? (size_t)nq_max * dims * 2 : 0);
@@ -1306,11 +1308,12 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_cnt = carve((size_t)nq_max * 4);
     const size_t o_cand = carve((size_t)nq_max * cap * 8);
     const size_t o_sel = carve((size_t)nq_max * kp * 8);
-    const size_t o_exact = carve((size_t)nq_max * std::max<size_t>((size_t)kp, nq_max <= 32 ? (size_t)cap : 0) * 8);
+    // small batches re-score EVERY collected candidate (~`target` rows per query) and skip the selection
+    auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)64 << 20); };
+    const size_t o_exact = carve((size_t)nq_max * (rescore_all(std::min(q, kGemmMaxQ)) ? (size_t)cap : (size_t)kp) * 8);
     const size_t o_flags = carve((size_t)q * 4);
     const size_t o_map = carve((size_t)kFixupMaxQ * 4);
     const size_t o_count = carve(4);
-    const size_t o_fix = carve((size_t)kFixupMaxQ * K * 8);
     const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
     const size_t o_res = carve((size_t)q * K * 8);     // result keys when the caller's buffer must stay outside (phase 2)
     int rc = ws->reserve_tensor(off);
@@ -1330,7 +1333,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     unsigned int *d_fl = (unsigned int *)(T + o_flags);
     int *d_map = (int *)(T + o_map);
     unsigned int *d_count = (unsigned int *)(T + o_count);
-    unsigned long long *d_fix = (unsigned long long *)(T + o_fix);
+    unsigned int *d_ticket = (unsigned int *)(T + o_ticket);
     float *d_qall = (float *)(T + o_qall);
     ws->t_res = (unsigned long long *)(T + o_res);
     ws->t_flags = d_fl;
@@ -1362,19 +1365,21 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         cudaEventRecord(e, stream);
         evs.push_back(e);
     };
+    const int fixq = std::min(kFixupMaxQ, scan_max_q(dims));
     for (int p0 = 0; p0 < q; p0 += kGemmMaxQ) {
         const int qp = std::min(kGemmMaxQ, q - p0);
         const int nq = gemm_pad_queries(qp);
         g.nq = nq;
         g.q = qp;
+        FixupPlan fix{};  // the last pass's finalize also lists the flagged queries of the whole call
+        if (p0 + kGemmMaxQ >= q) fix = FixupPlan{d_fl, q, fixq, d_map, d_count, d_small + 1, d_ticket};
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
                                         d_qn, d_qall + (size_t)p0 * dims, d_qbf, d_qres, stream),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
-        // small batches: re-score EVERY collected candidate (~1000 rows per query) and skip the selection
-        const bool all = (size_t)qp * (size_t)target * (size_t)dims * 4 <= ((size_t)64 << 20);
+        const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call: it sizes d_exact
         mark();
         g.mode = kGemmTileMax;
         g.tile_first = 0;
@@ -1402,7 +1407,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                     GF_ERR_CUDA);
             mark();
             GF_CUDA(finalize_launch(d_exact, d_cand, d_cnt, d_thr, cap, (int)cap, K, qp, scanned_rows, d_qn, d_small,
-                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 1, stream),
+                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 1, fix, stream),
                     GF_ERR_CUDA);
         } else {
             GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
@@ -1412,12 +1417,12 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                     GF_ERR_CUDA);
             mark();
             GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, qp, scanned_rows, d_qn, d_small,
-                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, stream),
+                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, fix, stream),
                     GF_ERR_CUDA);
         }
         mark();
         ctx->stats.gemm_launches += 2;
-        ctx->stats.other_launches += 5;
+        ctx->stats.other_launches += 4 + (all ? 0 : 1);
         ctx->stats.tensor_passes++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
     }
@@ -1425,18 +1430,15 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         ctx->stats.other_launches++;
         return GF_OK;
     }
-    // device-side fix-up: one exact scan pass over up to kFixupMaxQ flagged queries (a no-op launch
-    // when everything was certified)
-    const int fixq = std::min(kFixupMaxQ, scan_max_q(dims));
-    GF_CUDA(compact_failed_launch(d_fl, q, fixq, d_map, d_count, d_small + 1, stream), GF_ERR_CUDA);
-    rc = topk_scan(ws, stream, d_qall, fixq, dims, 1, K, false, nullptr, d_fix, d_map, d_count);
+    // device-side fix-up: one exact scan pass over up to kFixupMaxQ flagged queries (listed by the last
+    // finalize launch), merged straight into their rows of d_out; both launches are no-ops when everything
+    // was certified
+    rc = topk_scan(ws, stream, d_qall, fixq, dims, 1, K, false, nullptr, d_out, d_map, d_count, true);
     if (rc) return rc;
-    GF_CUDA(scatter_fix_launch(d_fix, d_map, d_count, fixq, K, d_out, stream), GF_ERR_CUDA);
-    ctx->stats.other_launches += 2;
     mark();
     if (stage_timing && !evs.empty()) {
         cudaEventSynchronize(evs.back());
-        static const char *names[] = {"prep+copy", "tilemax", "threshold", "collect", "select", "rescore", "finalize", "fixup"};
+        static const char *names[] = {"prep+copy", "tilemax", "threshold", "collect", "select", "rescore", "finalize", "fixup"};  // select = 0 when every candidate is re-scored
         fprintf(stderr, "[stage us]");
         for (size_t i = 0; i + 1 < evs.size(); ++i) {
             float ms = 0;
@@ -1454,7 +1456,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
 
 int Set::topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                    int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
-                   unsigned long long *d_out, const int *d_q_map, const unsigned int *d_q_count)
+                   unsigned long long *d_out, const int *d_q_map, const unsigned int *d_q_count, bool scatter_out)
 {
     const int nseg = (int)h_segs.size();
     const int maxq = scan_max_q(dims);
@@ -1478,7 +1480,8 @@ int Set::topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, i
         if (le != cudaSuccess) return cuda_fail(le, "scan_launch", GF_ERR_CUDA);
         ctx->stats.scan_launches++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
-        GF_CUDA(merge_launch(d_partial, plan.groups, plan.grid_x, qp, K, d_out + out_off, stream, d_q_count),
+        GF_CUDA(merge_launch(d_partial, plan.groups, plan.grid_x, qp, K, d_out + out_off, stream, d_q_count,
+                             scatter_out ? d_q_map : nullptr),
                 GF_ERR_CUDA);
         ctx->stats.merge_launches++;
         out_off += (size_t)plan.groups * qp * K;

@@ -310,7 +310,8 @@ struct gf_set {
                    unsigned long long *d_out, int path, unsigned int *d_flags);
     int topk_scan(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                   int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
-                  unsigned long long *d_out, const int *d_q_map = nullptr, const unsigned int *d_q_count = nullptr);
+                  unsigned long long *d_out, const int *d_q_map = nullptr, const unsigned int *d_q_count = nullptr,
+                  bool scatter_out = false);  // scatter_out: query i's result goes to row d_q_map[i] of d_out
     //   phase 0: everything, results to d_out / d_flags;  1: query preparation only;
     //   2: everything after the preparation, results to the workspace (ws->t_res / ws->t_flags)
     int topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
