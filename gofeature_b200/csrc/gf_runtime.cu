@@ -1189,10 +1189,16 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
             int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path);
             if (rc) return rc;
             GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
-            GF_CUDA(cudaMemcpyAsync(d_out, ws->t_res, (size_t)q * K * 8, cudaMemcpyDeviceToDevice, stream), GF_ERR_CUDA);
-            if (d_flags)
-                GF_CUDA(cudaMemcpyAsync(d_flags, ws->t_flags, (size_t)q * 4, cudaMemcpyDeviceToDevice, stream),
-                        GF_ERR_CUDA);
+            // d_out / d_flags may be device memory or pinned host memory (Search hands its staging buffers in)
+            const size_t res_b = align_up((size_t)q * K * 8, 256);
+            if (d_flags && (uint8_t *)d_flags == (uint8_t *)d_out + res_b &&
+                (uint8_t *)ws->t_flags == (uint8_t *)ws->t_res + res_b) {
+                GF_CUDA(cudaMemcpyAsync(d_out, ws->t_res, res_b + (size_t)q * 4, cudaMemcpyDefault, stream), GF_ERR_CUDA);
+            } else {
+                GF_CUDA(cudaMemcpyAsync(d_out, ws->t_res, (size_t)q * K * 8, cudaMemcpyDefault, stream), GF_ERR_CUDA);
+                if (d_flags)
+                    GF_CUDA(cudaMemcpyAsync(d_flags, ws->t_flags, (size_t)q * 4, cudaMemcpyDefault, stream), GF_ERR_CUDA);
+            }
             g.stamp = ++ws->graph_clock;
             st.scan_launches += g.d_scan;
             st.gemm_launches += g.d_gemm;
@@ -1311,11 +1317,11 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     // small batches re-score EVERY collected candidate (~`target` rows per query) and skip the selection
     auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)64 << 20); };
     const size_t o_exact = carve((size_t)nq_max * (rescore_all(std::min(q, kGemmMaxQ)) ? (size_t)cap : (size_t)kp) * 8);
-    const size_t o_flags = carve((size_t)q * 4);
     const size_t o_map = carve((size_t)kFixupMaxQ * 4);
     const size_t o_count = carve(4);
     const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
     const size_t o_res = carve((size_t)q * K * 8);     // result keys when the caller's buffer must stay outside (phase 2)
+    const size_t o_flags = carve((size_t)q * 4);       // right behind the keys: one copy returns both
     int rc = ws->reserve_tensor(off);
     if (rc) return rc;
     uint8_t *T = ws->d_tensor;
@@ -1449,7 +1455,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         for (auto e : evs) cudaEventDestroy(e);
     }
     if (d_flags && phase == 0)
-        GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream),
+        GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDefault, stream),
                 GF_ERR_CUDA);
     return GF_OK;
 }
@@ -1554,7 +1560,12 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
     unsigned int *h_flags = (unsigned int *)((uint8_t *)h_out + align_up(out_keys * 8, 256));
 
     memcpy(h_q, queries, qbytes);
-    GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
+    // Tensor path, one band: the kernels read the queries from the pinned staging buffer and the winners
+    // come back in ONE copy (keys + flags) -- three stream operations per call instead of seven.  The scan
+    // path re-reads the queries in every CTA, so it gets a device copy.
+    const bool direct = k_total <= kMaxK && q <= kGemmMaxQ && tensor_eligible(q, kb_max, false, nullptr, search_path);
+    if (!direct)
+        GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
     ctx->stats.h2d_bytes += qbytes;
 
     // ---- set-wide top-k_total, in bands of <= kMaxK keys
@@ -1568,19 +1579,29 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
             GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)q * 8, cudaMemcpyHostToDevice, ws->stream),
                     GF_ERR_WRITE_INPUT_BUFFER);
         }
-        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out,
-                         search_path, d_flags);
-        if (rc) return rc;
-        GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
-                GF_ERR_READ_CUDA_BUFFER);
-        GF_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)q * 4, cudaMemcpyDeviceToHost, ws->stream),
-                GF_ERR_READ_CUDA_BUFFER);
+        if (direct) {
+            rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags);
+            if (rc) return rc;
+        } else {
+            rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out,
+                             search_path, d_flags);
+            if (rc) return rc;
+            GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
+                    GF_ERR_READ_CUDA_BUFFER);
+            GF_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)q * 4, cudaMemcpyDeviceToHost, ws->stream),
+                    GF_ERR_READ_CUDA_BUFFER);
+        }
         GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
         ctx->stats.d2h_bytes += (size_t)q * kb * 8 + (size_t)q * 4;
         // tensor-path queries that could neither be certified nor fixed on the device: exact scan, one by one
+        bool dq_ready = !direct;
         for (int i = 0; i < q; ++i) {
             if (!h_flags[i]) continue;
             ctx->stats.uncertified_queries++;
+            if (!dq_ready) {  // the direct path never uploaded the queries
+                GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
+                dq_ready = true;
+            }
             rc = topk_scan(ws, ws->stream, d_q + (size_t)i * dims, 1, dims, 1, kb, false, nullptr,
                            d_out + (size_t)i * kb);
             if (rc) return rc;
