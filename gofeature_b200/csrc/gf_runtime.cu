@@ -1510,6 +1510,91 @@ struct KeyList {
     bool exhausted = false;
 };
 
+// a search call waits ~0.2 ms for its stream: poll instead of paying a blocking wait's wake-up
+static cudaError_t wait_stream(cudaStream_t s)
+{
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+    for (int i = 0;; ++i) {
+        cudaError_t e = cudaStreamQuery(s);
+        if (e != cudaErrorNotReady) return e;
+        if ((i & 15) == 15 && std::chrono::steady_clock::now() >= deadline) return cudaStreamSynchronize(s);
+    }
+}
+
+bool Set::direct_applies(int limit, int q, int *kb) const
+{
+    if (precision != 4 || scanned_rows <= 0 || limit <= 0 || q <= 0 || q > kGemmMaxQ) return false;
+    const int64_t k_total = std::min<int64_t>(limit, scanned_rows);
+    if (k_total > kMaxK) return false;
+    *kb = (int)k_total;
+    return tensor_eligible(q, (int)k_total, false, nullptr, search_path);
+}
+
+int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, const int *part_q, int nparts,
+                     unsigned long long **h_keys)
+{
+    const size_t qbytes = (size_t)q * dims * 4;
+    const size_t out_keys = (size_t)q * kb;
+    const size_t d_need = align_up(qbytes, 256) + align_up(out_keys * 8, 256) + scratch_bytes(this, q, kb, false);
+    const size_t h_need = align_up(qbytes, 256) + align_up(out_keys * 8, 256) + align_up((size_t)q * 4, 256);
+    int rc = ws->reserve(d_need, h_need);
+    if (rc) return rc;
+    float *d_q = (float *)ws->d_buf;
+    unsigned long long *d_out = (unsigned long long *)(ws->d_buf + align_up(qbytes, 256));
+    float *h_q = (float *)ws->h_buf;
+    unsigned long long *h_out = (unsigned long long *)(ws->h_buf + align_up(qbytes, 256));
+    unsigned int *h_flags = (unsigned int *)((uint8_t *)h_out + align_up(out_keys * 8, 256));
+    size_t off = 0;
+    for (int i = 0; i < nparts; ++i) {
+        memcpy((uint8_t *)h_q + off, parts[i], (size_t)part_q[i] * dims * 4);
+        off += (size_t)part_q[i] * dims * 4;
+    }
+    ctx->stats.h2d_bytes += qbytes;
+    // The kernels read the queries from the pinned staging buffer and the winners come back in ONE copy
+    // (keys + flags): three stream operations per call.
+    rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags);
+    if (rc) return rc;
+    GF_CUDA(wait_stream(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+    ctx->stats.d2h_bytes += out_keys * 8 + (size_t)q * 4;
+    // tensor-path queries that could neither be certified nor fixed on the device: exact scan, one by one
+    bool dq_ready = false;
+    for (int i = 0; i < q; ++i) {
+        if (!h_flags[i]) continue;
+        ctx->stats.uncertified_queries++;
+        if (!dq_ready) {
+            GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
+            dq_ready = true;
+        }
+        rc = topk_scan(ws, ws->stream, d_q + (size_t)i * dims, 1, dims, 1, kb, false, nullptr, d_out + (size_t)i * kb);
+        if (rc) return rc;
+        GF_CUDA(cudaMemcpyAsync(h_out + (size_t)i * kb, d_out + (size_t)i * kb, (size_t)kb * 8, cudaMemcpyDeviceToHost,
+                                ws->stream),
+                GF_ERR_READ_CUDA_BUFFER);
+        GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+    }
+    *h_keys = h_out;
+    return GF_OK;
+}
+
+bool Set::resolve_winners(const unsigned long long *keys, int kb, float threshold, Result *r) const
+{
+    int n = 0;
+    while (n < kb && keys[n] != 0ull) ++n;
+    for (int j = 0; j < n; ++j) {  // tombstones among the winners?  (block.go:236-243 selects before it drops them)
+        int bp, row;
+        if (!slot_to_block(key_slot(keys[j]), &bp, &row) || !blocks[bp]->live[row]) return false;
+    }
+    for (int j = 0; j < n; ++j) {
+        const float sc = key_score(keys[j]);
+        if (!(sc >= threshold)) continue;  // set.go:145
+        int bp, row;
+        slot_to_block(key_slot(keys[j]), &bp, &row);
+        r->push(sc, key_slot(keys[j]), blocks[bp]->id_at(row));
+    }
+    r->end_query();
+    return true;
+}
+
 // set.go:118-159 + block.go:184-249
 int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out)
 {
@@ -1542,6 +1627,21 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
         ~Release() { c->release_ws(w); }
     } rel{ctx, ws};
 
+    int kb_direct = 0;
+    if (direct_applies(limit, q, &kb_direct)) {
+        unsigned long long *h_keys = nullptr;
+        rc = direct_keys(ws, kb_direct, q, &queries, &q, 1, &h_keys);
+        if (rc) return rc;
+        bool quirk = false;
+        for (int i = 0; i < q && !quirk; ++i) quirk = !resolve_winners(h_keys + (size_t)i * kb_direct, kb_direct, threshold, res.get());
+        if (!quirk) {
+            *out = res.release();
+            return GF_OK;
+        }
+        res.reset(new Result());  // a tombstone among the winners: the generic code below takes the per-block path
+        res->begin(q);
+    }
+
     const size_t qbytes = (size_t)q * dims * 4;
     const size_t out_keys = (size_t)q * kb_max;
     size_t d_need = align_up(qbytes, 256) + align_up((size_t)q * 8, 256) + align_up(out_keys * 8, 256) +
@@ -1560,12 +1660,7 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
     unsigned int *h_flags = (unsigned int *)((uint8_t *)h_out + align_up(out_keys * 8, 256));
 
     memcpy(h_q, queries, qbytes);
-    // Tensor path, one band: the kernels read the queries from the pinned staging buffer and the winners
-    // come back in ONE copy (keys + flags) -- three stream operations per call instead of seven.  The scan
-    // path re-reads the queries in every CTA, so it gets a device copy.
-    const bool direct = k_total <= kMaxK && q <= kGemmMaxQ && tensor_eligible(q, kb_max, false, nullptr, search_path);
-    if (!direct)
-        GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
+    GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
     ctx->stats.h2d_bytes += qbytes;
 
     // ---- set-wide top-k_total, in bands of <= kMaxK keys
@@ -1579,29 +1674,19 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
             GF_CUDA(cudaMemcpyAsync(d_upper, h_upper, (size_t)q * 8, cudaMemcpyHostToDevice, ws->stream),
                     GF_ERR_WRITE_INPUT_BUFFER);
         }
-        if (direct) {
-            rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags);
-            if (rc) return rc;
-        } else {
-            rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out,
-                             search_path, d_flags);
-            if (rc) return rc;
-            GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
-                    GF_ERR_READ_CUDA_BUFFER);
-            GF_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)q * 4, cudaMemcpyDeviceToHost, ws->stream),
-                    GF_ERR_READ_CUDA_BUFFER);
-        }
+        rc = topk_device(ws, ws->stream, d_q, q, dims, 1, kb, false, first_band ? nullptr : d_upper, d_out,
+                         search_path, d_flags);
+        if (rc) return rc;
+        GF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)q * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
+                GF_ERR_READ_CUDA_BUFFER);
+        GF_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)q * 4, cudaMemcpyDeviceToHost, ws->stream),
+                GF_ERR_READ_CUDA_BUFFER);
         GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
         ctx->stats.d2h_bytes += (size_t)q * kb * 8 + (size_t)q * 4;
         // tensor-path queries that could neither be certified nor fixed on the device: exact scan, one by one
-        bool dq_ready = !direct;
         for (int i = 0; i < q; ++i) {
             if (!h_flags[i]) continue;
             ctx->stats.uncertified_queries++;
-            if (!dq_ready) {  // the direct path never uploaded the queries
-                GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
-                dq_ready = true;
-            }
             rc = topk_scan(ws, ws->stream, d_q + (size_t)i * dims, 1, dims, 1, kb, false, nullptr,
                            d_out + (size_t)i * kb);
             if (rc) return rc;
@@ -1760,6 +1845,22 @@ int Set::search(float threshold, int limit, int q, const uint8_t *queries, Resul
 // with no threshold, and hands every follower its slice with its own threshold applied
 // (set.go:145 filters after selection, so filtering a shared top-limit is exact).  While a batch
 // runs, new callers queue up and form the next batch.
+// GF_CO_TIMING=1: where a coalesced round spends its host time (printed every 256 batches to stderr)
+namespace {
+struct CoTiming {
+    bool on = getenv("GF_CO_TIMING") != nullptr;
+    double gather = 0, copy = 0, search = 0, split = 0, handoff = 0;
+    long n = 0;
+    std::chrono::steady_clock::time_point last_done;
+    bool have_last = false;
+};
+CoTiming g_cot;
+inline double us_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b)
+{
+    return std::chrono::duration<double, std::micro>(b - a).count();
+}
+}  // namespace
+
 int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *queries, Result **out)
 {
     PendingSearch me;
@@ -1776,11 +1877,6 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         explicit Inside(std::atomic<int> &c_) : c(c_) { ++c; }
         ~Inside() { --c; }
     } inside(co_inside);
-    std::unique_lock<std::mutex> lk(co_mu);
-    me.returnee = (tl_set == this && tl_batch == co_batch_id && co_batch_id != 0);
-    co_queue.push_back(&me);
-    co_queued.store((int)co_queue.size(), std::memory_order_release);
-    co_cv.notify_all();  // a parked leader re-counts its company
     auto spin_until = [](const std::function<bool()> &ready, int us) {
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(us);
         for (int i = 0;; ++i) {
@@ -1791,18 +1887,26 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
 #endif
         }
     };
+    std::unique_lock<std::mutex> lk(co_mu);
+    me.returnee = (tl_set == this && tl_batch == co_batch_id && co_batch_id != 0);
+    co_queue.push_back(&me);
+    co_queued.store((int)co_queue.size(), std::memory_order_release);
+    co_cv.notify_all();  // a parked leader re-counts its company
+    bool my_retry = false;  // fast hand-off only: a tombstone among MY winners -> my own uncoalesced search
     while (!me.done.load(std::memory_order_acquire)) {
         if (co_leader_active.load()) {  // someone else is leading: wait to be served (or to take over)
             // a batch takes a few hundred microseconds: spin through it before paying a futex sleep + wake-up
             if (co_inside.load() <= hw - 4) {  // more waiters than spare cores: spinning would starve the leader
                 lk.unlock();
                 spin_until([&] { return me.done.load(std::memory_order_acquire) || !co_leader_active.load(); }, 600);
+                if (me.done.load(std::memory_order_acquire)) break;  // served: nothing left to do under the lock
                 lk.lock();
             }
             if (!me.done.load(std::memory_order_acquire) && co_leader_active.load()) co_cv.wait(lk);
             continue;
         }
         co_leader_active = true;
+        const auto t_lead = std::chrono::steady_clock::now();
         // How many callers to expect: everybody served by the previous batch is about to come back,
         // plus whoever queued up meanwhile and was not in it.  Wait for them, but never longer than
         // coalesce_wait_us: two half-size batches alternating cost twice the HBM traffic of one.
@@ -1831,6 +1935,87 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         }
         co_queued.store((int)co_queue.size(), std::memory_order_release);
         lk.unlock();
+        const auto t_gathered = std::chrono::steady_clock::now();
+        auto t_copied = t_gathered, t_searched = t_gathered;
+        if (group.size() > 1) ctx->stats.coalesced_batches++;
+
+        // ---- fast hand-off: one tensor-path pass, raw keys published, every caller resolves its own
+        bool fast = false;
+        {
+            SharedGuard g(lock);
+            int kb = 0;
+            if (!destroyed && direct_applies(limit, total, &kb) && ctx->bind() == GF_OK) {
+                Workspace *ws = ctx->acquire_ws();
+                if (ws) {
+                    fast = true;
+                    ctx->stats.searches++;
+                    std::vector<const uint8_t *> parts(group.size());
+                    std::vector<int> part_q(group.size());
+                    for (size_t i = 0; i < group.size(); ++i) {
+                        parts[i] = group[i]->queries;
+                        part_q[i] = group[i]->q;
+                    }
+                    unsigned long long *h_keys = nullptr;
+                    const int rc = direct_keys(ws, kb, total, parts.data(), part_q.data(), (int)group.size(), &h_keys);
+                    t_copied = t_searched = std::chrono::steady_clock::now();
+                    std::atomic<int> resolvers{(int)group.size() - 1};
+                    lk.lock();
+                    const uint64_t bid = ++co_batch_id;
+                    co_last_group = (int)group.size();
+                    int q0 = 0;
+                    const unsigned long long *mine = nullptr;
+                    for (PendingSearch *p : group) {
+                        p->rc = rc;
+                        p->batch_id = bid;
+                        if (p == &me) {
+                            mine = rc == GF_OK ? h_keys + (size_t)q0 * kb : nullptr;
+                        } else {
+                            p->keys = rc == GF_OK ? h_keys + (size_t)q0 * kb : nullptr;
+                            p->kb = kb;
+                            p->resolvers = &resolvers;
+                        }
+                        q0 += p->q;
+                    }
+                    for (PendingSearch *p : group)
+                        if (p != &me) p->done.store(true, std::memory_order_release);  // p may be gone right after its resolve
+                    co_leader_active = false;
+                    co_cv.notify_all();
+                    lk.unlock();
+                    if (mine) {
+                        me.result = new Result();
+                        me.result->begin(me.q);
+                        for (int i = 0; i < me.q && !my_retry; ++i)
+                            my_retry = !resolve_winners(mine + (size_t)i * kb, kb, me.threshold, me.result);
+                    }
+                    // the staging buffer and the read lock stay until every caller has read its keys
+                    for (int i = 0; resolvers.load(std::memory_order_acquire) > 0; ++i)
+                        if ((i & 1023) == 1023) std::this_thread::yield();
+                    ctx->release_ws(ws);
+                    me.done.store(true, std::memory_order_release);
+                }
+            }
+        }
+        if (fast) {
+            if (g_cot.on) {
+                const auto t_split = std::chrono::steady_clock::now();
+                std::lock_guard<std::mutex> tg(co_mu);
+                if (g_cot.have_last) g_cot.handoff += us_between(g_cot.last_done, t_lead);
+                g_cot.gather += us_between(t_lead, t_gathered);
+                g_cot.search += us_between(t_gathered, t_searched);
+                g_cot.split += us_between(t_searched, t_split);
+                g_cot.last_done = t_searched;
+                g_cot.have_last = true;
+                if (++g_cot.n % 256 == 0) {
+                    fprintf(stderr, "[co us/batch, fast] handoff=%.1f gather=%.1f search=%.1f resolve+wait=%.1f (group %d)\n",
+                            g_cot.handoff / 256, g_cot.gather / 256, g_cot.search / 256, g_cot.split / 256,
+                            (int)group.size());
+                    g_cot.handoff = g_cot.gather = g_cot.copy = g_cot.search = g_cot.split = 0;
+                }
+            }
+            break;  // me.done is set; the lock is not held
+        }
+
+        // ---- generic path (scan kernel, bands, empty sets ...): one search_now, results split by the leader
         std::vector<uint8_t> flat((size_t)total * qbytes);
         size_t off = 0;
         for (PendingSearch *p : group) {
@@ -1838,8 +2023,9 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
             off += (size_t)p->q * qbytes;
         }
         Result *all = nullptr;
+        t_copied = std::chrono::steady_clock::now();
         int rc = search_now(-INFINITY, limit, total, flat.data(), &all);
-        if (group.size() > 1) ctx->stats.coalesced_batches++;
+        t_searched = std::chrono::steady_clock::now();
         int q0 = 0;
         for (PendingSearch *p : group) {
             p->rc = rc;
@@ -1860,18 +2046,50 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         }
         delete all;
         lk.lock();
-        ++co_batch_id;
+        if (g_cot.on) {
+            const auto t_split = std::chrono::steady_clock::now();
+            if (g_cot.have_last) g_cot.handoff += us_between(g_cot.last_done, t_lead);
+            g_cot.gather += us_between(t_lead, t_gathered);
+            g_cot.copy += us_between(t_gathered, t_copied);
+            g_cot.search += us_between(t_copied, t_searched);
+            g_cot.split += us_between(t_searched, t_split);
+            g_cot.last_done = t_split;
+            g_cot.have_last = true;
+            if (++g_cot.n % 256 == 0) {
+                fprintf(stderr, "[co us/batch] handoff=%.1f gather=%.1f copy=%.1f search=%.1f split=%.1f (group %d)\n",
+                        g_cot.handoff / 256, g_cot.gather / 256, g_cot.copy / 256, g_cot.search / 256,
+                        g_cot.split / 256, (int)group.size());
+                g_cot.handoff = g_cot.gather = g_cot.copy = g_cot.search = g_cot.split = 0;
+            }
+        }
+        const uint64_t bid = ++co_batch_id;
         co_last_group = (int)group.size();
+        for (PendingSearch *p : group) p->batch_id = bid;
         for (PendingSearch *p : group)
             if (p != &me) p->done.store(true, std::memory_order_release);  // p may be gone right after this
         me.done.store(true, std::memory_order_release);
         co_leader_active = false;
         co_cv.notify_all();
     }
+    if (lk.owns_lock()) lk.unlock();
     tl_set = this;
-    tl_batch = co_batch_id;  // approximately: the batch that served me is the latest or close to it
-    lk.unlock();
-    if (me.rc) return me.rc;
+    tl_batch = me.batch_id;
+    if (me.rc) {
+        if (me.resolvers) me.resolvers->fetch_sub(1, std::memory_order_release);
+        return me.rc;
+    }
+    if (me.keys != nullptr) {  // fast hand-off: build my own result; the leader holds the set's read lock meanwhile
+        Result *r = new Result();
+        r->begin(me.q);
+        for (int i = 0; i < me.q && !my_retry; ++i)
+            my_retry = !resolve_winners(me.keys + (size_t)i * me.kb, me.kb, me.threshold, r);
+        me.resolvers->fetch_sub(1, std::memory_order_release);  // last access to anything the leader owns
+        me.result = r;
+    }
+    if (my_retry) {  // block.go:236-243's tombstone quirk: rare, and exact only per block
+        delete me.result;
+        return search_now(threshold, limit, q, queries, out);
+    }
     *out = me.result;
     return GF_OK;
 }

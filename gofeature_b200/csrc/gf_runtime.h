@@ -214,6 +214,12 @@ struct PendingSearch {
     int rc = 0;
     std::atomic<bool> done{false};
     bool returnee = false;  // this thread was served by the immediately preceding batch
+    // fast hand-off (tensor path, one band): the leader publishes raw keys and every caller builds its own
+    // result from them, in parallel, while the leader keeps the set's read lock
+    const unsigned long long *keys = nullptr;  // [q][kb] inside the leader's pinned staging buffer
+    int kb = 0;
+    std::atomic<int> *resolvers = nullptr;     // decremented once this caller no longer reads `keys`
+    uint64_t batch_id = 0;                     // the batch that served this caller
 };
 }
 
@@ -293,6 +299,14 @@ struct gf_set {
     int search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
                       cudaStream_t stream);
     int resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out);
+    // device part of a one-band tensor-path search of q queries gathered from `parts` (pointer, count):
+    // the keys [q][kb] are left in the workspace's pinned buffer (*h_keys).  Read lock held by the caller.
+    int direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, const int *part_q, int nparts,
+                    unsigned long long **h_keys);
+    bool direct_applies(int limit, int q, int *kb) const;
+    // winners of ONE query (zero-terminated or kb keys) -> r, threshold applied (set.go:145); false when a
+    // winner is a tombstone: block.go:236-243 then needs the per-block path
+    bool resolve_winners(const unsigned long long *keys, int kb, float threshold, Result *r) const;
     int destroy();
     int compact(int64_t *reclaimed);
     int export_rows(uint8_t *out_values, uint64_t values_cap, char *out_ids, uint64_t ids_cap, uint64_t *out_off,
