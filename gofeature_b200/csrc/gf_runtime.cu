@@ -1176,7 +1176,7 @@ bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long lo
 // be captured), replay goes into the caller's stream.
 int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                      int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
-                     unsigned long long *d_out, int path, unsigned int *d_flags)
+                     unsigned long long *d_out, int path, unsigned int *d_flags, bool bake_io)
 {
     static const bool no_graphs = getenv("GF_NO_GRAPHS") != nullptr || getenv("GF_STAGE_TIMING") != nullptr;
     const bool tensor = tensor_eligible(q, K, per_segment, d_upper, path);
@@ -1184,13 +1184,28 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     Stats &st = ctx->stats;
     const int mode = use_shadow(path) ? 1 : 0;
+    // bake_io (Search's own staging buffers, stable per workspace): the query preparation and the copy of
+    // keys + flags are nodes of the graph too -- ONE stream operation per call
+    bake_io = bake_io && d_flags != nullptr && q_stride == dims && l_stride == 1 && stream == ws->stream;
+    const size_t res_b = align_up((size_t)q * K * 8, 256);
     for (auto &g : ws->graphs) {
-        if (g.set == this && g.version == version && g.q == q && g.K == K && g.mode == mode) {
+        if (g.set == this && g.version == version && g.q == q && g.K == K && g.mode == mode &&
+            g.src == (bake_io ? (const void *)d_queries : nullptr) && g.dst == (bake_io ? (void *)d_out : nullptr)) {
+            g.stamp = ++ws->graph_clock;
+            st.scan_launches += g.d_scan;
+            st.gemm_launches += g.d_gemm;
+            st.merge_launches += g.d_merge;
+            st.other_launches += g.d_other + (bake_io ? 0 : 1);
+            st.tensor_passes += g.d_tensor_passes;
+            st.rows_scanned += g.d_rows;
+            if (bake_io) {
+                GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
+                return GF_OK;
+            }
             int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path);
             if (rc) return rc;
             GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
-            // d_out / d_flags may be device memory or pinned host memory (Search hands its staging buffers in)
-            const size_t res_b = align_up((size_t)q * K * 8, 256);
+            // d_out / d_flags may be device memory or pinned host memory
             if (d_flags && (uint8_t *)d_flags == (uint8_t *)d_out + res_b &&
                 (uint8_t *)ws->t_flags == (uint8_t *)ws->t_res + res_b) {
                 GF_CUDA(cudaMemcpyAsync(d_out, ws->t_res, res_b + (size_t)q * 4, cudaMemcpyDefault, stream), GF_ERR_CUDA);
@@ -1199,13 +1214,6 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
                 if (d_flags)
                     GF_CUDA(cudaMemcpyAsync(d_flags, ws->t_flags, (size_t)q * 4, cudaMemcpyDefault, stream), GF_ERR_CUDA);
             }
-            g.stamp = ++ws->graph_clock;
-            st.scan_launches += g.d_scan;
-            st.gemm_launches += g.d_gemm;
-            st.merge_launches += g.d_merge;
-            st.other_launches += g.d_other + 1;
-            st.tensor_passes += g.d_tensor_passes;
-            st.rows_scanned += g.d_rows;
             return GF_OK;
         }
     }
@@ -1222,7 +1230,18 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         ws->graphs_broken = true;
         return GF_OK;
     }
-    int crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path);
+    int crc = GF_OK;
+    if (bake_io) crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path);
+    if (crc == GF_OK) crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path);
+    if (crc == GF_OK && bake_io) {
+        const bool contig = (uint8_t *)d_flags == (uint8_t *)d_out + res_b &&
+                            (uint8_t *)ws->t_flags == (uint8_t *)ws->t_res + res_b;
+        cudaError_t me = cudaMemcpyAsync(d_out, ws->t_res, contig ? res_b + (size_t)q * 4 : (size_t)q * K * 8,
+                                         cudaMemcpyDefault, ws->stream);
+        if (me == cudaSuccess && !contig)
+            me = cudaMemcpyAsync(d_flags, ws->t_flags, (size_t)q * 4, cudaMemcpyDefault, ws->stream);
+        if (me != cudaSuccess) crc = GF_ERR_CUDA;
+    }
     cudaError_t ce = cudaStreamEndCapture(ws->stream, &graph);
     Workspace::CachedGraph cg{};  // what the recording pass "launched" did not run: take its counters back
     cg.d_scan = st.scan_launches - s0;
@@ -1257,6 +1276,8 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     cg.q = q;
     cg.K = K;
     cg.mode = mode;
+    cg.src = bake_io ? (const void *)d_queries : nullptr;
+    cg.dst = bake_io ? (void *)d_out : nullptr;
     cg.exec = exec;
     cg.stamp = ++ws->graph_clock;
     ws->graphs.push_back(cg);
@@ -1552,7 +1573,7 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     ctx->stats.h2d_bytes += qbytes;
     // The kernels read the queries from the pinned staging buffer and the winners come back in ONE copy
     // (keys + flags): three stream operations per call.
-    rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags);
+    rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags, true);
     if (rc) return rc;
     GF_CUDA(wait_stream(ws->stream), GF_ERR_READ_CUDA_BUFFER);
     ctx->stats.d2h_bytes += out_keys * 8 + (size_t)q * 4;

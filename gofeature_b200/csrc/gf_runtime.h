@@ -80,6 +80,8 @@ struct Workspace {
         const void *set;
         uint64_t version;
         int q, K, mode;
+        const void *src;  // baked-in query source / result destination (Search's pinned staging buffers), or
+        void *dst;        // null: the query preparation and the result copy stay outside the graph
         cudaGraphExec_t exec;
         uint64_t d_scan, d_gemm, d_merge, d_other, d_tensor_passes, d_rows;  // counters one replay adds
         uint64_t stamp;
@@ -318,7 +320,7 @@ struct gf_set {
     //   d_flags (optional, [q]): 1 where a tensor-path query could not be certified nor fixed on the device
     int topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                     int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
-                    unsigned long long *d_out, int path = 1, unsigned int *d_flags = nullptr);
+                    unsigned long long *d_out, int path = 1, unsigned int *d_flags = nullptr, bool bake_io = false);
     int topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                    int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
                    unsigned long long *d_out, int path, unsigned int *d_flags);
