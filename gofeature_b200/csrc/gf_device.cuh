@@ -10,6 +10,34 @@
 
 namespace gf {
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The search pipeline is a chain of ~9 short kernels around one long one; each is launched with
+// programmatic stream serialization so that its launch latency and CTA start-up overlap the tail of its
+// predecessor.  Contract: EVERY kernel of the chain executes pdl_wait() in every CTA before it reads
+// anything another kernel wrote (and before it exits) -- completion is then transitive along the chain.
+// Both instructions are no-ops in a kernel that was launched normally.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ------------------------------------------------------------------ keys
 // (orderable image of the score) << 32 | (0xFFFFFFFF - slot).  Larger = better:
 // score descending, then slot ascending.  NaN -> image 0 (worst), -0.0 -> +0.0.

@@ -200,15 +200,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
-        thr_s[i] = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
-        tmax_s[i] = 0u;
-    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)Cfg::kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // everything above is CTA-local set-up and overlaps the previous kernel; below, its results are read
+    pdl_wait();
+    if (a.mode != 0 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
+    for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+        thr_s[i] = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
+        tmax_s[i] = 0u;
     }
     tc_fence_before();
     __syncthreads();
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
         }
+        if (a.mode == 0 && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
     }
     tc_fence_before();
     __syncthreads();
@@ -391,6 +395,8 @@ __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_s
                                     float *__restrict__ copy, __nv_bfloat16 *__restrict__ dst_bf,
                                     float *__restrict__ qres2)
 {
+    pdl_wait();  // the previous call's kernels may still be reading dst / dst_bf
+    pdl_launch_dependents();
     const int qi = blockIdx.x;
     float acc = 0.f, res = 0.f;
     for (int e = threadIdx.x; e < dims; e += blockDim.x) {
@@ -455,6 +461,8 @@ template <int NV>
 __global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, int nq, int q, int m,
                                  float *__restrict__ thr, unsigned int *__restrict__ cnt)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
@@ -487,6 +495,8 @@ __global__ void __launch_bounds__(256)
                    const unsigned int *__restrict__ d_cnt, const float *__restrict__ queries, int kp,
                    const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int qi = blockIdx.y;
@@ -649,6 +659,8 @@ __global__ void __launch_bounds__(256)
 {
     __shared__ unsigned long long buf[kGemmCandCap];
     __shared__ int s_cnt;
+    pdl_wait();
+    pdl_launch_dependents();
     const int qi = blockIdx.x;
     const unsigned int n = cnt[qi];
     const int valid = all ? (int)(n < cap ? n : cap) : (int)((unsigned)kp < n ? (unsigned)kp : n);
@@ -722,6 +734,8 @@ __global__ void __launch_bounds__(256)
 {
     __shared__ unsigned long long buf[kGemmCandCap];
     __shared__ int s_cnt;
+    pdl_wait();
+    pdl_launch_dependents();
     const int qi = blockIdx.x;
     unsigned int n = d_cnt[qi];
     if (n > cap) n = cap;
@@ -778,8 +792,7 @@ cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Ge
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
     const int grid = sms < (int)ngroups ? sms : (int)ngroups;
     if (grid < 1) return cudaSuccess;
-    gemm_kernel<NQ, TM, EB><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, a);
-    return cudaGetLastError();
+    return launch_chain(gemm_kernel<NQ, TM, EB>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, a);
 }
 
 }  // namespace
@@ -850,9 +863,8 @@ cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_st
                                 float *dst, float *qnorm2, float *copy, void *dst_bf16, float *qres2,
                                 cudaStream_t stream)
 {
-    prep_queries_kernel<<<nq, 128, 0, stream>>>(src, q_stride, l_stride, q, nq, dims, dst, qnorm2, copy,
-                                                (__nv_bfloat16 *)dst_bf16, qres2);
-    return cudaGetLastError();
+    return launch_chain(prep_queries_kernel, dim3(nq), dim3(128), 0, stream, src, (long long)q_stride,
+                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, (__nv_bfloat16 *)dst_bf16, qres2);
 }
 
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
@@ -869,13 +881,13 @@ cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, 
     const int nv = (ntiles + 31) / 32;
     const int grid = (nq + 3) / 4;
     if (nv <= 5)
-        threshold_kernel<5><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+        return launch_chain(threshold_kernel<5>, dim3(grid), dim3(128), 0, stream, d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
     else if (nv <= 10)
-        threshold_kernel<10><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+        return launch_chain(threshold_kernel<10>, dim3(grid), dim3(128), 0, stream, d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
     else if (nv <= 19)
-        threshold_kernel<19><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+        return launch_chain(threshold_kernel<19>, dim3(grid), dim3(128), 0, stream, d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
     else
-        threshold_kernel<kGemmMaxSampleTiles / 32><<<grid, 128, 0, stream>>>(d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
+        return launch_chain(threshold_kernel<kGemmMaxSampleTiles / 32>, dim3(grid), dim3(128), 0, stream, d_tilemax, ntiles, nq, q, m, d_thr, d_cnt);
     return cudaGetLastError();
 }
 
@@ -883,8 +895,7 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
                           unsigned long long *d_sel, cudaStream_t stream)
 {
     if (cap > (unsigned)kGemmCandCap || kp > kGemmCandCap) return cudaErrorInvalidValue;
-    select_kernel<<<q, 256, 0, stream>>>(d_cand, d_cnt, cap, kp, d_sel);
-    return cudaGetLastError();
+    return launch_chain(select_kernel, dim3(q), dim3(256), 0, stream, d_cand, d_cnt, cap, kp, d_sel);
 }
 
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
@@ -892,9 +903,8 @@ cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_bas
                            const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream)
 {
     dim3 grid((kp * 32 + 255) / 256, q);
-    rescore_kernel<<<grid, 256, 0, stream>>>(d_segs, d_seg_slot_base, nseg, dims, d_cnt, d_queries_padded, kp, d_sel,
-                                             d_exact);
-    return cudaGetLastError();
+    return launch_chain(rescore_kernel, grid, dim3(256), 0, stream, d_segs, d_seg_slot_base, nseg, dims, d_cnt,
+                        d_queries_padded, kp, d_sel, d_exact);
 }
 
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
@@ -905,9 +915,8 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             cudaStream_t stream)
 {
     if (kp > kGemmCandCap || K > kp) return cudaErrorInvalidValue;
-    finalize_kernel<<<q, 256, 0, stream>>>(d_exact, d_sel, d_cnt, d_thr, cap, kp, all, K, rows_total, d_qnorm2,
-                                           d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags, fix);
-    return cudaGetLastError();
+    return launch_chain(finalize_kernel, dim3(q), dim3(256), 0, stream, d_exact, d_sel, d_cnt, d_thr, cap, kp, all, K,
+                        rows_total, d_qnorm2, d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags, fix);
 }
 
 }  // namespace gf

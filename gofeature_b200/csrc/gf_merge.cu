@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const unsigned lon
                                                              const unsigned int *__restrict__ d_q_count,
                                                              const int *__restrict__ d_out_map)
 {
+    pdl_wait();  // a link of the search chain (gf_device.cuh)
+    if (threadIdx.x == 0) pdl_launch_dependents();
     if (d_q_count != nullptr && (unsigned)blockIdx.x >= *d_q_count) return;  // fix-up pass with fewer live queries
     __shared__ unsigned long long buf[kMergeBuf];
     __shared__ unsigned long long red[kMergeThreads / 32];
@@ -292,8 +294,8 @@ cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, 
     if (d_out_map != nullptr && groups != 1) return cudaErrorInvalidValue;
     if (K < 1 || K > kMaxK || q < 1 || lists < 1 || groups < 1) return cudaErrorInvalidValue;
     dim3 grid(q, groups);
-    merge_kernel<<<grid, kMergeThreads, 0, stream>>>(d_in, lists, q, K, d_out, d_q_count, d_out_map);
-    return cudaGetLastError();
+    return launch_chain(merge_kernel, grid, dim3(kMergeThreads), 0, stream, d_in, lists, q, K, d_out, d_q_count,
+                        d_out_map);
 }
 
 cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, uint64_t seed, int64_t first_row, int normalize,

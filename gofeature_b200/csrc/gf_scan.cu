@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     unsigned long long *lists = reinterpret_cast<unsigned long long *>(ctl + QT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait();  // launched as a link of the search chain (gf_device.cuh): nothing global is touched before this
+    if (threadIdx.x == 0) pdl_launch_dependents();
     int q_live = a.q;
     if (a.q_count != nullptr) {
         const unsigned int c = *a.q_count;
@@ -269,6 +271,8 @@ __global__ void __launch_bounds__(kConsumerThreads) scan_generic_kernel(const Sc
     unsigned long long *lists = reinterpret_cast<unsigned long long *>(ctl + QT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    if (threadIdx.x == 0) pdl_launch_dependents();
     int q_live = a.q;
     if (a.q_count != nullptr) {
         const unsigned int c = *a.q_count;
@@ -352,8 +356,7 @@ cudaError_t launch_tma(const ScanPlan &plan, const ScanArgs &args, cudaStream_t 
         cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT>, plan.smem_bytes);
         if (e != cudaSuccess) return e;
         dim3 grid(plan.grid_x, plan.groups);
-        scan_tma_kernel<D, QT><<<grid, kScanThreads, plan.smem_bytes, stream>>>(args);
-        return cudaGetLastError();
+        return launch_chain(scan_tma_kernel<D, QT>, grid, dim3(kScanThreads), plan.smem_bytes, stream, args);
     }
 }
 
@@ -375,8 +378,7 @@ cudaError_t launch_generic(const ScanPlan &plan, const ScanArgs &args, cudaStrea
     cudaError_t e = set_smem_attr(scan_generic_kernel<QT>, plan.smem_bytes);
     if (e != cudaSuccess) return e;
     dim3 grid(plan.grid_x, plan.groups);
-    scan_generic_kernel<QT><<<grid, kConsumerThreads, plan.smem_bytes, stream>>>(args);
-    return cudaGetLastError();
+    return launch_chain(scan_generic_kernel<QT>, grid, dim3(kConsumerThreads), plan.smem_bytes, stream, args);
 }
 
 }  // namespace
