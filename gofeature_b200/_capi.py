@@ -107,6 +107,12 @@ SIGNATURES = {
     "gf_context_set_profiling": (c_int, [c_vp, c_int]),
     "gf_set_set_coalescing": (c_int, [c_vp, c_int]),
     "gf_set_set_search_path": (c_int, [c_vp, c_int]),
+    "gf_set_search_device_ex": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "gf_exchange_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, P(c_vp)]),
+    "gf_exchange_handle": (c_int, [c_vp, c_vp, c_u64]),
+    "gf_exchange_connect": (c_int, [c_vp, c_vp, c_u64]),
+    "gf_exchange_merge_device": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gf_exchange_destroy": (c_int, [c_vp]),
 }
 
 _lib = None

@@ -799,6 +799,112 @@ int gf_set_search_device(gf_set *set, int limit, int q, const float *d_queries, 
     });
 }
 
+int gf_set_search_device_ex(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys,
+                            uint32_t *d_out_flags, int path, void *stream)
+{
+    if (!set || !d_queries || !d_out_keys) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        return set->search_device(limit, q, d_queries, (unsigned long long *)d_out_keys, path, (cudaStream_t)stream,
+                                  (unsigned int *)d_out_flags);
+    });
+}
+
+// ---- peer exchange of per-rank winners over NVLink peer memory (one process per GPU)
+struct gf_exchange {
+    gf_context *ctx = nullptr;
+    int rank = 0, world = 1, max_q = 0, max_k = 0;
+    void *inbox = nullptr;
+    std::vector<void *> peers;  // mapped inboxes; peers[rank] == inbox
+    void **d_peers = nullptr;
+    unsigned long long seq = 0;
+    bool connected = false;
+};
+
+int gf_exchange_create(gf_context *ctx, int rank, int world, int max_q, int max_limit, gf_exchange **out)
+{
+    if (!ctx || !out || world < 1 || world > 64 || rank < 0 || rank >= world || max_q < 1 || max_limit < 1)
+        return GF_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if ((int64_t)world * max_limit > kExchangeMaxKeys) return GF_ERR_UNSUPPORTED;
+    return guarded([&]() -> int {
+        int rc = ctx->bind();
+        if (rc) return rc;
+        std::unique_ptr<gf_exchange> x(new gf_exchange());
+        x->ctx = ctx;
+        x->rank = rank;
+        x->world = world;
+        x->max_q = max_q;
+        x->max_k = max_limit;
+        const size_t bytes = exchange_inbox_bytes(world, max_q, max_limit);
+        GF_CUDA(cudaMalloc(&x->inbox, bytes), GF_ERR_ALLOCATE_GPU_BUFFER);  // cudaMalloc: exportable through CUDA IPC
+        GF_CUDA(cudaMemset(x->inbox, 0, bytes), GF_ERR_CLEAR_CUDA_BUFFER);
+        GF_CUDA(cudaMalloc((void **)&x->d_peers, sizeof(void *) * world), GF_ERR_ALLOCATE_GPU_BUFFER);
+        GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
+        x->peers.assign((size_t)world, nullptr);
+        x->peers[rank] = x->inbox;
+        *out = x.release();
+        return GF_OK;
+    });
+}
+
+int gf_exchange_handle(gf_exchange *x, void *out_handle, uint64_t cap)
+{
+    if (!x || !out_handle || cap < sizeof(cudaIpcMemHandle_t)) return GF_ERR_INVALID_ARGUMENT;
+    int rc = x->ctx->bind();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    GF_CUDA(cudaIpcGetMemHandle(&h, x->inbox), GF_ERR_CUDA);
+    memcpy(out_handle, &h, sizeof h);
+    return GF_OK;
+}
+
+int gf_exchange_connect(gf_exchange *x, const void *handles, uint64_t len)
+{
+    if (!x || !handles || len < (uint64_t)x->world * sizeof(cudaIpcMemHandle_t)) return GF_ERR_INVALID_ARGUMENT;
+    if (x->connected) return GF_ERR_INVALID_ARGUMENT;
+    int rc = x->ctx->bind();
+    if (rc) return rc;
+    for (int p = 0; p < x->world; ++p) {
+        if (p == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t *)handles + (size_t)p * sizeof h, sizeof h);
+        GF_CUDA(cudaIpcOpenMemHandle(&x->peers[p], h, cudaIpcMemLazyEnablePeerAccess), GF_ERR_CUDA);
+    }
+    GF_CUDA(cudaMemcpy(x->d_peers, x->peers.data(), sizeof(void *) * x->world, cudaMemcpyHostToDevice), GF_ERR_CUDA);
+    x->connected = true;
+    return GF_OK;
+}
+
+int gf_exchange_merge_device(gf_exchange *x, int q, int limit, const uint64_t *d_local_keys,
+                             const uint32_t *d_local_flags, uint64_t *d_out_keys, uint32_t *d_out_flags, void *stream)
+{
+    if (!x || !x->connected || !d_local_keys || !d_out_keys) return GF_ERR_INVALID_ARGUMENT;
+    if (q < 1 || limit < 1 || q > x->max_q || limit > x->max_k) return GF_ERR_UNSUPPORTED;
+    int rc = x->ctx->bind();
+    if (rc) return rc;
+    // every rank calls this the same number of times in the same order: the sequence number is implicit
+    const unsigned long long seq = ++x->seq;
+    GF_CUDA(exchange_merge_launch(x->d_peers, x->rank, x->world, q, limit, x->max_q, x->max_k, seq,
+                                  (const unsigned long long *)d_local_keys, d_local_flags,
+                                  (unsigned long long *)d_out_keys, d_out_flags, (cudaStream_t)stream),
+            GF_ERR_CUDA);
+    x->ctx->stats.merge_launches++;
+    return GF_OK;
+}
+
+int gf_exchange_destroy(gf_exchange *x)
+{
+    if (!x) return GF_OK;
+    x->ctx->bind();
+    cudaDeviceSynchronize();
+    for (int p = 0; p < x->world; ++p)
+        if (p != x->rank && x->peers[p]) cudaIpcCloseMemHandle(x->peers[p]);
+    if (x->d_peers) cudaFree(x->d_peers);
+    if (x->inbox) cudaFree(x->inbox);
+    delete x;
+    return GF_OK;
+}
+
 int gf_merge_keys_device(gf_context *ctx, int lists, int q, int limit, const uint64_t *d_in, uint64_t *d_out,
                          void *stream)
 {

@@ -61,6 +61,18 @@ cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, 
                          unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count = nullptr,
                          const int *d_out_map = nullptr);
 
+// Peer exchange + merge over NVLink peer memory (gf_merge.cu): d_peers = world inbox base pointers, inbox
+// layout keys [2][world][max_q][max_k] u64 then words [2][world][max_q] u64; world * K <= 2048.
+constexpr int kExchangeMaxKeys = 2048;
+inline size_t exchange_inbox_bytes(int world, int max_q, int max_k)
+{
+    return ((size_t)2 * world * max_q * max_k + (size_t)2 * world * max_q) * 8;
+}
+cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int q, int K, int max_q, int max_k,
+                                  unsigned long long seq, const unsigned long long *d_local_keys,
+                                  const unsigned int *d_local_flags, unsigned long long *d_out_keys,
+                                  unsigned int *d_out_flags, cudaStream_t stream);
+
 // ---- tcgen05 contraction path (gf_gemm.cu) ----
 constexpr int kGemmMaxQ = 256;       // queries per pass (N of the MMA)
 constexpr int kGemmCandCap = 4096;   // candidate keys kept per query

@@ -287,6 +287,109 @@ cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ peer exchange + merge (multi-GPU)
+// One kernel instead of ncclAllGather + merge: CTA i (query i) STORES this rank's K winners of query i
+// straight into every peer's inbox over NVLink (peer memory mapped with CUDA IPC), publishes a sequence
+// word per (rank, query), waits until the `world` words of query i have arrived in its own inbox, and
+// folds the world x K keys into the top-K.  The payload is 8 K bytes per query per peer, so the cost is
+// one NVLink store round (a few microseconds) instead of a collective's launch + protocol latency.
+// Inbox (per rank, two slots alternating with the sequence parity so a fast peer can run one step ahead):
+//   keys  [2][world][max_q][max_k] u64      words [2][world][max_q] u64 = seq << 1 | uncertified-flag
+namespace {
+struct ExchangeArgs {
+    void *const *peers;  // world inbox base pointers (device array); peers[rank] is this rank's own
+    int rank, world, q, K, max_q, max_k;
+    unsigned long long seq;
+    const unsigned long long *local_keys;  // [q][K]
+    const unsigned int *local_flags;       // optional [q]
+    unsigned long long *out_keys;          // [q][K]
+    unsigned int *out_flags;               // optional [q]: OR of every rank's flag; 0xFFFFFFFF = a peer never arrived
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeArgs a)
+{
+    __shared__ unsigned long long buf[kMergeBuf];
+    __shared__ unsigned int s_flag;
+    pdl_wait();
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    const int qi = blockIdx.x, K = a.K, world = a.world;
+    const int slot = (int)(a.seq & 1ull);
+    const size_t keys_per_slot = (size_t)world * a.max_q * a.max_k;
+    const size_t words_off = 2 * keys_per_slot;  // in u64 units
+    // ---- push my K keys of this query into every inbox (mine included)
+    for (int i = threadIdx.x; i < world * K; i += blockDim.x) {
+        const int p = i / K, j = i - p * K;
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.peers[p]) + (size_t)slot * keys_per_slot +
+                                  ((size_t)a.rank * a.max_q + qi) * a.max_k + j;
+        *dst = a.local_keys[(size_t)qi * K + j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned long long word = (a.seq << 1) | ((a.local_flags != nullptr && a.local_flags[qi]) ? 1ull : 0ull);
+        volatile unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[threadIdx.x]) + words_off +
+                                         ((size_t)slot * world + a.rank) * a.max_q + qi;
+        *w = word;
+    }
+    // ---- wait for everybody's keys of this query
+    if (threadIdx.x == 0) s_flag = 0u;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        volatile unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[a.rank]) + words_off +
+                                         ((size_t)slot * world + threadIdx.x) * a.max_q + qi;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned long long word;
+        unsigned int spins = 0;
+        while (((word = *w) >> 1) != a.seq) {
+            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {  // a peer died: do not hang the GPU
+                atomicOr(&s_flag, 0xFFFFFFFFu);
+                break;
+            }
+        }
+        if (word & 1ull) atomicOr(&s_flag, 1u);
+    }
+    __threadfence_system();
+    __syncthreads();
+    // ---- fold world x K keys (world * K <= kMergeBuf, checked by the host)
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(a.peers[a.rank]) +
+                                     (size_t)slot * keys_per_slot;
+    const int n = world * K;
+    int np = 2;
+    while (np < n) np <<= 1;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        unsigned long long v = 0ull;
+        if (i < n) {
+            const int r = i / K, j = i - r * K;
+            v = __ldcv(mine + ((size_t)r * a.max_q + qi) * a.max_k + j);
+        }
+        buf[i] = v;
+    }
+    __syncthreads();
+    block_sort_desc(buf, np);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) a.out_keys[(size_t)qi * K + i] = buf[i];
+    if (a.out_flags != nullptr && threadIdx.x == 0) a.out_flags[qi] = s_flag;
+}
+}  // namespace
+
+cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int q, int K, int max_q, int max_k,
+                                  unsigned long long seq, const unsigned long long *d_local_keys,
+                                  const unsigned int *d_local_flags, unsigned long long *d_out_keys,
+                                  unsigned int *d_out_flags, cudaStream_t stream)
+{
+    if (q < 1 || K < 1 || q > max_q || K > max_k || world * K > kMergeBuf || world > 256) return cudaErrorInvalidValue;
+    ExchangeArgs a{d_peers, rank, world, q, K, max_q, max_k, seq, d_local_keys, d_local_flags, d_out_keys, d_out_flags,
+                   5000000000ull};
+    return launch_chain(exchange_merge_kernel, dim3(q), dim3(256), 0, stream, a);
+}
+
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
                          unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count,
                          const int *d_out_map)

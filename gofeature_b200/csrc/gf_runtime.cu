@@ -2116,7 +2116,7 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
 }
 
 int Set::search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
-                       cudaStream_t stream)
+                       cudaStream_t stream, unsigned int *d_flags)
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (q > batch) return GF_ERR_OUT_OF_BATCH;
@@ -2138,6 +2138,7 @@ int Set::search_device(int limit, int q, const float *d_queries, unsigned long l
     cudaStream_t st = stream;  // NULL is the CUDA legacy default stream, as everywhere in CUDA
     if (scanned_rows == 0) {
         GF_CUDA(cudaMemsetAsync(d_out, 0, (size_t)q * limit * 8, st), GF_ERR_CUDA);
+        if (d_flags) GF_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)q * 4, st), GF_ERR_CUDA);
         return GF_OK;
     }
     size_t need = scratch_bytes(this, q, limit, false);
@@ -2146,7 +2147,7 @@ int Set::search_device(int limit, int q, const float *d_queries, unsigned long l
         rc = ws->reserve(need, 0);
         if (rc) return rc;
     }
-    return topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out, path == 0 ? 0 : path, nullptr);
+    return topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out, path, d_flags);
 }
 
 int Set::resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out)

@@ -299,7 +299,7 @@ struct gf_set {
     int search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out);
     int search_coalesced(float threshold, int limit, int q, const uint8_t *queries, Result **out);
     int search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
-                      cudaStream_t stream);
+                      cudaStream_t stream, unsigned int *d_flags = nullptr);
     int resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out);
     // device part of a one-band tensor-path search of q queries gathered from `parts` (pointer, count):
     // the keys [q][kb] are left in the workspace's pinned buffer (*h_keys).  Read lock held by the caller.

@@ -14,6 +14,8 @@ The collective steps are free functions on tensors of any device so that the hos
 (striping, key merge, id exchange) is testable with gloo at world_size 2 without a GPU;
 `ShardedSet` binds them to the CUDA library.
 """
+import os
+
 import numpy as np
 
 from . import api
@@ -173,6 +175,45 @@ class ShardedSet:
         self.cap = cache.GetBlockSize() // (dims * 4)
         self.total_rows = 0
         self._bufs = {}
+        self._xchg = None
+        if world > 1 and os.environ.get("GF_NO_P2P") is None:
+            self._connect_exchange()
+
+    # ---- peer exchange (one kernel over NVLink peer memory instead of all-gather + merge)
+    def _connect_exchange(self):
+        """Collective.  Every rank maps every other rank's inbox through CUDA IPC; if any rank cannot
+        (no peer access, IPC closed in the container ...) ALL ranks keep the NCCL all-gather path."""
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        L = api.lib()
+        dev = "cuda:%d" % self.ctx.device
+        self._x_max_q = max(self.batch, 16)
+        self._x_max_k = min(256, 2048 // self.world)
+        h = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        ok = L.gf_exchange_create(self.ctx._h, self.rank, self.world, self._x_max_q, self._x_max_k, ctypes.byref(h)) == 0
+        ok = ok and L.gf_exchange_handle(h, handle, 64) == 0
+        mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+        everyone = torch.empty((self.world, 65), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        everyone = everyone.cpu().numpy()
+        if ok and everyone[:, 64].all():
+            blob = np.ascontiguousarray(everyone[:, :64]).tobytes()
+            ok = L.gf_exchange_connect(h, blob, len(blob)) == 0
+        else:
+            ok = False
+        agreed = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.group)
+        if int(agreed.item()) == 1:
+            self._xchg = h
+        elif h:
+            L.gf_exchange_destroy(h)
+
+    def close_exchange(self):
+        if self._xchg is not None:
+            api.lib().gf_exchange_destroy(self._xchg)
+            self._xchg = None
 
     # ---- mutation (collective: every rank passes the same arguments)
     def Add(self, values, ids):
@@ -207,6 +248,9 @@ class ShardedSet:
             self._bufs[key] = dict(
                 dq=torch.empty((q, self.dims), dtype=torch.float32, device=dev),
                 local=torch.zeros((q, limit), dtype=torch.int64, device=dev),
+                lflags=torch.zeros((q,), dtype=torch.int32, device=dev),
+                mflags=torch.zeros((q,), dtype=torch.int32, device=dev),
+                hflags=torch.zeros((q,), dtype=torch.int32).pin_memory(),
                 gathered=torch.zeros((self.world, q, limit), dtype=torch.int64, device=dev),
                 merged=torch.zeros((q, limit), dtype=torch.int64, device=dev),
                 hq=torch.empty((q, self.dims), dtype=torch.float32).pin_memory(),
@@ -214,23 +258,38 @@ class ShardedSet:
             )
         return self._bufs[key]
 
-    def search_device(self, limit, q, dq):
+    def search_device(self, limit, q, dq, path=0):
         """Collective device-resident search: dq [q, dims] float32 on this rank's GPU (same on all
         ranks) -> merged keys [q, limit] int64 tensor, identical on every rank.  Enqueues on the
-        current torch stream; no host synchronisation."""
+        current torch stream; no host synchronisation.  `self.flags(q, limit)` is non-zero for a query
+        that some rank could not certify on its tensor path (the caller re-runs with path=1)."""
         import torch
+        import torch.distributed as dist
         t = self._tensors(q, limit)
         stream = torch.cuda.current_stream().cuda_stream
-        self.local.SearchDevice(limit, q, dq.data_ptr(), t["local"].data_ptr(), 0, stream)
+        L = api.lib()
+        api._check(L.gf_set_search_device_ex(self.local._h, limit, q, dq.data_ptr(), t["local"].data_ptr(),
+                                             t["lflags"].data_ptr(), path, stream))
         if self.world == 1:
+            t["mflags"].copy_(t["lflags"], non_blocking=True)
             return t["local"]
+        if self._xchg is not None and q <= self._x_max_q and limit <= self._x_max_k:
+            # push my winners into every peer's inbox, wait for theirs, merge: one kernel
+            api._check(L.gf_exchange_merge_device(self._xchg, q, limit, t["local"].data_ptr(), t["lflags"].data_ptr(),
+                                                  t["merged"].data_ptr(), t["mflags"].data_ptr(), stream))
+            return t["merged"]
         gathered = gather_keys(t["local"], self.world, self.group, out=t["gathered"])
-        api._check(api.lib().gf_merge_keys_device(self.ctx._h, self.world, q, limit, gathered.data_ptr(),
-                                                  t["merged"].data_ptr(), stream))
+        api._check(L.gf_merge_keys_device(self.ctx._h, self.world, q, limit, gathered.data_ptr(),
+                                          t["merged"].data_ptr(), stream))
+        t["mflags"].copy_(t["lflags"], non_blocking=True)
+        dist.all_reduce(t["mflags"], op=dist.ReduceOp.MAX, group=self.group)
         return t["merged"]
 
+    def flags(self, q, limit):
+        return self._tensors(q, limit)["mflags"]
+
     def search_keys(self, limit, queries):
-        """Host queries [q, dims] -> merged keys [q, limit] uint64 on the host (H2D, scan, gather,
+        """Host queries [q, dims] -> merged keys [q, limit] uint64 on the host (H2D, scan, exchange,
         merge, D2H all inside)."""
         import torch
         queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dims)
@@ -242,7 +301,17 @@ class ShardedSet:
         t["dq"].copy_(t["hq"], non_blocking=True)
         merged = self.search_device(limit, q, t["dq"])
         t["hk"].copy_(merged, non_blocking=True)
+        t["hflags"].copy_(t["mflags"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        hf = t["hflags"].numpy()
+        if hf.any():
+            if (hf == -1).any():
+                raise RuntimeError("gofeature_b200: a peer rank did not reach the exchange within 5 s")
+            # some rank could not certify a query on its tensor path (every rank sees the same flags):
+            # run the batch again through the exact scan kernel
+            merged = self.search_device(limit, q, t["dq"], path=1)
+            t["hk"].copy_(merged, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         return t["hk"].numpy().view(np.uint64).copy()
 
     def Search(self, threshold, limit, queries):

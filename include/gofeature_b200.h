@@ -271,6 +271,28 @@ GF_API int gf_set_set_shard(gf_set *set, int rank, int world);
  * 3 = the same on the float32 rows (kind::tf32). */
 GF_API int gf_set_search_device(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys,
                                 int path, void *stream);
+/* gf_set_search_device with per-query flags: d_out_flags[q] (optional) is 1 where the tensor path could
+ * neither certify nor repair a query on the device (more than 8 such queries in one call); the keys
+ * of a flagged query are not guaranteed exact and the caller re-runs it with path = 1. */
+GF_API int gf_set_search_device_ex(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys,
+                                   uint32_t *d_out_flags, int path, void *stream);
+
+/* ---- Peer exchange (multi-GPU, one process per GPU): the cross-rank step of a sharded search as ONE
+ * kernel over NVLink peer memory instead of ncclAllGather + merge.  Every rank creates an exchange,
+ * publishes the 64-byte CUDA IPC handle of its inbox (gf_exchange_handle), receives everybody's
+ * handles (any transport: the tests use torch.distributed) and connects.  gf_exchange_merge_device is
+ * collective: all ranks call it once per search, in the same order, each with its own [q][limit]
+ * winners; every rank gets the merged top-`limit` per query.  d_out_flags[q] (optional) = OR of the
+ * ranks' d_local_flags, 0xFFFFFFFF if a peer did not arrive within 5 s.  world * max_limit <= 2048. */
+typedef struct gf_exchange gf_exchange;
+GF_API int gf_exchange_create(gf_context *ctx, int rank, int world, int max_q, int max_limit, gf_exchange **out);
+GF_API int gf_exchange_handle(gf_exchange *x, void *out_handle, uint64_t cap);           /* 64 bytes */
+GF_API int gf_exchange_connect(gf_exchange *x, const void *handles, uint64_t len);        /* world * 64 bytes, rank order */
+GF_API int gf_exchange_merge_device(gf_exchange *x, int q, int limit, const uint64_t *d_local_keys,
+                                    const uint32_t *d_local_flags, uint64_t *d_out_keys, uint32_t *d_out_flags,
+                                    void *stream);
+GF_API int gf_exchange_destroy(gf_exchange *x);
+
 /* Merge `lists` candidate lists (each [q][limit], e.g. the all-gathered per-rank winners)
  * into the top-`limit` per query.  d_in: [lists][q][limit]; d_out: [q][limit]. */
 GF_API int gf_merge_keys_device(gf_context *ctx, int lists, int q, int limit, const uint64_t *d_in, uint64_t *d_out,
