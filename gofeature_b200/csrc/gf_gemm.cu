@@ -153,17 +153,24 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
 // than the L2 latency lets 4 stages cover (measured: 53 % tensor utilisation, and sharing B across a CTA
 // pair by multicast did not help because the footprint per stage stayed).  With TM = 2 a stage feeds
 // 1024 MMA cycles with 64 KB, and the kernel goes back to being HBM-bound.
+// COLLECT appends are staged in shared memory and flushed 128 at a time: a global atomicAdd per survivor
+// inside the score loop stalled the whole epilogue warp for an L2 round trip (4 per warp per tile at 256
+// queries x ~500 candidates), longer than the MMAs of the next tile take
+constexpr int kAppendStage = 256;
+constexpr int kAppendStageBytes = kAppendStage * 12 + 16;
+
 template <int NQ, int TM>
 struct GemmCfg {
     static constexpr int kBBytes = NQ * 128;
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
-    static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 8 - 1024) / kStageBytes);
+    static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 8 - 1024 - kAppendStageBytes) / kStageBytes);
     static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
     static constexpr int kBuf = (2 * TM * NQ <= 512) ? 2 : 1;  // accumulator sets (double buffering when TMEM allows)
     static constexpr int kTmemColsRaw = kBuf * TM * NQ;
     static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
     static constexpr int kChunk = (NQ >= 32) ? 32 : 16;
-    static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 8;
+    static constexpr size_t kSmem =
+        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 8 + kAppendStageBytes;
     static_assert(kStages >= 2, "pipeline too shallow");
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
@@ -183,6 +190,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     float *thr_s = reinterpret_cast<float *>(tail + 256);
     unsigned int *tmax_s = reinterpret_cast<unsigned int *>(thr_s + NQ);
+    unsigned long long *stage_key = reinterpret_cast<unsigned long long *>(tmax_s + NQ);  // 8-byte aligned: NQ % 2 == 0
+    int *stage_q = reinterpret_cast<int *>(stage_key + kAppendStage);
+    int *stage_n = stage_q + kAppendStage;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kBK = KBlock<EB>::kElems;
@@ -213,6 +223,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         thr_s[i] = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
         tmax_s[i] = 0u;
     }
+    if (threadIdx.x == 0) *stage_n = 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -326,8 +337,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                             for (int jj = 0; jj < Cfg::kChunk; ++jj)
                                 if (jj == b) sc = __uint_as_float(r[jj]);
                             const int qi = c0 + b;
-                            const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
-                            if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
+                            const int sp = atomicAdd(stage_n, 1);
+                            if (sp < kAppendStage) {
+                                stage_key[sp] = make_key(sc, slot);
+                                stage_q[sp] = qi;
+                            } else {  // stage full (a burst of survivors): append directly
+                                const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
+                                if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
+                            }
                         }
                     } else if (a.mode == 1) {
                         // TILEMAX: per query the best score of this tile (threshold estimation sample)
@@ -375,6 +392,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (a.mode == 0) {
+                // the accumulator is released; flush the staged survivors when the stage is half full or
+                // this was the CTA's last group (all four epilogue warps take the same branch)
+                named_bar_sync(2, 128);
+                const int staged = *reinterpret_cast<volatile int *>(stage_n);
+                if (staged >= kAppendStage / 2 || g + gridDim.x >= ngroups) {
+                    const int n = staged < kAppendStage ? staged : kAppendStage;
+                    for (int e = (int)threadIdx.x - 64; e < n; e += 128) {
+                        const int qi = stage_q[e];
+                        const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
+                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = stage_key[e];
+                    }
+                    named_bar_sync(2, 128);
+                    if (threadIdx.x == 64) *stage_n = 0;
+                    named_bar_sync(2, 128);
+                }
+            }
         }
         if (a.mode == 0 && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
     }

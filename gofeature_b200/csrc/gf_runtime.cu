@@ -1314,7 +1314,9 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     int G = std::min(kGemmMaxSampleTiles, waves * ctx->sms);
     G = (int)std::min<uint32_t>((uint32_t)G, total_gtiles);
     const uint32_t stride = total_gtiles / (uint32_t)G;
-    const double target = std::max(512.0, 4.0 * kp);
+    // rows per query that should pass the COLLECT threshold: enough that K' of them are there despite the
+    // sampling noise of the threshold estimate, few enough that appends stay rare
+    const double target = std::max(512.0, 2.0 * kp + 64.0);
     int m = (int)std::ceil(target * G / (double)total_gtiles);
     m = std::max(2, std::min(m, G / 2));
 
