@@ -95,6 +95,17 @@ func NewCache(ctx *Context, blockNum, blockSize int) (Cache, error) {
 	return c, nil
 }
 
+// NewCacheNoShadow : NewCache without the bf16 shadow slab (blockSize/2 fewer bytes per block; the
+// tensor path then streams the float32 rows).  Results are identical either way.
+func NewCacheNoShadow(ctx *Context, blockNum, blockSize int) (Cache, error) {
+	c := &cache{ctx: ctx}
+	if err := errFromStatus(C.gf_cache_create_ex(ctx.h, C.int(blockNum), C.int64_t(blockSize),
+		C.uint(C.GF_CACHE_NO_SHADOW), &c.h)); err != nil {
+		return nil, err
+	}
+	return c, nil
+}
+
 func (c *cache) NewSet(name string, dims, precision, batch int) error {
 	n := C.CString(name)
 	defer C.free(unsafe.Pointer(n))
