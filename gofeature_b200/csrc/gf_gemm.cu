@@ -27,7 +27,11 @@ namespace gf {
 
 namespace {
 
-constexpr int kGemmThreads = 192;
+// warp 0 producer, warp 1 MMA, then the epilogue warps: 4 (one per TMEM lane quarter) or, from 64 queries up,
+// 8 (two per quarter, each taking half of the query columns) -- one warp per scheduler cannot hide its own
+// tcgen05.ld / compare latency, and at 256 queries the epilogue, not the MMA, bounded the tile time
+__host__ __device__ constexpr int gemm_epi_warps(int nq) { return nq >= 64 ? 8 : 4; }
+__host__ __device__ constexpr int gemm_threads(int nq) { return 64 + 32 * gemm_epi_warps(nq); }
 constexpr int kTileRows = 128;
 constexpr int kABytes = kTileRows * 128;  // one K block = one 128-byte swizzle row per feature row
 // elements per K block: 32 floats (kind::tf32 on the fp32 slab) or 64 bf16 (kind::f16 on the bf16 shadow)
@@ -62,6 +66,47 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// 2-CTA (cta_group::2) variants.  The pair's LEADER (cluster rank 0) owns the full / tempty barriers:
+// both CTAs' TMA loads complete on the leader's full barrier, the peer's epilogue warps arrive on the
+// leader's tempty barrier; `leader_addr` maps a local shared address to the same offset in CTA 0.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t leader_addr(const void *p)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar)  // arrives on `bar` in BOTH CTAs of the pair
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    // relaxed: the accumulator reads are ordered by tcgen05.wait::ld + fence::before_thread_sync already; a
+    // .release arrive at cluster scope costs MEMBAR.ALL.GPU + ERRBAR per tile (27 % of the pair kernel's samples)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -71,11 +116,18 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T over 32 bytes of K: one K = 8 step of kind::tf32 (EB = 4)
 // or one K = 16 step of kind::f16 with bf16 operands (EB = 2)
-template <int EB>
+template <int EB, bool PAIR>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate)
 {
-    if (EB == 4) {
+    if (PAIR) {  // M = 256 over the CTA pair, bf16 operands only
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if (EB == 4) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
@@ -159,9 +211,9 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
 constexpr int kAppendStage = 256;
 constexpr int kAppendStageBytes = kAppendStage * 12 + 16;
 
-template <int NQ, int TM>
+template <int NQ, int TM, bool PAIR = false>
 struct GemmCfg {
-    static constexpr int kBBytes = NQ * 128;
+    static constexpr int kBBytes = (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
     static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 8 - 1024 - kAppendStageBytes) / kStageBytes);
     static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
@@ -175,11 +227,12 @@ struct GemmCfg {
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
 
-template <int NQ, int TM, int EB>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int NQ, int TM, int EB, bool PAIR>
+__global__ void __launch_bounds__(gemm_threads(NQ), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
 {
-    using Cfg = GemmCfg<NQ, TM>;
+    static_assert(!PAIR || (TM == 1 && EB == 2), "the 2-CTA variant: one tile per CTA, bf16 operands");
+    using Cfg = GemmCfg<NQ, TM, PAIR>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *tail = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
@@ -197,7 +250,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kBK = KBlock<EB>::kElems;
     const int kblocks = a.dims / kBK;
-    const uint32_t ngroups = (a.tile_count + TM - 1) / TM;  // a group = TM consecutive tiles of this launch
+    // a group = the tiles one worker takes per step: TM consecutive tiles of a CTA, or (PAIR) two consecutive
+    // tiles, one per CTA of the pair (256 feature rows = M of one cta_group::2 MMA)
+    constexpr int kEpiWarps = gemm_epi_warps(NQ), kEpiThreads = 32 * kEpiWarps;
+    constexpr int kGroupTiles = PAIR ? 2 : TM;
+    const uint32_t ngroups = (a.tile_count + kGroupTiles - 1) / kGroupTiles;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+    const uint32_t nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
@@ -206,15 +266,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], (PAIR ? 2 : 1) * kEpiWarps);  // a pair: both CTAs' epilogue warps release the leader's accumulator
         }
         mbar_fence_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)Cfg::kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {  // both CTAs' warp 1, same shared offset for the result
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)Cfg::kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)Cfg::kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     // everything above is CTA-local set-up and overlaps the previous kernel; below, its results are read
     pdl_wait();
@@ -225,7 +292,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     if (threadIdx.x == 0) *stage_n = 0;
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -234,11 +304,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0, segi = 0;
-            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            for (uint32_t g = worker; g < ngroups; g += nworkers) {
                 int slab_row[TM];
 #pragma unroll
                 for (int j = 0; j < TM; ++j) {
-                    uint32_t i = g * TM + j;
+                    uint32_t i = PAIR ? g * 2 + cta_rank : g * TM + j;
                     if (i >= a.tile_count) i = a.tile_count - 1;  // odd tail: shadow the last tile
                     const uint32_t t = a.tile_first + i * a.tile_stride;
                     uint32_t row0, valid;
@@ -248,10 +318,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                    if (PAIR) {
+                        // each CTA loads its own 128 rows and its half of the queries; both complete on the
+                        // leader's barrier, which expects the bytes of the whole pair
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+                        const uint32_t lbar = leader_addr(&full[s]);
+                        tma_load_2d_pair(sa, &tmA, kb * kBK, slab_row[0], lbar);
+                        tma_load_2d_pair(sa + kABytes, &tmB, kb * kBK, (int)cta_rank * (NQ / 2), lbar);
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
 #pragma unroll
-                    for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
-                    tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
+                        for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
+                        tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
+                    }
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
@@ -260,12 +339,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc<EB>(kTileRows, NQ);
+        // ===================== MMA issuer (the pair's leader only) =====================
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = instr_desc<EB>(PAIR ? 2 * kTileRows : kTileRows, NQ);
             int s = 0;
             uint32_t ph = 0, it = 0;
-            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+            for (uint32_t g = worker; g < ngroups; g += nworkers, ++it) {
                 const uint32_t buf = it % Cfg::kBuf;
                 mbar_wait(&tempty[buf], ((it / Cfg::kBuf) & 1) ^ 1);
                 tc_fence_after();
@@ -280,30 +359,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                         const uint64_t adesc = smem_desc_sw128(sa + j * kABytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
-                            tc_mma<EB>(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                        (uint32_t)((kb | k) != 0));
+                            tc_mma<EB, PAIR>(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                             (uint32_t)((kb | k) != 0));
                     }
-                    tc_commit(&empty[s]);  // frees the stage when these MMAs have read it
+                    // frees the stage (in both CTAs of a pair) when these MMAs have read it
+                    if (PAIR) tc_commit_pair(&empty[s]); else tc_commit(&empty[s]);
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
                     }
                 }
-                tc_commit(&tfull[buf]);  // accumulators of the group complete
+                // accumulators of the group complete (each CTA of a pair holds its 128 rows)
+                if (PAIR) tc_commit_pair(&tfull[buf]); else tc_commit(&tfull[buf]);
             }
         }
     } else {
         // ===================== epilogue: one feature row per thread =====================
         const int quarter = warp & 3;  // TMEM lanes this warp may read
         const uint32_t row = quarter * 32 + lane;
+        // with 8 epilogue warps, warps 2..5 take the lower half of the query columns, warps 6..9 the upper half
+        constexpr int kColsPerWarp = NQ / (kEpiWarps / 4);
+        const int col_first = ((warp - 2) >> 2) * kColsPerWarp;
         uint32_t it = 0, segi = 0;
-        for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+        for (uint32_t g = worker; g < ngroups; g += nworkers, ++it) {
             const uint32_t buf = it % Cfg::kBuf;
             mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int j = 0; j < TM; ++j) {
-                const uint32_t i = g * TM + j;
+                const uint32_t i = PAIR ? g * 2 + cta_rank : g * TM + j;
                 if (i >= a.tile_count) break;  // shadow tile of an odd tail: nothing to report
                 const uint32_t t = a.tile_first + i * a.tile_stride;
                 uint32_t row0, valid;
@@ -312,7 +396,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 const uint32_t slot = a.segs[segi].slot_base + row0 + row;
                 const uint32_t acc_col = buf * (TM * NQ) + j * NQ;
 #pragma unroll 1
-                for (int c0 = 0; c0 < NQ; c0 += Cfg::kChunk) {
+                for (int c0 = col_first; c0 < col_first + kColsPerWarp; c0 += Cfg::kChunk) {
                     uint32_t r[Cfg::kChunk];
                     tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + c0, r);
                     tmem_ld_wait();
@@ -381,43 +465,52 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                     }
                 }
                 if (a.mode == 1) {
-                    named_bar_sync(2, 128);
-                    for (int c = threadIdx.x - 64; c < NQ; c += 128) {
+                    named_bar_sync(2, kEpiThreads);
+                    for (int c = threadIdx.x - 64; c < NQ; c += kEpiThreads) {
                         a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
                         tmax_s[c] = 0u;
                     }
-                    named_bar_sync(2, 128);
+                    named_bar_sync(2, kEpiThreads);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_remote(leader_addr(&tempty[buf])); else mbar_arrive(&tempty[buf]);
+            }
             if (a.mode == 0) {
                 // the accumulator is released; flush the staged survivors when the stage is half full or
                 // this was the CTA's last group (all four epilogue warps take the same branch)
-                named_bar_sync(2, 128);
-                const int staged = *reinterpret_cast<volatile int *>(stage_n);
-                if (staged >= kAppendStage / 2 || g + gridDim.x >= ngroups) {
+                named_bar_sync(2, kEpiThreads);
+                const int staged = *stage_n;  // ordered by the named barrier above
+                if (staged >= kAppendStage / 2 || g + nworkers >= ngroups) {
                     const int n = staged < kAppendStage ? staged : kAppendStage;
-                    for (int e = (int)threadIdx.x - 64; e < n; e += 128) {
+                    for (int e = (int)threadIdx.x - 64; e < n; e += kEpiThreads) {
                         const int qi = stage_q[e];
                         const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
                         if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = stage_key[e];
                     }
-                    named_bar_sync(2, 128);
+                    named_bar_sync(2, kEpiThreads);
                     if (threadIdx.x == 64) *stage_n = 0;
-                    named_bar_sync(2, 128);
+                    named_bar_sync(2, kEpiThreads);
                 }
             }
         }
         if (a.mode == 0 && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)Cfg::kTmemCols)
-                     : "memory");
+    if (PAIR) {
+        cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+        if (warp == 1)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)Cfg::kTmemCols)
+                         : "memory");
+    } else {
+        __syncthreads();
+        if (warp == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)Cfg::kTmemCols)
+                         : "memory");
     }
 }
 
@@ -820,13 +913,42 @@ cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Ge
                         cudaStream_t stream)
 {
     using Cfg = GemmCfg<NQ, TM>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmem);
     if (e != cudaSuccess) return e;
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
     const int grid = sms < (int)ngroups ? sms : (int)ngroups;
     if (grid < 1) return cudaSuccess;
-    return launch_chain(gemm_kernel<NQ, TM, EB>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, a);
+    return launch_chain(gemm_kernel<NQ, TM, EB, false>, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem, stream, tmA, tmB, a);
+}
+
+// 2-CTA variant: clusters of two CTAs (one TPC), each pair takes 256 consecutive feature rows per step
+template <int NQ>
+cudaError_t launch_gemm_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms,
+                             cudaStream_t stream)
+{
+    using Cfg = GemmCfg<NQ, 1, true>;
+    auto kern = gemm_kernel<NQ, 1, 2, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    const uint32_t ngroups = (a.tile_count + 1) / 2;
+    int pairs = sms / 2 < (int)ngroups ? sms / 2 : (int)ngroups;
+    if (pairs < 1) return cudaSuccess;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(gemm_threads(NQ));
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a);
 }
 
 }  // namespace
@@ -842,9 +964,16 @@ int gemm_pad_queries(int q)
 
 template <int EB>
 static cudaError_t gemm_dispatch(const GemmLaunch &g, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a,
-                                 cudaStream_t stream)
+                                 bool pair, cudaStream_t stream)
 {
     static const int tm_big = getenv("GF_GEMM_TM2") ? 2 : 1;  // tuning knob (TM = 2 measured slower: 0.58 vs 0.40 ms at NQ = 256)
+    if constexpr (EB == 2) {
+        if (pair) {
+            if (g.nq == 256) return launch_gemm_pair<256>(tmA, tmB, a, g.sms, stream);
+            if (g.nq == 128) return launch_gemm_pair<128>(tmA, tmB, a, g.sms, stream);
+            return cudaErrorInvalidValue;
+        }
+    }
     switch (g.nq) {
         case 16: return launch_gemm<16, 1, EB>(tmA, tmB, a, g.sms, stream);
         case 32: return launch_gemm<32, 1, EB>(tmA, tmB, a, g.sms, stream);
@@ -868,8 +997,15 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, bf16 ? g.shadow_base : (const void *)g.slab_base, g.slab_rows, g.dims, kTileRows, eb);
     if (e != cudaSuccess) return e;
+    // cta_group::2 variant (each SM of a pair stages half of the query operand; leader issues M = 256 MMAs):
+    // built and parity-tested, but measured SLOWER than one CTA per SM on this workload (256 queries:
+    // 0.246 vs 0.210 ms per 1 M rows; 128 queries: 0.202 vs 0.165 ms) -- ncu shows the producer blocked on a
+    // full ring and the epilogue idle, i.e. the pair's MMA stream itself runs at about half rate -- so it is off
+    // unless GF_GEMM_PAIR_MIN (smallest padded batch that uses it: 128 or 256) is set.
+    static const int pair_min = getenv("GF_GEMM_PAIR_MIN") ? atoi(getenv("GF_GEMM_PAIR_MIN")) : 1 << 30;
+    const bool pair = bf16 && g.nq >= pair_min && (g.nq == 256 || g.nq == 128) && g.tile_count >= 2 && g.sms >= 2;
     e = make_map(&tmB, bf16 ? g.d_queries_bf16 : (const void *)g.d_queries_padded, (uint64_t)g.nq, g.dims,
-                 (uint32_t)g.nq, eb);
+                 (uint32_t)(pair ? g.nq / 2 : g.nq), eb);
     if (e != cudaSuccess) return e;
     GemmArgs a{};
     a.segs = g.d_segs;
@@ -890,7 +1026,7 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.dump = g.d_dump;
     a.dump_ld = g.dump_ld;
     if (g.tile_count < 1) return cudaSuccess;
-    return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, stream) : gemm_dispatch<4>(g, tmA, tmB, a, stream);
+    return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, pair, stream) : gemm_dispatch<4>(g, tmA, tmB, a, false, stream);
 }
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
