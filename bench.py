@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_config(args, world):
@@ -403,7 +403,7 @@ def run_ours(args, rank, world, local_rank):
             cb, _ = cpu_scan_qps(min(args.cpu_sample_rows, args.rows_per_gpu), Q, K, args.cpu_seconds,
                                  args.rows_per_gpu)
             line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    emit(line)
     if cache is not None:
         cache.Close()
     ctx.Close()
@@ -411,7 +411,25 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL's version banner, torchrun notices) write to fd 1: keep stdout for the JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -193,3 +193,90 @@ def test_shadow_cache_with_dims_not_multiple_of_64(gpu_ctx):
     assert gpu_ctx.Stats()["tensor_passes"] == 1
     _assert_same(st.SearchArray(-1.0, 10, q[:1]), ost.search(-1.0, 10, q[:1]))     # q = 1: fused scan
     cache.Close()
+
+
+def test_coalesced_callers_fast_handoff_and_tombstone_retry(gpu_ctx):
+    """Concurrent gf_set_search callers folded into one tensor-path pass: the leader publishes raw keys and
+    every caller resolves its own ids under the leader's read lock (fast hand-off); a caller whose winners
+    contain a tombstone re-runs alone through the per-block path (block.go:236-243).  Every caller must get
+    exactly what an uncoalesced Search (= the oracle) returns, with its own threshold."""
+    import threading
+    dims, n, nthreads, rounds = 512, 70000, 6, 12
+    cache, st, ost = _pair(gpu_ctx, "co", dims, 8, 16384, 6)
+    rows = ol.synth_rows(1234, 0, n, dims).copy()
+    rows[:, 0] = np.abs(rows[:, 0]) + np.float32(0.05)                 # every row has a positive first component
+    ids = ["k%06d" % i for i in range(n)]
+    st.AddArray(rows, ids)
+    ost.add(rows, ids)
+    kill = [ids[i] for i in range(7, n, 1999)]
+    assert sorted(st.Delete(*kill)) == sorted(ost.delete(kill))
+    queries = ol.synth_rows(1235, 0, nthreads, dims).copy()
+    queries[0, :] = 0
+    queries[0, 0] = -1.0                                               # all live scores negative: tombstones (0.0) win
+    thresholds = [-10.0, 0.0, 0.12, -1.0, 0.15, -0.3]
+    limits = [10, 10, 10, 10, 10, 10]
+    want = [ost.search(thresholds[t], limits[t], queries[t:t + 1]) for t in range(nthreads)]
+    st.SetCoalescing(200)
+    gpu_ctx.ResetStats()
+    errors = []
+
+    def worker(t):
+        try:
+            for _ in range(rounds):
+                got = st.SearchArray(thresholds[t], limits[t], queries[t:t + 1])
+                _assert_same(got, want[t], "thread %d" % t)
+        except Exception as exc:  # noqa: BLE001
+            errors.append((t, repr(exc)))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+    stats = gpu_ctx.Stats()
+    assert stats["coalesced_batches"] > 0 and stats["tensor_passes"] > 0, stats
+    assert stats["quirk_fallbacks"] >= rounds, stats                   # thread 0 took the per-block path every time
+    assert want[0][0] and all(s < 0 for s, _ in want[0][0])            # and still got the live (negative) rows
+    st.SetCoalescing(0)
+    cache.Close()
+
+
+def test_device_search_flags(gpu_ctx):
+    """gf_set_search_device_ex: more uncertifiable queries than one device-side fix-up pass takes (8) leave
+    flags behind; every unflagged query is exact, flagged ones are exact after a path=1 re-run."""
+    import torch
+    from gofeature_b200 import api
+    dims, n, q, limit = 512, 70000, 24, 10
+    cache, st, ost = _pair(gpu_ctx, "flags", dims, q, 16384, 6)
+    rng = np.random.default_rng(29)
+    rows = ol.synth_rows(828, 0, n, dims)
+    centre = rows[1].copy()
+    rows[10000:16000] = centre[None, :] + rng.normal(0, 2e-6, (6000, dims)).astype(np.float32)
+    ids = ["c%06d" % i for i in range(n)]
+    st.AddArray(rows, ids)
+    ost.add(rows, ids)
+    queries = ol.synth_rows(829, 0, q, dims)
+    for i in range(16):                                                # 16 queries cannot be certified
+        queries[i] = centre / np.linalg.norm(centre) + rng.normal(0, 1e-3, dims).astype(np.float32)
+    dq = torch.from_numpy(queries).cuda()
+    keys = torch.zeros((q, limit), dtype=torch.int64, device="cuda")
+    flags = torch.zeros((q,), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    L = api.lib()
+    api._check(L.gf_set_search_device_ex(st._h, limit, q, dq.data_ptr(), keys.data_ptr(), flags.data_ptr(), 0, stream))
+    torch.cuda.synchronize()
+    hf = flags.cpu().numpy()
+    assert 0 < int(hf.sum()) <= 16 - 8, hf                             # 8 were repaired on the device
+    want = ost.search(-10.0, limit, queries)
+    hk = keys.cpu().numpy().view(np.uint64)
+    for i in range(q):
+        if hf[i]:
+            continue
+        assert [float(api.key_score(k)) for k in hk[i]] == [float(np.float32(s_)) for s_, _ in want[i]], i
+    api._check(L.gf_set_search_device_ex(st._h, limit, q, dq.data_ptr(), keys.data_ptr(), flags.data_ptr(), 1, stream))
+    torch.cuda.synchronize()
+    assert int(flags.cpu().numpy().sum()) == 0
+    res = st.ResolveKeys(-10.0, limit, keys.cpu().numpy().view(np.uint64))
+    _assert_same(res, want, "path 1 re-run")
+    cache.Close()
