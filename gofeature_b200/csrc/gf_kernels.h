@@ -146,6 +146,10 @@ cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, un
 cudaError_t shadow_rows_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, unsigned int *d_small,
                                cudaStream_t stream);
 
+// src / slots / elem_off may live in pinned host memory (the upload ring): the kernels read them over PCIe
+cudaError_t scatter_rows_launch(const float *src, const int *slots, int n, int dims, float *d_base, cudaStream_t stream);
+cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, const unsigned long long *elem_off, int n, int dims,
+                             cudaStream_t stream);
 cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int dims, float *d_dst,
                                cudaStream_t stream);
 

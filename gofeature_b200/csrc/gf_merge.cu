@@ -261,6 +261,66 @@ cudaError_t shadow_rows_launch(const float *d_rows, int64_t rows, int dims, void
     return cudaGetLastError();
 }
 
+// Mutation helpers that take their (small) argument lists straight from the pinned upload ring: a Delete of
+// 10 000 ids or an Add that refills 10 000 scattered tombstones used to be 10 000-20 000 tiny memset / memcpy
+// calls; each is now one kernel per ring chunk.
+namespace {
+// row i of `src` (pinned host memory or device) -> row slots[i] of the block at `base`
+__global__ void scatter_rows_kernel(const float *__restrict__ src, const int *__restrict__ slots, int n, int dims,
+                                    float *__restrict__ base)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < n; j += nwarps) {
+        const float *s = src + (size_t)j * dims;
+        float *d = base + (size_t)slots[j] * dims;
+        if ((dims & 3) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(s);
+            float4 *d4 = reinterpret_cast<float4 *>(d);
+            for (int e = lane; e < dims / 4; e += 32) d4[e] = s4[e];
+        } else {
+            for (int e = lane; e < dims; e += 32) d[e] = s[e];
+        }
+    }
+}
+// zero the float32 row (and its bf16 shadow row) at element offset off[i] of the slab(s)
+__global__ void zero_rows_kernel(float *__restrict__ slab, unsigned short *__restrict__ shadow,
+                                 const unsigned long long *__restrict__ off, int n, int dims)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < n; j += nwarps) {
+        float *d = slab + off[j];
+        for (int e = lane; e < dims; e += 32) d[e] = 0.f;
+        if (shadow != nullptr) {
+            unsigned short *h = shadow + off[j];
+            for (int e = lane; e < dims; e += 32) h[e] = 0;
+        }
+    }
+}
+}  // namespace
+
+cudaError_t scatter_rows_launch(const float *src, const int *slots, int n, int dims, float *d_base, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    int blocks = (n + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scatter_rows_kernel<<<blocks, 256, 0, stream>>>(src, slots, n, dims, d_base);
+    return cudaGetLastError();
+}
+
+cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, const unsigned long long *elem_off, int n, int dims,
+                             cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    int blocks = (n + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    zero_rows_kernel<<<blocks, 256, 0, stream>>>(d_slab, (unsigned short *)d_shadow, elem_off, n, dims);
+    return cudaGetLastError();
+}
+
 // dst row j = src row idx[j]: packs the live rows of a block (tombstone compaction)
 namespace {
 __global__ void gather_rows_kernel(const float *__restrict__ src, const int *__restrict__ idx, int n, int dims,

@@ -252,21 +252,56 @@ int Context::upload_scatter(uint8_t *base, const int *slots, size_t n, size_t ro
 {
     if (n == 0) return GF_OK;
     std::lock_guard<std::mutex> g(stage_mu);
-    const size_t per = std::max<size_t>(1, stage_bytes / rowb);
+    // more than a few rows of whole 32-bit words: the rows AND their slot list go into the pinned ring and one
+    // kernel per chunk scatters them (it reads the ring over PCIe); otherwise one small copy per row
+    const bool by_kernel = n > 4 && rowb % 4 == 0 && ((uintptr_t)base % 4) == 0;
+    const size_t per = std::max<size_t>(1, (stage_bytes - (by_kernel ? 16 : 0)) / (rowb + (by_kernel ? 4 : 0)));
     int k = 0;
     for (size_t r0 = 0; r0 < n; r0 += per, ++k) {
         const size_t cnt = std::min(per, n - r0);
         const int i = k & 1;
         GF_CUDA(cudaEventSynchronize(stage_ev[i]), GF_ERR_WRITE_CUDA_BUFFER);
         memcpy(stage[i], src + r0 * rowb, cnt * rowb);
-        for (size_t j = 0; j < cnt; ++j)
-            GF_CUDA(cudaMemcpyAsync(base + (size_t)slots[r0 + j] * rowb, stage[i] + j * rowb, rowb,
-                                    cudaMemcpyHostToDevice, mut_stream),
+        if (by_kernel) {
+            int *st_slots = reinterpret_cast<int *>(stage[i] + (cnt * rowb + 15) / 16 * 16);
+            memcpy(st_slots, slots + r0, cnt * sizeof(int));
+            GF_CUDA(scatter_rows_launch(reinterpret_cast<const float *>(stage[i]), st_slots, (int)cnt, (int)(rowb / 4),
+                                        reinterpret_cast<float *>(base), mut_stream),
                     GF_ERR_WRITE_CUDA_BUFFER);
+            stats.other_launches++;
+        } else {
+            for (size_t j = 0; j < cnt; ++j)
+                GF_CUDA(cudaMemcpyAsync(base + (size_t)slots[r0 + j] * rowb, stage[i] + j * rowb, rowb,
+                                        cudaMemcpyHostToDevice, mut_stream),
+                        GF_ERR_WRITE_CUDA_BUFFER);
+        }
         GF_CUDA(cudaEventRecord(stage_ev[i], mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
     }
     GF_CUDA(cudaStreamSynchronize(mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
     stats.h2d_bytes += n * rowb;
+    return GF_OK;
+}
+
+// zero whole float32 rows (and their bf16 shadow rows) given by element offsets into the slab(s): the list
+// travels through the pinned ring, one kernel per chunk
+int Context::zero_rows(float *d_slab, void *d_shadow, const std::vector<unsigned long long> &elem_off, int dims)
+{
+    if (elem_off.empty()) return GF_OK;
+    std::lock_guard<std::mutex> g(stage_mu);
+    const size_t per = stage_bytes / sizeof(unsigned long long);
+    int k = 0;
+    for (size_t r0 = 0; r0 < elem_off.size(); r0 += per, ++k) {
+        const size_t cnt = std::min(per, elem_off.size() - r0);
+        const int i = k & 1;
+        GF_CUDA(cudaEventSynchronize(stage_ev[i]), GF_ERR_CLEAR_CUDA_BUFFER);
+        memcpy(stage[i], elem_off.data() + r0, cnt * sizeof(unsigned long long));
+        GF_CUDA(zero_rows_launch(d_slab, d_shadow, reinterpret_cast<const unsigned long long *>(stage[i]), (int)cnt, dims,
+                                 mut_stream),
+                GF_ERR_CLEAR_CUDA_BUFFER);
+        stats.other_launches++;
+        GF_CUDA(cudaEventRecord(stage_ev[i], mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    }
+    GF_CUDA(cudaStreamSynchronize(mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     return GF_OK;
 }
 
@@ -316,6 +351,10 @@ std::string Block::id_at(int row) const
 {
     if (row < 0 || row >= (int)live.size() || !live[row]) return std::string();
     if (implicit_ids) {
+        if (!over.empty()) {
+            auto it = over.find(row);
+            if (it != over.end()) return it->second;
+        }
         char buf[32];
         snprintf(buf, sizeof buf, "%011lld", (long long)(id_first + row));
         return id_prefix + buf;
@@ -350,15 +389,18 @@ void Block::index_del(const std::string &id, int row)
 int Block::find_last(const std::string &id) const
 {
     if (implicit_ids) {
-        if (id.size() != id_prefix.size() + 11 || id.compare(0, id_prefix.size(), id_prefix) != 0) return -1;
+        int best = -1;
+        for (const auto &kv : over)  // overridden rows carry arbitrary ids (last match wins, block.go:140-144)
+            if (kv.first < next_index && live[kv.first] && kv.second == id) best = std::max(best, kv.first);
+        if (id.size() != id_prefix.size() + 11 || id.compare(0, id_prefix.size(), id_prefix) != 0) return best;
         long long ord = 0;
         for (size_t i = id_prefix.size(); i < id.size(); ++i) {
-            if (id[i] < '0' || id[i] > '9') return -1;
+            if (id[i] < '0' || id[i] > '9') return best;
             ord = ord * 10 + (id[i] - '0');
         }
         long long row = ord - id_first;
-        if (row < 0 || row >= next_index || !live[row]) return -1;
-        return (int)row;
+        if (row < 0 || row >= next_index || !live[row] || over.count((int)row)) return best;
+        return std::max(best, (int)row);
     }
     if (!use_index) {  // no per-block index: the reference's own linear scan, last match wins (block.go:140-144)
         for (int r = next_index - 1; r >= 0; --r)
@@ -377,6 +419,7 @@ void Block::materialize_ids()
     for (int r = 0; r < next_index; ++r)
         if (live[r]) v[r] = id_at(r);
     implicit_ids = false;
+    over.clear();
     ids.swap(v);
     id_index.clear();
     for (int r = 0; r < next_index; ++r)
@@ -397,6 +440,7 @@ int Block::acquire(const std::string &owner_, int dims_, int precision_, int bat
     live.assign((size_t)capacity(), 0);
     live_count = 0;
     implicit_ids = false;
+    over.clear();
     use_index = true;
     id_index.clear();
     empty.clear();
@@ -423,6 +467,7 @@ int Block::release()
     next_index = 0;
     live_count = 0;
     implicit_ids = false;
+    over.clear();
     set = nullptr;
     return GF_OK;
 }
@@ -437,7 +482,18 @@ int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::strin
     Context *ctx = cache->ctx;
     int rc = ctx->bind();
     if (rc) return rc;
-    materialize_ids();
+    // an implicit-id block keeps its generated ids and records the arbitrary ones row by row, unless that
+    // overlay would cover a quarter of the block
+    if (implicit_ids && over.size() + (size_t)n > (size_t)capacity() / 4) materialize_ids();
+    const bool overlay = implicit_ids;
+    auto set_id = [&](int slot, const std::string &id) {
+        if (overlay) {
+            over[slot] = id;
+        } else {
+            ids[slot] = id;
+            index_add(id, slot);
+        }
+    };
     const size_t rowb = (size_t)dims * precision;
     const size_t nempty = empty.size();
     const size_t refill = std::min(nempty, (size_t)n);
@@ -447,10 +503,9 @@ int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::strin
     }
     for (size_t i = 0; i < refill; ++i) {
         int slot = empty[i];
-        ids[slot] = ids_[i];
+        set_id(slot, ids_[i]);
         live[slot] = 1;
         ++live_count;
-        index_add(ids_[i], slot);
     }
     if ((size_t)n > nempty) {
         size_t tail = (size_t)n - nempty;
@@ -458,9 +513,8 @@ int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::strin
         if (rc) return rc;
         for (size_t i = 0; i < tail; ++i) {
             int slot = next_index + (int)i;
-            ids[slot] = ids_[nempty + i];
+            set_id(slot, ids_[nempty + i]);
             live[slot] = 1;
-            index_add(ids_[nempty + i], slot);
         }
         live_count += (int)tail;
         next_index += (int)tail;
@@ -537,6 +591,8 @@ int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &fo
         if (!implicit_ids) {
             index_del(ids_[i], row);
             ids[row].clear();
+        } else if (!over.empty()) {
+            over.erase(row);
         }
         live[row] = 0;
         --live_count;
@@ -548,7 +604,7 @@ int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &fo
     return GF_OK;
 }
 
-int Block::remove_rows(const std::vector<int> &rows)
+int Block::remove_rows(const std::vector<int> &rows, std::vector<unsigned long long> *zero_later)
 {
     if (rows.empty()) return GF_OK;
     std::lock_guard<std::mutex> g(mu);
@@ -556,13 +612,20 @@ int Block::remove_rows(const std::vector<int> &rows)
     const size_t rowb = (size_t)dims * precision;
     for (int row : rows) {
         if (row < 0 || row >= next_index || !live[row]) continue;
-        GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
-        if (shadow && precision == 4)
-            GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * (rowb / 2), 0, rowb / 2, ctx->mut_stream),
-                    GF_ERR_CLEAR_CUDA_BUFFER);
+        if (zero_later) {  // the caller zeroes all rows of the Delete with one kernel (element offset in the slab)
+            zero_later->push_back((unsigned long long)((dev - (uint8_t *)cache->slab->ptr) / 4) +
+                                  (unsigned long long)row * dims);
+        } else {
+            GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+            if (shadow && precision == 4)
+                GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * (rowb / 2), 0, rowb / 2, ctx->mut_stream),
+                        GF_ERR_CLEAR_CUDA_BUFFER);
+        }
         if (!implicit_ids) {
             index_del(ids[row], row);
             ids[row].clear();
+        } else if (!over.empty()) {
+            over.erase(row);
         }
         live[row] = 0;
         --live_count;
@@ -593,6 +656,7 @@ bool Set::find_implicit(const std::string &id, int *pos, int *row) const
     const Block *b = blocks[r.pos];
     const int rr = (int)(ord - r.first);
     if (!b->implicit_ids || rr >= b->next_index || !b->live[rr]) return false;
+    if (!b->over.empty() && b->over.count(rr)) return false;  // that row now carries an arbitrary id
     *pos = r.pos;
     *row = rr;
     return true;
@@ -650,11 +714,15 @@ void Set::materialize_block(int pos)
         b->rebuild_index();
         return;
     }
-    for (int r = 0; r < b->next_index; ++r)
-        if (b->live[r] && !loc.emplace(b->ids[r], ((uint64_t)pos << 32) | (uint32_t)r).second) {
+    for (int r = 0; r < b->next_index; ++r) {
+        if (!b->live[r]) continue;
+        const uint64_t where = ((uint64_t)pos << 32) | (uint32_t)r;
+        auto ins = loc.emplace(b->ids[r], where);
+        if (!ins.second && ins.first->second != where) {  // (an overridden row is in the locator already)
             enter_dup_mode();
             return;
         }
+    }
 }
 
 bool Set::slot_to_block(uint32_t slot, int *block_pos, int *row) const
@@ -673,7 +741,9 @@ static std::atomic<uint64_t> g_set_version{0};
 
 int Set::rebuild_segments()
 {
-    version = ++g_set_version;  // process-wide unique: a cached graph can never match a different table
+    const std::vector<Segment> old_segs = h_segs;
+    const int old_tile_rows = tile_rows;
+    const bool old_shadow_ok = shadow_ok, old_tensor_ok = tensor_ok;
     h_segs.clear();
     seg_block.clear();
     int tr = scan_tile_rows(dims);
@@ -701,6 +771,15 @@ int Set::rebuild_segments()
         seg_block.push_back((int)p);
     }
     total_tiles = tiles;
+    // An Add that only refilled tombstones leaves the table as it was: the device copy, the version and every
+    // recorded graph stay valid (under churn a re-capture per Add cost more than the Add)
+    if (d_segs != nullptr && old_tile_rows == tile_rows && old_segs.size() == h_segs.size() && !h_segs.empty() &&
+        memcmp(old_segs.data(), h_segs.data(), h_segs.size() * sizeof(Segment)) == 0) {
+        shadow_ok = old_shadow_ok;
+        tensor_ok = old_tensor_ok;
+        return GF_OK;
+    }
+    version = ++g_set_version;  // process-wide unique: a cached graph can never match a different table
     if (h_segs.empty()) return GF_OK;
     int rc = ctx->bind();
     if (rc) return rc;
@@ -810,7 +889,9 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
         Block *b = blocks[bp];
         int64_t length = std::min<int64_t>(b->margin(), remain);
         if (length > 0) {
-            materialize_block((int)bp);
+            // (an implicit-id block records arbitrary ids in its overlay; when Block::insert decides to turn it
+            // into explicit strings the locator has to learn its generated ids first)
+            if (b->implicit_ids && b->over.size() + (size_t)length > (size_t)b->capacity() / 4) materialize_block((int)bp);
             std::vector<std::string> sub(ids_.begin() + offset, ids_.begin() + offset + length);
             const std::vector<int> refilled(b->empty.begin(),
                                             b->empty.begin() + std::min<size_t>(b->empty.size(), (size_t)length));
@@ -882,6 +963,11 @@ int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int norm
         if (length > 0) {
             if (b->implicit_ids && b->next_index == 0) b->id_first = first_ordinal + done;
             const int tail0 = b->next_index;
+            // generated ids that do not continue this block's own range end its implicit life: the locator has
+            // to learn the ids it holds before Block::insert_synthetic turns them into strings
+            if (b->implicit_ids && b->next_index > 0 &&
+                !(b->id_prefix == prefix && b->id_first + b->next_index == first_ordinal + done))
+                materialize_block((int)bp);
             const bool was_implicit = b->implicit_ids;
             rc = b->insert_synthetic(length, seed, first_ordinal + done, normalize, prefix);
             if (rc) return rc;
@@ -942,13 +1028,23 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
         if (!find(ids_[i], &pos, &row)) continue;
         per_block[pos].push_back(row);
         found[i] = 1;
-        if (!has_dups && !blocks[pos]->implicit_ids) loc.erase(ids_[i]);
+        if (!has_dups && (!blocks[pos]->implicit_ids || blocks[pos]->over.count(row))) loc.erase(ids_[i]);
     }
+    size_t nrows = 0;
+    for (auto &kv : per_block) nrows += kv.second.size();
+    const bool batched = nrows > 4 && precision == 4;  // one zeroing kernel instead of two memsets per row
+    std::vector<unsigned long long> zero_off;
+    if (batched) zero_off.reserve(nrows);
     for (auto &kv : per_block) {
-        rc = blocks[kv.first]->remove_rows(kv.second);
+        rc = blocks[kv.first]->remove_rows(kv.second, batched ? &zero_off : nullptr);
         if (rc) return rc;
     }
-    if (!per_block.empty()) GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    if (batched) {
+        rc = ctx->zero_rows((float *)cache->slab->ptr, cache->shadow ? cache->shadow->ptr : nullptr, zero_off, dims);
+        if (rc) return rc;
+    } else if (!per_block.empty()) {
+        GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+    }
     return GF_OK;  // NextIndex never shrinks (block.go:159-160): the segment table is unchanged
 }
 

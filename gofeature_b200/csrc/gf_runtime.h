@@ -128,6 +128,7 @@ struct gf_context {
     int upload(void *dst, const void *src, size_t bytes);
     // n rows of `rowb` bytes, row i to base + slots[i]*rowb: staged through the ring, one sync at the end
     int upload_scatter(uint8_t *base, const int *slots, size_t n, size_t rowb, const uint8_t *src);
+    int zero_rows(float *d_slab, void *d_shadow, const std::vector<unsigned long long> &elem_off, int dims);
     ~gf_context();
 };
 
@@ -179,10 +180,13 @@ struct gf_block {
     std::vector<std::string> ids;  // explicit IDs[]; unused while implicit
     std::vector<uint8_t> live;     // live[j] = (IDs[j] != "")
     int live_count = 0;
-    // implicit ids "<prefix>%011d" of id_first + slot (synthetic fill); dropped on first refill
+    // implicit ids "<prefix>%011d" of id_first + slot (synthetic fill).  Rows that later take an arbitrary id
+    // (a tombstone refilled by Add, an explicit tail append) are kept in `over`; the block is only turned into
+    // explicit strings (materialize_ids) when a quarter of it has been overridden or it is compacted
     bool implicit_ids = false;
     std::string id_prefix;
     int64_t id_first = 0;
+    std::unordered_map<int, std::string> over;  // row -> explicit id, implicit blocks only
     std::unordered_map<std::string, std::vector<int>> id_index;  // id -> rows holding it (when use_index)
     bool use_index = true;  // false while a set keeps the set-wide locator for this block
     gf::Set *set = nullptr;
@@ -199,7 +203,9 @@ struct gf_block {
     int insert(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
     int insert_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
-    int remove_rows(const std::vector<int> &rows);  // zero + tombstone the rows (no stream sync)
+    // tombstone the rows; zero them on the device (no stream sync) or, with zero_later, only report their element
+    // offsets in the slab so that the caller zeroes the whole Delete with one kernel
+    int remove_rows(const std::vector<int> &rows, std::vector<unsigned long long> *zero_later = nullptr);
     void rebuild_index();
     void index_add(const std::string &id, int row);
     void index_del(const std::string &id, int row);
