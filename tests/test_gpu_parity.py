@@ -650,3 +650,58 @@ def test_random_operation_sequences(gpu_ctx, dims, block_rows, seed):
     vals, out_ids = st.Export()
     assert out_ids == [i for b in ost.blocks for i in b.ids[:b.next_index] if i != ""]
     cache.Close()
+
+
+def test_implicit_id_blocks_take_arbitrary_ids(gpu_ctx):
+    """Synthetic (implicit-id) blocks whose tombstones are refilled by Add keep their generated ids and record
+    the arbitrary ones in an overlay: Search / Delete / Update / Read / Export / Compact must behave exactly
+    like the oracle's model, which only knows explicit ids."""
+    from gofeature_b200 import api
+    dims, block_rows, n = 64, 400, 2000
+    cache, st, ost = _pair(gpu_ctx, "overlay", dims, 4, block_rows, 12)
+    st.AddSynthetic(n, 91)
+    syn = ol.synth_rows(91, 0, n, dims)
+    ost.add(syn, ["f%011d" % i for i in range(n)])
+    q = ol.synth_rows(92, 0, 4, dims)
+
+    def same(what, limit=20, thr=-1.0):
+        _assert_same(st.SearchArray(thr, limit, q), ost.search(thr, limit, q), what)
+        assert st.LiveRows() == sum(sum(1 for i in b.ids[:b.next_index] if i != "") for b in ost.blocks)
+
+    kill = ["f%011d" % i for i in (3, 4, 5, 401, 799, 800, 1999, 1200)]
+    assert sorted(st.Delete(*kill)) == sorted(ost.delete(kill))
+    extra = ol.synth_rows(93, 0, 30, dims)
+    eids = ["x%02d" % i for i in range(30)]
+    st.AddArray(extra, eids)                       # 8 refills spread over implicit blocks + a tail append
+    ost.add(extra, eids)
+    same("refill into implicit blocks")
+    # the generated name of a refilled slot is gone; the arbitrary id that replaced it is there
+    assert (st.Delete("f%011d" % 3, "x00", "f%011d" % 10) or []) == ost.delete(["f%011d" % 3, "x00", "f%011d" % 10])
+    same("delete overlay + implicit ids")
+    got = st.Read("x01", "f%011d" % 11, "f%011d" % 4)
+    assert [f.ID for f in got] == ["x01", "f%011d" % 11]
+    new = ol.synth_rows(94, 0, 1, dims)[0]
+    assert st.Update(api.Feature(new.tobytes(), "x02")) == ["x02"]
+    for b in ost.blocks:
+        if "x02" in b.ids:
+            b.rows[b.ids.index("x02")] = new
+    same("update of an overlay row")
+    vals, out_ids = st.Export()
+    assert out_ids == [i for b in ost.blocks for i in b.ids[:b.next_index] if i != ""]
+    # enough arbitrary ids into ONE implicit block to make it explicit (overlay > capacity / 4)
+    victims = ["f%011d" % i for i in range(400, 400 + 150)]
+    assert sorted(st.Delete(*victims)) == sorted(ost.delete(victims))
+    more = ol.synth_rows(95, 0, 150, dims)
+    mids = ["y%03d" % i for i in range(150)]
+    st.AddArray(more, mids)
+    ost.add(more, mids)
+    same("block turned explicit")
+    assert sorted(st.Delete("y000", "f%011d" % 560, "x05")) == sorted(ost.delete(["y000", "f%011d" % 560, "x05"]))
+    assert st.Compact() == ost.compact()
+    same("after compact", limit=50)
+    st.AddSynthetic(100, 96, first_ordinal=10 ** 6)
+    ost.add(ol.synth_rows(96, 10 ** 6, 100, dims), ["f%011d" % (10 ** 6 + i) for i in range(100)])
+    same("synthetic append after all that")
+    vals, out_ids = st.Export()
+    assert out_ids == [i for b in ost.blocks for i in b.ids[:b.next_index] if i != ""]
+    cache.Close()
