@@ -1279,7 +1279,8 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     if (!tensor || q > kGemmMaxQ || no_graphs || ws->graphs_broken || ctx->profiling.load())
         return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     Stats &st = ctx->stats;
-    const int mode = use_shadow(path) ? 1 : 0;
+    const bool device_fixup = d_flags == nullptr;  // nobody to report an uncertified query to: repair it here
+    const int mode = (use_shadow(path) ? 1 : 0) | (device_fixup ? 2 : 0);
     // bake_io (Search's own staging buffers, stable per workspace): the query preparation and the copy of
     // keys + flags are nodes of the graph too -- ONE stream operation per call
     bake_io = bake_io && d_flags != nullptr && q_stride == dims && l_stride == 1 && stream == ws->stream;
@@ -1298,7 +1299,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
                 GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
                 return GF_OK;
             }
-            int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path);
+            int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path, device_fixup);
             if (rc) return rc;
             GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
             // d_out / d_flags may be device memory or pinned host memory
@@ -1327,8 +1328,9 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         return GF_OK;
     }
     int crc = GF_OK;
-    if (bake_io) crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path);
-    if (crc == GF_OK) crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path);
+    if (bake_io) crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path, device_fixup);
+    if (crc == GF_OK)
+        crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path, device_fixup);
     if (crc == GF_OK && bake_io) {
         const bool contig = (uint8_t *)d_flags == (uint8_t *)d_out + res_b &&
                             (uint8_t *)ws->t_flags == (uint8_t *)ws->t_res + res_b;
@@ -1385,7 +1387,7 @@ int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, 
                     unsigned long long *d_out, int path, unsigned int *d_flags)
 {
     if (tensor_eligible(q, K, per_segment, d_upper, path))
-        return topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, d_out, d_flags, 0, path);
+        return topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, d_out, d_flags, 0, path, d_flags == nullptr);
     if (d_flags) GF_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)q * sizeof(unsigned int), stream), GF_ERR_CUDA);
     return topk_scan(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out);
 }
@@ -1396,7 +1398,8 @@ int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, 
 //   -> sort, emit K, certify.  Uncertified queries are re-run by one fix-up scan pass on the device
 //   (up to kFixupMaxQ per call); what is still flagged is reported through d_flags.
 int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
-                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase, int path)
+                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase, int path,
+                     bool device_fixup)
 {
     const int nseg = (int)h_segs.size();
     const bool bf16 = use_shadow(path);
@@ -1434,7 +1437,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_cand = carve((size_t)nq_max * cap * 8);
     const size_t o_sel = carve((size_t)nq_max * kp * 8);
     // small batches re-score EVERY collected candidate (~`target` rows per query) and skip the selection
-    auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)64 << 20); };
+    auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)32 << 20); };
     const size_t o_exact = carve((size_t)nq_max * (rescore_all(std::min(q, kGemmMaxQ)) ? (size_t)cap : (size_t)kp) * 8);
     const size_t o_map = carve((size_t)kFixupMaxQ * 4);
     const size_t o_count = carve(4);
@@ -1497,7 +1500,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         g.nq = nq;
         g.q = qp;
         FixupPlan fix{};  // the last pass's finalize also lists the flagged queries of the whole call
-        if (p0 + kGemmMaxQ >= q) fix = FixupPlan{d_fl, q, fixq, d_map, d_count, d_small + 1, d_ticket};
+        if (device_fixup && p0 + kGemmMaxQ >= q) fix = FixupPlan{d_fl, q, fixq, d_map, d_count, d_small + 1, d_ticket};
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
@@ -1558,8 +1561,12 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     // device-side fix-up: one exact scan pass over up to kFixupMaxQ flagged queries (listed by the last
     // finalize launch), merged straight into their rows of d_out; both launches are no-ops when everything
     // was certified
-    rc = topk_scan(ws, stream, d_qall, fixq, dims, 1, K, false, nullptr, d_out, d_map, d_count, true);
-    if (rc) return rc;
+    // A caller that takes the per-query flags re-runs flagged queries itself (Search does, with the exact scan):
+    // its chain ends with finalize and saves the two (normally empty) fix-up launches.
+    if (device_fixup) {
+        rc = topk_scan(ws, stream, d_qall, fixq, dims, 1, K, false, nullptr, d_out, d_map, d_count, true);
+        if (rc) return rc;
+    }
     mark();
     if (stage_timing && !evs.empty()) {
         cudaEventSynchronize(evs.back());

@@ -338,7 +338,7 @@ struct gf_set {
     //   2: everything after the preparation, results to the workspace (ws->t_res / ws->t_flags)
     int topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
                     int64_t l_stride, int K, unsigned long long *d_out, unsigned int *d_flags, int phase = 0,
-                    int path = 0);
+                    int path = 0, bool device_fixup = true);
     bool tensor_eligible(int q, int K, bool per_segment, const unsigned long long *d_upper, int path) const;
     // rows were written on the device: refresh their bf16 shadow and the certificate's bounds (mutation stream)
     int note_rows(const float *d_rows, int64_t rows);
