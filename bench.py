@@ -107,7 +107,7 @@ def hbm_peak():
 def traffic_from_profile(eb):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture of the same
     kernel (eb = bytes per element it streams: 4 float32 rows, 2 bf16 shadow), if any."""
-    p = os.path.join(ROOT, "profiles", "scan_traffic.json" if eb == 4 else "shadow_traffic.json")
+    p = os.path.join(ROOT, "profiles", {4: "scan_traffic.json", 2: "shadow_traffic.json", 1: "shadow_i8_traffic.json"}[eb])
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f).get("dram_bytes_per_launch")
@@ -173,9 +173,11 @@ def run_reference(args, rank, world):
 
 
 def bench_config(args, world):
-    shadow = not getattr(args, "no_shadow", False)
-    return {"shadow": "bf16 shadow slab (+50% HBM per row), candidates re-scored from the float32 rows" if shadow
-            else "none (float32 rows only)",
+    fmt = "none" if getattr(args, "no_shadow", False) else getattr(args, "shadow", "int8")
+    return {"shadow": {"int8": "int8 shadow slab + one float scale per row (+26% HBM per row), candidates re-scored "
+                               "from the float32 rows and certified against the measured quantisation residuals",
+                       "bf16": "bf16 shadow slab (+50% HBM per row), candidates re-scored from the float32 rows",
+                       "none": "none (float32 rows only)"}[fmt],
             "workload": "BASELINE configs[1]: %d x %d-d normalised float32 rows per GPU (%d blocks of 32 MiB), "
                         "top-%d, %d concurrent single-query searchers per step"
                         % (args.rows_per_gpu, DIMS, (args.rows_per_gpu + 16383) // 16384, args.limit, args.queries),
@@ -213,8 +215,9 @@ def run_ours(args, rank, world, local_rank):
     ctx = api.NewContext(local_rank)
     cap = BLOCK_SIZE // (DIMS * 4)
     gblocks = (rows_total + cap - 1) // cap
-    cache = api.NewCache(ctx, (gblocks + world - 1) // world + 1, BLOCK_SIZE, shadow=not args.no_shadow)
-    shadow = cache.HasShadow()
+    cache = api.NewCache(ctx, (gblocks + world - 1) // world + 1, BLOCK_SIZE,
+                         shadow=False if args.no_shadow else args.shadow)
+    shadow_eb = cache.ShadowBytesPerElement()
     sset = ShardedSet(ctx, cache, "bench", DIMS, max(Q, 16), rank, world)
     sset.AddSynthetic(rows_total, SEED)
     rows_local = sset.local.ScannedRows()
@@ -345,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
 
     peak, peak_src = hbm_peak()
     avg_q = Q / scans_per_step if scans_per_step else Q
-    eb = 2 if (tensor and shadow) else 4   # bytes per element the dominant kernel streams
+    eb = shadow_eb if (tensor and shadow_eb) else 4   # bytes per element the dominant kernel streams
     alg_bytes = rows_local * DIMS * eb + avg_q * DIMS * eb + avg_q * K * 8
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     qps_user = Q * args.steps / (dev_ms * 1e-3)
@@ -365,8 +368,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic_from_profile(eb),
                      "kernel": ("gemm_kernel<16,1,%d> (tcgen05 %s COLLECT pass over the %s)"
-                                % (eb, "kind::f16 bf16" if eb == 2 else "kind::tf32",
-                                   "bf16 shadow slab" if eb == 2 else "float32 rows")) if tensor
+                                % (eb, {1: "kind::i8 int8", 2: "kind::f16 bf16", 4: "kind::tf32"}[eb],
+                                   {1: "int8 shadow slab", 2: "bf16 shadow slab", 4: "float32 rows"}[eb])) if tensor
                      else "scan_tma_kernel<512,QT>",
                      "bytes_per_element": eb,
                      "frac_if_counted_as_f32_bytes": (achieved * 4 / eb) / peak if peak else None,
@@ -391,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
         line["e2e_parallel_error"] = demo
     if world == 1:
         l1 = sorted(x * 1e3 for x in lat1)
-        eb1 = 2 if (q1_tensor and shadow) else 4
+        eb1 = shadow_eb if (q1_tensor and shadow_eb) else 4
         b1 = rows_local * DIMS * eb1 + DIMS * eb1 + K * 8
         line["single_query"] = {"p50_ms": l1[len(l1) // 2], "p99_ms": l1[min(len(l1) - 1, int(len(l1) * 0.99))],
                                 "qps": 1e3 / (sum(l1) / len(l1)), "scan_kernel_ms": q1_ms,
@@ -441,7 +444,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-shadow", action="store_true", help="float32 rows only (no bf16 shadow slab)")
+    ap.add_argument("--no-shadow", action="store_true", help="float32 rows only (no shadow slab)")
+    ap.add_argument("--shadow", default="int8", choices=["int8", "bf16"], help="format of the shadow slab")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

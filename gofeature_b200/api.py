@@ -470,6 +470,10 @@ class Cache:
     def HasShadow(self):
         return bool(lib().gf_cache_has_shadow(self._h))
 
+    def ShadowBytesPerElement(self):
+        """0 = no shadow, 1 = int8 (+ one float scale per row), 2 = bf16."""
+        return int(lib().gf_cache_has_shadow(self._h))
+
     def GetEmptyBlock(self, blocknum):
         arr = (c_vp * max(blocknum, 1))()
         _check(lib().gf_cache_get_empty_block(self._h, blocknum, arr))
@@ -491,16 +495,22 @@ class Cache:
 
 CACHE_NO_SHADOW = 1
 CACHE_REQUIRE_SHADOW = 2
+CACHE_SHADOW_BF16 = 4
 
 
 def NewCache(ctx, blockNum, blockSize, shadow=None):
-    """cache.go:21-43.  shadow: None = library default (a bf16 shadow slab unless GF_SHADOW=0),
-    False = none, True = required."""
+    """cache.go:21-43.  shadow: None = library default (an int8 shadow slab unless GF_SHADOW says otherwise),
+    False = none, True / "int8" = int8 required, "bf16" = bf16 required."""
     h = c_vp()
     if shadow is None:
         _check(lib().gf_cache_create(ctx._h, blockNum, blockSize, ctypes.byref(h)))
     else:
-        flags = CACHE_REQUIRE_SHADOW if shadow else CACHE_NO_SHADOW
+        if shadow is False or shadow == "none":
+            flags = CACHE_NO_SHADOW
+        elif shadow == "bf16":
+            flags = CACHE_REQUIRE_SHADOW | CACHE_SHADOW_BF16
+        else:
+            flags = CACHE_REQUIRE_SHADOW
         _check(lib().gf_cache_create_ex(ctx._h, blockNum, blockSize, flags, ctypes.byref(h)))
     return Cache(h, ctx)
 

@@ -370,11 +370,14 @@ int gf_buffer_free(gf_buffer *buf)
 // ------------------------------------------------------------------ Cache (cache.go)
 int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache **out_cache)
 {
-    const char *env = getenv("GF_SHADOW");  // "0" = no bf16 shadow slab
-    return gf_cache_create_ex(ctx, block_num, block_size, (env && env[0] == '0') ? GF_CACHE_NO_SHADOW : 0, out_cache);
+    const char *env = getenv("GF_SHADOW");  // "0" = no shadow slab, "bf16" / "int8" = that format
+    unsigned flags = 0;
+    if (env && env[0] == '0') flags = GF_CACHE_NO_SHADOW;
+    if (env && env[0] == 'b') flags = GF_CACHE_SHADOW_BF16;
+    return gf_cache_create_ex(ctx, block_num, block_size, flags, out_cache);
 }
 
-int gf_cache_has_shadow(const gf_cache *cache) { return (cache && cache->shadow) ? 1 : 0; }
+int gf_cache_has_shadow(const gf_cache *cache) { return (cache && cache->shadow) ? cache->shadow_eb : 0; }
 
 int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsigned flags, gf_cache **out_cache)
 {
@@ -398,17 +401,24 @@ int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsig
         c->slab = std::make_shared<DeviceAlloc>(ctx, p, total, true);
         // bf16 shadow of the slab for the tensor path (half the bytes per scanned row).  It needs block_size / 2
         // bytes per block; when the device cannot hold it the cache works without (GF_CACHE_REQUIRE_SHADOW: fail).
-        const bool want_shadow = !(flags & GF_CACHE_NO_SHADOW) && block_size % 2 == 0 && total > 0;
+        const int seb = (flags & GF_CACHE_SHADOW_BF16) ? 2 : 1;  // default: int8 + one float scale per row
+        const bool want_shadow = !(flags & GF_CACHE_NO_SHADOW) && block_size % 512 == 0 && total > 0;
         if (want_shadow) {
-            void *sp = nullptr;
-            cudaError_t se = cudaMalloc(&sp, total / 2 + 256);
-            if (se == cudaSuccess) se = cudaMemset(sp, 0, total / 2 + 256);
+            void *sp = nullptr, *scp = nullptr;
+            const uint64_t sbytes = total / 4 * seb, scbytes = seb == 1 ? total / 128 : 0;
+            cudaError_t se = cudaMalloc(&sp, sbytes + 256);
+            if (se == cudaSuccess) se = cudaMemset(sp, 0, sbytes + 256);
+            if (se == cudaSuccess && scbytes) se = cudaMalloc(&scp, scbytes + 256);
+            if (se == cudaSuccess && scbytes) se = cudaMemset(scp, 0, scbytes + 256);
             if (se != cudaSuccess) {
                 if (sp) cudaFree(sp);
+                if (scp) cudaFree(scp);
                 cudaGetLastError();
                 if (flags & GF_CACHE_REQUIRE_SHADOW) return cuda_fail(se, "cudaMalloc(shadow)", GF_ERR_ALLOCATE_GPU_BUFFER);
             } else {
-                c->shadow = std::make_shared<DeviceAlloc>(ctx, sp, total / 2, true);
+                c->shadow = std::make_shared<DeviceAlloc>(ctx, sp, sbytes, true);
+                if (scp) c->scales = std::make_shared<DeviceAlloc>(ctx, scp, scbytes, true);
+                c->shadow_eb = seb;
             }
         } else if (flags & GF_CACHE_REQUIRE_SHADOW) {
             return GF_ERR_INVALID_ARGUMENT;
@@ -419,7 +429,10 @@ int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsig
             b->index = i;
             b->block_size = block_size;
             b->dev = (uint8_t *)p + (uint64_t)i * (uint64_t)block_size;
-            if (c->shadow) b->shadow = (uint8_t *)c->shadow->ptr + (uint64_t)i * (uint64_t)(block_size / 2);
+            if (c->shadow) {
+                b->shadow = (uint8_t *)c->shadow->ptr + (uint64_t)i * (uint64_t)(block_size / 4 * c->shadow_eb);
+                b->shadow_eb = c->shadow_eb;
+            }
             c->all_blocks.push_back(std::move(b));
         }
         *out_cache = c.release();

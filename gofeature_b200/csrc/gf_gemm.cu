@@ -34,7 +34,8 @@ __host__ __device__ constexpr int gemm_epi_warps(int nq) { return nq >= 64 ? 8 :
 __host__ __device__ constexpr int gemm_threads(int nq) { return 64 + 32 * gemm_epi_warps(nq); }
 constexpr int kTileRows = 128;
 constexpr int kABytes = kTileRows * 128;  // one K block = one 128-byte swizzle row per feature row
-// elements per K block: 32 floats (kind::tf32 on the fp32 slab) or 64 bf16 (kind::f16 on the bf16 shadow)
+// elements per K block: 32 floats (kind::tf32 on the fp32 slab), 64 bf16 (kind::f16 on the bf16 shadow) or
+// 128 int8 (kind::i8 on the int8 shadow, int32 accumulators)
 template <int EB>
 struct KBlock {
     static constexpr int kElems = 128 / EB;
@@ -56,6 +57,11 @@ struct GemmArgs {
     float *tilemax;
     float *dump;
     unsigned long long dump_ld;
+    // int8 shadow (EB = 1): score = acc_int32 * row_scale * q_scale
+    const float *row_scales;      // [block][scales_per_block]: scale of row j of slab block b at b * scales_per_block + j
+    const float *q_scale;         // [nq]
+    uint32_t scales_per_block;
+    long long block_floats;       // block_size / 4: slab offset (in floats) -> block index
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
@@ -127,6 +133,13 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
             "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
+    } else if (EB == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
     } else if (EB == 4) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -157,11 +170,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(const void *p)
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A and B formats in bits
 // 7-9 / 10-12 (kind::tf32: TF32 = 2; kind::f16: BF16 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+// kind::i8: D = S32 (2), A = B = signed 8-bit (1)
 template <int EB>
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N)
 {
-    return (1u << 4) | ((EB == 4 ? 2u : 1u) << 7) | ((EB == 4 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
+    return ((EB == 1 ? 2u : 1u) << 4) | ((EB == 4 ? 2u : 1u) << 7) | ((EB == 4 ? 2u : 1u) << 10) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 template <int N>
@@ -215,14 +229,14 @@ template <int NQ, int TM, bool PAIR = false>
 struct GemmCfg {
     static constexpr int kBBytes = (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
-    static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 8 - 1024 - kAppendStageBytes) / kStageBytes);
+    static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 12 - 1024 - kAppendStageBytes) / kStageBytes);
     static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
     static constexpr int kBuf = (2 * TM * NQ <= 512) ? 2 : 1;  // accumulator sets (double buffering when TMEM allows)
     static constexpr int kTmemColsRaw = kBuf * TM * NQ;
     static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
     static constexpr int kChunk = (NQ >= 32) ? 32 : 16;
     static constexpr size_t kSmem =
-        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 8 + kAppendStageBytes;
+        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 12 + kAppendStageBytes;
     static_assert(kStages >= 2, "pipeline too shallow");
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
@@ -243,7 +257,8 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     float *thr_s = reinterpret_cast<float *>(tail + 256);
     unsigned int *tmax_s = reinterpret_cast<unsigned int *>(thr_s + NQ);
-    unsigned long long *stage_key = reinterpret_cast<unsigned long long *>(tmax_s + NQ);  // 8-byte aligned: NQ % 2 == 0
+    float *qs_s = reinterpret_cast<float *>(tmax_s + NQ);  // int8 path: per-query dequantisation scale
+    unsigned long long *stage_key = reinterpret_cast<unsigned long long *>(qs_s + NQ);  // 8-byte aligned: NQ % 2 == 0
     int *stage_q = reinterpret_cast<int *>(stage_key + kAppendStage);
     int *stage_n = stage_q + kAppendStage;
 
@@ -287,7 +302,14 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     pdl_wait();
     if (a.mode != 0 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
     for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
-        thr_s[i] = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
+        float th = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
+        if (EB == 1) {
+            // the epilogue compares acc * row_scale against thr / q_scale: one multiply per score instead of two
+            const float qs = a.q_scale[i];
+            qs_s[i] = qs;
+            th = qs > 0.f ? th / qs : __int_as_float(0x7f800000);
+        }
+        thr_s[i] = th;
         tmax_s[i] = 0u;
     }
     if (threadIdx.x == 0) *stage_n = 0;
@@ -395,6 +417,13 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 const bool live = row < valid;
                 const uint32_t slot = a.segs[segi].slot_base + row0 + row;
                 const uint32_t acc_col = buf * (TM * NQ) + j * NQ;
+                float rs = 1.f;  // int8 path: this row's dequantisation scale (a segment is one slab block)
+                if (EB == 1 && live)
+                    rs = a.row_scales[(size_t)((a.segs[segi].base - a.slab_base) / a.block_floats) * a.scales_per_block +
+                                      row0 + row];
+                auto val = [&](uint32_t bits) -> float {  // accumulator -> score (int8: still without the query's scale)
+                    return EB == 1 ? __int2float_rn((int)bits) * rs : __uint_as_float(bits);
+                };
 #pragma unroll 1
                 for (int c0 = col_first; c0 < col_first + kColsPerWarp; c0 += Cfg::kChunk) {
                     uint32_t r[Cfg::kChunk];
@@ -407,10 +436,10 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
 #pragma unroll
                         for (int jj = 0; jj < Cfg::kChunk; jj += 4) {
                             const float4 th = thr4[jj >> 2];
-                            pass |= (__uint_as_float(r[jj + 0]) > th.x) ? (1u << (jj + 0)) : 0u;
-                            pass |= (__uint_as_float(r[jj + 1]) > th.y) ? (1u << (jj + 1)) : 0u;
-                            pass |= (__uint_as_float(r[jj + 2]) > th.z) ? (1u << (jj + 2)) : 0u;
-                            pass |= (__uint_as_float(r[jj + 3]) > th.w) ? (1u << (jj + 3)) : 0u;
+                            pass |= (val(r[jj + 0]) > th.x) ? (1u << (jj + 0)) : 0u;
+                            pass |= (val(r[jj + 1]) > th.y) ? (1u << (jj + 1)) : 0u;
+                            pass |= (val(r[jj + 2]) > th.z) ? (1u << (jj + 2)) : 0u;
+                            pass |= (val(r[jj + 3]) > th.w) ? (1u << (jj + 3)) : 0u;
                         }
                         if (!live) pass = 0;
                         while (pass) {
@@ -419,8 +448,9 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                             float sc = 0.f;
 #pragma unroll
                             for (int jj = 0; jj < Cfg::kChunk; ++jj)
-                                if (jj == b) sc = __uint_as_float(r[jj]);
+                                if (jj == b) sc = val(r[jj]);
                             const int qi = c0 + b;
+                            if (EB == 1) sc *= qs_s[qi];
                             const int sp = atomicAdd(stage_n, 1);
                             if (sp < kAppendStage) {
                                 stage_key[sp] = make_key(sc, slot);
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         float v[Cfg::kChunk];
 #pragma unroll
                         for (int jj = 0; jj < Cfg::kChunk; ++jj)
-                            v[jj] = live ? __uint_as_float(r[jj]) : __int_as_float(0xff800000);
+                            v[jj] = live ? (EB == 1 ? val(r[jj]) * qs_s[c0 + jj] : val(r[jj])) : __int_as_float(0xff800000);
                         // transposed max-reduce: lane jj ends with the max of column c0 + jj over 32 rows
                         int off = 16;
 #pragma unroll
@@ -460,7 +490,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                             for (int jj = 0; jj < Cfg::kChunk; ++jj)
                                 if (c0 + jj < a.q)
                                     a.dump[(size_t)(c0 + jj) * a.dump_ld + (size_t)i * kTileRows + row] =
-                                        __uint_as_float(r[jj]);
+                                        EB == 1 ? val(r[jj]) * qs_s[c0 + jj] : val(r[jj]);
                         }
                     }
                 }
@@ -516,29 +546,53 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
 
 // ------------------------------------------------------------------ helper kernels
 // queries [q][dims] (any stride) -> padded row-major batch [nq][dims] (rows >= q zeroed) + |q|^2
-// With a bf16 shadow: dst_bf [nq][dims] = round-to-nearest bf16 of the batch, qres2 = |q - bf16(q)|^2.
+// With a shadow: dst_sh [nq][dims] = the batch in the shadow's format -- bf16 round-to-nearest (sh_eb = 2) or
+// int8 with one scale per query, scale = max|q| / 127 (sh_eb = 1, q_scale out) -- and qres2 = |q - dequantised|^2.
 __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
                                     int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2,
-                                    float *__restrict__ copy, __nv_bfloat16 *__restrict__ dst_bf,
-                                    float *__restrict__ qres2)
+                                    float *__restrict__ copy, void *__restrict__ dst_sh, int sh_eb,
+                                    float *__restrict__ qres2, float *__restrict__ q_scale)
 {
-    pdl_wait();  // the previous call's kernels may still be reading dst / dst_bf
+    pdl_wait();  // the previous call's kernels may still be reading dst / dst_sh
     pdl_launch_dependents();
     const int qi = blockIdx.x;
-    float acc = 0.f, res = 0.f;
+    __shared__ float red[32], red2[32];
+    __shared__ float s_scale;
+    float acc = 0.f, res = 0.f, amax = 0.f;
     for (int e = threadIdx.x; e < dims; e += blockDim.x) {
         float v = qi < q ? src[(long long)qi * q_stride + (long long)e * l_stride] : 0.f;
         dst[(size_t)qi * dims + e] = v;
         if (copy != nullptr && qi < q) copy[(size_t)qi * dims + e] = v;
         acc += v * v;
-        if (dst_bf != nullptr) {
+        amax = fmaxf(amax, fabsf(v));  // (NaN is skipped by fmaxf: the norm below still turns NaN)
+        if (dst_sh != nullptr && sh_eb == 2) {
             const __nv_bfloat16 b = __float2bfloat16_rn(v);
-            dst_bf[(size_t)qi * dims + e] = b;
+            reinterpret_cast<__nv_bfloat16 *>(dst_sh)[(size_t)qi * dims + e] = b;
             const float d = __bfloat162float(b) - v;
             res += d * d;
         }
     }
-    __shared__ float red[32], red2[32];
+    if (dst_sh != nullptr && sh_eb == 1) {
+        for (int off = 16; off >= 1; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = 0.f;
+            for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fmaxf(m, red[w]);
+            s_scale = m / 127.f;
+        }
+        __syncthreads();
+        const float sc = s_scale, inv = sc > 0.f ? 1.f / sc : 0.f;
+        for (int e = threadIdx.x; e < dims; e += blockDim.x) {
+            const float v = dst[(size_t)qi * dims + e];
+            int qv = __float2int_rn(v * inv);
+            qv = qv > 127 ? 127 : (qv < -127 ? -127 : qv);
+            reinterpret_cast<signed char *>(dst_sh)[(size_t)qi * dims + e] = (signed char)qv;
+            const float d = (float)qv * sc - v;
+            res += d * d;
+        }
+        __syncthreads();
+    }
     for (int off = 16; off >= 1; off >>= 1) {
         acc += __shfl_xor_sync(0xffffffffu, acc, off);
         res += __shfl_xor_sync(0xffffffffu, res, off);
@@ -555,7 +609,8 @@ __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_s
             t2 += red2[w];
         }
         qnorm2[qi] = t * 1.0001f;  // upper bounds are what the certificate needs
-        if (qres2 != nullptr) qres2[qi] = t2 * 1.0001f;
+        if (qres2 != nullptr) qres2[qi] = (t2 == t2 ? t2 : __int_as_float(0x7f800000)) * 1.0001f;
+        if (q_scale != nullptr) q_scale[qi] = (dst_sh != nullptr && sh_eb == 1) ? s_scale : 1.f;
     }
 }
 
@@ -809,14 +864,16 @@ __global__ void __launch_bounds__(256)
             if (!all && n > (unsigned)kp)      // collected but not among the best kp by approx score
                 ceil_approx = fmaxf(ceil_approx, key_score(d_sel[(size_t)qi * kp + kp - 1]));
             // tf32: |approx - exact| <= coeff |row| |q| (operand truncation + accumulation).
-            // bf16 shadow (qres2 != null): approx - exact = <r^ - r, q^> + <r, q^ - q>, bounded by the MEASURED
-            // residual norms max|r^ - r| (kept current by shadow_rows_kernel) and |q^ - q|, with |q^| <=
-            // |q| (1 + 2^-9); coeff |row| |q| covers the fp32 accumulation inside the tensor core.
+            // shadow pass (qres2 != null; r^, q^ = the bf16 or scaled-int8 images): approx - exact =
+            // <r^ - r, q^> + <r, q^ - q>, bounded by the MEASURED residual norms max|r^ - r| (kept current by the
+            // shadow_rows kernels) and |q^ - q|; coeff |row| |q| covers the accumulation (fp32 in the tensor core
+            // for bf16; exact int32 + two float roundings for int8).
             const float mn = sqrtf(__uint_as_float(*maxnorm2_bits)), qn = sqrtf(qnorm2[qi]);
             float delta = err_coeff * mn * qn;
-            if (qres2 != nullptr)
-                delta += sqrtf(__uint_as_float(*maxres2_bits)) * qn * 1.002f + mn * sqrtf(qres2[qi]) +
-                         1e-30f * (1.f + qn);
+            if (qres2 != nullptr) {  // |q^| <= |q| + |q^ - q|
+                const float qr = sqrtf(qres2[qi]);
+                delta += sqrtf(__uint_as_float(*maxres2_bits)) * (qn + qr) * 1.0001f + mn * qr + 1e-30f * (1.f + qn);
+            }
             const unsigned long long kth = buf[keff - 1];
             if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
         }
@@ -901,7 +958,9 @@ cudaError_t make_map(CUtensorMap *map, const void *base, uint64_t rows, int dims
     cuuint64_t gstride[1] = {(cuuint64_t)dims * (cuuint64_t)eb};
     cuuint32_t box[2] = {(cuuint32_t)(128 / eb), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base,
+    CUresult r = fn(map, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                             : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                    2, (void *)base,
                     gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -990,12 +1049,15 @@ static cudaError_t gemm_dispatch(const GemmLaunch &g, const CUtensorMap &tmA, co
 
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
 {
-    const bool bf16 = g.shadow_base != nullptr;
-    const int eb = bf16 ? 2 : 4;
+    const bool shadow = g.shadow_base != nullptr;
+    const int eb = shadow ? g.shadow_eb : 4;  // bytes per element the pass streams: 1 int8, 2 bf16, 4 float32
+    if (eb != 1 && eb != 2 && eb != 4) return cudaErrorInvalidValue;
+    const bool bf16 = eb == 2;
     if (g.dims % (128 / eb) != 0 || g.q < 1 || g.q > g.nq) return cudaErrorInvalidValue;
-    if (bf16 && g.d_queries_bf16 == nullptr) return cudaErrorInvalidValue;
+    if (shadow && g.d_queries_shadow == nullptr) return cudaErrorInvalidValue;
+    if (eb == 1 && (g.d_row_scales == nullptr || g.d_q_scale == nullptr || g.block_size < 512)) return cudaErrorInvalidValue;
     CUtensorMap tmA, tmB;
-    cudaError_t e = make_map(&tmA, bf16 ? g.shadow_base : (const void *)g.slab_base, g.slab_rows, g.dims, kTileRows, eb);
+    cudaError_t e = make_map(&tmA, shadow ? g.shadow_base : (const void *)g.slab_base, g.slab_rows, g.dims, kTileRows, eb);
     if (e != cudaSuccess) return e;
     // cta_group::2 variant (each SM of a pair stages half of the query operand; leader issues M = 256 MMAs):
     // built and parity-tested, but measured SLOWER than one CTA per SM on this workload (256 queries:
@@ -1004,7 +1066,7 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     // unless GF_GEMM_PAIR_MIN (smallest padded batch that uses it: 128 or 256) is set.
     static const int pair_min = getenv("GF_GEMM_PAIR_MIN") ? atoi(getenv("GF_GEMM_PAIR_MIN")) : 1 << 30;
     const bool pair = bf16 && g.nq >= pair_min && (g.nq == 256 || g.nq == 128) && g.tile_count >= 2 && g.sms >= 2;
-    e = make_map(&tmB, bf16 ? g.d_queries_bf16 : (const void *)g.d_queries_padded, (uint64_t)g.nq, g.dims,
+    e = make_map(&tmB, shadow ? g.d_queries_shadow : (const void *)g.d_queries_padded, (uint64_t)g.nq, g.dims,
                  (uint32_t)(pair ? g.nq / 2 : g.nq), eb);
     if (e != cudaSuccess) return e;
     GemmArgs a{};
@@ -1025,16 +1087,21 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.tilemax = g.d_tilemax;
     a.dump = g.d_dump;
     a.dump_ld = g.dump_ld;
+    a.row_scales = g.d_row_scales;
+    a.q_scale = g.d_q_scale;
+    a.scales_per_block = (uint32_t)(g.block_size / 512);
+    a.block_floats = g.block_size / 4;
     if (g.tile_count < 1) return cudaSuccess;
+    if (eb == 1) return gemm_dispatch<1>(g, tmA, tmB, a, false, stream);
     return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, pair, stream) : gemm_dispatch<4>(g, tmA, tmB, a, false, stream);
 }
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
-                                float *dst, float *qnorm2, float *copy, void *dst_bf16, float *qres2,
-                                cudaStream_t stream)
+                                float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
+                                float *q_scale, cudaStream_t stream)
 {
     return launch_chain(prep_queries_kernel, dim3(nq), dim3(128), 0, stream, src, (long long)q_stride,
-                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, (__nv_bfloat16 *)dst_bf16, qres2);
+                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale);
 }
 
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,

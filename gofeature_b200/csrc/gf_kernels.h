@@ -79,6 +79,7 @@ constexpr int kGemmCandCap = 4096;   // candidate keys kept per query
 constexpr int kGemmMaxSampleTiles = 1024;
 constexpr float kTf32ErrCoeff = 2.2e-3f;  // |tf32 score - exact| <= coeff * |row| * |query| (two 10-bit truncations)
 constexpr float kAccErrCoeff = 2.5e-4f;   // fp32 accumulation inside the tensor core (the slack kTf32ErrCoeff holds too)
+constexpr float kI8ErrCoeff = 2e-6f;      // int8 pass: exact int32 accumulation, then two float roundings of the scales
 enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2 };
 
 struct GemmLaunch {
@@ -89,8 +90,12 @@ struct GemmLaunch {
     const float *slab_base;   // first row of the cache slab (tensor map A covers the whole slab)
     uint64_t slab_rows;
     const float *d_queries_padded;  // [nq][dims]
-    const void *shadow_base;        // bf16 shadow of the slab (same row geometry); null = kind::tf32 on the fp32 rows
-    const void *d_queries_bf16;     // [nq][dims] bf16, used with the shadow
+    const void *shadow_base;        // shadow of the slab (same row geometry); null = kind::tf32 on the fp32 rows
+    int shadow_eb;                  // bytes per shadow element: 2 = bf16 (kind::f16), 1 = int8 + row scales (kind::i8)
+    const void *d_queries_shadow;   // [nq][dims] in the shadow's format
+    const float *d_row_scales;      // int8: one scale per slab row, block b row j at b * (block_size / 512) + j
+    const float *d_q_scale;         // int8: [nq]
+    int64_t block_size;             // bytes of one slab block (int8: locates a row's scale)
     int nq, q;
     int mode;
     uint32_t tile_first, tile_stride, tile_count;
@@ -106,8 +111,8 @@ struct GemmLaunch {
 int gemm_pad_queries(int q);
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
-                                float *dst, float *qnorm2, float *copy, void *dst_bf16, float *qres2,
-                                cudaStream_t stream);
+                                float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
+                                float *q_scale, cudaStream_t stream);
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
@@ -145,11 +150,15 @@ cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, un
 // d_small[0] = max |row|^2 bits, d_small[2] = max |bf16(row) - row|^2 bits (atomicMax, upper-bounded)
 cudaError_t shadow_rows_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, unsigned int *d_small,
                                cudaStream_t stream);
+// int8 variant: shadow row = round(row / scale), scale = max|row| / 127 (one float per row, d_scales[i]);
+// the same two bounds in d_small, the residual measured against scale * int8
+cudaError_t shadow_rows_i8_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, float *d_scales,
+                                  unsigned int *d_small, cudaStream_t stream);
 
 // src / slots / elem_off may live in pinned host memory (the upload ring): the kernels read them over PCIe
 cudaError_t scatter_rows_launch(const float *src, const int *slots, int n, int dims, float *d_base, cudaStream_t stream);
-cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, const unsigned long long *elem_off, int n, int dims,
-                             cudaStream_t stream);
+cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, int shadow_eb, const unsigned long long *elem_off, int n,
+                             int dims, cudaStream_t stream);
 cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int dims, float *d_dst,
                                cudaStream_t stream);
 

@@ -250,6 +250,72 @@ __global__ void shadow_rows_kernel(const float *__restrict__ base, long long row
 }
 }  // namespace
 
+namespace {
+// int8 shadow: one warp per row, the row stays in registers between the max pass and the rounding pass
+__global__ void shadow_rows_i8_kernel(const float *__restrict__ base, long long rows, int dims,
+                                      signed char *__restrict__ out, float *__restrict__ scales, unsigned int *small)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f, best_res = 0.f;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float4 *x = reinterpret_cast<const float4 *>(base + (size_t)r * dims);
+        float acc = 0.f, amax = 0.f;
+        bool bad = false;
+        for (int e = lane; e < dims / 4; e += 32) {
+            const float4 v = x[e];
+            acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        }
+        const float sc = amax / 127.f, inv = sc > 0.f ? 1.f / sc : 0.f;
+        if (!(acc == acc) || !(amax < __int_as_float(0x7f800000)) || !(inv < __int_as_float(0x7f800000))) bad = true;
+        float res = 0.f;
+        unsigned int *o = reinterpret_cast<unsigned int *>(out + (size_t)r * dims);
+        for (int e = lane; e < dims / 4; e += 32) {
+            const float4 v = x[e];  // second read: L1/L2 hit
+            int q0 = __float2int_rn(v.x * inv), q1 = __float2int_rn(v.y * inv), q2 = __float2int_rn(v.z * inv),
+                q3 = __float2int_rn(v.w * inv);
+            q0 = max(-127, min(127, q0));
+            q1 = max(-127, min(127, q1));
+            q2 = max(-127, min(127, q2));
+            q3 = max(-127, min(127, q3));
+            if (bad) q0 = q1 = q2 = q3 = 0;
+            o[e] = (unsigned)(q0 & 255) | ((unsigned)(q1 & 255) << 8) | ((unsigned)(q2 & 255) << 16) |
+                   ((unsigned)(q3 & 255) << 24);
+            const float d0 = (float)q0 * sc - v.x, d1 = (float)q1 * sc - v.y, d2 = (float)q2 * sc - v.z,
+                        d3 = (float)q3 * sc - v.w;
+            res += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+        for (int off = 16; off >= 1; off >>= 1) res += __shfl_xor_sync(0xffffffffu, res, off);
+        if (lane == 0) scales[r] = bad ? 0.f : sc;
+        if (acc == acc) best = fmaxf(best, acc);
+        // Inf / NaN / overflowing rows cannot be bounded: every certificate of this set must fail
+        best_res = (!bad && res == res) ? fmaxf(best_res, res) : __int_as_float(0x7f800000);
+    }
+    if (lane == 0) {
+        if (best > 0.f) atomicMax(small + 0, __float_as_uint(best * 1.0001f));
+        if (best_res > 0.f) atomicMax(small + 2, __float_as_uint(best_res * 1.0001f));
+    }
+}
+}  // namespace
+
+cudaError_t shadow_rows_i8_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, float *d_scales,
+                                  unsigned int *d_small, cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    if (dims % 4 != 0) return cudaErrorInvalidValue;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    shadow_rows_i8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, rows, dims, (signed char *)d_shadow_rows, d_scales,
+                                                                d_small);
+    return cudaGetLastError();
+}
+
 cudaError_t shadow_rows_launch(const float *d_rows, int64_t rows, int dims, void *d_shadow_rows, unsigned int *d_small,
                                cudaStream_t stream)
 {
@@ -285,7 +351,7 @@ __global__ void scatter_rows_kernel(const float *__restrict__ src, const int *__
     }
 }
 // zero the float32 row (and its bf16 shadow row) at element offset off[i] of the slab(s)
-__global__ void zero_rows_kernel(float *__restrict__ slab, unsigned short *__restrict__ shadow,
+__global__ void zero_rows_kernel(float *__restrict__ slab, unsigned char *__restrict__ shadow, int shadow_eb,
                                  const unsigned long long *__restrict__ off, int n, int dims)
 {
     const int lane = threadIdx.x & 31;
@@ -294,9 +360,9 @@ __global__ void zero_rows_kernel(float *__restrict__ slab, unsigned short *__res
     for (int j = warp; j < n; j += nwarps) {
         float *d = slab + off[j];
         for (int e = lane; e < dims; e += 32) d[e] = 0.f;
-        if (shadow != nullptr) {
-            unsigned short *h = shadow + off[j];
-            for (int e = lane; e < dims; e += 32) h[e] = 0;
+        if (shadow != nullptr) {  // dims * shadow_eb bytes at the same element offset (dims % 4 == 0 on shadow paths)
+            unsigned int *h = reinterpret_cast<unsigned int *>(shadow + off[j] * shadow_eb);
+            for (int e = lane; e < dims * shadow_eb / 4; e += 32) h[e] = 0u;
         }
     }
 }
@@ -311,13 +377,14 @@ cudaError_t scatter_rows_launch(const float *src, const int *slots, int n, int d
     return cudaGetLastError();
 }
 
-cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, const unsigned long long *elem_off, int n, int dims,
-                             cudaStream_t stream)
+cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, int shadow_eb, const unsigned long long *elem_off, int n,
+                             int dims, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
+    if (d_shadow != nullptr && dims % 4 != 0) d_shadow = nullptr;  // no shadow path for such a set
     int blocks = (n + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    zero_rows_kernel<<<blocks, 256, 0, stream>>>(d_slab, (unsigned short *)d_shadow, elem_off, n, dims);
+    zero_rows_kernel<<<blocks, 256, 0, stream>>>(d_slab, (unsigned char *)d_shadow, shadow_eb, elem_off, n, dims);
     return cudaGetLastError();
 }
 

@@ -284,7 +284,8 @@ int Context::upload_scatter(uint8_t *base, const int *slots, size_t n, size_t ro
 
 // zero whole float32 rows (and their bf16 shadow rows) given by element offsets into the slab(s): the list
 // travels through the pinned ring, one kernel per chunk
-int Context::zero_rows(float *d_slab, void *d_shadow, const std::vector<unsigned long long> &elem_off, int dims)
+int Context::zero_rows(float *d_slab, void *d_shadow, int shadow_eb, const std::vector<unsigned long long> &elem_off,
+                       int dims)
 {
     if (elem_off.empty()) return GF_OK;
     std::lock_guard<std::mutex> g(stage_mu);
@@ -295,7 +296,7 @@ int Context::zero_rows(float *d_slab, void *d_shadow, const std::vector<unsigned
         const int i = k & 1;
         GF_CUDA(cudaEventSynchronize(stage_ev[i]), GF_ERR_CLEAR_CUDA_BUFFER);
         memcpy(stage[i], elem_off.data() + r0, cnt * sizeof(unsigned long long));
-        GF_CUDA(zero_rows_launch(d_slab, d_shadow, reinterpret_cast<const unsigned long long *>(stage[i]), (int)cnt, dims,
+        GF_CUDA(zero_rows_launch(d_slab, d_shadow, shadow_eb, reinterpret_cast<const unsigned long long *>(stage[i]), (int)cnt, dims,
                                  mut_stream),
                 GF_ERR_CLEAR_CUDA_BUFFER);
         stats.other_launches++;
@@ -456,7 +457,8 @@ int Block::release()
     if (rc) return rc;
     GF_CUDA(cudaMemsetAsync(dev, 0, (size_t)block_size, cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     if (shadow)
-        GF_CUDA(cudaMemsetAsync(shadow, 0, (size_t)block_size / 2, cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
+        GF_CUDA(cudaMemsetAsync(shadow, 0, (size_t)block_size * shadow_eb / 4, cache->ctx->mut_stream),
+                GF_ERR_CLEAR_CUDA_BUFFER);
     GF_CUDA(cudaStreamSynchronize(cache->ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     dims = precision = batch = 0;
     owner.clear();
@@ -586,7 +588,7 @@ int Block::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &fo
         if (row < 0) continue;
         GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
         if (shadow && precision == 4)
-            GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * (rowb / 2), 0, rowb / 2, ctx->mut_stream),
+            GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * dims * shadow_eb, 0, (size_t)dims * shadow_eb, ctx->mut_stream),
                     GF_ERR_CLEAR_CUDA_BUFFER);
         if (!implicit_ids) {
             index_del(ids_[i], row);
@@ -618,7 +620,8 @@ int Block::remove_rows(const std::vector<int> &rows, std::vector<unsigned long l
         } else {
             GF_CUDA(cudaMemsetAsync(dev + (size_t)row * rowb, 0, rowb, ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
             if (shadow && precision == 4)
-                GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * (rowb / 2), 0, rowb / 2, ctx->mut_stream),
+                GF_CUDA(cudaMemsetAsync(shadow + (size_t)row * dims * shadow_eb, 0, (size_t)dims * shadow_eb,
+                                        ctx->mut_stream),
                         GF_ERR_CLEAR_CUDA_BUFFER);
         }
         if (!implicit_ids) {
@@ -807,7 +810,9 @@ int Set::rebuild_segments()
     total_gtiles = gt;
     tensor_ok = precision == 4 && dims % 32 == 0 && dims >= 32 && (cache->block_size % ((int64_t)dims * 4)) == 0 &&
                 ((uintptr_t)cache->slab->ptr % 128) == 0;
-    shadow_ok = tensor_ok && cache->shadow != nullptr && dims % 64 == 0 && ((uintptr_t)cache->shadow->ptr % 128) == 0;
+    // one K block of the shadow pass is a 128-byte swizzle row: 64 bf16 or 128 int8 elements
+    shadow_ok = tensor_ok && cache->shadow != nullptr && dims % (128 / cache->shadow_eb) == 0 &&
+                ((uintptr_t)cache->shadow->ptr % 128) == 0;
     GF_CUDA(cudaMemcpyAsync(d_segs, h_segs.data(), n * sizeof(Segment), cudaMemcpyHostToDevice, ctx->mut_stream),
             GF_ERR_WRITE_CUDA_BUFFER);
     GF_CUDA(cudaMemcpyAsync(d_gtile_start, aux.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
@@ -829,11 +834,20 @@ int Set::note_rows(const float *d_rows, int64_t rows)
         GF_CUDA(cudaMalloc((void **)&d_small, 64), GF_ERR_ALLOCATE_GPU_BUFFER);
         GF_CUDA(cudaMemsetAsync(d_small, 0, 64, ctx->mut_stream), GF_ERR_CUDA);
     }
-    if (cache->shadow != nullptr && dims % 4 == 0) {
+    if (cache->shadow != nullptr && dims % 4 == 0 && (cache->shadow_eb == 2 || dims % 128 == 0)) {
         // same element index in both slabs: row j of block i sits at the same (i, j) in the shadow
         const size_t elem = (size_t)(d_rows - (const float *)cache->slab->ptr);
-        GF_CUDA(shadow_rows_launch(d_rows, rows, dims, (uint16_t *)cache->shadow->ptr + elem, d_small, ctx->mut_stream),
-                GF_ERR_CUDA);
+        if (cache->shadow_eb == 2) {
+            GF_CUDA(shadow_rows_launch(d_rows, rows, dims, (uint16_t *)cache->shadow->ptr + elem, d_small, ctx->mut_stream),
+                    GF_ERR_CUDA);
+        } else {
+            const size_t block_floats = (size_t)cache->block_size / 4;
+            const size_t blk = elem / block_floats, row0 = (elem % block_floats) / (size_t)dims;
+            float *sc = (float *)cache->scales->ptr + blk * ((size_t)cache->block_size / 512) + row0;
+            GF_CUDA(shadow_rows_i8_launch(d_rows, rows, dims, (uint8_t *)cache->shadow->ptr + elem, sc, d_small,
+                                          ctx->mut_stream),
+                    GF_ERR_CUDA);
+        }
     } else {
         GF_CUDA(rownorm_range_launch(d_rows, rows, dims, d_small, ctx->mut_stream), GF_ERR_CUDA);
     }
@@ -1040,7 +1054,8 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
         if (rc) return rc;
     }
     if (batched) {
-        rc = ctx->zero_rows((float *)cache->slab->ptr, cache->shadow ? cache->shadow->ptr : nullptr, zero_off, dims);
+        rc = ctx->zero_rows((float *)cache->slab->ptr, cache->shadow ? cache->shadow->ptr : nullptr, cache->shadow_eb,
+                            zero_off, dims);
         if (rc) return rc;
     } else if (!per_block.empty()) {
         GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
@@ -1139,8 +1154,8 @@ int Set::compact(int64_t *reclaimed)
                 rc = note_rows((const float *)b->dev, n_live);
                 if (rc) return rc;
             }
-            GF_CUDA(cudaMemsetAsync(b->shadow + (size_t)n_live * dims * 2, 0,
-                                    (size_t)(b->next_index - n_live) * dims * 2, ctx->mut_stream),
+            GF_CUDA(cudaMemsetAsync(b->shadow + (size_t)n_live * dims * b->shadow_eb, 0,
+                                    (size_t)(b->next_index - n_live) * dims * b->shadow_eb, ctx->mut_stream),
                     GF_ERR_CLEAR_CUDA_BUFFER);
         }
         GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CUDA);  // rows[] is reused by the next block
@@ -1258,7 +1273,7 @@ bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long lo
     if (K > 512) return false;                               // K' = K + slack must fit the 1024-key re-score
     if (total_gtiles < 2 * 256) return false;                // small sets: the sample would be the set
     if (path == 2 || path == 3) return true;
-    // the bf16 shadow halves the bytes of a pass: it wins for every batch size
+    // the shadow pass streams a half (bf16) or a quarter (int8) of the bytes: it wins for every batch size
     if (shadow_ok) return true;
     // one scan pass cannot hold the batch, or K is beyond what the per-CTA sorted lists do cheaply
     return q > scan_max_q(dims) || K > 32;
@@ -1280,7 +1295,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     Stats &st = ctx->stats;
     const bool device_fixup = d_flags == nullptr;  // nobody to report an uncertified query to: repair it here
-    const int mode = (use_shadow(path) ? 1 : 0) | (device_fixup ? 2 : 0);
+    const int mode = (use_shadow(path) ? cache->shadow_eb : 0) | (device_fixup ? 4 : 0);
     // bake_io (Search's own staging buffers, stable per workspace): the query preparation and the copy of
     // keys + flags are nodes of the graph too -- ONE stream operation per call
     bake_io = bake_io && d_flags != nullptr && q_stride == dims && l_stride == 1 && stream == ws->stream;
@@ -1402,10 +1417,13 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                      bool device_fixup)
 {
     const int nseg = (int)h_segs.size();
-    const bool bf16 = use_shadow(path);
+    const int seb = use_shadow(path) ? cache->shadow_eb : 0;  // 0 float32 rows (tf32), 2 bf16 shadow, 1 int8 shadow
+    const bool bf16 = seb != 0;                                // (a shadow pass: measured-residual certificate)
     // K' re-scored per query when the batch is too large to re-score everything collected: the certificate
-    // needs exact[K] > approx[K'] + delta, and delta is ~3.5e-3 with bf16 operands (2.2e-3 with tf32)
-    const int kp = bf16 ? std::min(1024, std::max(K + 64, 2 * K + 32)) : std::min(1024, std::max(K + 32, K + K / 2));
+    // needs exact[K] > approx[K'] + delta; delta ~ 2.2e-3 with tf32, ~3.5e-3 with bf16, ~8e-3 .. 2e-2 with int8
+    const int kp = seb == 1   ? std::min(1024, std::max(K + 96, 3 * K + 64))
+                   : seb == 2 ? std::min(1024, std::max(K + 64, 2 * K + 32))
+                              : std::min(1024, std::max(K + 32, K + K / 2));
     const unsigned cap = kGemmCandCap;
     // sample: G strided tiles; threshold = m-th largest tile maximum so that ~target rows pass
     // whole waves of the grid: one tile per SM on a 1 M-row set, up to 6 on the largest
@@ -1429,8 +1447,9 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_ticket = carve(4);  // always offset 0: zeroed when the arena is allocated, left zero by every call
     const size_t o_qpad = carve((size_t)nq_max * dims * 4);
     const size_t o_qn = carve((size_t)nq_max * 4);
-    const size_t o_qbf = carve(bf16 ? (size_t)nq_max * dims * 2 : 0);
+    const size_t o_qbf = carve(bf16 ? (size_t)nq_max * dims * seb : 0);
     const size_t o_qres = carve((size_t)nq_max * 4);
+    const size_t o_qsc = carve((size_t)nq_max * 4);
     const size_t o_tmax = carve((size_t)kGemmMaxSampleTiles * nq_max * 4);
     const size_t o_thr = carve((size_t)nq_max * 4);
     const size_t o_cnt = carve((size_t)nq_max * 4);
@@ -1451,7 +1470,8 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     float *d_qn = (float *)(T + o_qn);
     void *d_qbf = bf16 ? (void *)(T + o_qbf) : nullptr;
     float *d_qres = bf16 ? (float *)(T + o_qres) : nullptr;
-    const float err_coeff = bf16 ? kAccErrCoeff : kTf32ErrCoeff;
+    float *d_qsc = (float *)(T + o_qsc);
+    const float err_coeff = seb == 1 ? kI8ErrCoeff : seb == 2 ? kAccErrCoeff : kTf32ErrCoeff;
     float *d_tmax = (float *)(T + o_tmax);
     float *d_thr = (float *)(T + o_thr);
     unsigned int *d_cnt = (unsigned int *)(T + o_cnt);
@@ -1476,7 +1496,11 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     g.slab_rows = (uint64_t)(cache->slab->size / ((uint64_t)dims * 4));
     g.d_queries_padded = d_qpad;
     g.shadow_base = bf16 ? cache->shadow->ptr : nullptr;
-    g.d_queries_bf16 = d_qbf;
+    g.shadow_eb = seb;
+    g.d_queries_shadow = d_qbf;
+    g.d_row_scales = seb == 1 ? (const float *)cache->scales->ptr : nullptr;
+    g.d_q_scale = d_qsc;
+    g.block_size = cache->block_size;
     g.d_thr = d_thr;
     g.d_cand = d_cand;
     g.d_cnt = d_cnt;
@@ -1504,7 +1528,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
-                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, d_qres, stream),
+                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
         const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call: it sizes d_exact

@@ -128,7 +128,8 @@ struct gf_context {
     int upload(void *dst, const void *src, size_t bytes);
     // n rows of `rowb` bytes, row i to base + slots[i]*rowb: staged through the ring, one sync at the end
     int upload_scatter(uint8_t *base, const int *slots, size_t n, size_t rowb, const uint8_t *src);
-    int zero_rows(float *d_slab, void *d_shadow, const std::vector<unsigned long long> &elem_off, int dims);
+    int zero_rows(float *d_slab, void *d_shadow, int shadow_eb, const std::vector<unsigned long long> &elem_off,
+                  int dims);
     ~gf_context();
 };
 
@@ -170,7 +171,8 @@ struct gf_block {
     int index = 0;
     int64_t block_size = 0;
     uint8_t *dev = nullptr;
-    uint8_t *shadow = nullptr;  // this block's rows in the cache's bf16 shadow slab (null: no shadow)
+    uint8_t *shadow = nullptr;  // this block's rows in the cache's shadow slab (null: no shadow)
+    int shadow_eb = 0;          // bytes per shadow element: 2 bf16, 1 int8 (+ one float scale per row)
     std::mutex mu;  // block.go:19
     // feature info (block.go:24-31)
     int dims = 0, precision = 0, batch = 0;
@@ -256,7 +258,7 @@ struct gf_set {
     uint32_t total_gtiles = 0;
     unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter, [2] max |bf16(row) - row|^2 bits
     bool tensor_ok = false;
-    bool shadow_ok = false;   // the bf16 shadow of this set's rows is maintained and usable by the tensor path
+    bool shadow_ok = false;   // the shadow of this set's rows is maintained and usable by the tensor path
     int search_path = 0;      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32
     uint64_t version = 0;  // bumped whenever the segment table or the shard identity changes
     uint32_t total_tiles = 0;
@@ -350,7 +352,11 @@ struct gf_cache {
     gf::Context *ctx = nullptr;
     int64_t block_size = 0;
     std::shared_ptr<gf::DeviceAlloc> slab;
-    std::shared_ptr<gf::DeviceAlloc> shadow;  // bf16 copy of the slab, same row geometry at half the bytes (optional)
+    // optional shadow of the slab, same row geometry: bf16 (shadow_eb = 2, half the bytes) or int8 with one float
+    // scale per row (shadow_eb = 1, a quarter of the bytes; scales: block b, row j at b * (block_size / 512) + j)
+    std::shared_ptr<gf::DeviceAlloc> shadow;
+    std::shared_ptr<gf::DeviceAlloc> scales;
+    int shadow_eb = 0;
     std::vector<std::unique_ptr<gf::Block>> all_blocks;
     std::mutex mu;  // cache.go:17
     std::unordered_map<std::string, gf::Set *> sets;

@@ -138,15 +138,18 @@ GF_API int gf_buffer_free(gf_buffer *buf);
 /* ------------------------------------------------- L4: Cache (interface.go:12-34) */
 /* NewCache(ctx, blockNum, blockSize) (cache.go:21-43): one zeroed slab cut into blocks. */
 GF_API int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache **out_cache);
-/* gf_cache_create with options.  By default the cache also keeps a bf16 SHADOW of the slab
- * (block_size / 2 more bytes per block, rows converted on the device whenever Add / Update /
- * Delete / Compact writes them): the tensor-core candidate pass then streams 2 bytes per
- * element instead of 4, and every candidate is still re-scored from the float32 rows, so
- * results are identical with and without it.  GF_CACHE_NO_SHADOW (or the environment variable
- * GF_SHADOW=0 for gf_cache_create) turns it off; GF_CACHE_REQUIRE_SHADOW fails instead of
- * continuing without when the device cannot hold it. */
+/* gf_cache_create with options.  By default the cache also keeps a SHADOW of the slab: the rows
+ * quantised to int8 with one float scale per row (block_size / 4 + block_size / 128 more bytes per
+ * block; GF_CACHE_SHADOW_BF16: bf16 instead, block_size / 2 more bytes), converted on the device
+ * whenever Add / Update / Delete / Compact writes rows.  The tensor-core candidate pass then
+ * streams 1 (or 2) bytes per element instead of 4; every candidate is still re-scored from the
+ * float32 rows and certified against the MEASURED quantisation residuals, so results are identical
+ * with and without it.  GF_CACHE_NO_SHADOW (environment for gf_cache_create: GF_SHADOW=0, =bf16)
+ * turns it off; GF_CACHE_REQUIRE_SHADOW fails instead of continuing without when the device cannot
+ * hold it.  gf_cache_has_shadow: 0 none, 1 int8, 2 bf16. */
 #define GF_CACHE_NO_SHADOW 1u
 #define GF_CACHE_REQUIRE_SHADOW 2u
+#define GF_CACHE_SHADOW_BF16 4u
 GF_API int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsigned flags,
                               gf_cache **out_cache);
 GF_API int gf_cache_has_shadow(const gf_cache *cache);

@@ -12,7 +12,7 @@ from oracle import model
 pytestmark = pytest.mark.gpu
 
 
-def _pair(gpu_ctx, name, dims, batch, block_rows, block_num, shadow=True):
+def _pair(gpu_ctx, name, dims, batch, block_rows, block_num, shadow="int8"):
     from gofeature_b200 import api
     bs = block_rows * dims * 4
     cache = api.NewCache(gpu_ctx, block_num, bs, shadow=shadow)
@@ -31,6 +31,7 @@ def _assert_same(got, want, what=""):
         assert gs.tobytes() == ws.tobytes(), "%s query %d scores" % (what, q)
 
 
+@pytest.mark.parametrize("fmt", ["int8", "bf16"])
 @pytest.mark.parametrize("dims,n,q,limit", [
     (512, 70000, 1, 10),        # a single query: the shadow path takes every batch size
     (512, 70000, 3, 1),
@@ -40,11 +41,12 @@ def _assert_same(got, want, what=""):
     (128, 140000, 5, 10),
     (256, 80000, 17, 50),
     (1024, 66000, 2, 10),
+    (192, 100000, 12, 10),      # 64 | dims but not 128: bf16 shadow pass, or TF32 over the float32 rows (int8 cache)
 ])
-def test_shadow_path_parity(gpu_ctx, dims, n, q, limit):
+def test_shadow_path_parity(gpu_ctx, dims, n, q, limit, fmt):
     block_rows = 16384
-    cache, st, ost = _pair(gpu_ctx, "shadow", dims, q, block_rows, (n + block_rows - 1) // block_rows + 1)
-    assert cache.HasShadow()
+    cache, st, ost = _pair(gpu_ctx, "shadow", dims, q, block_rows, (n + block_rows - 1) // block_rows + 1, shadow=fmt)
+    assert cache.ShadowBytesPerElement() == {"int8": 1, "bf16": 2}[fmt]
     st.AddSynthetic(n, 777 + dims)
     rows = ol.synth_rows(777 + dims, 0, n, dims)
     ost.add(rows, ["f%011d" % i for i in range(n)])
@@ -87,12 +89,13 @@ def test_shadow_off_and_required(gpu_ctx):
     cache.Close()
 
 
-def test_shadow_follows_every_mutation(gpu_ctx):
+@pytest.mark.parametrize("fmt", ["int8", "bf16"])
+def test_shadow_follows_every_mutation(gpu_ctx, fmt):
     """Explicit Add (tail + tombstone refill), Delete, Update and Compact on a set large enough for the
     tensor path: after each step the bf16 shadow must describe the float32 rows, or winners go missing."""
     from gofeature_b200 import api
     dims, block_rows = 512, 8192
-    cache, st, ost = _pair(gpu_ctx, "mut", dims, 8, block_rows, 14)
+    cache, st, ost = _pair(gpu_ctx, "mut", dims, 8, block_rows, 14, shadow=fmt)
     rng = np.random.default_rng(5)
     n0 = 70000
     rows = ol.synth_rows(900, 0, n0, dims)
@@ -148,11 +151,12 @@ def test_shadow_follows_every_mutation(gpu_ctx):
     cache.Close()
 
 
-def test_shadow_certificate_fallback_and_extreme_rows(gpu_ctx):
+@pytest.mark.parametrize("fmt", ["int8", "bf16"])
+def test_shadow_certificate_fallback_and_extreme_rows(gpu_ctx, fmt):
     """Near-duplicates closer than the bf16 error, un-normalised rows, and rows whose elements leave the bf16
     range (the residual bound becomes infinite): the certificate must refuse and the exact scan must answer."""
     dims, n, q, limit = 512, 70000, 12, 10
-    cache, st, ost = _pair(gpu_ctx, "scert", dims, q, 16384, 6)
+    cache, st, ost = _pair(gpu_ctx, "scert", dims, q, 16384, 6, shadow=fmt)
     rng = np.random.default_rng(23)
     rows = ol.synth_rows(818, 0, n, dims)
     rows[::3] *= np.float32(2.5)
