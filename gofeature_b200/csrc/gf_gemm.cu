@@ -222,6 +222,9 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
 // COLLECT appends are staged in shared memory and flushed 128 at a time: a global atomicAdd per survivor
 // inside the score loop stalled the whole epilogue warp for an L2 round trip (4 per warp per tile at 256
 // queries x ~500 candidates), longer than the MMAs of the next tile take
+#ifndef GF_GEMM_STAGES_SMALL
+#define GF_GEMM_STAGES_SMALL 6
+#endif
 constexpr int kAppendStage = 256;
 constexpr int kAppendStageBytes = kAppendStage * 12 + 16;
 
@@ -230,7 +233,10 @@ struct GemmCfg {
     static constexpr int kBBytes = (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
     static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 12 - 1024 - kAppendStageBytes) / kStageBytes);
-    static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+    // small batches are pure HBM streaming with short tiles (int8: 4 K blocks of 18 KB per tile): a deep ring
+    // keeps more than two tiles of loads in flight across the per-tile work of the producer
+    static constexpr int kStagesCap = GF_GEMM_STAGES_SMALL;
+    static constexpr int kStages = kStagesFit > (NQ <= 32 ? kStagesCap : 6) ? (NQ <= 32 ? kStagesCap : 6) : kStagesFit;
     static constexpr int kBuf = (2 * TM * NQ <= 512) ? 2 : 1;  // accumulator sets (double buffering when TMEM allows)
     static constexpr int kTmemColsRaw = kBuf * TM * NQ;
     static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
