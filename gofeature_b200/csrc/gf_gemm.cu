@@ -62,7 +62,42 @@ struct GemmArgs {
     const float *q_scale;         // [nq]
     uint32_t scales_per_block;
     long long block_floats;       // block_size / 4: slab offset (in floats) -> block index
+    // FUSED mode (3): the threshold sample is each CTA's own first tile
+    float *thr_out;               // [nq] thresholds written by CTA 0 (finalize's certificate reads them)
+    unsigned int *sync;           // [0] arrival count, [1] generation, [2] sticky "a barrier timed out"
+    int sample_m;                 // threshold = sample_m-th largest of the gridDim.x tile maxima
 };
+
+// All CTAs of the grid are co-resident (grid <= SMs, one CTA per SM fits by construction), so a counter +
+// generation barrier is safe; a timeout turns a scheduling surprise into "collect nothing" (every query is
+// then flagged and answered by the exact scan) instead of a hung GPU.
+__device__ __forceinline__ bool grid_barrier(unsigned int *sync, unsigned int n)
+{
+    volatile unsigned int *vs = sync;
+    if (vs[2] != 0u) return false;
+    const unsigned int my = vs[1];
+    __threadfence();
+    if (atomicAdd(sync, 1u) == n - 1u) {
+        atomicExch(sync, 0u);
+        __threadfence();
+        atomicAdd(sync + 1, 1u);
+        return true;
+    }
+    unsigned long long t0 = 0ull;
+    for (unsigned int spins = 0; vs[1] == my; ++spins) {
+        if ((spins & 4095u) == 4095u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            if (now - t0 > 2000000000ull) {
+                atomicExch(sync + 2, 1u);
+                return false;
+            }
+        }
+    }
+    __threadfence();
+    return true;
+}
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
@@ -222,6 +257,9 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
 // COLLECT appends are staged in shared memory and flushed 128 at a time: a global atomicAdd per survivor
 // inside the score loop stalled the whole epilogue warp for an L2 round trip (4 per warp per tile at 256
 // queries x ~500 candidates), longer than the MMAs of the next tile take
+#ifndef GF_GEMM_TMEM_BUFS
+#define GF_GEMM_TMEM_BUFS 2
+#endif
 #ifndef GF_GEMM_STAGES_SMALL
 #define GF_GEMM_STAGES_SMALL 6
 #endif
@@ -232,17 +270,22 @@ template <int NQ, int TM, bool PAIR = false>
 struct GemmCfg {
     static constexpr int kBBytes = (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
-    static constexpr int kStagesFit = (int)((232448 - 1024 - 256 - NQ * 12 - 1024 - kAppendStageBytes) / kStageBytes);
+    static constexpr int kStagesFit = (int)((232448 - 1024 - 320 - NQ * 12 - 1024 - kAppendStageBytes) / kStageBytes);
     // small batches are pure HBM streaming with short tiles (int8: 4 K blocks of 18 KB per tile): a deep ring
     // keeps more than two tiles of loads in flight across the per-tile work of the producer
     static constexpr int kStagesCap = GF_GEMM_STAGES_SMALL;
     static constexpr int kStages = kStagesFit > (NQ <= 32 ? kStagesCap : 6) ? (NQ <= 32 ? kStagesCap : 6) : kStagesFit;
-    static constexpr int kBuf = (2 * TM * NQ <= 512) ? 2 : 1;  // accumulator sets (double buffering when TMEM allows)
+    // accumulator sets in TMEM: up to 8 (small batches leave most of the 512 columns free, and the FUSED launch
+    // lets the MMAs run that many tiles ahead while the epilogue waits for the thresholds behind the grid barrier)
+    static constexpr int kBufFit = 512 / (TM * NQ);
+    static constexpr int kBufMax = GF_GEMM_TMEM_BUFS;  // 2 measured best (8: COLLECT 0.088 -> 0.096 ms at 16 queries)
+    static constexpr int kBuf = kBufFit >= kBufMax ? kBufMax : (kBufFit >= 4 && kBufMax >= 4 ? 4 : (kBufFit >= 2 ? 2 : 1));
+    static_assert((2 * 11 + 2 * 8) * 8 + 8 <= 312, "barrier region");
     static constexpr int kTmemColsRaw = kBuf * TM * NQ;
     static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
     static constexpr int kChunk = (NQ >= 32) ? 32 : 16;
     static constexpr size_t kSmem =
-        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + NQ * 12 + kAppendStageBytes;
+        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 320 /*barriers*/ + NQ * 12 + kAppendStageBytes;
     static_assert(kStages >= 2, "pipeline too shallow");
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
@@ -259,9 +302,9 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     uint64_t *full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *empty = full + Cfg::kStages;
     uint64_t *tfull = empty + Cfg::kStages;
-    uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    float *thr_s = reinterpret_cast<float *>(tail + 256);
+    uint64_t *tempty = tfull + Cfg::kBuf;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + Cfg::kBuf);
+    float *thr_s = reinterpret_cast<float *>(tail + 320);
     unsigned int *tmax_s = reinterpret_cast<unsigned int *>(thr_s + NQ);
     float *qs_s = reinterpret_cast<float *>(tmax_s + NQ);  // int8 path: per-query dequantisation scale
     unsigned long long *stage_key = reinterpret_cast<unsigned long long *>(qs_s + NQ);  // 8-byte aligned: NQ % 2 == 0
@@ -279,13 +322,20 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
     const uint32_t worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
     const uint32_t nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
+    // which groups this worker takes: strided over the workers, or (FUSED) one contiguous chunk, so that the
+    // first tiles of the CTAs -- the threshold sample -- are spread evenly over the set
+    const bool fused = !PAIR && TM == 1 && a.mode == 3;
+    const uint32_t g_begin = fused ? (uint32_t)((unsigned long long)worker * ngroups / nworkers) : worker;
+    const uint32_t g_step = fused ? 1u : nworkers;
+    const uint32_t g_count = fused ? (uint32_t)((unsigned long long)(worker + 1) * ngroups / nworkers) - g_begin
+                                   : (ngroups > worker ? (ngroups - worker + nworkers - 1) / nworkers : 0u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < Cfg::kBuf; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], (PAIR ? 2 : 1) * kEpiWarps);  // a pair: both CTAs' epilogue warps release the leader's accumulator
         }
@@ -306,7 +356,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     }
     // everything above is CTA-local set-up and overlaps the previous kernel; below, its results are read
     pdl_wait();
-    if (a.mode != 0 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
+    if (a.mode != 0 && a.mode != 3 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
     for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
         float th = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
         if (EB == 1) {
@@ -332,7 +382,8 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0, segi = 0;
-            for (uint32_t g = worker; g < ngroups; g += nworkers) {
+            for (uint32_t itp = 0; itp < g_count; ++itp) {
+                const uint32_t g = g_begin + itp * g_step;
                 int slab_row[TM];
 #pragma unroll
                 for (int j = 0; j < TM; ++j) {
@@ -372,7 +423,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             constexpr uint32_t idesc = instr_desc<EB>(PAIR ? 2 * kTileRows : kTileRows, NQ);
             int s = 0;
             uint32_t ph = 0, it = 0;
-            for (uint32_t g = worker; g < ngroups; g += nworkers, ++it) {
+            for (; it < g_count; ++it) {
                 const uint32_t buf = it % Cfg::kBuf;
                 mbar_wait(&tempty[buf], ((it / Cfg::kBuf) & 1) ^ 1);
                 tc_fence_after();
@@ -409,10 +460,16 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         constexpr int kColsPerWarp = NQ / (kEpiWarps / 4);
         const int col_first = ((warp - 2) >> 2) * kColsPerWarp;
         uint32_t it = 0, segi = 0;
-        for (uint32_t g = worker; g < ngroups; g += nworkers, ++it) {
+        for (; it < g_count; ++it) {
+            const uint32_t g = g_begin + it * g_step;
             const uint32_t buf = it % Cfg::kBuf;
             mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
             tc_fence_after();
+            // FUSED: the first tile is read twice -- tile maxima for the threshold, then the COLLECT pass
+            const int npass = (fused && it == 0) ? 2 : 1;
+#pragma unroll 1
+            for (int pass_i = 0; pass_i < npass; ++pass_i) {
+            const int mode = fused ? (pass_i + 1 < npass ? 1 : 0) : a.mode;
 #pragma unroll 1
             for (int j = 0; j < TM; ++j) {
                 const uint32_t i = PAIR ? g * 2 + cta_rank : g * TM + j;
@@ -435,7 +492,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     uint32_t r[Cfg::kChunk];
                     tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + c0, r);
                     tmem_ld_wait();
-                    if (a.mode == 0) {
+                    if (mode == 0) {
                         // COLLECT: fixed per-query threshold, atomic append of the rare survivor
                         unsigned pass = 0;
                         const float4 *thr4 = reinterpret_cast<const float4 *>(thr_s + c0);  // 16-byte aligned
@@ -466,7 +523,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                                 if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
                             }
                         }
-                    } else if (a.mode == 1) {
+                    } else if (mode == 1) {
                         // TILEMAX: per query the best score of this tile (threshold estimation sample)
                         float v[Cfg::kChunk];
 #pragma unroll
@@ -500,26 +557,65 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         }
                     }
                 }
-                if (a.mode == 1) {
+                if (mode == 1) {
                     named_bar_sync(2, kEpiThreads);
                     for (int c = threadIdx.x - 64; c < NQ; c += kEpiThreads) {
-                        a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
+                        a.tilemax[(size_t)(fused ? worker : i) * NQ + c] = image_score(tmax_s[c]);
                         tmax_s[c] = 0u;
+                        if (fused && worker == 0) a.cnt[c] = 0u;  // nothing is appended before the grid barrier
                     }
                     named_bar_sync(2, kEpiThreads);
                 }
             }
+            if (fused && pass_i + 1 < npass) {
+                // every CTA has published its tile maxima -> per-query threshold (the sample_m-th largest), all
+                // CTAs compute all of them (NQ <= 32: a few per warp, ~0.5 us each) from the L2-resident table
+                __shared__ int s_ok;
+                __threadfence();
+                named_bar_sync(2, kEpiThreads);
+                if (threadIdx.x == 64) s_ok = grid_barrier(a.sync, nworkers) ? 1 : 0;
+                named_bar_sync(2, kEpiThreads);
+                const bool ok = s_ok != 0;
+                for (int qi = warp - 2; qi < NQ; qi += kEpiWarps) {
+                    unsigned int v[5];  // gridDim.x <= 160 sample tiles
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const uint32_t t = lane + 32 * k;
+                        v[k] = (ok && t < nworkers) ? score_image(__ldcg(a.tilemax + (size_t)t * NQ + qi)) : 0u;
+                    }
+                    unsigned int prefix = 0u;
+                    for (int bit = 31; bit >= 0; --bit) {
+                        const unsigned int cand = prefix | (1u << bit);
+                        int c = 0;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) c += (v[k] >= cand) ? 1 : 0;
+                        c = __reduce_add_sync(0xffffffffu, c);
+                        if (c >= a.sample_m) prefix = cand;
+                    }
+                    if (lane == 0) {
+                        float th = (ok && qi < a.q) ? image_score(prefix) : __int_as_float(0x7f800000);
+                        if (worker == 0) a.thr_out[qi] = th;
+                        if (EB == 1) {
+                            const float qs = qs_s[qi];
+                            th = qs > 0.f ? th / qs : __int_as_float(0x7f800000);
+                        }
+                        thr_s[qi] = th;
+                    }
+                }
+                named_bar_sync(2, kEpiThreads);
+            }
+            }  // pass_i
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (PAIR) mbar_arrive_remote(leader_addr(&tempty[buf])); else mbar_arrive(&tempty[buf]);
             }
-            if (a.mode == 0) {
+            if (a.mode == 0 || fused) {
                 // the accumulator is released; flush the staged survivors when the stage is half full or
                 // this was the CTA's last group (all four epilogue warps take the same branch)
                 named_bar_sync(2, kEpiThreads);
                 const int staged = *stage_n;  // ordered by the named barrier above
-                if (staged >= kAppendStage / 2 || g + nworkers >= ngroups) {
+                if (staged >= kAppendStage / 2 || it + 1 >= g_count) {
                     const int n = staged < kAppendStage ? staged : kAppendStage;
                     for (int e = (int)threadIdx.x - 64; e < n; e += kEpiThreads) {
                         const int qi = stage_q[e];
@@ -532,7 +628,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 }
             }
         }
-        if (a.mode == 0 && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
+        if ((a.mode == 0 || fused) && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
     }
     tc_fence_before();
     if (PAIR) {
@@ -1097,6 +1193,16 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.q_scale = g.d_q_scale;
     a.scales_per_block = (uint32_t)(g.block_size / 512);
     a.block_floats = g.block_size / 4;
+    if (g.mode == kGemmFused) {
+        // one launch: every CTA's first tile is the sample, thresholds are computed behind a grid barrier
+        if (g.nq > 32 || g.d_sync == nullptr || g.d_thr == nullptr || g.sample_m < 1 || (int)g.tile_count < g.sms ||
+            g.sms > 160 || g.tile_stride != 1 || pair)
+            return cudaErrorInvalidValue;
+        a.thr = nullptr;
+        a.thr_out = const_cast<float *>(g.d_thr);
+        a.sync = g.d_sync;
+        a.sample_m = g.sample_m;
+    }
     if (g.tile_count < 1) return cudaSuccess;
     if (eb == 1) return gemm_dispatch<1>(g, tmA, tmB, a, false, stream);
     return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, pair, stream) : gemm_dispatch<4>(g, tmA, tmB, a, false, stream);

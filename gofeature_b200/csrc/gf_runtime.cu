@@ -1533,15 +1533,30 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         if (phase == 1) continue;
         const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call: it sizes d_exact
         mark();
-        g.mode = kGemmTileMax;
+        // small batches on sets where one tile per SM is a big enough sample: sample, thresholds and COLLECT
+        // are ONE launch (each CTA's first tile is the sample; thresholds behind a grid barrier)
+        // Measured: NOT faster (10 queries, int8: fused launch 0.117 ms vs 0.088 + ~0.014 ms for the three; bf16:
+        // 0.170 vs 0.157 + ~0.014 ms) -- the stream stalls behind the barrier about as long as the small sample
+        // launch takes -- so it is opt-in (GF_FUSED_SAMPLE=1) and kept for sets where launch latency dominates.
+        static const bool no_fused = getenv("GF_FUSED_SAMPLE") == nullptr;
+        const bool fuse = !no_fused && nq <= 32 && waves == 1 && G == ctx->sms && total_gtiles >= (uint32_t)ctx->sms &&
+                          ctx->sms <= 160;
         g.tile_first = 0;
-        g.tile_stride = stride;
-        g.tile_count = (uint32_t)G;
-        GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
-        mark();
-        GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
-        mark();
-        g.mode = kGemmCollect;
+        if (!fuse) {
+            g.mode = kGemmTileMax;
+            g.tile_stride = stride;
+            g.tile_count = (uint32_t)G;
+            GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
+            mark();
+            GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
+            mark();
+        } else {
+            mark();
+            mark();
+        }
+        g.mode = fuse ? kGemmFused : kGemmCollect;
+        g.sample_m = m;
+        g.d_sync = (unsigned int *)(T + 16);  // zeroed with the head of the arena, self-resetting
         g.tile_stride = 1;
         g.tile_count = total_gtiles;
         {
@@ -1573,8 +1588,8 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                     GF_ERR_CUDA);
         }
         mark();
-        ctx->stats.gemm_launches += 2;
-        ctx->stats.other_launches += 4 + (all ? 0 : 1);
+        ctx->stats.gemm_launches += fuse ? 1 : 2;
+        ctx->stats.other_launches += (fuse ? 3 : 4) + (all ? 0 : 1);
         ctx->stats.tensor_passes++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
     }
