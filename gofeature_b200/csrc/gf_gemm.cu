@@ -27,10 +27,13 @@ namespace gf {
 
 namespace {
 
+#ifndef GF_GEMM_EPI16_MIN
+#define GF_GEMM_EPI16_MIN 256
+#endif
 // warp 0 producer, warp 1 MMA, then the epilogue warps: 4 (one per TMEM lane quarter) or, from 64 queries up,
 // 8 (two per quarter, each taking half of the query columns) -- one warp per scheduler cannot hide its own
 // tcgen05.ld / compare latency, and at 256 queries the epilogue, not the MMA, bounded the tile time
-__host__ __device__ constexpr int gemm_epi_warps(int nq) { return nq >= 64 ? 8 : 4; }
+__host__ __device__ constexpr int gemm_epi_warps(int nq) { return nq >= GF_GEMM_EPI16_MIN ? 16 : (nq >= 64 ? 8 : 4); }
 __host__ __device__ constexpr int gemm_threads(int nq) { return 64 + 32 * gemm_epi_warps(nq); }
 constexpr int kTileRows = 128;
 constexpr int kABytes = kTileRows * 128;  // one K block = one 128-byte swizzle row per feature row
@@ -263,8 +266,9 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint3
 #ifndef GF_GEMM_STAGES_SMALL
 #define GF_GEMM_STAGES_SMALL 6
 #endif
-constexpr int kAppendStage = 256;
-constexpr int kAppendStageBytes = kAppendStage * 12 + 16;
+constexpr int kAppendStage = 256;                  // entries in all: 16 per epilogue warp (up to 16 warps)
+constexpr int kAppendPerWarp = 16;
+constexpr int kAppendStageBytes = kAppendStage * 12 + 64;
 
 template <int NQ, int TM, bool PAIR = false>
 struct GemmCfg {
@@ -283,14 +287,16 @@ struct GemmCfg {
     static_assert((2 * 11 + 2 * 8) * 8 + 8 <= 312, "barrier region");
     static constexpr int kTmemColsRaw = kBuf * TM * NQ;
     static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
-    static constexpr int kChunk = (NQ >= 32) ? 32 : 16;
+    static constexpr int kColsPerEpiWarp = NQ / (gemm_epi_warps(NQ) / 4);
+    static constexpr int kChunk = kColsPerEpiWarp >= 32 ? 32 : 16;  // columns per tcgen05.ld
+    static_assert(kColsPerEpiWarp % kChunk == 0, "epilogue column split");
     static constexpr size_t kSmem =
         1024 /*align slack*/ + (size_t)kStages * kStageBytes + 320 /*barriers*/ + NQ * 12 + kAppendStageBytes;
     static_assert(kStages >= 2, "pipeline too shallow");
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
 
-template <int NQ, int TM, int EB, bool PAIR>
+template <int NQ, int TM, int EB, bool PAIR, bool FUSED = false>
 __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
 {
@@ -324,7 +330,8 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     const uint32_t nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
     // which groups this worker takes: strided over the workers, or (FUSED) one contiguous chunk, so that the
     // first tiles of the CTAs -- the threshold sample -- are spread evenly over the set
-    const bool fused = !PAIR && TM == 1 && a.mode == 3;
+    static_assert(!FUSED || (!PAIR && TM == 1 && NQ <= 32), "the fused launch: small batches, one tile per step");
+    constexpr bool fused = FUSED;  // (a template parameter: the plain instantiations carry none of its code)
     const uint32_t g_begin = fused ? (uint32_t)((unsigned long long)worker * ngroups / nworkers) : worker;
     const uint32_t g_step = fused ? 1u : nworkers;
     const uint32_t g_count = fused ? (uint32_t)((unsigned long long)(worker + 1) * ngroups / nworkers) - g_begin
@@ -368,7 +375,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         thr_s[i] = th;
         tmax_s[i] = 0u;
     }
-    if (threadIdx.x == 0) *stage_n = 0;
+    if (threadIdx.x < 16) stage_n[threadIdx.x] = 0;
     tc_fence_before();
     if (PAIR)
         cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
@@ -459,12 +466,14 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         // with 8 epilogue warps, warps 2..5 take the lower half of the query columns, warps 6..9 the upper half
         constexpr int kColsPerWarp = NQ / (kEpiWarps / 4);
         const int col_first = ((warp - 2) >> 2) * kColsPerWarp;
+        const int wslot = warp - 2;  // this warp's private append stage
         uint32_t it = 0, segi = 0;
         for (; it < g_count; ++it) {
             const uint32_t g = g_begin + it * g_step;
             const uint32_t buf = it % Cfg::kBuf;
-            mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
-            tc_fence_after();
+            // the wait for the accumulators comes AFTER this tile's segment / slot / row-scale loads have been
+            // issued (the epilogue is the critical path at large batches: their latency hides behind the wait)
+            bool waited = false;
             // FUSED: the first tile is read twice -- tile maxima for the threshold, then the COLLECT pass
             const int npass = (fused && it == 0) ? 2 : 1;
 #pragma unroll 1
@@ -487,6 +496,11 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 auto val = [&](uint32_t bits) -> float {  // accumulator -> score (int8: still without the query's scale)
                     return EB == 1 ? __int2float_rn((int)bits) * rs : __uint_as_float(bits);
                 };
+                if (!waited) {
+                    mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
+                    tc_fence_after();
+                    waited = true;
+                }
 #pragma unroll 1
                 for (int c0 = col_first; c0 < col_first + kColsPerWarp; c0 += Cfg::kChunk) {
                     uint32_t r[Cfg::kChunk];
@@ -494,30 +508,39 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     tmem_ld_wait();
                     if (mode == 0) {
                         // COLLECT: fixed per-query threshold, atomic append of the rare survivor
+                        // score > threshold  <=>  sign of (threshold - score); the sign bits are shifted into
+                        // `pass` one per score (column jj ends up in bit kChunk-1-jj): 3 instructions per score
+                        // (I2F, FFMA, SHF) for int8, 2 (FADD, SHF) for float accumulators
                         unsigned pass = 0;
                         const float4 *thr4 = reinterpret_cast<const float4 *>(thr_s + c0);  // 16-byte aligned
+                        auto below = [&](uint32_t bits, float th) -> uint32_t {
+                            const float t = EB == 1 ? __fmaf_rn(-__int2float_rn((int)bits), rs, th)
+                                                    : __fadd_rn(th, -__uint_as_float(bits));
+                            return __float_as_uint(t);
+                        };
 #pragma unroll
                         for (int jj = 0; jj < Cfg::kChunk; jj += 4) {
                             const float4 th = thr4[jj >> 2];
-                            pass |= (val(r[jj + 0]) > th.x) ? (1u << (jj + 0)) : 0u;
-                            pass |= (val(r[jj + 1]) > th.y) ? (1u << (jj + 1)) : 0u;
-                            pass |= (val(r[jj + 2]) > th.z) ? (1u << (jj + 2)) : 0u;
-                            pass |= (val(r[jj + 3]) > th.w) ? (1u << (jj + 3)) : 0u;
+                            pass = __funnelshift_l(below(r[jj + 0], th.x), pass, 1);
+                            pass = __funnelshift_l(below(r[jj + 1], th.y), pass, 1);
+                            pass = __funnelshift_l(below(r[jj + 2], th.z), pass, 1);
+                            pass = __funnelshift_l(below(r[jj + 3], th.w), pass, 1);
                         }
                         if (!live) pass = 0;
                         while (pass) {
-                            const int b = __ffs(pass) - 1;
+                            const int bit = __ffs(pass) - 1;
                             pass &= pass - 1;
+                            const int b = Cfg::kChunk - 1 - bit;
                             float sc = 0.f;
 #pragma unroll
                             for (int jj = 0; jj < Cfg::kChunk; ++jj)
                                 if (jj == b) sc = val(r[jj]);
                             const int qi = c0 + b;
                             if (EB == 1) sc *= qs_s[qi];
-                            const int sp = atomicAdd(stage_n, 1);
-                            if (sp < kAppendStage) {
-                                stage_key[sp] = make_key(sc, slot);
-                                stage_q[sp] = qi;
+                            const int sp = atomicAdd(&stage_n[wslot], 1);
+                            if (sp < kAppendPerWarp) {
+                                stage_key[wslot * kAppendPerWarp + sp] = make_key(sc, slot);
+                                stage_q[wslot * kAppendPerWarp + sp] = qi;
                             } else {  // stage full (a burst of survivors): append directly
                                 const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
                                 if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
@@ -605,26 +628,30 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 named_bar_sync(2, kEpiThreads);
             }
             }  // pass_i
+            if (!waited) {  // (only a shadow tile of an odd tail gets here without having waited)
+                mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
+                tc_fence_after();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (PAIR) mbar_arrive_remote(leader_addr(&tempty[buf])); else mbar_arrive(&tempty[buf]);
             }
             if (a.mode == 0 || fused) {
-                // the accumulator is released; flush the staged survivors when the stage is half full or
-                // this was the CTA's last group (all four epilogue warps take the same branch)
-                named_bar_sync(2, kEpiThreads);
-                const int staged = *stage_n;  // ordered by the named barrier above
-                if (staged >= kAppendStage / 2 || it + 1 >= g_count) {
-                    const int n = staged < kAppendStage ? staged : kAppendStage;
-                    for (int e = (int)threadIdx.x - 64; e < n; e += kEpiThreads) {
-                        const int qi = stage_q[e];
+                // the accumulator is released; each warp flushes ITS staged survivors when its stage is half
+                // full or this was the CTA's last group -- no barrier between the epilogue warps
+                __syncwarp();
+                const int staged = stage_n[wslot];
+                if (staged >= kAppendPerWarp / 2 || it + 1 >= g_count) {
+                    const int n = staged < kAppendPerWarp ? staged : kAppendPerWarp;
+                    if (lane < n) {
+                        const int qi = stage_q[wslot * kAppendPerWarp + lane];
                         const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
-                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = stage_key[e];
+                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = stage_key[wslot * kAppendPerWarp + lane];
                     }
-                    named_bar_sync(2, kEpiThreads);
-                    if (threadIdx.x == 64) *stage_n = 0;
-                    named_bar_sync(2, kEpiThreads);
+                    __syncwarp();
+                    if (lane == 0) stage_n[wslot] = 0;
+                    __syncwarp();
                 }
             }
         }
@@ -1080,6 +1107,17 @@ cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Ge
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
     const int grid = sms < (int)ngroups ? sms : (int)ngroups;
     if (grid < 1) return cudaSuccess;
+    if (a.mode == kGemmFused) {
+        if constexpr (NQ <= 32 && TM == 1) {
+            e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)Cfg::kSmem);
+            if (e != cudaSuccess) return e;
+            return launch_chain(gemm_kernel<NQ, TM, EB, false, true>, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem,
+                                stream, tmA, tmB, a);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     return launch_chain(gemm_kernel<NQ, TM, EB, false>, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem, stream, tmA, tmB, a);
 }
 

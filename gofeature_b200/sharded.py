@@ -268,11 +268,12 @@ class ShardedSet:
         t = self._tensors(q, limit)
         stream = torch.cuda.current_stream().cuda_stream
         L = api.lib()
+        if self.world == 1:   # the local flags are the merged flags
+            api._check(L.gf_set_search_device_ex(self.local._h, limit, q, dq.data_ptr(), t["local"].data_ptr(),
+                                                 t["mflags"].data_ptr(), path, stream))
+            return t["local"]
         api._check(L.gf_set_search_device_ex(self.local._h, limit, q, dq.data_ptr(), t["local"].data_ptr(),
                                              t["lflags"].data_ptr(), path, stream))
-        if self.world == 1:
-            t["mflags"].copy_(t["lflags"], non_blocking=True)
-            return t["local"]
         if self._xchg is not None and q <= self._x_max_q and limit <= self._x_max_k:
             # push my winners into every peer's inbox, wait for theirs, merge: one kernel
             api._check(L.gf_exchange_merge_device(self._xchg, q, limit, t["local"].data_ptr(), t["lflags"].data_ptr(),

@@ -1,6 +1,6 @@
 """Small driver for the ncu capture of the tcgen05 COLLECT pass at a large batch (256 queries, 1 M x 512, top-10).
     python profiles/prof_gemm.py > gpurun_out/plain.log 2>&1 &&
-    ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 6 -c 2 -o gpurun_out/prof_gemm256 python profiles/prof_gemm.py
+    ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 6 -c 2 -o gpurun_out/prof_gemm256 python profiles/prof_gemm.py
 """
 import os
 import sys
