@@ -28,7 +28,7 @@ namespace gf {
 namespace {
 
 #ifndef GF_GEMM_EPI16_MIN
-#define GF_GEMM_EPI16_MIN 256
+#define GF_GEMM_EPI16_MIN 128
 #endif
 // warp 0 producer, warp 1 MMA, then the epilogue warps: 4 (one per TMEM lane quarter) or, from 64 queries up,
 // 8 (two per quarter, each taking half of the query columns) -- one warp per scheduler cannot hide its own
