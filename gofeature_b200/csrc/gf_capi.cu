@@ -956,7 +956,7 @@ int gf_set_add_synthetic(gf_set *set, int64_t n, uint64_t seed, int64_t first_or
 
 int gf_set_set_search_path(gf_set *set, int path)
 {
-    if (!set || path < 0 || path > 3) return GF_ERR_INVALID_ARGUMENT;
+    if (!set || path < 0 || path > 5) return GF_ERR_INVALID_ARGUMENT;
     set->search_path = path;
     return GF_OK;
 }

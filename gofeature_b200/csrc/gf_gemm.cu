@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "gf_device.cuh"
@@ -69,6 +70,11 @@ struct GemmArgs {
     float *thr_out;               // [nq] thresholds written by CTA 0 (finalize's certificate reads them)
     unsigned int *sync;           // [0] arrival count, [1] generation, [2] sticky "a barrier timed out"
     int sample_m;                 // threshold = sample_m-th largest of the gridDim.x tile maxima
+    // GROUPTOP mode (4): best two keys of every 32-row group + histogram of the best one
+    uint2 *gtop;                  // [nq][groups]
+    unsigned int *hist;           // [nq][kGtBins]
+    uint32_t groups;              // 4 * tile_count
+    uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment
 };
 
 // All CTAs of the grid are co-resident (grid <= SMs, one CTA per SM fits by construction), so a counter +
@@ -242,14 +248,49 @@ __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// which segment holds 128-row tile t; `segi` only moves forward (tiles of a CTA ascend)
-__device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, uint32_t &segi, uint32_t &row0,
-                                            uint32_t &valid)
+// The segment a worker is in, held in registers: a worker's tiles ascend, and with the contiguous tile ranges of
+// the full passes a segment lasts for ~50 tiles, so the dependent metadata loads (tile prefix -> segment -> row
+// scale) leave the per-tile critical path.
+struct SegCursor {
+    uint32_t segi = 0, t_begin = 0, t_end = 0;  // tiles [t_begin, t_end) belong to segment segi; t_end == 0: not loaded
+    uint32_t rows = 0, slot_base = 0;
+    long long slab_row0 = 0;                    // row of the slab the segment starts at (TMA coordinate)
+    size_t scale_base = 0;                      // int8: index of the segment's first row scale
+};
+__device__ __forceinline__ void seek_tile(const GemmArgs &a, SegCursor &c, uint32_t t)
 {
-    while (segi + 1 < (uint32_t)a.nseg && t >= a.gtile_start[segi + 1]) ++segi;
-    row0 = (t - a.gtile_start[segi]) * kTileRows;
-    uint32_t rows = a.segs[segi].rows;
-    valid = rows - row0 < (uint32_t)kTileRows ? rows - row0 : (uint32_t)kTileRows;
+    if (t < c.t_end) return;
+    const uint32_t last = (uint32_t)a.nseg - 1u;
+    uint32_t s = c.t_end == 0u ? 0u : c.segi + 1u;  // the next segment, usually
+    if (s > last) s = last;
+    if (!(a.gtile_start[s] <= t && (s == last || t < a.gtile_start[s + 1]))) {
+        // a jump (a worker's first tile, or a strided sample): blocks fill in order, so tile / tiles-per-block is
+        // the segment unless earlier blocks are partial -- verify, else binary search
+        s = t / a.tiles_per_block;
+        if (s > last) s = last;
+        if (!(a.gtile_start[s] <= t && (s == last || t < a.gtile_start[s + 1]))) {
+            uint32_t lo = 0, hi = last;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (a.gtile_start[mid] <= t) lo = mid; else hi = mid - 1;
+            }
+            s = lo;
+        }
+    }
+    c.segi = s;
+    c.t_begin = a.gtile_start[s];
+    c.t_end = s == last ? 0xFFFFFFFFu : a.gtile_start[s + 1];
+    const Segment sg = a.segs[s];
+    c.rows = sg.rows;
+    c.slot_base = sg.slot_base;
+    c.slab_row0 = (long long)((sg.base - a.slab_base) / a.dims);
+    c.scale_base = a.row_scales != nullptr ? (size_t)((sg.base - a.slab_base) / a.block_floats) * a.scales_per_block : 0;
+}
+__device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, SegCursor &c, uint32_t &row0, uint32_t &valid)
+{
+    seek_tile(a, c, t);
+    row0 = (t - c.t_begin) * kTileRows;
+    valid = c.rows - row0 < (uint32_t)kTileRows ? c.rows - row0 : (uint32_t)kTileRows;
 }
 
 // TM = feature-row tiles that share one load of the query operand.  The ring can only hold ~190 KB of
@@ -332,10 +373,13 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     // first tiles of the CTAs -- the threshold sample -- are spread evenly over the set
     static_assert(!FUSED || (!PAIR && TM == 1 && NQ <= 32), "the fused launch: small batches, one tile per step");
     constexpr bool fused = FUSED;  // (a template parameter: the plain instantiations carry none of its code)
-    const uint32_t g_begin = fused ? (uint32_t)((unsigned long long)worker * ngroups / nworkers) : worker;
-    const uint32_t g_step = fused ? 1u : nworkers;
-    const uint32_t g_count = fused ? (uint32_t)((unsigned long long)(worker + 1) * ngroups / nworkers) - g_begin
-                                   : (ngroups > worker ? (ngroups - worker + nworkers - 1) / nworkers : 0u);
+    // the full passes (COLLECT, GROUPTOP: every tile, stride 1) give each worker ONE contiguous range of tiles too: a
+    // worker then stays inside a segment for ~50 tiles instead of changing segment with every tile
+    const bool chunked = fused || (a.tile_stride == 1u && (a.mode == 0 || a.mode == 4));
+    const uint32_t g_begin = chunked ? (uint32_t)((unsigned long long)worker * ngroups / nworkers) : worker;
+    const uint32_t g_step = chunked ? 1u : nworkers;
+    const uint32_t g_count = chunked ? (uint32_t)((unsigned long long)(worker + 1) * ngroups / nworkers) - g_begin
+                                     : (ngroups > worker ? (ngroups - worker + nworkers - 1) / nworkers : 0u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
@@ -363,7 +407,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     }
     // everything above is CTA-local set-up and overlaps the previous kernel; below, its results are read
     pdl_wait();
-    if (a.mode != 0 && a.mode != 3 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
+    if (a.mode != 0 && a.mode != 3 && a.mode != 4 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
     for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
         float th = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
         if (EB == 1) {
@@ -388,7 +432,8 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0;
-            uint32_t ph = 0, segi = 0;
+            uint32_t ph = 0;
+            SegCursor segc;
             for (uint32_t itp = 0; itp < g_count; ++itp) {
                 const uint32_t g = g_begin + itp * g_step;
                 int slab_row[TM];
@@ -398,8 +443,8 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     if (i >= a.tile_count) i = a.tile_count - 1;  // odd tail: shadow the last tile
                     const uint32_t t = a.tile_first + i * a.tile_stride;
                     uint32_t row0, valid;
-                    locate_tile(a, t, segi, row0, valid);
-                    slab_row[j] = (int)((a.segs[segi].base - a.slab_base) / a.dims) + (int)row0;
+                    locate_tile(a, t, segc, row0, valid);
+                    slab_row[j] = (int)segc.slab_row0 + (int)row0;
                 }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
@@ -467,13 +512,30 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         constexpr int kColsPerWarp = NQ / (kEpiWarps / 4);
         const int col_first = ((warp - 2) >> 2) * kColsPerWarp;
         const int wslot = warp - 2;  // this warp's private append stage
-        uint32_t it = 0, segi = 0;
+        uint32_t it = 0;
+        SegCursor segc;
+        // int8: a row's dequantisation scale comes from a 4-bytes-per-row array that streams from DRAM; loaded when
+        // its tile starts, that ~1 us latency sat on the epilogue's critical path once per tile (measured: the pass
+        // went from HBM-bound to epilogue-bound as soon as the per-tile work grew).  It is loaded ONE TILE AHEAD.
+        constexpr bool kPrefRs = EB == 1 && TM == 1 && !PAIR && !FUSED;
+        // (the cursor moves on to the next tile's segment here; this tile's row0 / valid / slot are taken before)
+        auto load_rs = [&](uint32_t it_) -> float {
+            if (it_ >= g_count) return 1.f;
+            const uint32_t i_ = g_begin + it_ * g_step;
+            if (i_ >= a.tile_count) return 1.f;
+            uint32_t row0_, valid_;
+            locate_tile(a, a.tile_first + i_ * a.tile_stride, segc, row0_, valid_);
+            if (row >= valid_) return 1.f;
+            return a.row_scales[segc.scale_base + row0_ + row];
+        };
+        float rs_pref = 1.f;
+        if (kPrefRs) rs_pref = load_rs(0);
         for (; it < g_count; ++it) {
             const uint32_t g = g_begin + it * g_step;
             const uint32_t buf = it % Cfg::kBuf;
             // the wait for the accumulators comes AFTER this tile's segment / slot / row-scale loads have been
             // issued (the epilogue is the critical path at large batches: their latency hides behind the wait)
-            bool waited = false;
+            bool waited = false, released = false;
             // FUSED: the first tile is read twice -- tile maxima for the threshold, then the COLLECT pass
             const int npass = (fused && it == 0) ? 2 : 1;
 #pragma unroll 1
@@ -485,14 +547,17 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 if (i >= a.tile_count) break;  // shadow tile of an odd tail: nothing to report
                 const uint32_t t = a.tile_first + i * a.tile_stride;
                 uint32_t row0, valid;
-                locate_tile(a, t, segi, row0, valid);
+                locate_tile(a, t, segc, row0, valid);
                 const bool live = row < valid;
-                const uint32_t slot = a.segs[segi].slot_base + row0 + row;
+                const uint32_t slot = segc.slot_base + row0 + row;
                 const uint32_t acc_col = buf * (TM * NQ) + j * NQ;
                 float rs = 1.f;  // int8 path: this row's dequantisation scale (a segment is one slab block)
-                if (EB == 1 && live)
-                    rs = a.row_scales[(size_t)((a.segs[segi].base - a.slab_base) / a.block_floats) * a.scales_per_block +
-                                      row0 + row];
+                if (kPrefRs) {
+                    rs = rs_pref;
+                    rs_pref = load_rs(it + 1);  // in flight across the wait below and this tile's work
+                } else if (EB == 1 && live) {
+                    rs = a.row_scales[segc.scale_base + row0 + row];
+                }
                 auto val = [&](uint32_t bits) -> float {  // accumulator -> score (int8: still without the query's scale)
                     return EB == 1 ? __int2float_rn((int)bits) * rs : __uint_as_float(bits);
                 };
@@ -569,6 +634,60 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         for (; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
                         const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
                         if (Cfg::kChunk == 32 || (lane & 1) == 0) atomicMax(&tmax_s[col], score_image(m));
+                    } else if (mode == 4) {
+                        if constexpr (NQ <= kGtMaxQ && TM == 1 && !PAIR) {
+                            // the scores are in registers (one chunk holds all NQ columns): release the accumulator
+                            // NOW -- an arrive (release) issued after the global store / histogram atomic below
+                            // would wait for their acknowledgement, an L2 round trip per tile
+                            static_assert(Cfg::kChunk == kColsPerWarp, "GROUPTOP: one chunk per warp");
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[buf]);
+                            released = true;
+                            // GROUPTOP: per query the best TWO keys of this warp's 32 rows.  key = score image with
+                            // its low 5 bits replaced by the lane (the row inside the group): max() carries the
+                            // argmax along, and a hidden row's image is <= (second key | 31).  Transposed
+                            // top-2 reduce: at each step a lane hands half of its columns to its partner.
+                            uint32_t k1[Cfg::kChunk], k2[Cfg::kChunk];
+#pragma unroll
+                            for (int jj = 0; jj < Cfg::kChunk; ++jj) {
+                                // branch-free orderable image (-0.0 sorts just below +0.0, NaN on top: approximate
+                                // keys only select candidates, a NaN never passes the certificate)
+                                const uint32_t u = __float_as_uint(val(r[jj]));
+                                const uint32_t im = u ^ ((uint32_t)((int)u >> 31) | 0x80000000u);
+                                k1[jj] = live ? ((im & ~31u) | (uint32_t)lane) : 0u;
+                                k2[jj] = 0u;
+                            }
+                            int off = 16;
+#pragma unroll
+                            for (int n = Cfg::kChunk; n > 1; n >>= 1) {
+                                const bool up = (lane & off) != 0;
+#pragma unroll
+                                for (int k = 0; k < n / 2; ++k) {
+                                    const uint32_t s1 = up ? k1[k] : k1[k + n / 2], s2 = up ? k2[k] : k2[k + n / 2];
+                                    const uint32_t m1 = up ? k1[k + n / 2] : k1[k], m2 = up ? k2[k + n / 2] : k2[k];
+                                    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, s1, off);
+                                    // (the first step exchanges single keys: every second key is still 0)
+                                    const uint32_t r2 = n == Cfg::kChunk ? 0u : __shfl_xor_sync(0xffffffffu, s2, off);
+                                    k1[k] = max(m1, r1);
+                                    k2[k] = max(min(m1, r1), max(m2, r2));
+                                }
+                                off >>= 1;
+                            }
+                            uint32_t b1 = k1[0], b2 = k2[0];
+                            for (; off >= 1; off >>= 1) {  // 16 columns: lanes l and l ^ 1 hold halves of the same column
+                                const uint32_t r1 = __shfl_xor_sync(0xffffffffu, b1, off);
+                                const uint32_t r2 = __shfl_xor_sync(0xffffffffu, b2, off);
+                                const uint32_t hi = max(b1, r1);
+                                b2 = max(min(b1, r1), max(b2, r2));
+                                b1 = hi;
+                            }
+                            const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
+                            if ((Cfg::kChunk == 32 || (lane & 1) == 0) && col < a.q) {
+                                a.gtop[(size_t)col * a.groups + (size_t)i * 4 + quarter] = make_uint2(b1, b2);
+                                atomicAdd(&a.hist[(size_t)col * kGtBins + (b1 >> 20)], 1u);
+                            }
+                        }
                     } else {
                         // DUMP: every score, coalesced over rows (small sets and diagnostics)
                         if (live) {
@@ -634,7 +753,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !released) {
                 if (PAIR) mbar_arrive_remote(leader_addr(&tempty[buf])); else mbar_arrive(&tempty[buf]);
             }
             if (a.mode == 0 || fused) {
@@ -655,7 +774,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 }
             }
         }
-        if ((a.mode == 0 || fused) && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
+        if ((a.mode == 0 || a.mode == 4 || fused) && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
     }
     tc_fence_before();
     if (PAIR) {
@@ -680,11 +799,17 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
 __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
                                     int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2,
                                     float *__restrict__ copy, void *__restrict__ dst_sh, int sh_eb,
-                                    float *__restrict__ qres2, float *__restrict__ q_scale)
+                                    float *__restrict__ qres2, float *__restrict__ q_scale,
+                                    unsigned int *__restrict__ gt_hist, unsigned int *__restrict__ gt_state)
 {
     pdl_wait();  // the previous call's kernels may still be reading dst / dst_sh
     pdl_launch_dependents();
     const int qi = blockIdx.x;
+    if (gt_hist != nullptr) {  // the one-pass path's histogram and per-query state start every call at zero
+        uint4 *h4 = reinterpret_cast<uint4 *>(gt_hist + (size_t)qi * kGtBins);
+        for (int e = threadIdx.x; e < kGtBins / 4; e += blockDim.x) h4[e] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < kGtStateWords) gt_state[qi * kGtStateWords + threadIdx.x] = 0u;
+    }
     __shared__ float red[32], red2[32];
     __shared__ float s_scale;
     float acc = 0.f, res = 0.f, amax = 0.f;
@@ -799,34 +924,10 @@ __global__ void threshold_kernel(const float *__restrict__ tilemax, int ntiles, 
     }
 }
 
-// candidates (approx keys) -> for the best `kp` of each query: exact canonical score of the row.
-// d_sel [q][kp] approx keys (descending, zero padded) in; d_exact [q][kp] exact keys out.
-__global__ void __launch_bounds__(256)
-    rescore_kernel(const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_slot_base, int nseg, int dims,
-                   const unsigned int *__restrict__ d_cnt, const float *__restrict__ queries, int kp,
-                   const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact)
+// <row, query> in the canonical float32 order (oracle/gf_oracle.c: four strided partial sums per lane, then
+// canonical_reduce); every lane of the warp returns the score
+__device__ __forceinline__ float exact_dot(const float *__restrict__ x, const float *__restrict__ qv, int dims, int lane)
 {
-    pdl_wait();
-    pdl_launch_dependents();
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int qi = blockIdx.y;
-    if (w >= kp) return;
-    if (d_cnt != nullptr && (unsigned)w >= d_cnt[qi]) return;  // unsorted candidate buffer: only cnt entries are valid
-    const unsigned long long key = d_sel[(size_t)qi * kp + w];
-    if (key == 0ull) {
-        if (lane == 0) d_exact[(size_t)qi * kp + w] = 0ull;
-        return;
-    }
-    const uint32_t slot = key_slot(key);
-    // segment whose slot range holds this slot: slot_base values ascend with the segment index
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (seg_slot_base[mid] <= slot) lo = mid; else hi = mid - 1;
-    }
-    const float *x = segs[lo].base + (size_t)(slot - seg_slot_base[lo]) * dims;
-    const float *qv = queries + (size_t)qi * dims;
     float p[4] = {0.f, 0.f, 0.f, 0.f};
     if ((dims & 511) == 0) {
         // the tensor path's rows are 16-byte aligned: four 128-bit loads per operand in flight at once
@@ -854,7 +955,36 @@ __global__ void __launch_bounds__(256)
             }
         }
     }
-    const float sc = canonical_reduce(p[0], p[1], p[2], p[3]);
+    return canonical_reduce(p[0], p[1], p[2], p[3]);
+}
+
+// candidates (approx keys) -> for the best `kp` of each query: exact canonical score of the row.
+// d_sel [q][kp] approx keys (descending, zero padded) in; d_exact [q][kp] exact keys out.
+__global__ void __launch_bounds__(256)
+    rescore_kernel(const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_slot_base, int nseg, int dims,
+                   const unsigned int *__restrict__ d_cnt, const float *__restrict__ queries, int kp,
+                   const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int qi = blockIdx.y;
+    if (w >= kp) return;
+    if (d_cnt != nullptr && (unsigned)w >= d_cnt[qi]) return;  // unsorted candidate buffer: only cnt entries are valid
+    const unsigned long long key = d_sel[(size_t)qi * kp + w];
+    if (key == 0ull) {
+        if (lane == 0) d_exact[(size_t)qi * kp + w] = 0ull;
+        return;
+    }
+    const uint32_t slot = key_slot(key);
+    // segment whose slot range holds this slot: slot_base values ascend with the segment index
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (seg_slot_base[mid] <= slot) lo = mid; else hi = mid - 1;
+    }
+    const float sc = exact_dot(segs[lo].base + (size_t)(slot - seg_slot_base[lo]) * dims, queries + (size_t)qi * dims, dims, lane);
     if (lane == 0) d_exact[(size_t)qi * kp + w] = make_key(sc, slot);
 }
 
@@ -1062,6 +1192,295 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < kp; i += blockDim.x) d_sel[(size_t)qi * kp + i] = buf[i];
 }
 
+
+// ------------------------------------------------------------------ one-pass path: the tail
+// |approx - exact| bound of the candidate pass (the same bound finalize_kernel certifies with)
+__device__ __forceinline__ float cert_delta(int qi, const float *qnorm2, const unsigned int *maxnorm2_bits, float err_coeff,
+                                            const float *qres2, const unsigned int *maxres2_bits)
+{
+    const float mn = sqrtf(__uint_as_float(__ldcg(maxnorm2_bits))), qn = sqrtf(__ldcg(qnorm2 + qi));
+    float delta = err_coeff * mn * qn;
+    if (qres2 != nullptr) {
+        const float qr = sqrtf(__ldcg(qres2 + qi));
+        delta += sqrtf(__uint_as_float(__ldcg(maxres2_bits))) * (qn + qr) * 1.0001f + mn * qr + 1e-30f * (1.f + qn);
+    }
+    return delta;
+}
+
+// group index (4 per 128-row tile of the set-wide tile order) + row inside the group -> the row and its slot
+__device__ __forceinline__ bool gt_locate(const GtTail &a, uint32_t group, uint32_t lane_row, const float **x, uint32_t *slot)
+{
+    const uint32_t tile = group >> 2;
+    // blocks are filled in order, so nearly every segment holds tiles_per_block tiles: guess, verify with two
+    // independent loads, and only search when the guess is off (a binary search is 6+ DEPENDENT loads)
+    int lo = (int)(tile / a.tiles_per_block);
+    if (lo > a.nseg - 1) lo = a.nseg - 1;
+    const uint32_t s0 = a.d_gtile_start[lo], s1 = a.d_gtile_start[lo + 1];
+    if (!(s0 <= tile && tile < s1)) {
+        int hi = a.nseg - 1;
+        lo = 0;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (a.d_gtile_start[mid] <= tile) lo = mid; else hi = mid - 1;
+        }
+    }
+    const uint32_t row = (tile - a.d_gtile_start[lo]) * (uint32_t)kTileRows + (group & 3u) * 32u + lane_row;
+    if (row >= a.d_segs[lo].rows) return false;
+    *x = a.d_segs[lo].base + (size_t)row * a.dims;
+    *slot = a.d_segs[lo].slot_base + row;
+    return true;
+}
+
+// grid (ctas per query, q), 256 threads.
+//   A  every CTA: cut = the histogram bin holding the kp-th best group of its query (suffix scan of 4096 bins)
+//   B  its share of the groups: best key at or above the cut -> candidate, else -> running max (ceiling 1)
+//   C  a warp per candidate: exact canonical score of the group's best row -> d_exact, (second key, group) -> d_c2
+//   D  last CTA of the query (ticket): rank the exact keys, emit the best K; a group whose SECOND key could still
+//      reach the K-th score has all its rows re-scored (the third-best row of a group is only known to be below
+//      the second key); certificate: K-th exact score > every approximate ceiling + delta.
+__global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
+{
+    __shared__ unsigned long long s_keys[kGtCap];  // phase B/C: [0, kGtCap) uint32 candidates | second keys behind them
+    __shared__ uint2 s_c2[kGtCap];
+    __shared__ int s_wsum[8];
+    __shared__ int s_cut, s_n, s_nexp;
+    __shared__ unsigned int s_ncmax, s_ticket;
+    __shared__ unsigned long long s_kth;
+    __shared__ uint32_t s_exp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qi = blockIdx.y;
+    unsigned long long tm[10];
+    int tmi = 0;
+#define GT_TICK() do { if (a.dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tm[tmi++] = t_; } } while (0)
+    GT_TICK();
+    if (tid == 0) {
+        s_cut = 0;
+        s_n = 0;
+        s_ncmax = 0u;
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    GT_TICK();
+    unsigned int *state = a.d_state + (size_t)qi * kGtStateWords;
+    // this CTA's share of the groups; the first kGtPre entries per thread are loaded NOW, next to the histogram, so
+    // that the two L2 round trips overlap
+    constexpr int kGtPre = 6;
+    const uint32_t per = (a.groups + gridDim.x - 1) / gridDim.x;
+    const uint32_t e0 = blockIdx.x * per;
+    const uint32_t e1 = e0 + per < a.groups ? e0 + per : a.groups;
+    const uint2 *gt = a.d_gtop + (size_t)qi * a.groups;
+    uint2 pre[kGtPre];
+#pragma unroll
+    for (int u = 0; u < kGtPre; ++u) {
+        const uint32_t e = e0 + tid + 256u * u;
+        pre[u] = e < e1 ? __ldcg(gt + e) : make_uint2(0u, 0u);
+    }
+    // ---- A: thread t owns bins 4095 - 16 t .. 4080 - 16 t (descending)
+    {
+        const unsigned int *h = a.d_hist + (size_t)qi * kGtBins;
+        const int top = kGtBins - 1 - 16 * tid;
+        int c[16], local = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(h + top - 15) + u);
+            c[15 - 4 * u] = (int)w.x;
+            c[14 - 4 * u] = (int)w.y;
+            c[13 - 4 * u] = (int)w.z;
+            c[12 - 4 * u] = (int)w.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) local += c[j];
+        int incl = local;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_wsum[w];
+        incl += before;
+        const int excl = incl - local;
+        if (excl < a.kp && incl >= a.kp) {
+            int run = excl, bin = top;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (run < a.kp && run + c[j] >= a.kp) bin = top - j;
+                run += c[j];
+            }
+            s_cut = bin;
+        }
+        __syncthreads();
+    }
+    GT_TICK();
+    const unsigned int cutimg = (unsigned int)s_cut << 20;
+    uint32_t *s_e = reinterpret_cast<uint32_t *>(s_keys);
+    uint32_t *s_k2 = s_e + kGtCap;
+    // ---- B
+    {
+        unsigned int ncmax = 0u;
+        auto classify = [&](uint32_t e, uint2 v) {
+            if (v.x >= cutimg && v.x != 0u && cutimg != 0u) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < kGtCap) {
+                    s_e[pos] = (e << 5) | (v.x & 31u);
+                    s_k2[pos] = v.y;
+                }
+            } else {
+                ncmax = max(ncmax, v.x);
+            }
+        };
+#pragma unroll
+        for (int u = 0; u < kGtPre; ++u) {
+            const uint32_t e = e0 + tid + 256u * u;
+            if (e < e1) classify(e, pre[u]);
+        }
+#pragma unroll 4
+        for (uint32_t e = e0 + tid + 256u * kGtPre; e < e1; e += 256) classify(e, __ldcg(gt + e));
+        ncmax = __reduce_max_sync(0xffffffffu, ncmax);
+        if (lane == 0 && ncmax != 0u) atomicMax(&s_ncmax, ncmax);
+        __syncthreads();
+        if (tid == 0) {
+            if (s_ncmax != 0u) atomicMax(&state[2], s_ncmax);
+            if (s_n > kGtCap || cutimg == 0u) atomicOr(&state[3], 1u);
+        }
+    }
+    GT_TICK();
+    // ---- C
+    const float *qv = a.d_queries_padded + (size_t)qi * a.dims;
+    {
+        const int n = s_n < kGtCap ? s_n : kGtCap;
+        // this warp's slots in the query's exact list: ONE reservation, issued before the dot products (its round
+        // trip hides behind their loads)
+        unsigned int gp = 0u;
+        if (lane == 0 && warp < n) gp = atomicAdd(&state[0], (unsigned int)((n - warp + 7) / 8));
+        for (int idx = warp; idx < n; idx += 8, ++gp) {
+            const uint32_t ee = s_e[idx];
+            const float *x;
+            uint32_t slot;
+            const bool found = gt_locate(a, ee >> 5, ee & 31u, &x, &slot);  // (always: a dead row has no key)
+            const float sc = found ? exact_dot(x, qv, a.dims, lane) : 0.f;
+            if (lane == 0 && gp < (unsigned)kGtCap) {
+                a.d_exact[(size_t)qi * kGtCap + gp] = found ? make_key(sc, slot) : 0ull;
+                a.d_c2[(size_t)qi * kGtCap + gp] = make_uint2(found ? s_k2[idx] : 0u, ee);
+            }
+        }
+    }
+    GT_TICK();
+    // ---- D: the last CTA of this query
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&state[1], 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    GT_TICK();
+    // everything the last CTA needs, in ONE round trip: the first 512 slots are loaded whatever the count is
+    // (what lies beyond the count is never looked at)
+    unsigned long long lk[2];
+    uint2 lc[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        lk[u] = __ldcg(a.d_exact + (size_t)qi * kGtCap + tid + 256 * u);
+        lc[u] = __ldcg(a.d_c2 + (size_t)qi * kGtCap + tid + 256 * u);
+    }
+    const unsigned int total = __ldcg(&state[0]);
+    const bool over = __ldcg(&state[3]) != 0u || total > (unsigned)kGtCap;
+    const float qs = a.d_q_scale != nullptr ? __ldcg(a.d_q_scale + qi) : 1.f;
+    const float delta = cert_delta(qi, a.d_qnorm2, a.d_maxnorm2_bits, a.err_coeff, a.d_qres2, a.d_maxres2_bits);
+    int n = (int)(total < (unsigned)kGtCap ? total : (unsigned)kGtCap);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        s_keys[tid + 256 * u] = lk[u];
+        s_c2[tid + 256 * u] = lc[u];
+    }
+    for (int i = tid + 512; i < n; i += 256) {
+        s_keys[i] = __ldcg(a.d_exact + (size_t)qi * kGtCap + i);
+        s_c2[i] = __ldcg(a.d_c2 + (size_t)qi * kGtCap + i);
+    }
+    const long long keff = a.rows_total < a.K ? a.rows_total : a.K;
+    // approximate score a row with key image <= im can reach (the low 5 bits of a key are not score bits)
+    auto reach = [&](unsigned int im) -> float {
+        const float v = image_score(im | 31u) * qs;
+        return v + 4e-6f * fabsf(v);
+    };
+    bool ok = !over;
+    unsigned long long *out = a.d_out + (size_t)qi * a.K;
+    __syncthreads();
+    GT_TICK();
+    for (int round = 0; round < 2; ++round) {
+        if (tid == 0) {
+            s_kth = 0ull;
+            s_nexp = 0;
+        }
+        __syncthreads();
+        // rank of every key among the n exact keys (distinct: one per slot); the best K go straight out
+        for (int i = tid; i < n; i += 256) {
+            const unsigned long long my = s_keys[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += s_keys[j] > my ? 1 : 0;
+            if (rank < a.K) out[rank] = my;
+            if (rank == (int)keff - 1) s_kth = my;
+        }
+        for (int i = n + tid; i < a.K; i += 256) out[i] = 0ull;
+        __syncthreads();
+        const unsigned long long kth = s_kth;
+        if (kth == 0ull) {  // not even K candidates
+            ok = false;
+            break;
+        }
+        const float tk = key_score(kth);
+        // groups whose hidden rows (bounded by the second key) could still reach the K-th score
+        for (int i = tid; i < n; i += 256) {
+            const uint2 c = s_c2[i];
+            if (c.x != 0u && !(tk > reach(c.x) + delta)) {
+                const int pos = atomicAdd(&s_nexp, 1);
+                if (pos < 8) s_exp[pos] = c.y;
+                s_c2[i].x = 0u;  // (re-scored below, or the query is flagged)
+            }
+        }
+        __syncthreads();
+        const int nexp = s_nexp;
+        if (nexp == 0) break;
+        if (round == 1 || nexp > 8 || n + 31 * nexp > kGtCap) {
+            ok = false;
+            break;
+        }
+        // re-score every other row of those groups: a warp per row
+        if (tid == 0) s_n = n;
+        __syncthreads();
+        for (int w = warp; w < nexp * 32; w += 8) {
+            const uint32_t ee = s_exp[w >> 5];
+            const uint32_t lr = (uint32_t)(w & 31);
+            if (lr == (ee & 31u)) continue;  // the group's best row is already there
+            const float *x;
+            uint32_t slot;
+            if (!gt_locate(a, ee >> 5, lr, &x, &slot)) continue;  // beyond the segment's rows
+            const float sc = exact_dot(x, qv, a.dims, lane);
+            if (lane == 0) {
+                const int pos = atomicAdd(&s_n, 1);
+                s_keys[pos] = make_key(sc, slot);
+                s_c2[pos] = make_uint2(0u, 0u);
+            }
+        }
+        __syncthreads();
+        n = s_n;
+        __syncthreads();
+    }
+    GT_TICK();
+    if (a.dbg && tid == 0 && qi == 0)
+        printf("[tail] n=%d launch->wait %llu A %llu B %llu C %llu ticket %llu load %llu rank+cert %llu\n", n, tm[1] - tm[0],
+               tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[6] - tm[5], tm[7] - tm[6]);
+    if (tid == 0) {
+        if (ok) {
+            // rows of groups below the cut: their best key is <= the largest non-candidate key
+            const unsigned int nc = __ldcg(&state[2]);
+            if (nc != 0u && !(key_score(s_kth) > reach(nc) + delta)) ok = false;
+        }
+        a.d_flags[qi] = ok ? 0u : 1u;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1231,6 +1650,18 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.q_scale = g.d_q_scale;
     a.scales_per_block = (uint32_t)(g.block_size / 512);
     a.block_floats = g.block_size / 4;
+    {
+        const long long block_rows = g.block_size / ((long long)g.dims * 4);
+        a.tiles_per_block = (uint32_t)((block_rows + kTileRows - 1) / kTileRows);
+        if (a.tiles_per_block < 1u) a.tiles_per_block = 1u;
+    }
+    if (g.mode == kGemmGroupTop) {
+        if (g.nq > kGtMaxQ || g.d_gtop == nullptr || g.d_hist == nullptr || g.tile_first != 0 || g.tile_stride != 1)
+            return cudaErrorInvalidValue;
+        a.gtop = g.d_gtop;
+        a.hist = g.d_hist;
+        a.groups = 4u * g.tile_count;
+    }
     if (g.mode == kGemmFused) {
         // one launch: every CTA's first tile is the sample, thresholds are computed behind a grid barrier
         if (g.nq > 32 || g.d_sync == nullptr || g.d_thr == nullptr || g.sample_m < 1 || (int)g.tile_count < g.sms ||
@@ -1248,10 +1679,11 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
                                 float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
-                                float *q_scale, cudaStream_t stream)
+                                float *q_scale, cudaStream_t stream, unsigned int *gt_hist, unsigned int *gt_state)
 {
     return launch_chain(prep_queries_kernel, dim3(nq), dim3(128), 0, stream, src, (long long)q_stride,
-                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale);
+                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale,
+                        gt_hist, gt_state);
 }
 
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
@@ -1283,6 +1715,12 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
 {
     if (cap > (unsigned)kGemmCandCap || kp > kGemmCandCap) return cudaErrorInvalidValue;
     return launch_chain(select_kernel, dim3(q), dim3(256), 0, stream, d_cand, d_cnt, cap, kp, d_sel);
+}
+
+cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream)
+{
+    if (t.q < 1 || t.ctas < 1 || t.K < 1 || t.kp < t.K || t.kp > kGtCap || t.groups >= (1u << 27)) return cudaErrorInvalidValue;
+    return launch_chain(grouptop_tail_kernel, dim3(t.ctas, t.q), dim3(256), 0, stream, t);
 }
 
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,

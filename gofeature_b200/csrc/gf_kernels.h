@@ -81,7 +81,14 @@ constexpr float kTf32ErrCoeff = 2.2e-3f;  // |tf32 score - exact| <= coeff * |ro
 constexpr float kAccErrCoeff = 2.5e-4f;   // fp32 accumulation inside the tensor core (the slack kTf32ErrCoeff holds too)
 constexpr float kI8ErrCoeff = 2e-6f;      // int8 pass: exact int32 accumulation, then two float roundings of the scales
 // kGemmFused: TILEMAX of each CTA's first tile + grid barrier + thresholds + COLLECT in ONE launch (nq <= 32)
-enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2, kGemmFused = 3 };
+// kGemmGroupTop: ONE pass, no threshold -- per (32-row group, query) the best two approximate keys go to d_gtop
+// and the best one is counted in a 4096-bin histogram of its score image; grouptop_tail_kernel does the rest
+enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2, kGemmFused = 3, kGemmGroupTop = 4 };
+constexpr int kGtBins = 4096;      // histogram bins = top 12 bits of the score image (sign, exponent, 3 mantissa bits)
+constexpr int kGtCap = 1024;       // candidates re-scored per query at most
+constexpr int kGtStateWords = 8;   // per query: [0] candidate count, [1] CTA ticket, [2] best non-candidate key, [3] overflow
+constexpr int kGtMaxQ = 32;        // padded batch sizes that take the one-pass path
+constexpr int kGtMaxK = 32;        // ... up to this K (the tail ranks its candidates with an O(n^2 / threads) count)
 
 struct GemmLaunch {
     const Segment *d_segs;
@@ -110,12 +117,16 @@ struct GemmLaunch {
     float *d_dump;
     unsigned long long dump_ld;
     int sms;
+    uint2 *d_gtop;            // kGemmGroupTop: [nq][4 * tile_count] (best key, second key) of every 32-row group
+    unsigned int *d_hist;     // kGemmGroupTop: [nq][kGtBins], zeroed by prep_queries_launch
 };
 int gemm_pad_queries(int q);
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
+// gt_hist / gt_state (optional): the one-pass path's histogram [nq][kGtBins] and state [nq][kGtStateWords], zeroed here
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
                                 float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
-                                float *q_scale, cudaStream_t stream);
+                                float *q_scale, cudaStream_t stream, unsigned int *gt_hist = nullptr,
+                                unsigned int *gt_state = nullptr);
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
@@ -146,6 +157,37 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
                             unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
                             cudaStream_t stream);
+
+// The one-pass path's second (and last) kernel: per query, cut = the histogram bin that holds the kp-th best
+// group; every group at or above the cut has its best row re-scored exactly (canonical float32 order); the last
+// CTA of a query ranks the exact keys, re-scores whole groups whose SECOND key could still matter, emits the best
+// K and certifies them against everything that was not re-scored.  ctas = CTAs per query.
+struct GtTail {
+    const uint2 *d_gtop;
+    const unsigned int *d_hist;
+    unsigned int *d_state;
+    uint32_t groups;              // 4 * tile_count
+    const Segment *d_segs;
+    const uint32_t *d_gtile_start;
+    int nseg, dims;
+    const float *d_queries_padded;
+    const float *d_q_scale;       // int8 shadow: the keys hold acc * row_scale, still without the query's scale; else null
+    int kp, K, q;
+    long long rows_total;
+    const float *d_qnorm2;
+    const unsigned int *d_maxnorm2_bits;
+    float err_coeff;
+    const float *d_qres2;
+    const unsigned int *d_maxres2_bits;
+    unsigned long long *d_exact;  // [q][kGtCap]
+    uint2 *d_c2;                  // [q][kGtCap] (second key of the group, group << 5 | lane of the best row)
+    unsigned long long *d_out;    // [q][K]
+    unsigned int *d_flags;        // [q]
+    int ctas;
+    uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment
+    int dbg;
+};
+cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream);
 
 cudaError_t rownorm_range_launch(const float *d_rows, int64_t rows, int dims, unsigned int *d_out_bits,
                                  cudaStream_t stream);

@@ -1272,7 +1272,7 @@ bool Set::tensor_eligible(int q, int K, bool per_segment, const unsigned long lo
     if (path == 1 || per_segment || d_upper != nullptr || !tensor_ok || d_small == nullptr) return false;
     if (K > 512) return false;                               // K' = K + slack must fit the 1024-key re-score
     if (total_gtiles < 2 * 256) return false;                // small sets: the sample would be the set
-    if (path == 2 || path == 3) return true;
+    if (path >= 2 && path <= 5) return true;
     // the shadow pass streams a half (bf16) or a quarter (int8) of the bytes: it wins for every batch size
     if (shadow_ok) return true;
     // one scan pass cannot hold the batch, or K is beyond what the per-CTA sorted lists do cheaply
@@ -1295,7 +1295,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     Stats &st = ctx->stats;
     const bool device_fixup = d_flags == nullptr;  // nobody to report an uncertified query to: repair it here
-    const int mode = (use_shadow(path) ? cache->shadow_eb : 0) | (device_fixup ? 4 : 0);
+    const int mode = (use_shadow(path) ? cache->shadow_eb : 0) | (device_fixup ? 4 : 0) | (two_pass_only(path) ? 8 : 0);
     // bake_io (Search's own staging buffers, stable per workspace): the query preparation and the copy of
     // keys + flags are nodes of the graph too -- ONE stream operation per call
     bake_io = bake_io && d_flags != nullptr && q_stride == dims && l_stride == 1 && stream == ws->stream;
@@ -1463,6 +1463,21 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
     const size_t o_res = carve((size_t)q * K * 8);     // result keys when the caller's buffer must stay outside (phase 2)
     const size_t o_flags = carve((size_t)q * 4);       // right behind the keys: one copy returns both
+    // One-pass path (small batches whose caller takes the certificate flags): no threshold sample -- the big
+    // kernel emits the best two keys of every 32-row group + a histogram, ONE tail kernel does the rest
+    // (prep -> GROUPTOP -> tail: 3 launches instead of 6).  GF_ONEPASS=0 keeps the threshold + COLLECT chain.
+    static const bool onepass_on = getenv("GF_ONEPASS") == nullptr || atoi(getenv("GF_ONEPASS")) != 0;
+    // groups at or above the cut (all of them are re-scored, like the two-pass chain re-scores everything a small
+    // batch collects): deep enough that the certificate's margin, score[K] - score[cut], clears delta on small sets
+    const int kp1 = std::max(kp, 6 * K + 64);
+    const bool onepass = onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && nq_max <= kGtMaxQ &&
+                         K <= kGtMaxK && kp1 <= kGtCap / 2 && (uint64_t)total_gtiles * 4u < (1ull << 27);
+    const uint32_t gt_groups = total_gtiles * 4u;
+    const size_t o_gthist = carve(onepass ? (size_t)nq_max * kGtBins * 4 : 0);
+    const size_t o_gtstate = carve(onepass ? (size_t)nq_max * kGtStateWords * 4 : 0);
+    const size_t o_gtop = carve(onepass ? (size_t)nq_max * gt_groups * 8 : 0);
+    const size_t o_gtexact = carve(onepass ? (size_t)nq_max * kGtCap * 8 : 0);
+    const size_t o_gtc2 = carve(onepass ? (size_t)nq_max * kGtCap * 8 : 0);
     int rc = ws->reserve_tensor(off);
     if (rc) return rc;
     uint8_t *T = ws->d_tensor;
@@ -1528,9 +1543,63 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
-                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream),
+                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream,
+                                        onepass ? (unsigned int *)(T + o_gthist) : nullptr,
+                                        onepass ? (unsigned int *)(T + o_gtstate) : nullptr),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
+        if (onepass) {
+            mark();
+            g.mode = kGemmGroupTop;
+            g.tile_first = 0;
+            g.tile_stride = 1;
+            g.tile_count = total_gtiles;
+            g.d_gtop = (uint2 *)(T + o_gtop);
+            g.d_hist = (unsigned int *)(T + o_gthist);
+            {
+                std::pair<cudaEvent_t, cudaEvent_t> ev;
+                ctx->prof_begin(stream, &ev);
+                cudaError_t le = gemm_launch(g, stream);
+                ctx->prof_end(stream, ev, true);
+                if (le != cudaSuccess) return cuda_fail(le, "gemm_launch", GF_ERR_CUDA);
+            }
+            mark();
+            GtTail t{};
+            t.d_gtop = g.d_gtop;
+            t.d_hist = g.d_hist;
+            t.d_state = (unsigned int *)(T + o_gtstate);
+            t.groups = gt_groups;
+            t.d_segs = d_segs;
+            t.d_gtile_start = d_gtile_start;
+            t.nseg = nseg;
+            t.dims = dims;
+            t.d_queries_padded = d_qpad;
+            t.d_q_scale = seb == 1 ? d_qsc : nullptr;
+            t.kp = kp1;
+            t.K = K;
+            t.q = qp;
+            t.rows_total = scanned_rows;
+            t.d_qnorm2 = d_qn;
+            t.d_maxnorm2_bits = d_small;
+            t.err_coeff = err_coeff;
+            t.d_qres2 = d_qres;
+            t.d_maxres2_bits = d_small + 2;
+            t.d_exact = (unsigned long long *)(T + o_gtexact);
+            t.d_c2 = (uint2 *)(T + o_gtc2);
+            t.d_out = d_out + (size_t)p0 * K;
+            t.d_flags = d_fl + p0;
+            // CTAs per query: enough to spread the group scan and the re-scores over the SMs
+            t.ctas = std::max(1, std::min<int>({128, (2 * ctx->sms) / qp, (int)((gt_groups + 511) / 512)}));
+            t.tiles_per_block = (uint32_t)std::max<int64_t>(1, (cache->block_size / ((int64_t)dims * 4) + 127) / 128);
+            t.dbg = getenv("GF_TAIL_DBG") ? 1 : 0;
+            GF_CUDA(grouptop_tail_launch(t, stream), GF_ERR_CUDA);
+            mark();
+            ctx->stats.gemm_launches += 1;
+            ctx->stats.other_launches += phase != 2 ? 2 : 1;  // (prep,) tail
+            ctx->stats.tensor_passes++;
+            ctx->stats.rows_scanned += (uint64_t)scanned_rows;
+            continue;
+        }
         const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call: it sizes d_exact
         mark();
         // small batches on sets where one tile per SM is a big enough sample: sample, thresholds and COLLECT

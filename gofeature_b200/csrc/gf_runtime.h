@@ -259,7 +259,7 @@ struct gf_set {
     unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter, [2] max |bf16(row) - row|^2 bits
     bool tensor_ok = false;
     bool shadow_ok = false;   // the shadow of this set's rows is maintained and usable by the tensor path
-    int search_path = 0;      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32
+    int search_path = 0;      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32, 4 / 5 = 2 / 3 without the one-pass chain
     uint64_t version = 0;  // bumped whenever the segment table or the shard identity changes
     uint32_t total_tiles = 0;
     int64_t scanned_rows = 0;
@@ -344,7 +344,8 @@ struct gf_set {
     bool tensor_eligible(int q, int K, bool per_segment, const unsigned long long *d_upper, int path) const;
     // rows were written on the device: refresh their bf16 shadow and the certificate's bounds (mutation stream)
     int note_rows(const float *d_rows, int64_t rows);
-    bool use_shadow(int path) const { return shadow_ok && path != 3; }
+    bool use_shadow(int path) const { return shadow_ok && path != 3 && path != 5; }
+    static bool two_pass_only(int path) { return path == 4 || path == 5; }  // pin the threshold + COLLECT chain
     bool slot_to_block(uint32_t slot, int *block_pos, int *row) const;
 };
 

@@ -337,7 +337,9 @@ GF_API int gf_context_reset_stats(gf_context *ctx);
 GF_API int gf_context_set_profiling(gf_context *ctx, int on);
 
 /* Kernel path the host-side Search of this set takes: 0 = choose (default), 1 = fused scan,
- * 2 = tensor path, 3 = tensor path on the float32 rows (kind::tf32) even when a shadow exists.
+ * 2 = tensor path, 3 = tensor path on the float32 rows (kind::tf32) even when a shadow exists,
+ * 4 / 5 = 2 / 3 pinned to the two-pass chain (threshold sample + COLLECT) instead of the one-pass chain
+ * small batches take by default.
  * Results do not depend on it; tests and benchmarks use it to pin one path. */
 GF_API int gf_set_set_search_path(gf_set *set, int path);
 
