@@ -5,19 +5,22 @@ Workload (BASELINE.json configs[1]): 1 000 000 x 512-d L2-normalised float32 fea
 (2.048 GB, 62 blocks of 32 MiB = demo geometry, demo/main.go:19-23), top-10, 10 concurrent
 single-query searchers.  One "step" serves one query from each of the 10 searchers.
 
-  value     queries/s with the 10 queries already resident in HBM (gf_set_search_device: fused
-            scan kernel passes + merge kernel; at N > 1 also the NCCL all-gather of 10 keys per
-            query per rank and the cross-rank merge kernel), CUDA-event timed, max over ranks.
-            Weak scaling: every rank holds its own 1 M-row shard of an N-million-row set, and a
-            query is counted once per 1 M-row shard it scans (N per query), so value is the
+  value     queries/s with the 10 queries already resident in HBM (gf_set_search_device_ex: query
+            preparation, the tcgen05 candidate pass over the int8 shadow slab, the tail kernel that re-scores
+            the candidates from the float32 rows and certifies them; at N > 1 also the exchange of 10 keys
+            per query per rank over NVLink peer memory and the cross-rank merge), CUDA-event timed, max
+            over ranks.  Weak scaling: every rank holds its own 1 M-row shard of an N-million-row set, and
+            a query is counted once per 1 M-row shard it scans (N per query), so value is the
             1 M-row-equivalent QPS of the whole job; `qps_user` is the plain end-user QPS.
-  e2e       the same through the public host-buffer call (gf_set_search at N = 1, the collective
-            ShardedSet.search_keys at N > 1): H2D of the queries and D2H of the winners inside
-            the timed region, wall clock bracketed by device synchronisation.
+  e2e       the same through the public host-buffer call: 10 real host threads x gf_set_search(q=1),
+            coalesced by the library (tools/gf_demo; at N > 1 the collective ShardedSet.search_keys): queries
+            read from pinned host memory and winners written back to it inside the timed region.
   roofline  the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  With the
-            bf16 shadow slab (default) that kernel is the tcgen05 kind::f16 candidate pass and its algorithmic
-            bytes are the SHADOW bytes it must stream (rows x dims x 2), not the float32 bytes: the
-            fraction says how well the kernel uses HBM, the halved traffic shows up in `value`.
+            int8 shadow slab (default) that kernel is the tcgen05 kind::i8 candidate pass and its algorithmic
+            bytes are the SHADOW bytes it must stream (rows x dims x 1 + one float scale per row), not the
+            float32 bytes: the fraction says how well the kernel uses HBM, the smaller traffic shows up in
+            `value`.  `float32_paths` times the same step WITHOUT the shadow (kind::tf32 over the float32
+            rows, and the fused exact scan), whose algorithmic bytes are SURVEY 8(d)'s rows x dims x 4.
   cpu_baseline / --impl reference
             the oracle's plain multi-threaded CPU scan ("port": the reference has no CPU build and
             there is no Go toolchain) on a bounded row sample, scaled to 1 M rows.
@@ -319,6 +322,39 @@ def run_ours(args, rank, world, local_rank):
             q1_ms = s1["gemm_kernel_ns"] / 1e6 / max(s1["gemm_kernel_timed"], 1)
         else:
             q1_ms = s1["scan_kernel_ns"] / 1e6 / max(s1["scan_kernel_timed"], 1)
+    # ---- the same step on the float32 rows only (no shadow traffic saved): kind::tf32 candidate pass, and the
+    # fused exact scan -- SURVEY 8(d)'s algorithmic bytes (rows x dims x 4) apply to these as they stand
+    f32_paths = {}
+    if world == 1:
+        fsteps = max(20, min(args.steps, 100))
+        for name, path in (("tf32_candidate_pass", 3), ("exact_scan", 1)):
+            for i in range(3):
+                sset.search_device(K, Q, dpool[i % npool], path=path)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(fsteps):
+                sset.search_device(K, Q, dpool[i % npool], path=path)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / fsteps
+            ctx.ResetStats()
+            ctx.SetProfiling(True)
+            for i in range(20):
+                sset.search_device(K, Q, dpool[i % npool], path=path)
+            torch.cuda.synchronize()
+            fs = ctx.Stats()
+            ctx.SetProfiling(False)
+            if fs["tensor_passes"] > 0:
+                kms = fs["gemm_kernel_ns"] / 1e6 / max(fs["gemm_kernel_timed"], 1)
+                per_step = fs["gemm_kernel_timed"] / 20.0
+            else:
+                kms = fs["scan_kernel_ns"] / 1e6 / max(fs["scan_kernel_timed"], 1)
+                per_step = fs["scan_kernel_timed"] / 20.0
+            fbytes = rows_local * DIMS * 4 + (Q / max(per_step, 1)) * DIMS * 4
+            f32_paths[name] = {"ms_per_step": fms, "value": Q / (fms * 1e-3), "unit": UNIT,
+                               "kernel_ms": kms, "kernel_launches_per_step": per_step,
+                               "achieved_gbs": fbytes / (kms * 1e-3) / 1e9 if kms > 0 else None}
     # ---- config[1] exactly as written: 10 concurrent host threads, one query each, through the C ABI
     # (tools/gf_demo, the counterpart of the reference's demo/main.go), request coalescing on
     demo = None
@@ -363,11 +399,12 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": Q * K * 8, "qps_user": e2e_user, "ms_per_step": e2e_ms / args.steps,
                 "p50_ms": lat_ms[len(lat_ms) // 2], "p99_ms": lat_ms[min(len(lat_ms) - 1, int(len(lat_ms) * 0.99))],
                 "call": "one gf_set_search(q=%d) per step" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q},
+        "units": "a query counts once per %d-row shard it scans: value = qps_user x n_gpus (weak scaling)" % args.rows_per_gpu,
         "gpu_launches": int(launches), "tensor_passes": stats["tensor_passes"],
         "uncertified_queries": stats["uncertified_queries"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic_from_profile(eb),
-                     "kernel": ("gemm_kernel<16,1,%d> (tcgen05 %s COLLECT pass over the %s)"
+                     "kernel": ("gemm_kernel<16,1,%d> (tcgen05 %s candidate pass over the %s)"
                                 % (eb, {1: "kind::i8 int8", 2: "kind::f16 bf16", 4: "kind::tf32"}[eb],
                                    {1: "int8 shadow slab", 2: "bf16 shadow slab", 4: "float32 rows"}[eb])) if tensor
                      else "scan_tma_kernel<512,QT>",
@@ -393,6 +430,10 @@ def run_ours(args, rank, world, local_rank):
     elif demo:
         line["e2e_parallel_error"] = demo
     if world == 1:
+        for v in f32_paths.values():
+            if v.get("achieved_gbs"):
+                v["roofline_frac"] = v["achieved_gbs"] / peak
+        line["float32_paths"] = f32_paths
         l1 = sorted(x * 1e3 for x in lat1)
         eb1 = shadow_eb if (q1_tensor and shadow_eb) else 4
         b1 = rows_local * DIMS * eb1 + DIMS * eb1 + K * 8

@@ -813,12 +813,42 @@ __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_s
     __shared__ float red[32], red2[32];
     __shared__ float s_scale;
     float acc = 0.f, res = 0.f, amax = 0.f;
-    for (int e = threadIdx.x; e < dims; e += blockDim.x) {
-        float v = qi < q ? src[(long long)qi * q_stride + (long long)e * l_stride] : 0.f;
+    // up to kHold elements per thread stay in registers between the two passes (dims <= 1024 with 128 threads):
+    // re-reading the padded copy from global memory was a second dependent round trip in a kernel that is all latency
+    constexpr int kHold = 8;
+    const bool hold = dims <= kHold * (int)blockDim.x;
+    float hv[kHold];
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) hv[u] = 0.f;
+    if (hold) {
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) {
+            const int e = threadIdx.x + u * blockDim.x;
+            if (e < dims && qi < q) hv[u] = src[(long long)qi * q_stride + (long long)e * l_stride];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        const int e = threadIdx.x + u * blockDim.x;
+        if (!hold || e >= dims) continue;
+        const float v = hv[u];
         dst[(size_t)qi * dims + e] = v;
         if (copy != nullptr && qi < q) copy[(size_t)qi * dims + e] = v;
         acc += v * v;
         amax = fmaxf(amax, fabsf(v));  // (NaN is skipped by fmaxf: the norm below still turns NaN)
+        if (dst_sh != nullptr && sh_eb == 2) {
+            const __nv_bfloat16 b = __float2bfloat16_rn(v);
+            reinterpret_cast<__nv_bfloat16 *>(dst_sh)[(size_t)qi * dims + e] = b;
+            const float d = __bfloat162float(b) - v;
+            res += d * d;
+        }
+    }
+    for (int e = threadIdx.x; e < dims && !hold; e += blockDim.x) {
+        float v = qi < q ? src[(long long)qi * q_stride + (long long)e * l_stride] : 0.f;
+        dst[(size_t)qi * dims + e] = v;
+        if (copy != nullptr && qi < q) copy[(size_t)qi * dims + e] = v;
+        acc += v * v;
+        amax = fmaxf(amax, fabsf(v));
         if (dst_sh != nullptr && sh_eb == 2) {
             const __nv_bfloat16 b = __float2bfloat16_rn(v);
             reinterpret_cast<__nv_bfloat16 *>(dst_sh)[(size_t)qi * dims + e] = b;
@@ -837,14 +867,19 @@ __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_s
         }
         __syncthreads();
         const float sc = s_scale, inv = sc > 0.f ? 1.f / sc : 0.f;
-        for (int e = threadIdx.x; e < dims; e += blockDim.x) {
-            const float v = dst[(size_t)qi * dims + e];
+        auto quant = [&](int e, float v) {
             int qv = __float2int_rn(v * inv);
             qv = qv > 127 ? 127 : (qv < -127 ? -127 : qv);
             reinterpret_cast<signed char *>(dst_sh)[(size_t)qi * dims + e] = (signed char)qv;
             const float d = (float)qv * sc - v;
             res += d * d;
+        };
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) {
+            const int e = threadIdx.x + u * blockDim.x;
+            if (hold && e < dims) quant(e, hv[u]);
         }
+        for (int e = threadIdx.x; e < dims && !hold; e += blockDim.x) quant(e, dst[(size_t)qi * dims + e]);
         __syncthreads();
     }
     for (int off = 16; off >= 1; off >>= 1) {
@@ -1231,28 +1266,45 @@ __device__ __forceinline__ bool gt_locate(const GtTail &a, uint32_t group, uint3
     return true;
 }
 
-// grid (ctas per query, q), 256 threads.
+// One thread-block CLUSTER per query (kGtCluster CTAs of 512 threads): the candidates' exact keys meet in the
+// leader CTA's shared memory over DSMEM, so the tail has no global atomics, no ticket and no second trip to L2.
 //   A  every CTA: cut = the histogram bin holding the kp-th best group of its query (suffix scan of 4096 bins)
-//   B  its share of the groups: best key at or above the cut -> candidate, else -> running max (ceiling 1)
-//   C  a warp per candidate: exact canonical score of the group's best row -> d_exact, (second key, group) -> d_c2
-//   D  last CTA of the query (ticket): rank the exact keys, emit the best K; a group whose SECOND key could still
-//      reach the K-th score has all its rows re-scored (the third-best row of a group is only known to be below
-//      the second key); certificate: K-th exact score > every approximate ceiling + delta.
-__global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
+//   B  its share of the groups (32-entry chunks dealt round-robin to the CTAs, so that a run of good rows spreads
+//      over the cluster): best key at or above the cut -> candidate, else -> running max (ceiling 1)
+//   C  a warp per candidate: exact canonical score of the group's best row -> the leader's region of this CTA
+//   D  leader: rank the exact keys, emit the best K; a group whose SECOND key could still reach the K-th score has
+//      all its rows re-scored (the third-best row of a group is only known to be below the second key);
+//      certificate: K-th exact score > every approximate ceiling + delta.
+constexpr int kGtCluster = 8;
+constexpr int kGtThreads = 512;
+constexpr int kGtRegion = kGtCap / kGtCluster;  // exact keys one CTA may hand to the leader
+constexpr int kGtLocal = 256;                   // candidates one CTA may find
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long v)
 {
-    __shared__ unsigned long long s_keys[kGtCap];  // phase B/C: [0, kGtCap) uint32 candidates | second keys behind them
-    __shared__ uint2 s_c2[kGtCap];
-    __shared__ int s_wsum[8];
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail a)
+{
+    __shared__ unsigned long long r_keys[kGtCap];  // leader: region r = [r * kGtRegion, ...) written by CTA r
+    __shared__ unsigned long long r_c2[kGtCap];    // (second key << 32) | (group << 5 | lane of the best row)
+    __shared__ unsigned long long d_keys[kGtCap];  // leader: the same, dense
+    __shared__ uint2 d_c2[kGtCap];
+    __shared__ uint32_t r_cnt[kGtCluster], r_ncmax[kGtCluster], r_over[kGtCluster];
+    __shared__ uint32_t s_e[kGtLocal], s_k2[kGtLocal];
+    __shared__ int s_wsum[kGtThreads / 32];
     __shared__ int s_cut, s_n, s_nexp;
-    __shared__ unsigned int s_ncmax, s_ticket;
+    __shared__ unsigned int s_ncmax;
     __shared__ unsigned long long s_kth;
+    __shared__ unsigned long long s_out[kGtMaxK];  // the answer, written out in one piece (it may live in pinned host memory)
     __shared__ uint32_t s_exp[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qi = blockIdx.y;
-    unsigned long long tm[10];
-    int tmi = 0;
-#define GT_TICK() do { if (a.dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tm[tmi++] = t_; } } while (0)
-    GT_TICK();
+    const uint32_t rank = cluster_ctarank();
     if (tid == 0) {
         s_cut = 0;
         s_n = 0;
@@ -1260,36 +1312,35 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
     }
     pdl_wait();
     pdl_launch_dependents();
-    GT_TICK();
-    unsigned int *state = a.d_state + (size_t)qi * kGtStateWords;
-    // this CTA's share of the groups; the first kGtPre entries per thread are loaded NOW, next to the histogram, so
-    // that the two L2 round trips overlap
-    constexpr int kGtPre = 6;
-    const uint32_t per = (a.groups + gridDim.x - 1) / gridDim.x;
-    const uint32_t e0 = blockIdx.x * per;
-    const uint32_t e1 = e0 + per < a.groups ? e0 + per : a.groups;
+    // this CTA's 32-entry chunks: chunk c = (k * kGtCluster + rank), k = iteration * 16 + warp; the first kGtPre
+    // per thread are loaded NOW, next to the histogram, so that the two L2 round trips overlap
+    constexpr int kGtPre = 8;
+    constexpr int kWarps = kGtThreads / 32;
     const uint2 *gt = a.d_gtop + (size_t)qi * a.groups;
+    auto entry_of = [&](int iter) -> uint32_t {
+        return ((uint32_t)(iter * kWarps + warp) * kGtCluster + rank) * 32u + (uint32_t)lane;
+    };
     uint2 pre[kGtPre];
 #pragma unroll
     for (int u = 0; u < kGtPre; ++u) {
-        const uint32_t e = e0 + tid + 256u * u;
-        pre[u] = e < e1 ? __ldcg(gt + e) : make_uint2(0u, 0u);
+        const uint32_t e = entry_of(u);
+        pre[u] = e < a.groups ? __ldcg(gt + e) : make_uint2(0u, 0u);
     }
-    // ---- A: thread t owns bins 4095 - 16 t .. 4080 - 16 t (descending)
+    // ---- A: thread t owns bins 4095 - 8 t .. 4088 - 8 t (descending)
     {
         const unsigned int *h = a.d_hist + (size_t)qi * kGtBins;
-        const int top = kGtBins - 1 - 16 * tid;
-        int c[16], local = 0;
+        const int top = kGtBins - 1 - 8 * tid;
+        int c[8], local = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(h + top - 15) + u);
-            c[15 - 4 * u] = (int)w.x;
-            c[14 - 4 * u] = (int)w.y;
-            c[13 - 4 * u] = (int)w.z;
-            c[12 - 4 * u] = (int)w.w;
+        for (int u = 0; u < 2; ++u) {
+            const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(h + top - 7) + u);
+            c[7 - 4 * u] = (int)w.x;
+            c[6 - 4 * u] = (int)w.y;
+            c[5 - 4 * u] = (int)w.z;
+            c[4 - 4 * u] = (int)w.w;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) local += c[j];
+        for (int j = 0; j < 8; ++j) local += c[j];
         int incl = local;
         for (int off = 1; off < 32; off <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, off);
@@ -1304,7 +1355,7 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
         if (excl < a.kp && incl >= a.kp) {
             int run = excl, bin = top;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 if (run < a.kp && run + c[j] >= a.kp) bin = top - j;
                 run += c[j];
             }
@@ -1312,17 +1363,14 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
         }
         __syncthreads();
     }
-    GT_TICK();
     const unsigned int cutimg = (unsigned int)s_cut << 20;
-    uint32_t *s_e = reinterpret_cast<uint32_t *>(s_keys);
-    uint32_t *s_k2 = s_e + kGtCap;
     // ---- B
     {
         unsigned int ncmax = 0u;
         auto classify = [&](uint32_t e, uint2 v) {
             if (v.x >= cutimg && v.x != 0u && cutimg != 0u) {
                 const int pos = atomicAdd(&s_n, 1);
-                if (pos < kGtCap) {
+                if (pos < kGtLocal) {
                     s_e[pos] = (e << 5) | (v.x & 31u);
                     s_k2[pos] = v.y;
                 }
@@ -1332,73 +1380,70 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
         };
 #pragma unroll
         for (int u = 0; u < kGtPre; ++u) {
-            const uint32_t e = e0 + tid + 256u * u;
-            if (e < e1) classify(e, pre[u]);
+            const uint32_t e = entry_of(u);
+            if (e < a.groups) classify(e, pre[u]);
         }
-#pragma unroll 4
-        for (uint32_t e = e0 + tid + 256u * kGtPre; e < e1; e += 256) classify(e, __ldcg(gt + e));
+        for (int it = kGtPre;; ++it) {
+            const uint32_t e = entry_of(it);
+            if (e - (uint32_t)lane >= a.groups) break;  // (warp-uniform)
+            if (e < a.groups) classify(e, __ldcg(gt + e));
+        }
         ncmax = __reduce_max_sync(0xffffffffu, ncmax);
         if (lane == 0 && ncmax != 0u) atomicMax(&s_ncmax, ncmax);
         __syncthreads();
-        if (tid == 0) {
-            if (s_ncmax != 0u) atomicMax(&state[2], s_ncmax);
-            if (s_n > kGtCap || cutimg == 0u) atomicOr(&state[3], 1u);
-        }
     }
-    GT_TICK();
-    // ---- C
+    // ---- C: exact scores straight into the leader's shared memory
     const float *qv = a.d_queries_padded + (size_t)qi * a.dims;
     {
-        const int n = s_n < kGtCap ? s_n : kGtCap;
-        // this warp's slots in the query's exact list: ONE reservation, issued before the dot products (its round
-        // trip hides behind their loads)
-        unsigned int gp = 0u;
-        if (lane == 0 && warp < n) gp = atomicAdd(&state[0], (unsigned int)((n - warp + 7) / 8));
-        for (int idx = warp; idx < n; idx += 8, ++gp) {
+        const int found_n = s_n;
+        const int n = found_n < kGtRegion ? found_n : kGtRegion;
+        const uint32_t keys0 = leader_addr(r_keys + rank * kGtRegion), c20 = leader_addr(r_c2 + rank * kGtRegion);
+        for (int idx = warp; idx < n; idx += kWarps) {
             const uint32_t ee = s_e[idx];
             const float *x;
             uint32_t slot;
             const bool found = gt_locate(a, ee >> 5, ee & 31u, &x, &slot);  // (always: a dead row has no key)
             const float sc = found ? exact_dot(x, qv, a.dims, lane) : 0.f;
-            if (lane == 0 && gp < (unsigned)kGtCap) {
-                a.d_exact[(size_t)qi * kGtCap + gp] = found ? make_key(sc, slot) : 0ull;
-                a.d_c2[(size_t)qi * kGtCap + gp] = make_uint2(found ? s_k2[idx] : 0u, ee);
+            if (lane == 0) {
+                st_cluster_u64(keys0 + 8u * idx, found ? make_key(sc, slot) : 0ull);
+                st_cluster_u64(c20 + 8u * idx, ((unsigned long long)(found ? s_k2[idx] : 0u) << 32) | ee);
             }
         }
+        if (tid == 0) {
+            st_cluster_u32(leader_addr(r_cnt + rank), (uint32_t)n);
+            st_cluster_u32(leader_addr(r_ncmax + rank), s_ncmax);
+            st_cluster_u32(leader_addr(r_over + rank), (found_n > kGtRegion || cutimg == 0u) ? 1u : 0u);
+        }
     }
-    GT_TICK();
-    // ---- D: the last CTA of this query
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&state[1], 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-    GT_TICK();
-    // everything the last CTA needs, in ONE round trip: the first 512 slots are loaded whatever the count is
-    // (what lies beyond the count is never looked at)
-    unsigned long long lk[2];
-    uint2 lc[2];
+    cluster_sync_all();  // release / acquire at cluster scope: the leader sees every CTA's keys
+    if (rank != 0) return;
+    // ---- D: the leader
+    int n = 0;
+    bool over = false;
+    unsigned int ncmax_all = 0u;
+    int base_of[kGtCluster];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        lk[u] = __ldcg(a.d_exact + (size_t)qi * kGtCap + tid + 256 * u);
-        lc[u] = __ldcg(a.d_c2 + (size_t)qi * kGtCap + tid + 256 * u);
+    for (int r = 0; r < kGtCluster; ++r) {
+        base_of[r] = n;
+        n += (int)r_cnt[r];
+        over = over || r_over[r] != 0u;
+        ncmax_all = max(ncmax_all, r_ncmax[r]);
     }
-    const unsigned int total = __ldcg(&state[0]);
-    const bool over = __ldcg(&state[3]) != 0u || total > (unsigned)kGtCap;
-    const float qs = a.d_q_scale != nullptr ? __ldcg(a.d_q_scale + qi) : 1.f;
-    const float delta = cert_delta(qi, a.d_qnorm2, a.d_maxnorm2_bits, a.err_coeff, a.d_qres2, a.d_maxres2_bits);
-    int n = (int)(total < (unsigned)kGtCap ? total : (unsigned)kGtCap);
+    for (int sl = tid; sl < kGtCap; sl += kGtThreads) {
+        const int r = sl / kGtRegion, idx = sl % kGtRegion;
+        if (idx < (int)r_cnt[r]) {
+            int b = 0;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        s_keys[tid + 256 * u] = lk[u];
-        s_c2[tid + 256 * u] = lc[u];
-    }
-    for (int i = tid + 512; i < n; i += 256) {
-        s_keys[i] = __ldcg(a.d_exact + (size_t)qi * kGtCap + i);
-        s_c2[i] = __ldcg(a.d_c2 + (size_t)qi * kGtCap + i);
+            for (int rr = 0; rr < kGtCluster; ++rr)
+                if (rr == r) b = base_of[rr];
+            d_keys[b + idx] = r_keys[sl];
+            const unsigned long long c = r_c2[sl];
+            d_c2[b + idx] = make_uint2((uint32_t)(c >> 32), (uint32_t)c);
+        }
     }
     const long long keff = a.rows_total < a.K ? a.rows_total : a.K;
+    const float qs = a.d_q_scale != nullptr ? __ldcg(a.d_q_scale + qi) : 1.f;
+    const float delta = cert_delta(qi, a.d_qnorm2, a.d_maxnorm2_bits, a.err_coeff, a.d_qres2, a.d_maxres2_bits);
     // approximate score a row with key image <= im can reach (the low 5 bits of a key are not score bits)
     auto reach = [&](unsigned int im) -> float {
         const float v = image_score(im | 31u) * qs;
@@ -1406,8 +1451,6 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
     };
     bool ok = !over;
     unsigned long long *out = a.d_out + (size_t)qi * a.K;
-    __syncthreads();
-    GT_TICK();
     for (int round = 0; round < 2; ++round) {
         if (tid == 0) {
             s_kth = 0ull;
@@ -1415,14 +1458,14 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
         }
         __syncthreads();
         // rank of every key among the n exact keys (distinct: one per slot); the best K go straight out
-        for (int i = tid; i < n; i += 256) {
-            const unsigned long long my = s_keys[i];
-            int rank = 0;
-            for (int j = 0; j < n; ++j) rank += s_keys[j] > my ? 1 : 0;
-            if (rank < a.K) out[rank] = my;
-            if (rank == (int)keff - 1) s_kth = my;
+        for (int i = tid; i < n; i += kGtThreads) {
+            const unsigned long long my = d_keys[i];
+            int rk = 0;
+            for (int j = 0; j < n; ++j) rk += d_keys[j] > my ? 1 : 0;
+            if (rk < a.K) s_out[rk] = my;
+            if (rk == (int)keff - 1) s_kth = my;
         }
-        for (int i = n + tid; i < a.K; i += 256) out[i] = 0ull;
+        for (int i = n + tid; i < a.K; i += kGtThreads) s_out[i] = 0ull;
         __syncthreads();
         const unsigned long long kth = s_kth;
         if (kth == 0ull) {  // not even K candidates
@@ -1431,12 +1474,12 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
         }
         const float tk = key_score(kth);
         // groups whose hidden rows (bounded by the second key) could still reach the K-th score
-        for (int i = tid; i < n; i += 256) {
-            const uint2 c = s_c2[i];
+        for (int i = tid; i < n; i += kGtThreads) {
+            const uint2 c = d_c2[i];
             if (c.x != 0u && !(tk > reach(c.x) + delta)) {
                 const int pos = atomicAdd(&s_nexp, 1);
                 if (pos < 8) s_exp[pos] = c.y;
-                s_c2[i].x = 0u;  // (re-scored below, or the query is flagged)
+                d_c2[i].x = 0u;  // (re-scored below, or the query is flagged)
             }
         }
         __syncthreads();
@@ -1449,7 +1492,7 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
         // re-score every other row of those groups: a warp per row
         if (tid == 0) s_n = n;
         __syncthreads();
-        for (int w = warp; w < nexp * 32; w += 8) {
+        for (int w = warp; w < nexp * 32; w += kWarps) {
             const uint32_t ee = s_exp[w >> 5];
             const uint32_t lr = (uint32_t)(w & 31);
             if (lr == (ee & 31u)) continue;  // the group's best row is already there
@@ -1459,24 +1502,18 @@ __global__ void __launch_bounds__(256) grouptop_tail_kernel(const GtTail a)
             const float sc = exact_dot(x, qv, a.dims, lane);
             if (lane == 0) {
                 const int pos = atomicAdd(&s_n, 1);
-                s_keys[pos] = make_key(sc, slot);
-                s_c2[pos] = make_uint2(0u, 0u);
+                d_keys[pos] = make_key(sc, slot);
+                d_c2[pos] = make_uint2(0u, 0u);
             }
         }
         __syncthreads();
         n = s_n;
         __syncthreads();
     }
-    GT_TICK();
-    if (a.dbg && tid == 0 && qi == 0)
-        printf("[tail] n=%d launch->wait %llu A %llu B %llu C %llu ticket %llu load %llu rank+cert %llu\n", n, tm[1] - tm[0],
-               tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[6] - tm[5], tm[7] - tm[6]);
+    if (tid < a.K) out[tid] = s_out[tid];  // (every way out of the loop is behind a barrier that follows the ranking)
     if (tid == 0) {
-        if (ok) {
-            // rows of groups below the cut: their best key is <= the largest non-candidate key
-            const unsigned int nc = __ldcg(&state[2]);
-            if (nc != 0u && !(key_score(s_kth) > reach(nc) + delta)) ok = false;
-        }
+        // rows of groups below the cut: their best key is <= the largest non-candidate key
+        if (ok && ncmax_all != 0u && !(key_score(s_kth) > reach(ncmax_all) + delta)) ok = false;
         a.d_flags[qi] = ok ? 0u : 1u;
     }
 }
@@ -1719,8 +1756,22 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
 
 cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream)
 {
-    if (t.q < 1 || t.ctas < 1 || t.K < 1 || t.kp < t.K || t.kp > kGtCap || t.groups >= (1u << 27)) return cudaErrorInvalidValue;
-    return launch_chain(grouptop_tail_kernel, dim3(t.ctas, t.q), dim3(256), 0, stream, t);
+    if (t.q < 1 || t.K < 1 || t.K > kGtMaxK || t.kp < t.K || t.kp > kGtCap || t.groups >= (1u << 27)) return cudaErrorInvalidValue;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kGtCluster, t.q);
+    cfg.blockDim = dim3(kGtThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kGtCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, grouptop_tail_kernel, t);
 }
 
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,

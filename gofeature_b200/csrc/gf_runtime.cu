@@ -1299,6 +1299,11 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     // bake_io (Search's own staging buffers, stable per workspace): the query preparation and the copy of
     // keys + flags are nodes of the graph too -- ONE stream operation per call
     bake_io = bake_io && d_flags != nullptr && q_stride == dims && l_stride == 1 && stream == ws->stream;
+    // The one-pass chain is three launches that write straight into the caller's buffers: replaying a graph would
+    // need an eager preparation before it and a copy of the results behind it -- as many stream operations, and
+    // the copy sits on the device's critical path.  Only Search's own stable buffers (bake_io) are worth a graph.
+    if (!bake_io && onepass_applies(q, K, path, device_fixup))
+        return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     const size_t res_b = align_up((size_t)q * K * 8, 256);
     for (auto &g : ws->graphs) {
         if (g.set == this && g.version == version && g.q == q && g.K == K && g.mode == mode &&
@@ -1344,9 +1349,14 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     }
     int crc = GF_OK;
     if (bake_io) crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path, device_fixup);
+    ws->wrote_direct = false;
+    ws->direct_out = bake_io ? d_out : nullptr;
+    ws->direct_flags = bake_io ? d_flags : nullptr;
     if (crc == GF_OK)
         crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path, device_fixup);
-    if (crc == GF_OK && bake_io) {
+    ws->direct_out = nullptr;
+    ws->direct_flags = nullptr;
+    if (crc == GF_OK && bake_io && !ws->wrote_direct) {
         const bool contig = (uint8_t *)d_flags == (uint8_t *)d_out + res_b &&
                             (uint8_t *)ws->t_flags == (uint8_t *)ws->t_res + res_b;
         cudaError_t me = cudaMemcpyAsync(d_out, ws->t_res, contig ? res_b + (size_t)q * 4 : (size_t)q * K * 8,
@@ -1395,6 +1405,22 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     cg.stamp = ++ws->graph_clock;
     ws->graphs.push_back(cg);
     return GF_OK;
+}
+
+bool Set::onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out) const
+{
+    // GF_ONEPASS=0 keeps the threshold + COLLECT chain everywhere
+    static const bool onepass_on = getenv("GF_ONEPASS") == nullptr || atoi(getenv("GF_ONEPASS")) != 0;
+    const int seb = use_shadow(path) ? cache->shadow_eb : 0;
+    const int kp = seb == 1   ? std::min(1024, std::max(K + 96, 3 * K + 64))
+                   : seb == 2 ? std::min(1024, std::max(K + 64, 2 * K + 32))
+                              : std::min(1024, std::max(K + 32, K + K / 2));
+    // groups at or above the cut (all of them are re-scored, like the two-pass chain re-scores everything a small
+    // batch collects): deep enough that the certificate's margin, score[K] - score[cut], clears delta on small sets
+    const int kp1 = std::max(kp, 6 * K + 64);
+    if (kp_out) *kp_out = kp1;
+    return onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && K <= kGtMaxK && kp1 <= kGtCap / 2 &&
+           (uint64_t)total_gtiles * 4u < (1ull << 27);
 }
 
 int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,
@@ -1466,12 +1492,8 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     // One-pass path (small batches whose caller takes the certificate flags): no threshold sample -- the big
     // kernel emits the best two keys of every 32-row group + a histogram, ONE tail kernel does the rest
     // (prep -> GROUPTOP -> tail: 3 launches instead of 6).  GF_ONEPASS=0 keeps the threshold + COLLECT chain.
-    static const bool onepass_on = getenv("GF_ONEPASS") == nullptr || atoi(getenv("GF_ONEPASS")) != 0;
-    // groups at or above the cut (all of them are re-scored, like the two-pass chain re-scores everything a small
-    // batch collects): deep enough that the certificate's margin, score[K] - score[cut], clears delta on small sets
-    const int kp1 = std::max(kp, 6 * K + 64);
-    const bool onepass = onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && nq_max <= kGtMaxQ &&
-                         K <= kGtMaxK && kp1 <= kGtCap / 2 && (uint64_t)total_gtiles * 4u < (1ull << 27);
+    int kp1 = kp;
+    const bool onepass = onepass_applies(q, K, path, device_fixup, &kp1);
     const uint32_t gt_groups = total_gtiles * 4u;
     const size_t o_gthist = carve(onepass ? (size_t)nq_max * kGtBins * 4 : 0);
     const size_t o_gtstate = carve(onepass ? (size_t)nq_max * kGtStateWords * 4 : 0);
@@ -1533,6 +1555,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         evs.push_back(e);
     };
     const int fixq = std::min(kFixupMaxQ, scan_max_q(dims));
+    bool flags_direct = false;
     for (int p0 = 0; p0 < q; p0 += kGemmMaxQ) {
         const int qp = std::min(kGemmMaxQ, q - p0);
         const int nq = gemm_pad_queries(qp);
@@ -1588,6 +1611,14 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             t.d_c2 = (uint2 *)(T + o_gtc2);
             t.d_out = d_out + (size_t)p0 * K;
             t.d_flags = d_fl + p0;
+            if (phase == 2 && ws->direct_out != nullptr && ws->direct_flags != nullptr) {
+                t.d_out = ws->direct_out;  // (one pass: p0 == 0)
+                t.d_flags = ws->direct_flags;
+                ws->wrote_direct = true;
+            } else if (phase == 0 && d_flags != nullptr) {
+                t.d_flags = d_flags;       // the caller's own flags: no copy behind the chain
+                flags_direct = true;
+            }
             // CTAs per query: enough to spread the group scan and the re-scores over the SMs
             t.ctas = std::max(1, std::min<int>({128, (2 * ctx->sms) / qp, (int)((gt_groups + 511) / 512)}));
             t.tiles_per_block = (uint32_t)std::max<int64_t>(1, (cache->block_size / ((int64_t)dims * 4) + 127) / 128);
@@ -1688,7 +1719,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         fprintf(stderr, "\n");
         for (auto e : evs) cudaEventDestroy(e);
     }
-    if (d_flags && phase == 0)
+    if (d_flags && phase == 0 && !flags_direct)
         GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDefault, stream),
                 GF_ERR_CUDA);
     return GF_OK;

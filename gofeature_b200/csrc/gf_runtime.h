@@ -91,6 +91,11 @@ struct Workspace {
     bool graphs_broken = false;
     unsigned long long *t_res = nullptr;  // tensor path: internal result keys / flags of the last carve
     unsigned int *t_flags = nullptr;
+    // recording a graph whose results go to the caller's own (stable, possibly pinned host) buffers: the one-pass
+    // chain's last kernel writes them itself and sets wrote_direct -- no copy node behind it
+    unsigned long long *direct_out = nullptr;
+    unsigned int *direct_flags = nullptr;
+    bool wrote_direct = false;
     void drop_graphs();
     int reserve(size_t d_bytes, size_t h_bytes);
     int reserve_tensor(size_t bytes);
@@ -346,6 +351,8 @@ struct gf_set {
     int note_rows(const float *d_rows, int64_t rows);
     bool use_shadow(int path) const { return shadow_ok && path != 3 && path != 5; }
     static bool two_pass_only(int path) { return path == 4 || path == 5; }  // pin the threshold + COLLECT chain
+    // the one-pass chain (prep -> GROUPTOP -> tail) serves this call; kp_out = groups at or above the histogram cut
+    bool onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out = nullptr) const;
     bool slot_to_block(uint32_t slot, int *block_pos, int *row) const;
 };
 
