@@ -70,9 +70,8 @@ struct GemmArgs {
     float *thr_out;               // [nq] thresholds written by CTA 0 (finalize's certificate reads them)
     unsigned int *sync;           // [0] arrival count, [1] generation, [2] sticky "a barrier timed out"
     int sample_m;                 // threshold = sample_m-th largest of the gridDim.x tile maxima
-    // GROUPTOP mode (4): best two keys of every 32-row group + histogram of the best one
-    uint2 *gtop;                  // [nq][groups]
-    unsigned int *hist;           // [nq][kGtBins]
+    // GROUPTOP mode (4): best two keys of every 32-row group
+    uint2 *gtop;                  // [nq][4 quarters][tile_count]
     uint32_t groups;              // 4 * tile_count
     uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment
 };
@@ -310,12 +309,18 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, SegCu
 constexpr int kAppendStage = 256;                  // entries in all: 16 per epilogue warp (up to 16 warps)
 constexpr int kAppendPerWarp = 16;
 constexpr int kAppendStageBytes = kAppendStage * 12 + 64;
+// GROUPTOP: each epilogue warp stages its (best, second) keys of kGtFlush consecutive tiles per query column in its own
+// piece of shared memory and writes them out 128 bytes per column at a time (rows padded to 17 entries: bank spread)
+constexpr int kGtFlush = 16;
+constexpr int kGtStageRow = kGtFlush + 1;
+__host__ __device__ constexpr int gt_stage_bytes(int nq) { return nq <= kGtMaxQ ? 4 * nq * kGtStageRow * 8 : 0; }
 
 template <int NQ, int TM, bool PAIR = false>
 struct GemmCfg {
     static constexpr int kBBytes = (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
-    static constexpr int kStagesFit = (int)((232448 - 1024 - 320 - NQ * 12 - 1024 - kAppendStageBytes) / kStageBytes);
+    static constexpr int kStagesFit =
+        (int)((232448 - 1024 - 320 - NQ * 12 - 1024 - kAppendStageBytes - gt_stage_bytes(NQ)) / kStageBytes);
     // small batches are pure HBM streaming with short tiles (int8: 4 K blocks of 18 KB per tile): a deep ring
     // keeps more than two tiles of loads in flight across the per-tile work of the producer
     static constexpr int kStagesCap = GF_GEMM_STAGES_SMALL;
@@ -332,7 +337,8 @@ struct GemmCfg {
     static constexpr int kChunk = kColsPerEpiWarp >= 32 ? 32 : 16;  // columns per tcgen05.ld
     static_assert(kColsPerEpiWarp % kChunk == 0, "epilogue column split");
     static constexpr size_t kSmem =
-        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 320 /*barriers*/ + NQ * 12 + kAppendStageBytes;
+        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 320 /*barriers*/ + NQ * 12 + kAppendStageBytes +
+        gt_stage_bytes(NQ);
     static_assert(kStages >= 2, "pipeline too shallow");
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
@@ -357,6 +363,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     unsigned long long *stage_key = reinterpret_cast<unsigned long long *>(qs_s + NQ);  // 8-byte aligned: NQ % 2 == 0
     int *stage_q = reinterpret_cast<int *>(stage_key + kAppendStage);
     int *stage_n = stage_q + kAppendStage;
+    uint2 *gt_stage = reinterpret_cast<uint2 *>(stage_n + 16);  // [4 warps][NQ][kGtStageRow]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kBK = KBlock<EB>::kElems;
@@ -682,10 +689,22 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                                 b2 = max(min(b1, r1), max(b2, r2));
                                 b1 = hi;
                             }
+                            // d_gtop is [query][quarter][tile]: a warp's keys of consecutive tiles are consecutive in
+                            // memory.  They wait in the warp's own stage and leave 128 bytes per column at a time --
+                            // one scattered 8-byte store per column per tile cost the pass ~0.5 us per query column.
                             const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
-                            if ((Cfg::kChunk == 32 || (lane & 1) == 0) && col < a.q) {
-                                a.gtop[(size_t)col * a.groups + (size_t)i * 4 + quarter] = make_uint2(b1, b2);
-                                atomicAdd(&a.hist[(size_t)col * kGtBins + (b1 >> 20)], 1u);
+                            uint2 *stw = gt_stage + (size_t)quarter * NQ * kGtStageRow;
+                            const uint32_t fslot = it % kGtFlush;
+                            if (Cfg::kChunk == 32 || (lane & 1) == 0) stw[col * kGtStageRow + fslot] = make_uint2(b1, b2);
+                            if (fslot == kGtFlush - 1 || it + 1 >= g_count) {
+                                __syncwarp();
+                                const uint32_t i0 = i - fslot;  // (a worker's tiles are consecutive in this mode)
+                                if ((uint32_t)lane <= fslot) {
+                                    uint2 *dst = a.gtop + (size_t)quarter * a.tile_count + i0 + lane;
+#pragma unroll 4
+                                    for (int c = 0; c < a.q; ++c) dst[(size_t)c * a.groups] = stw[c * kGtStageRow + lane];
+                                }
+                                __syncwarp();
                             }
                         }
                     } else {
@@ -799,17 +818,11 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
 __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
                                     int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2,
                                     float *__restrict__ copy, void *__restrict__ dst_sh, int sh_eb,
-                                    float *__restrict__ qres2, float *__restrict__ q_scale,
-                                    unsigned int *__restrict__ gt_hist, unsigned int *__restrict__ gt_state)
+                                    float *__restrict__ qres2, float *__restrict__ q_scale)
 {
     pdl_wait();  // the previous call's kernels may still be reading dst / dst_sh
     pdl_launch_dependents();
     const int qi = blockIdx.x;
-    if (gt_hist != nullptr) {  // the one-pass path's histogram and per-query state start every call at zero
-        uint4 *h4 = reinterpret_cast<uint4 *>(gt_hist + (size_t)qi * kGtBins);
-        for (int e = threadIdx.x; e < kGtBins / 4; e += blockDim.x) h4[e] = make_uint4(0u, 0u, 0u, 0u);
-        if (threadIdx.x < kGtStateWords) gt_state[qi * kGtStateWords + threadIdx.x] = 0u;
-    }
     __shared__ float red[32], red2[32];
     __shared__ float s_scale;
     float acc = 0.f, res = 0.f, amax = 0.f;
@@ -1242,10 +1255,11 @@ __device__ __forceinline__ float cert_delta(int qi, const float *qnorm2, const u
     return delta;
 }
 
-// group index (4 per 128-row tile of the set-wide tile order) + row inside the group -> the row and its slot
+// group index (quarter * tiles + tile of the set-wide tile order) + row inside the group -> the row and its slot
 __device__ __forceinline__ bool gt_locate(const GtTail &a, uint32_t group, uint32_t lane_row, const float **x, uint32_t *slot)
 {
-    const uint32_t tile = group >> 2;
+    const uint32_t ntiles = a.groups >> 2;  // d_gtop is [query][quarter][tile]
+    const uint32_t tile = group % ntiles, quarter = group / ntiles;
     // blocks are filled in order, so nearly every segment holds tiles_per_block tiles: guess, verify with two
     // independent loads, and only search when the guess is off (a binary search is 6+ DEPENDENT loads)
     int lo = (int)(tile / a.tiles_per_block);
@@ -1259,7 +1273,7 @@ __device__ __forceinline__ bool gt_locate(const GtTail &a, uint32_t group, uint3
             if (a.d_gtile_start[mid] <= tile) lo = mid; else hi = mid - 1;
         }
     }
-    const uint32_t row = (tile - a.d_gtile_start[lo]) * (uint32_t)kTileRows + (group & 3u) * 32u + lane_row;
+    const uint32_t row = (tile - a.d_gtile_start[lo]) * (uint32_t)kTileRows + quarter * 32u + lane_row;
     if (row >= a.d_segs[lo].rows) return false;
     *x = a.d_segs[lo].base + (size_t)row * a.dims;
     *slot = a.d_segs[lo].slot_base + row;
@@ -1292,8 +1306,12 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
 {
     __shared__ unsigned long long r_keys[kGtCap];  // leader: region r = [r * kGtRegion, ...) written by CTA r
     __shared__ unsigned long long r_c2[kGtCap];    // (second key << 32) | (group << 5 | lane of the best row)
-    __shared__ unsigned long long d_keys[kGtCap];  // leader: the same, dense
-    __shared__ uint2 d_c2[kGtCap];
+    // phase A: the histogram; phase D (leader, long after): the exact keys and second keys, dense
+    __shared__ __align__(16) unsigned char s_union[kGtCap * 16];
+    static_assert(kGtBins * 4 <= kGtCap * 16, "histogram fits the dense arrays");
+    unsigned int *lh = reinterpret_cast<unsigned int *>(s_union);
+    unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(s_union);
+    uint2 *d_c2 = reinterpret_cast<uint2 *>(s_union + kGtCap * 8);
     __shared__ uint32_t r_cnt[kGtCluster], r_ncmax[kGtCluster], r_over[kGtCluster];
     __shared__ uint32_t s_e[kGtLocal], s_k2[kGtLocal];
     __shared__ int s_wsum[kGtThreads / 32];
@@ -1326,42 +1344,67 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
         const uint32_t e = entry_of(u);
         pre[u] = e < a.groups ? __ldcg(gt + e) : make_uint2(0u, 0u);
     }
-    // ---- A: thread t owns bins 4095 - 8 t .. 4088 - 8 t (descending)
+    // ---- A: the cut.  Histogram (4096 bins = top 12 bits of the key) of every thread's BEST key -- 4096 values per
+    // query, each the best of 1/4096 of the groups, so the kp-th largest of them is the kp-th best group's key give
+    // or take a few per cent -- built in shared memory, summed into the leader's over DSMEM, cut found by the
+    // leader and handed back.  (The pass used to count every group in a global histogram: one more scattered
+    // write per group and query column in its epilogue.)
     {
-        const unsigned int *h = a.d_hist + (size_t)qi * kGtBins;
-        const int top = kGtBins - 1 - 8 * tid;
-        int c[8], local = 0;
+        unsigned int tbest = 0u;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(h + top - 7) + u);
-            c[7 - 4 * u] = (int)w.x;
-            c[6 - 4 * u] = (int)w.y;
-            c[5 - 4 * u] = (int)w.z;
-            c[4 - 4 * u] = (int)w.w;
+        for (int u = 0; u < kGtPre; ++u) tbest = max(tbest, pre[u].x);
+        for (int it = kGtPre;; ++it) {  // (sets beyond 1 M rows: the rest of this thread's share, read again in B)
+            const uint32_t e = entry_of(it);
+            if (e - (uint32_t)lane >= a.groups) break;
+            if (e < a.groups) tbest = max(tbest, __ldcg(gt + e).x);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) local += c[j];
-        int incl = local;
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
+        for (int b = tid; b < kGtBins; b += kGtThreads) lh[b] = 0u;
+        cluster_sync_all();  // every CTA's histogram is zero before anybody adds to the leader's
+        if (tbest != 0u) atomicAdd(&lh[tbest >> 20], 1u);
         __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += s_wsum[w];
-        incl += before;
-        const int excl = incl - local;
-        if (excl < a.kp && incl >= a.kp) {
-            int run = excl, bin = top;
+        if (rank != 0) {
+            for (int b = tid; b < kGtBins; b += kGtThreads) {
+                const unsigned int c = lh[b];
+                if (c != 0u)
+                    asm volatile("red.shared::cluster.add.u32 [%0], %1;" ::"r"(leader_addr(&lh[b])), "r"(c) : "memory");
+            }
+        }
+        cluster_sync_all();
+        if (rank == 0) {
+            // thread t owns bins 4095 - 8 t .. 4088 - 8 t (descending): suffix scan
+            const int top = kGtBins - 1 - 8 * tid;
+            int c[8], local = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (run < a.kp && run + c[j] >= a.kp) bin = top - j;
-                run += c[j];
+                c[j] = (int)lh[top - j];
+                local += c[j];
             }
-            s_cut = bin;
+            int incl = local;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_wsum[w];
+            incl += before;
+            const int excl = incl - local;
+            if (excl < a.kp && incl >= a.kp) {
+                int run = excl, bin = top;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (run < a.kp && run + c[j] >= a.kp) bin = top - j;
+                    run += c[j];
+                }
+                for (uint32_t r = 0; r < (uint32_t)kGtCluster; ++r) {  // hand the cut to every CTA of the cluster
+                    uint32_t ra;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&s_cut)), "r"(r));
+                    st_cluster_u32(ra, (uint32_t)bin);
+                }
+            }
         }
-        __syncthreads();
+        cluster_sync_all();
     }
     const unsigned int cutimg = (unsigned int)s_cut << 20;
     // ---- B
@@ -1693,10 +1736,8 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
         if (a.tiles_per_block < 1u) a.tiles_per_block = 1u;
     }
     if (g.mode == kGemmGroupTop) {
-        if (g.nq > kGtMaxQ || g.d_gtop == nullptr || g.d_hist == nullptr || g.tile_first != 0 || g.tile_stride != 1)
-            return cudaErrorInvalidValue;
+        if (g.nq > kGtMaxQ || g.d_gtop == nullptr || g.tile_first != 0 || g.tile_stride != 1) return cudaErrorInvalidValue;
         a.gtop = g.d_gtop;
-        a.hist = g.d_hist;
         a.groups = 4u * g.tile_count;
     }
     if (g.mode == kGemmFused) {
@@ -1716,11 +1757,10 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
                                 float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
-                                float *q_scale, cudaStream_t stream, unsigned int *gt_hist, unsigned int *gt_state)
+                                float *q_scale, cudaStream_t stream)
 {
     return launch_chain(prep_queries_kernel, dim3(nq), dim3(128), 0, stream, src, (long long)q_stride,
-                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale,
-                        gt_hist, gt_state);
+                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale);
 }
 
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,

@@ -81,12 +81,11 @@ constexpr float kTf32ErrCoeff = 2.2e-3f;  // |tf32 score - exact| <= coeff * |ro
 constexpr float kAccErrCoeff = 2.5e-4f;   // fp32 accumulation inside the tensor core (the slack kTf32ErrCoeff holds too)
 constexpr float kI8ErrCoeff = 2e-6f;      // int8 pass: exact int32 accumulation, then two float roundings of the scales
 // kGemmFused: TILEMAX of each CTA's first tile + grid barrier + thresholds + COLLECT in ONE launch (nq <= 32)
-// kGemmGroupTop: ONE pass, no threshold -- per (32-row group, query) the best two approximate keys go to d_gtop
-// and the best one is counted in a 4096-bin histogram of its score image; grouptop_tail_kernel does the rest
+// kGemmGroupTop: ONE pass, no threshold -- per (32-row group, query) the best two approximate keys go to d_gtop;
+// grouptop_tail_kernel finds the cut (a 4096-bin histogram of score images), re-scores and certifies
 enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2, kGemmFused = 3, kGemmGroupTop = 4 };
 constexpr int kGtBins = 4096;      // histogram bins = top 12 bits of the score image (sign, exponent, 3 mantissa bits)
 constexpr int kGtCap = 1024;       // candidates re-scored per query at most
-constexpr int kGtStateWords = 8;   // per query: [0] candidate count, [1] CTA ticket, [2] best non-candidate key, [3] overflow
 constexpr int kGtMaxQ = 32;        // padded batch sizes that take the one-pass path
 constexpr int kGtMaxK = 32;        // ... up to this K (the tail ranks its candidates with an O(n^2 / threads) count)
 
@@ -117,16 +116,13 @@ struct GemmLaunch {
     float *d_dump;
     unsigned long long dump_ld;
     int sms;
-    uint2 *d_gtop;            // kGemmGroupTop: [nq][4 * tile_count] (best key, second key) of every 32-row group
-    unsigned int *d_hist;     // kGemmGroupTop: [nq][kGtBins], zeroed by prep_queries_launch
+    uint2 *d_gtop;            // kGemmGroupTop: [nq][4 quarters][tile_count] (best key, second key) of every 32-row group
 };
 int gemm_pad_queries(int q);
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
-// gt_hist / gt_state (optional): the one-pass path's histogram [nq][kGtBins] and state [nq][kGtStateWords], zeroed here
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
                                 float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
-                                float *q_scale, cudaStream_t stream, unsigned int *gt_hist = nullptr,
-                                unsigned int *gt_state = nullptr);
+                                float *q_scale, cudaStream_t stream);
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
@@ -164,8 +160,6 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
 // K and certifies them against everything that was not re-scored.  ctas = CTAs per query.
 struct GtTail {
     const uint2 *d_gtop;
-    const unsigned int *d_hist;
-    unsigned int *d_state;
     uint32_t groups;              // 4 * tile_count
     const Segment *d_segs;
     const uint32_t *d_gtile_start;

@@ -1495,8 +1495,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     int kp1 = kp;
     const bool onepass = onepass_applies(q, K, path, device_fixup, &kp1);
     const uint32_t gt_groups = total_gtiles * 4u;
-    const size_t o_gthist = carve(onepass ? (size_t)nq_max * kGtBins * 4 : 0);
-    const size_t o_gtstate = carve(onepass ? (size_t)nq_max * kGtStateWords * 4 : 0);
     const size_t o_gtop = carve(onepass ? (size_t)nq_max * gt_groups * 8 : 0);
     const size_t o_gtexact = carve(onepass ? (size_t)nq_max * kGtCap * 8 : 0);
     const size_t o_gtc2 = carve(onepass ? (size_t)nq_max * kGtCap * 8 : 0);
@@ -1566,9 +1564,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
-                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream,
-                                        onepass ? (unsigned int *)(T + o_gthist) : nullptr,
-                                        onepass ? (unsigned int *)(T + o_gtstate) : nullptr),
+                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
         if (onepass) {
@@ -1578,7 +1574,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             g.tile_stride = 1;
             g.tile_count = total_gtiles;
             g.d_gtop = (uint2 *)(T + o_gtop);
-            g.d_hist = (unsigned int *)(T + o_gthist);
             {
                 std::pair<cudaEvent_t, cudaEvent_t> ev;
                 ctx->prof_begin(stream, &ev);
@@ -1589,8 +1584,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             mark();
             GtTail t{};
             t.d_gtop = g.d_gtop;
-            t.d_hist = g.d_hist;
-            t.d_state = (unsigned int *)(T + o_gtstate);
             t.groups = gt_groups;
             t.d_segs = d_segs;
             t.d_gtile_start = d_gtile_start;
