@@ -823,6 +823,7 @@ int gf_set_search_device_ex(gf_set *set, int limit, int q, const float *d_querie
 }
 
 // ---- peer exchange of per-rank winners over NVLink peer memory (one process per GPU)
+// (gf_set_search_device_xchg, below gf_exchange_merge_device, runs a search that ends with the exchange)
 struct gf_exchange {
     gf_context *ctx = nullptr;
     int rank = 0, world = 1, max_q = 0, max_k = 0;
@@ -903,6 +904,37 @@ int gf_exchange_merge_device(gf_exchange *x, int q, int limit, const uint64_t *d
             GF_ERR_CUDA);
     x->ctx->stats.merge_launches++;
     return GF_OK;
+}
+
+int gf_set_search_device_xchg(gf_set *set, gf_exchange *x, int limit, int q, const float *d_queries,
+                              uint64_t *d_local_keys, uint32_t *d_local_flags, uint64_t *d_out_keys,
+                              uint32_t *d_out_flags, int path, void *stream)
+{
+    if (!set || !x || !x->connected || !d_queries || !d_local_keys || !d_local_flags || !d_out_keys || !d_out_flags)
+        return GF_ERR_INVALID_ARGUMENT;
+    if (q < 1 || limit < 1 || q > x->max_q || limit > x->max_k) return GF_ERR_UNSUPPORTED;
+    return guarded([&]() -> int {
+        // every rank calls this the same number of times in the same order: the sequence number is implicit
+        const unsigned long long seq = ++x->seq;
+        ExchangeArgs a{x->d_peers, x->rank, x->world, q, limit, x->max_q, x->max_k, seq,
+                       (const unsigned long long *)d_local_keys, d_local_flags, (unsigned long long *)d_out_keys,
+                       d_out_flags, 5000000000ull};
+        bool fused = false;
+        int rc = set->search_device(limit, q, d_queries, (unsigned long long *)d_local_keys, path, (cudaStream_t)stream,
+                                    d_local_flags, &a, &fused);
+        if (rc) {
+            --x->seq;  // nothing was pushed: the peers' next step still carries this number
+            return rc;
+        }
+        if (!fused) {
+            GF_CUDA(exchange_merge_launch(x->d_peers, x->rank, x->world, q, limit, x->max_q, x->max_k, seq,
+                                          (const unsigned long long *)d_local_keys, d_local_flags,
+                                          (unsigned long long *)d_out_keys, d_out_flags, (cudaStream_t)stream),
+                    GF_ERR_CUDA);
+            x->ctx->stats.merge_launches++;
+        }
+        return GF_OK;
+    });
 }
 
 int gf_exchange_destroy(gf_exchange *x)

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "gf_device.cuh"
+#include "gf_exchange.cuh"
 #include "gf_kernels.h"
 
 namespace gf {
@@ -1316,7 +1317,7 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
     __shared__ uint32_t s_e[kGtLocal], s_k2[kGtLocal];
     __shared__ int s_wsum[kGtThreads / 32];
     __shared__ int s_cut, s_n, s_nexp;
-    __shared__ unsigned int s_ncmax;
+    __shared__ unsigned int s_ncmax, s_myflag, s_xflag;
     __shared__ unsigned long long s_kth;
     __shared__ unsigned long long s_out[kGtMaxK];  // the answer, written out in one piece (it may live in pinned host memory)
     __shared__ uint32_t s_exp[8];
@@ -1558,6 +1559,15 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
         // rows of groups below the cut: their best key is <= the largest non-candidate key
         if (ok && ncmax_all != 0u && !(key_score(s_kth) > reach(ncmax_all) + delta)) ok = false;
         a.d_flags[qi] = ok ? 0u : 1u;
+        s_myflag = ok ? 0u : 1u;
+    }
+    if (a.has_xchg) {
+        // sharded set: push these K winners and the flag to every rank, wait for theirs, fold (the histogram /
+        // dense-key storage is free again: it holds the world x K keys)
+        static_assert(kGtCap * 16 >= kMergeBuf * 8, "the fold fits the tail's shared memory");
+        __syncthreads();
+        exchange_fold(a.xchg, qi, s_out, s_myflag, reinterpret_cast<unsigned long long *>(s_union), &s_xflag,
+                      a.xchg.out_keys, a.xchg.out_flags);
     }
 }
 

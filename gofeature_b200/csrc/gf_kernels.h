@@ -68,6 +68,18 @@ inline size_t exchange_inbox_bytes(int world, int max_q, int max_k)
 {
     return ((size_t)2 * world * max_q * max_k + (size_t)2 * world * max_q) * 8;
 }
+// arguments of the cross-rank step (exchange_fold, gf_exchange.cuh)
+struct ExchangeArgs {
+    void *const *peers;  // world inbox base pointers (device array); peers[rank] is this rank's own
+    int rank, world, q, K, max_q, max_k;
+    unsigned long long seq;
+    const unsigned long long *local_keys;  // [q][K] (exchange_merge_kernel; the fused tail pushes from shared memory)
+    const unsigned int *local_flags;       // optional [q]
+    unsigned long long *out_keys;          // [q][K]
+    unsigned int *out_flags;               // optional [q]: OR of every rank's flag; 0xFFFFFFFF = a peer never arrived
+    unsigned long long timeout_ns;
+};
+constexpr int kExchangeMergeBuf = 2048;    // world * K keys folded in shared memory
 cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int q, int K, int max_q, int max_k,
                                   unsigned long long seq, const unsigned long long *d_local_keys,
                                   const unsigned int *d_local_flags, unsigned long long *d_out_keys,
@@ -177,9 +189,10 @@ struct GtTail {
     uint2 *d_c2;                  // [q][kGtCap] (second key of the group, group << 5 | lane of the best row)
     unsigned long long *d_out;    // [q][K]
     unsigned int *d_flags;        // [q]
-    int ctas;
     uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment
-    int dbg;
+    // sharded sets: the leader ends with the cross-rank exchange + fold (d_out / d_flags then take the LOCAL winners)
+    int has_xchg;
+    ExchangeArgs xchg;
 };
 cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream);
 

@@ -5,6 +5,7 @@
 // as used at set.go:154-157, on (score,slot) keys instead of Go structs.
 #include <cuda_bf16.h>
 #include "gf_device.cuh"
+#include "gf_exchange.cuh"
 #include "gf_kernels.h"
 
 namespace gf {
@@ -12,29 +13,6 @@ namespace gf {
 namespace {
 
 constexpr int kMergeThreads = 256;
-constexpr int kMergeBuf = 2048;  // keys held in shared memory; kMaxK <= kMergeBuf/2
-
-// bitonic sort (descending) of n (power of two, <= kMergeBuf) keys in shared memory by the CTA
-__device__ void block_sort_desc(unsigned long long *buf, int n)
-{
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = buf[i], b = buf[ixj];
-                    bool desc = ((i & k) == 0);
-                    if (desc ? (a < b) : (a > b)) {
-                        buf[i] = b;
-                        buf[ixj] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 __device__ __forceinline__ int pow2_at_least(int v)
 {
     int p = 2;
@@ -423,86 +401,15 @@ cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int 
 // Inbox (per rank, two slots alternating with the sequence parity so a fast peer can run one step ahead):
 //   keys  [2][world][max_q][max_k] u64      words [2][world][max_q] u64 = seq << 1 | uncertified-flag
 namespace {
-struct ExchangeArgs {
-    void *const *peers;  // world inbox base pointers (device array); peers[rank] is this rank's own
-    int rank, world, q, K, max_q, max_k;
-    unsigned long long seq;
-    const unsigned long long *local_keys;  // [q][K]
-    const unsigned int *local_flags;       // optional [q]
-    unsigned long long *out_keys;          // [q][K]
-    unsigned int *out_flags;               // optional [q]: OR of every rank's flag; 0xFFFFFFFF = a peer never arrived
-    unsigned long long timeout_ns;
-};
-
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 __global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeArgs a)
 {
     __shared__ unsigned long long buf[kMergeBuf];
     __shared__ unsigned int s_flag;
     pdl_wait();
     if (threadIdx.x == 0) pdl_launch_dependents();
-    const int qi = blockIdx.x, K = a.K, world = a.world;
-    const int slot = (int)(a.seq & 1ull);
-    const size_t keys_per_slot = (size_t)world * a.max_q * a.max_k;
-    const size_t words_off = 2 * keys_per_slot;  // in u64 units
-    // ---- push my K keys of this query into every inbox (mine included)
-    for (int i = threadIdx.x; i < world * K; i += blockDim.x) {
-        const int p = i / K, j = i - p * K;
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.peers[p]) + (size_t)slot * keys_per_slot +
-                                  ((size_t)a.rank * a.max_q + qi) * a.max_k + j;
-        *dst = a.local_keys[(size_t)qi * K + j];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) {
-        const unsigned long long word = (a.seq << 1) | ((a.local_flags != nullptr && a.local_flags[qi]) ? 1ull : 0ull);
-        volatile unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[threadIdx.x]) + words_off +
-                                         ((size_t)slot * world + a.rank) * a.max_q + qi;
-        *w = word;
-    }
-    // ---- wait for everybody's keys of this query
-    if (threadIdx.x == 0) s_flag = 0u;
-    __syncthreads();
-    if (threadIdx.x < world) {
-        volatile unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[a.rank]) + words_off +
-                                         ((size_t)slot * world + threadIdx.x) * a.max_q + qi;
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned long long word;
-        unsigned int spins = 0;
-        while (((word = *w) >> 1) != a.seq) {
-            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {  // a peer died: do not hang the GPU
-                atomicOr(&s_flag, 0xFFFFFFFFu);
-                break;
-            }
-        }
-        if (word & 1ull) atomicOr(&s_flag, 1u);
-    }
-    __threadfence_system();
-    __syncthreads();
-    // ---- fold world x K keys (world * K <= kMergeBuf, checked by the host)
-    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(a.peers[a.rank]) +
-                                     (size_t)slot * keys_per_slot;
-    const int n = world * K;
-    int np = 2;
-    while (np < n) np <<= 1;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        unsigned long long v = 0ull;
-        if (i < n) {
-            const int r = i / K, j = i - r * K;
-            v = __ldcv(mine + ((size_t)r * a.max_q + qi) * a.max_k + j);
-        }
-        buf[i] = v;
-    }
-    __syncthreads();
-    block_sort_desc(buf, np);
-    for (int i = threadIdx.x; i < K; i += blockDim.x) a.out_keys[(size_t)qi * K + i] = buf[i];
-    if (a.out_flags != nullptr && threadIdx.x == 0) a.out_flags[qi] = s_flag;
+    const int qi = blockIdx.x;
+    exchange_fold(a, qi, a.local_keys + (size_t)qi * a.K, a.local_flags != nullptr ? a.local_flags[qi] : 0u, buf, &s_flag,
+                  a.out_keys, a.out_flags);
 }
 }  // namespace
 

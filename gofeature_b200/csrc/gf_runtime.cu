@@ -1611,11 +1611,13 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             } else if (phase == 0 && d_flags != nullptr) {
                 t.d_flags = d_flags;       // the caller's own flags: no copy behind the chain
                 flags_direct = true;
+                if (ws->xchg != nullptr && ws->xchg->q == qp && ws->xchg->K == K && qp == q) {
+                    t.has_xchg = 1;        // ... and the cross-rank exchange + fold at the end of the same kernel
+                    t.xchg = *ws->xchg;
+                    ws->xchg_used = true;
+                }
             }
-            // CTAs per query: enough to spread the group scan and the re-scores over the SMs
-            t.ctas = std::max(1, std::min<int>({128, (2 * ctx->sms) / qp, (int)((gt_groups + 511) / 512)}));
             t.tiles_per_block = (uint32_t)std::max<int64_t>(1, (cache->block_size / ((int64_t)dims * 4) + 127) / 128);
-            t.dbg = getenv("GF_TAIL_DBG") ? 1 : 0;
             GF_CUDA(grouptop_tail_launch(t, stream), GF_ERR_CUDA);
             mark();
             ctx->stats.gemm_launches += 1;
@@ -2353,8 +2355,9 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
 }
 
 int Set::search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
-                       cudaStream_t stream, unsigned int *d_flags)
+                       cudaStream_t stream, unsigned int *d_flags, const ExchangeArgs *xchg, bool *xchg_used)
 {
+    if (xchg_used) *xchg_used = false;
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (q > batch) return GF_ERR_OUT_OF_BATCH;
     if (q <= 0 || limit <= 0) return GF_ERR_INVALID_ARGUMENT;
@@ -2384,7 +2387,12 @@ int Set::search_device(int limit, int q, const float *d_queries, unsigned long l
         rc = ws->reserve(need, 0);
         if (rc) return rc;
     }
-    return topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out, path, d_flags);
+    ws->xchg = d_flags != nullptr ? xchg : nullptr;
+    ws->xchg_used = false;
+    rc = topk_device(ws, st, d_queries, q, dims, 1, limit, false, nullptr, d_out, path, d_flags);
+    if (xchg_used) *xchg_used = ws->xchg_used;
+    ws->xchg = nullptr;
+    return rc;
 }
 
 int Set::resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out)

@@ -96,6 +96,9 @@ struct Workspace {
     unsigned long long *direct_out = nullptr;
     unsigned int *direct_flags = nullptr;
     bool wrote_direct = false;
+    // a sharded caller's cross-rank step: the one-pass chain's tail ends with it (sets xchg_used) instead of a launch
+    const ExchangeArgs *xchg = nullptr;
+    bool xchg_used = false;
     void drop_graphs();
     int reserve(size_t d_bytes, size_t h_bytes);
     int reserve_tensor(size_t bytes);
@@ -311,8 +314,11 @@ struct gf_set {
     int search(float threshold, int limit, int q, const uint8_t *queries, Result **out);
     int search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out);
     int search_coalesced(float threshold, int limit, int q, const uint8_t *queries, Result **out);
+    // xchg (optional, needs d_flags): the sharded caller's cross-rank step; *xchg_used tells whether the search's
+    // last kernel performed it (one-pass chain) or the caller still has to launch exchange_merge_launch
     int search_device(int limit, int q, const float *d_queries, unsigned long long *d_out, int path,
-                      cudaStream_t stream, unsigned int *d_flags = nullptr);
+                      cudaStream_t stream, unsigned int *d_flags = nullptr, const gf::ExchangeArgs *xchg = nullptr,
+                      bool *xchg_used = nullptr);
     int resolve_keys(float threshold, int limit, int q, const unsigned long long *h_keys, Result **out);
     // device part of a one-band tensor-path search of q queries gathered from `parts` (pointer, count):
     // the keys [q][kb] are left in the workspace's pinned buffer (*h_keys).  Read lock held by the caller.

@@ -272,13 +272,15 @@ class ShardedSet:
             api._check(L.gf_set_search_device_ex(self.local._h, limit, q, dq.data_ptr(), t["local"].data_ptr(),
                                                  t["mflags"].data_ptr(), path, stream))
             return t["local"]
+        if self._xchg is not None and q <= self._x_max_q and limit <= self._x_max_k:
+            # search + exchange as one call: the one-pass chain's last kernel pushes my winners into every peer's
+            # inbox, waits for theirs and merges (otherwise the exchange kernel is launched behind the search)
+            api._check(L.gf_set_search_device_xchg(self.local._h, self._xchg, limit, q, dq.data_ptr(),
+                                                   t["local"].data_ptr(), t["lflags"].data_ptr(),
+                                                   t["merged"].data_ptr(), t["mflags"].data_ptr(), path, stream))
+            return t["merged"]
         api._check(L.gf_set_search_device_ex(self.local._h, limit, q, dq.data_ptr(), t["local"].data_ptr(),
                                              t["lflags"].data_ptr(), path, stream))
-        if self._xchg is not None and q <= self._x_max_q and limit <= self._x_max_k:
-            # push my winners into every peer's inbox, wait for theirs, merge: one kernel
-            api._check(L.gf_exchange_merge_device(self._xchg, q, limit, t["local"].data_ptr(), t["lflags"].data_ptr(),
-                                                  t["merged"].data_ptr(), t["mflags"].data_ptr(), stream))
-            return t["merged"]
         gathered = gather_keys(t["local"], self.world, self.group, out=t["gathered"])
         api._check(L.gf_merge_keys_device(self.ctx._h, self.world, q, limit, gathered.data_ptr(),
                                           t["merged"].data_ptr(), stream))

@@ -294,6 +294,14 @@ GF_API int gf_exchange_connect(gf_exchange *x, const void *handles, uint64_t len
 GF_API int gf_exchange_merge_device(gf_exchange *x, int q, int limit, const uint64_t *d_local_keys,
                                     const uint32_t *d_local_flags, uint64_t *d_out_keys, uint32_t *d_out_flags,
                                     void *stream);
+/* A device-resident search of this rank's shard that ENDS with the exchange: gf_set_search_device_ex followed by
+ * gf_exchange_merge_device, as one collective call (all ranks, same order).  When the search takes the one-pass chain
+ * its last kernel pushes the winners to the peers, waits for theirs and folds them -- no separate launch; otherwise
+ * the exchange kernel is launched behind it.  d_local_keys [q][limit] / d_local_flags [q] receive this rank's own
+ * winners and flags, d_out_keys / d_out_flags the merged result (flags as in gf_exchange_merge_device). */
+GF_API int gf_set_search_device_xchg(gf_set *set, gf_exchange *x, int limit, int q, const float *d_queries,
+                                     uint64_t *d_local_keys, uint32_t *d_local_flags, uint64_t *d_out_keys,
+                                     uint32_t *d_out_flags, int path, void *stream);
 GF_API int gf_exchange_destroy(gf_exchange *x);
 
 /* Merge `lists` candidate lists (each [q][limit], e.g. the all-gathered per-rank winners)

@@ -72,6 +72,9 @@ def _free_port():
     return p
 
 
+_BIG_ROWS = 180000
+
+
 def _negative_set():
     rows = ol.synth_rows(63, 0, 3000, 512).copy()
     rows[:, 0] = np.abs(rows[:, 0]) + np.float32(0.5)
@@ -108,8 +111,27 @@ def _nccl_worker(rank, world, port, q_out):
         s2.Add(rows2, ids2)
         s2.Delete(*dead2)
         res2 = s2.Search(-10.0, 10, q2)
+        # third set: shards big enough for the tcgen05 path -- the one-pass chain whose tail kernel ENDS with the
+        # cross-rank exchange (gf_set_search_device_xchg), 10 and then 40 queries (the latter: two-pass chain +
+        # the separate exchange kernel), and a deleted winner
+        cache3 = api.NewCache(ctx, 7, 16384 * 512 * 4)
+        s3 = ShardedSet(ctx, cache3, "big", 512, 64, rank, world)
+        s3.AddSynthetic(_BIG_ROWS, 71)
+        big = ol.synth_rows(71, 0, _BIG_ROWS, 512)
+        q3 = ol.synth_rows(72, 0, 40, 512)
+        q3[0] = big[123456]
+        q3[1] = big[7]
+        ctx.ResetStats()
+        res3 = s3.Search(-1.0, 10, q3[:10])
+        st3 = ctx.Stats()
+        assert st3["tensor_passes"] >= 1 and st3["merge_launches"] == 0, st3   # no exchange launch: the tail did it
+        res4 = s3.Search(-1.0, 10, q3)
+        s3.Delete("f%011d" % 123456)
+        res5 = s3.Search(-1.0, 10, q3[:10])
         q_out.put((rank, [[(float(r.Score), r.ID) for r in row] for row in res],
-                   [[(float(r.Score), r.ID) for r in row] for row in res2]))
+                   [[(float(r.Score), r.ID) for r in row] for row in res2],
+                   [[[(float(r.Score), r.ID) for r in row] for row in rr] for rr in (res3, res4, res5)]))
+        cache3.Close()
         cache.Close()
         ctx.Close()
     finally:
@@ -131,9 +153,10 @@ def test_nccl_sharded_search_two_gpus():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    got = {r: a for r, a, _ in outs}
-    got2 = {r: b for r, _, b in outs}
-    assert got[0] == got[1] and got2[0] == got2[1]
+    got = {r: a for r, a, _, _ in outs}
+    got2 = {r: b for r, _, b, _ in outs}
+    got3 = {r: c for r, _, _, c in outs}
+    assert got[0] == got[1] and got2[0] == got2[1] and got3[0] == got3[1]
     oc = model.Cache(12, 1024 * 512 * 4)
     oc.new_set("one", 512, 4, 8)
     o = oc.get_set("one")
@@ -153,3 +176,21 @@ def test_nccl_sharded_search_two_gpus():
     for g, w in zip(got2[0], want2):
         assert [i for _, i in g] == [i for _, i in w]
         assert [s_ for s_, _ in g] == [float(np.float32(s_)) for s_, _ in w]
+    # the tcgen05 shards (fused exchange in the one-pass tail / separate exchange kernel) against the oracle
+    ob = model.Cache(12, 16384 * 512 * 4)
+    ob.new_set("big", 512, 4, 64)
+    o3 = ob.get_set("big")
+    o3.add(ol.synth_rows(71, 0, _BIG_ROWS, 512), ["f%011d" % i for i in range(_BIG_ROWS)])
+    q3 = ol.synth_rows(72, 0, 40, 512)
+    big = ol.synth_rows(71, 0, _BIG_ROWS, 512)
+    q3[0] = big[123456]
+    q3[1] = big[7]
+    wants = [o3.search(-1.0, 10, q3[:10]), o3.search(-1.0, 10, q3)]
+    o3.delete(["f%011d" % 123456])
+    wants.append(o3.search(-1.0, 10, q3[:10]))
+    for gs, ws in zip(got3[0], wants):
+        assert len(gs) == len(ws)
+        for g, w in zip(gs, ws):
+            assert [i for _, i in g] == [i for _, i in w]
+            assert [s_ for s_, _ in g] == [float(np.float32(s_)) for s_, _ in w]
+
