@@ -8,10 +8,15 @@
 // Rows on M / queries on N makes the tensor time scale with the real batch (N/2 cycles per K = 8
 // step) instead of a batch padded to 128, so the kernel stays HBM-bound up to ~256 queries per pass.
 //
-// kind::tf32 reads the fp32 bits and keeps 10 mantissa bits: these scores only SELECT candidates.
-// Every candidate is re-scored in the canonical float32 order (rescore_kernel) and a certificate
-// proves that no row outside the candidate set can be in the top-K (gf_runtime.cu); the Q x N score
-// matrix never leaves the SM except in DUMP mode (small sets / diagnostics).
+// kind::tf32 reads the fp32 bits and keeps 10 mantissa bits (kind::f16 / kind::i8 read a bf16 / int8 shadow of
+// the rows): these scores only SELECT candidates.  Every candidate is re-scored in the canonical float32 order
+// and a certificate proves that no row outside the candidate set can be in the top-K; the Q x N score
+// matrix never leaves the SM except in DUMP mode (small sets / diagnostics).  Epilogue modes:
+//   COLLECT  (0) compare against a per-query threshold estimated by a TILEMAX (1) sample, append the survivors
+//                (select / rescore / finalize kernels follow: the two-pass chain)
+//   GROUPTOP (4) no threshold: the best two keys of every 32-row group per query; grouptop_tail_kernel (one
+//                thread-block cluster per query) cuts, re-scores, certifies -- the one-pass chain of small batches
+//   DUMP (2), FUSED (3, experimental) as described at their code
 //
 // Warp roles (192 threads): warp 0 TMA producer (one thread), warp 1 TMEM allocator + MMA issuer
 // (one thread), warps 2..5 epilogue (tcgen05.ld, one feature row per thread).
