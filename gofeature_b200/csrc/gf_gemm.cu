@@ -1359,10 +1359,16 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
         unsigned int tbest = 0u;
 #pragma unroll
         for (int u = 0; u < kGtPre; ++u) tbest = max(tbest, pre[u].x);
-        for (int it = kGtPre;; ++it) {  // (sets beyond 1 M rows: the rest of this thread's share, read again in B)
-            const uint32_t e = entry_of(it);
-            if (e - (uint32_t)lane >= a.groups) break;
-            if (e < a.groups) tbest = max(tbest, __ldcg(gt + e).x);
+        // (sets beyond 1 M rows: the rest of this thread's share, kGtPre independent loads at a time; read again in B)
+        for (int it0 = kGtPre; entry_of(it0) - (uint32_t)lane < a.groups; it0 += kGtPre) {
+            uint2 more[kGtPre];
+#pragma unroll
+            for (int u = 0; u < kGtPre; ++u) {
+                const uint32_t e = entry_of(it0 + u);
+                more[u] = e < a.groups ? __ldcg(gt + e) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kGtPre; ++u) tbest = max(tbest, more[u].x);
         }
         for (int b = tid; b < kGtBins; b += kGtThreads) lh[b] = 0u;
         cluster_sync_all();  // every CTA's histogram is zero before anybody adds to the leader's
@@ -1432,10 +1438,18 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
             const uint32_t e = entry_of(u);
             if (e < a.groups) classify(e, pre[u]);
         }
-        for (int it = kGtPre;; ++it) {
-            const uint32_t e = entry_of(it);
-            if (e - (uint32_t)lane >= a.groups) break;  // (warp-uniform)
-            if (e < a.groups) classify(e, __ldcg(gt + e));
+        for (int it0 = kGtPre; entry_of(it0) - (uint32_t)lane < a.groups; it0 += kGtPre) {  // (warp-uniform bound)
+            uint2 more[kGtPre];
+#pragma unroll
+            for (int u = 0; u < kGtPre; ++u) {
+                const uint32_t e = entry_of(it0 + u);
+                more[u] = e < a.groups ? __ldcg(gt + e) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kGtPre; ++u) {
+                const uint32_t e = entry_of(it0 + u);
+                if (e < a.groups) classify(e, more[u]);
+            }
         }
         ncmax = __reduce_max_sync(0xffffffffu, ncmax);
         if (lane == 0 && ncmax != 0u) atomicMax(&s_ncmax, ncmax);

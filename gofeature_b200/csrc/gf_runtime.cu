@@ -1419,8 +1419,13 @@ bool Set::onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out
     // batch collects): deep enough that the certificate's margin, score[K] - score[cut], clears delta on small sets
     const int kp1 = std::max(kp, 6 * K + 64);
     if (kp_out) *kp_out = kp1;
+    // The GROUPTOP pass is a few per cent slower per tile than COLLECT (measured: +1.8 us per million rows at one
+    // query, +5.7 us at ten), the chain around it ~17 us shorter: beyond these sizes the two-pass chain wins
+    // (10 M rows, 10 queries: 0.790 vs 0.823 ms).  Path 2 / 3 (tests, sweeps) pins the one-pass chain at any size.
+    const int64_t row_limit = q <= 2 ? 8000000 : 3000000;
+    const bool size_ok = path == 2 || path == 3 || scanned_rows <= row_limit;
     return onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && K <= kGtMaxK && kp1 <= kGtCap / 2 &&
-           (uint64_t)total_gtiles * 4u < (1ull << 27);
+           size_ok && (uint64_t)total_gtiles * 4u < (1ull << 27);
 }
 
 int Set::topk_eager(Workspace *ws, cudaStream_t stream, const float *d_queries, int q, int64_t q_stride,

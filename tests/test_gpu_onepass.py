@@ -46,8 +46,11 @@ def _unit(v):
     (512, 70000, 32, 32),
     (128, 140000, 5, 10),
     (1024, 66000, 2, 32),
+    (128, 1200000, 10, 10),     # more than 32 768 groups per query: the tail's threads take several rounds of entries
 ])
 def test_onepass_parity(gpu_ctx, dims, n, q, limit, fmt):
+    if n > 1000000 and fmt != "int8":
+        pytest.skip("the large geometry runs once, on the default shadow")
     block_rows = 16384
     cache, st, ost = _pair(gpu_ctx, "onepass", dims, q, block_rows, (n + block_rows - 1) // block_rows + 1, shadow=fmt)
     st.AddSynthetic(n, 4242 + dims)
