@@ -317,7 +317,10 @@ constexpr int kAppendPerWarp = 16;
 constexpr int kAppendStageBytes = kAppendStage * 12 + 64;
 // GROUPTOP: each epilogue warp stages its (best, second) keys of kGtFlush consecutive tiles per query column in its own
 // piece of shared memory and writes them out 128 bytes per column at a time (rows padded to 17 entries: bank spread)
-constexpr int kGtFlush = 16;
+#ifndef GF_GT_FLUSH
+#define GF_GT_FLUSH 64
+#endif
+constexpr int kGtFlush = GF_GT_FLUSH;  // a multiple of 16 (128 bytes of keys per column), 32 entries per warp store
 constexpr int kGtStageRow = kGtFlush + 1;
 __host__ __device__ constexpr int gt_stage_bytes(int nq) { return nq <= kGtMaxQ ? 4 * nq * kGtStageRow * 8 : 0; }
 
@@ -705,10 +708,14 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                             if (fslot == kGtFlush - 1 || it + 1 >= g_count) {
                                 __syncwarp();
                                 const uint32_t i0 = i - fslot;  // (a worker's tiles are consecutive in this mode)
-                                if ((uint32_t)lane <= fslot) {
-                                    uint2 *dst = a.gtop + (size_t)quarter * a.tile_count + i0 + lane;
+#pragma unroll
+                                for (uint32_t s0 = 0; s0 < (uint32_t)kGtFlush; s0 += 32u) {
+                                    const uint32_t sl = s0 + (uint32_t)lane;
+                                    if (sl <= fslot) {
+                                        uint2 *dst = a.gtop + (size_t)quarter * a.tile_count + i0 + sl;
 #pragma unroll 4
-                                    for (int c = 0; c < a.q; ++c) dst[(size_t)c * a.groups] = stw[c * kGtStageRow + lane];
+                                        for (int c = 0; c < a.q; ++c) dst[(size_t)c * a.groups] = stw[c * kGtStageRow + sl];
+                                    }
                                 }
                                 __syncwarp();
                             }

@@ -1419,10 +1419,11 @@ bool Set::onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out
     // batch collects): deep enough that the certificate's margin, score[K] - score[cut], clears delta on small sets
     const int kp1 = std::max(kp, 6 * K + 64);
     if (kp_out) *kp_out = kp1;
-    // The GROUPTOP pass is a few per cent slower per tile than COLLECT (measured: +1.8 us per million rows at one
-    // query, +5.7 us at ten), the chain around it ~17 us shorter: beyond these sizes the two-pass chain wins
-    // (10 M rows, 10 queries: 0.790 vs 0.823 ms).  Path 2 / 3 (tests, sweeps) pins the one-pass chain at any size.
-    const int64_t row_limit = q <= 2 ? 8000000 : 3000000;
+    // The GROUPTOP pass is 1 - 3 % slower per tile than COLLECT and its tail reads 8 bytes per 32 rows and query,
+    // the chain around it ~17 us shorter.  Measured (one-pass vs two-pass, ms per step): 4 M rows 0.312 / 0.337 at
+    // one query, 0.340 / 0.338 at ten; 10 M rows 0.748 / 0.766 and 0.806 / 0.781.  Path 2 / 3 (tests, sweeps) pins
+    // the one-pass chain at any size.
+    const int64_t row_limit = q <= 2 ? 12000000 : 3000000;
     const bool size_ok = path == 2 || path == 3 || scanned_rows <= row_limit;
     return onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && K <= kGtMaxK && kp1 <= kGtCap / 2 &&
            size_ok && (uint64_t)total_gtiles * 4u < (1ull << 27);
