@@ -367,7 +367,8 @@ def run_ours(args, rank, world, local_rank):
             cache = None
             try:
                 out = subprocess.run([exe, "--rows", str(args.rows_per_gpu), "--threads", str(Q), "--rounds",
-                                      str(max(args.steps, 50)), "--limit", str(K), "--coalesce-us", "100",
+                                      str(max(args.steps, 200)), "--warm-rounds", str(max(args.warmup, 30)),
+                                      "--limit", str(K), "--coalesce-us", "100",
                                       "--device", str(local_rank)], capture_output=True, text=True, timeout=300)
                 if out.returncode == 0:
                     demo = json.loads(out.stdout.strip().splitlines()[-1])

@@ -43,6 +43,7 @@ int main(int argc, char **argv)
     const int dims = (int)arg(argc, argv, "--dims", 512);       // Dimension demo/main.go:21
     const int threads = (int)arg(argc, argv, "--threads", 5);   // SearchParallel demo/main.go:27
     const int rounds = (int)arg(argc, argv, "--rounds", 200);   // Round     demo/main.go:24
+    const int warm_rounds = (int)arg(argc, argv, "--warm-rounds", 30);  // untimed rounds of all searcher threads
     const int batch = (int)arg(argc, argv, "--batch", 1);       // Batch     demo/main.go:22
     const int limit = (int)arg(argc, argv, "--limit", 10);
     const int coalesce = (int)arg(argc, argv, "--coalesce-us", 30);
@@ -85,6 +86,23 @@ int main(int argc, char **argv)
         gf_result *r;
         CK(gf_set_search(set, 0.f, limit, batch, qpool.data(), (uint64_t)batch * dims * 4, &r));
         gf_result_free(r);
+    }
+    // ... and with every searcher thread at once: the batch shapes the coalescer forms (2 .. threads queries) are each
+    // recorded as a CUDA graph on first use, which must not fall into the timed rounds
+    if (warm_rounds > 0 && threads > 1) {
+        std::vector<std::thread> wt;
+        for (int p = 0; p < threads; ++p) {
+            wt.emplace_back([&, p]() {
+                for (int b = 0; b < warm_rounds; ++b) {
+                    const float *q = qpool.data() + (size_t)((b * threads + p) % pool) * batch * dims;
+                    gf_result *r;
+                    int rc = gf_set_search(set, 0.f, limit, batch, q, (uint64_t)batch * dims * 4, &r);
+                    if (rc) die("gf_set_search (warm-up)", rc);
+                    gf_result_free(r);
+                }
+            });
+        }
+        for (auto &t : wt) t.join();
     }
     gf_context_reset_stats(ctx);
 
