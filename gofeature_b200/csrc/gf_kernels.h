@@ -166,10 +166,11 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
                             cudaStream_t stream);
 
-// The one-pass path's second (and last) kernel: per query, cut = the histogram bin that holds the kp-th best
-// group; every group at or above the cut has its best row re-scored exactly (canonical float32 order); the last
-// CTA of a query ranks the exact keys, re-scores whole groups whose SECOND key could still matter, emits the best
-// K and certifies them against everything that was not re-scored.  ctas = CTAs per query.
+// The one-pass path's last kernel, one thread-block cluster per query: cut = the histogram bin that holds the kp-th
+// best group; every group at or above the cut has its best row re-scored exactly (canonical float32 order); the
+// cluster's leader ranks the exact keys, re-scores whole groups whose SECOND key could still matter, emits the best K
+// and certifies them against everything that was not re-scored -- and, for a sharded set, ends with the cross-rank
+// exchange (has_xchg).
 struct GtTail {
     const uint2 *d_gtop;
     uint32_t groups;              // 4 * tile_count
@@ -185,8 +186,6 @@ struct GtTail {
     float err_coeff;
     const float *d_qres2;
     const unsigned int *d_maxres2_bits;
-    unsigned long long *d_exact;  // [q][kGtCap]
-    uint2 *d_c2;                  // [q][kGtCap] (second key of the group, group << 5 | lane of the best row)
     unsigned long long *d_out;    // [q][K]
     unsigned int *d_flags;        // [q]
     uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment

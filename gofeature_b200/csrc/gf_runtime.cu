@@ -1502,8 +1502,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const bool onepass = onepass_applies(q, K, path, device_fixup, &kp1);
     const uint32_t gt_groups = total_gtiles * 4u;
     const size_t o_gtop = carve(onepass ? (size_t)nq_max * gt_groups * 8 : 0);
-    const size_t o_gtexact = carve(onepass ? (size_t)nq_max * kGtCap * 8 : 0);
-    const size_t o_gtc2 = carve(onepass ? (size_t)nq_max * kGtCap * 8 : 0);
     int rc = ws->reserve_tensor(off);
     if (rc) return rc;
     uint8_t *T = ws->d_tensor;
@@ -1606,8 +1604,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             t.err_coeff = err_coeff;
             t.d_qres2 = d_qres;
             t.d_maxres2_bits = d_small + 2;
-            t.d_exact = (unsigned long long *)(T + o_gtexact);
-            t.d_c2 = (uint2 *)(T + o_gtc2);
             t.d_out = d_out + (size_t)p0 * K;
             t.d_flags = d_fl + p0;
             if (phase == 2 && ws->direct_out != nullptr && ws->direct_flags != nullptr) {
