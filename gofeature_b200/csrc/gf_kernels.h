@@ -79,7 +79,6 @@ struct ExchangeArgs {
     unsigned int *out_flags;               // optional [q]: OR of every rank's flag; 0xFFFFFFFF = a peer never arrived
     unsigned long long timeout_ns;
 };
-constexpr int kExchangeMergeBuf = 2048;    // world * K keys folded in shared memory
 cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int q, int K, int max_q, int max_k,
                                   unsigned long long seq, const unsigned long long *d_local_keys,
                                   const unsigned int *d_local_flags, unsigned long long *d_out_keys,
