@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- search QPS of the brute-force cosine top-K hot path on B200.
 
-Workload (BASELINE.json configs[1]): 1 000 000 x 512-d L2-normalised float32 features per GPU
+Headline workload (BASELINE.json configs[1]): 1 000 000 x 512-d L2-normalised float32 features per GPU
 (2.048 GB, 62 blocks of 32 MiB = demo geometry, demo/main.go:19-23), top-10, 10 concurrent
 single-query searchers.  One "step" serves one query from each of the 10 searchers.
 
@@ -9,23 +9,36 @@ single-query searchers.  One "step" serves one query from each of the 10 searche
             preparation, the tcgen05 candidate pass over the int8 shadow slab, the tail kernel that re-scores
             the candidates from the float32 rows and certifies them; at N > 1 also the exchange of 10 keys
             per query per rank over NVLink peer memory and the cross-rank merge), CUDA-event timed, max
-            over ranks.  Weak scaling: every rank holds its own 1 M-row shard of an N-million-row set, and
-            a query is counted once per 1 M-row shard it scans (N per query), so value is the
-            1 M-row-equivalent QPS of the whole job; `qps_user` is the plain end-user QPS.
-  e2e       the same through the public host-buffer call: 10 real host threads x gf_set_search(q=1),
-            coalesced by the library (tools/gf_demo; at N > 1 the collective ShardedSet.search_keys): queries
-            read from pinned host memory and winners written back to it inside the timed region.
+            over ranks.  The driver's K steps are repeated back to back until >= 1.2 s of device time has been
+            measured (every repetition bracketed by its own events); value / ms_per_step are the MEDIAN
+            repetition.  Weak scaling: every rank holds its own 1 M-row shard of an N-million-row set, and a
+            query is counted once per 1 M-row shard it scans (N per query), so value is the 1 M-row-equivalent
+            QPS of the whole job; `qps_user` is the plain end-user QPS.
+  e2e       the same through the public host-buffer call: N = 1: 10 real host threads x gf_set_search(q=1),
+            coalesced by the library (tools/gf_demo); N > 1: one caller, gf_set_search(q=10) on a set the library
+            itself shards over the N devices of the process (gf_context_create_multi) when available, else the
+            collective ShardedSet.search_keys.  Queries are read from host memory and winners written back to
+            it inside the timed region.
+  parity_check
+            after the timed regions every batch of the query pool is answered again by the exact float32
+            scan kernel (path 1) and compared key for key with what the timed path returned; stored rows owned
+            by every rank are searched as needles.  mismatches must be 0 (bench exits non-zero otherwise).
   roofline  the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  With the
             int8 shadow slab (default) that kernel is the tcgen05 kind::i8 candidate pass and its algorithmic
             bytes are the SHADOW bytes it must stream (rows x dims x 1 + one float scale per row), not the
             float32 bytes: the fraction says how well the kernel uses HBM, the smaller traffic shows up in
             `value`.  `float32_paths` times the same step WITHOUT the shadow (kind::tf32 over the float32
             rows, and the fused exact scan), whose algorithmic bytes are SURVEY 8(d)'s rows x dims x 4.
+  legs      config3 (1024 queries x top-100, tensor roofline), config4_shard (12.5 M rows per GPU, 64 queries:
+            at --gpus 8 the 100 M-row set), strong_scaling (8 M rows split over the ranks), churn (10 M rows,
+            Add / Delete 100 k rows under concurrent searches), baselines (the reference's own cuBLAS path
+            replayed on this GPU, a 1-thread CPU scan, numpy/BLAS) -- extra keys of the same JSON line.
   cpu_baseline / --impl reference
             the oracle's plain multi-threaded CPU scan ("port": the reference has no CPU build and
-            there is no Go toolchain) on a bounded row sample, scaled to 1 M rows.
+            there is no Go toolchain) over the FULL 1 M rows, persistent thread pool, all host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -40,10 +53,12 @@ sys.path.insert(0, ROOT)
 
 DIMS = 512
 BLOCK_SIZE = 1024 * 1024 * 32      # demo/main.go:19
+CAP = BLOCK_SIZE // (DIMS * 4)
 SEED = 20260101
 QUERY_SEED = 20260102
 UNIT = "queries/s"
 METRIC = "search_qps_1Mx512_top10_parallel10"
+MIN_TIMED_S = 1.2
 
 
 def make_queries(n, dims, seed):
@@ -66,7 +81,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -75,9 +90,6 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
-
-    def mark(self):
-        return time.time()
 
     def stop(self):
         if self.proc:
@@ -88,28 +100,36 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or \
-               [r for _, r in self.rows if len(r) >= 7]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7]
+        inside = len(rows)
+        if not rows:
+            rows = [r for t, r in self.rows if t0 - 0.1 <= t <= t1 + 0.2 and len(r) >= 7] or \
+                   [r for _, r in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+                "samples": len(rows), "samples_inside_timed_region": inside,
+                "power_w_max": max(float(r[2]) for r in rows)}
 
 
-def hbm_peak():
+def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            d = json.load(f)
+        return {"hbm": float(d["hbm_gbs"]), "hbm_src": "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "bf16": float(d.get("bf16_tflops", 1642.4)),
+                "bf16_src": "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)"}
+    return {"hbm": 6650.0, "hbm_src": "fallback (B200_PROFILING.md 6.65 TB/s)", "bf16": 1650.0,
+            "bf16_src": "fallback (B200_PROFILING.md)"}
 
 
 def traffic_from_profile(eb):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture of the same
-    kernel (eb = bytes per element it streams: 4 float32 rows, 2 bf16 shadow), if any."""
+    kernel (eb = bytes per element it streams: 4 float32 rows, 2 bf16 shadow, 1 int8 shadow), if any."""
     p = os.path.join(ROOT, "profiles", {4: "scan_traffic.json", 2: "shadow_traffic.json", 1: "shadow_i8_traffic.json"}[eb])
     if os.path.exists(p):
         with open(p) as f:
@@ -117,54 +137,69 @@ def traffic_from_profile(eb):
     return None
 
 
-# --------------------------------------------------------------------------- CPU arms
-def cpu_scan_qps(sample_rows, nq, limit, min_seconds, rows_full):
-    """The oracle's multi-threaded plain scan on `sample_rows` rows; QPS scaled to rows_full rows."""
+# --------------------------------------------------------------------------- CPU arms (the oracle: checker / baseline only)
+def cpu_port_qps(rows, nq, limit, min_seconds, threads, max_passes=400):
+    """The oracle's plain scan over `rows` rows (persistent thread pool) -> (qps, ms per pass, passes)."""
     from oracle import lib as ol
-    cores = os.cpu_count() or 1
-    X = ol.synth_rows(SEED, 0, sample_rows, DIMS)
+    X = ol.synth_rows(SEED, 0, rows, DIMS)
     Q = make_queries(nq, DIMS, QUERY_SEED)
-    ol.scan_topk(X[:1000], Q, limit, ol.MODE_CANONICAL, cores)  # warm
+    ol.scan_topk(X[:4096], Q, limit, ol.MODE_CANONICAL, threads)  # warm: the pool's threads exist
+    ol.scan_topk(X, Q, limit, ol.MODE_CANONICAL, threads)
     t0 = time.perf_counter()
-    reps, times = 0, []
+    times = []
     while True:
         a = time.perf_counter()
-        ol.scan_topk(X, Q, limit, ol.MODE_CANONICAL, cores)
+        ol.scan_topk(X, Q, limit, ol.MODE_CANONICAL, threads)
         times.append(time.perf_counter() - a)
-        reps += 1
-        if time.perf_counter() - t0 >= min_seconds and reps >= 2:
+        if (time.perf_counter() - t0 >= min_seconds and len(times) >= 3) or len(times) >= max_passes:
             break
     per_pass = float(np.median(times))
-    qps_sample = nq / per_pass
-    return {"value": qps_sample * sample_rows / rows_full, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of %d rows x %d-d, %d queries top-%d per pass, %d passes, median %.1f ms/pass, "
-                      "oracle canonical-order AVX2 scan, pthreads; QPS scaled by rows ratio"
-                      % (sample_rows, rows_full, DIMS, nq, limit, reps, per_pass * 1e3)}, per_pass
+    return nq / per_pass, per_pass * 1e3, len(times), X, Q
+
+
+def cpu_blas_qps(X, Q, limit, min_seconds):
+    """'Best library CPU': numpy (OpenBLAS sgemm, all cores) scores + argpartition + sort of the K best."""
+    def one():
+        S = X @ Q.T                                           # [rows, q]
+        idx = np.argpartition(-S, limit - 1, axis=0)[:limit]  # [limit, q]
+        top = np.take_along_axis(S, idx, axis=0)
+        order = np.argsort(-top, axis=0, kind="stable")
+        return np.take_along_axis(idx, order, axis=0)
+    one()
+    t0, times = time.perf_counter(), []
+    while True:
+        a = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - a)
+        if (time.perf_counter() - t0 >= min_seconds and len(times) >= 3) or len(times) >= 200:
+            break
+    per = float(np.median(times))
+    return Q.shape[0] / per, per * 1e3, len(times)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path.  goFeature has no non-cublas build and this image
-    has no Go toolchain, so this is the oracle port (plain brute-force scan, all host threads)."""
+    has no Go toolchain, so this is the oracle port (plain brute-force scan, all host threads, persistent
+    pool) over the full workload: every step scans all rows_per_gpu rows for the step's queries."""
     if rank != 0:
         return
     from oracle import lib as ol
     cores = os.cpu_count() or 1
-    rows_full = args.rows_per_gpu
-    sample = min(args.cpu_sample_rows, rows_full)
-    X = ol.synth_rows(SEED, 0, sample, DIMS)
+    rows = args.rows_per_gpu
+    X = ol.synth_rows(SEED, 0, rows, DIMS)
     Q = make_queries(args.queries, DIMS, QUERY_SEED)
+    ol.scan_topk(X[:4096], Q, args.limit, ol.MODE_CANONICAL, cores)
     for _ in range(max(args.warmup, 1)):
         ol.scan_topk(X, Q, args.limit, ol.MODE_CANONICAL, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ol.scan_topk(X, Q, args.limit, ol.MODE_CANONICAL, cores)
     dt = time.perf_counter() - t0
-    ms_step_sample = dt / args.steps * 1e3
-    ms_step = ms_step_sample * rows_full / sample
+    ms_step = dt / args.steps * 1e3
     # same unit as the GPU arm (1 M-row shard scans per second): the host cores are one pool, so it does not grow with N
     value = args.queries / (ms_step / 1e3)
-    sample_txt = ("each step scans %d of %d rows (%d queries top-%d, all %d host threads) and is scaled by the "
-                  "rows ratio" % (sample, rows_full, args.queries, args.limit, cores))
+    sample_txt = ("each step scans all %d rows x %d-d for %d queries top-%d with %d host threads (persistent pool); "
+                  "%d steps, %.1f s" % (rows, DIMS, args.queries, args.limit, cores, args.steps, dt))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -183,59 +218,190 @@ def bench_config(args, world):
                        "none": "none (float32 rows only)"}[fmt],
             "workload": "BASELINE configs[1]: %d x %d-d normalised float32 rows per GPU (%d blocks of 32 MiB), "
                         "top-%d, %d concurrent single-query searchers per step"
-                        % (args.rows_per_gpu, DIMS, (args.rows_per_gpu + 16383) // 16384, args.limit, args.queries),
+                        % (args.rows_per_gpu, DIMS, (args.rows_per_gpu + CAP - 1) // CAP, args.limit, args.queries),
             "rows_per_gpu": args.rows_per_gpu, "rows_total": args.rows_per_gpu * world, "dims": DIMS,
             "limit": args.limit, "queries_per_step": args.queries, "sharding": "row-sharded x%d" % world,
-            "l2": "inputs exceed L2 (2.05 GB per GPU streamed per pass vs 126 MB L2)"}
+            "l2": "inputs exceed L2 (0.51 GB int8 shadow / 2.05 GB float32 rows per GPU streamed per pass vs 126 MB L2)"}
 
 
 # --------------------------------------------------------------------------- GPU arm
+class Harness:
+    """One rank's view of the job: torch.distributed plumbing + event timing helpers."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, xs):
+        """element-wise max over ranks of a list of floats."""
+        if self.world == 1:
+            return list(xs)
+        t = self.torch.tensor(list(xs), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().tolist()
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed_reps(self, step, steps, min_seconds, max_reps=20000):
+        """`steps` calls of step(i) per repetition, repetitions back to back until min_seconds of device time;
+        every repetition has its own CUDA events.  Returns (per-repetition ms, max over ranks; wall marks)."""
+        torch = self.torch
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            step(i)
+        b.record()
+        torch.cuda.synchronize()
+        first = self.max_over_ranks([a.elapsed_time(b)])[0]
+        reps = int(min(max_reps, max(1, np.ceil(min_seconds * 1e3 / max(first, 1e-3)))))
+        self.barrier()
+        t0 = time.time()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        evs[0].record()
+        k = 0
+        for r in range(reps):
+            for i in range(steps):
+                step(k)
+                k += 1
+            evs[r + 1].record()
+        self.barrier()
+        t1 = time.time()
+        ms = self.max_over_ranks([evs[r].elapsed_time(evs[r + 1]) for r in range(reps)])
+        return ms, t0, t1
+
+
+def kernel_ms(stats):
+    if stats["tensor_passes"] > 0:
+        return stats["gemm_kernel_ns"] / 1e6 / max(stats["gemm_kernel_timed"], 1), stats["gemm_kernel_timed"], True
+    return stats["scan_kernel_ns"] / 1e6 / max(stats["scan_kernel_timed"], 1), stats["scan_kernel_timed"], False
+
+
+def profile_kernel(ctx, fn, n):
+    """n calls of fn() with CUDA events around every launch of the dominant kernel (the library brackets them on
+    the launching stream; profiling runs the pipeline un-graphed, kernel for kernel)."""
+    import torch
+    ctx.ResetStats()
+    ctx.SetProfiling(True)
+    for i in range(n):
+        fn(i)
+    torch.cuda.synchronize()
+    st = ctx.Stats()
+    ctx.SetProfiling(False)
+    ms, launches, tensor = kernel_ms(st)
+    return ms, launches / float(n), tensor, st
+
+
+def new_sharded(H, api, ShardedSet, ctx, rows_total, batch, shadow, name):
+    gblocks = (rows_total + CAP - 1) // CAP
+    cache = api.NewCache(ctx, (gblocks + H.world - 1) // H.world + 1, BLOCK_SIZE, shadow=shadow)
+    sset = ShardedSet(ctx, cache, name, DIMS, batch, H.rank, H.world)
+    sset.AddSynthetic(rows_total, SEED)
+    return cache, sset
+
+
+def parity_check(H, sset, pool_dev, K, Q, rows_total):
+    """Every batch of the pool: the default path's keys against the exact float32 scan's (path 1), key for key;
+    plus needles -- one stored row owned by each rank must come back first with score ~1."""
+    torch = H.torch
+    npool = pool_dev.shape[0]
+    mism = flagged = 0
+    for b in range(npool):
+        k0 = sset.search_device(K, Q, pool_dev[b]).clone()
+        f0 = sset.flags(Q, K).clone()
+        k1 = sset.search_device(K, Q, pool_dev[b], path=1).clone()
+        torch.cuda.synchronize()
+        bad = (k0 != k1).any(dim=1)
+        fl = f0 != 0
+        flagged += int(fl.sum().item())
+        mism += int((bad & ~fl).sum().item())       # a flagged query is re-run by the caller; an unflagged one must be exact
+    # needles: rank r reads a row it owns back through the C ABI (gf_set_read) and everyone searches for it
+    needles = torch.zeros((H.world, DIMS), dtype=torch.float32, device="cuda")
+    ordinals = []
+    for r in range(H.world):
+        g = r + H.world * max(0, ((rows_total // CAP) // H.world) // 2)      # a global block owned by rank r
+        o = min(g * CAP + 77, rows_total - 1)
+        if (o // CAP) % H.world != r:
+            o = r * CAP + 77 if r * CAP + 77 < rows_total else None
+        ordinals.append(o)
+        if o is not None and r == H.rank:
+            feats = sset.local.Read("f%011d" % o)
+            if feats:
+                needles[r] = torch.from_numpy(np.frombuffer(feats[0].Value, dtype=np.float32).copy()).cuda()
+    if H.world > 1:
+        H.dist.all_reduce(needles)
+    ok = True
+    from gofeature_b200 import api
+    for r0 in range(0, H.world, Q):
+        nb = min(Q, H.world - r0)
+        qb = torch.zeros((Q, DIMS), dtype=torch.float32, device="cuda")
+        qb[:nb] = needles[r0:r0 + nb]
+        qb[nb:] = pool_dev[0][:Q - nb]
+        keys = sset.search_device(K, Q, qb).clone()
+        torch.cuda.synchronize()
+        hk = keys.cpu().numpy().view(np.uint64)
+        for j in range(nb):
+            o = ordinals[r0 + j]
+            if o is None:
+                continue
+            ok = ok and api.key_slot(hk[j][0]) == o and abs(float(api.key_score(hk[j][0])) - 1.0) < 1e-5
+    return {"batches": npool, "queries": npool * Q, "mismatches": mism, "flagged_queries": flagged,
+            "needles": sum(1 for o in ordinals if o is not None), "needles_ok": bool(ok),
+            "against": "exact float32 scan kernel (path 1) on the same resident rows; both paths are bit-exact "
+                       "against the CPU oracle in tests/test_gpu_configs.py"}
+
+
+def run_tool(cmd, timeout):
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if out.returncode == 0 and out.stdout.strip():
+            return json.loads(out.stdout.strip().splitlines()[-1])
+        return {"error": "rc=%d %s" % (out.returncode, (out.stderr or "")[-300:])}
+    except Exception as exc:  # the bench line must still come out
+        return {"error": str(exc)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
-    import torch.distributed as dist
 
     from gofeature_b200 import _capi, api
     from gofeature_b200.sharded import ShardedSet
 
     _capi.lib()  # raises if the CUDA library is missing: no fallback
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    Q, K, rows_total = args.queries, args.limit, args.rows_per_gpu * world
+    H = Harness(rank, world, local_rank)
+    PK = peaks()
+    Q, K = args.queries, args.limit
+    rows_total = args.rows_per_gpu * world
     ctx = api.NewContext(local_rank)
-    cap = BLOCK_SIZE // (DIMS * 4)
-    gblocks = (rows_total + cap - 1) // cap
-    cache = api.NewCache(ctx, (gblocks + world - 1) // world + 1, BLOCK_SIZE,
-                         shadow=False if args.no_shadow else args.shadow)
+    shadow = False if args.no_shadow else args.shadow
+    cache, sset = new_sharded(H, api, ShardedSet, ctx, rows_total, max(Q, 16, 1024 if world == 1 else 16), shadow, "bench")
     shadow_eb = cache.ShadowBytesPerElement()
-    sset = ShardedSet(ctx, cache, "bench", DIMS, max(Q, 16), rank, world)
-    sset.AddSynthetic(rows_total, SEED)
     rows_local = sset.local.ScannedRows()
 
     npool = 32
     pool = make_queries(npool * Q, DIMS, QUERY_SEED).reshape(npool, Q, DIMS)
     dpool = torch.from_numpy(pool).cuda()
     hpool = torch.from_numpy(pool).pin_memory()
+    lean = api.lib()
+    handle = ctypes.c_void_p()
 
     def step_device(i):
         return sset.search_device(K, Q, dpool[i % npool])
-
-    lean = api.lib()
-    import ctypes
-    handle = ctypes.c_void_p()
 
     def step_e2e(i):
         if world == 1:
@@ -253,155 +419,151 @@ def run_ours(args, rank, world, local_rank):
     for i in range(W):
         step_device(i)
         step_e2e(i)
-    barrier()
+    H.barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if rank == 0 else 0.0)
+    time.sleep(0.25 if rank == 0 else 0.0)
+    flagged0 = sset.local.DeviceCounters()[0]
     ctx.ResetStats()
-    barrier()
-    t_mark0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        step_device(i)
-    ev1.record()
-    barrier()
-    t_mark1 = time.time()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    rep_ms, t_mark0, t_mark1 = H.timed_reps(step_device, args.steps, MIN_TIMED_S)
+    flagged_timed = H.sum_over_ranks(sset.local.DeviceCounters()[0] - flagged0)
     launches_timed = ctx.Stats()
-    # the same K steps once more with CUDA events around every launch of the dominant kernel (the library
-    # brackets them on the launching stream; profiling runs the pipeline un-graphed, kernel for kernel)
-    ctx.ResetStats()
-    ctx.SetProfiling(True)
-    for i in range(args.steps):
-        step_device(i)
-    torch.cuda.synchronize()
-    stats = ctx.Stats()
-    ctx.SetProfiling(False)
-    barrier()
     launches = (launches_timed["scan_launches"] + launches_timed["merge_launches"] +
                 launches_timed["other_launches"] + launches_timed["gemm_launches"])
-    tensor = stats["tensor_passes"] > 0
-    if tensor:   # the dominant kernel of a step is the tcgen05 COLLECT pass (one per <= 256 queries)
-        scan_ms = stats["gemm_kernel_ns"] / 1e6 / max(stats["gemm_kernel_timed"], 1)
-        scans_per_step = stats["gemm_kernel_timed"] / args.steps
-    else:
-        scan_ms = stats["scan_kernel_ns"] / 1e6 / max(stats["scan_kernel_timed"], 1)
-        scans_per_step = stats["scan_launches"] / args.steps
+    reps = len(rep_ms)
+    med_ms = float(np.median(rep_ms))
+    scan_ms, per_step, tensor, stats = profile_kernel(ctx, step_device, max(args.steps, 20))
+    H.barrier()
 
-    # ---- e2e timed region (host buffers, H2D + D2H inside)
-    barrier()
+    # ---- correctness of what was just timed, at this N
+    parity = parity_check(H, sset, dpool, K, Q, rows_total)
+
+    # ---- e2e timed region (host buffers, H2D + D2H inside), same >= 1 s rule
+    def e2e_run(n, first, lat_out):
+        H.barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            a = time.perf_counter()
+            step_e2e(first + i)
+            lat_out.append(time.perf_counter() - a)
+        torch.cuda.synchronize()
+        H.barrier()
+        return H.max_over_ranks([(time.perf_counter() - t0) * 1e3])[0]
+
+    probe_ms = e2e_run(args.steps, 0, [])
+    n_e2e = int(min(20000, max(args.steps, np.ceil(MIN_TIMED_S * 1e3 / max(probe_ms, 1e-3) * args.steps))))
     lat = []
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        a = time.perf_counter()
-        step_e2e(i)
-        lat.append(time.perf_counter() - a)
-    torch.cuda.synchronize()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_ms = e2e_run(n_e2e, args.steps, lat)
 
-    # ---- single-query latency through the host call (north_star: sub-0.5 ms p50)
-    lat1 = []
+    line_extra = {}
+    lat1, q1 = [], None
+    f32_paths = {}
     if world == 1:
-        for i in range(max(30, min(args.steps, 200))):
+        # ---- single-query latency through the host call (north_star: sub-0.5 ms p50)
+        for i in range(300):
             hq = hpool[i % npool][:1]
             a = time.perf_counter()
             lean.gf_set_search(sset.local._h, -2.0, K, 1, hq.data_ptr(), DIMS * 4, ctypes.byref(handle))
             lat1.append(time.perf_counter() - a)
             lean.gf_result_free(handle)
-        ctx.ResetStats()
-        ctx.SetProfiling(True)
-        for i in range(20):
-            sset.search_device(K, 1, dpool[i % npool][:1])
-        torch.cuda.synchronize()
-        s1 = ctx.Stats()
-        ctx.SetProfiling(False)
-        q1_tensor = s1["tensor_passes"] > 0
-        if q1_tensor:
-            q1_ms = s1["gemm_kernel_ns"] / 1e6 / max(s1["gemm_kernel_timed"], 1)
-        else:
-            q1_ms = s1["scan_kernel_ns"] / 1e6 / max(s1["scan_kernel_timed"], 1)
-    # ---- the same step on the float32 rows only (no shadow traffic saved): kind::tf32 candidate pass, and the
-    # fused exact scan -- SURVEY 8(d)'s algorithmic bytes (rows x dims x 4) apply to these as they stand
-    f32_paths = {}
-    if world == 1:
-        fsteps = max(20, min(args.steps, 100))
+        q1_ms, _, q1_tensor, _ = profile_kernel(ctx, lambda i: sset.search_device(K, 1, dpool[i % npool][:1]), 20)
+        q1 = (q1_ms, q1_tensor)
+        # ---- the same step on the float32 rows only (no shadow traffic saved): kind::tf32 candidate pass, and the
+        # fused exact scan -- SURVEY 8(d)'s algorithmic bytes (rows x dims x 4) apply to these as they stand
         for name, path in (("tf32_candidate_pass", 3), ("exact_scan", 1)):
+            fn = lambda i, p=path: sset.search_device(K, Q, dpool[i % npool], path=p)   # noqa: E731
             for i in range(3):
-                sset.search_device(K, Q, dpool[i % npool], path=path)
-            torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for i in range(fsteps):
-                sset.search_device(K, Q, dpool[i % npool], path=path)
-            f1.record()
-            torch.cuda.synchronize()
-            fms = f0.elapsed_time(f1) / fsteps
-            ctx.ResetStats()
-            ctx.SetProfiling(True)
-            for i in range(20):
-                sset.search_device(K, Q, dpool[i % npool], path=path)
-            torch.cuda.synchronize()
-            fs = ctx.Stats()
-            ctx.SetProfiling(False)
-            if fs["tensor_passes"] > 0:
-                kms = fs["gemm_kernel_ns"] / 1e6 / max(fs["gemm_kernel_timed"], 1)
-                per_step = fs["gemm_kernel_timed"] / 20.0
-            else:
-                kms = fs["scan_kernel_ns"] / 1e6 / max(fs["scan_kernel_timed"], 1)
-                per_step = fs["scan_kernel_timed"] / 20.0
-            fbytes = rows_local * DIMS * 4 + (Q / max(per_step, 1)) * DIMS * 4
-            f32_paths[name] = {"ms_per_step": fms, "value": Q / (fms * 1e-3), "unit": UNIT,
-                               "kernel_ms": kms, "kernel_launches_per_step": per_step,
-                               "achieved_gbs": fbytes / (kms * 1e-3) / 1e9 if kms > 0 else None}
+                fn(i)
+            ms, _, _ = H.timed_reps(fn, 20, 0.3)
+            fms = float(np.median(ms)) / 20
+            kms, per, _, _ = profile_kernel(ctx, fn, 20)
+            fbytes = rows_local * DIMS * 4 + (Q / max(per, 1)) * DIMS * 4
+            f32_paths[name] = {"ms_per_step": fms, "value": Q / (fms * 1e-3), "unit": UNIT, "kernel_ms": kms,
+                               "kernel_launches_per_step": per,
+                               "achieved_gbs": fbytes / (kms * 1e-3) / 1e9 if kms > 0 else None,
+                               "roofline_frac": (fbytes / (kms * 1e-3) / 1e9 / PK["hbm"]) if kms > 0 else None}
+        # ---- config 3: 1024 queries x top-100 on the same 1 M rows (tensor roofline)
+        line_extra["config3"] = leg_config3(H, ctx, sset, rows_local, shadow_eb, PK)
+    sset.close_exchange()
+    cache.Close()
+    cache = None
+
+    # ---- config 4: 12.5 M rows per GPU, 64 queries top-10 (8 GPUs: the 100 M-row set); strong scaling: 8 M rows
+    if not args.quick:
+        line_extra["config4_shard"] = leg_rows(H, api, ShardedSet, ctx, args.config4_rows_per_gpu * world, 64, 10,
+                                               shadow, PK, "config4")
+        if args.strong_rows >= world * 2 * CAP:
+            line_extra["strong_scaling"] = leg_rows(H, api, ShardedSet, ctx, args.strong_rows, Q, K, shadow, PK, "strong")
+
     # ---- config[1] exactly as written: 10 concurrent host threads, one query each, through the C ABI
     # (tools/gf_demo, the counterpart of the reference's demo/main.go), request coalescing on
-    demo = None
+    demo = churn = None
+    baselines = {}
     if world == 1 and rank == 0:
-        exe = os.path.join(ROOT, "tools", "gf_demo")
-        if not os.path.exists(exe):
-            subprocess.call(["make", "-C", os.path.join(ROOT, "tools")], stdout=subprocess.DEVNULL,
-                            stderr=subprocess.DEVNULL)
+        tools = os.path.join(ROOT, "tools")
+        if not (os.path.exists(os.path.join(tools, "gf_demo")) and os.path.exists(os.path.join(tools, "ref_replica"))):
+            subprocess.call(["make", "-C", tools], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        exe = os.path.join(tools, "gf_demo")
         if os.path.exists(exe):
-            cache.Close()      # give the memory back: the tool builds its own 1 M-row set
-            cache = None
-            try:
-                out = subprocess.run([exe, "--rows", str(args.rows_per_gpu), "--threads", str(Q), "--rounds",
-                                      str(max(args.steps, 200)), "--warm-rounds", str(max(args.warmup, 30)),
-                                      "--limit", str(K), "--coalesce-us", "100",
-                                      "--device", str(local_rank)], capture_output=True, text=True, timeout=300)
-                if out.returncode == 0:
-                    demo = json.loads(out.stdout.strip().splitlines()[-1])
-            except Exception as exc:  # the bench line must still come out
-                demo = {"error": str(exc)}
+            demo = run_tool([exe, "--rows", str(args.rows_per_gpu), "--threads", str(Q), "--rounds", "10000",
+                             "--warm-rounds", str(max(args.warmup, 30)), "--limit", str(K), "--coalesce-us", "100",
+                             "--device", str(local_rank)], 300)
+            if not args.quick:
+                # config 5: 10 M rows, 4 searchers, Add / Delete 100 k rows in 10 k chunks meanwhile -- and the same
+                # searchers on the same set without the churn
+                common = [exe, "--rows", "10000000", "--threads", "4", "--limit", str(K), "--coalesce-us", "100",
+                          "--device", str(local_rank), "--warm-rounds", "20"]
+                churn = {"idle": run_tool(common + ["--rounds", "1500"], 300),
+                         "churn": run_tool(common + ["--rounds", "1500", "--adds", "10", "--add-size", "10000",
+                                                     "--deletes", "10", "--delete-size", "10000", "--add-gap-us",
+                                                     "20000"], 300)}
+        rep = os.path.join(tools, "ref_replica")
+        if os.path.exists(rep) and not args.quick:
+            # the reference's own path on this GPU: cublasSgemm per block + full D2H + CPU sort (block.go:196-246)
+            baselines["ref_replica_gpu"] = run_tool([rep, "--rows", str(args.rows_per_gpu), "--threads", str(Q),
+                                                     "--queries", "1", "--limit", str(K), "--seconds", "4",
+                                                     "--device", str(local_rank)], 120)
+            baselines["ref_replica_gpu"]["what"] = ("tools/ref_replica: the reference's Set.Search replayed with the "
+                                                    "image's cuBLAS -- per block H2D of the transposed query, "
+                                                    "cublasSgemm, D2H of the whole score matrix, full CPU sort "
+                                                    "(block.go:196-246, util.go:76-93); %d concurrent callers" % Q)
     if sampler:
         sampler.stop()
 
     if rank != 0:
+        ctx.Close()
         if world > 1:
-            dist.destroy_process_group()
+            H.dist.destroy_process_group()
         return
 
-    peak, peak_src = hbm_peak()
-    avg_q = Q / scans_per_step if scans_per_step else Q
+    avg_q = Q / per_step if per_step else Q
     eb = shadow_eb if (tensor and shadow_eb) else 4   # bytes per element the dominant kernel streams
-    alg_bytes = rows_local * DIMS * eb + avg_q * DIMS * eb + avg_q * K * 8
+    alg_bytes = rows_local * DIMS * eb + (rows_local * 4 if eb == 1 else 0) + avg_q * DIMS * eb + avg_q * K * 8
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    qps_user = Q * args.steps / (dev_ms * 1e-3)
-    e2e_user = Q * args.steps / (e2e_ms * 1e-3)
+    qps_user = Q * args.steps / (med_ms * 1e-3)
+    e2e_user = Q * n_e2e / (e2e_ms * 1e-3)
     lat_ms = sorted(x * 1e3 for x in lat)
+    peak = PK["hbm"]
     line = {
         "metric": METRIC, "value": qps_user * world, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": med_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(args, world),
         "qps_user": qps_user, "rows_local_rank0": rows_local,
+        "timing": {"repetitions": reps, "steps_per_repetition": args.steps, "timed_region_s": sum(rep_ms) / 1e3,
+                   "ms_per_step_median": med_ms / args.steps, "ms_per_step_min": min(rep_ms) / args.steps,
+                   "ms_per_step_p90": float(np.percentile(rep_ms, 90)) / args.steps,
+                   "how": "the driver's K steps repeated back to back until >= %.1f s of device time; CUDA events "
+                          "around every repetition, max over ranks per repetition, median reported" % MIN_TIMED_S},
         "e2e": {"value": e2e_user * world, "unit": UNIT, "h2d_bytes_per_step": Q * DIMS * 4,
-                "d2h_bytes_per_step": Q * K * 8, "qps_user": e2e_user, "ms_per_step": e2e_ms / args.steps,
+                "d2h_bytes_per_step": Q * K * 8, "qps_user": e2e_user, "ms_per_step": e2e_ms / n_e2e, "calls": n_e2e,
                 "p50_ms": lat_ms[len(lat_ms) // 2], "p99_ms": lat_ms[min(len(lat_ms) - 1, int(len(lat_ms) * 0.99))],
                 "call": "one gf_set_search(q=%d) per step" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q},
         "units": "a query counts once per %d-row shard it scans: value = qps_user x n_gpus (weak scaling)" % args.rows_per_gpu,
-        "gpu_launches": int(launches), "tensor_passes": stats["tensor_passes"],
-        "uncertified_queries": stats["uncertified_queries"],
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / float(max(reps * args.steps, 1)),
+        "tensor_passes": stats["tensor_passes"],
+        "uncertified_queries": int(flagged_timed),
+        "uncertified_note": "queries of the timed region whose certificate refused (device counter, summed over ranks); "
+                            "the host API re-runs such a query through the exact scan",
+        "parity_check": parity,
         "exactness": "ids, order and scores are the canonical float32 answer (bit-identical to the oracle in the GPU "
                      "tests): the int8 / bf16 / tf32 pass only selects candidates, every winner is re-scored from the "
                      "float32 rows and certified against the measured quantisation residual; a query that cannot be "
@@ -414,12 +576,13 @@ def run_ours(args, rank, world, local_rank):
                      else "scan_tma_kernel<512,QT>",
                      "bytes_per_element": eb,
                      "frac_if_counted_as_f32_bytes": (achieved * 4 / eb) / peak if peak else None,
-                     "launches_per_step": scans_per_step,
-                     "avg_launch_ms": scan_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "timed": "CUDA events around each launch, second pass of the same %d steps" % args.steps,
+                     "launches_per_step": per_step,
+                     "avg_launch_ms": scan_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": PK["hbm_src"],
+                     "timed": "CUDA events around each launch, a second pass of %d steps" % max(args.steps, 20),
                      "frac_of_nominal_8000": achieved / 8000.0},
         "clocks": sampler.summary(t_mark0, t_mark1) if sampler else None,
     }
+    line.update(line_extra)
     if demo and "qps" in demo:
         # the headline end-to-end number: 10 real concurrent callers, host buffers, coalesced by the library
         line["e2e_batched_call"] = line["e2e"]
@@ -427,36 +590,139 @@ def run_ours(args, rank, world, local_rank):
                        "h2d_bytes_per_step": int(demo["h2d_bytes"] / max(demo["searches"], 1) * Q),
                        "d2h_bytes_per_step": int(demo["d2h_bytes"] / max(demo["searches"], 1) * Q),
                        "qps_user": demo["qps"], "ms_per_step": demo["wall_ms"] / demo["rounds"],
-                       "p50_ms": demo["p50_ms"], "p99_ms": demo["p99_ms"],
+                       "wall_s": demo["wall_ms"] / 1e3, "p50_ms": demo["p50_ms"], "p99_ms": demo["p99_ms"],
                        "call": "%d host threads x gf_set_search(q=1), coalescing 100 us (tools/gf_demo)" % Q,
                        "coalesced_batches": demo["coalesced_batches"], "tensor_passes": demo["tensor_passes"],
                        "self_check": demo["self_check"]}
     elif demo:
         line["e2e_parallel_error"] = demo
+    if churn:
+        c, i = churn.get("churn", {}), churn.get("idle", {})
+        line["churn"] = {"workload": "BASELINE configs[4]: 10 M x 512 rows, 4 searcher threads x gf_set_search(q=1, top-%d), "
+                                     "Add + Delete of 100 000 rows in chunks of 10 000 meanwhile (tools/gf_demo)" % K,
+                         "idle": {k: i.get(k) for k in ("qps", "p50_ms", "p99_ms", "searches", "error") if k in i},
+                         "under_churn": {k: c.get(k) for k in ("qps", "p50_ms", "p99_ms", "searches", "rows_added",
+                                                               "add_rows_per_s", "deleted", "delete_ids_per_s",
+                                                               "self_check", "error") if k in c}}
     if world == 1:
-        for v in f32_paths.values():
-            if v.get("achieved_gbs"):
-                v["roofline_frac"] = v["achieved_gbs"] / peak
         line["float32_paths"] = f32_paths
         l1 = sorted(x * 1e3 for x in lat1)
-        eb1 = shadow_eb if (q1_tensor and shadow_eb) else 4
-        b1 = rows_local * DIMS * eb1 + DIMS * eb1 + K * 8
+        eb1 = shadow_eb if (q1[1] and shadow_eb) else 4
+        b1 = rows_local * DIMS * eb1 + (rows_local * 4 if eb1 == 1 else 0) + DIMS * eb1 + K * 8
         line["single_query"] = {"p50_ms": l1[len(l1) // 2], "p99_ms": l1[min(len(l1) - 1, int(len(l1) * 0.99))],
-                                "qps": 1e3 / (sum(l1) / len(l1)), "scan_kernel_ms": q1_ms,
-                                "kernel": "tcgen05 candidate pass" if q1_tensor else "scan_tma_kernel<512,1>",
+                                "qps": 1e3 / (sum(l1) / len(l1)), "scan_kernel_ms": q1[0],
+                                "kernel": "tcgen05 candidate pass" if q1[1] else "scan_tma_kernel<512,1>",
                                 "bytes_per_element": eb1,
-                                "roofline_frac": (b1 / (q1_ms * 1e-3) / 1e9 / peak) if q1_ms > 0 else None,
-                                "achieved_gbs": (b1 / (q1_ms * 1e-3) / 1e9) if q1_ms > 0 else None}
+                                "roofline_frac": (b1 / (q1[0] * 1e-3) / 1e9 / peak) if q1[0] > 0 else None,
+                                "achieved_gbs": (b1 / (q1[0] * 1e-3) / 1e9) if q1[0] > 0 else None}
         if not args.no_cpu_baseline:
-            cb, _ = cpu_scan_qps(min(args.cpu_sample_rows, args.rows_per_gpu), Q, K, args.cpu_seconds,
-                                 args.rows_per_gpu)
-            line["cpu_baseline"] = cb
+            cores = os.cpu_count() or 1
+            qps, ms_pass, passes, X, Qh = cpu_port_qps(args.rows_per_gpu, Q, K, args.cpu_seconds, cores)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "all %d rows x %d-d, %d queries top-%d per pass, %d passes, median %.1f ms/pass, "
+                                              "oracle canonical-order AVX2 scan, persistent pool of %d threads"
+                                              % (args.rows_per_gpu, DIMS, Q, K, passes, ms_pass, cores)}
+            if not args.quick:
+                sub = min(250_000, args.rows_per_gpu)
+                from oracle import lib as ol
+                t0 = time.perf_counter()
+                n1 = 0
+                while n1 < 2 or time.perf_counter() - t0 < 3.0:
+                    ol.scan_topk(X[:sub], Qh, K, ol.MODE_CANONICAL, 1)
+                    n1 += 1
+                ms1 = (time.perf_counter() - t0) / n1 * 1e3 * args.rows_per_gpu / sub
+                baselines["cpu_scan_1t"] = {"value": Q / (ms1 * 1e-3), "unit": UNIT, "cores": 1,
+                                            "sample": "%d of %d rows, %d passes, scaled by the rows ratio" % (sub, args.rows_per_gpu, n1)}
+                bq, bms, bn = cpu_blas_qps(X, Qh, K, 3.0)
+                baselines["cpu_blas"] = {"value": bq, "unit": UNIT, "cores": cores, "ms_per_pass": bms, "passes": bn,
+                                         "what": "numpy %s matmul (all rows x %d queries) + argpartition + sort of the "
+                                                 "%d best per query" % (np.__version__, Q, K)}
+            del X
+    if baselines:
+        for b in baselines.values():
+            if "qps" in b and "value" not in b:
+                b["value"], b["unit"] = b["qps"], UNIT
+        line["baselines"] = baselines
     emit(line)
-    if cache is not None:
-        cache.Close()
     ctx.Close()
     if world > 1:
-        dist.destroy_process_group()
+        H.dist.destroy_process_group()
+    if parity["mismatches"] != 0 or not parity["needles_ok"]:
+        sys.stderr.write("bench.py: parity_check FAILED: %r\n" % (parity,))
+        sys.exit(3)
+
+
+def leg_config3(H, ctx, sset, rows_local, shadow_eb, PK):
+    """BASELINE configs[2]: 1024 queries x top-100 on 1 M rows -- four 256-query tcgen05 passes + select + re-score."""
+    torch = H.torch
+    Q3, K3 = 1024, 100
+    q3 = torch.from_numpy(make_queries(Q3 * 2, DIMS, QUERY_SEED + 7).reshape(2, Q3, DIMS)).cuda()
+    fn = lambda i: sset.search_device(K3, Q3, q3[i % 2])   # noqa: E731
+    for i in range(3):
+        fn(i)
+    ms, _, _ = H.timed_reps(fn, 10, 0.5)
+    step_ms = float(np.median(ms)) / 10
+    kms, per, tensor, st = profile_kernel(ctx, fn, 6)
+    flops = 2.0 * Q3 * rows_local * DIMS
+    mult = {1: 2.0, 2: 1.0}.get(shadow_eb, 0.5)        # int8 runs at twice, tf32 at half the bf16 rate
+    peak = PK["bf16"] * mult
+    pass_flops = 2.0 * 256 * rows_local * DIMS
+    k0 = sset.search_device(K3, Q3, q3[0]).clone()
+    f0 = sset.flags(Q3, K3).clone()
+    k1 = sset.search_device(K3, Q3, q3[0], path=1).clone()
+    torch.cuda.synchronize()
+    bad = ((k0 != k1).any(dim=1) & (f0 == 0)).sum().item()
+    return {"workload": "BASELINE configs[2]: %d x %d-d rows, %d queries top-%d per step" % (rows_local, DIMS, Q3, K3),
+            "ms_per_step": step_ms, "value": Q3 / (step_ms * 1e-3), "unit": UNIT,
+            "roofline": {"bound": "tensor", "achieved": flops / (step_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (step_ms * 1e-3) / 1e12 / peak,
+                         "what": "useful 2*Q*N*D of the WHOLE step (4 passes + select + re-score + finalize) against "
+                                 "%.1fx the %s" % (mult, PK["bf16_src"]),
+                         "pass_kernel_ms": kms, "passes_per_step": per,
+                         "pass_kernel_tflops": pass_flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                         "pass_kernel_frac": (pass_flops / (kms * 1e-3) / 1e12 / peak) if kms > 0 else None},
+            "parity_check": {"queries": Q3, "mismatches": int(bad), "flagged_queries": int((f0 != 0).sum().item())}}
+
+
+def leg_rows(H, api, ShardedSet, ctx, rows_total, Qx, Kx, shadow, PK, name):
+    """A sharded set of rows_total rows (block-striped over the ranks), Qx queries top-Kx per step."""
+    torch = H.torch
+    cache, sset = new_sharded(H, api, ShardedSet, ctx, rows_total, max(Qx, 16), shadow, name)
+    rows_local = sset.local.ScannedRows()
+    eb = cache.ShadowBytesPerElement() or 4
+    qh = make_queries(Qx * 4, DIMS, QUERY_SEED + 11).reshape(4, Qx, DIMS)
+    qd = torch.from_numpy(qh).cuda()
+    fn = lambda i: sset.search_device(Kx, Qx, qd[i % 4])   # noqa: E731
+    for i in range(3):
+        fn(i)
+        sset.search_keys(Kx, qh[i % 4])
+    ms, _, _ = H.timed_reps(fn, 10, 0.5)
+    step_ms = float(np.median(ms)) / 10
+    kms, per, tensor, _ = profile_kernel(ctx, fn, 10)
+    kms = H.max_over_ranks([kms])[0]
+    H.barrier()
+    t0 = time.perf_counter()
+    n = 20
+    for i in range(n):
+        sset.search_keys(Kx, qh[i % 4])
+    H.barrier()
+    e2e_ms = H.max_over_ranks([(time.perf_counter() - t0) * 1e3])[0] / n
+    k0 = sset.search_device(Kx, Qx, qd[0]).clone()
+    f0 = sset.flags(Qx, Kx).clone()
+    k1 = sset.search_device(Kx, Qx, qd[0], path=1).clone()
+    torch.cuda.synchronize()
+    bad = ((k0 != k1).any(dim=1) & (f0 == 0)).sum().item()
+    alg = rows_local * DIMS * eb + (rows_local * 4 if eb == 1 else 0)
+    out = {"workload": "%d x %d-d rows row-sharded over %d GPU(s) (%d on rank 0), %d queries top-%d per step"
+                       % (rows_total, DIMS, H.world, rows_local, Qx, Kx),
+           "rows_total": rows_total, "ms_per_step": step_ms, "qps_user": Qx / (step_ms * 1e-3), "unit": UNIT,
+           "e2e_ms_per_step": e2e_ms, "e2e_qps_user": Qx / (e2e_ms * 1e-3),
+           "pass_kernel_ms_max_over_ranks": kms, "pass_launches_per_step": per,
+           "hbm_frac_per_rank": (alg / (kms * 1e-3) / 1e9 / PK["hbm"]) if (kms > 0 and tensor) else None,
+           "parity_check": {"queries": Qx, "mismatches": int(bad), "flagged_queries": int((f0 != 0).sum().item())}}
+    sset.close_exchange()
+    cache.Close()
+    return out
 
 
 _REAL_STDOUT = None
@@ -486,11 +752,13 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--queries", type=int, default=10)
     ap.add_argument("--limit", type=int, default=10)
-    ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shadow", action="store_true", help="float32 rows only (no shadow slab)")
     ap.add_argument("--shadow", default="int8", choices=["int8", "bf16"], help="format of the shadow slab")
+    ap.add_argument("--quick", action="store_true", help="headline + parity only (no config 3/4/5, strong, baselines)")
+    ap.add_argument("--config4-rows-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--strong-rows", type=int, default=8_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

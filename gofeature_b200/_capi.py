@@ -108,6 +108,7 @@ SIGNATURES = {
     "gf_set_set_coalescing": (c_int, [c_vp, c_int]),
     "gf_set_set_search_path": (c_int, [c_vp, c_int]),
     "gf_set_search_device_ex": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "gf_set_device_counters": (c_int, [c_vp, P(c_u64), P(c_u64)]),
     "gf_exchange_create": (c_int, [c_vp, c_int, c_int, c_int, c_int, P(c_vp)]),
     "gf_exchange_handle": (c_int, [c_vp, c_vp, c_u64]),
     "gf_exchange_connect": (c_int, [c_vp, c_vp, c_u64]),

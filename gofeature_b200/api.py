@@ -393,6 +393,17 @@ class Set:
     def SearchDevice(self, limit, q, d_queries_ptr, d_out_keys_ptr, path=0, stream=None):
         _check(lib().gf_set_search_device(self._h, limit, q, d_queries_ptr, d_out_keys_ptr, path, stream))
 
+    def SearchDeviceEx(self, limit, q, d_queries_ptr, d_out_keys_ptr, d_out_flags_ptr, path=0, stream=None):
+        """gf_set_search_device_ex: d_out_flags[i] = 1 where the certificate refused query i (re-run with path=1)."""
+        _check(lib().gf_set_search_device_ex(self._h, limit, q, d_queries_ptr, d_out_keys_ptr, d_out_flags_ptr, path,
+                                             stream))
+
+    def DeviceCounters(self):
+        """(queries the certificate refused, queries the flag-less device call left unrepaired) so far."""
+        a, b = c_u64(0), c_u64(0)
+        _check(lib().gf_set_device_counters(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
     def ResolveKeys(self, threshold, limit, keys):
         k = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1, limit)
         h = c_vp()

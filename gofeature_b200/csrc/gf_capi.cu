@@ -822,6 +822,25 @@ int gf_set_search_device_ex(gf_set *set, int limit, int q, const float *d_querie
     });
 }
 
+int gf_set_device_counters(gf_set *set, uint64_t *out_flagged, uint64_t *out_unrepaired)
+{
+    if (!set) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        unsigned int h[4] = {0, 0, 0, 0};
+        set->lock.lock_shared();
+        cudaError_t e = cudaSuccess;
+        if (set->d_small != nullptr && set->ctx->bind() == GF_OK) {
+            e = cudaDeviceSynchronize();
+            if (e == cudaSuccess) e = cudaMemcpy(h, set->d_small, sizeof h, cudaMemcpyDeviceToHost);
+        }
+        set->lock.unlock_shared();
+        if (e != cudaSuccess) return cuda_fail(e, "gf_set_device_counters", GF_ERR_READ_CUDA_BUFFER);
+        if (out_flagged) *out_flagged = h[3];
+        if (out_unrepaired) *out_unrepaired = h[1];
+        return GF_OK;
+    });
+}
+
 // ---- peer exchange of per-rank winners over NVLink peer memory (one process per GPU)
 // (gf_set_search_device_xchg, below gf_exchange_merge_device, runs a search that ends with the exchange)
 struct gf_exchange {

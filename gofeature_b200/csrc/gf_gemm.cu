@@ -1198,6 +1198,7 @@ __global__ void __launch_bounds__(256)
             if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
         }
         d_flags[qi] = ok ? 0u : 1u;  // flagged queries are re-run by the exact scan
+        if (!ok && fix.flagged != nullptr) atomicAdd(fix.flagged, 1u);
     }
     if (fix.flags_all == nullptr) return;
     // the last CTA of the call's last finalize launch lists the flagged queries for the fix-up scan
@@ -1585,6 +1586,7 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
         // rows of groups below the cut: their best key is <= the largest non-candidate key
         if (ok && ncmax_all != 0u && !(key_score(s_kth) > reach(ncmax_all) + delta)) ok = false;
         a.d_flags[qi] = ok ? 0u : 1u;
+        if (!ok && a.d_flagged != nullptr) atomicAdd(a.d_flagged, 1u);
         s_myflag = ok ? 0u : 1u;
     }
     if (a.has_xchg) {

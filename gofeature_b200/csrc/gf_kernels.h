@@ -156,6 +156,7 @@ struct FixupPlan {
     unsigned int *count;
     unsigned int *uncertified;
     unsigned int *ticket;  // zero between calls
+    unsigned int *flagged = nullptr;  // always counted (atomicAdd per flagged query): gf_set_device_counters
 };
 // d_flags[qi] = 1 when query qi could not be certified (it must be re-run by the exact scan)
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
@@ -187,6 +188,7 @@ struct GtTail {
     const unsigned int *d_maxres2_bits;
     unsigned long long *d_out;    // [q][K]
     unsigned int *d_flags;        // [q]
+    unsigned int *d_flagged;      // set-wide counter of queries the certificate refused (gf_set_device_counters)
     uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment
     // sharded sets: the leader ends with the cross-rank exchange + fold (d_out / d_flags then take the LOCAL winners)
     int has_xchg;

@@ -1565,6 +1565,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         g.q = qp;
         FixupPlan fix{};  // the last pass's finalize also lists the flagged queries of the whole call
         if (device_fixup && p0 + kGemmMaxQ >= q) fix = FixupPlan{d_fl, q, fixq, d_map, d_count, d_small + 1, d_ticket};
+        fix.flagged = d_small + 3;
         mark();
         if (phase != 2)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
@@ -1606,6 +1607,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             t.d_maxres2_bits = d_small + 2;
             t.d_out = d_out + (size_t)p0 * K;
             t.d_flags = d_fl + p0;
+            t.d_flagged = d_small + 3;
             if (phase == 2 && ws->direct_out != nullptr && ws->direct_flags != nullptr) {
                 t.d_out = ws->direct_out;  // (one pass: p0 == 0)
                 t.d_flags = ws->direct_flags;

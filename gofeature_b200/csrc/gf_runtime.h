@@ -264,7 +264,7 @@ struct gf_set {
     uint32_t *d_gtile_start = nullptr;
     uint32_t *d_seg_slot_base = nullptr;
     uint32_t total_gtiles = 0;
-    unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] uncertified-query counter, [2] max |bf16(row) - row|^2 bits
+    unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] queries the flag-less device call could not repair, [2] max |shadow(row) - row|^2 bits, [3] queries the certificate refused
     bool tensor_ok = false;
     bool shadow_ok = false;   // the shadow of this set's rows is maintained and usable by the tensor path
     int search_path = 0;      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32, 4 / 5 = 2 / 3 without the one-pass chain

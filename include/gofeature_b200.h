@@ -274,11 +274,19 @@ GF_API int gf_set_set_shard(gf_set *set, int rank, int world);
  * 3 = the same on the float32 rows (kind::tf32). */
 GF_API int gf_set_search_device(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys,
                                 int path, void *stream);
-/* gf_set_search_device with per-query flags: d_out_flags[q] (optional) is 1 where the tensor path could
- * neither certify nor repair a query on the device (more than 8 such queries in one call); the keys
- * of a flagged query are not guaranteed exact and the caller re-runs it with path = 1. */
+/* gf_set_search_device with per-query flags.  With d_out_flags (q words) the library does NO device-side
+ * repair: d_out_flags[i] = 1 where the tensor path's certificate refused query i; the keys of a flagged query
+ * are not guaranteed exact and the caller re-runs it with path = 1 (gf_set_search does exactly that).
+ * Without flags (NULL, = gf_set_search_device) up to 8 refused queries per call are re-run on the device by
+ * the exact scan; any further ones keep their candidate-pass keys and are counted (gf_set_device_counters:
+ * out_unrepaired) -- callers that cannot tolerate that pass flags. */
 GF_API int gf_set_search_device_ex(gf_set *set, int limit, int q, const float *d_queries, uint64_t *d_out_keys,
                                    uint32_t *d_out_flags, int path, void *stream);
+
+/* Device-side counters of this set since it was created (a blocking 16-byte read): queries the tensor
+ * path's certificate refused (whoever repaired them), and queries the flag-less gf_set_search_device left
+ * unrepaired (more than 8 refusals in one call).  bench.py reads them after its timed region. */
+GF_API int gf_set_device_counters(gf_set *set, uint64_t *out_flagged, uint64_t *out_unrepaired);
 
 /* ---- Peer exchange (multi-GPU, one process per GPU): the cross-rank step of a sharded search as ONE
  * kernel over NVLink peer memory instead of ncclAllGather + merge.  Every rank creates an exchange,

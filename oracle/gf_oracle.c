@@ -361,15 +361,89 @@ static void *gf_scan_worker(void *arg)
     return NULL;
 }
 
+/*
+ * Persistent worker pool (the reference keeps one goroutine per block alive, block.go:76; spawning
+ * threads per search cost the CPU baseline up to a third of a 7 ms pass).  gf_pool_run(n, fn, jobs,
+ * stride) runs fn(jobs + i*stride) for i in [0, n): job 0 on the caller, the rest on parked workers
+ * that are created on first use and never exit.  One run at a time.
+ */
+#define GF_POOL_MAX 512
+static pthread_mutex_t gp_run_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t gp_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t gp_start = PTHREAD_COND_INITIALIZER, gp_done = PTHREAD_COND_INITIALIZER;
+static int gp_workers = 0, gp_active = 0, gp_left = 0;
+static unsigned long gp_gen = 0;
+static void *(*gp_fn)(void *) = NULL;
+static char *gp_jobs = NULL;
+static size_t gp_stride = 0;
+
+static void *gf_pool_worker(void *arg)
+{
+    const int id = (int)(intptr_t)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&gp_mu);
+    for (;;) {
+        while (gp_gen == seen) pthread_cond_wait(&gp_start, &gp_mu);
+        seen = gp_gen;
+        if (id < gp_active) {
+            void *(*fn)(void *) = gp_fn;
+            void *job = gp_jobs + (size_t)(id + 1) * gp_stride;
+            pthread_mutex_unlock(&gp_mu);
+            fn(job);
+            pthread_mutex_lock(&gp_mu);
+            if (--gp_left == 0) pthread_cond_signal(&gp_done);
+        }
+    }
+    return NULL;
+}
+
+static void gf_pool_run(int n, void *(*fn)(void *), void *jobs, size_t stride)
+{
+    if (n > GF_POOL_MAX) n = GF_POOL_MAX; /* (callers size their job arrays with gf_pool_clamp) */
+    pthread_mutex_lock(&gp_run_mu);
+    pthread_mutex_lock(&gp_mu);
+    while (gp_workers < n - 1) {
+        pthread_t th;
+        pthread_attr_t at;
+        pthread_attr_init(&at);
+        pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+        if (pthread_create(&th, &at, gf_pool_worker, (void *)(intptr_t)gp_workers) != 0) {
+            pthread_attr_destroy(&at);
+            break;
+        }
+        pthread_attr_destroy(&at);
+        ++gp_workers;
+    }
+    {
+        const int helpers = gp_workers < n - 1 ? gp_workers : n - 1;
+        int i;
+        gp_fn = fn;
+        gp_jobs = (char *)jobs;
+        gp_stride = stride;
+        gp_active = helpers;
+        gp_left = helpers;
+        ++gp_gen;
+        pthread_cond_broadcast(&gp_start);
+        pthread_mutex_unlock(&gp_mu);
+        fn(jobs);
+        for (i = helpers + 1; i < n; ++i) fn((char *)jobs + (size_t)i * stride); /* (thread creation failed) */
+        pthread_mutex_lock(&gp_mu);
+        while (gp_left > 0) pthread_cond_wait(&gp_done, &gp_mu);
+        pthread_mutex_unlock(&gp_mu);
+    }
+    pthread_mutex_unlock(&gp_run_mu);
+}
+
+static int gf_pool_clamp(int nthreads) { return nthreads < 1 ? 1 : nthreads > GF_POOL_MAX ? GF_POOL_MAX : nthreads; }
+
 GF_EXPORT int gf_oracle_scan_topk(const float *rows, int64_t n, int dims, const float *queries, int Q, int limit,
                                   int mode, int nthreads, int *out_counts, double *out_scores, int64_t *out_index)
 {
     int t, q, i;
-    if (nthreads < 1) nthreads = 1;
+    nthreads = gf_pool_clamp(nthreads);
     if (limit < 0) limit = 0;
     if ((int64_t)nthreads > n && n > 0) nthreads = (int)n;
     gf_scan_job *jobs = (gf_scan_job *)calloc((size_t)nthreads, sizeof(gf_scan_job));
-    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
     for (t = 0; t < nthreads; ++t) {
         jobs[t].rows = rows;
         jobs[t].lo = n * t / nthreads;
@@ -381,10 +455,8 @@ GF_EXPORT int gf_oracle_scan_topk(const float *rows, int64_t n, int dims, const 
         jobs[t].queries = queries;
         jobs[t].best = (gf_cand *)calloc((size_t)Q * (size_t)(limit ? limit : 1), sizeof(gf_cand));
         jobs[t].cnt = (int *)calloc((size_t)Q, sizeof(int));
-        if (t > 0) pthread_create(&th[t], NULL, gf_scan_worker, &jobs[t]);
     }
-    gf_scan_worker(&jobs[0]);
-    for (t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    gf_pool_run(nthreads, gf_scan_worker, jobs, sizeof(gf_scan_job));
     for (q = 0; q < Q; ++q) {
         gf_cand *fin = jobs[0].best + (size_t)q * limit;
         int *fc = jobs[0].cnt + q;
@@ -401,7 +473,6 @@ GF_EXPORT int gf_oracle_scan_topk(const float *rows, int64_t n, int dims, const 
         free(jobs[t].cnt);
     }
     free(jobs);
-    free(th);
     return 0;
 }
 
@@ -447,4 +518,39 @@ GF_EXPORT void gf_oracle_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, 
             }
         }
     }
+}
+
+typedef struct {
+    uint64_t seed;
+    int64_t row0, nrows;
+    int dims, normalize;
+    float *out;
+} gf_synth_job;
+
+static void *gf_synth_worker(void *arg)
+{
+    gf_synth_job *j = (gf_synth_job *)arg;
+    gf_oracle_synth_rows(j->seed, j->row0, j->nrows, j->dims, j->normalize, j->out);
+    return NULL;
+}
+
+/* the same rows, generated by `nthreads` pool threads (a 1 M-row CPU baseline is 2 GB of them) */
+GF_EXPORT void gf_oracle_synth_rows_mt(uint64_t seed, int64_t row0, int64_t nrows, int dims, int normalize, float *out,
+                                       int nthreads)
+{
+    int t;
+    nthreads = gf_pool_clamp(nthreads);
+    if ((int64_t)nthreads > nrows) nthreads = nrows > 0 ? (int)nrows : 1;
+    gf_synth_job *jobs = (gf_synth_job *)calloc((size_t)nthreads, sizeof(gf_synth_job));
+    for (t = 0; t < nthreads; ++t) {
+        const int64_t lo = nrows * t / nthreads, hi = nrows * (t + 1) / nthreads;
+        jobs[t].seed = seed;
+        jobs[t].row0 = row0 + lo;
+        jobs[t].nrows = hi - lo;
+        jobs[t].dims = dims;
+        jobs[t].normalize = normalize;
+        jobs[t].out = out + (size_t)lo * dims;
+    }
+    gf_pool_run(nthreads, gf_synth_worker, jobs, sizeof(gf_synth_job));
+    free(jobs);
 }

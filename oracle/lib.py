@@ -50,6 +50,9 @@ def lib():
         L.gf_oracle_synth_rows.restype = None
         L.gf_oracle_synth_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                            ctypes.c_int, fp]
+        L.gf_oracle_synth_rows_mt.restype = None
+        L.gf_oracle_synth_rows_mt.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                              ctypes.c_int, fp, ctypes.c_int]
         L.gf_oracle_have_avx2.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -155,9 +158,12 @@ def scan_topk(rows, queries, limit, mode=MODE_CANONICAL, nthreads=1):
             for q in range(Q)]
 
 
-def synth_rows(seed, row0, nrows, dims, normalize=True):
-    """Counter-based synthetic rows, bit-identical to the CUDA fill kernel."""
+def synth_rows(seed, row0, nrows, dims, normalize=True, nthreads=0):
+    """Counter-based synthetic rows, bit-identical to the CUDA fill kernel (large requests use every host core)."""
     out = np.empty((nrows, dims), dtype=np.float32)
-    lib().gf_oracle_synth_rows(ctypes.c_uint64(seed), ctypes.c_int64(row0), ctypes.c_int64(nrows),
-                               ctypes.c_int(dims), ctypes.c_int(1 if normalize else 0), _fp(out))
+    if nthreads <= 0:
+        nthreads = (os.cpu_count() or 1) if nrows >= 4096 else 1
+    lib().gf_oracle_synth_rows_mt(ctypes.c_uint64(seed), ctypes.c_int64(row0), ctypes.c_int64(nrows),
+                                  ctypes.c_int(dims), ctypes.c_int(1 if normalize else 0), _fp(out),
+                                  ctypes.c_int(nthreads))
     return out
