@@ -234,8 +234,16 @@ class Harness:
         self.torch, self.dist = torch, dist
         self.rank, self.world, self.local_rank = rank, world, local_rank
         torch.cuda.set_device(local_rank)
+        self.host_group = None
         if world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.host_group = dist.new_group(backend="gloo")
+
+    def host_barrier(self):
+        """ranks meet on the HOST (gloo): a NCCL barrier would park a spinning kernel on every GPU, and rank 0's
+        in-library multi-device leg needs those GPUs."""
+        if self.world > 1:
+            self.dist.barrier(group=self.host_group)
 
     def barrier(self):
         if self.world > 1:
@@ -455,6 +463,19 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = e2e_run(n_e2e, args.steps, lat)
 
     line_extra = {}
+    # ---- N > 1: the same N x 1 M-row set INSIDE the library (one process, N devices, gf_context_create_multi):
+    # rank 0 drives all N GPUs through the reference-facing host call; the other ranks wait on the host
+    multi = None
+    if world > 1:
+        ref_keys = [sset.search_device(K, Q, dpool[b]).clone().cpu().numpy().view(np.uint64) for b in range(4)]
+        torch.cuda.synchronize()
+        H.host_barrier()
+        if rank == 0:
+            try:
+                multi = leg_multi(api, world, rows_total, shadow, pool, ref_keys, Q, K, args.steps)
+            except Exception as exc:   # the bench line must still come out
+                multi = {"error": repr(exc)}
+        H.host_barrier()
     lat1, q1 = [], None
     f32_paths = {}
     if world == 1:
@@ -583,6 +604,19 @@ def run_ours(args, rank, world, local_rank):
         "clocks": sampler.summary(t_mark0, t_mark1) if sampler else None,
     }
     line.update(line_extra)
+    if multi is not None and "qps_user" in multi:
+        # the headline end-to-end number at N > 1: ONE process, one caller, gf_set_search(q=10) with host buffers on
+        # a set the library shards over the N devices; ids resolved
+        line["e2e_torchrun_collective"] = line["e2e"]
+        line["e2e"] = {"value": multi["qps_user"] * world, "unit": UNIT, "h2d_bytes_per_step": Q * DIMS * 4 * world,
+                       "d2h_bytes_per_step": Q * K * 8 + Q * 4, "qps_user": multi["qps_user"],
+                       "ms_per_step": multi["ms_per_step"], "calls": multi["calls"], "p50_ms": multi["p50_ms"],
+                       "p99_ms": multi["p99_ms"],
+                       "call": "one process, gf_context_create_multi(%d devices): gf_set_search(q=%d) per step, host "
+                               "buffers in, ids out" % (world, Q),
+                       "parity_check": multi["parity_check"]}
+    elif multi is not None:
+        line["e2e_multi_error"] = multi
     if demo and "qps" in demo:
         # the headline end-to-end number: 10 real concurrent callers, host buffers, coalesced by the library
         line["e2e_batched_call"] = line["e2e"]
@@ -650,6 +684,62 @@ def run_ours(args, rank, world, local_rank):
     if parity["mismatches"] != 0 or not parity["needles_ok"]:
         sys.stderr.write("bench.py: parity_check FAILED: %r\n" % (parity,))
         sys.exit(3)
+
+
+def leg_multi(api, world, rows_total, shadow, pool, ref_keys, Q, K, steps):
+    """rank 0 only: the N-device set behind the C ABI.  Host queries in, [][]FeatureSearchResult out."""
+    lean = api.lib()
+    mctx = api.NewContextMulti(list(range(world)))
+    gblocks = (rows_total + CAP - 1) // CAP
+    cache = api.NewCache(mctx, gblocks + world, BLOCK_SIZE, shadow=shadow)
+    cache.NewSet("multi", DIMS, 4, max(Q, 16))
+    st = cache.GetSet("multi")
+    st.AddSynthetic(rows_total, SEED)
+    npool = pool.shape[0]
+    handle = ctypes.c_void_p()
+    hq = [np.ascontiguousarray(pool[b]) for b in range(npool)]
+
+    def call(i):
+        a = hq[i % npool]
+        rc = lean.gf_set_search(st._h, -2.0, K, Q, a.ctypes.data, a.nbytes, ctypes.byref(handle))
+        if rc != 0:
+            raise api.GoFeatureError(rc)
+        n = lean.gf_result_total(handle)
+        lean.gf_result_free(handle)
+        return n
+
+    # what the library returns (ids, slots, scores) against the keys the torchrun path merged for the same batches
+    mism = 0
+    for b, rk in enumerate(ref_keys):
+        got = st.SearchArray(-2.0, K, pool[b])
+        for i in range(Q):
+            want = [(api.key_slot(k), np.float32(api.key_score(k))) for k in rk[i] if k != 0]
+            have = [(r.Slot, np.float32(r.Score)) for r in got[i]]
+            ids_ok = all(r.ID == "f%011d" % r.Slot for r in got[i])
+            mism += 0 if (want == have and ids_ok) else 1
+    for i in range(10):
+        call(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        call(i)
+    probe = time.perf_counter() - t0
+    n = int(min(20000, max(steps, np.ceil(MIN_TIMED_S / max(probe, 1e-6) * steps))))
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(n):
+        a = time.perf_counter()
+        call(i)
+        lat.append(time.perf_counter() - a)
+    wall = time.perf_counter() - t0
+    stats = mctx.Stats()
+    cache.Close()
+    mctx.Close()
+    l = sorted(x * 1e3 for x in lat)
+    return {"qps_user": Q * n / wall, "ms_per_step": wall / n * 1e3, "calls": n, "p50_ms": l[len(l) // 2],
+            "p99_ms": l[min(len(l) - 1, int(len(l) * 0.99))], "uncertified_queries": stats["uncertified_queries"],
+            "parity_check": {"queries": len(ref_keys) * Q, "mismatches": mism,
+                             "against": "the keys the one-process-per-GPU path (NCCL harness, in-kernel exchange) merged "
+                                        "for the same batches; ids must be f<slot>"}}
 
 
 def leg_config3(H, ctx, sset, rows_local, shadow_eb, PK):

@@ -38,6 +38,8 @@ SIGNATURES = {
     "gf_device_count": (c_int, [P(c_int)]),
     "gf_device_total_mem": (c_int, [c_int, P(c_u64)]),
     "gf_context_create": (c_int, [c_int, P(c_vp)]),
+    "gf_context_create_multi": (c_int, [P(c_int), c_int, P(c_vp)]),
+    "gf_context_device_count": (c_int, [c_vp]),
     "gf_context_destroy": (c_int, [c_vp]),
     "gf_context_device": (c_int, [c_vp]),
     "gf_context_synchronize": (c_int, [c_vp]),

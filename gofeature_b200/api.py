@@ -188,11 +188,20 @@ def TotalMem(device):
 class Context:
     """Stands in for *cuda.Context (search_test.go:40)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         h = c_vp()
-        _check(lib().gf_context_create(device, ctypes.byref(h)))
+        if devices is not None:
+            arr = (c_int * len(devices))(*devices)
+            _check(lib().gf_context_create_multi(arr, len(devices), ctypes.byref(h)))
+            device = devices[0]
+        else:
+            _check(lib().gf_context_create(device, ctypes.byref(h)))
         self._h = h
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
+
+    def DeviceCount(self):
+        return int(lib().gf_context_device_count(self._h))
 
     def Synchronize(self):
         _check(lib().gf_context_synchronize(self._h))
@@ -216,6 +225,12 @@ class Context:
 
 def NewContext(device=0, _flags=-1):
     return Context(device)
+
+
+def NewContextMulti(devices):
+    """One context over several devices of this process (gf_context_create_multi): caches created on it stripe
+    their blocks over the devices, Set.Search scans all of them and returns one merged, id-resolved result."""
+    return Context(devices=list(devices))
 
 
 # ------------------------------------------------------------------ L1 Buffer (interface.go:120-143)

@@ -167,6 +167,49 @@ int gf_device_total_mem(int device, uint64_t *out_bytes)
     return GF_OK;
 }
 
+int gf_context_create_multi(const int *devices, int n, gf_context **out_ctx)
+{
+    if (!out_ctx || !devices || n < 1 || n > 64) return GF_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    // (a device may be listed more than once: its shards then share that device -- how the 1-GPU test box
+    // exercises the striping, the gather and the id resolution of a multi-device set)
+    gf_context *parent = nullptr;
+    int rc = gf_context_create(devices[0], &parent);
+    if (rc) return rc;
+    return guarded([&]() -> int {
+        for (int i = 0; i < n; ++i) {
+            gf_context *c = nullptr;
+            int r = gf_context_create(devices[i], &c);
+            if (r) {
+                delete parent;
+                return r;
+            }
+            parent->children.push_back(c);
+        }
+        // every device stores its winners into the root device's inbox: peer access (NVLink / NVSwitch on a B200 box)
+        bool ok = true;
+        for (int i = 0; i < n && ok; ++i)
+            for (int j = 0; j < n; ++j) {
+                if (devices[i] == devices[j]) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) {
+                    ok = false;
+                    break;
+                }
+                cudaSetDevice(devices[i]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+            }
+        parent->peer_ok = ok || n == 1;  // without it a search still works: the shards answer one by one (generic path)
+        cudaSetDevice(devices[0]);
+        *out_ctx = parent;
+        return GF_OK;
+    });
+}
+
+int gf_context_device_count(const gf_context *ctx) { return ctx ? (ctx->is_multi() ? (int)ctx->children.size() : 1) : 0; }
+
 int gf_context_create(int device, gf_context **out_ctx)
 {
     if (!out_ctx) return GF_ERR_INVALID_ARGUMENT;
@@ -200,6 +243,10 @@ int gf_context_create(int device, gf_context **out_ctx)
 int gf_context_destroy(gf_context *ctx)
 {
     if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    for (gf_context *c : ctx->children) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     delete ctx;
@@ -211,6 +258,11 @@ int gf_context_device(const gf_context *ctx) { return ctx ? ctx->device : -1; }
 int gf_context_synchronize(gf_context *ctx)
 {
     if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    for (gf_context *c : ctx->children) {
+        int rc = c->bind();
+        if (rc) return rc;
+        GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
+    }
     int rc = ctx->bind();
     if (rc) return rc;
     GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
@@ -220,6 +272,26 @@ int gf_context_synchronize(gf_context *ctx)
 int gf_context_stats(const gf_context *ctx, gf_stats *out)
 {
     if (!ctx || !out) return GF_ERR_INVALID_ARGUMENT;
+    if (ctx->is_multi()) {  // the sum over the parent and its devices
+        memset(out, 0, sizeof *out);
+        std::vector<const gf_context *> all(ctx->children.begin(), ctx->children.end());
+        uint64_t *acc = reinterpret_cast<uint64_t *>(out);
+        for (const gf_context *c : all) {
+            gf_stats one;
+            int rc = gf_context_stats(c, &one);
+            if (rc) return rc;
+            const uint64_t *v = reinterpret_cast<const uint64_t *>(&one);
+            for (size_t i = 0; i < sizeof(gf_stats) / sizeof(uint64_t); ++i) acc[i] += v[i];
+        }
+        const Stats &p = ctx->stats;
+        out->searches = p.searches;  // a search of the set, not one per shard
+        out->coalesced_batches += p.coalesced_batches;
+        out->quirk_fallbacks += p.quirk_fallbacks;
+        out->uncertified_queries += p.uncertified_queries;
+        out->h2d_bytes += p.h2d_bytes;
+        out->d2h_bytes += p.d2h_bytes;
+        return GF_OK;
+    }
     const_cast<gf_context *>(ctx)->prof_collect();
     const Stats &s = ctx->stats;
     out->scan_kernel_ns = s.scan_kernel_ns;
@@ -244,6 +316,7 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
 int gf_context_reset_stats(gf_context *ctx)
 {
     if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    for (gf_context *c : ctx->children) gf_context_reset_stats(c);
     Stats &s = ctx->stats;
     s.searches = s.scan_launches = s.gemm_launches = s.merge_launches = s.other_launches = 0;
     s.rows_scanned = s.quirk_fallbacks = s.coalesced_batches = s.h2d_bytes = s.d2h_bytes = 0;
@@ -257,6 +330,7 @@ int gf_context_reset_stats(gf_context *ctx)
 int gf_context_set_profiling(gf_context *ctx, int on)
 {
     if (!ctx) return GF_ERR_INVALID_ARGUMENT;
+    for (gf_context *c : ctx->children) c->profiling = on ? 1 : 0;
     ctx->profiling = on ? 1 : 0;
     return GF_OK;
 }
@@ -377,12 +451,42 @@ int gf_cache_create(gf_context *ctx, int block_num, int64_t block_size, gf_cache
     return gf_cache_create_ex(ctx, block_num, block_size, flags, out_cache);
 }
 
-int gf_cache_has_shadow(const gf_cache *cache) { return (cache && cache->shadow) ? cache->shadow_eb : 0; }
+int gf_cache_has_shadow(const gf_cache *cache)
+{
+    if (cache && cache->is_multi()) return gf_cache_has_shadow(cache->children[0]);
+    return (cache && cache->shadow) ? cache->shadow_eb : 0;
+}
 
 int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsigned flags, gf_cache **out_cache)
 {
     if (!ctx || !out_cache || block_num < 0 || block_size <= 0) return GF_ERR_INVALID_ARGUMENT;
     *out_cache = nullptr;
+    if (ctx->is_multi()) {
+        // block i of the cache = block i / G of device i % G's slab (cache.go:33-41 cuts ONE slab; here one per device)
+        return guarded([&]() -> int {
+            const int G = (int)ctx->children.size();
+            std::unique_ptr<gf_cache> c(new gf_cache());
+            c->ctx = ctx;
+            c->block_size = block_size;
+            c->multi_blocks = block_num;
+            bool shadow_everywhere = true;
+            for (int d = 0; d < G; ++d) {
+                gf_cache *cc = nullptr;
+                const int nb = (block_num - d + G - 1) / G;
+                int rc = gf_cache_create_ex(ctx->children[d], nb < 0 ? 0 : nb, block_size, flags, &cc);
+                if (rc) {
+                    for (gf_cache *x : c->children) gf_cache_destroy(x);
+                    return rc;
+                }
+                c->children.push_back(cc);
+                shadow_everywhere = shadow_everywhere && (cc->shadow != nullptr || nb <= 0);
+            }
+            (void)shadow_everywhere;
+            ctx->bind();
+            *out_cache = c.release();
+            return GF_OK;
+        });
+    }
     return guarded([&]() -> int {
         int rc = ctx->bind();
         if (rc) return rc;
@@ -443,6 +547,16 @@ int gf_cache_create_ex(gf_context *ctx, int block_num, int64_t block_size, unsig
 int gf_cache_destroy(gf_cache *cache)
 {
     if (!cache) return GF_ERR_INVALID_ARGUMENT;
+    if (cache->is_multi()) {
+        for (gf_context *c : cache->ctx->children) {  // no search of a parent set may still be running
+            cudaSetDevice(c->device);
+            cudaDeviceSynchronize();
+        }
+        for (gf_cache *cc : cache->children) gf_cache_destroy(cc);
+        cache->children.clear();
+        delete cache;
+        return GF_OK;
+    }
     cudaSetDevice(cache->ctx->device);
     cudaDeviceSynchronize();
     for (auto &s : cache->owned_sets) {
@@ -463,7 +577,23 @@ int gf_cache_new_set(gf_cache *cache, const char *name, int dims, int precision,
     return guarded([&]() -> int {
         std::lock_guard<std::mutex> g(cache->mu);
         if (cache->sets.count(name)) return GF_ERR_FEATURE_SET_EXIST;  // cache.go:47-50
+        std::vector<gf_set *> shards;
+        if (cache->is_multi()) {
+            const int G = (int)cache->children.size();
+            for (int d = 0; d < G; ++d) {
+                gf_set *sh = nullptr;
+                int rc = gf_cache_new_set(cache->children[d], name, dims, precision, batch);
+                if (rc == GF_OK) rc = gf_cache_get_set(cache->children[d], name, &sh);
+                if (rc == GF_OK) rc = gf_set_set_shard(sh, d, G);
+                if (rc) {
+                    for (int u = 0; u <= d; ++u) gf_cache_destroy_set(cache->children[u], name);
+                    return rc;
+                }
+                shards.push_back(sh);
+            }
+        }
         std::unique_ptr<Set> s(new gf_set());
+        s->shards = shards;
         s->cache = cache;
         s->ctx = cache->ctx;
         s->name = name;
@@ -514,6 +644,15 @@ int64_t gf_cache_get_block_size(const gf_cache *cache) { return cache ? cache->b
 int gf_cache_get_empty_block(gf_cache *cache, int block_num, gf_block **out_blocks)
 {
     if (!cache || block_num < 0 || (block_num > 0 && !out_blocks)) return GF_ERR_INVALID_ARGUMENT;
+    if (cache->is_multi()) {  // AllBlocks order over the striped view
+        std::lock_guard<std::mutex> g(cache->mu);
+        int k = 0;
+        for (int i = 0; i < cache->multi_blocks && k < block_num; ++i) {
+            Block *b = cache->multi_block_at(i);
+            if (!b->is_owned()) out_blocks[k++] = b;
+        }
+        return k < block_num ? GF_ERR_NOT_ENOUGH_BLOCKS : GF_OK;
+    }
     std::lock_guard<std::mutex> g(cache->mu);
     int n = 0;
     for (auto &b : cache->all_blocks)
@@ -527,10 +666,17 @@ int gf_cache_get_empty_block(gf_cache *cache, int block_num, gf_block **out_bloc
     return GF_OK;
 }
 
-int gf_cache_block_count(const gf_cache *cache) { return cache ? (int)cache->all_blocks.size() : 0; }
+int gf_cache_block_count(const gf_cache *cache)
+{
+    return cache ? (cache->is_multi() ? cache->multi_blocks : (int)cache->all_blocks.size()) : 0;
+}
 
 int gf_cache_block_at(gf_cache *cache, int index, gf_block **out_block)
 {
+    if (cache && cache->is_multi() && out_block && index >= 0 && index < cache->multi_blocks) {
+        *out_block = cache->multi_block_at(index);
+        return GF_OK;
+    }
     if (!cache || !out_block || index < 0 || index >= (int)cache->all_blocks.size()) return GF_ERR_INVALID_ARGUMENT;
     *out_block = cache->all_blocks[index].get();
     return GF_OK;
@@ -729,12 +875,19 @@ int gf_set_export(gf_set *set, void *out_values, uint64_t values_cap, char *out_
 int gf_set_dims(const gf_set *set) { return set ? set->dims : 0; }
 int gf_set_precision(const gf_set *set) { return set ? set->precision : 0; }
 int gf_set_batch(const gf_set *set) { return set ? set->batch : 0; }
-int gf_set_block_count(const gf_set *set) { return set ? (int)set->blocks.size() : 0; }
+int gf_set_block_count(const gf_set *set)
+{
+    if (!set) return 0;
+    int n = (int)set->blocks.size();
+    for (const gf_set *sh : set->shards) n += (int)sh->blocks.size();
+    return n;
+}
 int64_t gf_set_scanned_rows(const gf_set *set) { return set ? set->scanned_rows : 0; }
 int64_t gf_set_live_rows(const gf_set *set)
 {
     if (!set) return 0;
     int64_t n = 0;
+    for (const gf_set *sh : set->shards) n += gf_set_live_rows(sh);
     for (const Block *b : set->blocks) n += b->live_count;
     return n;
 }
@@ -793,6 +946,7 @@ uint32_t gf_key_slot(uint64_t key) { return key_slot(key); }
 int gf_set_set_shard(gf_set *set, int rank, int world)
 {
     if (!set || world < 1 || rank < 0 || rank >= world) return GF_ERR_INVALID_ARGUMENT;
+    if (set->is_multi()) return GF_ERR_UNSUPPORTED;  // its shards already carry their identities
     return guarded([&]() -> int {
         set->lock.lock();
         set->shard_rank = rank;
@@ -827,6 +981,19 @@ int gf_set_device_counters(gf_set *set, uint64_t *out_flagged, uint64_t *out_unr
     if (!set) return GF_ERR_INVALID_ARGUMENT;
     return guarded([&]() -> int {
         unsigned int h[4] = {0, 0, 0, 0};
+        if (set->is_multi()) {
+            uint64_t a = 0, b = 0;
+            for (gf_set *sh : set->shards) {
+                uint64_t x = 0, y = 0;
+                int rc = gf_set_device_counters(sh, &x, &y);
+                if (rc) return rc;
+                a += x;
+                b += y;
+            }
+            if (out_flagged) *out_flagged = a;
+            if (out_unrepaired) *out_unrepaired = b;
+            return GF_OK;
+        }
         set->lock.lock_shared();
         cudaError_t e = cudaSuccess;
         if (set->d_small != nullptr && set->ctx->bind() == GF_OK) {
@@ -1008,6 +1175,7 @@ int gf_set_add_synthetic(gf_set *set, int64_t n, uint64_t seed, int64_t first_or
 int gf_set_set_search_path(gf_set *set, int path)
 {
     if (!set || path < 0 || path > 5) return GF_ERR_INVALID_ARGUMENT;
+    for (gf_set *sh : set->shards) sh->search_path = path;
     set->search_path = path;
     return GF_OK;
 }

@@ -49,6 +49,55 @@ __device__ __forceinline__ void exchange_fold(const ExchangeArgs &a, int qi, con
     const int slot = (int)(a.seq & 1ull);
     const size_t keys_per_slot = (size_t)world * a.max_q * a.max_k;
     const size_t words_off = 2 * keys_per_slot;  // in u64 units
+    if (a.gather_root_plus1 > 0) {
+        // ---- gather to one rank: K stores + one word per query instead of world x (K + 1), one waiter
+        const int root = a.gather_root_plus1 - 1;
+        unsigned long long *rbase = reinterpret_cast<unsigned long long *>(a.peers[root]);
+        for (int j = threadIdx.x; j < K; j += blockDim.x)
+            rbase[(size_t)slot * keys_per_slot + ((size_t)a.rank * a.max_q + qi) * a.max_k + j] = local[j];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            volatile unsigned long long *w = rbase + words_off + ((size_t)slot * world + a.rank) * a.max_q + qi;
+            *w = (a.seq << 1) | (local_flag ? 1ull : 0ull);
+        }
+        if (a.rank != root) return;
+        if (threadIdx.x == 0) *s_flag = 0u;
+        __syncthreads();
+        if ((int)threadIdx.x < world) {
+            volatile unsigned long long *w = rbase + words_off + ((size_t)slot * world + threadIdx.x) * a.max_q + qi;
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned long long word;
+            unsigned int spins = 0;
+            while (((word = *w) >> 1) != a.seq) {
+                if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {
+                    atomicOr(s_flag, 0xFFFFFFFFu);
+                    break;
+                }
+            }
+            if (word & 1ull) atomicOr(s_flag, 1u);
+            *w = 0ull;  // consumed: the next step may carry the same sequence number
+        }
+        __threadfence_system();
+        __syncthreads();
+        const unsigned long long *mine = rbase + (size_t)slot * keys_per_slot;
+        const int n = world * K;
+        int np = 2;
+        while (np < n) np <<= 1;
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            unsigned long long v = 0ull;
+            if (i < n) {
+                const int r = i / K, j = i - r * K;
+                v = __ldcv(mine + ((size_t)r * a.max_q + qi) * a.max_k + j);
+            }
+            buf[i] = v;
+        }
+        __syncthreads();
+        block_sort_desc(buf, np);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) out_keys[(size_t)qi * K + i] = buf[i];
+        if (out_flag != nullptr && threadIdx.x == 0) out_flag[qi] = *s_flag;
+        return;
+    }
     // ---- push my K keys of this query into every inbox (mine included)
     for (int i = threadIdx.x; i < world * K; i += blockDim.x) {
         const int p = i / K, j = i - p * K;

@@ -78,11 +78,19 @@ struct ExchangeArgs {
     unsigned long long *out_keys;          // [q][K]
     unsigned int *out_flags;               // optional [q]: OR of every rank's flag; 0xFFFFFFFF = a peer never arrived
     unsigned long long timeout_ns;
+    // 0: every rank pushes to every rank and folds (one process per GPU: all ranks need the answer).
+    // r + 1: gather to rank r -- the others push their keys into r's inbox only and leave; r alone waits, folds,
+    // writes out_keys / out_flags and clears the words it consumed, so the SAME sequence number serves the next
+    // step (the caller does not start one before r has finished: gf_context_create_multi's in-process sets,
+    // whose steps are recorded CUDA graphs with these arguments baked in).
+    int gather_root_plus1;
 };
 cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int q, int K, int max_q, int max_k,
                                   unsigned long long seq, const unsigned long long *d_local_keys,
                                   const unsigned int *d_local_flags, unsigned long long *d_out_keys,
                                   unsigned int *d_out_flags, cudaStream_t stream);
+
+cudaError_t exchange_args_launch(const ExchangeArgs &a, cudaStream_t stream);
 
 // ---- tcgen05 contraction path (gf_gemm.cu) ----
 constexpr int kGemmMaxQ = 256;       // queries per pass (N of the MMA)

@@ -424,6 +424,14 @@ cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int
     return launch_chain(exchange_merge_kernel, dim3(q), dim3(256), 0, stream, a);
 }
 
+// the same kernel with caller-built arguments (gather to one rank: gf_context_create_multi's in-process sets)
+cudaError_t exchange_args_launch(const ExchangeArgs &a, cudaStream_t stream)
+{
+    if (a.q < 1 || a.K < 1 || a.q > a.max_q || a.K > a.max_k || a.world * a.K > kMergeBuf || a.world > 256)
+        return cudaErrorInvalidValue;
+    return launch_chain(exchange_merge_kernel, dim3(a.q), dim3(256), 0, stream, a);
+}
+
 cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, int q, int K,
                          unsigned long long *d_out, cudaStream_t stream, const unsigned int *d_q_count,
                          const int *d_out_map)

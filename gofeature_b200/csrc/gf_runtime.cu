@@ -124,6 +124,7 @@ int Workspace::reserve_tensor(size_t bytes)
 
 Workspace::~Workspace()
 {
+    delete multi;
     drop_graphs();
     if (d_tensor) cudaFree(d_tensor);
     if (d_buf) cudaFree(d_buf);
@@ -321,6 +322,7 @@ Context::~gf_context()
         if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
     }
     if (mut_stream) cudaStreamDestroy(mut_stream);
+    for (gf_context *c : children) delete c;  // after ws_all: a multi-device workspace hands its parts back to them
 }
 
 gf::DeviceAlloc::~DeviceAlloc()
@@ -740,7 +742,25 @@ bool Set::slot_to_block(uint32_t slot, int *block_pos, int *row) const
     return true;
 }
 
+bool Set::locate_slot(uint32_t slot, const Block **b, int *row) const
+{
+    if (cap <= 0) return false;
+    if (is_multi()) {
+        const uint64_t gb = slot / (uint32_t)cap;
+        const Set *sh = shards[(size_t)(gb % shards.size())];
+        int bp;
+        if (!sh->slot_to_block(slot, &bp, row)) return false;
+        *b = sh->blocks[bp];
+        return true;
+    }
+    int bp;
+    if (!slot_to_block(slot, &bp, row)) return false;
+    *b = blocks[bp];
+    return true;
+}
+
 static std::atomic<uint64_t> g_set_version{0};
+uint64_t gf::next_set_version() { return ++g_set_version; }
 
 int Set::rebuild_segments()
 {
@@ -782,7 +802,7 @@ int Set::rebuild_segments()
         tensor_ok = old_tensor_ok;
         return GF_OK;
     }
-    version = ++g_set_version;  // process-wide unique: a cached graph can never match a different table
+    version = next_set_version();  // process-wide unique: a cached graph can never match a different table
     if (h_segs.empty()) return GF_OK;
     int rc = ctx->bind();
     if (rc) return rc;
@@ -870,7 +890,9 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (n == 0) return GF_OK;
+    if (is_multi()) return multi_add(n, values, ids_);
     ExclusiveGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;  // DestroySet won the lock first
     int rc = quiesce(ctx);
     if (rc) return rc;
     int64_t empty = 0;
@@ -888,9 +910,13 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
                 if (!ub->is_owned()) got.push_back(ub.get());
             }
             if ((int64_t)got.size() < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
-            for (Block *b : got) {
+            for (size_t gi = 0; gi < got.size(); ++gi) {
+                Block *b = got[gi];
                 rc = b->acquire(name, dims, precision, batch);
-                if (rc) return rc;
+                if (rc) {  // hand back what this call took: nothing may stay owned outside `blocks`
+                    for (size_t u = 0; u < gi; ++u) got[u]->release();
+                    return rc;
+                }
                 b->set = this;
                 b->use_index = has_dups;
             }
@@ -938,7 +964,9 @@ int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int norm
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (precision != 4) return GF_ERR_UNSUPPORTED;
     if (n == 0) return GF_OK;
+    if (is_multi()) return multi_add_synthetic(n, seed, first_ordinal, normalize, prefix);
     ExclusiveGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
     if (rc) return rc;
     // synthetic rows only append (never refill tombstones): count tail room
@@ -955,9 +983,13 @@ int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int norm
             if (!ub->is_owned()) got.push_back(ub.get());
         }
         if ((int64_t)got.size() < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
-        for (Block *b : got) {
+        for (size_t gi = 0; gi < got.size(); ++gi) {
+            Block *b = got[gi];
             rc = b->acquire(name, dims, precision, batch);
-            if (rc) return rc;
+            if (rc) {
+                for (size_t u = 0; u < gi; ++u) got[u]->release();
+                return rc;
+            }
             b->set = this;
             b->use_index = has_dups;
             // implicit ids: do not keep capacity() empty strings per block
@@ -1027,7 +1059,9 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     found.assign(ids_.size(), 0);
     if (ids_.empty()) return GF_OK;
+    if (is_multi()) return multi_remove(ids_, found);
     ExclusiveGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
     if (rc) return rc;
     // set.go:163-193 walks the blocks and block.go:136-147 scans every IDs[]; the locator answers the same
@@ -1069,7 +1103,9 @@ int Set::update(int64_t n, const uint8_t *values, const std::vector<std::string>
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     found.assign(ids_.size(), 0);
     if (n == 0) return GF_OK;
+    if (is_multi()) return multi_update(n, values, ids_, found);
     ExclusiveGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
     if (rc) return rc;
     const size_t rowb = (size_t)dims * precision;
@@ -1091,7 +1127,9 @@ int Set::read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<ui
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     found.assign(ids_.size(), 0);
+    if (is_multi()) return multi_read(ids_, out, found);
     SharedGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = ctx->bind();
     if (rc) return rc;
     const size_t rowb = (size_t)dims * precision;
@@ -1115,7 +1153,9 @@ int Set::compact(int64_t *reclaimed)
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (precision != 4) return GF_ERR_UNSUPPORTED;
+    if (is_multi()) return multi_compact(reclaimed);
     ExclusiveGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
     if (rc) return rc;
     int64_t freed = 0;
@@ -1182,6 +1222,7 @@ int Set::export_rows(uint8_t *out_values, uint64_t values_cap, char *out_ids, ui
                      int64_t *out_rows, uint64_t *out_id_bytes)
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (is_multi()) return multi_export(out_values, values_cap, out_ids, ids_cap, out_off, out_rows, out_id_bytes);
     SharedGuard g(lock);
     int rc = ctx->bind();
     if (rc) return rc;
@@ -1224,7 +1265,9 @@ int Set::export_rows(uint8_t *out_values, uint64_t values_cap, char *out_ids, ui
 int Set::destroy()
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (is_multi()) return multi_destroy();
     ExclusiveGuard g(lock);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
     if (rc) return rc;
     destroyed = true;
@@ -1299,6 +1342,8 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     // bake_io (Search's own staging buffers, stable per workspace): the query preparation and the copy of
     // keys + flags are nodes of the graph too -- ONE stream operation per call
     bake_io = bake_io && d_flags != nullptr && q_stride == dims && l_stride == 1 && stream == ws->stream;
+    // a multi-device set's step ends with the gather-to-root exchange: baked into the graph like the buffers
+    const void *xkey = (bake_io && ws->xchg != nullptr) ? (const void *)ws->xchg->peers : nullptr;
     // The one-pass chain is three launches that write straight into the caller's buffers: replaying a graph would
     // need an eager preparation before it and a copy of the results behind it -- as many stream operations, and
     // the copy sits on the device's critical path.  Only Search's own stable buffers (bake_io) are worth a graph.
@@ -1307,7 +1352,8 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t res_b = align_up((size_t)q * K * 8, 256);
     for (auto &g : ws->graphs) {
         if (g.set == this && g.version == version && g.q == q && g.K == K && g.mode == mode &&
-            g.src == (bake_io ? (const void *)d_queries : nullptr) && g.dst == (bake_io ? (void *)d_out : nullptr)) {
+            g.src == (bake_io ? (const void *)d_queries : nullptr) && g.dst == (bake_io ? (void *)d_out : nullptr) &&
+            g.xkey == xkey) {
             g.stamp = ++ws->graph_clock;
             st.scan_launches += g.d_scan;
             st.gemm_launches += g.d_gemm;
@@ -1317,6 +1363,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
             st.rows_scanned += g.d_rows;
             if (bake_io) {
                 GF_CUDA(cudaGraphLaunch(g.exec, stream), GF_ERR_CUDA);
+                ws->xchg_used = g.xchg_in_graph;
                 return GF_OK;
             }
             int rc = topk_tensor(ws, stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 1, path, device_fixup);
@@ -1356,6 +1403,7 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
         crc = topk_tensor(ws, ws->stream, d_queries, q, q_stride, l_stride, K, nullptr, nullptr, 2, path, device_fixup);
     ws->direct_out = nullptr;
     ws->direct_flags = nullptr;
+    const bool graph_xchg = ws->xchg_used;  // (the eager first run above used it too, or neither did)
     if (crc == GF_OK && bake_io && !ws->wrote_direct) {
         const bool contig = (uint8_t *)d_flags == (uint8_t *)d_out + res_b &&
                             (uint8_t *)ws->t_flags == (uint8_t *)ws->t_res + res_b;
@@ -1401,6 +1449,8 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
     cg.mode = mode;
     cg.src = bake_io ? (const void *)d_queries : nullptr;
     cg.dst = bake_io ? (void *)d_out : nullptr;
+    cg.xkey = xkey;
+    cg.xchg_in_graph = graph_xchg;
     cg.exec = exec;
     cg.stamp = ++ws->graph_clock;
     ws->graphs.push_back(cg);
@@ -1612,6 +1662,12 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                 t.d_out = ws->direct_out;  // (one pass: p0 == 0)
                 t.d_flags = ws->direct_flags;
                 ws->wrote_direct = true;
+                if (ws->xchg != nullptr && ws->xchg->gather_root_plus1 > 0 && ws->xchg->q == qp && ws->xchg->K == K &&
+                    qp == q) {
+                    t.has_xchg = 1;        // a multi-device set: the recorded step ends with the gather to the root
+                    t.xchg = *ws->xchg;
+                    ws->xchg_used = true;
+                }
             } else if (phase == 0 && d_flags != nullptr) {
                 t.d_flags = d_flags;       // the caller's own flags: no copy behind the chain
                 flags_direct = true;
@@ -1787,6 +1843,7 @@ static cudaError_t wait_stream(cudaStream_t s)
 
 bool Set::direct_applies(int limit, int q, int *kb) const
 {
+    if (is_multi()) return multi_direct_applies(limit, q, kb);
     if (precision != 4 || scanned_rows <= 0 || limit <= 0 || q <= 0 || q > kGemmMaxQ) return false;
     const int64_t k_total = std::min<int64_t>(limit, scanned_rows);
     if (k_total > kMaxK) return false;
@@ -1797,6 +1854,7 @@ bool Set::direct_applies(int limit, int q, int *kb) const
 int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, const int *part_q, int nparts,
                      unsigned long long **h_keys)
 {
+    if (is_multi()) return multi_direct_keys(ws, kb, q, parts, part_q, nparts, h_keys);
     const size_t qbytes = (size_t)q * dims * 4;
     const size_t out_keys = (size_t)q * kb;
     const size_t d_need = align_up(qbytes, 256) + align_up(out_keys * 8, 256) + scratch_bytes(this, q, kb, false);
@@ -1845,15 +1903,17 @@ bool Set::resolve_winners(const unsigned long long *keys, int kb, float threshol
     int n = 0;
     while (n < kb && keys[n] != 0ull) ++n;
     for (int j = 0; j < n; ++j) {  // tombstones among the winners?  (block.go:236-243 selects before it drops them)
-        int bp, row;
-        if (!slot_to_block(key_slot(keys[j]), &bp, &row) || !blocks[bp]->live[row]) return false;
+        const Block *b;
+        int row;
+        if (!locate_slot(key_slot(keys[j]), &b, &row) || !b->live[row]) return false;
     }
     for (int j = 0; j < n; ++j) {
         const float sc = key_score(keys[j]);
         if (!(sc >= threshold)) continue;  // set.go:145
-        int bp, row;
-        slot_to_block(key_slot(keys[j]), &bp, &row);
-        r->push(sc, key_slot(keys[j]), blocks[bp]->id_at(row));
+        const Block *b;
+        int row;
+        locate_slot(key_slot(keys[j]), &b, &row);
+        r->push(sc, key_slot(keys[j]), b->id_at(row));
     }
     r->end_query();
     return true;
@@ -1862,6 +1922,7 @@ bool Set::resolve_winners(const unsigned long long *keys, int kb, float threshol
 // set.go:118-159 + block.go:184-249
 int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out)
 {
+    if (is_multi()) return multi_search_now(threshold, limit, q, queries, out);
     std::unique_ptr<Result> res(new Result());
     res->begin(q);
     SharedGuard g(lock);
@@ -2363,6 +2424,10 @@ int Set::search_device(int limit, int q, const float *d_queries, unsigned long l
 {
     if (xchg_used) *xchg_used = false;
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
+    if (is_multi()) {
+        set_error_detail("device-resident searches address one device: use gf_set_search on a multi-device set");
+        return GF_ERR_UNSUPPORTED;
+    }
     if (q > batch) return GF_ERR_OUT_OF_BATCH;
     if (q <= 0 || limit <= 0) return GF_ERR_INVALID_ARGUMENT;
     if (limit > kMaxK) return GF_ERR_UNSUPPORTED;
@@ -2411,10 +2476,11 @@ int Set::resolve_keys(float threshold, int limit, int q, const unsigned long lon
             if (k == 0ull) break;
             float sc = key_score(k);
             if (!(sc >= threshold)) continue;
-            int bp, row;
-            if (slot_to_block(key_slot(k), &bp, &row)) {
-                if (!blocks[bp]->live[row]) continue;
-                res->push(sc, key_slot(k), blocks[bp]->id_at(row));
+            const Block *b;
+            int row;
+            if (locate_slot(key_slot(k), &b, &row)) {
+                if (!b->live[row]) continue;
+                res->push(sc, key_slot(k), b->id_at(row));
             } else {
                 res->push(sc, key_slot(k), std::string());  // another shard owns this slot
             }

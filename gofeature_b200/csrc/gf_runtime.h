@@ -36,6 +36,7 @@ using Set = ::gf_set;
 using Result = ::gf_result;
 
 void set_error_detail(const std::string &s);
+uint64_t next_set_version();
 int cuda_fail(cudaError_t e, const char *what, int status = GF_ERR_CUDA);
 
 #define GF_CUDA(call, status)                                   \
@@ -82,6 +83,8 @@ struct Workspace {
         int q, K, mode;
         const void *src;  // baked-in query source / result destination (Search's pinned staging buffers), or
         void *dst;        // null: the query preparation and the result copy stay outside the graph
+        const void *xkey; // baked-in cross-device exchange (its inbox table), or null
+        bool xchg_in_graph;  // ... and whether the recorded chain performs it (one-pass chain) or the caller launches it
         cudaGraphExec_t exec;
         uint64_t d_scan, d_gemm, d_merge, d_other, d_tensor_passes, d_rows;  // counters one replay adds
         uint64_t stamp;
@@ -99,10 +102,26 @@ struct Workspace {
     // a sharded caller's cross-rank step: the one-pass chain's tail ends with it (sets xchg_used) instead of a launch
     const ExchangeArgs *xchg = nullptr;
     bool xchg_used = false;
+    struct MultiExt *multi = nullptr;  // a multi-device set's per-search state (child workspaces, inboxes): gf_multi.cu
     void drop_graphs();
     int reserve(size_t d_bytes, size_t h_bytes);
     int reserve_tensor(size_t bytes);
     ~Workspace();
+};
+
+// What one in-flight search of a multi-device set (gf_context_create_multi) owns besides its parent workspace:
+// a workspace on every device, an inbox on every device for the gather-to-root exchange, and one portable
+// pinned buffer every device reads the queries from and the root device writes the merged winners to.
+struct MultiExt {
+    std::vector<::gf_context *> ctxs;
+    std::vector<Workspace *> ws;
+    std::vector<void *> inbox;
+    std::vector<void **> d_peers;
+    int max_q = 0, max_k = 0;
+    uint8_t *h_pin = nullptr;
+    size_t h_cap = 0;
+    bool dirty = false;  // a step failed half way: clear the inboxes before the next one
+    ~MultiExt();
 };
 
 }  // namespace gf
@@ -129,6 +148,11 @@ struct gf_context {
     std::vector<Workspace *> ws_free;
     std::vector<Workspace *> ws_all;
 
+    // gf_context_create_multi: this context lives on devices[0] (buffers, bare blocks) and owns one child context
+    // per device (children[0] is a second context on devices[0]); caches created on it stripe their blocks
+    std::vector<gf_context *> children;
+    bool peer_ok = false;  // every child device can store into the root device's memory
+    bool is_multi() const { return !children.empty(); }
     int bind() const;  // cudaSetDevice
     Workspace *acquire_ws();
     void release_ws(Workspace *w);
@@ -301,6 +325,29 @@ struct gf_set {
     uint64_t co_batch_id = 0;   // batches served so far
     int co_last_group = 0;      // requests in the last batch
 
+    // ---- a set of a multi-device cache: no blocks of its own, one shard per device (shard d = rank d of
+    // shards.size(), owned by the child cache); every public operation goes through the parent (gf_multi.cu)
+    std::vector<gf_set *> shards;
+    bool is_multi() const { return !shards.empty(); }
+    void multi_refresh();  // scanned_rows / version after a mutation
+    int multi_add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
+    int multi_add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
+    int multi_remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
+    int multi_update(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
+    int multi_read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<uint8_t> &found);
+    int multi_search_now(float threshold, int limit, int q, const uint8_t *queries, Result **out);
+    int multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, const int *part_q, int nparts,
+                          unsigned long long **h_keys);
+    bool multi_direct_applies(int limit, int q, int *kb) const;
+    int multi_destroy();
+    int multi_compact(int64_t *reclaimed);
+    int multi_export(uint8_t *out_values, uint64_t values_cap, char *out_ids, uint64_t ids_cap, uint64_t *out_off,
+                     int64_t *out_rows, uint64_t *out_id_bytes);
+    // owner shard of an id: the first block in GLOBAL block order holding it (set.go:167-170)
+    bool multi_find(const std::string &id, int *shard, int *pos, int *row) const;
+    // the block and row of a (global) slot, whichever shard owns it; false: no such block
+    bool locate_slot(uint32_t slot, const Block **b, int *row) const;
+
     uint32_t slot_base_of(int block_pos) const
     {
         return (uint32_t)(((uint64_t)block_pos * shard_world + shard_rank) * (uint64_t)cap);
@@ -375,6 +422,16 @@ struct gf_cache {
     std::mutex mu;  // cache.go:17
     std::unordered_map<std::string, gf::Set *> sets;
     std::vector<std::unique_ptr<gf::Set>> owned_sets;  // live and destroyed (handles stay valid)
+    // multi-device cache: block i of the cache = block i / G of children[i % G] (cache.go:104-115 hands blocks out
+    // in AllBlocks order, so a growing set is striped evenly over the devices); no slab of its own
+    std::vector<gf_cache *> children;
+    int multi_blocks = 0;
+    bool is_multi() const { return !children.empty(); }
+    gf::Block *multi_block_at(int i) const
+    {
+        const int G = (int)children.size();
+        return children[i % G]->all_blocks[i / G].get();
+    }
 };
 
 namespace gf {

@@ -107,6 +107,17 @@ GF_API int gf_device_total_mem(int device, uint64_t *out_bytes);
 /* cuda.NewContext(devices[i], -1) (search_test.go:40).  Fails with GF_ERR_CREATE_CONTEXT /
  * GF_ERR_INVALID_DEVICE_ID; never falls back to the CPU. */
 GF_API int gf_context_create(int device, gf_context **out_ctx);
+/* One context over several devices of THIS process (north_star: a set row-sharded over the GPUs of one box, behind
+ * the same Cache / Set API).  Caches created on it stripe their blocks -- block i on devices[i % n], the order
+ * Cache.GetEmptyBlock hands them out (cache.go:104-115) -- so a growing set spreads evenly; slots in results stay
+ * global ((block position in Set.Blocks) * capacity + row).  gf_set_search launches every device's scan from the
+ * calling thread; the per-device winners meet in devices[0] over peer memory (one kernel, no collective library)
+ * and the merged, id-resolved result comes back exactly as from a one-device set.  Buffers and bare blocks created
+ * through this context live on devices[0].  A device may be listed more than once (its shards share it).  The device-resident entry points (gf_set_search_device*) address one
+ * device and return GF_ERR_UNSUPPORTED on such a set. */
+GF_API int gf_context_create_multi(const int *devices, int n, gf_context **out_ctx);
+/* Devices behind this context (1 for gf_context_create). */
+GF_API int gf_context_device_count(const gf_context *ctx);
 GF_API int gf_context_destroy(gf_context *ctx);
 GF_API int gf_context_device(const gf_context *ctx);
 /* Block the caller until all work submitted through this context has finished. */

@@ -53,6 +53,7 @@ int main(int argc, char **argv)
     const int add_size = (int)arg(argc, argv, "--add-size", 0);      // rows per Add call (0 = 1..10 like the demo)
     const int del_size = (int)arg(argc, argv, "--delete-size", 1);   // ids per Delete call
     const int device = (int)arg(argc, argv, "--device", 0);
+    const int ndev = (int)arg(argc, argv, "--devices", 1);   // > 1: one set striped over that many devices of this process
     const long block_size = 1024L * 1024 * 32;                  // BlockSize demo/main.go:19
     const long cap = block_size / (dims * 4L);
     const int block_num = (int)((rows + cap - 1) / cap) + 4;
@@ -60,7 +61,15 @@ int main(int argc, char **argv)
     gf_context *ctx;
     gf_cache *cache;
     gf_set *set;
-    CK(gf_context_create(device, &ctx));
+    if (ndev > 1) {
+        int have = 0;
+        CK(gf_device_count(&have));
+        std::vector<int> devs;
+        for (int i = 0; i < ndev; ++i) devs.push_back((device + i) % std::max(have, 1));
+        CK(gf_context_create_multi(devs.data(), ndev, &ctx));
+    } else {
+        CK(gf_context_create(device, &ctx));
+    }
     CK(gf_cache_create(ctx, block_num, block_size, &cache));
     CK(gf_cache_new_set(cache, "test0", dims, 4, std::max(batch, 16)));
     CK(gf_cache_get_set(cache, "test0", &set));
@@ -207,7 +216,8 @@ int main(int argc, char **argv)
         gf_result_free(r);
     }
     const double nsearch = (double)all.size();
-    printf("{\"rows\": %ld, \"dims\": %d, \"threads\": %d, \"rounds\": %d, \"batch\": %d, \"limit\": %d, \"coalesce_us\": %d, "
+    printf("{\"devices\": %d, ", gf_context_device_count(ctx));
+    printf("\"rows\": %ld, \"dims\": %d, \"threads\": %d, \"rounds\": %d, \"batch\": %d, \"limit\": %d, \"coalesce_us\": %d, "
            "\"fill_ms\": %.1f, \"wall_ms\": %.3f, \"searches\": %.0f, \"queries\": %.0f, \"qps\": %.1f, \"avg_ms\": %.4f, "
            "\"p50_ms\": %.4f, \"p99_ms\": %.4f, \"hits\": %ld, ",
            rows, dims, threads, rounds, batch, limit, coalesce, fill_ms, wall_ms, nsearch, nsearch * batch,
