@@ -442,6 +442,32 @@ def run_ours(args, rank, world, local_rank):
     scan_ms, per_step, tensor, stats = profile_kernel(ctx, step_device, max(args.steps, 20))
     H.barrier()
 
+    # ---- where the cross-rank step spends its time (device clock, per rank; the wait includes the skew between ranks)
+    xtrace = None
+    if world > 1:
+        ctx.SetProfiling(True)
+        rows_ns = []
+        for i in range(40):
+            for j in range(12):          # back to back: the ranks fall into lock step, the last step is the sample
+                step_device(i * 12 + j)
+            tr = sset.exchange_trace(Q)
+            if tr is None:
+                break
+            if i >= 5:
+                t = tr.astype(np.int64)
+                rows_ns.append([float((t[:, 1] - t[:, 0]).mean()), float((t[:, 2] - t[:, 1]).mean()),
+                                float((t[:, 3] - t[:, 2]).mean()), float(t[:, 3].max() - t[:, 0].min())])
+        ctx.SetProfiling(False)
+        if rows_ns:
+            m = np.median(np.array(rows_ns), axis=0) / 1e3
+            worst = H.max_over_ranks(list(m))
+            xtrace = {"push_publish_us": m[0], "wait_for_peers_us": m[1], "fold_us": m[2], "first_enter_to_last_done_us": m[3],
+                      "max_over_ranks": {"push_publish_us": worst[0], "wait_for_peers_us": worst[1], "fold_us": worst[2],
+                                         "first_enter_to_last_done_us": worst[3]},
+                      "how": "globaltimer stamps inside the tail kernel's exchange (rank 0's medians over 35 samples, each the "
+                             "last of 12 back-to-back steps)"}
+    H.barrier()
+
     # ---- correctness of what was just timed, at this N
     parity = parity_check(H, sset, dpool, K, Q, rows_total)
 
@@ -584,7 +610,7 @@ def run_ours(args, rank, world, local_rank):
         "uncertified_queries": int(flagged_timed),
         "uncertified_note": "queries of the timed region whose certificate refused (device counter, summed over ranks); "
                             "the host API re-runs such a query through the exact scan",
-        "parity_check": parity,
+        "parity_check": parity, "exchange_trace": xtrace,
         "exactness": "ids, order and scores are the canonical float32 answer (bit-identical to the oracle in the GPU "
                      "tests): the int8 / bf16 / tf32 pass only selects candidates, every winner is re-scored from the "
                      "float32 rows and certified against the measured quantisation residual; a query that cannot be "

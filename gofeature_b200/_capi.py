@@ -116,6 +116,7 @@ SIGNATURES = {
     "gf_exchange_connect": (c_int, [c_vp, c_vp, c_u64]),
     "gf_exchange_merge_device": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gf_set_search_device_xchg": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "gf_exchange_trace": (c_int, [c_vp, c_int, c_vp]),
     "gf_exchange_destroy": (c_int, [c_vp]),
 }
 

@@ -1008,6 +1008,15 @@ int gf_set_device_counters(gf_set *set, uint64_t *out_flagged, uint64_t *out_unr
     });
 }
 
+// The low word of a sequence number tags every word of the step (gf_exchange.cuh) and must never be 0 (a fresh
+// inbox is zeroed); skipping TWO numbers keeps the slot parity alternating.
+static unsigned long long next_exchange_seq(unsigned long long s)
+{
+    unsigned long long n = s + 1;
+    if ((n & 0xFFFFFFFFull) == 0ull) n += 2;
+    return n;
+}
+
 // ---- peer exchange of per-rank winners over NVLink peer memory (one process per GPU)
 // (gf_set_search_device_xchg, below gf_exchange_merge_device, runs a search that ends with the exchange)
 struct gf_exchange {
@@ -1018,6 +1027,7 @@ struct gf_exchange {
     void **d_peers = nullptr;
     unsigned long long seq = 0;
     bool connected = false;
+    unsigned long long *d_trace = nullptr;  // [max_q][4] timestamps of the last step (gf_exchange_trace)
 };
 
 int gf_exchange_create(gf_context *ctx, int rank, int world, int max_q, int max_limit, gf_exchange **out)
@@ -1039,6 +1049,8 @@ int gf_exchange_create(gf_context *ctx, int rank, int world, int max_q, int max_
         GF_CUDA(cudaMalloc(&x->inbox, bytes), GF_ERR_ALLOCATE_GPU_BUFFER);  // cudaMalloc: exportable through CUDA IPC
         GF_CUDA(cudaMemset(x->inbox, 0, bytes), GF_ERR_CLEAR_CUDA_BUFFER);
         GF_CUDA(cudaMalloc((void **)&x->d_peers, sizeof(void *) * world), GF_ERR_ALLOCATE_GPU_BUFFER);
+        GF_CUDA(cudaMalloc((void **)&x->d_trace, sizeof(unsigned long long) * 4 * max_q), GF_ERR_ALLOCATE_GPU_BUFFER);
+        GF_CUDA(cudaMemset(x->d_trace, 0, sizeof(unsigned long long) * 4 * max_q), GF_ERR_CLEAR_CUDA_BUFFER);
         GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
         x->peers.assign((size_t)world, nullptr);
         x->peers[rank] = x->inbox;
@@ -1083,7 +1095,7 @@ int gf_exchange_merge_device(gf_exchange *x, int q, int limit, const uint64_t *d
     int rc = x->ctx->bind();
     if (rc) return rc;
     // every rank calls this the same number of times in the same order: the sequence number is implicit
-    const unsigned long long seq = ++x->seq;
+    const unsigned long long seq = x->seq = next_exchange_seq(x->seq);
     GF_CUDA(exchange_merge_launch(x->d_peers, x->rank, x->world, q, limit, x->max_q, x->max_k, seq,
                                   (const unsigned long long *)d_local_keys, d_local_flags,
                                   (unsigned long long *)d_out_keys, d_out_flags, (cudaStream_t)stream),
@@ -1101,15 +1113,17 @@ int gf_set_search_device_xchg(gf_set *set, gf_exchange *x, int limit, int q, con
     if (q < 1 || limit < 1 || q > x->max_q || limit > x->max_k) return GF_ERR_UNSUPPORTED;
     return guarded([&]() -> int {
         // every rank calls this the same number of times in the same order: the sequence number is implicit
-        const unsigned long long seq = ++x->seq;
+        const unsigned long long prev_seq = x->seq;
+        const unsigned long long seq = x->seq = next_exchange_seq(prev_seq);
         ExchangeArgs a{x->d_peers, x->rank, x->world, q, limit, x->max_q, x->max_k, seq,
                        (const unsigned long long *)d_local_keys, d_local_flags, (unsigned long long *)d_out_keys,
                        d_out_flags, 5000000000ull};
+        a.trace = x->ctx->profiling.load() ? x->d_trace : nullptr;
         bool fused = false;
         int rc = set->search_device(limit, q, d_queries, (unsigned long long *)d_local_keys, path, (cudaStream_t)stream,
                                     d_local_flags, &a, &fused);
         if (rc) {
-            --x->seq;  // nothing was pushed: the peers' next step still carries this number
+            x->seq = prev_seq;  // nothing was pushed: the peers' next step still carries this number
             return rc;
         }
         if (!fused) {
@@ -1123,6 +1137,16 @@ int gf_set_search_device_xchg(gf_set *set, gf_exchange *x, int limit, int q, con
     });
 }
 
+int gf_exchange_trace(gf_exchange *x, int q, uint64_t *out_ns)
+{
+    if (!x || !out_ns || q < 1 || q > x->max_q) return GF_ERR_INVALID_ARGUMENT;
+    int rc = x->ctx->bind();
+    if (rc) return rc;
+    GF_CUDA(cudaDeviceSynchronize(), GF_ERR_CUDA);
+    GF_CUDA(cudaMemcpy(out_ns, x->d_trace, sizeof(uint64_t) * 4 * q, cudaMemcpyDeviceToHost), GF_ERR_READ_CUDA_BUFFER);
+    return GF_OK;
+}
+
 int gf_exchange_destroy(gf_exchange *x)
 {
     if (!x) return GF_OK;
@@ -1131,6 +1155,7 @@ int gf_exchange_destroy(gf_exchange *x)
     for (int p = 0; p < x->world; ++p)
         if (p != x->rank && x->peers[p]) cudaIpcCloseMemHandle(x->peers[p]);
     if (x->d_peers) cudaFree(x->d_peers);
+    if (x->d_trace) cudaFree(x->d_trace);
     if (x->inbox) cudaFree(x->inbox);
     delete x;
     return GF_OK;

@@ -36,120 +36,130 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// The whole CTA (blockDim.x >= world): push the K winners `local` of query qi (shared or global memory) and the
-// certificate flag into every rank's inbox over NVLink peer memory, wait until the `world` words of this query
-// carry this step's sequence number, fold the world x K keys.  buf: kMergeBuf keys of shared memory; s_flag: one
-// shared word.  Inbox (per rank, two slots alternating with the sequence parity so a fast peer can run one step
-// ahead):  keys [2][world][max_q][max_k] u64      words [2][world][max_q] u64 = seq << 1 | uncertified-flag
+// The whole CTA (blockDim.x >= world): hand the K winners `local` of query qi (shared or global memory) and the
+// certificate flag to every rank (or to the gather root only) over NVLink peer memory, wait for everybody's, fold
+// the world x K keys.  buf: kMergeBuf keys of shared memory; s_flag: one shared word.
+//
+// Protocol: every 8-byte word that crosses the link validates ITSELF -- its upper half is the step's 32-bit sequence
+// tag, its lower half the payload (a key travels as two words: score image, slot image; the flag as one).  An
+// aligned 8-byte store is atomic, so the receiver simply polls its own inbox until a word carries this step's tag:
+// no fence between data and flag, no second hop (the fence.sys behind the remote stores alone cost ~6.8 us of a
+// 21 us exchange at 2 GPUs; measured with `trace`).  Inbox (per rank), two slots alternating with the sequence
+// parity so a fast peer can run one step ahead:
+//   keys  [2][world][max_q][max_k][2] u64      flags [2][world][max_q] u64
+// Gather mode (a.gather_root_plus1 = r + 1): only rank r receives, folds and writes out_keys / out_flag; it zeroes
+// every word it consumed, so the next step may carry the same tag (its arguments are baked into a recorded graph).
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void exchange_fold(const ExchangeArgs &a, int qi, const unsigned long long *local,
                                               unsigned int local_flag, unsigned long long *buf, unsigned int *s_flag,
                                               unsigned long long *out_keys, unsigned int *out_flag)
 {
     const int K = a.K, world = a.world;
     const int slot = (int)(a.seq & 1ull);
-    const size_t keys_per_slot = (size_t)world * a.max_q * a.max_k;
-    const size_t words_off = 2 * keys_per_slot;  // in u64 units
-    if (a.gather_root_plus1 > 0) {
-        // ---- gather to one rank: K stores + one word per query instead of world x (K + 1), one waiter
-        const int root = a.gather_root_plus1 - 1;
-        unsigned long long *rbase = reinterpret_cast<unsigned long long *>(a.peers[root]);
-        for (int j = threadIdx.x; j < K; j += blockDim.x)
-            rbase[(size_t)slot * keys_per_slot + ((size_t)a.rank * a.max_q + qi) * a.max_k + j] = local[j];
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            volatile unsigned long long *w = rbase + words_off + ((size_t)slot * world + a.rank) * a.max_q + qi;
-            *w = (a.seq << 1) | (local_flag ? 1ull : 0ull);
-        }
-        if (a.rank != root) return;
-        if (threadIdx.x == 0) *s_flag = 0u;
-        __syncthreads();
-        if ((int)threadIdx.x < world) {
-            volatile unsigned long long *w = rbase + words_off + ((size_t)slot * world + threadIdx.x) * a.max_q + qi;
-            const unsigned long long t0 = globaltimer_ns();
-            unsigned long long word;
-            unsigned int spins = 0;
-            while (((word = *w) >> 1) != a.seq) {
-                if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {
-                    atomicOr(s_flag, 0xFFFFFFFFu);
-                    break;
-                }
-            }
-            if (word & 1ull) atomicOr(s_flag, 1u);
-            *w = 0ull;  // consumed: the next step may carry the same sequence number
-        }
-        __threadfence_system();
-        __syncthreads();
-        const unsigned long long *mine = rbase + (size_t)slot * keys_per_slot;
-        const int n = world * K;
-        int np = 2;
-        while (np < n) np <<= 1;
-        for (int i = threadIdx.x; i < np; i += blockDim.x) {
-            unsigned long long v = 0ull;
-            if (i < n) {
-                const int r = i / K, j = i - r * K;
-                v = __ldcv(mine + ((size_t)r * a.max_q + qi) * a.max_k + j);
-            }
-            buf[i] = v;
-        }
-        __syncthreads();
-        block_sort_desc(buf, np);
-        for (int i = threadIdx.x; i < K; i += blockDim.x) out_keys[(size_t)qi * K + i] = buf[i];
-        if (out_flag != nullptr && threadIdx.x == 0) out_flag[qi] = *s_flag;
-        return;
-    }
-    // ---- push my K keys of this query into every inbox (mine included)
-    for (int i = threadIdx.x; i < world * K; i += blockDim.x) {
-        const int p = i / K, j = i - p * K;
+    const unsigned long long tag = (a.seq & 0xFFFFFFFFull) << 32;  // (the host never hands out a sequence number whose low word is 0)
+    const size_t keys_per_slot = (size_t)world * a.max_q * a.max_k * 2;  // u64 words
+    const size_t flags_off = 2 * keys_per_slot;
+    const int root = a.gather_root_plus1 - 1;  // -1: all to all
+    const bool gather = root >= 0;
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[qi * 4 + 0] = globaltimer_ns();
+    // ---- push: my K keys of this query (and the flag) into every receiving inbox, mine included
+    const int ntarget = gather ? 1 : world;
+    for (int i = threadIdx.x; i < ntarget * K; i += blockDim.x) {
+        const int t = i / K, j = i - t * K;
+        const int p = gather ? root : t;
+        const unsigned long long key = local[j];
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.peers[p]) + (size_t)slot * keys_per_slot +
-                                  ((size_t)a.rank * a.max_q + qi) * a.max_k + j;
-        *dst = local[j];
+                                  (((size_t)a.rank * a.max_q + qi) * a.max_k + j) * 2;
+        st_volatile_u64(dst, tag | (key >> 32));
+        st_volatile_u64(dst + 1, tag | (key & 0xFFFFFFFFull));
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < world) {
-        const unsigned long long word = (a.seq << 1) | (local_flag ? 1ull : 0ull);
-        volatile unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[threadIdx.x]) + words_off +
-                                         ((size_t)slot * world + a.rank) * a.max_q + qi;
-        *w = word;
+    if ((int)threadIdx.x < ntarget) {
+        const int p = gather ? root : (int)threadIdx.x;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[p]) + flags_off +
+                                ((size_t)slot * world + a.rank) * a.max_q + qi;
+        st_volatile_u64(w, tag | (local_flag ? 1ull : 0ull));
     }
-    // ---- wait for everybody's keys of this query
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[qi * 4 + 1] = globaltimer_ns();
+    if (gather && a.rank != root) return;
+    // ---- receive: poll my own inbox until every word of this query carries the tag
     if (threadIdx.x == 0) *s_flag = 0u;
     __syncthreads();
-    if ((int)threadIdx.x < world) {
-        volatile unsigned long long *w = reinterpret_cast<unsigned long long *>(a.peers[a.rank]) + words_off +
-                                         ((size_t)slot * world + threadIdx.x) * a.max_q + qi;
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned long long word;
-        unsigned int spins = 0;
-        while (((word = *w) >> 1) != a.seq) {
-            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {  // a peer died: do not hang the GPU
-                atomicOr(s_flag, 0xFFFFFFFFu);
-                break;
-            }
-        }
-        if (word & 1ull) atomicOr(s_flag, 1u);
-    }
-    __threadfence_system();
-    __syncthreads();
-    // ---- fold world x K keys (world * K <= kMergeBuf, checked by the host)
-    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(a.peers[a.rank]) +
-                                     (size_t)slot * keys_per_slot;
+    unsigned long long *mine = reinterpret_cast<unsigned long long *>(a.peers[a.rank]);
     const int n = world * K;
     int np = 2;
     while (np < n) np <<= 1;
+    const unsigned long long t0 = globaltimer_ns();
     for (int i = threadIdx.x; i < np; i += blockDim.x) {
         unsigned long long v = 0ull;
         if (i < n) {
             const int r = i / K, j = i - r * K;
-            v = __ldcv(mine + ((size_t)r * a.max_q + qi) * a.max_k + j);
+            unsigned long long *src = mine + (size_t)slot * keys_per_slot + (((size_t)r * a.max_q + qi) * a.max_k + j) * 2;
+            unsigned long long w0, w1;
+            unsigned int spins = 0;
+            for (;;) {
+                w0 = ld_volatile_u64(src);
+                w1 = ld_volatile_u64(src + 1);
+                if ((w0 & 0xFFFFFFFF00000000ull) == tag && (w1 & 0xFFFFFFFF00000000ull) == tag) break;
+                if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {  // a peer died: do not hang the GPU
+                    atomicOr(s_flag, 0xFFFFFFFFu);
+                    w0 = w1 = 0ull;
+                    break;
+                }
+            }
+            v = (w0 << 32) | (w1 & 0xFFFFFFFFull);
+            if (gather) {  // consumed
+                st_volatile_u64(src, 0ull);
+                st_volatile_u64(src + 1, 0ull);
+            }
         }
         buf[i] = v;
     }
+    if ((int)threadIdx.x < world) {
+        unsigned long long *w = mine + flags_off + ((size_t)slot * world + threadIdx.x) * a.max_q + qi;
+        unsigned long long word;
+        unsigned int spins = 0;
+        for (;;) {
+            word = ld_volatile_u64(w);
+            if ((word & 0xFFFFFFFF00000000ull) == tag) break;
+            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > a.timeout_ns) {
+                atomicOr(s_flag, 0xFFFFFFFFu);
+                word = 0ull;
+                break;
+            }
+        }
+        if (word & 1ull) atomicOr(s_flag, 1u);
+        if (gather) st_volatile_u64(w, 0ull);
+    }
     __syncthreads();
-    block_sort_desc(buf, np);
-    for (int i = threadIdx.x; i < K; i += blockDim.x) out_keys[(size_t)qi * K + i] = buf[i];
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[qi * 4 + 2] = globaltimer_ns();
+    // ---- fold world x K keys (world * K <= kMergeBuf, checked by the host)
+    if (n <= 256 && np <= (int)blockDim.x) {
+        // few keys: every key counts the keys above it (keys are unique: one per slot) -- one barrier instead of the
+        // ~15 of a bitonic sort
+        const int i = threadIdx.x;
+        const unsigned long long my = i < n ? buf[i] : 0ull;
+        int rk = 0;
+        if (my != 0ull)
+            for (int j = 0; j < n; ++j) rk += buf[j] > my ? 1 : 0;
+        const int nz = __syncthreads_count(my != 0ull);
+        if (my != 0ull && rk < K) out_keys[(size_t)qi * K + rk] = my;
+        if (i < K && i >= nz) out_keys[(size_t)qi * K + i] = 0ull;
+    } else {
+        block_sort_desc(buf, np);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) out_keys[(size_t)qi * K + i] = buf[i];
+    }
     if (out_flag != nullptr && threadIdx.x == 0) out_flag[qi] = *s_flag;
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[qi * 4 + 3] = globaltimer_ns();
 }
 
 }  // namespace gf

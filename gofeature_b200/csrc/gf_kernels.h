@@ -62,11 +62,12 @@ cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, 
                          const int *d_out_map = nullptr);
 
 // Peer exchange + merge over NVLink peer memory (gf_merge.cu): d_peers = world inbox base pointers, inbox
-// layout keys [2][world][max_q][max_k] u64 then words [2][world][max_q] u64; world * K <= 2048.
+// layout keys [2][world][max_q][max_k][2] u64 (a key travels as two self-validating words, gf_exchange.cuh) then flag
+// words [2][world][max_q] u64; world * K <= 2048.
 constexpr int kExchangeMaxKeys = 2048;
 inline size_t exchange_inbox_bytes(int world, int max_q, int max_k)
 {
-    return ((size_t)2 * world * max_q * max_k + (size_t)2 * world * max_q) * 8;
+    return ((size_t)4 * world * max_q * max_k + (size_t)2 * world * max_q) * 8;
 }
 // arguments of the cross-rank step (exchange_fold, gf_exchange.cuh)
 struct ExchangeArgs {
@@ -84,6 +85,9 @@ struct ExchangeArgs {
     // step (the caller does not start one before r has finished: gf_context_create_multi's in-process sets,
     // whose steps are recorded CUDA graphs with these arguments baked in).
     int gather_root_plus1;
+    // optional [max_q][4] device words: globaltimer (ns) when query qi's CTA entered the exchange, had pushed and
+    // published, had seen every rank's word, had folded -- the breakdown bench.py reports as `exchange_trace`
+    unsigned long long *trace;
 };
 cudaError_t exchange_merge_launch(void *const *d_peers, int rank, int world, int q, int K, int max_q, int max_k,
                                   unsigned long long seq, const unsigned long long *d_local_keys,

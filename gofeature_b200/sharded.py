@@ -210,6 +210,15 @@ class ShardedSet:
         elif h:
             L.gf_exchange_destroy(h)
 
+    def exchange_trace(self, q):
+        """[q, 4] device-clock ns of the last fused search's cross-rank step on THIS rank (entered, published, all
+        ranks seen, folded); needs ctx.SetProfiling(True) while it ran.  None without the peer exchange."""
+        if self._xchg is None:
+            return None
+        out = np.zeros((q, 4), dtype=np.uint64)
+        api._check(api.lib().gf_exchange_trace(self._xchg, q, out.ctypes.data))
+        return out
+
     def close_exchange(self):
         if self._xchg is not None:
             api.lib().gf_exchange_destroy(self._xchg)

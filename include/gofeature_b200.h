@@ -321,6 +321,10 @@ GF_API int gf_exchange_merge_device(gf_exchange *x, int q, int limit, const uint
 GF_API int gf_set_search_device_xchg(gf_set *set, gf_exchange *x, int limit, int q, const float *d_queries,
                                      uint64_t *d_local_keys, uint32_t *d_local_flags, uint64_t *d_out_keys,
                                      uint32_t *d_out_flags, int path, void *stream);
+/* Where the cross-rank step of the LAST fused search spent its time (needs gf_context_set_profiling on while it
+ * ran; blocking): out_ns[4 * i .. 4 * i + 3] = device clock (ns) when query i's CTA entered the exchange, had pushed
+ * and published its winners, had seen every rank's, had folded them. */
+GF_API int gf_exchange_trace(gf_exchange *x, int q, uint64_t *out_ns);
 GF_API int gf_exchange_destroy(gf_exchange *x);
 
 /* Merge `lists` candidate lists (each [q][limit], e.g. the all-gathered per-rank winners)
