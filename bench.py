@@ -486,7 +486,15 @@ def run_ours(args, rank, world, local_rank):
     probe_ms = e2e_run(args.steps, 0, [])
     n_e2e = int(min(20000, max(args.steps, np.ceil(MIN_TIMED_S * 1e3 / max(probe_ms, 1e-3) * args.steps))))
     lat = []
+    ctx.ResetStats()
     e2e_ms = e2e_run(n_e2e, args.steps, lat)
+    hs = ctx.Stats()
+    host_breakdown = None
+    if hs["host_calls"]:
+        c = float(hs["host_calls"])
+        host_breakdown = {"stage_queries_us": hs["host_stage_ns"] / c / 1e3, "enqueue_us": hs["host_launch_ns"] / c / 1e3,
+                          "wait_for_device_us": hs["host_wait_ns"] / c / 1e3, "resolve_ids_us": hs["host_resolve_ns"] / c / 1e3,
+                          "calls": int(c), "note": "inside gf_set_search; the rest of a call is the caller's own (ctypes) overhead"}
 
     line_extra = {}
     # ---- N > 1: the same N x 1 M-row set INSIDE the library (one process, N devices, gf_context_create_multi):
@@ -534,6 +542,8 @@ def run_ours(args, rank, world, local_rank):
     cache.Close()
     cache = None
 
+    if world == 1 and not args.quick:
+        line_extra["clustered"] = leg_clustered(H, api, ctx, args.rows_per_gpu, Q, K, shadow)
     # ---- config 4: 12.5 M rows per GPU, 64 queries top-10 (8 GPUs: the 100 M-row set); strong scaling: 8 M rows
     if not args.quick:
         line_extra["config4_shard"] = leg_rows(H, api, ShardedSet, ctx, args.config4_rows_per_gpu * world, 64, 10,
@@ -603,7 +613,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_user * world, "unit": UNIT, "h2d_bytes_per_step": Q * DIMS * 4,
                 "d2h_bytes_per_step": Q * K * 8, "qps_user": e2e_user, "ms_per_step": e2e_ms / n_e2e, "calls": n_e2e,
                 "p50_ms": lat_ms[len(lat_ms) // 2], "p99_ms": lat_ms[min(len(lat_ms) - 1, int(len(lat_ms) * 0.99))],
-                "call": "one gf_set_search(q=%d) per step" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q},
+                "call": "one gf_set_search(q=%d) per step" % Q if world == 1 else "ShardedSet.search_keys(q=%d)" % Q,
+                "host_breakdown": host_breakdown},
         "units": "a query counts once per %d-row shard it scans: value = qps_user x n_gpus (weak scaling)" % args.rows_per_gpu,
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / float(max(reps * args.steps, 1)),
         "tensor_passes": stats["tensor_passes"],
@@ -640,7 +651,7 @@ def run_ours(args, rank, world, local_rank):
                        "p99_ms": multi["p99_ms"],
                        "call": "one process, gf_context_create_multi(%d devices): gf_set_search(q=%d) per step, host "
                                "buffers in, ids out" % (world, Q),
-                       "parity_check": multi["parity_check"]}
+                       "host_breakdown": multi["host_breakdown"], "parity_check": multi["parity_check"]}
     elif multi is not None:
         line["e2e_multi_error"] = multi
     if demo and "qps" in demo:
@@ -758,14 +769,102 @@ def leg_multi(api, world, rows_total, shadow, pool, ref_keys, Q, K, steps):
         lat.append(time.perf_counter() - a)
     wall = time.perf_counter() - t0
     stats = mctx.Stats()
+    c = float(max(stats["host_calls"], 1))
+    hb = {"stage_queries_us": stats["host_stage_ns"] / c / 1e3, "enqueue_us": stats["host_launch_ns"] / c / 1e3,
+          "wait_for_device_us": stats["host_wait_ns"] / c / 1e3, "resolve_ids_us": stats["host_resolve_ns"] / c / 1e3,
+          "calls": int(c)}
     cache.Close()
     mctx.Close()
     l = sorted(x * 1e3 for x in lat)
     return {"qps_user": Q * n / wall, "ms_per_step": wall / n * 1e3, "calls": n, "p50_ms": l[len(l) // 2],
             "p99_ms": l[min(len(l) - 1, int(len(l) * 0.99))], "uncertified_queries": stats["uncertified_queries"],
+            "host_breakdown": hb,
             "parity_check": {"queries": len(ref_keys) * Q, "mismatches": mism,
                              "against": "the keys the one-process-per-GPU path (NCCL harness, in-kernel exchange) merged "
                                         "for the same batches; ids must be f<slot>"}}
+
+
+def _mix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def cluster_centre(seed, centre, dims):
+    """centre vector of a clustered synthetic set (the hash gf_set_add_synthetic_ex uses, restated in numpy)."""
+    with np.errstate(over="ignore"):
+        cnt = np.uint64(centre) * np.uint64(dims) + np.arange(dims, dtype=np.uint64)
+        h = _mix64(np.uint64(seed ^ 0xC3A7E25) ^ _mix64(cnt))
+    return (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 8388608.0) - np.float32(1.0)
+
+
+def leg_clustered(H, api, ctx, rows, Q, K, shadow):
+    """The headline step on CLUSTERED data: 10 000 centres x ~100 members at cosine ~0.975 to their centre, 1 % exact
+    duplicates, queries near centres (about 100 rows score within 0.01 of the winner).  How many queries does the
+    certificate refuse, and what does the step cost?"""
+    torch = H.torch
+    seed, centres, spread, dup = 777, max(1, rows // 100), 0.228, 10000
+    cache = api.NewCache(ctx, (rows + CAP - 1) // CAP + 1, BLOCK_SIZE, shadow=shadow)
+    cache.NewSet("clustered", DIMS, 4, max(Q, 16))
+    st = cache.GetSet("clustered")
+    st.AddSynthetic(rows, seed, 0, True, "f", centres, spread, dup)
+    rng = np.random.default_rng(5)
+    npool = 32
+    pool = np.empty((npool, Q, DIMS), dtype=np.float32)
+    for b in range(npool):
+        for i in range(Q):
+            v = cluster_centre(seed, int(rng.integers(0, centres)), DIMS) + 0.1 * rng.uniform(-1, 1, DIMS).astype(np.float32)
+            pool[b, i] = v / np.linalg.norm(v)
+    dpool = torch.from_numpy(pool).cuda()
+    keys = torch.zeros((Q, K), dtype=torch.int64, device="cuda")
+    flags = torch.zeros((Q,), dtype=torch.int32, device="cuda")
+
+    def step(i, path=0):
+        st.SearchDeviceEx(K, Q, dpool[i % npool].data_ptr(), keys.data_ptr(), flags.data_ptr(), path, None)
+
+    for i in range(5):
+        step(i)
+    f0 = st.DeviceCounters()[0]
+    ms, _, _ = H.timed_reps(step, 20, 0.5)
+    n_steps = 20 * (len(ms) + 1)
+    refused = st.DeviceCounters()[0] - f0
+    step_ms = float(np.median(ms)) / 20
+    # correctness + spread of the winners, batch by batch, against the exact scan on the same rows
+    mism = flagged = 0
+    gaps = []
+    for b in range(npool):
+        step(b)
+        k0, fl = keys.clone(), flags.clone()
+        step(b, 1)
+        torch.cuda.synchronize()
+        bad = (k0 != keys).any(dim=1)
+        flagged += int((fl != 0).sum().item())
+        mism += int((bad & (fl == 0)).sum().item())
+        hk = keys.cpu().numpy().view(np.uint64)
+        gaps += [float(api.key_score(r[0]) - api.key_score(r[K - 1])) for r in hk]
+    # through the host call: refused queries are re-run by the exact scan inside
+    ctx.ResetStats()
+    lean = api.lib()
+    handle = ctypes.c_void_p()
+    t0 = time.perf_counter()
+    n = 400
+    for i in range(n):
+        a = pool[i % npool]
+        lean.gf_set_search(st._h, -2.0, K, Q, a.ctypes.data, a.nbytes, ctypes.byref(handle))
+        lean.gf_result_free(handle)
+    e2e_ms = (time.perf_counter() - t0) / n * 1e3
+    hs = ctx.Stats()
+    cache.Close()
+    return {"workload": "%d x %d-d rows in %d clusters (members at cosine ~0.975 to their centre), 1%% exact duplicates; "
+                        "%d queries near centres, top-%d per step" % (rows, DIMS, centres, Q, K),
+            "median_score_gap_best_to_kth": float(np.median(gaps)),
+            "ms_per_step": step_ms, "value": Q / (step_ms * 1e-3), "unit": UNIT,
+            "uncertified_rate": refused / float(max(n_steps * Q, 1)), "queries_timed": n_steps * Q,
+            "e2e_ms_per_step": e2e_ms, "e2e_value": Q / (e2e_ms * 1e-3),
+            "e2e_uncertified_rate": hs["uncertified_queries"] / float(n * Q),
+            "parity_check": {"queries": npool * Q, "mismatches": mism, "flagged_queries": flagged,
+                             "against": "exact float32 scan kernel (path 1)"}}
 
 
 def leg_config3(H, ctx, sset, rows_local, shadow_eb, PK):

@@ -24,7 +24,9 @@ class gf_stats(ctypes.Structure):
     _fields_ = [(n, c_u64) for n in ("searches", "scan_launches", "gemm_launches", "merge_launches",
                                      "other_launches", "rows_scanned", "quirk_fallbacks", "coalesced_batches",
                                      "h2d_bytes", "d2h_bytes", "scan_kernel_ns", "scan_kernel_timed",
-                                     "tensor_passes", "uncertified_queries", "gemm_kernel_ns", "gemm_kernel_timed")]
+                                     "tensor_passes", "uncertified_queries", "gemm_kernel_ns", "gemm_kernel_timed",
+                                     "host_stage_ns", "host_launch_ns", "host_wait_ns", "host_resolve_ns",
+                                     "host_calls")]
 
 
 # name -> (restype, argtypes); every symbol include/gofeature_b200.h declares
@@ -104,6 +106,7 @@ SIGNATURES = {
     "gf_merge_keys_device": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "gf_set_resolve_keys": (c_int, [c_vp, c_f32, c_int, c_int, c_vp, P(c_vp)]),
     "gf_set_add_synthetic": (c_int, [c_vp, c_i64, c_u64, c_i64, c_int, c_cp]),
+    "gf_set_add_synthetic_ex": (c_int, [c_vp, c_i64, c_u64, c_i64, c_int, c_cp, c_u64, c_f32, c_u32]),
     "gf_context_stats": (c_int, [c_vp, P(gf_stats)]),
     "gf_context_reset_stats": (c_int, [c_vp]),
     "gf_context_set_profiling": (c_int, [c_vp, c_int]),

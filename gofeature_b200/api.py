@@ -401,7 +401,11 @@ class Set:
                                    ctypes.byref(h)))
         return _take_result(h)
 
-    def AddSynthetic(self, n, seed, first_ordinal=0, normalize=True, id_prefix="f"):
+    def AddSynthetic(self, n, seed, first_ordinal=0, normalize=True, id_prefix="f", centres=0, spread=0.0, dup_ppm=0):
+        if centres or dup_ppm:
+            _check(lib().gf_set_add_synthetic_ex(self._h, n, seed, first_ordinal, 1 if normalize else 0,
+                                                 id_prefix.encode(), centres, spread, dup_ppm))
+            return
         _check(lib().gf_set_add_synthetic(self._h, n, seed, first_ordinal, 1 if normalize else 0,
                                           id_prefix.encode()))
 

@@ -290,6 +290,11 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
         out->uncertified_queries += p.uncertified_queries;
         out->h2d_bytes += p.h2d_bytes;
         out->d2h_bytes += p.d2h_bytes;
+        out->host_stage_ns = p.host_stage_ns;  // (the parent's call, not the shards')
+        out->host_launch_ns = p.host_launch_ns;
+        out->host_wait_ns = p.host_wait_ns;
+        out->host_resolve_ns = p.host_resolve_ns;
+        out->host_calls = p.host_calls;
         return GF_OK;
     }
     const_cast<gf_context *>(ctx)->prof_collect();
@@ -300,6 +305,11 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
     out->uncertified_queries = s.uncertified_queries;
     out->gemm_kernel_ns = s.gemm_kernel_ns;
     out->gemm_kernel_timed = s.gemm_kernel_timed;
+    out->host_stage_ns = s.host_stage_ns;
+    out->host_launch_ns = s.host_launch_ns;
+    out->host_wait_ns = s.host_wait_ns;
+    out->host_resolve_ns = s.host_resolve_ns;
+    out->host_calls = s.host_calls;
     out->searches = s.searches;
     out->scan_launches = s.scan_launches;
     out->gemm_launches = s.gemm_launches;
@@ -324,6 +334,7 @@ int gf_context_reset_stats(gf_context *ctx)
     s.scan_kernel_ns = s.scan_kernel_timed = 0;
     s.tensor_passes = s.uncertified_queries = 0;
     s.gemm_kernel_ns = s.gemm_kernel_timed = 0;
+    s.host_stage_ns = s.host_launch_ns = s.host_wait_ns = s.host_resolve_ns = s.host_calls = 0;
     return GF_OK;
 }
 
@@ -1194,6 +1205,19 @@ int gf_set_add_synthetic(gf_set *set, int64_t n, uint64_t seed, int64_t first_or
     if (!set || n < 0 || first_ordinal < 0) return GF_ERR_INVALID_ARGUMENT;
     return guarded([&]() -> int {
         return set->add_synthetic(n, seed, first_ordinal, normalize, id_prefix ? id_prefix : "f");
+    });
+}
+
+int gf_set_add_synthetic_ex(gf_set *set, int64_t n, uint64_t seed, int64_t first_ordinal, int normalize,
+                            const char *id_prefix, uint64_t centres, float spread, uint32_t dup_ppm)
+{
+    if (!set || n < 0 || first_ordinal < 0 || dup_ppm > 1000000u || !(spread >= 0.f)) return GF_ERR_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        SynthSpec sp(seed);
+        sp.centres = centres;
+        sp.spread = spread;
+        sp.dup_ppm = dup_ppm;
+        return set->add_synthetic(n, sp, first_ordinal, normalize, id_prefix ? id_prefix : "f");
     });
 }
 

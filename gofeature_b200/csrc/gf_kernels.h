@@ -226,8 +226,20 @@ cudaError_t zero_rows_launch(float *d_slab, void *d_shadow, int shadow_eb, const
 cudaError_t gather_rows_launch(const float *d_src, const int *d_idx, int n, int dims, float *d_dst,
                                cudaStream_t stream);
 
-// Synthetic rows, bit-identical to oracle/gf_oracle.c gf_oracle_synth_rows.
-cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, uint64_t seed, int64_t first_row, int normalize,
-                              cudaStream_t stream);
+// What a synthetic row is made of (bit-identical to oracle/gf_oracle.c gf_oracle_synth_rows / _synth_rows_ex):
+//   centres == 0  row(o)[e] = U(-1,1) of a counter hash (search_test.go:65), the uniform recipe
+//   centres  > 0  row(o) = centre(c(o)) + spread * U(-1,1)^dims, c(o) a hash of the ordinal: `centres` clusters whose
+//                 members are scattered over the set (what a face-feature index holds: many near neighbours)
+//   dup_ppm       that many rows per million are exact copies of an EARLIER ordinal's row
+// then per-row L2 normalisation (normalize != 0).
+struct SynthSpec {
+    uint64_t seed;
+    uint64_t centres = 0;
+    float spread = 0.f;
+    uint32_t dup_ppm = 0;
+    SynthSpec(uint64_t s = 0) : seed(s) {}
+};
+cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, const SynthSpec &spec, int64_t first_row,
+                              int normalize, cudaStream_t stream);
 
 }  // namespace gf

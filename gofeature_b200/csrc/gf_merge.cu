@@ -112,15 +112,33 @@ __device__ __forceinline__ float uniform_pm1(unsigned long long seed, unsigned l
     return __fadd_rn(__fmul_rn((float)m, 1.0f / 8388608.0f), -1.0f);
 }
 
+// the source ordinal of row `ord` (itself, or an earlier row it duplicates) and its value at element e
+__device__ __forceinline__ unsigned long long synth_source(const SynthSpec &sp, unsigned long long ord)
+{
+    if (sp.dup_ppm != 0u && ord > 0ull &&
+        splitmix64(sp.seed ^ 0xD0B1E5ull ^ splitmix64(ord)) % 1000000ull < (unsigned long long)sp.dup_ppm)
+        return splitmix64(sp.seed ^ 0x5EED0FD0ull ^ splitmix64(ord)) % ord;
+    return ord;
+}
+__device__ __forceinline__ float synth_value(const SynthSpec &sp, unsigned long long src, unsigned long long centre,
+                                             int dims, int e)
+{
+    const float nv = uniform_pm1(sp.seed, src * (unsigned long long)dims + (unsigned long long)e);
+    if (sp.centres == 0ull) return nv;
+    const float cv = uniform_pm1(sp.seed ^ 0xC3A7E25ull, centre * (unsigned long long)dims + (unsigned long long)e);
+    return __fmaf_rn(sp.spread, nv, cv);
+}
+
 // one warp per row; element e handled by lane (e%128)/4, partial sum e%4 (canonical order)
 __global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ rows, long long nrows, int dims,
-                                                         unsigned long long seed, long long first_row, int normalize)
+                                                         const SynthSpec sp, long long first_row, int normalize)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = warp; r < nrows; r += nwarps) {
-        const unsigned long long c0 = (unsigned long long)(first_row + r) * (unsigned long long)dims;
+        const unsigned long long src = synth_source(sp, (unsigned long long)(first_row + r));
+        const unsigned long long centre = sp.centres ? splitmix64(sp.seed ^ 0xC1A55E5ull ^ splitmix64(src)) % sp.centres : 0ull;
         float inv_ok = 1.0f, nrm = 1.0f;
         if (normalize) {
             float p[4] = {0.f, 0.f, 0.f, 0.f};
@@ -129,7 +147,7 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ row
                 for (int c = 0; c < 4; ++c) {
                     int e = j + 4 * lane + c;
                     if (e < dims) {
-                        float v = uniform_pm1(seed, c0 + e);
+                        float v = synth_value(sp, src, centre, dims, e);
                         p[c] = __fmaf_rn(v, v, p[c]);
                     }
                 }
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ row
             for (int c = 0; c < 4; ++c) {
                 int e = j + 4 * lane + c;
                 if (e < dims) {
-                    float v = uniform_pm1(seed, c0 + e);
+                    float v = synth_value(sp, src, centre, dims, e);
                     if (normalize) v = (inv_ok == 0.0f) ? 0.0f : __fdiv_rn(v, nrm);
                     out[e] = v;
                 }
@@ -443,14 +461,14 @@ cudaError_t merge_launch(const unsigned long long *d_in, int groups, int lists, 
                         d_out_map);
 }
 
-cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, uint64_t seed, int64_t first_row, int normalize,
-                              cudaStream_t stream)
+cudaError_t synth_fill_launch(float *d_rows, int64_t nrows, int dims, const SynthSpec &spec, int64_t first_row,
+                              int normalize, cudaStream_t stream)
 {
     if (nrows <= 0) return cudaSuccess;
     long long warps = nrows;
     long long blocks = (warps + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    synth_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, nrows, dims, seed, first_row, normalize);
+    synth_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows, nrows, dims, spec, first_row, normalize);
     return cudaGetLastError();
 }
 

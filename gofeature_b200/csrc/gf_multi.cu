@@ -13,6 +13,7 @@
 // first-block-in-order rule (set.go:163-193), the per-block tombstone rule (block.go:236-243) through the shards'
 // own Search when a tombstone reaches the winners.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -190,7 +191,7 @@ int Set::multi_add(int64_t n, const uint8_t *values, const std::vector<std::stri
     return GF_OK;
 }
 
-int Set::multi_add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix)
+int Set::multi_add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix)
 {
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
@@ -468,6 +469,7 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
         GF_CUDA(cudaHostAlloc((void **)&x->h_pin, want, cudaHostAllocPortable), GF_ERR_ALLOCATE_GPU_BUFFER);
         x->h_cap = want;
     }
+    const auto t_a = std::chrono::steady_clock::now();
     float *h_q = (float *)x->h_pin;
     unsigned long long *h_out = (unsigned long long *)(x->h_pin + align_up(qbytes, 256));
     unsigned int *h_flags = (unsigned int *)((uint8_t *)h_out + keyb);
@@ -486,6 +488,7 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
     std::vector<ExchangeArgs> xa((size_t)G);
     const int root = 0;
     bool launched_any = false;
+    const auto t_b = std::chrono::steady_clock::now();
     auto fail = [&](int code) {
         if (launched_any) x->dirty = true;
         return code;
@@ -535,6 +538,7 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
             sh->ctx->stats.merge_launches++;
         }
     }
+    const auto t_c = std::chrono::steady_clock::now();
     shards[root]->ctx->bind();
     cudaError_t we = wait_stream(x->ws[root]->stream);
     if (we != cudaSuccess) return fail(cuda_fail(we, "multi-device search", GF_ERR_READ_CUDA_BUFFER));
@@ -543,6 +547,11 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
         cudaError_t e = cudaStreamSynchronize(x->ws[d]->stream);
         if (e != cudaSuccess) return fail(cuda_fail(e, "multi-device search", GF_ERR_READ_CUDA_BUFFER));
     }
+    const auto t_d = std::chrono::steady_clock::now();
+    ctx->stats.host_stage_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_b - t_a).count();
+    ctx->stats.host_launch_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_c - t_b).count();
+    ctx->stats.host_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_d - t_c).count();
+    ctx->stats.host_calls++;
     ctx->stats.d2h_bytes += (size_t)q * kb * 8 + (size_t)q * 4;
     // queries some shard could not certify: every shard re-runs JUST those through its exact scan, the host folds
     bool any = false;
@@ -558,31 +567,32 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
         for (int i = 0; i < q; ++i)
             if (h_flags[i]) bad.push_back(i);
         ctx->stats.uncertified_queries += bad.size();
+        const int nb = (int)bad.size();
         for (int d = 0; d < G; ++d) {
             Set *sh = shards[d];
             Workspace *cws = x->ws[d];
             rc = sh->ctx->bind();
             if (rc) return rc;
-            GF_CUDA(cudaMemcpyAsync(d_q[d], h_q, qbytes, cudaMemcpyHostToDevice, cws->stream), GF_ERR_WRITE_INPUT_BUFFER);
-            for (int i : bad) {
-                rc = sh->topk_scan(cws, cws->stream, d_q[d] + (size_t)i * dims, 1, dims, 1, kb, false, nullptr,
-                                   d_loc[d] + (size_t)i * kb);
-                if (rc) return rc;
-                GF_CUDA(cudaMemcpyAsync(h_shard + (size_t)d * q * kb + (size_t)i * kb, d_loc[d] + (size_t)i * kb,
-                                        (size_t)kb * 8, cudaMemcpyDeviceToHost, cws->stream),
-                        GF_ERR_READ_CUDA_BUFFER);
-            }
+            for (int j = 0; j < nb; ++j)  // the refused queries, packed: one compact batch per shard
+                GF_CUDA(cudaMemcpyAsync(d_q[d] + (size_t)j * dims, h_q + (size_t)bad[j] * dims, (size_t)dims * 4,
+                                        cudaMemcpyHostToDevice, cws->stream),
+                        GF_ERR_WRITE_INPUT_BUFFER);
+            rc = sh->topk_scan(cws, cws->stream, d_q[d], nb, dims, 1, kb, false, nullptr, d_loc[d]);
+            if (rc) return rc;
+            GF_CUDA(cudaMemcpyAsync(h_shard + (size_t)d * q * kb, d_loc[d], (size_t)nb * kb * 8, cudaMemcpyDeviceToHost,
+                                    cws->stream),
+                    GF_ERR_READ_CUDA_BUFFER);
         }
         for (int d = 0; d < G; ++d) {
             shards[d]->ctx->bind();
             GF_CUDA(cudaStreamSynchronize(x->ws[d]->stream), GF_ERR_READ_CUDA_BUFFER);
         }
         std::vector<unsigned long long> all((size_t)G * kb);
-        for (int i : bad) {
+        for (int j = 0; j < nb; ++j) {
             for (int d = 0; d < G; ++d)
-                memcpy(all.data() + (size_t)d * kb, h_shard + (size_t)d * q * kb + (size_t)i * kb, (size_t)kb * 8);
+                memcpy(all.data() + (size_t)d * kb, h_shard + (size_t)d * q * kb + (size_t)j * kb, (size_t)kb * 8);
             std::sort(all.begin(), all.end(), std::greater<unsigned long long>());
-            memcpy(h_out + (size_t)i * kb, all.data(), (size_t)kb * 8);
+            memcpy(h_out + (size_t)bad[j] * kb, all.data(), (size_t)kb * 8);
         }
     }
     *h_keys = h_out;
@@ -614,8 +624,11 @@ int Set::multi_search_now(float threshold, int limit, int q, const uint8_t *quer
         unsigned long long *h_keys = nullptr;
         int rc = multi_direct_keys(ws, kb, q, &queries, &q, 1, &h_keys);
         bool quirk = false;
+        const auto t_r0 = std::chrono::steady_clock::now();
         if (rc == GF_OK)
             for (int i = 0; i < q && !quirk; ++i) quirk = !resolve_winners(h_keys + (size_t)i * kb, kb, threshold, res.get());
+        ctx->stats.host_resolve_ns +=
+            (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_r0).count();
         ctx->release_ws(ws);
         if (rc) return rc;
         if (!quirk) {

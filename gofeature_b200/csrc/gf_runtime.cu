@@ -358,8 +358,21 @@ std::string Block::id_at(int row) const
             auto it = over.find(row);
             if (it != over.end()) return it->second;
         }
+        long long v = (long long)(id_first + row);
+        if (v >= 0 && v < 100000000000ll) {  // "%011lld" by hand: snprintf was most of the id resolution of a search
+            char buf[11];
+            for (int i = 10; i >= 0; --i) {
+                buf[i] = (char)('0' + v % 10);
+                v /= 10;
+            }
+            std::string out;
+            out.reserve(id_prefix.size() + 11);
+            out.append(id_prefix);
+            out.append(buf, 11);
+            return out;
+        }
         char buf[32];
-        snprintf(buf, sizeof buf, "%011lld", (long long)(id_first + row));
+        snprintf(buf, sizeof buf, "%011lld", v);
         return id_prefix + buf;
     }
     return ids[row];
@@ -529,7 +542,7 @@ int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::strin
     return GF_OK;
 }
 
-int Block::insert_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix)
+int Block::insert_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix)
 {
     if (owner.empty() || precision != 4) return GF_ERR_INVALID_ARGUMENT;
     if (n > capacity() - next_index) return GF_ERR_BLOCK_IS_FULL;
@@ -959,7 +972,7 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
     return rebuild_segments();
 }
 
-int Set::add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix)
+int Set::add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix)
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (precision != 4) return GF_ERR_UNSUPPORTED;
@@ -1861,6 +1874,7 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     const size_t h_need = align_up(qbytes, 256) + align_up(out_keys * 8, 256) + align_up((size_t)q * 4, 256);
     int rc = ws->reserve(d_need, h_need);
     if (rc) return rc;
+    const auto t_a = std::chrono::steady_clock::now();
     float *d_q = (float *)ws->d_buf;
     unsigned long long *d_out = (unsigned long long *)(ws->d_buf + align_up(qbytes, 256));
     float *h_q = (float *)ws->h_buf;
@@ -1874,25 +1888,46 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     ctx->stats.h2d_bytes += qbytes;
     // The kernels read the queries from the pinned staging buffer and the winners come back in ONE copy
     // (keys + flags): three stream operations per call.
+    const auto t_b = std::chrono::steady_clock::now();
     rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags, true);
     if (rc) return rc;
+    const auto t_c = std::chrono::steady_clock::now();
     GF_CUDA(wait_stream(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+    const auto t_d = std::chrono::steady_clock::now();
+    ctx->stats.host_stage_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_b - t_a).count();
+    ctx->stats.host_launch_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_c - t_b).count();
+    ctx->stats.host_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_d - t_c).count();
+    ctx->stats.host_calls++;
     ctx->stats.d2h_bytes += out_keys * 8 + (size_t)q * 4;
-    // tensor-path queries that could neither be certified nor fixed on the device: exact scan, one by one
-    bool dq_ready = false;
-    for (int i = 0; i < q; ++i) {
-        if (!h_flags[i]) continue;
-        ctx->stats.uncertified_queries++;
-        if (!dq_ready) {
-            GF_CUDA(cudaMemcpyAsync(d_q, h_q, qbytes, cudaMemcpyHostToDevice, ws->stream), GF_ERR_WRITE_INPUT_BUFFER);
-            dq_ready = true;
-        }
-        rc = topk_scan(ws, ws->stream, d_q + (size_t)i * dims, 1, dims, 1, kb, false, nullptr, d_out + (size_t)i * kb);
+    // tensor-path queries the certificate refused: ONLY those go through the exact scan, as one compact batch
+    // (the refused query vectors are packed at the front of the device staging area; passes of scan_max_q queries)
+    std::vector<int> bad;
+    for (int i = 0; i < q; ++i)
+        if (h_flags[i]) bad.push_back(i);
+    if (!bad.empty()) {
+        ctx->stats.uncertified_queries += bad.size();
+        const int nb = (int)bad.size();
+        // d_q: [q][dims] staging; d_out: [q][kb].  Pack the refused queries into d_q[0 .. nb), results into d_out[0 .. nb)
+        for (int j = 0; j < nb; ++j)
+            GF_CUDA(cudaMemcpyAsync(d_q + (size_t)j * dims, h_q + (size_t)bad[j] * dims, (size_t)dims * 4,
+                                    cudaMemcpyHostToDevice, ws->stream),
+                    GF_ERR_WRITE_INPUT_BUFFER);
+        rc = topk_scan(ws, ws->stream, d_q, nb, dims, 1, kb, false, nullptr, d_out);
         if (rc) return rc;
-        GF_CUDA(cudaMemcpyAsync(h_out + (size_t)i * kb, d_out + (size_t)i * kb, (size_t)kb * 8, cudaMemcpyDeviceToHost,
-                                ws->stream),
-                GF_ERR_READ_CUDA_BUFFER);
-        GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+        // (h_q is free again: the winners of the re-run land there before they are scattered)
+        unsigned long long *h_fix = (unsigned long long *)h_q;
+        if ((size_t)nb * kb * 8 <= align_up(qbytes, 256)) {
+            GF_CUDA(cudaMemcpyAsync(h_fix, d_out, (size_t)nb * kb * 8, cudaMemcpyDeviceToHost, ws->stream),
+                    GF_ERR_READ_CUDA_BUFFER);
+            GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+            for (int j = 0; j < nb; ++j) memcpy(h_out + (size_t)bad[j] * kb, h_fix + (size_t)j * kb, (size_t)kb * 8);
+        } else {
+            for (int j = 0; j < nb; ++j)
+                GF_CUDA(cudaMemcpyAsync(h_out + (size_t)bad[j] * kb, d_out + (size_t)j * kb, (size_t)kb * 8,
+                                        cudaMemcpyDeviceToHost, ws->stream),
+                        GF_ERR_READ_CUDA_BUFFER);
+            GF_CUDA(cudaStreamSynchronize(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+        }
     }
     *h_keys = h_out;
     return GF_OK;
@@ -1958,7 +1993,10 @@ int Set::search_now(float threshold, int limit, int q, const uint8_t *queries, R
         rc = direct_keys(ws, kb_direct, q, &queries, &q, 1, &h_keys);
         if (rc) return rc;
         bool quirk = false;
+        const auto t_r0 = std::chrono::steady_clock::now();
         for (int i = 0; i < q && !quirk; ++i) quirk = !resolve_winners(h_keys + (size_t)i * kb_direct, kb_direct, threshold, res.get());
+        ctx->stats.host_resolve_ns +=
+            (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_r0).count();
         if (!quirk) {
             *out = res.release();
             return GF_OK;

@@ -64,7 +64,8 @@ class RWLock {
 struct Stats {
     std::atomic<uint64_t> searches{0}, scan_launches{0}, gemm_launches{0}, merge_launches{0}, other_launches{0},
         rows_scanned{0}, quirk_fallbacks{0}, coalesced_batches{0}, h2d_bytes{0}, d2h_bytes{0}, scan_kernel_ns{0},
-        scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0}, gemm_kernel_ns{0}, gemm_kernel_timed{0};
+        scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0}, gemm_kernel_ns{0}, gemm_kernel_timed{0},
+        host_stage_ns{0}, host_launch_ns{0}, host_wait_ns{0}, host_resolve_ns{0}, host_calls{0};
 };
 
 // per-search scratch: a stream, device and pinned arenas
@@ -235,7 +236,7 @@ struct gf_block {
     int release();
     // values: n rows of dims*precision bytes; ids[i] non-empty
     int insert(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
-    int insert_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
+    int insert_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     // tombstone the rows; zero them on the device (no stream sync) or, with zero_later, only report their element
     // offsets in the slab so that the caller zeroes the whole Delete with one kernel
@@ -331,7 +332,7 @@ struct gf_set {
     bool is_multi() const { return !shards.empty(); }
     void multi_refresh();  // scanned_rows / version after a mutation
     int multi_add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
-    int multi_add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
+    int multi_add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int multi_remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     int multi_update(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     int multi_read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<uint8_t> &found);
@@ -354,7 +355,7 @@ struct gf_set {
     }
     int rebuild_segments();  // caller holds the exclusive lock
     int add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
-    int add_synthetic(int64_t n, uint64_t seed, int64_t first_ordinal, int normalize, const std::string &prefix);
+    int add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     int update(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     int read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<uint8_t> &found);

@@ -176,6 +176,7 @@ class ShardedSet:
         self.total_rows = 0
         self._bufs = {}
         self._xchg = None
+        self.refused_queries = 0   # queries some rank's certificate refused (re-run through the exact scan)
         if world > 1 and os.environ.get("GF_NO_P2P") is None:
             self._connect_exchange()
 
@@ -232,10 +233,10 @@ class ShardedSet:
                 self.local.AddArray(values[a:b], ids[a:b])
         self.total_rows += len(ids)
 
-    def AddSynthetic(self, n, seed, normalize=True, id_prefix="f"):
+    def AddSynthetic(self, n, seed, normalize=True, id_prefix="f", centres=0, spread=0.0, dup_ppm=0):
         for r, a, b in split_rows(self.total_rows, n, self.cap, self.world):
             if r == self.rank:
-                self.local.AddSynthetic(b - a, seed, self.total_rows + a, normalize, id_prefix)
+                self.local.AddSynthetic(b - a, seed, self.total_rows + a, normalize, id_prefix, centres, spread, dup_ppm)
         self.total_rows += n
 
     def Delete(self, *ids):
@@ -319,11 +320,18 @@ class ShardedSet:
         if hf.any():
             if (hf == -1).any():
                 raise RuntimeError("gofeature_b200: a peer rank did not reach the exchange within 5 s")
-            # some rank could not certify a query on its tensor path (every rank sees the same flags):
-            # run the batch again through the exact scan kernel
-            merged = self.search_device(limit, q, t["dq"], path=1)
-            t["hk"].copy_(merged, non_blocking=True)
+            # some rank could not certify a query on its tensor path (every rank sees the same flags): ONLY those
+            # queries go through the exact scan kernel again, as one compact batch on every rank
+            bad = np.nonzero(hf)[0]
+            self.refused_queries += len(bad)
+            out = t["hk"].numpy().view(np.uint64).copy()
+            sub = t["dq"][torch.from_numpy(bad).to(t["dq"].device)].contiguous()
+            t2 = self._tensors(len(bad), limit)
+            merged = self.search_device(limit, len(bad), sub, path=1)
+            t2["hk"].copy_(merged, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            out[bad] = t2["hk"].numpy().view(np.uint64)
+            return out
         return t["hk"].numpy().view(np.uint64).copy()
 
     def Search(self, threshold, limit, queries):

@@ -342,6 +342,14 @@ GF_API int gf_set_resolve_keys(gf_set *set, float threshold, int limit, int q, c
 GF_API int gf_set_add_synthetic(gf_set *set, int64_t n, uint64_t seed, int64_t first_ordinal, int normalize,
                                 const char *id_prefix);
 
+/* gf_set_add_synthetic with structure (what a face-feature index holds: many near neighbours and re-enrolled
+ * duplicates): centres > 0 makes row(o) = centre(c(o)) + spread * U(-1,1)^dims, the cluster c(o) a hash of the ordinal
+ * (members are scattered over the set); dup_ppm rows per million are exact copies of an earlier ordinal's row.
+ * spread 0.228 gives members at cosine ~0.975 to their centre (~0.95 to each other) at 512-d.  Bit-identical to
+ * oracle/gf_oracle.c gf_oracle_synth_rows_ex. */
+GF_API int gf_set_add_synthetic_ex(gf_set *set, int64_t n, uint64_t seed, int64_t first_ordinal, int normalize,
+                                   const char *id_prefix, uint64_t centres, float spread, uint32_t dup_ppm);
+
 /* counters for the bench harness */
 typedef struct gf_stats {
     uint64_t searches;          /* gf_set_search + gf_set_search_device calls */
@@ -360,6 +368,13 @@ typedef struct gf_stats {
     uint64_t uncertified_queries; /* tensor-path queries the host API re-ran through the exact scan */
     uint64_t gemm_kernel_ns;    /* CUDA-event time of the timed tcgen05 COLLECT launches (profiling on) */
     uint64_t gemm_kernel_timed;
+    /* where the host-buffer search call (tensor path, one band) spends its wall time, summed over host_calls calls:
+     * staging the queries, enqueueing the recorded chain, waiting for the device, building the id-resolved result */
+    uint64_t host_stage_ns;
+    uint64_t host_launch_ns;
+    uint64_t host_wait_ns;
+    uint64_t host_resolve_ns;
+    uint64_t host_calls;
 } gf_stats;
 GF_API int gf_context_stats(const gf_context *ctx, gf_stats *out);
 GF_API int gf_context_reset_stats(gf_context *ctx);

@@ -520,8 +520,48 @@ GF_EXPORT void gf_oracle_synth_rows(uint64_t seed, int64_t row0, int64_t nrows, 
     }
 }
 
+/*
+ * Clustered variant (same as the CUDA fill kernel, bit for bit): with centres > 0 a row is
+ * centre(c) + spread * U(-1,1)^dims where the cluster c is a hash of the row's ordinal (members scattered
+ * over the set); dup_ppm rows per million are exact copies of an EARLIER ordinal's row.  centres == 0 and
+ * dup_ppm == 0 is gf_oracle_synth_rows.
+ */
+GF_EXPORT void gf_oracle_synth_rows_ex(uint64_t seed, uint64_t centres, float spread, uint32_t dup_ppm, int64_t row0,
+                                       int64_t nrows, int dims, int normalize, float *out)
+{
+    int64_t r;
+    int c;
+    for (r = 0; r < nrows; ++r) {
+        float *x = out + (size_t)r * dims;
+        uint64_t ord = (uint64_t)(row0 + r), src = ord;
+        if (dup_ppm != 0u && ord > 0 && gf_splitmix64(seed ^ 0xD0B1E5ull ^ gf_splitmix64(ord)) % 1000000ull < (uint64_t)dup_ppm)
+            src = gf_splitmix64(seed ^ 0x5EED0FD0ull ^ gf_splitmix64(ord)) % ord;
+        uint64_t centre = centres ? gf_splitmix64(seed ^ 0xC1A55E5ull ^ gf_splitmix64(src)) % centres : 0;
+        for (c = 0; c < dims; ++c) {
+            float nv = gf_uniform_pm1(seed, src * (uint64_t)dims + (uint64_t)c);
+            if (centres) {
+                float cv = gf_uniform_pm1(seed ^ 0xC3A7E25ull, centre * (uint64_t)dims + (uint64_t)c);
+                x[c] = fmaf(spread, nv, cv);
+            } else {
+                x[c] = nv;
+            }
+        }
+        if (normalize) {
+            float ss = gf_dot_canonical(x, x, dims);
+            float nrm = sqrtf(ss);
+            if (nrm == 0.0f) {
+                for (c = 0; c < dims; ++c) x[c] = 0.0f;
+            } else {
+                for (c = 0; c < dims; ++c) x[c] = x[c] / nrm;
+            }
+        }
+    }
+}
+
 typedef struct {
-    uint64_t seed;
+    uint64_t seed, centres;
+    float spread;
+    uint32_t dup_ppm;
     int64_t row0, nrows;
     int dims, normalize;
     float *out;
@@ -530,13 +570,28 @@ typedef struct {
 static void *gf_synth_worker(void *arg)
 {
     gf_synth_job *j = (gf_synth_job *)arg;
-    gf_oracle_synth_rows(j->seed, j->row0, j->nrows, j->dims, j->normalize, j->out);
+    gf_oracle_synth_rows_ex(j->seed, j->centres, j->spread, j->dup_ppm, j->row0, j->nrows, j->dims, j->normalize, j->out);
     return NULL;
 }
 
 /* the same rows, generated by `nthreads` pool threads (a 1 M-row CPU baseline is 2 GB of them) */
+static void gf_synth_rows_mt(uint64_t seed, uint64_t centres, float spread, uint32_t dup_ppm, int64_t row0,
+                             int64_t nrows, int dims, int normalize, float *out, int nthreads);
+
 GF_EXPORT void gf_oracle_synth_rows_mt(uint64_t seed, int64_t row0, int64_t nrows, int dims, int normalize, float *out,
                                        int nthreads)
+{
+    gf_synth_rows_mt(seed, 0, 0.0f, 0, row0, nrows, dims, normalize, out, nthreads);
+}
+
+GF_EXPORT void gf_oracle_synth_rows_ex_mt(uint64_t seed, uint64_t centres, float spread, uint32_t dup_ppm, int64_t row0,
+                                          int64_t nrows, int dims, int normalize, float *out, int nthreads)
+{
+    gf_synth_rows_mt(seed, centres, spread, dup_ppm, row0, nrows, dims, normalize, out, nthreads);
+}
+
+static void gf_synth_rows_mt(uint64_t seed, uint64_t centres, float spread, uint32_t dup_ppm, int64_t row0,
+                             int64_t nrows, int dims, int normalize, float *out, int nthreads)
 {
     int t;
     nthreads = gf_pool_clamp(nthreads);
@@ -545,6 +600,9 @@ GF_EXPORT void gf_oracle_synth_rows_mt(uint64_t seed, int64_t row0, int64_t nrow
     for (t = 0; t < nthreads; ++t) {
         const int64_t lo = nrows * t / nthreads, hi = nrows * (t + 1) / nthreads;
         jobs[t].seed = seed;
+        jobs[t].centres = centres;
+        jobs[t].spread = spread;
+        jobs[t].dup_ppm = dup_ppm;
         jobs[t].row0 = row0 + lo;
         jobs[t].nrows = hi - lo;
         jobs[t].dims = dims;

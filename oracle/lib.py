@@ -53,6 +53,10 @@ def lib():
         L.gf_oracle_synth_rows_mt.restype = None
         L.gf_oracle_synth_rows_mt.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                               ctypes.c_int, fp, ctypes.c_int]
+        L.gf_oracle_synth_rows_ex_mt.restype = None
+        L.gf_oracle_synth_rows_ex_mt.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_float, ctypes.c_uint32,
+                                                 ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, fp,
+                                                 ctypes.c_int]
         L.gf_oracle_have_avx2.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -166,4 +170,32 @@ def synth_rows(seed, row0, nrows, dims, normalize=True, nthreads=0):
     lib().gf_oracle_synth_rows_mt(ctypes.c_uint64(seed), ctypes.c_int64(row0), ctypes.c_int64(nrows),
                                   ctypes.c_int(dims), ctypes.c_int(1 if normalize else 0), _fp(out),
                                   ctypes.c_int(nthreads))
+    return out
+
+
+def synth_rows_ex(seed, row0, nrows, dims, centres=0, spread=0.0, dup_ppm=0, normalize=True, nthreads=0):
+    """Clustered / duplicated synthetic rows (gf_oracle_synth_rows_ex), bit-identical to gf_set_add_synthetic_ex."""
+    out = np.empty((nrows, dims), dtype=np.float32)
+    if nthreads <= 0:
+        nthreads = (os.cpu_count() or 1) if nrows >= 4096 else 1
+    lib().gf_oracle_synth_rows_ex_mt(ctypes.c_uint64(seed), ctypes.c_uint64(centres), ctypes.c_float(spread),
+                                     ctypes.c_uint32(dup_ppm), ctypes.c_int64(row0), ctypes.c_int64(nrows),
+                                     ctypes.c_int(dims), ctypes.c_int(1 if normalize else 0), _fp(out),
+                                     ctypes.c_int(nthreads))
+    return out
+
+
+def synth_centre(seed, centre, dims):
+    """The (un-normalised) centre vector of cluster `centre` of a clustered synthetic set."""
+    # a set of one centre whose single row has spread 0 would go through the ordinal hash: restate the hash instead
+    def mix(x):
+        x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return x ^ (x >> 31)
+    s2 = seed ^ 0xC3A7E25
+    out = np.empty(dims, dtype=np.float32)
+    for c in range(dims):
+        h = mix(s2 ^ mix(centre * dims + c))
+        out[c] = np.float32(h >> 40) * np.float32(1.0 / 8388608.0) - np.float32(1.0)
     return out
