@@ -1549,10 +1549,14 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_thr = carve((size_t)nq_max * 4);
     const size_t o_cnt = carve((size_t)nq_max * 4);
     const size_t o_cand = carve((size_t)nq_max * cap * 8);
-    const size_t o_sel = carve((size_t)nq_max * kp * 8);
+    // selection depth of the large-batch chain: select_kernel sorts the best kp_sel candidates by approximate score
+    // and decides PER QUERY how many of them the exact re-score must cover (at least kp)
+    const int kp_sel = std::min(1024, std::max(512, 2 * kp));
+    const size_t o_sel = carve((size_t)nq_max * kp_sel * 8);
+    const size_t o_need = carve((size_t)nq_max * 4);
     // small batches re-score EVERY collected candidate (~`target` rows per query) and skip the selection
     auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)32 << 20); };
-    const size_t o_exact = carve((size_t)nq_max * (rescore_all(std::min(q, kGemmMaxQ)) ? (size_t)cap : (size_t)kp) * 8);
+    const size_t o_exact = carve((size_t)nq_max * (rescore_all(std::min(q, kGemmMaxQ)) ? (size_t)cap : (size_t)kp_sel) * 8);
     const size_t o_map = carve((size_t)kFixupMaxQ * 4);
     const size_t o_count = carve(4);
     const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
@@ -1580,6 +1584,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     unsigned long long *d_cand = (unsigned long long *)(T + o_cand);
     unsigned long long *d_sel = (unsigned long long *)(T + o_sel);
     unsigned long long *d_exact = (unsigned long long *)(T + o_exact);
+    unsigned int *d_need = (unsigned int *)(T + o_need);
     unsigned int *d_fl = (unsigned int *)(T + o_flags);
     int *d_map = (int *)(T + o_map);
     unsigned int *d_count = (unsigned int *)(T + o_count);
@@ -1745,14 +1750,24 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                                     err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 1, fix, stream),
                     GF_ERR_CUDA);
         } else {
-            GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp, d_sel, stream), GF_ERR_CUDA);
+            SelectNeed sn;
+            sn.K = K;
+            sn.kp_min = kp;
+            sn.d_qnorm2 = d_qn;
+            sn.d_maxnorm2_bits = d_small;
+            sn.err_coeff = err_coeff;
+            sn.d_qres2 = d_qres;
+            sn.d_maxres2_bits = d_small + 2;
+            sn.d_need = d_need;
+            GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp_sel, d_sel, stream, sn), GF_ERR_CUDA);
             mark();
-            GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp, d_sel, nullptr, d_exact,
-                                   stream),
+            GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp_sel, d_sel, nullptr, d_exact,
+                                   stream, d_need),
                     GF_ERR_CUDA);
             mark();
-            GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp, K, qp, scanned_rows, d_qn, d_small,
-                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, fix, stream),
+            GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp_sel, K, qp, scanned_rows, d_qn, d_small,
+                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, fix, stream,
+                                    d_need),
                     GF_ERR_CUDA);
         }
         mark();
