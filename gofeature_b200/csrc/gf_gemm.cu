@@ -80,6 +80,11 @@ struct GemmArgs {
     uint2 *gtop;                  // [nq][4 quarters][tile_count]
     uint32_t groups;              // 4 * tile_count
     uint32_t tiles_per_block;     // 128-row tiles of a full block: first guess of a tile's segment
+    // overlapped one-pass chains: instead of waiting for the whole previous kernel (griddepcontrol.wait -- grids
+    // retire in stream order, so that would also wait for the previous STEP's tail), wait until the query
+    // preparation's CTAs have counted themselves in
+    const unsigned int *wait_ctr;
+    unsigned int wait_expect;
 };
 
 // All CTAs of the grid are co-resident (grid <= SMs, one CTA per SM fits by construction), so a counter +
@@ -422,7 +427,16 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         }
     }
     // everything above is CTA-local set-up and overlaps the previous kernel; below, its results are read
-    pdl_wait();
+    if (a.wait_ctr == nullptr) {
+        pdl_wait();
+    } else {
+        if (threadIdx.x == 0) {
+            while ((int)(*(volatile const unsigned int *)a.wait_ctr - a.wait_expect) < 0) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
     if (a.mode != 0 && a.mode != 3 && a.mode != 4 && threadIdx.x == 0) pdl_launch_dependents();  // short launches: let the successor start up now
     for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
         float th = (a.thr != nullptr && i < a.q) ? a.thr[i] : __int_as_float(0x7f800000);
@@ -831,10 +845,22 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
 __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_stride, long long l_stride, int q,
                                     int nq, int dims, float *__restrict__ dst, float *__restrict__ qnorm2,
                                     float *__restrict__ copy, void *__restrict__ dst_sh, int sh_eb,
-                                    float *__restrict__ qres2, float *__restrict__ q_scale)
+                                    float *__restrict__ qres2, float *__restrict__ q_scale,
+                                    const unsigned int *__restrict__ wait_ctr, unsigned int wait_expect,
+                                    unsigned int *__restrict__ done_ctr)
 {
-    pdl_wait();  // the previous call's kernels may still be reading dst / dst_sh
+    // Plain chains: the previous call's kernels may still be reading dst / dst_sh -> wait for them.  Overlapped
+    // one-pass chains (wait_ctr != null) write the OTHER of two scratch sets: nothing of the previous step reads it,
+    // so this kernel does not wait for the previous step's tail at all -- that tail then runs next to this step's
+    // candidate pass.  The step before the previous one used this set: its tail's completion counter is checked.
+    if (wait_ctr == nullptr) pdl_wait();
     pdl_launch_dependents();
+    if (wait_ctr != nullptr) {
+        if (threadIdx.x == 0)
+            while ((int)(*(volatile const unsigned int *)wait_ctr - wait_expect) < 0) {
+            }
+        __syncthreads();
+    }
     const int qi = blockIdx.x;
     __shared__ float red[32], red2[32];
     __shared__ float s_scale;
@@ -926,6 +952,11 @@ __global__ void prep_queries_kernel(const float *__restrict__ src, long long q_s
         qnorm2[qi] = t * 1.0001f;  // upper bounds are what the certificate needs
         if (qres2 != nullptr) qres2[qi] = (t2 == t2 ? t2 : __int_as_float(0x7f800000)) * 1.0001f;
         if (q_scale != nullptr) q_scale[qi] = (dst_sh != nullptr && sh_eb == 1) ? s_scale : 1.f;
+    }
+    if (done_ctr != nullptr) {  // the candidate pass of an overlapped chain waits for nq of these
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(done_ctr, 1u);
     }
 }
 
@@ -1378,6 +1409,14 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
     }
     pdl_wait();
     pdl_launch_dependents();
+    if (a.wait_ctr != nullptr) {
+        // overlapped chains: the previous step's tail may still be running next to the pass that just finished; it
+        // writes the caller's result rows and pushes into the same exchange inbox -- stay behind it
+        if (tid == 0)
+            while ((int)(*(volatile const unsigned int *)a.wait_ctr - a.wait_expect) < 0) {
+            }
+        __syncthreads();
+    }
     // this CTA's 32-entry chunks: chunk c = (k * kGtCluster + rank), k = iteration * 16 + warp; the first kGtPre
     // per thread are loaded NOW, next to the histogram, so that the two L2 round trips overlap
     constexpr int kGtPre = 8;
@@ -1631,6 +1670,11 @@ __global__ void __launch_bounds__(kGtThreads) grouptop_tail_kernel(const GtTail 
         exchange_fold(a.xchg, qi, s_out, s_myflag, reinterpret_cast<unsigned long long *>(s_union), &s_xflag,
                       a.xchg.out_keys, a.xchg.out_flags);
     }
+    if (a.done_ctr != nullptr) {  // this query's answer is out: one more finished cluster of this scratch set
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.done_ctr, 1u);
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -1675,6 +1719,8 @@ cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Ge
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmem);
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
     const int grid = sms < (int)ngroups ? sms : (int)ngroups;
     if (grid < 1) return cudaSuccess;
@@ -1802,6 +1848,8 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     a.q_scale = g.d_q_scale;
     a.scales_per_block = (uint32_t)(g.block_size / 512);
     a.block_floats = g.block_size / 4;
+    a.wait_ctr = g.d_wait_ctr;
+    a.wait_expect = g.wait_expect;
     {
         const long long block_rows = g.block_size / ((long long)g.dims * 4);
         a.tiles_per_block = (uint32_t)((block_rows + kTileRows - 1) / kTileRows);
@@ -1829,10 +1877,17 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
                                 float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
-                                float *q_scale, cudaStream_t stream)
+                                float *q_scale, cudaStream_t stream, const unsigned int *wait_ctr, unsigned int wait_expect,
+                                unsigned int *done_ctr)
 {
+    static bool carve_set = false;
+    if (!carve_set) {
+        cudaFuncSetAttribute(prep_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
     return launch_chain(prep_queries_kernel, dim3(nq), dim3(128), 0, stream, src, (long long)q_stride,
-                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale);
+                        (long long)l_stride, q, nq, dims, dst, qnorm2, copy, dst_shadow, shadow_eb, qres2, q_scale,
+                        wait_ctr, wait_expect, done_ctr);
 }
 
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
@@ -1885,6 +1940,13 @@ cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream)
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
+    // the same shared-memory carve-out as the candidate pass: an SM can only change its carve-out when it is empty,
+    // so with different preferences the next step's pass could not join this kernel's CTAs on their SMs
+    static bool carve_set = false;
+    if (!carve_set) {
+        cudaFuncSetAttribute(grouptop_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
     return cudaLaunchKernelEx(&cfg, grouptop_tail_kernel, t);
 }
 

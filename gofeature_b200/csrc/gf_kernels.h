@@ -140,12 +140,18 @@ struct GemmLaunch {
     unsigned long long dump_ld;
     int sms;
     uint2 *d_gtop;            // kGemmGroupTop: [nq][4 quarters][tile_count] (best key, second key) of every 32-row group
+    // overlapped chains: wait for *d_wait_ctr >= wait_expect (the preparation's CTAs) instead of the previous grid
+    const unsigned int *d_wait_ctr;
+    unsigned int wait_expect;
 };
 int gemm_pad_queries(int q);
 cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream);
+// wait_ctr (optional): the kernel does not wait for its predecessor in the stream (an overlapped one-pass chain,
+// Set::topk_tensor) but for *wait_ctr to reach wait_expect -- the tails that last used the scratch set it writes
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,
                                 float *dst, float *qnorm2, float *copy, void *dst_shadow, int shadow_eb, float *qres2,
-                                float *q_scale, cudaStream_t stream);
+                                float *q_scale, cudaStream_t stream, const unsigned int *wait_ctr = nullptr,
+                                unsigned int wait_expect = 0, unsigned int *done_ctr = nullptr);
 cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsigned int *d_out_bits, int sms,
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
@@ -217,6 +223,11 @@ struct GtTail {
     // sharded sets: the leader ends with the cross-rank exchange + fold (d_out / d_flags then take the LOCAL winners)
     int has_xchg;
     ExchangeArgs xchg;
+    // overlapped chains: stay behind the previous step's tail (*wait_ctr >= wait_expect), count this step's finished
+    // clusters in *done_ctr
+    const unsigned int *wait_ctr;
+    unsigned int wait_expect;
+    unsigned int *done_ctr;
 };
 cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream);
 

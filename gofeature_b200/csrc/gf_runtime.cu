@@ -117,8 +117,11 @@ int Workspace::reserve_tensor(size_t bytes)
         d_tensor_cap = 0;
     }
     GF_CUDA(cudaMalloc((void **)&d_tensor, bytes), GF_ERR_ALLOCATE_GPU_BUFFER);
-    GF_CUDA(cudaMemset(d_tensor, 0, 256), GF_ERR_CUDA);  // the finalize ticket lives at offset 0
+    GF_CUDA(cudaMemset(d_tensor, 0, 256), GF_ERR_CUDA);  // the finalize ticket lives at offset 0, the overlap counters at 64
     d_tensor_cap = bytes;
+    op_step = 0;
+    done_total[0] = done_total[1] = 0u;
+    prep_total[0] = prep_total[1] = 0u;
     return GF_OK;
 }
 
@@ -1569,6 +1572,13 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const bool onepass = onepass_applies(q, K, path, device_fixup, &kp1);
     const uint32_t gt_groups = total_gtiles * 4u;
     const size_t o_gtop = carve(onepass ? (size_t)nq_max * gt_groups * 8 : 0);
+    // second scratch set of the overlapped one-pass chain (see the launch below)
+    const size_t o_qpad2 = carve(onepass ? (size_t)nq_max * dims * 4 : 0);
+    const size_t o_qn2 = carve(onepass ? (size_t)nq_max * 4 : 0);
+    const size_t o_qbf2 = carve(onepass && bf16 ? (size_t)nq_max * dims * seb : 0);
+    const size_t o_qres2 = carve(onepass ? (size_t)nq_max * 4 : 0);
+    const size_t o_qsc2 = carve(onepass ? (size_t)nq_max * 4 : 0);
+    const size_t o_gtop2 = carve(onepass ? (size_t)nq_max * gt_groups * 8 : 0);
     int rc = ws->reserve_tensor(off);
     if (rc) return rc;
     uint8_t *T = ws->d_tensor;
@@ -1635,18 +1645,45 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         if (device_fixup && p0 + kGemmMaxQ >= q) fix = FixupPlan{d_fl, q, fixq, d_map, d_count, d_small + 1, d_ticket};
         fix.flagged = d_small + 3;
         mark();
-        if (phase != 2)
+        // (the overlapped one-pass chain launches its own preparation into the scratch set of the step's parity)
+        const bool overlap = onepass && phase == 0 && d_flags != nullptr && qp == q && !ctx->profiling.load();
+        if (phase != 2 && !overlap)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
                                         d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
         if (onepass) {
+            // Overlap across steps (eager device-resident calls, one pass): step i's tail -- re-score, certificate,
+            // cross-rank exchange, ~10 us and mostly latency -- needs nothing of step i+1 and step i+1's candidate pass
+            // nothing of it, once their scratch is separate.  Two scratch sets alternate; the preparation kernel of
+            // step i+1 does not wait for tail i (it waits for tail i-1's completion counter, the last user of its
+            // set), so the pass that depends on it starts while tail i is still running; tail i+1 stays behind
+            // tail i (same result rows, same exchange inbox) through the other counter.  A recorded graph bakes its
+            // arguments in and keeps the plain serial chain.
+            const int par = overlap ? (int)(ws->op_step & 1ull) : 0;
+            unsigned int *d_done = (unsigned int *)(T + 64);
+            float *o_pad = par ? (float *)(T + o_qpad2) : d_qpad;
+            float *o_qn = par ? (float *)(T + o_qn2) : d_qn;
+            void *o_qbf = bf16 ? (par ? (void *)(T + o_qbf2) : d_qbf) : nullptr;
+            float *o_qres = bf16 ? (par ? (float *)(T + o_qres2) : d_qres) : nullptr;
+            float *o_qsc = par ? (float *)(T + o_qsc2) : d_qsc;
+            if (overlap) {
+                GF_CUDA(prep_queries_launch(d_queries, q_stride, l_stride, qp, nq, dims, o_pad, o_qn, nullptr, o_qbf, seb,
+                                            o_qres, o_qsc, stream, d_done + par, ws->done_total[par], d_done + 2 + par),
+                        GF_ERR_CUDA);
+                ws->prep_total[par] += (unsigned int)nq;
+                g.d_wait_ctr = d_done + 2 + par;
+                g.wait_expect = ws->prep_total[par];
+                g.d_queries_padded = o_pad;
+                g.d_queries_shadow = o_qbf;
+                g.d_q_scale = o_qsc;
+            }
             mark();
             g.mode = kGemmGroupTop;
             g.tile_first = 0;
             g.tile_stride = 1;
             g.tile_count = total_gtiles;
-            g.d_gtop = (uint2 *)(T + o_gtop);
+            g.d_gtop = (uint2 *)(T + (par ? o_gtop2 : o_gtop));
             {
                 std::pair<cudaEvent_t, cudaEvent_t> ev;
                 ctx->prof_begin(stream, &ev);
@@ -1662,16 +1699,21 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             t.d_gtile_start = d_gtile_start;
             t.nseg = nseg;
             t.dims = dims;
-            t.d_queries_padded = d_qpad;
-            t.d_q_scale = seb == 1 ? d_qsc : nullptr;
+            t.d_queries_padded = overlap ? o_pad : d_qpad;
+            t.d_q_scale = seb == 1 ? (overlap ? o_qsc : d_qsc) : nullptr;
             t.kp = kp1;
             t.K = K;
             t.q = qp;
             t.rows_total = scanned_rows;
-            t.d_qnorm2 = d_qn;
+            t.d_qnorm2 = overlap ? o_qn : d_qn;
             t.d_maxnorm2_bits = d_small;
             t.err_coeff = err_coeff;
-            t.d_qres2 = d_qres;
+            t.d_qres2 = overlap ? o_qres : d_qres;
+            if (overlap) {
+                t.wait_ctr = d_done + (par ^ 1);
+                t.wait_expect = ws->done_total[par ^ 1];
+                t.done_ctr = d_done + par;
+            }
             t.d_maxres2_bits = d_small + 2;
             t.d_out = d_out + (size_t)p0 * K;
             t.d_flags = d_fl + p0;
@@ -1697,6 +1739,14 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             }
             t.tiles_per_block = (uint32_t)std::max<int64_t>(1, (cache->block_size / ((int64_t)dims * 4) + 127) / 128);
             GF_CUDA(grouptop_tail_launch(t, stream), GF_ERR_CUDA);
+            if (overlap) {
+                ws->done_total[par] += (unsigned int)qp;
+                ws->op_step++;
+                g.d_wait_ctr = nullptr;
+                g.d_queries_padded = d_qpad;  // (the launch descriptor is reused by later passes of a larger call)
+                g.d_queries_shadow = d_qbf;
+                g.d_q_scale = d_qsc;
+            }
             mark();
             ctx->stats.gemm_launches += 1;
             ctx->stats.other_launches += phase != 2 ? 2 : 1;  // (prep,) tail

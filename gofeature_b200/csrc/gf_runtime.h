@@ -103,6 +103,12 @@ struct Workspace {
     // a sharded caller's cross-rank step: the one-pass chain's tail ends with it (sets xchg_used) instead of a launch
     const ExchangeArgs *xchg = nullptr;
     bool xchg_used = false;
+    // Overlapped one-pass chains (Set::topk_tensor): two scratch sets alternate with the step's parity so that a
+    // step's tail runs next to the following step's candidate pass; done_total[p] = tail clusters launched so far on
+    // set p (the device-side completion counters live at the head of d_tensor and are compared against these)
+    uint64_t op_step = 0;
+    unsigned int done_total[2] = {0u, 0u};
+    unsigned int prep_total[2] = {0u, 0u};  // preparation CTAs launched so far per scratch set
     struct MultiExt *multi = nullptr;  // a multi-device set's per-search state (child workspaces, inboxes): gf_multi.cu
     void drop_graphs();
     int reserve(size_t d_bytes, size_t h_bytes);
