@@ -329,12 +329,18 @@ constexpr int kGtFlush = GF_GT_FLUSH;  // a multiple of 16 (128 bytes of keys pe
 constexpr int kGtStageRow = kGtFlush + 1;
 __host__ __device__ constexpr int gt_stage_bytes(int nq) { return nq <= kGtMaxQ ? 4 * nq * kGtStageRow * 8 : 0; }
 
-template <int NQ, int TM, bool PAIR = false>
+// RESB: the query operand stays RESIDENT in shared memory for the whole launch (dims * element bytes = 512 per query:
+// 512-d int8, all four K blocks, loaded once) instead of travelling with every stage.  At 256 queries the 32 KB of
+// queries per stage were two thirds of the L2 -> SM traffic (ncu: 1.54 GB of TMA loads for 0.52 GB of DRAM reads per
+// pass) and held the tensor pipe at 51 %; resident, a stage is 16 KB of feature rows and nothing else.
+constexpr int kResRowBytes = 512;
+template <int NQ, int TM, bool PAIR = false, bool RESB = false>
 struct GemmCfg {
-    static constexpr int kBBytes = (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
+    static constexpr int kResBytes = RESB ? NQ * kResRowBytes : 0;
+    static constexpr int kBBytes = RESB ? 0 : (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
     static constexpr int kStagesFit =
-        (int)((232448 - 1024 - 320 - NQ * 12 - 1024 - kAppendStageBytes - gt_stage_bytes(NQ)) / kStageBytes);
+        (int)((232448 - 1024 - 320 - NQ * 12 - 1024 - kAppendStageBytes - gt_stage_bytes(NQ) - kResBytes) / kStageBytes);
     // small batches are pure HBM streaming with short tiles (int8: 4 K blocks of 18 KB per tile): a deep ring
     // keeps more than two tiles of loads in flight across the per-tile work of the producer
     static constexpr int kStagesCap = GF_GEMM_STAGES_SMALL;
@@ -351,21 +357,26 @@ struct GemmCfg {
     static constexpr int kChunk = kColsPerEpiWarp >= 32 ? 32 : 16;  // columns per tcgen05.ld
     static_assert(kColsPerEpiWarp % kChunk == 0, "epilogue column split");
     static constexpr size_t kSmem =
-        1024 /*align slack*/ + (size_t)kStages * kStageBytes + 320 /*barriers*/ + NQ * 12 + kAppendStageBytes +
-        gt_stage_bytes(NQ);
+        1024 /*align slack*/ + (size_t)kResBytes + (size_t)kStages * kStageBytes + 320 /*barriers*/ + NQ * 12 +
+        kAppendStageBytes + gt_stage_bytes(NQ);
+    static_assert((2 * kStages + 2 * kBuf) * 8 + 8 <= 304, "room for the resident operand's barrier at +304");
     static_assert(kStages >= 2, "pipeline too shallow");
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
 
-template <int NQ, int TM, int EB, bool PAIR, bool FUSED = false>
+template <int NQ, int TM, int EB, bool PAIR, bool FUSED = false, bool RESB = false>
 __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
 {
     static_assert(!PAIR || (TM == 1 && EB == 2), "the 2-CTA variant: one tile per CTA, bf16 operands");
-    using Cfg = GemmCfg<NQ, TM, PAIR>;
+    static_assert(!RESB || (TM == 1 && !PAIR && !FUSED), "resident query operand: one tile per step, one CTA");
+    using Cfg = GemmCfg<NQ, TM, PAIR, RESB>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_al = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *res_b = smem_al;                        // RESB: [K block][NQ rows][128 B], each K block a TMA box
+    uint8_t *smem = smem_al + Cfg::kResBytes;        // the stage ring
     uint8_t *tail = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
+    uint64_t *bfull = reinterpret_cast<uint64_t *>(tail + 304);
     uint64_t *full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *empty = full + Cfg::kStages;
     uint64_t *tfull = empty + Cfg::kStages;
@@ -411,6 +422,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], (PAIR ? 2 : 1) * kEpiWarps);  // a pair: both CTAs' epilogue warps release the leader's accumulator
         }
+        if (RESB) mbar_init(bfull, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -464,6 +476,10 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             int s = 0;
             uint32_t ph = 0;
             SegCursor segc;
+            if (RESB && g_count > 0) {  // the whole query operand, once
+                mbar_arrive_expect_tx(bfull, (uint32_t)kblocks * NQ * 128u);
+                for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(res_b + (size_t)kb * NQ * 128, &tmB, kb * kBK, 0, bfull);
+            }
             for (uint32_t itp = 0; itp < g_count; ++itp) {
                 const uint32_t g = g_begin + itp * g_step;
                 int slab_row[TM];
@@ -490,7 +506,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
 #pragma unroll
                         for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
-                        tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
+                        if (!RESB) tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
                     }
                     if (++s == Cfg::kStages) {
                         s = 0;
@@ -505,6 +521,10 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             constexpr uint32_t idesc = instr_desc<EB>(PAIR ? 2 * kTileRows : kTileRows, NQ);
             int s = 0;
             uint32_t ph = 0, it = 0;
+            if (RESB && g_count > 0) {
+                mbar_wait(bfull, 0);
+                tc_fence_after();
+            }
             for (; it < g_count; ++it) {
                 const uint32_t buf = it % Cfg::kBuf;
                 mbar_wait(&tempty[buf], ((it / Cfg::kBuf) & 1) ^ 1);
@@ -514,7 +534,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
-                    const uint64_t bdesc = smem_desc_sw128(sa + TM * kABytes);
+                    const uint64_t bdesc = smem_desc_sw128(RESB ? res_b + (size_t)kb * NQ * 128 : sa + TM * kABytes);
 #pragma unroll
                     for (int j = 0; j < TM; ++j) {
                         const uint64_t adesc = smem_desc_sw128(sa + j * kABytes);
@@ -1711,6 +1731,20 @@ cudaError_t make_map(CUtensorMap *map, const void *base, uint64_t rows, int dims
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// resident query operand (RESB): 512 bytes per query = all K blocks of a 512-d int8 / 256-d bf16 / 128-d float32 query
+template <int NQ, int EB>
+cudaError_t launch_gemm_resb(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms, cudaStream_t stream)
+{
+    using Cfg = GemmCfg<NQ, 1, false, true>;
+    auto kern = gemm_kernel<NQ, 1, EB, false, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int grid = sms < (int)a.tile_count ? sms : (int)a.tile_count;
+    if (grid < 1) return cudaSuccess;
+    return launch_chain(kern, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem, stream, tmA, tmB, a);
+}
+
 template <int NQ, int TM, int EB>
 cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms,
                         cudaStream_t stream)
@@ -1788,6 +1822,13 @@ static cudaError_t gemm_dispatch(const GemmLaunch &g, const CUtensorMap &tmA, co
             if (g.nq == 256) return launch_gemm_pair<256>(tmA, tmB, a, g.sms, stream);
             if (g.nq == 128) return launch_gemm_pair<128>(tmA, tmB, a, g.sms, stream);
             return cudaErrorInvalidValue;
+        }
+    }
+    if constexpr (EB == 1) {
+        // large int8 batches on 512-d rows: the query operand stays resident in shared memory
+        if (g.dims * EB == kResRowBytes && !pair) {
+            if (g.nq == 256) return launch_gemm_resb<256, EB>(tmA, tmB, a, g.sms, stream);
+            if (g.nq == 128) return launch_gemm_resb<128, EB>(tmA, tmB, a, g.sms, stream);
         }
     }
     switch (g.nq) {
