@@ -1489,7 +1489,10 @@ bool Set::onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out
     // the chain around it ~17 us shorter.  Measured (one-pass vs two-pass, ms per step): 4 M rows 0.312 / 0.337 at
     // one query, 0.340 / 0.338 at ten; 10 M rows 0.748 / 0.766 and 0.806 / 0.781.  Path 2 / 3 (tests, sweeps) pins
     // the one-pass chain at any size.
-    const int64_t row_limit = q <= 2 ? 12000000 : 3000000;
+    // (round 2, with a step's tail running next to the following step's pass: 4 M rows 0.312 / 0.342 at ten queries,
+    // 8 M rows 0.598 / 0.648; sixteen queries 0.341 / 0.350 and 0.670 / 0.659; 12.5 M rows 0.985 / 0.988 at ten --
+    // profiles/r2n_onepass_sweep.txt)
+    const int64_t row_limit = q <= 10 ? 12000000 : (q <= 16 ? 6000000 : 3000000);
     const bool size_ok = path == 2 || path == 3 || scanned_rows <= row_limit;
     return onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && K <= kGtMaxK && kp1 <= kGtCap / 2 &&
            size_ok && (uint64_t)total_gtiles * 4u < (1ull << 27);
