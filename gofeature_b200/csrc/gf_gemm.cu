@@ -16,7 +16,7 @@
 //                (select / rescore / finalize kernels follow: the two-pass chain)
 //   GROUPTOP (4) no threshold: the best two keys of every 32-row group per query; grouptop_tail_kernel (one
 //                thread-block cluster per query) cuts, re-scores, certifies -- the one-pass chain of small batches
-//   DUMP (2), FUSED (3, experimental) as described at their code
+//   DUMP (2) every score, for small sets and diagnostics
 //
 // Warp roles (192 threads): warp 0 TMA producer (one thread), warp 1 TMEM allocator + MMA issuer
 // (one thread), warps 2..5 epilogue (tcgen05.ld, one feature row per thread).
@@ -72,10 +72,6 @@ struct GemmArgs {
     const float *q_scale;         // [nq]
     uint32_t scales_per_block;
     long long block_floats;       // block_size / 4: slab offset (in floats) -> block index
-    // FUSED mode (3): the threshold sample is each CTA's own first tile
-    float *thr_out;               // [nq] thresholds written by CTA 0 (finalize's certificate reads them)
-    unsigned int *sync;           // [0] arrival count, [1] generation, [2] sticky "a barrier timed out"
-    int sample_m;                 // threshold = sample_m-th largest of the gridDim.x tile maxima
     // GROUPTOP mode (4): best two keys of every 32-row group
     uint2 *gtop;                  // [nq][4 quarters][tile_count]
     uint32_t groups;              // 4 * tile_count
@@ -87,37 +83,6 @@ struct GemmArgs {
     unsigned int wait_expect;
 };
 
-// All CTAs of the grid are co-resident (grid <= SMs, one CTA per SM fits by construction), so a counter +
-// generation barrier is safe; a timeout turns a scheduling surprise into "collect nothing" (every query is
-// then flagged and answered by the exact scan) instead of a hung GPU.
-__device__ __forceinline__ bool grid_barrier(unsigned int *sync, unsigned int n)
-{
-    volatile unsigned int *vs = sync;
-    if (vs[2] != 0u) return false;
-    const unsigned int my = vs[1];
-    __threadfence();
-    if (atomicAdd(sync, 1u) == n - 1u) {
-        atomicExch(sync, 0u);
-        __threadfence();
-        atomicAdd(sync + 1, 1u);
-        return true;
-    }
-    unsigned long long t0 = 0ull;
-    for (unsigned int spins = 0; vs[1] == my; ++spins) {
-        if ((spins & 4095u) == 4095u) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0ull) t0 = now;
-            if (now - t0 > 2000000000ull) {
-                atomicExch(sync + 2, 1u);
-                return false;
-            }
-        }
-    }
-    __threadfence();
-    return true;
-}
-
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
     asm volatile(
@@ -126,9 +91,8 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
-// 2-CTA (cta_group::2) variants.  The pair's LEADER (cluster rank 0) owns the full / tempty barriers:
-// both CTAs' TMA loads complete on the leader's full barrier, the peer's epilogue warps arrive on the
-// leader's tempty barrier; `leader_addr` maps a local shared address to the same offset in CTA 0.
+// thread-block cluster helpers (the one-pass chain's tail): `leader_addr` maps a local shared address to the same
+// offset in CTA 0 of the cluster
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -145,28 +109,6 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint64_t *bar)  // arrives on `bar` in BOTH CTAs of the pair
-{
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"((uint16_t)3)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
-{
-    // relaxed: the accumulator reads are ordered by tcgen05.wait::ld + fence::before_thread_sync already; a
-    // .release arrive at cluster scope costs MEMBAR.ALL.GPU + ERRBAR per tile (27 % of the pair kernel's samples)
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -176,18 +118,11 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T over 32 bytes of K: one K = 8 step of kind::tf32 (EB = 4)
 // or one K = 16 step of kind::f16 with bf16 operands (EB = 2)
-template <int EB, bool PAIR>
+template <int EB>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate)
 {
-    if (PAIR) {  // M = 256 over the CTA pair, bf16 operands only
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else if (EB == 1) {
+    if (EB == 1) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
@@ -303,11 +238,7 @@ __device__ __forceinline__ void locate_tile(const GemmArgs &a, uint32_t t, SegCu
     valid = c.rows - row0 < (uint32_t)kTileRows ? c.rows - row0 : (uint32_t)kTileRows;
 }
 
-// TM = feature-row tiles that share one load of the query operand.  The ring can only hold ~190 KB of
-// loads in flight; at NQ = 256 one K block is 16 KB of rows + 32 KB of queries per 512 MMA cycles, more
-// than the L2 latency lets 4 stages cover (measured: 53 % tensor utilisation, and sharing B across a CTA
-// pair by multicast did not help because the footprint per stage stayed).  With TM = 2 a stage feeds
-// 1024 MMA cycles with 64 KB, and the kernel goes back to being HBM-bound.
+// TM = feature-row tiles that share one load of the query operand (only TM = 1 is instantiated: TM = 2 measured slower).
 // COLLECT appends are staged in shared memory and flushed 128 at a time: a global atomicAdd per survivor
 // inside the score loop stalled the whole epilogue warp for an L2 round trip (4 per warp per tile at 256
 // queries x ~500 candidates), longer than the MMAs of the next tile take
@@ -334,10 +265,10 @@ __host__ __device__ constexpr int gt_stage_bytes(int nq) { return nq <= kGtMaxQ 
 // queries per stage were two thirds of the L2 -> SM traffic (ncu: 1.54 GB of TMA loads for 0.52 GB of DRAM reads per
 // pass) and held the tensor pipe at 51 %; resident, a stage is 16 KB of feature rows and nothing else.
 constexpr int kResRowBytes = 512;
-template <int NQ, int TM, bool PAIR = false, bool RESB = false>
+template <int NQ, int TM, bool RESB = false>
 struct GemmCfg {
     static constexpr int kResBytes = RESB ? NQ * kResRowBytes : 0;
-    static constexpr int kBBytes = RESB ? 0 : (PAIR ? NQ / 2 : NQ) * 128;  // a pair splits the query operand: half per SM
+    static constexpr int kBBytes = RESB ? 0 : NQ * 128;
     static constexpr int kStageBytes = TM * kABytes + kBBytes;
     static constexpr int kStagesFit =
         (int)((232448 - 1024 - 320 - NQ * 12 - 1024 - kAppendStageBytes - gt_stage_bytes(NQ) - kResBytes) / kStageBytes);
@@ -345,8 +276,7 @@ struct GemmCfg {
     // keeps more than two tiles of loads in flight across the per-tile work of the producer
     static constexpr int kStagesCap = GF_GEMM_STAGES_SMALL;
     static constexpr int kStages = kStagesFit > (NQ <= 32 ? kStagesCap : 6) ? (NQ <= 32 ? kStagesCap : 6) : kStagesFit;
-    // accumulator sets in TMEM: up to 8 (small batches leave most of the 512 columns free, and the FUSED launch
-    // lets the MMAs run that many tiles ahead while the epilogue waits for the thresholds behind the grid barrier)
+    // accumulator sets in TMEM (small batches leave most of the 512 columns free, but more than two sets measured slower)
     static constexpr int kBufFit = 512 / (TM * NQ);
     static constexpr int kBufMax = GF_GEMM_TMEM_BUFS;  // 2 measured best (8: COLLECT 0.088 -> 0.096 ms at 16 queries)
     static constexpr int kBuf = kBufFit >= kBufMax ? kBufMax : (kBufFit >= 4 && kBufMax >= 4 ? 4 : (kBufFit >= 2 ? 2 : 1));
@@ -364,13 +294,12 @@ struct GemmCfg {
     static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 };
 
-template <int NQ, int TM, int EB, bool PAIR, bool FUSED = false, bool RESB = false>
+template <int NQ, int TM, int EB, bool RESB = false>
 __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a)
 {
-    static_assert(!PAIR || (TM == 1 && EB == 2), "the 2-CTA variant: one tile per CTA, bf16 operands");
-    static_assert(!RESB || (TM == 1 && !PAIR && !FUSED), "resident query operand: one tile per step, one CTA");
-    using Cfg = GemmCfg<NQ, TM, PAIR, RESB>;
+    static_assert(!RESB || TM == 1, "resident query operand: one tile per step");
+    using Cfg = GemmCfg<NQ, TM, RESB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem_al = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *res_b = smem_al;                        // RESB: [K block][NQ rows][128 B], each K block a TMA box
@@ -393,21 +322,16 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kBK = KBlock<EB>::kElems;
     const int kblocks = a.dims / kBK;
-    // a group = the tiles one worker takes per step: TM consecutive tiles of a CTA, or (PAIR) two consecutive
-    // tiles, one per CTA of the pair (256 feature rows = M of one cta_group::2 MMA)
+    // a group = the tiles one worker (CTA) takes per step: TM consecutive tiles
     constexpr int kEpiWarps = gemm_epi_warps(NQ), kEpiThreads = 32 * kEpiWarps;
-    constexpr int kGroupTiles = PAIR ? 2 : TM;
+    constexpr int kGroupTiles = TM;
     const uint32_t ngroups = (a.tile_count + kGroupTiles - 1) / kGroupTiles;
-    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
-    const uint32_t worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-    const uint32_t nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
-    // which groups this worker takes: strided over the workers, or (FUSED) one contiguous chunk, so that the
-    // first tiles of the CTAs -- the threshold sample -- are spread evenly over the set
-    static_assert(!FUSED || (!PAIR && TM == 1 && NQ <= 32), "the fused launch: small batches, one tile per step");
-    constexpr bool fused = FUSED;  // (a template parameter: the plain instantiations carry none of its code)
-    // the full passes (COLLECT, GROUPTOP: every tile, stride 1) give each worker ONE contiguous range of tiles too: a
-    // worker then stays inside a segment for ~50 tiles instead of changing segment with every tile
-    const bool chunked = fused || (a.tile_stride == 1u && (a.mode == 0 || a.mode == 4));
+    const uint32_t worker = blockIdx.x;
+    const uint32_t nworkers = gridDim.x;
+    // which groups this worker takes: strided over the workers (the threshold sample), or -- the full passes, COLLECT
+    // and GROUPTOP: every tile, stride 1 -- ONE contiguous range of tiles per worker: a worker then stays inside a
+    // segment for ~50 tiles instead of changing segment with every tile
+    const bool chunked = a.tile_stride == 1u && (a.mode == 0 || a.mode == 4);
     const uint32_t g_begin = chunked ? (uint32_t)((unsigned long long)worker * ngroups / nworkers) : worker;
     const uint32_t g_step = chunked ? 1u : nworkers;
     const uint32_t g_count = chunked ? (uint32_t)((unsigned long long)(worker + 1) * ngroups / nworkers) - g_begin
@@ -420,23 +344,16 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         }
         for (int i = 0; i < Cfg::kBuf; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], (PAIR ? 2 : 1) * kEpiWarps);  // a pair: both CTAs' epilogue warps release the leader's accumulator
+            mbar_init(&tempty[i], kEpiWarps);
         }
         if (RESB) mbar_init(bfull, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
-        if (PAIR) {  // both CTAs' warp 1, same shared offset for the result
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "r"((uint32_t)Cfg::kTmemCols)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "r"((uint32_t)Cfg::kTmemCols)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // everything above is CTA-local set-up and overlaps the previous kernel; below, its results are read
     if (a.wait_ctr == nullptr) {
@@ -463,10 +380,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     }
     if (threadIdx.x < 16) stage_n[threadIdx.x] = 0;
     tc_fence_before();
-    if (PAIR)
-        cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
-    else
-        __syncthreads();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -485,7 +399,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 int slab_row[TM];
 #pragma unroll
                 for (int j = 0; j < TM; ++j) {
-                    uint32_t i = PAIR ? g * 2 + cta_rank : g * TM + j;
+                    uint32_t i = g * TM + j;
                     if (i >= a.tile_count) i = a.tile_count - 1;  // odd tail: shadow the last tile
                     const uint32_t t = a.tile_first + i * a.tile_stride;
                     uint32_t row0, valid;
@@ -495,19 +409,10 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
-                    if (PAIR) {
-                        // each CTA loads its own 128 rows and its half of the queries; both complete on the
-                        // leader's barrier, which expects the bytes of the whole pair
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
-                        const uint32_t lbar = leader_addr(&full[s]);
-                        tma_load_2d_pair(sa, &tmA, kb * kBK, slab_row[0], lbar);
-                        tma_load_2d_pair(sa + kABytes, &tmB, kb * kBK, (int)cta_rank * (NQ / 2), lbar);
-                    } else {
-                        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
 #pragma unroll
-                        for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
-                        if (!RESB) tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
-                    }
+                    for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
+                    if (!RESB) tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
@@ -516,9 +421,9 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (the pair's leader only) =====================
-        if (lane == 0 && cta_rank == 0) {
-            constexpr uint32_t idesc = instr_desc<EB>(PAIR ? 2 * kTileRows : kTileRows, NQ);
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc<EB>(kTileRows, NQ);
             int s = 0;
             uint32_t ph = 0, it = 0;
             if (RESB && g_count > 0) {
@@ -540,18 +445,16 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         const uint64_t adesc = smem_desc_sw128(sa + j * kABytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)  // 32 bytes (>> 4 = 2) further along the swizzled row
-                            tc_mma<EB, PAIR>(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
+                            tc_mma<EB>(d_addr + j * NQ, adesc + 2 * k, bdesc + 2 * k, idesc,
                                              (uint32_t)((kb | k) != 0));
                     }
-                    // frees the stage (in both CTAs of a pair) when these MMAs have read it
-                    if (PAIR) tc_commit_pair(&empty[s]); else tc_commit(&empty[s]);
+                    tc_commit(&empty[s]);  // frees the stage when these MMAs have read it
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
                     }
                 }
-                // accumulators of the group complete (each CTA of a pair holds its 128 rows)
-                if (PAIR) tc_commit_pair(&tfull[buf]); else tc_commit(&tfull[buf]);
+                tc_commit(&tfull[buf]);  // accumulators of the group complete
             }
         }
     } else {
@@ -567,7 +470,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         // int8: a row's dequantisation scale comes from a 4-bytes-per-row array that streams from DRAM; loaded when
         // its tile starts, that ~1 us latency sat on the epilogue's critical path once per tile (measured: the pass
         // went from HBM-bound to epilogue-bound as soon as the per-tile work grew).  It is loaded ONE TILE AHEAD.
-        constexpr bool kPrefRs = EB == 1 && TM == 1 && !PAIR && !FUSED;
+        constexpr bool kPrefRs = EB == 1 && TM == 1;
         // (the cursor moves on to the next tile's segment here; this tile's row0 / valid / slot are taken before)
         auto load_rs = [&](uint32_t it_) -> float {
             if (it_ >= g_count) return 1.f;
@@ -586,14 +489,10 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             // the wait for the accumulators comes AFTER this tile's segment / slot / row-scale loads have been
             // issued (the epilogue is the critical path at large batches: their latency hides behind the wait)
             bool waited = false, released = false;
-            // FUSED: the first tile is read twice -- tile maxima for the threshold, then the COLLECT pass
-            const int npass = (fused && it == 0) ? 2 : 1;
-#pragma unroll 1
-            for (int pass_i = 0; pass_i < npass; ++pass_i) {
-            const int mode = fused ? (pass_i + 1 < npass ? 1 : 0) : a.mode;
+            const int mode = a.mode;
 #pragma unroll 1
             for (int j = 0; j < TM; ++j) {
-                const uint32_t i = PAIR ? g * 2 + cta_rank : g * TM + j;
+                const uint32_t i = g * TM + j;
                 if (i >= a.tile_count) break;  // shadow tile of an odd tail: nothing to report
                 const uint32_t t = a.tile_first + i * a.tile_stride;
                 uint32_t row0, valid;
@@ -685,7 +584,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
                         if (Cfg::kChunk == 32 || (lane & 1) == 0) atomicMax(&tmax_s[col], score_image(m));
                     } else if (mode == 4) {
-                        if constexpr (NQ <= kGtMaxQ && TM == 1 && !PAIR) {
+                        if constexpr (NQ <= kGtMaxQ && TM == 1) {
                             // the scores are in registers (one chunk holds all NQ columns): release the accumulator
                             // NOW -- an arrive (release) issued after the global store / histogram atomic below
                             // would wait for their acknowledgement, an L2 round trip per tile
@@ -768,51 +667,12 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 if (mode == 1) {
                     named_bar_sync(2, kEpiThreads);
                     for (int c = threadIdx.x - 64; c < NQ; c += kEpiThreads) {
-                        a.tilemax[(size_t)(fused ? worker : i) * NQ + c] = image_score(tmax_s[c]);
+                        a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
                         tmax_s[c] = 0u;
-                        if (fused && worker == 0) a.cnt[c] = 0u;  // nothing is appended before the grid barrier
                     }
                     named_bar_sync(2, kEpiThreads);
                 }
             }
-            if (fused && pass_i + 1 < npass) {
-                // every CTA has published its tile maxima -> per-query threshold (the sample_m-th largest), all
-                // CTAs compute all of them (NQ <= 32: a few per warp, ~0.5 us each) from the L2-resident table
-                __shared__ int s_ok;
-                __threadfence();
-                named_bar_sync(2, kEpiThreads);
-                if (threadIdx.x == 64) s_ok = grid_barrier(a.sync, nworkers) ? 1 : 0;
-                named_bar_sync(2, kEpiThreads);
-                const bool ok = s_ok != 0;
-                for (int qi = warp - 2; qi < NQ; qi += kEpiWarps) {
-                    unsigned int v[5];  // gridDim.x <= 160 sample tiles
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const uint32_t t = lane + 32 * k;
-                        v[k] = (ok && t < nworkers) ? score_image(__ldcg(a.tilemax + (size_t)t * NQ + qi)) : 0u;
-                    }
-                    unsigned int prefix = 0u;
-                    for (int bit = 31; bit >= 0; --bit) {
-                        const unsigned int cand = prefix | (1u << bit);
-                        int c = 0;
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) c += (v[k] >= cand) ? 1 : 0;
-                        c = __reduce_add_sync(0xffffffffu, c);
-                        if (c >= a.sample_m) prefix = cand;
-                    }
-                    if (lane == 0) {
-                        float th = (ok && qi < a.q) ? image_score(prefix) : __int_as_float(0x7f800000);
-                        if (worker == 0) a.thr_out[qi] = th;
-                        if (EB == 1) {
-                            const float qs = qs_s[qi];
-                            th = qs > 0.f ? th / qs : __int_as_float(0x7f800000);
-                        }
-                        thr_s[qi] = th;
-                    }
-                }
-                named_bar_sync(2, kEpiThreads);
-            }
-            }  // pass_i
             if (!waited) {  // (only a shadow tile of an odd tail gets here without having waited)
                 mbar_wait(&tfull[buf], (it / Cfg::kBuf) & 1);
                 tc_fence_after();
@@ -820,9 +680,9 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0 && !released) {
-                if (PAIR) mbar_arrive_remote(leader_addr(&tempty[buf])); else mbar_arrive(&tempty[buf]);
+                mbar_arrive(&tempty[buf]);
             }
-            if (a.mode == 0 || fused) {
+            if (a.mode == 0) {
                 // the accumulator is released; each warp flushes ITS staged survivors when its stage is half
                 // full or this was the CTA's last group -- no barrier between the epilogue warps
                 __syncwarp();
@@ -840,22 +700,13 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 }
             }
         }
-        if ((a.mode == 0 || a.mode == 4 || fused) && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
+        if ((a.mode == 0 || a.mode == 4) && warp == 2 && lane == 0) pdl_launch_dependents();  // this CTA's tiles are done
     }
     tc_fence_before();
-    if (PAIR) {
-        cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
-        if (warp == 1)
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)Cfg::kTmemCols)
-                         : "memory");
-    } else {
-        __syncthreads();
-        if (warp == 1)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)Cfg::kTmemCols)
-                         : "memory");
-    }
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
 }
 
 // ------------------------------------------------------------------ helper kernels
@@ -1735,8 +1586,8 @@ cudaError_t make_map(CUtensorMap *map, const void *base, uint64_t rows, int dims
 template <int NQ, int EB>
 cudaError_t launch_gemm_resb(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms, cudaStream_t stream)
 {
-    using Cfg = GemmCfg<NQ, 1, false, true>;
-    auto kern = gemm_kernel<NQ, 1, EB, false, false, true>;
+    using Cfg = GemmCfg<NQ, 1, true>;
+    auto kern = gemm_kernel<NQ, 1, EB, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1750,55 +1601,16 @@ cudaError_t launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Ge
                         cudaStream_t stream)
 {
     using Cfg = GemmCfg<NQ, TM>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmem);
+    auto kern = gemm_kernel<NQ, TM, EB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
+    // one carve-out for every kernel of a search chain: an SM only changes it when it is empty, and the one-pass
+    // chain's tail shares SMs with the next step's pass (grouptop_tail_launch)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const uint32_t ngroups = (a.tile_count + TM - 1) / TM;
     const int grid = sms < (int)ngroups ? sms : (int)ngroups;
     if (grid < 1) return cudaSuccess;
-    if (a.mode == kGemmFused) {
-        if constexpr (NQ <= 32 && TM == 1) {
-            e = cudaFuncSetAttribute(gemm_kernel<NQ, TM, EB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)Cfg::kSmem);
-            if (e != cudaSuccess) return e;
-            return launch_chain(gemm_kernel<NQ, TM, EB, false, true>, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem,
-                                stream, tmA, tmB, a);
-        } else {
-            return cudaErrorInvalidValue;
-        }
-    }
-    return launch_chain(gemm_kernel<NQ, TM, EB, false>, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem, stream, tmA, tmB, a);
-}
-
-// 2-CTA variant: clusters of two CTAs (one TPC), each pair takes 256 consecutive feature rows per step
-template <int NQ>
-cudaError_t launch_gemm_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a, int sms,
-                             cudaStream_t stream)
-{
-    using Cfg = GemmCfg<NQ, 1, true>;
-    auto kern = gemm_kernel<NQ, 1, 2, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-    if (e != cudaSuccess) return e;
-    const uint32_t ngroups = (a.tile_count + 1) / 2;
-    int pairs = sms / 2 < (int)ngroups ? sms / 2 : (int)ngroups;
-    if (pairs < 1) return cudaSuccess;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(gemm_threads(NQ));
-    cfg.dynamicSmemBytes = Cfg::kSmem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a);
+    return launch_chain(kern, dim3(grid), dim3(gemm_threads(NQ)), Cfg::kSmem, stream, tmA, tmB, a);
 }
 
 }  // namespace
@@ -1814,33 +1626,23 @@ int gemm_pad_queries(int q)
 
 template <int EB>
 static cudaError_t gemm_dispatch(const GemmLaunch &g, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &a,
-                                 bool pair, cudaStream_t stream)
+                                 cudaStream_t stream)
 {
-    static const int tm_big = getenv("GF_GEMM_TM2") ? 2 : 1;  // tuning knob (TM = 2 measured slower: 0.58 vs 0.40 ms at NQ = 256)
-    if constexpr (EB == 2) {
-        if (pair) {
-            if (g.nq == 256) return launch_gemm_pair<256>(tmA, tmB, a, g.sms, stream);
-            if (g.nq == 128) return launch_gemm_pair<128>(tmA, tmB, a, g.sms, stream);
-            return cudaErrorInvalidValue;
-        }
-    }
     if constexpr (EB == 1) {
         // large int8 batches on 512-d rows: the query operand stays resident in shared memory
-        if (g.dims * EB == kResRowBytes && !pair) {
+        if (g.dims * EB == kResRowBytes) {
             if (g.nq == 256) return launch_gemm_resb<256, EB>(tmA, tmB, a, g.sms, stream);
             if (g.nq == 128) return launch_gemm_resb<128, EB>(tmA, tmB, a, g.sms, stream);
         }
     }
+    // (tried and dropped: two row tiles per query load, TM = 2 -- 0.58 vs 0.40 ms at 256 queries; a cta_group::2
+    // pair with M = 256 -- 0.246 vs 0.210 ms; sample + thresholds + COLLECT behind a grid barrier in one launch)
     switch (g.nq) {
         case 16: return launch_gemm<16, 1, EB>(tmA, tmB, a, g.sms, stream);
         case 32: return launch_gemm<32, 1, EB>(tmA, tmB, a, g.sms, stream);
         case 64: return launch_gemm<64, 1, EB>(tmA, tmB, a, g.sms, stream);
-        case 128:
-            return tm_big == 2 ? launch_gemm<128, 2, EB>(tmA, tmB, a, g.sms, stream)
-                               : launch_gemm<128, 1, EB>(tmA, tmB, a, g.sms, stream);
-        case 256:
-            return tm_big == 2 ? launch_gemm<256, 2, EB>(tmA, tmB, a, g.sms, stream)
-                               : launch_gemm<256, 1, EB>(tmA, tmB, a, g.sms, stream);
+        case 128: return launch_gemm<128, 1, EB>(tmA, tmB, a, g.sms, stream);
+        case 256: return launch_gemm<256, 1, EB>(tmA, tmB, a, g.sms, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -1857,15 +1659,8 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, shadow ? g.shadow_base : (const void *)g.slab_base, g.slab_rows, g.dims, kTileRows, eb);
     if (e != cudaSuccess) return e;
-    // cta_group::2 variant (each SM of a pair stages half of the query operand; leader issues M = 256 MMAs):
-    // built and parity-tested, but measured SLOWER than one CTA per SM on this workload (256 queries:
-    // 0.246 vs 0.210 ms per 1 M rows; 128 queries: 0.202 vs 0.165 ms) -- ncu shows the producer blocked on a
-    // full ring and the epilogue idle, i.e. the pair's MMA stream itself runs at about half rate -- so it is off
-    // unless GF_GEMM_PAIR_MIN (smallest padded batch that uses it: 128 or 256) is set.
-    static const int pair_min = getenv("GF_GEMM_PAIR_MIN") ? atoi(getenv("GF_GEMM_PAIR_MIN")) : 1 << 30;
-    const bool pair = bf16 && g.nq >= pair_min && (g.nq == 256 || g.nq == 128) && g.tile_count >= 2 && g.sms >= 2;
     e = make_map(&tmB, shadow ? g.d_queries_shadow : (const void *)g.d_queries_padded, (uint64_t)g.nq, g.dims,
-                 (uint32_t)(pair ? g.nq / 2 : g.nq), eb);
+                 (uint32_t)g.nq, eb);
     if (e != cudaSuccess) return e;
     GemmArgs a{};
     a.segs = g.d_segs;
@@ -1901,19 +1696,9 @@ cudaError_t gemm_launch(const GemmLaunch &g, cudaStream_t stream)
         a.gtop = g.d_gtop;
         a.groups = 4u * g.tile_count;
     }
-    if (g.mode == kGemmFused) {
-        // one launch: every CTA's first tile is the sample, thresholds are computed behind a grid barrier
-        if (g.nq > 32 || g.d_sync == nullptr || g.d_thr == nullptr || g.sample_m < 1 || (int)g.tile_count < g.sms ||
-            g.sms > 160 || g.tile_stride != 1 || pair)
-            return cudaErrorInvalidValue;
-        a.thr = nullptr;
-        a.thr_out = const_cast<float *>(g.d_thr);
-        a.sync = g.d_sync;
-        a.sample_m = g.sample_m;
-    }
     if (g.tile_count < 1) return cudaSuccess;
-    if (eb == 1) return gemm_dispatch<1>(g, tmA, tmB, a, false, stream);
-    return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, pair, stream) : gemm_dispatch<4>(g, tmA, tmB, a, false, stream);
+    if (eb == 1) return gemm_dispatch<1>(g, tmA, tmB, a, stream);
+    return bf16 ? gemm_dispatch<2>(g, tmA, tmB, a, stream) : gemm_dispatch<4>(g, tmA, tmB, a, stream);
 }
 
 cudaError_t prep_queries_launch(const float *src, int64_t q_stride, int64_t l_stride, int q, int nq, int dims,

@@ -103,10 +103,9 @@ constexpr int kGemmMaxSampleTiles = 1024;
 constexpr float kTf32ErrCoeff = 2.2e-3f;  // |tf32 score - exact| <= coeff * |row| * |query| (two 10-bit truncations)
 constexpr float kAccErrCoeff = 2.5e-4f;   // fp32 accumulation inside the tensor core (the slack kTf32ErrCoeff holds too)
 constexpr float kI8ErrCoeff = 2e-6f;      // int8 pass: exact int32 accumulation, then two float roundings of the scales
-// kGemmFused: TILEMAX of each CTA's first tile + grid barrier + thresholds + COLLECT in ONE launch (nq <= 32)
 // kGemmGroupTop: ONE pass, no threshold -- per (32-row group, query) the best two approximate keys go to d_gtop;
 // grouptop_tail_kernel finds the cut (a 4096-bin histogram of score images), re-scores and certifies
-enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2, kGemmFused = 3, kGemmGroupTop = 4 };
+enum { kGemmCollect = 0, kGemmTileMax = 1, kGemmDump = 2, kGemmGroupTop = 4 };
 constexpr int kGtBins = 4096;      // histogram bins = top 12 bits of the score image (sign, exponent, 3 mantissa bits)
 constexpr int kGtCap = 1024;       // candidates re-scored per query at most
 constexpr int kGtMaxQ = 32;        // padded batch sizes that take the one-pass path
@@ -126,8 +125,6 @@ struct GemmLaunch {
     const float *d_row_scales;      // int8: one scale per slab row, block b row j at b * (block_size / 512) + j
     const float *d_q_scale;         // int8: [nq]
     int64_t block_size;             // bytes of one slab block (int8: locates a row's scale)
-    unsigned int *d_sync;           // kGemmFused: 3 zero-initialised words (count, generation, sticky timeout)
-    int sample_m;                   // kGemmFused: threshold = sample_m-th largest of the `sms` tile maxima
     int nq, q;
     int mode;
     uint32_t tile_first, tile_stride, tile_count;

@@ -324,6 +324,7 @@ Context::~gf_context()
         if (stage[i]) cudaFreeHost(stage[i]);
         if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
     }
+    if (d_add) cudaFree(d_add);
     if (mut_stream) cudaStreamDestroy(mut_stream);
     for (gf_context *c : children) delete c;  // after ws_all: a multi-device workspace hands its parts back to them
 }
@@ -535,6 +536,85 @@ int Block::insert(int64_t n, const uint8_t *values, const std::vector<std::strin
             int slot = next_index + (int)i;
             set_id(slot, ids_[nempty + i]);
             live[slot] = 1;
+        }
+        live_count += (int)tail;
+        next_index += (int)tail;
+        empty.clear();
+    } else {
+        empty.erase(empty.begin(), empty.begin() + n);
+    }
+    return GF_OK;
+}
+
+int Block::insert_staged(int64_t n, const float *d_rows, const uint8_t *d_shadow_rows, const float *d_scales,
+                         std::vector<std::string> &ids_, int64_t first, std::vector<int> *placed_rows)
+{
+    if (owner.empty() || precision != 4) return GF_ERR_INVALID_ARGUMENT;
+    if (n > margin()) return GF_ERR_BLOCK_IS_FULL;
+    if (n == 0) return GF_OK;
+    std::lock_guard<std::mutex> g(mu);
+    Context *ctx = cache->ctx;
+    int rc = ctx->bind();
+    if (rc) return rc;
+    if (implicit_ids && over.size() + (size_t)n > (size_t)capacity() / 4) materialize_ids();
+    const bool overlay = implicit_ids;
+    auto set_id = [&](int slot, std::string &&id) {
+        if (overlay) {
+            over[slot] = std::move(id);
+        } else {
+            ids[slot] = std::move(id);
+            index_add(ids[slot], slot);
+        }
+    };
+    cudaStream_t st = ctx->mut_stream;
+    const size_t rowb = (size_t)dims * 4;
+    const bool sh = shadow != nullptr && d_shadow_rows != nullptr;
+    const size_t shb = (size_t)dims * shadow_eb;  // bytes of a shadow row
+    float *my_scales = nullptr;
+    if (sh && shadow_eb == 1 && d_scales != nullptr)
+        my_scales = (float *)cache->scales->ptr + (size_t)index * ((size_t)block_size / 512);
+    const size_t nempty = empty.size();
+    const size_t refill = std::min(nempty, (size_t)n);
+    if (refill > 0) {
+        // tombstoned slots, in free-list order (block.go:93-108): one scatter kernel per array, the slot list travels
+        // through the pinned ring
+        std::lock_guard<std::mutex> sg(ctx->stage_mu);
+        if (refill * sizeof(int) > ctx->stage_bytes) return GF_ERR_INVALID_ARGUMENT;
+        GF_CUDA(cudaEventSynchronize(ctx->stage_ev[0]), GF_ERR_WRITE_CUDA_BUFFER);
+        int *slots = reinterpret_cast<int *>(ctx->stage[0]);
+        memcpy(slots, empty.data(), refill * sizeof(int));
+        GF_CUDA(scatter_rows_launch(d_rows, slots, (int)refill, dims, (float *)dev, st), GF_ERR_WRITE_CUDA_BUFFER);
+        if (sh)
+            GF_CUDA(scatter_rows_launch((const float *)d_shadow_rows, slots, (int)refill, (int)(shb / 4), (float *)shadow, st),
+                    GF_ERR_WRITE_CUDA_BUFFER);
+        if (my_scales) GF_CUDA(scatter_rows_launch(d_scales, slots, (int)refill, 1, my_scales, st), GF_ERR_WRITE_CUDA_BUFFER);
+        GF_CUDA(cudaEventRecord(ctx->stage_ev[0], st), GF_ERR_WRITE_CUDA_BUFFER);
+        ctx->stats.other_launches += 1 + (sh ? 1 : 0) + (my_scales ? 1 : 0);
+    }
+    for (size_t i = 0; i < refill; ++i) {
+        const int slot = empty[i];
+        set_id(slot, std::move(ids_[(size_t)first + i]));
+        live[slot] = 1;
+        ++live_count;
+        if (placed_rows) placed_rows->push_back(slot);
+    }
+    if ((size_t)n > nempty) {
+        const size_t tail = (size_t)n - nempty;
+        GF_CUDA(cudaMemcpyAsync(dev + (size_t)next_index * rowb, d_rows + nempty * dims, tail * rowb,
+                                cudaMemcpyDeviceToDevice, st),
+                GF_ERR_WRITE_CUDA_BUFFER);
+        if (sh)
+            GF_CUDA(cudaMemcpyAsync(shadow + (size_t)next_index * shb, d_shadow_rows + nempty * shb, tail * shb,
+                                    cudaMemcpyDeviceToDevice, st),
+                    GF_ERR_WRITE_CUDA_BUFFER);
+        if (my_scales)
+            GF_CUDA(cudaMemcpyAsync(my_scales + next_index, d_scales + nempty, tail * 4, cudaMemcpyDeviceToDevice, st),
+                    GF_ERR_WRITE_CUDA_BUFFER);
+        for (size_t i = 0; i < tail; ++i) {
+            const int slot = next_index + (int)i;
+            set_id(slot, std::move(ids_[(size_t)first + nempty + i]));
+            live[slot] = 1;
+            if (placed_rows) placed_rows->push_back(slot);
         }
         live_count += (int)tail;
         next_index += (int)tail;
@@ -901,14 +981,166 @@ static int quiesce(Context *ctx)
     return GF_OK;
 }
 
-// set.go:77-116
+// Stage `rows` float32 rows on the device and quantise their shadow there (no set lock held): the context's staging
+// area is rows | shadow rows | row scales.  Returns the three device pointers; the caller holds ctx->add_mu.
+static int stage_rows(Set *s, const uint8_t *values, int64_t rows, float **d_rows, uint8_t **d_shadow_rows,
+                      float **d_scales)
+{
+    Context *ctx = s->ctx;
+    Cache *cache = s->cache;
+    const int dims = s->dims;
+    const size_t rowb = (size_t)dims * 4;
+    const bool sh = cache->shadow != nullptr && dims % 4 == 0 && (cache->shadow_eb == 2 || dims % 128 == 0);
+    const size_t shb = sh ? (size_t)dims * cache->shadow_eb : 0;
+    const size_t o_sh = ((size_t)rows * rowb + 255) / 256 * 256;
+    const size_t o_sc = o_sh + ((size_t)rows * shb + 255) / 256 * 256;
+    const size_t need = o_sc + (size_t)rows * 4 + 256;
+    if (need > ctx->d_add_cap) {
+        if (ctx->d_add) {
+            GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CUDA);
+            cudaFree(ctx->d_add);
+            ctx->d_add = nullptr;
+            ctx->d_add_cap = 0;
+        }
+        GF_CUDA(cudaMalloc((void **)&ctx->d_add, need), GF_ERR_ALLOCATE_GPU_BUFFER);
+        ctx->d_add_cap = need;
+    }
+    *d_rows = (float *)ctx->d_add;
+    *d_shadow_rows = sh ? ctx->d_add + o_sh : nullptr;
+    *d_scales = (sh && cache->shadow_eb == 1) ? (float *)(ctx->d_add + o_sc) : nullptr;
+    int rc = ctx->upload(*d_rows, values, (size_t)rows * rowb);  // pinned ring, ends with a stream sync
+    if (rc) return rc;
+    if (sh && cache->shadow_eb == 2) {
+        GF_CUDA(shadow_rows_launch(*d_rows, rows, dims, *d_shadow_rows, s->d_small, ctx->mut_stream), GF_ERR_CUDA);
+    } else if (sh) {
+        GF_CUDA(shadow_rows_i8_launch(*d_rows, rows, dims, *d_shadow_rows, *d_scales, s->d_small, ctx->mut_stream), GF_ERR_CUDA);
+    } else {
+        GF_CUDA(rownorm_range_launch(*d_rows, rows, dims, s->d_small, ctx->mut_stream), GF_ERR_CUDA);
+    }
+    ctx->stats.other_launches++;
+    GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CUDA);
+    return GF_OK;
+}
+
+// set.go:77-116.  Three phases (see gf_set::mut_mu): (A) no set lock: rows to a device staging area through the
+// pinned ring, shadow rows + row scales + the certificate's bounds computed there; (B) exclusive lock: blocks
+// acquired, rows placed device-to-device (tombstoned slots first, in free-list order, then the tail), ids and live
+// flags set, segment table rebuilt; (C) no set lock: the id locator learns the new ids.  Searches wait for (B) only.
 int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_)
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (n == 0) return GF_OK;
     if (is_multi()) return multi_add(n, values, ids_);
+    std::lock_guard<std::mutex> mg(mut_mu);
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;  // DestroySet won
+    if (precision != 4) return add_plain(n, values, ids_);
+    int rc = ctx->bind();
+    if (rc) return rc;
+    if (!d_small) {  // (searches test this pointer: publish it under the exclusive lock)
+        unsigned int *p = nullptr;
+        GF_CUDA(cudaMalloc((void **)&p, 64), GF_ERR_ALLOCATE_GPU_BUFFER);
+        GF_CUDA(cudaMemset(p, 0, 64), GF_ERR_CUDA);
+        ExclusiveGuard g(lock);
+        d_small = p;
+    }
+    // cache.go:111-113 before anything is written: the whole request must fit
+    {
+        int64_t empty = 0;
+        for (Block *b : blocks) empty += b->margin();
+        if (n > empty) {
+            const int64_t block_length = cache->block_size / ((int64_t)dims * precision);
+            if (block_length <= 0) return GF_ERR_NOT_ENOUGH_BLOCKS;
+            const int64_t block_num = (n - empty + block_length - 1) / block_length;
+            std::lock_guard<std::mutex> cg(cache->mu);
+            int64_t free_blocks = 0;
+            for (auto &ub : cache->all_blocks)
+                if (!ub->is_owned()) ++free_blocks;
+            if (free_blocks < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
+        }
+    }
+    const size_t rowb = (size_t)dims * 4;
+    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)64 << 20) / (int64_t)rowb);  // 64 MiB of rows per chunk
+    std::vector<std::string> ids(ids_);  // moved into the blocks chunk by chunk
+    for (int64_t c0 = 0; c0 < n; c0 += chunk_rows) {
+        const int64_t cn = std::min(chunk_rows, n - c0);
+        std::lock_guard<std::mutex> ag(ctx->add_mu);
+        float *d_rows = nullptr, *d_scales = nullptr;
+        uint8_t *d_shadow_rows = nullptr;
+        rc = stage_rows(this, values + (size_t)c0 * rowb, cn, &d_rows, &d_shadow_rows, &d_scales);  // (A)
+        if (rc) return rc;
+        struct Placed {
+            int bp;
+            std::vector<int> rows;
+        };
+        std::vector<Placed> placed;
+        {
+            ExclusiveGuard g(lock);  // (B)
+            rc = quiesce(ctx);
+            if (rc) return rc;
+            int64_t empty = 0;
+            for (Block *b : blocks) empty += b->margin();
+            if (cn > empty) {
+                const int64_t block_length = cache->block_size / ((int64_t)dims * precision);
+                const int64_t block_num = (cn - empty + block_length - 1) / block_length;
+                std::vector<Block *> got;
+                {
+                    std::lock_guard<std::mutex> cg(cache->mu);
+                    for (auto &ub : cache->all_blocks) {  // cache.go:104-115
+                        if ((int64_t)got.size() == block_num) break;
+                        if (!ub->is_owned()) got.push_back(ub.get());
+                    }
+                    if ((int64_t)got.size() < block_num) return GF_ERR_NOT_ENOUGH_BLOCKS;
+                    for (size_t gi = 0; gi < got.size(); ++gi) {
+                        Block *b = got[gi];
+                        rc = b->acquire(name, dims, precision, batch);
+                        if (rc) {  // hand back what this call took: nothing may stay owned outside `blocks`
+                            for (size_t u = 0; u < gi; ++u) got[u]->release();
+                            return rc;
+                        }
+                        b->set = this;
+                        b->use_index = has_dups;
+                    }
+                }
+                blocks.insert(blocks.end(), got.begin(), got.end());
+            }
+            int64_t offset = 0, remain = cn;
+            for (size_t bp = 0; bp < blocks.size() && remain > 0; ++bp) {
+                Block *b = blocks[bp];
+                const int64_t length = std::min<int64_t>(b->margin(), remain);
+                if (length <= 0) continue;
+                // (an implicit-id block records arbitrary ids in its overlay; when the insert decides to turn it
+                // into explicit strings the locator has to learn its generated ids first)
+                if (b->implicit_ids && b->over.size() + (size_t)length > (size_t)b->capacity() / 4) materialize_block((int)bp);
+                placed.push_back(Placed{(int)bp, {}});
+                placed.back().rows.reserve((size_t)length);
+                const size_t shb = d_shadow_rows ? (size_t)dims * cache->shadow_eb : 0;
+                rc = b->insert_staged(length, d_rows + (size_t)offset * dims,
+                                      d_shadow_rows ? d_shadow_rows + (size_t)offset * shb : nullptr,
+                                      d_scales ? d_scales + offset : nullptr, ids, c0 + offset, &placed.back().rows);
+                if (rc) {
+                    rebuild_segments();
+                    return rc;
+                }
+                offset += length;
+                remain -= length;
+            }
+            rc = rebuild_segments();  // (ends with a sync of the mutation stream: the copies above are done)
+            if (rc) return rc;
+            GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
+        }
+        if (!has_dups) loc.reserve(loc.size() + (size_t)cn);
+        int64_t k = c0;  // (C) rows were placed in request order: the caller's own strings name them
+        for (const Placed &p : placed)
+            for (int row : p.rows) note_id(ids_[(size_t)k++], p.bp, row);
+    }
+    return GF_OK;
+}
+
+// the reference's own sequence for the precisions the search path does not serve (whole Add under the exclusive lock)
+int Set::add_plain(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_)
+{
     ExclusiveGuard g(lock);
-    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;  // DestroySet won the lock first
+    if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
     if (rc) return rc;
     int64_t empty = 0;
@@ -929,7 +1161,7 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
             for (size_t gi = 0; gi < got.size(); ++gi) {
                 Block *b = got[gi];
                 rc = b->acquire(name, dims, precision, batch);
-                if (rc) {  // hand back what this call took: nothing may stay owned outside `blocks`
+                if (rc) {
                     for (size_t u = 0; u < gi; ++u) got[u]->release();
                     return rc;
                 }
@@ -945,8 +1177,6 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
         Block *b = blocks[bp];
         int64_t length = std::min<int64_t>(b->margin(), remain);
         if (length > 0) {
-            // (an implicit-id block records arbitrary ids in its overlay; when Block::insert decides to turn it
-            // into explicit strings the locator has to learn its generated ids first)
             if (b->implicit_ids && b->over.size() + (size_t)length > (size_t)b->capacity() / 4) materialize_block((int)bp);
             std::vector<std::string> sub(ids_.begin() + offset, ids_.begin() + offset + length);
             const std::vector<int> refilled(b->empty.begin(),
@@ -956,13 +1186,6 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
             if (rc) {
                 rebuild_segments();
                 return rc;
-            }
-            if (refilled.size() > 8) {
-                note_rows((const float *)b->dev, b->next_index);  // one pass over the block beats a launch per slot
-            } else {
-                for (int slot : refilled) note_rows((const float *)b->dev + (size_t)slot * dims, 1);
-                if (b->next_index > tail0)
-                    note_rows((const float *)b->dev + (size_t)tail0 * dims, b->next_index - tail0);
             }
             for (size_t i = 0; i < refilled.size(); ++i) note_id(sub[i], (int)bp, refilled[i]);
             for (int64_t i = (int64_t)refilled.size(); i < length; ++i)
@@ -981,6 +1204,7 @@ int Set::add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordin
     if (precision != 4) return GF_ERR_UNSUPPORTED;
     if (n == 0) return GF_OK;
     if (is_multi()) return multi_add_synthetic(n, seed, first_ordinal, normalize, prefix);
+    std::lock_guard<std::mutex> mg(mut_mu);
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1076,12 +1300,11 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
     found.assign(ids_.size(), 0);
     if (ids_.empty()) return GF_OK;
     if (is_multi()) return multi_remove(ids_, found);
-    ExclusiveGuard g(lock);
+    std::lock_guard<std::mutex> mg(mut_mu);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
-    int rc = quiesce(ctx);
-    if (rc) return rc;
-    // set.go:163-193 walks the blocks and block.go:136-147 scans every IDs[]; the locator answers the same
-    // question (first block holding the id, last row in it) in O(1) per id
+    // (A) no set lock: which rows?  set.go:163-193 walks the blocks and block.go:136-147 scans every IDs[]; the
+    // locator answers the same question (first block holding the id, last row in it) in O(1) per id, and searches
+    // never look at it
     std::unordered_map<std::string, size_t> first;
     first.reserve(ids_.size() * 2);
     for (size_t i = 0; i < ids_.size(); ++i) first.emplace(ids_[i], i);  // a repeated id is looked up once
@@ -1094,11 +1317,16 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
         found[i] = 1;
         if (!has_dups && (!blocks[pos]->implicit_ids || blocks[pos]->over.count(row))) loc.erase(ids_[i]);
     }
+    if (per_block.empty()) return GF_OK;
     size_t nrows = 0;
     for (auto &kv : per_block) nrows += kv.second.size();
     const bool batched = nrows > 4 && precision == 4;  // one zeroing kernel instead of two memsets per row
     std::vector<unsigned long long> zero_off;
     if (batched) zero_off.reserve(nrows);
+    // (B) exclusive: tombstone (ids, live flags, free lists) and zero the rows on the device
+    ExclusiveGuard g(lock);
+    int rc = quiesce(ctx);
+    if (rc) return rc;
     for (auto &kv : per_block) {
         rc = blocks[kv.first]->remove_rows(kv.second, batched ? &zero_off : nullptr);
         if (rc) return rc;
@@ -1107,7 +1335,7 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
         rc = ctx->zero_rows((float *)cache->slab->ptr, cache->shadow ? cache->shadow->ptr : nullptr, cache->shadow_eb,
                             zero_off, dims);
         if (rc) return rc;
-    } else if (!per_block.empty()) {
+    } else {
         GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_CLEAR_CUDA_BUFFER);
     }
     return GF_OK;  // NextIndex never shrinks (block.go:159-160): the segment table is unchanged
@@ -1120,6 +1348,7 @@ int Set::update(int64_t n, const uint8_t *values, const std::vector<std::string>
     found.assign(ids_.size(), 0);
     if (n == 0) return GF_OK;
     if (is_multi()) return multi_update(n, values, ids_, found);
+    std::lock_guard<std::mutex> mg(mut_mu);
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1144,6 +1373,7 @@ int Set::read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<ui
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     found.assign(ids_.size(), 0);
     if (is_multi()) return multi_read(ids_, out, found);
+    std::lock_guard<std::mutex> mg(mut_mu);  // (the id locator is only stable between mutations)
     SharedGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = ctx->bind();
@@ -1170,6 +1400,7 @@ int Set::compact(int64_t *reclaimed)
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (precision != 4) return GF_ERR_UNSUPPORTED;
     if (is_multi()) return multi_compact(reclaimed);
+    std::lock_guard<std::mutex> mg(mut_mu);
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1282,6 +1513,7 @@ int Set::destroy()
 {
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (is_multi()) return multi_destroy();
+    std::lock_guard<std::mutex> mg(mut_mu);
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1348,9 +1580,8 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
                      int64_t l_stride, int K, bool per_segment, const unsigned long long *d_upper,
                      unsigned long long *d_out, int path, unsigned int *d_flags, bool bake_io)
 {
-    static const bool no_graphs = getenv("GF_NO_GRAPHS") != nullptr || getenv("GF_STAGE_TIMING") != nullptr;
     const bool tensor = tensor_eligible(q, K, per_segment, d_upper, path);
-    if (!tensor || q > kGemmMaxQ || no_graphs || ws->graphs_broken || ctx->profiling.load())
+    if (!tensor || q > kGemmMaxQ || ws->graphs_broken || ctx->profiling.load())
         return topk_eager(ws, stream, d_queries, q, q_stride, l_stride, K, per_segment, d_upper, d_out, path, d_flags);
     Stats &st = ctx->stats;
     const bool device_fixup = d_flags == nullptr;  // nobody to report an uncertified query to: repair it here
@@ -1475,8 +1706,6 @@ int Set::topk_device(Workspace *ws, cudaStream_t stream, const float *d_queries,
 
 bool Set::onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out) const
 {
-    // GF_ONEPASS=0 keeps the threshold + COLLECT chain everywhere
-    static const bool onepass_on = getenv("GF_ONEPASS") == nullptr || atoi(getenv("GF_ONEPASS")) != 0;
     const int seb = use_shadow(path) ? cache->shadow_eb : 0;
     const int kp = seb == 1   ? std::min(1024, std::max(K + 96, 3 * K + 64))
                    : seb == 2 ? std::min(1024, std::max(K + 64, 2 * K + 32))
@@ -1494,7 +1723,7 @@ bool Set::onepass_applies(int q, int K, int path, bool device_fixup, int *kp_out
     // profiles/r2n_onepass_sweep.txt)
     const int64_t row_limit = q <= 10 ? 12000000 : (q <= 16 ? 6000000 : 3000000);
     const bool size_ok = path == 2 || path == 3 || scanned_rows <= row_limit;
-    return onepass_on && !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && K <= kGtMaxK && kp1 <= kGtCap / 2 &&
+    return !two_pass_only(path) && !device_fixup && q <= kGtMaxQ && K <= kGtMaxK && kp1 <= kGtCap / 2 &&
            size_ok && (uint64_t)total_gtiles * 4u < (1ull << 27);
 }
 
@@ -1570,7 +1799,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     const size_t o_flags = carve((size_t)q * 4);       // right behind the keys: one copy returns both
     // One-pass path (small batches whose caller takes the certificate flags): no threshold sample -- the big
     // kernel emits the best two keys of every 32-row group + a histogram, ONE tail kernel does the rest
-    // (prep -> GROUPTOP -> tail: 3 launches instead of 6).  GF_ONEPASS=0 keeps the threshold + COLLECT chain.
+    // (prep -> GROUPTOP -> tail: 3 launches instead of 6).  Search paths 4 / 5 pin the threshold + COLLECT chain.
     int kp1 = kp;
     const bool onepass = onepass_applies(q, K, path, device_fixup, &kp1);
     const uint32_t gt_groups = total_gtiles * 4u;
@@ -1628,15 +1857,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     g.d_tilemax = d_tmax;
     g.sms = ctx->sms;
 
-    static const bool stage_timing = getenv("GF_STAGE_TIMING") != nullptr;
-    std::vector<cudaEvent_t> evs;
-    auto mark = [&]() {
-        if (!stage_timing) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, stream);
-        evs.push_back(e);
-    };
     const int fixq = std::min(kFixupMaxQ, scan_max_q(dims));
     bool flags_direct = false;
     for (int p0 = 0; p0 < q; p0 += kGemmMaxQ) {
@@ -1647,7 +1867,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         FixupPlan fix{};  // the last pass's finalize also lists the flagged queries of the whole call
         if (device_fixup && p0 + kGemmMaxQ >= q) fix = FixupPlan{d_fl, q, fixq, d_map, d_count, d_small + 1, d_ticket};
         fix.flagged = d_small + 3;
-        mark();
         // (the overlapped one-pass chain launches its own preparation into the scratch set of the step's parity)
         const bool overlap = onepass && phase == 0 && d_flags != nullptr && qp == q && !ctx->profiling.load();
         if (phase != 2 && !overlap)
@@ -1681,7 +1900,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                 g.d_queries_shadow = o_qbf;
                 g.d_q_scale = o_qsc;
             }
-            mark();
             g.mode = kGemmGroupTop;
             g.tile_first = 0;
             g.tile_stride = 1;
@@ -1694,7 +1912,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                 ctx->prof_end(stream, ev, true);
                 if (le != cudaSuccess) return cuda_fail(le, "gemm_launch", GF_ERR_CUDA);
             }
-            mark();
             GtTail t{};
             t.d_gtop = g.d_gtop;
             t.groups = gt_groups;
@@ -1750,7 +1967,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
                 g.d_queries_shadow = d_qbf;
                 g.d_q_scale = d_qsc;
             }
-            mark();
             ctx->stats.gemm_launches += 1;
             ctx->stats.other_launches += phase != 2 ? 2 : 1;  // (prep,) tail
             ctx->stats.tensor_passes++;
@@ -1758,31 +1974,13 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             continue;
         }
         const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call: it sizes d_exact
-        mark();
-        // small batches on sets where one tile per SM is a big enough sample: sample, thresholds and COLLECT
-        // are ONE launch (each CTA's first tile is the sample; thresholds behind a grid barrier)
-        // Measured: NOT faster (10 queries, int8: fused launch 0.117 ms vs 0.088 + ~0.014 ms for the three; bf16:
-        // 0.170 vs 0.157 + ~0.014 ms) -- the stream stalls behind the barrier about as long as the small sample
-        // launch takes -- so it is opt-in (GF_FUSED_SAMPLE=1) and kept for sets where launch latency dominates.
-        static const bool no_fused = getenv("GF_FUSED_SAMPLE") == nullptr;
-        const bool fuse = !no_fused && nq <= 32 && waves == 1 && G == ctx->sms && total_gtiles >= (uint32_t)ctx->sms &&
-                          ctx->sms <= 160;
         g.tile_first = 0;
-        if (!fuse) {
-            g.mode = kGemmTileMax;
-            g.tile_stride = stride;
-            g.tile_count = (uint32_t)G;
-            GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
-            mark();
-            GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
-            mark();
-        } else {
-            mark();
-            mark();
-        }
-        g.mode = fuse ? kGemmFused : kGemmCollect;
-        g.sample_m = m;
-        g.d_sync = (unsigned int *)(T + 16);  // zeroed with the head of the arena, self-resetting
+        g.mode = kGemmTileMax;
+        g.tile_stride = stride;
+        g.tile_count = (uint32_t)G;
+        GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
+        GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
+        g.mode = kGemmCollect;
         g.tile_stride = 1;
         g.tile_count = total_gtiles;
         {
@@ -1792,13 +1990,10 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             ctx->prof_end(stream, ev, true);
             if (le != cudaSuccess) return cuda_fail(le, "gemm_launch", GF_ERR_CUDA);
         }
-        mark();
         if (all) {
-            mark();
             GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, (int)cap, d_cand, d_cnt, d_exact,
                                    stream),
                     GF_ERR_CUDA);
-            mark();
             GF_CUDA(finalize_launch(d_exact, d_cand, d_cnt, d_thr, cap, (int)cap, K, qp, scanned_rows, d_qn, d_small,
                                     err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 1, fix, stream),
                     GF_ERR_CUDA);
@@ -1813,19 +2008,16 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             sn.d_maxres2_bits = d_small + 2;
             sn.d_need = d_need;
             GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp_sel, d_sel, stream, sn), GF_ERR_CUDA);
-            mark();
             GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp_sel, d_sel, nullptr, d_exact,
                                    stream, d_need),
                     GF_ERR_CUDA);
-            mark();
             GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp_sel, K, qp, scanned_rows, d_qn, d_small,
                                     err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, fix, stream,
                                     d_need),
                     GF_ERR_CUDA);
         }
-        mark();
-        ctx->stats.gemm_launches += fuse ? 1 : 2;
-        ctx->stats.other_launches += (fuse ? 3 : 4) + (all ? 0 : 1);
+        ctx->stats.gemm_launches += 2;
+        ctx->stats.other_launches += 4 + (all ? 0 : 1);
         ctx->stats.tensor_passes++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
     }
@@ -1841,19 +2033,6 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     if (device_fixup) {
         rc = topk_scan(ws, stream, d_qall, fixq, dims, 1, K, false, nullptr, d_out, d_map, d_count, true);
         if (rc) return rc;
-    }
-    mark();
-    if (stage_timing && !evs.empty()) {
-        cudaEventSynchronize(evs.back());
-        static const char *names[] = {"prep+copy", "tilemax", "threshold", "collect", "select", "rescore", "finalize", "fixup"};  // select = 0 when every candidate is re-scored
-        fprintf(stderr, "[stage us]");
-        for (size_t i = 0; i + 1 < evs.size(); ++i) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
-            fprintf(stderr, " %s=%.1f", names[i % 8], ms * 1e3);
-        }
-        fprintf(stderr, "\n");
-        for (auto e : evs) cudaEventDestroy(e);
     }
     if (d_flags && phase == 0 && !flags_direct)
         GF_CUDA(cudaMemcpyAsync(d_flags, d_fl, (size_t)q * sizeof(unsigned int), cudaMemcpyDefault, stream),
@@ -2276,22 +2455,6 @@ int Set::search(float threshold, int limit, int q, const uint8_t *queries, Resul
 // with no threshold, and hands every follower its slice with its own threshold applied
 // (set.go:145 filters after selection, so filtering a shared top-limit is exact).  While a batch
 // runs, new callers queue up and form the next batch.
-// GF_CO_TIMING=1: where a coalesced round spends its host time (printed every 256 batches to stderr)
-namespace {
-struct CoTiming {
-    bool on = getenv("GF_CO_TIMING") != nullptr;
-    double gather = 0, copy = 0, search = 0, split = 0, handoff = 0;
-    long n = 0;
-    std::chrono::steady_clock::time_point last_done;
-    bool have_last = false;
-};
-CoTiming g_cot;
-inline double us_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b)
-{
-    return std::chrono::duration<double, std::micro>(b - a).count();
-}
-}  // namespace
-
 int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *queries, Result **out)
 {
     PendingSearch me;
@@ -2337,7 +2500,6 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
             continue;
         }
         co_leader_active = true;
-        const auto t_lead = std::chrono::steady_clock::now();
         // How many callers to expect: everybody served by the previous batch is about to come back,
         // plus whoever queued up meanwhile and was not in it.  Wait for them, but never longer than
         // coalesce_wait_us: two half-size batches alternating cost twice the HBM traffic of one.
@@ -2366,8 +2528,6 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         }
         co_queued.store((int)co_queue.size(), std::memory_order_release);
         lk.unlock();
-        const auto t_gathered = std::chrono::steady_clock::now();
-        auto t_copied = t_gathered, t_searched = t_gathered;
         if (group.size() > 1) ctx->stats.coalesced_batches++;
 
         // ---- fast hand-off: one tensor-path pass, raw keys published, every caller resolves its own
@@ -2388,7 +2548,6 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
                     }
                     unsigned long long *h_keys = nullptr;
                     const int rc = direct_keys(ws, kb, total, parts.data(), part_q.data(), (int)group.size(), &h_keys);
-                    t_copied = t_searched = std::chrono::steady_clock::now();
                     std::atomic<int> resolvers{(int)group.size() - 1};
                     lk.lock();
                     const uint64_t bid = ++co_batch_id;
@@ -2427,22 +2586,6 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
             }
         }
         if (fast) {
-            if (g_cot.on) {
-                const auto t_split = std::chrono::steady_clock::now();
-                std::lock_guard<std::mutex> tg(co_mu);
-                if (g_cot.have_last) g_cot.handoff += us_between(g_cot.last_done, t_lead);
-                g_cot.gather += us_between(t_lead, t_gathered);
-                g_cot.search += us_between(t_gathered, t_searched);
-                g_cot.split += us_between(t_searched, t_split);
-                g_cot.last_done = t_searched;
-                g_cot.have_last = true;
-                if (++g_cot.n % 256 == 0) {
-                    fprintf(stderr, "[co us/batch, fast] handoff=%.1f gather=%.1f search=%.1f resolve+wait=%.1f (group %d)\n",
-                            g_cot.handoff / 256, g_cot.gather / 256, g_cot.search / 256, g_cot.split / 256,
-                            (int)group.size());
-                    g_cot.handoff = g_cot.gather = g_cot.copy = g_cot.search = g_cot.split = 0;
-                }
-            }
             break;  // me.done is set; the lock is not held
         }
 
@@ -2454,9 +2597,7 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
             off += (size_t)p->q * qbytes;
         }
         Result *all = nullptr;
-        t_copied = std::chrono::steady_clock::now();
         int rc = search_now(-INFINITY, limit, total, flat.data(), &all);
-        t_searched = std::chrono::steady_clock::now();
         int q0 = 0;
         for (PendingSearch *p : group) {
             p->rc = rc;
@@ -2477,22 +2618,6 @@ int Set::search_coalesced(float threshold, int limit, int q, const uint8_t *quer
         }
         delete all;
         lk.lock();
-        if (g_cot.on) {
-            const auto t_split = std::chrono::steady_clock::now();
-            if (g_cot.have_last) g_cot.handoff += us_between(g_cot.last_done, t_lead);
-            g_cot.gather += us_between(t_lead, t_gathered);
-            g_cot.copy += us_between(t_gathered, t_copied);
-            g_cot.search += us_between(t_copied, t_searched);
-            g_cot.split += us_between(t_searched, t_split);
-            g_cot.last_done = t_split;
-            g_cot.have_last = true;
-            if (++g_cot.n % 256 == 0) {
-                fprintf(stderr, "[co us/batch] handoff=%.1f gather=%.1f copy=%.1f search=%.1f split=%.1f (group %d)\n",
-                        g_cot.handoff / 256, g_cot.gather / 256, g_cot.copy / 256, g_cot.search / 256,
-                        g_cot.split / 256, (int)group.size());
-                g_cot.handoff = g_cot.gather = g_cot.copy = g_cot.search = g_cot.split = 0;
-            }
-        }
         const uint64_t bid = ++co_batch_id;
         co_last_group = (int)group.size();
         for (PendingSearch *p : group) p->batch_id = bid;

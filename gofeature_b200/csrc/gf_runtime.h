@@ -143,6 +143,11 @@ struct gf_context {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     std::mutex stage_mu;
+    // Add staging on the device (rows | shadow rows | row scales of one Add chunk): filled and quantised BEFORE the
+    // set's exclusive lock is taken, copied into the blocks device-to-device under it (Set::add)
+    std::mutex add_mu;
+    uint8_t *d_add = nullptr;
+    size_t d_add_cap = 0;
     Stats stats;
     // optional CUDA-event timing of the scan launches
     std::atomic<int> profiling{0};
@@ -242,6 +247,10 @@ struct gf_block {
     int release();
     // values: n rows of dims*precision bytes; ids[i] non-empty
     int insert(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
+    // the same with the rows (and their shadow rows / scales, when the cache keeps a shadow) already on the device:
+    // device-to-device copies only; ids are MOVED out of ids_[first .. first + n)
+    int insert_staged(int64_t n, const float *d_rows, const uint8_t *d_shadow_rows, const float *d_scales,
+                      std::vector<std::string> &ids_, int64_t first, std::vector<int> *placed_rows);
     int insert_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     // tombstone the rows; zero them on the device (no stream sync) or, with zero_later, only report their element
@@ -284,6 +293,11 @@ struct gf_set {
     int cap = 0;  // BlockFeatureNum (cache.go:59)
     std::vector<Block *> blocks;
     gf::RWLock lock;
+    // Mutations (Add / Delete / Update / Compact / Destroy, and Read, which walks the id locator) are serialised by
+    // mut_mu; the exclusive side of `lock` is only held while something a SEARCH reads changes (device rows inside
+    // NextIndex, ids / live flags, the segment table) -- host staging, H2D, shadow quantisation and the id locator
+    // are worked on outside it, so searches stall for microseconds, not for the length of the upload
+    std::mutex mut_mu;
     bool destroyed = false;
     int shard_rank = 0, shard_world = 1;
     // device segment table of the scanned rows, rebuilt after every mutation that moves NextIndex
@@ -361,6 +375,7 @@ struct gf_set {
     }
     int rebuild_segments();  // caller holds the exclusive lock
     int add(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
+    int add_plain(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_);
     int add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordinal, int normalize, const std::string &prefix);
     int remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &found);
     int update(int64_t n, const uint8_t *values, const std::vector<std::string> &ids_, std::vector<uint8_t> &found);

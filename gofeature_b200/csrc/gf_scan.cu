@@ -417,10 +417,6 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
         if (lists_bytes + fixed + 2 * (size_t)kScanTileBytes > kSmemLimit) return cudaErrorInvalidValue;
         int st = (int)((kSmemLimit - fixed - lists_bytes) / kScanTileBytes);
         p.stages = st > 7 ? 7 : st;
-        if (const char *e = getenv("GF_SCAN_STAGES")) {  // tuning knob
-            int v = atoi(e);
-            if (v >= 2 && v <= p.stages) p.stages = v;
-        }
         p.smem_bytes = (size_t)p.stages * kScanTileBytes + fixed + lists_bytes;
     } else {
         p.tile_rows = 64;
