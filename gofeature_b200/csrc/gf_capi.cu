@@ -310,6 +310,10 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
     out->host_wait_ns = s.host_wait_ns;
     out->host_resolve_ns = s.host_resolve_ns;
     out->host_calls = s.host_calls;
+    out->add_stage_ns = s.add_stage_ns;
+    out->add_place_ns = s.add_place_ns;
+    out->add_index_ns = s.add_index_ns;
+    out->add_rows = s.add_rows;
     out->searches = s.searches;
     out->scan_launches = s.scan_launches;
     out->gemm_launches = s.gemm_launches;
@@ -335,6 +339,7 @@ int gf_context_reset_stats(gf_context *ctx)
     s.tensor_passes = s.uncertified_queries = 0;
     s.gemm_kernel_ns = s.gemm_kernel_timed = 0;
     s.host_stage_ns = s.host_launch_ns = s.host_wait_ns = s.host_resolve_ns = s.host_calls = 0;
+    s.add_stage_ns = s.add_place_ns = s.add_index_ns = s.add_rows = 0;
     return GF_OK;
 }
 

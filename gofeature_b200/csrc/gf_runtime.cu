@@ -171,6 +171,75 @@ void Context::release_ws(Workspace *w)
     ws_free.push_back(w);
 }
 
+// ---- parallel host copy into the pinned ring
+struct CopyPool {
+    static constexpr int kHelpers = 3;
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    std::thread th[kHelpers];
+    uint8_t *dst = nullptr;
+    const uint8_t *src = nullptr;
+    size_t part = 0, bytes = 0;
+    uint64_t gen = 0;
+    int left = 0;
+    bool stop = false;
+    CopyPool()
+    {
+        for (int i = 0; i < kHelpers; ++i)
+            th[i] = std::thread([this, i]() {
+                uint64_t seen = 0;
+                std::unique_lock<std::mutex> lk(mu);
+                for (;;) {
+                    cv_start.wait(lk, [&] { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    const size_t off = (size_t)(i + 1) * part;
+                    const size_t n = off < bytes ? std::min(part, bytes - off) : 0;
+                    uint8_t *d = dst + off;
+                    const uint8_t *s = src + off;
+                    lk.unlock();
+                    if (n) memcpy(d, s, n);
+                    lk.lock();
+                    if (--left == 0) cv_done.notify_one();
+                }
+            });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            stop = true;
+        }
+        cv_start.notify_all();
+        for (auto &t : th) t.join();
+    }
+    void run(void *d, const void *s, size_t n)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        dst = (uint8_t *)d;
+        src = (const uint8_t *)s;
+        bytes = n;
+        part = (n / (kHelpers + 1) + 63) / 64 * 64;
+        left = kHelpers;
+        ++gen;
+        cv_start.notify_all();
+        lk.unlock();
+        memcpy(d, s, std::min(part, n));
+        lk.lock();
+        cv_done.wait(lk, [&] { return left == 0; });
+    }
+};
+
+void Context::parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    if (bytes < ((size_t)1 << 20)) {  // small copies: the hand-off costs more than it saves
+        memcpy(dst, src, bytes);
+        return;
+    }
+    if (!copy_pool) copy_pool = new CopyPool();  // (callers hold stage_mu)
+    copy_pool->run(dst, src, bytes);
+}
+
 int Context::upload(void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return GF_OK;
@@ -181,7 +250,7 @@ int Context::upload(void *dst, const void *src, size_t bytes)
         size_t n = std::min(stage_bytes, bytes - off);
         int i = k & 1;
         GF_CUDA(cudaEventSynchronize(stage_ev[i]), GF_ERR_WRITE_CUDA_BUFFER);
-        memcpy(stage[i], (const uint8_t *)src + off, n);
+        parallel_copy(stage[i], (const uint8_t *)src + off, n);
         GF_CUDA(cudaMemcpyAsync((uint8_t *)dst + off, stage[i], n, cudaMemcpyHostToDevice, mut_stream),
                 GF_ERR_WRITE_CUDA_BUFFER);
         GF_CUDA(cudaEventRecord(stage_ev[i], mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
@@ -324,6 +393,7 @@ Context::~gf_context()
         if (stage[i]) cudaFreeHost(stage[i]);
         if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
     }
+    delete copy_pool;
     if (d_add) cudaFree(d_add);
     if (mut_stream) cudaStreamDestroy(mut_stream);
     for (gf_context *c : children) delete c;  // after ws_all: a multi-device workspace hands its parts back to them
@@ -1066,8 +1136,10 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
         std::lock_guard<std::mutex> ag(ctx->add_mu);
         float *d_rows = nullptr, *d_scales = nullptr;
         uint8_t *d_shadow_rows = nullptr;
+        const auto t_a = std::chrono::steady_clock::now();
         rc = stage_rows(this, values + (size_t)c0 * rowb, cn, &d_rows, &d_shadow_rows, &d_scales);  // (A)
         if (rc) return rc;
+        const auto t_b = std::chrono::steady_clock::now();
         struct Placed {
             int bp;
             std::vector<int> rows;
@@ -1128,10 +1200,19 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
             if (rc) return rc;
             GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
         }
+        const auto t_c = std::chrono::steady_clock::now();
         if (!has_dups) loc.reserve(loc.size() + (size_t)cn);
         int64_t k = c0;  // (C) rows were placed in request order: the caller's own strings name them
         for (const Placed &p : placed)
             for (int row : p.rows) note_id(ids_[(size_t)k++], p.bp, row);
+        const auto t_d = std::chrono::steady_clock::now();
+        auto ns = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
+            return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count();
+        };
+        ctx->stats.add_stage_ns += ns(t_a, t_b);
+        ctx->stats.add_place_ns += ns(t_b, t_c);
+        ctx->stats.add_index_ns += ns(t_c, t_d);
+        ctx->stats.add_rows += (uint64_t)cn;
     }
     return GF_OK;
 }

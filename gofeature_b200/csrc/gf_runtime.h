@@ -65,7 +65,8 @@ struct Stats {
     std::atomic<uint64_t> searches{0}, scan_launches{0}, gemm_launches{0}, merge_launches{0}, other_launches{0},
         rows_scanned{0}, quirk_fallbacks{0}, coalesced_batches{0}, h2d_bytes{0}, d2h_bytes{0}, scan_kernel_ns{0},
         scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0}, gemm_kernel_ns{0}, gemm_kernel_timed{0},
-        host_stage_ns{0}, host_launch_ns{0}, host_wait_ns{0}, host_resolve_ns{0}, host_calls{0};
+        host_stage_ns{0}, host_launch_ns{0}, host_wait_ns{0}, host_resolve_ns{0}, host_calls{0},
+        add_stage_ns{0}, add_place_ns{0}, add_index_ns{0}, add_rows{0};
 };
 
 // per-search scratch: a stream, device and pinned arenas
@@ -148,6 +149,10 @@ struct gf_context {
     std::mutex add_mu;
     uint8_t *d_add = nullptr;
     size_t d_add_cap = 0;
+    // helper threads of upload(): the copy from the caller's pageable rows into the pinned ring is what bounds Add
+    // (one core copies ~8 GB/s, the link takes ~50): three parked helpers + the caller split every chunk
+    struct CopyPool *copy_pool = nullptr;
+    void parallel_copy(void *dst, const void *src, size_t bytes);
     Stats stats;
     // optional CUDA-event timing of the scan launches
     std::atomic<int> profiling{0};
@@ -298,7 +303,7 @@ struct gf_set {
     // NextIndex, ids / live flags, the segment table) -- host staging, H2D, shadow quantisation and the id locator
     // are worked on outside it, so searches stall for microseconds, not for the length of the upload
     std::mutex mut_mu;
-    bool destroyed = false;
+    std::atomic<bool> destroyed{false};  // read before any lock is taken (TSAN: tools/race_test)
     int shard_rank = 0, shard_world = 1;
     // device segment table of the scanned rows, rebuilt after every mutation that moves NextIndex
     std::vector<Segment> h_segs;
@@ -312,7 +317,7 @@ struct gf_set {
     unsigned int *d_small = nullptr;  // [0] max |row|^2 bits, [1] queries the flag-less device call could not repair, [2] max |shadow(row) - row|^2 bits, [3] queries the certificate refused
     bool tensor_ok = false;
     bool shadow_ok = false;   // the shadow of this set's rows is maintained and usable by the tensor path
-    int search_path = 0;      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32, 4 / 5 = 2 / 3 without the one-pass chain
+    std::atomic<int> search_path{0};      // path the host Search takes (gf_set_set_search_path): 0 choose, 1 scan, 2 tensor, 3 tensor tf32, 4 / 5 = 2 / 3 without the one-pass chain
     uint64_t version = 0;  // bumped whenever the segment table or the shard identity changes
     uint32_t total_tiles = 0;
     int64_t scanned_rows = 0;
@@ -336,7 +341,7 @@ struct gf_set {
     void enter_dup_mode();
     void materialize_block(int pos);
     // coalescer
-    int coalesce_wait_us = 0;
+    std::atomic<int> coalesce_wait_us{0};
     std::mutex co_mu;
     std::condition_variable co_cv;
     std::vector<gf::PendingSearch *> co_queue;

@@ -375,6 +375,13 @@ typedef struct gf_stats {
     uint64_t host_wait_ns;
     uint64_t host_resolve_ns;
     uint64_t host_calls;
+    /* where Set.Add spends its wall time, summed over add_rows rows: staging (host -> pinned -> device, shadow
+     * quantisation; no set lock), placement (the set's exclusive lock: device-to-device copies, ids, segment table),
+     * id locator (no set lock) */
+    uint64_t add_stage_ns;
+    uint64_t add_place_ns;
+    uint64_t add_index_ns;
+    uint64_t add_rows;
 } gf_stats;
 GF_API int gf_context_stats(const gf_context *ctx, gf_stats *out);
 GF_API int gf_context_reset_stats(gf_context *ctx);

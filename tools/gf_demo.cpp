@@ -228,6 +228,9 @@ int main(int argc, char **argv)
            n_adds.load(), rows_added.load(), add_us.load() ? rows_added.load() / (add_us.load() / 1e6) : 0.0,
            n_dels.load(), n_deleted.load(),
            del_us.load() ? (double)n_dels.load() * del_size / (del_us.load() / 1e6) : 0.0);
+    printf("\"add_stage_us_per_krow\": %.1f, \"add_place_us_per_krow\": %.1f, \"add_index_us_per_krow\": %.1f, ",
+           st.add_rows ? st.add_stage_ns / 1e3 / (st.add_rows / 1e3) : 0.0, st.add_rows ? st.add_place_ns / 1e3 / (st.add_rows / 1e3) : 0.0,
+           st.add_rows ? st.add_index_ns / 1e3 / (st.add_rows / 1e3) : 0.0);
     printf("\"scan_launches\": %llu, \"tensor_passes\": %llu, \"coalesced_batches\": %llu, \"quirk_fallbacks\": %llu, "
            "\"uncertified_queries\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"self_check\": \"%s\"}\n",
            (unsigned long long)st.scan_launches, (unsigned long long)st.tensor_passes,
