@@ -19,9 +19,13 @@ import "C"
 
 import (
 	"errors"
+	"runtime"
 	"unsafe"
 )
 
+// errFromStatus maps a status code onto the error.go sentinels.  Codes >= 100 carry a detail string that the
+// library keeps PER OS THREAD (gf_last_error_detail): a goroutine may migrate between the failing call and the
+// fetch, so callers that can fail with such a code wrap both in withThread (runtime.LockOSThread).
 func errFromStatus(st C.int) error {
 	if st == 0 {
 		return nil
@@ -30,6 +34,13 @@ func errFromStatus(st C.int) error {
 		return statusTable[st]
 	}
 	return errors.New(C.GoString(C.gf_strerror(st)) + ": " + C.GoString(C.gf_last_error_detail()))
+}
+
+// withThread runs one C call and the translation of its status on the same OS thread.
+func withThread(call func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	return errFromStatus(call())
 }
 
 // Context replaces *cuda.Context (search_test.go:40: cuda.NewContext(devices[0], -1)).
@@ -51,7 +62,26 @@ func AllDevices() ([]int, error) {
 // NewContext replaces cuda.NewContext.
 func NewContext(device int, _ int) (*Context, error) {
 	c := &Context{}
-	if err := errFromStatus(C.gf_context_create(C.int(device), &c.h)); err != nil {
+	if err := withThread(func() C.int { return C.gf_context_create(C.int(device), &c.h) }); err != nil {
+		return nil, err
+	}
+	return c, nil
+}
+
+// NewContextMulti : one context over several devices of this process (gf_context_create_multi).  A cache created
+// on it stripes its blocks over the devices (block i on devices[i % n], the order GetEmptyBlock hands them out,
+// cache.go:104-115), Set.Search scans all of them and returns one merged, id-resolved result; everything else of
+// the Cache / Set API is unchanged.  The reference has no counterpart (cache.go:21-43 builds on one context).
+func NewContextMulti(devices []int) (*Context, error) {
+	if len(devices) == 0 {
+		return nil, ErrInvalidDeviceID
+	}
+	ds := make([]C.int, len(devices))
+	for i, d := range devices {
+		ds[i] = C.int(d)
+	}
+	c := &Context{}
+	if err := withThread(func() C.int { return C.gf_context_create_multi(&ds[0], C.int(len(ds)), &c.h) }); err != nil {
 		return nil, err
 	}
 	return c, nil
@@ -95,8 +125,8 @@ func NewCache(ctx *Context, blockNum, blockSize int) (Cache, error) {
 	return c, nil
 }
 
-// NewCacheNoShadow : NewCache without the bf16 shadow slab (blockSize/2 fewer bytes per block; the
-// tensor path then streams the float32 rows).  Results are identical either way.
+// NewCacheNoShadow : NewCache without the shadow slab (by default int8 rows + one float scale per row: blockSize/4 +
+// blockSize/128 more bytes per block; the tensor path then streams the float32 rows).  Results are identical either way.
 func NewCacheNoShadow(ctx *Context, blockNum, blockSize int) (Cache, error) {
 	c := &cache{ctx: ctx}
 	if err := errFromStatus(C.gf_cache_create_ex(ctx.h, C.int(blockNum), C.int64_t(blockSize),
