@@ -227,6 +227,12 @@ class ShardedSet:
 
     # ---- mutation (collective: every rank passes the same arguments)
     def Add(self, values, ids):
+        """ids longer than ID_WIDTH bytes are rejected (the id exchange of `Search` carries fixed-width ids; the
+        in-library multi-device set, gf_context_create_multi, has no such limit).  A duplicate id is deleted by
+        `Delete` on EVERY rank that holds it, whereas one set deletes only its first occurrence (set.go:163-193)."""
+        for i in ids:
+            if len(i.encode() if isinstance(i, str) else bytes(i)) > ID_WIDTH:
+                raise api.GoFeatureError(api.ErrInvalidFeautres)
         values = np.ascontiguousarray(values, dtype=np.float32).reshape(len(ids), self.dims)
         for r, a, b in split_rows(self.total_rows, len(ids), self.cap, self.world):
             if r == self.rank:
