@@ -26,7 +26,8 @@ class gf_stats(ctypes.Structure):
                                      "h2d_bytes", "d2h_bytes", "scan_kernel_ns", "scan_kernel_timed",
                                      "tensor_passes", "uncertified_queries", "gemm_kernel_ns", "gemm_kernel_timed",
                                      "host_stage_ns", "host_launch_ns", "host_wait_ns", "host_resolve_ns",
-                                     "host_calls", "add_stage_ns", "add_place_ns", "add_index_ns", "add_rows")]
+                                     "host_calls", "add_stage_ns", "add_place_ns", "add_index_ns", "add_rows",
+                                     "tier2_queries")]
 
 
 # name -> (restype, argtypes); every symbol include/gofeature_b200.h declares

@@ -288,6 +288,7 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
         out->coalesced_batches += p.coalesced_batches;
         out->quirk_fallbacks += p.quirk_fallbacks;
         out->uncertified_queries += p.uncertified_queries;
+        out->tier2_queries += p.tier2_queries;
         out->h2d_bytes += p.h2d_bytes;
         out->d2h_bytes += p.d2h_bytes;
         out->host_stage_ns = p.host_stage_ns;  // (the parent's call, not the shards')
@@ -314,6 +315,7 @@ int gf_context_stats(const gf_context *ctx, gf_stats *out)
     out->add_place_ns = s.add_place_ns;
     out->add_index_ns = s.add_index_ns;
     out->add_rows = s.add_rows;
+    out->tier2_queries = s.tier2_queries;
     out->searches = s.searches;
     out->scan_launches = s.scan_launches;
     out->gemm_launches = s.gemm_launches;
@@ -340,6 +342,7 @@ int gf_context_reset_stats(gf_context *ctx)
     s.gemm_kernel_ns = s.gemm_kernel_timed = 0;
     s.host_stage_ns = s.host_launch_ns = s.host_wait_ns = s.host_resolve_ns = s.host_calls = 0;
     s.add_stage_ns = s.add_place_ns = s.add_index_ns = s.add_rows = 0;
+    s.tier2_queries = 0;
     return GF_OK;
 }
 

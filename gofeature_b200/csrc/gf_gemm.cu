@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     static_assert(!RESB || TM == 1, "resident query operand: one tile per step");
     using Cfg = GemmCfg<NQ, TM, RESB>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem_al = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (aligned by an OFFSET from the shared-memory symbol: rounding the generic address through an integer made every
+    // access below a generic LD.E / ST.E / ATOM.E instead of LDS / STS / ATOMS)
+    uint8_t *smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *res_b = smem_al;                        // RESB: [K block][NQ rows][128 B], each K block a TMA box
     uint8_t *smem = smem_al + Cfg::kResBytes;        // the stage ring
     uint8_t *tail = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
@@ -383,6 +385,21 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // COLLECT over int8 accumulators: the smallest threshold of every 8 query columns (the epilogue's group test);
+    // the tile-maximum words are not used in this mode
+    float *thrmin_s = reinterpret_cast<float *>(tmax_s);
+    if (EB == 1 && a.mode == 0) {
+        for (int g = threadIdx.x; g < NQ / 8; g += blockDim.x) {
+            float m = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = thr_s[8 * g + j];
+                m = (t < m || t != t) ? t : m;  // (a NaN threshold sticks: the group test then always passes on)
+            }
+            thrmin_s[g] = m;
+        }
+        __syncthreads();
+    }
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -489,7 +506,9 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
             // the wait for the accumulators comes AFTER this tile's segment / slot / row-scale loads have been
             // issued (the epilogue is the critical path at large batches: their latency hides behind the wait)
             bool waited = false, released = false;
-            const int mode = a.mode;
+            // (three flags instead of `switch (mode)`: the compiler turned the chain of comparisons into a jump table,
+            // an indirect branch per chunk of columns in the hottest loop)
+            const bool m_collect = a.mode == 0, m_tilemax = a.mode == 1, m_grouptop = a.mode == 4;
 #pragma unroll 1
             for (int j = 0; j < TM; ++j) {
                 const uint32_t i = g * TM + j;
@@ -515,52 +534,143 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     tc_fence_after();
                     waited = true;
                 }
+                // COLLECT: fixed per-query threshold, the rare survivor is staged and appended later.
+                // A survivor is staged RAW -- (float(acc) * row scale, slot, query) -- and becomes a key when
+                // the warp flushes its stage, one lane per entry.
+                auto stage_raw = [&](float sc_raw, int qi) {
+                    const int sp = atomicAdd(&stage_n[wslot], 1);
+                    if (sp < kAppendPerWarp) {
+                        stage_key[wslot * kAppendPerWarp + sp] =
+                            ((unsigned long long)slot << 32) | (unsigned long long)__float_as_uint(sc_raw);
+                        stage_q[wslot * kAppendPerWarp + sp] = qi;
+                    } else {  // stage full (a burst of survivors): append directly
+                        const float sc = EB == 1 ? sc_raw * qs_s[qi] : sc_raw;
+                        const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
+                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
+                    }
+                };
+                if constexpr (EB == 1 && TM == 1) {
+                    if (m_collect) {
+                        // int8 COLLECT.  (1) ALL of this warp's columns go to registers and the accumulator set is
+                        // released at once: held for the whole epilogue, it made the MMAs of tile i+2 wait for the
+                        // epilogue of tile i, the ring filled up and drained in bursts, and a 5-stage ring cannot
+                        // cover the HBM latency of bursts (256 queries: 2.5 us per tile for 1.3 us of MMAs).
+                        // (2) score > threshold  <=>  sign of fma(-float(acc), row scale, threshold').  Survivors
+                        // are ~8e-4 of the scores, so the test runs on the MAXIMUM of 8 accumulators against the
+                        // smallest of their 8 thresholds first: the integer maximum is 4 instructions per 8 scores
+                        // (VIMNMX3), the float test 3 per group, against I2F + FFMA + SHF per score.
+                        // float_ru(max) >= float_rn(acc), min threshold <= threshold, row scale >= 0 and the single
+                        // rounding of the fma make the group test a superset of the per-score test (monotone);
+                        // `!(t > 0)` also passes -0 and NaN on.  A group that passes (every fourth) re-tests its
+                        // scores exactly as before, after an integer pre-compare against a conservative bound.
+                        static_assert(kColsPerWarp % 8 == 0 && kColsPerWarp <= 64, "groups of 8 columns, in registers");
+                        uint32_t r[kColsPerWarp];
+#pragma unroll
+                        for (int c = 0; c < kColsPerWarp; c += Cfg::kChunk)
+                            tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + col_first + c,
+                                                 reinterpret_cast<uint32_t(&)[Cfg::kChunk]>(r[c]));
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[buf]);
+                        released = true;
+                        // group tests, branch-free: bit g of `trig` = group g may hold a survivor of this row
+                        unsigned trig = 0;
+#pragma unroll
+                        for (int g = 0; g < kColsPerWarp / 8; ++g) {
+                            const int b = 8 * g;
+                            int m = __vimax3_s32((int)r[b], (int)r[b + 1], (int)r[b + 2]);
+                            const int m2 = __vimax3_s32((int)r[b + 3], (int)r[b + 4], (int)r[b + 5]);
+                            m = __vimax3_s32(m, (int)r[b + 6], (int)r[b + 7]);
+                            m = max(m, m2);
+                            const float tp = __fmaf_rn(-__int2float_ru(m), rs, thrmin_s[(col_first >> 3) + g]);
+                            trig |= (tp > 0.f) ? 0u : (1u << g);
+                        }
+                        if (!live) trig = 0;
+                        // the rare group that passed: its 8 accumulators move to a common set of registers (ONE copy
+                        // of the code below for all groups -- unrolled per group, with the survivor path inline, the
+                        // kernel was 6 760 instructions and spent two thirds of its time in instruction-cache misses)
+                        while (trig) {
+                            const int g = __ffs(trig) - 1;
+                            trig &= trig - 1;
+                            uint32_t v[8];
+                            switch (g) {
+#define GF_PICK(G)                                                      \
+    case G:                                                             \
+        if constexpr (8 * G < kColsPerWarp) {                           \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = r[(8 * G + j) % kColsPerWarp]; \
+        }                                                               \
+        break;
+                                GF_PICK(0) GF_PICK(1) GF_PICK(2) GF_PICK(3) GF_PICK(4) GF_PICK(5) GF_PICK(6)
+                                default:
+                                    if constexpr (56 < kColsPerWarp) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[j] = r[(56 + j) % kColsPerWarp];
+                                    }
+                                    break;
+#undef GF_PICK
+                            }
+                            const int cg = col_first + 8 * g;
+                            const float4 tha = *reinterpret_cast<const float4 *>(thr_s + cg);
+                            const float4 thb = *reinterpret_cast<const float4 *>(thr_s + cg + 4);
+                            const float th[8] = {tha.x, tha.y, tha.z, tha.w, thb.x, thb.y, thb.z, thb.w};
+                            unsigned pass = 0;  // column j of the group -> bit 7 - j
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                pass = __funnelshift_l(__float_as_uint(__fmaf_rn(-__int2float_rn((int)v[j]), rs, th[j])),
+                                                       pass, 1);
+                            while (pass) {
+                                const int bit = __ffs(pass) - 1;
+                                pass &= pass - 1;
+                                const int j = 7 - bit;
+                                uint32_t acc = v[0];
+#pragma unroll
+                                for (int jj = 1; jj < 8; ++jj)
+                                    if (jj == j) acc = v[jj];
+                                stage_raw(__int2float_rn((int)acc) * rs, cg + j);
+                            }
+                        }
+                        continue;  // (TM == 1: the tile is done)
+                    }
+                }
 #pragma unroll 1
                 for (int c0 = col_first; c0 < col_first + kColsPerWarp; c0 += Cfg::kChunk) {
                     uint32_t r[Cfg::kChunk];
                     tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + c0, r);
                     tmem_ld_wait();
-                    if (mode == 0) {
-                        // COLLECT: fixed per-query threshold, atomic append of the rare survivor
-                        // score > threshold  <=>  sign of (threshold - score); the sign bits are shifted into
-                        // `pass` one per score (column jj ends up in bit kChunk-1-jj): 3 instructions per score
-                        // (I2F, FFMA, SHF) for int8, 2 (FADD, SHF) for float accumulators
-                        unsigned pass = 0;
-                        const float4 *thr4 = reinterpret_cast<const float4 *>(thr_s + c0);  // 16-byte aligned
-                        auto below = [&](uint32_t bits, float th) -> uint32_t {
-                            const float t = EB == 1 ? __fmaf_rn(-__int2float_rn((int)bits), rs, th)
-                                                    : __fadd_rn(th, -__uint_as_float(bits));
-                            return __float_as_uint(t);
-                        };
+                    if (m_collect) {
+                        if constexpr (EB == 1) {
+                            // (int8 COLLECT runs before this loop: all columns in registers, accumulator released)
+                        } else {
+                            // float accumulators: score > threshold  <=>  sign of (threshold - score); the sign bits
+                            // are shifted into `pass` one per score (column jj ends up in bit kChunk-1-jj): 2
+                            // instructions per score (FADD, SHF)
+                            unsigned pass = 0;
+                            const float4 *thr4 = reinterpret_cast<const float4 *>(thr_s + c0);  // 16-byte aligned
+                            auto below = [&](uint32_t bits, float th) -> uint32_t {
+                                return __float_as_uint(__fadd_rn(th, -__uint_as_float(bits)));
+                            };
 #pragma unroll
-                        for (int jj = 0; jj < Cfg::kChunk; jj += 4) {
-                            const float4 th = thr4[jj >> 2];
-                            pass = __funnelshift_l(below(r[jj + 0], th.x), pass, 1);
-                            pass = __funnelshift_l(below(r[jj + 1], th.y), pass, 1);
-                            pass = __funnelshift_l(below(r[jj + 2], th.z), pass, 1);
-                            pass = __funnelshift_l(below(r[jj + 3], th.w), pass, 1);
-                        }
-                        if (!live) pass = 0;
-                        while (pass) {
-                            const int bit = __ffs(pass) - 1;
-                            pass &= pass - 1;
-                            const int b = Cfg::kChunk - 1 - bit;
-                            float sc = 0.f;
+                            for (int jj = 0; jj < Cfg::kChunk; jj += 4) {
+                                const float4 th = thr4[jj >> 2];
+                                pass = __funnelshift_l(below(r[jj + 0], th.x), pass, 1);
+                                pass = __funnelshift_l(below(r[jj + 1], th.y), pass, 1);
+                                pass = __funnelshift_l(below(r[jj + 2], th.z), pass, 1);
+                                pass = __funnelshift_l(below(r[jj + 3], th.w), pass, 1);
+                            }
+                            if (!live) pass = 0;
+                            while (pass) {
+                                const int bit = __ffs(pass) - 1;
+                                pass &= pass - 1;
+                                const int b = Cfg::kChunk - 1 - bit;
+                                float sc = 0.f;
 #pragma unroll
-                            for (int jj = 0; jj < Cfg::kChunk; ++jj)
-                                if (jj == b) sc = val(r[jj]);
-                            const int qi = c0 + b;
-                            if (EB == 1) sc *= qs_s[qi];
-                            const int sp = atomicAdd(&stage_n[wslot], 1);
-                            if (sp < kAppendPerWarp) {
-                                stage_key[wslot * kAppendPerWarp + sp] = make_key(sc, slot);
-                                stage_q[wslot * kAppendPerWarp + sp] = qi;
-                            } else {  // stage full (a burst of survivors): append directly
-                                const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
-                                if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, slot);
+                                for (int jj = 0; jj < Cfg::kChunk; ++jj)
+                                    if (jj == b) sc = val(r[jj]);
+                                stage_raw(sc, c0 + b);
                             }
                         }
-                    } else if (mode == 1) {
+                    } else if (m_tilemax) {
                         // TILEMAX: per query the best score of this tile (threshold estimation sample)
                         float v[Cfg::kChunk];
 #pragma unroll
@@ -583,7 +693,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         for (; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
                         const int col = c0 + (lane >> (Cfg::kChunk == 32 ? 0 : 1));
                         if (Cfg::kChunk == 32 || (lane & 1) == 0) atomicMax(&tmax_s[col], score_image(m));
-                    } else if (mode == 4) {
+                    } else if (m_grouptop) {
                         if constexpr (NQ <= kGtMaxQ && TM == 1) {
                             // the scores are in registers (one chunk holds all NQ columns): release the accumulator
                             // NOW -- an arrive (release) issued after the global store / histogram atomic below
@@ -664,7 +774,7 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                         }
                     }
                 }
-                if (mode == 1) {
+                if (m_tilemax) {
                     named_bar_sync(2, kEpiThreads);
                     for (int c = threadIdx.x - 64; c < NQ; c += kEpiThreads) {
                         a.tilemax[(size_t)i * NQ + c] = image_score(tmax_s[c]);
@@ -691,8 +801,11 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     const int n = staged < kAppendPerWarp ? staged : kAppendPerWarp;
                     if (lane < n) {
                         const int qi = stage_q[wslot * kAppendPerWarp + lane];
+                        const unsigned long long raw = stage_key[wslot * kAppendPerWarp + lane];
+                        float sc = __uint_as_float((uint32_t)raw);
+                        if (EB == 1) sc *= qs_s[qi];
                         const unsigned pos = atomicAdd(&a.cnt[qi], 1u);
-                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = stage_key[wslot * kAppendPerWarp + lane];
+                        if (pos < a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc, (uint32_t)(raw >> 32));
                     }
                     __syncwarp();
                     if (lane == 0) stage_n[wslot] = 0;
@@ -1064,6 +1177,40 @@ __device__ __forceinline__ float cert_delta(int qi, const float *qnorm2, const u
     return delta;
 }
 
+// the last CTA of a call's last finalize / tail launch lists the flagged queries for the fix-up scan
+__device__ __forceinline__ void fixup_list(const FixupPlan &fix)
+{
+    if (fix.flags_all == nullptr) return;
+    __shared__ unsigned int s_ticket;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_ticket = atomicAdd(fix.ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    if (threadIdx.x < 32) {
+        __threadfence();
+        const int lane = threadIdx.x;
+        int n = 0;
+        for (int base = 0; base < fix.q_total; base += 32) {
+            const int i = base + lane;
+            const bool f = i < fix.q_total && __ldcg(fix.flags_all + i) != 0u;
+            const unsigned ball = __ballot_sync(0xffffffffu, f);
+            const int pos = n + __popc(ball & ((1u << lane) - 1u));
+            if (f && pos < fix.maxn) {
+                fix.map[pos] = i;
+                fix.flags_all[i] = 0u;
+            }
+            n += __popc(ball);
+        }
+        if (lane == 0) {
+            *fix.count = (unsigned)(n < fix.maxn ? n : fix.maxn);
+            if (n > fix.maxn) atomicAdd(fix.uncertified, (unsigned)(n - fix.maxn));
+            *fix.ticket = 0u;
+        }
+    }
+}
+
 // per query: sort the re-scored keys, emit the best K, and certify: the K-th exact score must beat
 // everything a row outside the re-scored set could reach (its approx ceiling + the TF32 error bound).
 //   all == 0: d_exact [q][kp] holds the best kp candidates by approx score (select_kernel)
@@ -1122,36 +1269,7 @@ __global__ void __launch_bounds__(256)
         d_flags[qi] = ok ? 0u : 1u;  // flagged queries are re-run by the exact scan
         if (!ok && fix.flagged != nullptr) atomicAdd(fix.flagged, 1u);
     }
-    if (fix.flags_all == nullptr) return;
-    // the last CTA of the call's last finalize launch lists the flagged queries for the fix-up scan
-    __shared__ unsigned int s_ticket;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_ticket = atomicAdd(fix.ticket, 1u);
-    }
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    if (threadIdx.x < 32) {
-        __threadfence();
-        const int lane = threadIdx.x;
-        int n = 0;
-        for (int base = 0; base < fix.q_total; base += 32) {
-            const int i = base + lane;
-            const bool f = i < fix.q_total && __ldcg(fix.flags_all + i) != 0u;
-            const unsigned ball = __ballot_sync(0xffffffffu, f);
-            const int pos = n + __popc(ball & ((1u << lane) - 1u));
-            if (f && pos < fix.maxn) {
-                fix.map[pos] = i;
-                fix.flags_all[i] = 0u;
-            }
-            n += __popc(ball);
-        }
-        if (lane == 0) {
-            *fix.count = (unsigned)(n < fix.maxn ? n : fix.maxn);
-            if (n > fix.maxn) atomicAdd(fix.uncertified, (unsigned)(n - fix.maxn));
-            *fix.ticket = 0u;
-        }
-    }
+    fixup_list(fix);
 }
 
 // best kp keys of an unsorted candidate buffer: one CTA per query
@@ -1203,6 +1321,113 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) d_need[qi] = (unsigned int)need;
 }
 
+
+// ------------------------------------------------------------------ two-pass chain: the fused tail (gf_kernels.h)
+__global__ void __launch_bounds__(256) collect_tail_kernel(const CollectTail a, const FixupPlan fix)
+{
+    // [0, 1024): the selection, sorted by approximate score; [1024, 2048): row pointers, then exact keys;
+    // [2048, 4096): the final top-K (block_topk_256 may use all 4096 entries for the selection before that)
+    __shared__ unsigned long long buf[kGemmCandCap];
+    __shared__ int s_cnt, s_need;
+    __shared__ unsigned long long s_kth;
+    pdl_wait();
+    pdl_launch_dependents();
+    const int qi = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int n = a.d_cnt[qi];
+    const unsigned int ncl = n < a.cap ? n : a.cap;
+    unsigned long long mine[kGemmCandCap / 256];
+#pragma unroll
+    for (int i = 0; i < kGemmCandCap / 256; ++i) {
+        const unsigned idx = threadIdx.x + 256 * i;
+        mine[i] = idx < ncl ? a.d_cand[(size_t)qi * a.cap + idx] : 0ull;
+    }
+    const int m = block_topk_256(mine, a.kp_sel, buf, &s_cnt);
+    const int have = m < a.kp_sel ? m : a.kp_sel;
+    unsigned long long *ex = buf + 1024;
+    const float *qv = a.d_queries + (size_t)qi * a.dims;
+    const int K = a.K;
+
+    // rows [lo, hi) of the selection: locate (all threads, the dependent loads of the searches overlap), then a warp
+    // per row computes the canonical float32 score
+    auto rescore_range = [&](int lo, int hi) {
+        for (int i = lo + (int)threadIdx.x; i < hi; i += 256) {
+            const uint32_t slot = key_slot(buf[i]);
+            int s = (int)(slot / a.rows_per_block);
+            if (s > a.nseg - 1) s = a.nseg - 1;
+            if (!(a.d_seg_slot_base[s] <= slot && (s + 1 == a.nseg || slot < a.d_seg_slot_base[s + 1]))) {
+                int l = 0, h = a.nseg - 1;
+                while (l < h) {
+                    const int mid = (l + h + 1) >> 1;
+                    if (a.d_seg_slot_base[mid] <= slot) l = mid; else h = mid - 1;
+                }
+                s = l;
+            }
+            ex[i] = (unsigned long long)(uintptr_t)(a.d_segs[s].base + (size_t)(slot - a.d_seg_slot_base[s]) * a.dims);
+        }
+        __syncthreads();
+        for (int i = lo + warp; i < hi; i += 8) {
+            const float *x = reinterpret_cast<const float *>((uintptr_t)ex[i]);
+            const uint32_t slot = key_slot(buf[i]);
+            __syncwarp();
+            const float sc = exact_dot(x, qv, a.dims, lane);
+            if (lane == 0) ex[i] = make_key(sc, slot);
+        }
+        __syncthreads();
+    };
+
+    const float delta = cert_delta(qi, a.d_qnorm2, a.d_maxnorm2_bits, a.err_coeff, a.d_qres2, a.d_maxres2_bits);
+    const int k1 = have < K + 32 ? have : K + 32;
+    rescore_range(0, k1);
+    int need = have;
+    if (k1 >= K && k1 < have) {
+        // L = the K-th best exact key of the first k1 (keys are unique: rank by counting)
+        for (int i = threadIdx.x; i < k1; i += 256) {
+            const unsigned long long me = ex[i];
+            int rank = 0;
+            for (int j = 0; j < k1; ++j) rank += ex[j] > me ? 1 : 0;
+            if (rank == K - 1) s_kth = me;
+        }
+        if (threadIdx.x == 0) s_need = 0;
+        __syncthreads();
+        // (a hair more than delta: finalize's own float test, K-th > ceiling + delta, must hold after rounding)
+        const float cut = key_score(s_kth) - delta * 1.001f - 1e-30f;
+        int c = 0;
+        for (int i = k1 + (int)threadIdx.x; i < have; i += 256) c += (key_score(buf[i]) >= cut) ? 1 : 0;  // sorted: a prefix
+        if (c) atomicAdd(&s_need, c);
+        __syncthreads();
+        need = cut == cut ? k1 + s_need : have;  // (NaN scores: no shortcut)
+        rescore_range(k1, need);
+    }
+
+    // best K of the `need` exact keys
+#pragma unroll
+    for (int i = 0; i < kGemmCandCap / 256; ++i) {
+        const int idx = threadIdx.x + 256 * i;
+        mine[i] = idx < need ? ex[idx] : 0ull;
+    }
+    unsigned long long *fin = buf + 2048;
+    block_topk_256(mine, K, fin, &s_cnt);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) a.d_out[(size_t)qi * K + i] = fin[i];
+    if (threadIdx.x == 0) {
+        const long long keff = a.rows_total < K ? a.rows_total : K;
+        bool ok = true;
+        if (n > a.cap) ok = false;              // candidate buffer overflowed: the selection saw a subset
+        if ((long long)n < keff) ok = false;    // threshold too high: not even K candidates
+        if (ok && (long long)n < a.rows_total) {
+            float ceil_approx = a.d_thr[qi];    // rows that were never collected have approx <= thr
+            if (need < have)                    // selected (sorted by approx) but not re-scored: the first bounds the rest
+                ceil_approx = fmaxf(ceil_approx, key_score(buf[need]));
+            else if (n > (unsigned)a.kp_sel)    // collected but not among the best kp_sel by approx score
+                ceil_approx = fmaxf(ceil_approx, key_score(buf[a.kp_sel - 1]));
+            const unsigned long long kth = fin[keff - 1];
+            if (kth == 0ull || !(key_score(kth) > ceil_approx + delta)) ok = false;
+        }
+        a.d_flags[qi] = ok ? 0u : 1u;
+        if (!ok && fix.flagged != nullptr) atomicAdd(fix.flagged, 1u);
+    }
+    fixup_list(fix);
+}
 
 // ------------------------------------------------------------------ one-pass path: the tail
 // group index (quarter * tiles + tile of the set-wide tile order) + row inside the group -> the row and its slot
@@ -1747,6 +1972,14 @@ cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *
     return launch_chain(select_kernel, dim3(q), dim3(256), 0, stream, d_cand, d_cnt, cap, kp, d_sel, need.K, need.kp_min,
                         need.d_qnorm2, need.d_maxnorm2_bits, need.err_coeff, need.d_qres2, need.d_maxres2_bits,
                         need.d_need);
+}
+
+cudaError_t collect_tail_launch(const CollectTail &t, const FixupPlan &fix, cudaStream_t stream)
+{
+    if (t.cap > (unsigned)kGemmCandCap || t.kp_sel > 1024 || t.K > t.kp_sel || t.K + 32 > 1024 || t.q < 1 ||
+        t.rows_per_block == 0)
+        return cudaErrorInvalidValue;
+    return launch_chain(collect_tail_kernel, dim3(t.q), dim3(256), 0, stream, t, fix);
 }
 
 cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream)

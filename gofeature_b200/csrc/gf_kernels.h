@@ -193,6 +193,42 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
                             cudaStream_t stream, const unsigned int *d_need = nullptr);
 
+// The large-batch (two-pass) chain's tail as ONE kernel, one CTA per query, for all queries of up to
+// kTailBatchPasses candidate passes at once (round 1 / 2a: select -> rescore -> finalize, three launches per pass of
+// 256 queries, ~0.11 ms per pass against 0.13 ms for the pass itself at 1 024 queries x top-100):
+//   1  best kp_sel candidates by approximate score, sorted (radix select + bitonic sort in shared memory)
+//   2  exact canonical score of the best K + 32 of them; L = the K-th best exact score so far
+//   3  exact score of every further candidate whose approximate score reaches L - delta.  Everything left out has
+//      approx < L - delta, hence exact < L <= the final K-th score: the certificate holds by construction, and the
+//      depth is ~1 delta below the K-th score instead of the 2.25 delta a depth chosen from approximate scores alone
+//      needs (uniform rows, top-100 of 1 M: ~230 re-scored rows per query instead of ~470)
+//   4  best K exact keys -> d_out, certificate against the COLLECT threshold and the first candidate not re-scored
+struct CollectTail {
+    const unsigned long long *d_cand;  // [q][cap] unsorted approximate keys
+    const unsigned int *d_cnt;         // [q] keys appended (may exceed cap: overflow -> flagged)
+    const float *d_thr;                // [q] COLLECT thresholds: approx <= thr for every row never collected
+    unsigned int cap;
+    int kp_sel;                        // depth of the approximate selection, <= 1024
+    int K;
+    int q;
+    long long rows_total;
+    const Segment *d_segs;
+    const uint32_t *d_seg_slot_base;
+    int nseg;
+    int dims;
+    uint32_t rows_per_block;           // first guess of a slot's segment: slot / rows_per_block
+    const float *d_queries;            // [q][dims] float32, row-major
+    const float *d_qnorm2;
+    const unsigned int *d_maxnorm2_bits;
+    float err_coeff;
+    const float *d_qres2;
+    const unsigned int *d_maxres2_bits;
+    unsigned long long *d_out;         // [q][K]
+    unsigned int *d_flags;             // [q]
+};
+constexpr int kTailBatchPasses = 4;
+cudaError_t collect_tail_launch(const CollectTail &t, const FixupPlan &fix, cudaStream_t stream);
+
 // The one-pass path's last kernel, one thread-block cluster per query: cut = the histogram bin that holds the kp-th
 // best group; every group at or above the cut has its best row re-scored exactly (canonical float32 order); the
 // cluster's leader ranks the exact keys, re-scores whole groups whose SECOND key could still matter, emits the best K

@@ -1849,6 +1849,12 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     m = std::max(2, std::min(m, G / 2));
 
     const int nq_max = gemm_pad_queries(std::min(q, kGemmMaxQ));
+    // small batches re-score EVERY collected candidate (~`target` rows per query) and skip the selection
+    auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)32 << 20); };
+    const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call
+    // The large-batch chain ends with ONE tail launch (collect_tail_kernel) per group of up to kTailBatchPasses passes:
+    // thresholds, counters, norms and candidate buffers of a group's queries stay side by side until then.
+    const int tail_span = all ? nq_max : std::min((q + kGemmMaxQ - 1) / kGemmMaxQ, kTailBatchPasses) * kGemmMaxQ;
     size_t off = 0;
     auto carve = [&](size_t bytes) {
         size_t o = off;
@@ -1857,22 +1863,18 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     };
     const size_t o_ticket = carve(4);  // always offset 0: zeroed when the arena is allocated, left zero by every call
     const size_t o_qpad = carve((size_t)nq_max * dims * 4);
-    const size_t o_qn = carve((size_t)nq_max * 4);
+    const size_t o_qn = carve((size_t)tail_span * 4);
     const size_t o_qbf = carve(bf16 ? (size_t)nq_max * dims * seb : 0);
-    const size_t o_qres = carve((size_t)nq_max * 4);
+    const size_t o_qres = carve((size_t)tail_span * 4);
     const size_t o_qsc = carve((size_t)nq_max * 4);
     const size_t o_tmax = carve((size_t)kGemmMaxSampleTiles * nq_max * 4);
-    const size_t o_thr = carve((size_t)nq_max * 4);
-    const size_t o_cnt = carve((size_t)nq_max * 4);
-    const size_t o_cand = carve((size_t)nq_max * cap * 8);
-    // selection depth of the large-batch chain: select_kernel sorts the best kp_sel candidates by approximate score
-    // and decides PER QUERY how many of them the exact re-score must cover (at least kp)
+    const size_t o_thr = carve((size_t)tail_span * 4);
+    const size_t o_cnt = carve((size_t)tail_span * 4);
+    const size_t o_cand = carve((size_t)tail_span * cap * 8);
+    // selection depth of the large-batch chain: the tail sorts the best kp_sel candidates by approximate score and
+    // decides PER QUERY how many of them the exact re-score must cover
     const int kp_sel = std::min(1024, std::max(512, 2 * kp));
-    const size_t o_sel = carve((size_t)nq_max * kp_sel * 8);
-    const size_t o_need = carve((size_t)nq_max * 4);
-    // small batches re-score EVERY collected candidate (~`target` rows per query) and skip the selection
-    auto rescore_all = [&](int qp_) { return (size_t)qp_ * (size_t)target * (size_t)dims * 4 <= ((size_t)32 << 20); };
-    const size_t o_exact = carve((size_t)nq_max * (rescore_all(std::min(q, kGemmMaxQ)) ? (size_t)cap : (size_t)kp_sel) * 8);
+    const size_t o_exact = carve(all ? (size_t)nq_max * (size_t)cap * 8 : 0);
     const size_t o_map = carve((size_t)kFixupMaxQ * 4);
     const size_t o_count = carve(4);
     const size_t o_qall = carve((size_t)q * dims * 4);  // row-major copy of all queries for the fix-up scan
@@ -1905,9 +1907,7 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
     float *d_thr = (float *)(T + o_thr);
     unsigned int *d_cnt = (unsigned int *)(T + o_cnt);
     unsigned long long *d_cand = (unsigned long long *)(T + o_cand);
-    unsigned long long *d_sel = (unsigned long long *)(T + o_sel);
     unsigned long long *d_exact = (unsigned long long *)(T + o_exact);
-    unsigned int *d_need = (unsigned int *)(T + o_need);
     unsigned int *d_fl = (unsigned int *)(T + o_flags);
     int *d_map = (int *)(T + o_map);
     unsigned int *d_count = (unsigned int *)(T + o_count);
@@ -1950,9 +1950,12 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
         fix.flagged = d_small + 3;
         // (the overlapped one-pass chain launches its own preparation into the scratch set of the step's parity)
         const bool overlap = onepass && phase == 0 && d_flags != nullptr && qp == q && !ctx->profiling.load();
+        // (|q|^2 and the quantisation residual go to the pass's place in its tail group's arrays)
+        const int pq = (all || onepass) ? 0 : p0 % (kTailBatchPasses * kGemmMaxQ);
         if (phase != 2 && !overlap)
             GF_CUDA(prep_queries_launch(d_queries + (size_t)p0 * q_stride, q_stride, l_stride, qp, nq, dims, d_qpad,
-                                        d_qn, d_qall + (size_t)p0 * dims, d_qbf, seb, d_qres, d_qsc, stream),
+                                        d_qn + pq, d_qall + (size_t)p0 * dims, d_qbf, seb, bf16 ? d_qres + pq : nullptr,
+                                        d_qsc, stream),
                     GF_ERR_CUDA);
         if (phase == 1) continue;
         if (onepass) {
@@ -2054,13 +2057,18 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             ctx->stats.rows_scanned += (uint64_t)scanned_rows;
             continue;
         }
-        const bool all = rescore_all(std::min(q, kGemmMaxQ));  // one decision per call: it sizes d_exact
+        // where this pass's queries sit in the per-query arrays of its tail group
+        const int group0 = all ? p0 : (p0 / (kTailBatchPasses * kGemmMaxQ)) * (kTailBatchPasses * kGemmMaxQ);
+        const int gq = p0 - group0;
+        g.d_thr = d_thr + gq;
+        g.d_cand = d_cand + (size_t)gq * cap;
+        g.d_cnt = d_cnt + gq;
         g.tile_first = 0;
         g.mode = kGemmTileMax;
         g.tile_stride = stride;
         g.tile_count = (uint32_t)G;
         GF_CUDA(gemm_launch(g, stream), GF_ERR_CUDA);
-        GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr, d_cnt, stream), GF_ERR_CUDA);
+        GF_CUDA(threshold_launch(d_tmax, G, nq, qp, m, d_thr + gq, d_cnt + gq, stream), GF_ERR_CUDA);
         g.mode = kGemmCollect;
         g.tile_stride = 1;
         g.tile_count = total_gtiles;
@@ -2078,27 +2086,38 @@ int Set::topk_tensor(Workspace *ws, cudaStream_t stream, const float *d_queries,
             GF_CUDA(finalize_launch(d_exact, d_cand, d_cnt, d_thr, cap, (int)cap, K, qp, scanned_rows, d_qn, d_small,
                                     err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 1, fix, stream),
                     GF_ERR_CUDA);
+            ctx->stats.other_launches += 4;
+        } else if (p0 + kGemmMaxQ >= q || gq + kGemmMaxQ >= kTailBatchPasses * kGemmMaxQ) {
+            // the group's last pass: ONE tail launch for all its queries (selection, two-stage exact re-score,
+            // top-K, certificate -- gf_kernels.h CollectTail)
+            CollectTail t{};
+            t.d_cand = d_cand;
+            t.d_cnt = d_cnt;
+            t.d_thr = d_thr;
+            t.cap = cap;
+            t.kp_sel = kp_sel;
+            t.K = K;
+            t.q = gq + qp;
+            t.rows_total = scanned_rows;
+            t.d_segs = d_segs;
+            t.d_seg_slot_base = d_seg_slot_base;
+            t.nseg = nseg;
+            t.dims = dims;
+            t.rows_per_block = (uint32_t)std::max<int64_t>(1, cache->block_size / ((int64_t)dims * 4));
+            t.d_queries = d_qall + (size_t)group0 * dims;
+            t.d_qnorm2 = d_qn;
+            t.d_maxnorm2_bits = d_small;
+            t.err_coeff = err_coeff;
+            t.d_qres2 = d_qres;
+            t.d_maxres2_bits = d_small + 2;
+            t.d_out = d_out + (size_t)group0 * K;
+            t.d_flags = d_fl + group0;
+            GF_CUDA(collect_tail_launch(t, fix, stream), GF_ERR_CUDA);
+            ctx->stats.other_launches += 3;
         } else {
-            SelectNeed sn;
-            sn.K = K;
-            sn.kp_min = kp;
-            sn.d_qnorm2 = d_qn;
-            sn.d_maxnorm2_bits = d_small;
-            sn.err_coeff = err_coeff;
-            sn.d_qres2 = d_qres;
-            sn.d_maxres2_bits = d_small + 2;
-            sn.d_need = d_need;
-            GF_CUDA(select_launch(d_cand, d_cnt, cap, qp, kp_sel, d_sel, stream, sn), GF_ERR_CUDA);
-            GF_CUDA(rescore_launch(d_segs, d_seg_slot_base, nseg, dims, qp, d_qpad, kp_sel, d_sel, nullptr, d_exact,
-                                   stream, d_need),
-                    GF_ERR_CUDA);
-            GF_CUDA(finalize_launch(d_exact, d_sel, d_cnt, d_thr, cap, kp_sel, K, qp, scanned_rows, d_qn, d_small,
-                                    err_coeff, d_qres, d_small + 2, d_out + (size_t)p0 * K, d_fl + p0, 0, fix, stream,
-                                    d_need),
-                    GF_ERR_CUDA);
+            ctx->stats.other_launches += 2;
         }
         ctx->stats.gemm_launches += 2;
-        ctx->stats.other_launches += 4 + (all ? 0 : 1);
         ctx->stats.tensor_passes++;
         ctx->stats.rows_scanned += (uint64_t)scanned_rows;
     }
@@ -2199,7 +2218,8 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     const size_t qbytes = (size_t)q * dims * 4;
     const size_t out_keys = (size_t)q * kb;
     const size_t d_need = align_up(qbytes, 256) + align_up(out_keys * 8, 256) + scratch_bytes(this, q, kb, false);
-    const size_t h_need = align_up(qbytes, 256) + align_up(out_keys * 8, 256) + align_up((size_t)q * 4, 256);
+    // (a second keys + flags area: the refused queries' second tier answers into it)
+    const size_t h_need = align_up(qbytes, 256) + 2 * (align_up(out_keys * 8, 256) + align_up((size_t)q * 4, 256));
     int rc = ws->reserve(d_need, h_need);
     if (rc) return rc;
     const auto t_a = std::chrono::steady_clock::now();
@@ -2208,6 +2228,8 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     float *h_q = (float *)ws->h_buf;
     unsigned long long *h_out = (unsigned long long *)(ws->h_buf + align_up(qbytes, 256));
     unsigned int *h_flags = (unsigned int *)((uint8_t *)h_out + align_up(out_keys * 8, 256));
+    unsigned long long *h_out2 = (unsigned long long *)((uint8_t *)h_flags + align_up((size_t)q * 4, 256));
+    unsigned int *h_flags2 = (unsigned int *)((uint8_t *)h_out2 + align_up(out_keys * 8, 256));
     size_t off = 0;
     for (int i = 0; i < nparts; ++i) {
         memcpy((uint8_t *)h_q + off, parts[i], (size_t)part_q[i] * dims * 4);
@@ -2227,19 +2249,51 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     ctx->stats.host_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_d - t_c).count();
     ctx->stats.host_calls++;
     ctx->stats.d2h_bytes += out_keys * 8 + (size_t)q * 4;
-    // tensor-path queries the certificate refused: ONLY those go through the exact scan, as one compact batch
-    // (the refused query vectors are packed at the front of the device staging area; passes of scan_max_q queries)
+    // Tensor-path queries the certificate refused: ONLY those are re-run, as one compact batch (the refused query
+    // vectors are packed at the front of the device staging area), in tiers:
+    //   2  more than one scan pass worth of them (> scan_max_q) and a shadow pass refused them: ONE kind::tf32 candidate
+    //      pass over the float32 rows for the whole batch -- its error bound is ~4x (bf16) to ~10x (int8) tighter, so
+    //      near neighbours the shadow could not separate certify here (0.30 ms per pass at 1 M x 512 whatever the
+    //      batch, against 0.35 ms per EIGHT queries of the exact scan);
+    //   3  what is still refused (or a small batch): the exact scan, passes of scan_max_q queries.
     std::vector<int> bad;
     for (int i = 0; i < q; ++i)
         if (h_flags[i]) bad.push_back(i);
-    if (!bad.empty()) {
-        ctx->stats.uncertified_queries += bad.size();
-        const int nb = (int)bad.size();
-        // d_q: [q][dims] staging; d_out: [q][kb].  Pack the refused queries into d_q[0 .. nb), results into d_out[0 .. nb)
-        for (int j = 0; j < nb; ++j)
-            GF_CUDA(cudaMemcpyAsync(d_q + (size_t)j * dims, h_q + (size_t)bad[j] * dims, (size_t)dims * 4,
+    auto pack = [&](const std::vector<int> &idx) -> int {
+        for (size_t j = 0; j < idx.size(); ++j)
+            GF_CUDA(cudaMemcpyAsync(d_q + j * dims, h_q + (size_t)idx[j] * dims, (size_t)dims * 4,
                                     cudaMemcpyHostToDevice, ws->stream),
                     GF_ERR_WRITE_INPUT_BUFFER);
+        return GF_OK;
+    };
+    if (!bad.empty()) {
+        ctx->stats.uncertified_queries += bad.size();
+        const int sp = search_path.load();
+        if ((int)bad.size() > scan_max_q(dims) && sp != 3 && sp != 5 && use_shadow(sp) &&
+            tensor_eligible((int)bad.size(), kb, false, nullptr, 5)) {
+            const int nb = (int)bad.size();
+            rc = pack(bad);
+            if (rc) return rc;
+            rc = topk_device(ws, ws->stream, d_q, nb, dims, 1, kb, false, nullptr, h_out2, 5, h_flags2, false);
+            if (rc) return rc;
+            GF_CUDA(wait_stream(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+            std::vector<int> still;
+            for (int j = 0; j < nb; ++j) {
+                if (h_flags2[j]) {
+                    still.push_back(bad[j]);
+                    continue;
+                }
+                memcpy(h_out + (size_t)bad[j] * kb, h_out2 + (size_t)j * kb, (size_t)kb * 8);
+            }
+            ctx->stats.tier2_queries += (uint64_t)(nb - (int)still.size());
+            bad.swap(still);
+        }
+    }
+    if (!bad.empty()) {
+        const int nb = (int)bad.size();
+        // d_q: [q][dims] staging; d_out: [q][kb].  Refused queries in d_q[0 .. nb), results into d_out[0 .. nb)
+        rc = pack(bad);
+        if (rc) return rc;
         rc = topk_scan(ws, ws->stream, d_q, nb, dims, 1, kb, false, nullptr, d_out);
         if (rc) return rc;
         // (h_q is free again: the winners of the re-run land there before they are scattered)

@@ -66,7 +66,7 @@ struct Stats {
         rows_scanned{0}, quirk_fallbacks{0}, coalesced_batches{0}, h2d_bytes{0}, d2h_bytes{0}, scan_kernel_ns{0},
         scan_kernel_timed{0}, tensor_passes{0}, uncertified_queries{0}, gemm_kernel_ns{0}, gemm_kernel_timed{0},
         host_stage_ns{0}, host_launch_ns{0}, host_wait_ns{0}, host_resolve_ns{0}, host_calls{0},
-        add_stage_ns{0}, add_place_ns{0}, add_index_ns{0}, add_rows{0};
+        add_stage_ns{0}, add_place_ns{0}, add_index_ns{0}, add_rows{0}, tier2_queries{0};
 };
 
 // per-search scratch: a stream, device and pinned arenas

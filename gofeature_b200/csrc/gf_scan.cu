@@ -58,6 +58,9 @@ struct TileMeta {
 
 constexpr int kConsumerWarps = kScanConsumerWarps;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
+// threads of the bulk-copy kernel: QG groups of 7 consumer warps + the producer warp
+__host__ __device__ constexpr int scan_threads(int qg) { return (kConsumerWarps * qg + 1) * 32; }
+static_assert(scan_threads(1) == kScanThreads, "one query group: 7 consumer warps + the producer");
 
 __device__ __forceinline__ void tile_range(const ScanArgs &a, uint32_t &first, uint32_t &end, uint32_t &stride,
                                            uint32_t &group)
@@ -87,14 +90,24 @@ __device__ __forceinline__ void offer(ListCtl *ctl, unsigned long long *buf, int
 // --------------------------------------------------------------------------------------
 // Bulk-copy (TMA) pipeline kernel.  D in {128,256,512,1024}; CH = D/128 chunks per lane.
 // --------------------------------------------------------------------------------------
-template <int D, int QT>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArgs a)
+//
+// QG = query groups.  QT queries in registers cost QT * CH * 4 registers per thread: at QT * CH = 32 (8 queries of
+// 512-d) that is 128 of the 255 a thread can have, the CTA is 8 warps and each scheduler has two warps to hide the
+// FFMA2 / shuffle / shared-memory latencies of a 250-instruction dependent chain per row pair (ncu: issue active
+// 40 %, 5.4 TB/s).  With QG = 2 the same tile is read by two groups of 7 consumer warps, each holding HALF of the
+// queries (QW = QT / QG, 128 registers per thread, 15 warps): the arithmetic per SM is unchanged, twice as many
+// warps interleave on it, and every feature byte still crosses HBM once (shared memory is read twice).
+template <int D, int QT, int QG>
+__global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const ScanArgs a)
 {
     constexpr int CH = D / 128;
+    constexpr int QW = QT / QG;                      // queries a consumer warp holds
+    constexpr int kWarpsAll = kConsumerWarps * QG;   // consumer warps of the CTA
     constexpr int TILE_ROWS = kScanTileBytes / (D * 4);
     constexpr int RPW = TILE_ROWS / kConsumerWarps;  // rows per warp per tile
-    constexpr int RB = (RPW >= 2 && QT * CH <= 32) ? 2 : 1;  // rows in flight per warp
+    constexpr int RB = (RPW >= 2 && QW * CH <= 32) ? 2 : 1;  // rows in flight per warp
     static_assert(RPW >= 1 && RPW % RB == 0, "tile split");
+    static_assert(QT % QG == 0 && QW >= 1, "query groups");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int stages = a.stages;
@@ -119,7 +132,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(&empty[s], kWarpsAll);
         }
         mbar_fence_init();
     }
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     uint32_t first, end, stride, group;
     tile_range(a, first, end, stride, group);
 
-    if (warp == kConsumerWarps) {
+    if (warp == kWarpsAll) {
         // ===================== producer: one thread feeds the ring =====================
         if (lane == 0 && first < end) {
             const uint64_t policy = l2_policy_evict_first();
@@ -164,27 +177,30 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     }
 
     // ===================== consumers =====================
-    float4 qreg[QT][CH];
+    // warp = qg * kConsumerWarps + rw: row share rw of every tile, queries [qg * QW, qg * QW + QW)
+    const int qg = warp / kConsumerWarps, rw = warp - qg * kConsumerWarps;
+    const int q0 = qg * QW;
+    float4 qreg[QW][CH];
 #pragma unroll
-    for (int qi = 0; qi < QT; ++qi) {
+    for (int qi = 0; qi < QW; ++qi) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             float v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 int e = 128 * j + 4 * lane + c;
-                const int qsrc = (qi < q_live && a.q_map != nullptr) ? a.q_map[qi] : qi;
-                v[c] = (qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+                const int qsrc = (q0 + qi < q_live && a.q_map != nullptr) ? a.q_map[q0 + qi] : q0 + qi;
+                v[c] = (q0 + qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
             }
             qreg[qi][j] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    // V = RB*QT scores are reduced together; afterwards this lane holds score index vi = b*QT + qi
-    constexpr int V = RB * QT;
+    // V = RB*QW scores are reduced together; afterwards this lane holds score index vi = b*QW + qi
+    constexpr int V = RB * QW;
     constexpr int LOG2V = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : 4;
     constexpr int GROUP = 32 >> LOG2V;  // lanes that end up with the same score
     const int vi = lane >> (5 - LOG2V);
-    const int my_b = vi / QT, my_q = vi % QT;
+    const int my_b = vi / QW, my_q = q0 + vi % QW;
     const bool my_live = my_q < q_live;
 
     const int cap = a.list_cap, K = a.K;
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * (kScanTileBytes / 4));
 #pragma unroll
         for (int rb = 0; rb < RPW; rb += RB) {
-            const int r0 = warp * RPW + rb;
+            const int r0 = rw * RPW + rb;
             float4 x[RB][CH];
 #pragma unroll
             for (int b = 0; b < RB; ++b)
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
 #pragma unroll
             for (int b = 0; b < RB; ++b) {
 #pragma unroll
-                for (int qi = 0; qi < QT; ++qi) {
+                for (int qi = 0; qi < QW; ++qi) {
                     // P[4l..4l+3] as two packed pairs: fma.rn.f32x2 (FFMA2) is two independent IEEE fmas
                     float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
                         p23 = __ffma2_rn(make_float2(x[b][j].z, x[b][j].w),
                                          make_float2(qreg[qi][j].z, qreg[qi][j].w), p23);
                     }
-                    tsum[b * QT + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
+                    tsum[b * QW + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
                 }
             }
             const float sc = canonical_reduce_many<V>(tsum, lane);
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
                 const float ls = __shfl_sync(0xffffffffu, sc, leader);
                 const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lvi * GROUP));
                 bal &= ~gmask;
-                const int lb = lvi / QT, lq = lvi % QT;
+                const int lb = lvi / QW, lq = q0 + lvi % QW;
                 const unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + lq] : ~0ull;
                 offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
             }
@@ -248,8 +264,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         }
     }
 
-    named_bar_sync(1, kConsumerThreads);
-    for (int qi = warp; qi < q_live && qi < QT; qi += kConsumerWarps) {
+    named_bar_sync(1, kWarpsAll * 32);
+    for (int qi = warp; qi < q_live && qi < QT; qi += kWarpsAll) {
         unsigned long long *out =
             a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
         list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
@@ -353,10 +369,13 @@ cudaError_t launch_tma(const ScanPlan &plan, const ScanArgs &args, cudaStream_t 
     if constexpr (QT * D > 4096) {
         return cudaErrorInvalidValue;
     } else {
-        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT>, plan.smem_bytes);
+        // the register-heaviest shapes (QT * D / 128 = 32: 8 queries of 512-d, 4 of 1024-d) split the queries over
+        // two groups of consumer warps
+        constexpr int QG = (QT * D == 4096 && QT >= 2) ? 2 : 1;
+        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT, QG>, plan.smem_bytes);
         if (e != cudaSuccess) return e;
         dim3 grid(plan.grid_x, plan.groups);
-        return launch_chain(scan_tma_kernel<D, QT>, grid, dim3(kScanThreads), plan.smem_bytes, stream, args);
+        return launch_chain(scan_tma_kernel<D, QT, QG>, grid, dim3(scan_threads(QG)), plan.smem_bytes, stream, args);
     }
 }
 

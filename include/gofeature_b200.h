@@ -382,6 +382,9 @@ typedef struct gf_stats {
     uint64_t add_place_ns;
     uint64_t add_index_ns;
     uint64_t add_rows;
+    /* of uncertified_queries: answered (and certified) by the second tier -- one kind::tf32 candidate pass over the
+     * float32 rows for the whole compact batch -- instead of the exact scan (passes of 8 queries) */
+    uint64_t tier2_queries;
 } gf_stats;
 GF_API int gf_context_stats(const gf_context *ctx, gf_stats *out);
 GF_API int gf_context_reset_stats(gf_context *ctx);

@@ -12,6 +12,7 @@ import torch
 from gofeature_b200 import api
 
 Q = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 ctx = api.NewContext(0)
 cache = api.NewCache(ctx, 63, 32 << 20)
 cache.NewSet("prof", 512, 4, 1024)
@@ -21,11 +22,11 @@ rng = np.random.default_rng(0)
 x = rng.uniform(-1, 1, (Q, 512)).astype(np.float32)
 x /= np.linalg.norm(x, axis=1, keepdims=True)
 dq = torch.from_numpy(x).cuda()
-keys = torch.zeros((Q, 10), dtype=torch.int64, device="cuda")
+keys = torch.zeros((Q, K), dtype=torch.int64, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
 ctx.SetProfiling(True)            # kernel by kernel (no graph replay) so that ncu sees plain launches
 for _ in range(5):
-    st.SearchDevice(10, Q, dq.data_ptr(), keys.data_ptr(), 2, stream)
+    st.SearchDevice(K, Q, dq.data_ptr(), keys.data_ptr(), 2, stream)
     torch.cuda.synchronize()
 print("ok", ctx.Stats()["tensor_passes"])
 cache.Close()

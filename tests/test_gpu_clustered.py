@@ -65,3 +65,47 @@ def test_clustered_queries_certify_and_match_the_oracle(gpu_ctx, batch, limit):
         assert [np.float32(r.Score) for r in g] == [np.float32(x) for x in sc]
     assert s["uncertified_queries"] <= max(1, nq // 100), s      # >= 99 % certified without the exact scan
     cache.Close()
+
+
+def test_refused_batch_takes_the_tf32_tier_before_the_exact_scan(gpu_ctx):
+    """More than one scan pass worth (> 8) of queries the int8 pass cannot certify: 4 800 rows spread evenly within 0.03
+    of the winner (160 rows per 0.001), so the 124 groups the one-pass chain re-scores end 0.0008 below the winner --
+    far inside the int8 bound (~0.008).  The second tier -- ONE kind::tf32 pass over the float32 rows for the compact
+    batch, bound 2.2e-3, every collected row re-scored -- certifies them; answers stay bit-identical to the oracle and
+    the exact scan is not launched."""
+    from gofeature_b200 import api
+    dims, cap = 128, 16384
+    rng = np.random.default_rng(77)
+    n_bg, n_near = 70_000, 4_800
+    base = rng.uniform(-1, 1, dims).astype(np.float32)
+    base /= np.linalg.norm(base)
+    bg = rng.uniform(-1, 1, (n_bg, dims)).astype(np.float32)
+    bg /= np.linalg.norm(bg, axis=1, keepdims=True)
+    # near rows: cos(row, base) = 1 - t, t spread evenly over [0, 0.03]
+    t = np.linspace(0.0, 0.03, n_near).astype(np.float64)
+    noise = rng.uniform(-1, 1, (n_near, dims))
+    noise -= np.outer(noise @ base.astype(np.float64), base.astype(np.float64))
+    noise /= np.linalg.norm(noise, axis=1, keepdims=True)
+    c = 1.0 - t
+    near = (c[:, None] * base.astype(np.float64)[None, :] + np.sqrt(1.0 - c * c)[:, None] * noise).astype(np.float32)
+    rows = np.concatenate([bg, near])
+    rows = rows[rng.permutation(len(rows))]
+    cache = api.NewCache(gpu_ctx, len(rows) // cap + 2, cap * dims * 4)
+    cache.NewSet("near", dims, 4, 16)
+    st = cache.GetSet("near")
+    st.AddArray(rows, ["r%06d" % i for i in range(len(rows))])
+    nq, limit = 12, 10
+    q = base[None, :] + 1e-4 * rng.uniform(-1, 1, (nq, dims)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    import os
+    want = ol.scan_topk(rows, q, limit, ol.MODE_CANONICAL, os.cpu_count() or 1)
+    gpu_ctx.ResetStats()
+    got = st.SearchArray(-2.0, limit, q)
+    s = gpu_ctx.Stats()
+    for g, (sc, idx) in zip(got, want):
+        assert [r.ID for r in g] == ["r%06d" % i for i in idx]
+        assert [np.float32(r.Score) for r in g] == [np.float32(x) for x in sc]
+    assert s["uncertified_queries"] == nq, s          # the int8 pass refused all of them ...
+    assert s["tier2_queries"] == nq, s                # ... the tf32 tier certified all of them ...
+    assert s["scan_launches"] == 0, s                 # ... and the exact scan never ran
+    cache.Close()
