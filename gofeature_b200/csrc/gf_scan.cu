@@ -45,6 +45,7 @@ struct ScanArgs {
     int tile_rows;
     int dims;
     int per_segment;
+    int warp_lists;
     const int *q_map;             // optional: query i of this launch is row q_map[i] of `queries`
     const unsigned int *q_count;  // optional: live query count lives on the device (0 -> nothing to do)
     const unsigned long long *upper;
@@ -137,7 +138,14 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
         mbar_fence_init();
     }
     if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
-    for (int i = threadIdx.x; i < QT * a.list_cap; i += blockDim.x) lists[i] = 0ull;
+    // locked lists: [query][list_cap]; owner-computes lists: [query][32], then one mailbox per query
+    const int list_words = a.warp_lists ? QT * 32 : QT * a.list_cap;
+    Mailbox *mbox = reinterpret_cast<Mailbox *>(lists + (size_t)QT * 32);
+    unsigned int *done_warps = reinterpret_cast<unsigned int *>(mbox + QT);  // consumer warps that have posted everything
+    for (int i = threadIdx.x; i < list_words; i += blockDim.x) lists[i] = 0ull;
+    if (a.warp_lists)
+        for (int i = threadIdx.x; i < (int)(QT * sizeof(Mailbox) / 8) + 1; i += blockDim.x)
+            reinterpret_cast<unsigned long long *>(mbox)[i] = 0ull;  // (+ the done counter behind the mailboxes)
     __syncthreads();
 
     uint32_t first, end, stride, group;
@@ -207,11 +215,15 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
     int s = 0;
     uint32_t ph = 0;
     for (uint32_t t = first; t < end; t += stride) {
+        if (a.warp_lists)  // candidates the other warps posted for the queries this warp owns
+            for (int oq = warp; oq < QT; oq += kWarpsAll)
+                mailbox_drain(&mbox[oq], lists + (size_t)oq * 32, K, &ctl[oq].gate_img, lane);
         mbar_wait(&full[s], ph);
         const uint32_t vrows = meta[s].rows;
         const uint32_t slot0 = meta[s].slot0;
         // one-compare pre-gate, refreshed per tile; a stale (lower) value only lets extra keys through
-        const float tau_l = *(volatile float *)&ctl[my_q].tauf;
+        const float tau_l = a.warp_lists ? image_score(*(volatile unsigned int *)&ctl[my_q].gate_img)  // (0 -> NaN: all pass)
+                                         : *(volatile float *)&ctl[my_q].tauf;
         const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * (kScanTileBytes / 4));
 #pragma unroll
         for (int rb = 0; rb < RPW; rb += RB) {
@@ -255,7 +267,27 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
                 bal &= ~gmask;
                 const int lb = lvi / QW, lq = q0 + lvi % QW;
                 const unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + lq] : ~0ull;
-                offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
+                if (a.warp_lists) {
+                    const unsigned long long key = make_key(ls, slot0 + r0 + lb);
+                    unsigned long long *lst = lists + (size_t)lq * 32;
+                    // (a peek at the owner's K-th key: it only grows, a stale value lets an extra candidate through)
+                    if (key > *(volatile unsigned long long *)&lst[K - 1] && key < up) {
+                        if (lq % kWarpsAll == warp) {
+                            owner_list_insert(lst, K, key, &ctl[lq].gate_img, lane);
+                        } else {
+                            Mailbox *mb = &mbox[lq];
+                            unsigned int idx = 0;
+                            if (lane == 0) idx = atomicAdd(&mb->tail, 1u);
+                            idx = __shfl_sync(0xffffffffu, idx, 0);
+                            // mailbox full: serve this warp's own mailboxes meanwhile (somebody may be waiting on them)
+                            while (idx - *(volatile unsigned int *)&mb->head >= (unsigned)kMailboxCap)
+                                for (int oq = warp; oq < QT; oq += kWarpsAll)
+                                    mailbox_drain(&mbox[oq], lists + (size_t)oq * 32, K, &ctl[oq].gate_img, lane);
+                            if (lane == 0) *(volatile unsigned long long *)&mb->slot[idx % kMailboxCap] = key;
+                        }
+                    }
+                } else
+                    offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
             }
         }
         if (++s == stages) {
@@ -264,11 +296,33 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
         }
     }
 
-    named_bar_sync(1, kWarpsAll * 32);
-    for (int qi = warp; qi < q_live && qi < QT; qi += kWarpsAll) {
+    if (a.warp_lists) {
+        // No plain barrier here: a warp that is done keeps serving its mailboxes until EVERY warp has posted its last
+        // candidate -- a sender up to a ring's depth behind could otherwise fill the mailbox of an owner that already
+        // waits at the barrier (rows sorted by score make every row a candidate) and block for ever.
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(done_warps, 1u);
+        }
+        bool all_done;
+        do {
+            all_done = *(volatile unsigned int *)done_warps >= (unsigned)kWarpsAll;  // (read BEFORE the drain it covers)
+            __threadfence_block();
+            for (int oq = warp; oq < QT; oq += kWarpsAll)
+                mailbox_drain(&mbox[oq], lists + (size_t)oq * 32, K, &ctl[oq].gate_img, lane);
+        } while (!all_done);
+    } else {
+        named_bar_sync(1, kWarpsAll * 32);
+    }
+    for (int qi = warp; qi < q_live && qi < QT; qi += kWarpsAll) {  // (the owner of qi flushes it)
         unsigned long long *out =
             a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
-        list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
+        if (a.warp_lists) {
+            for (int i = lane; i < K; i += 32) out[i] = lists[(size_t)qi * 32 + i];
+        } else {
+            list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
+        }
     }
 }
 
@@ -430,6 +484,8 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
     size_t lists_bytes = (size_t)p.qt * p.list_cap * 8;
     int tr = scan_tile_rows(dims);
     p.tma = aligned16 && tr > 0 && p.qt * dims <= 4096;
+    p.warp_lists = p.tma && K <= 32;
+    if (p.warp_lists) lists_bytes = (size_t)p.qt * (32 * 8 + sizeof(Mailbox)) + 16;
     if (p.tma) {
         p.tile_rows = tr;
         size_t fixed = 1024;
@@ -476,6 +532,7 @@ cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, u
     a.tile_rows = plan.tile_rows;
     a.dims = plan.dims;
     a.per_segment = (plan.groups != 1) ? 1 : 0;
+    a.warp_lists = plan.warp_lists ? 1 : 0;
     a.upper = d_upper;
     a.partial = d_partial;
     if (plan.tma) {
