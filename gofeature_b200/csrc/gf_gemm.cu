@@ -551,83 +551,86 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                 };
                 if constexpr (EB == 1 && TM == 1) {
                     if (m_collect) {
-                        // int8 COLLECT.  (1) ALL of this warp's columns go to registers and the accumulator set is
-                        // released at once: held for the whole epilogue, it made the MMAs of tile i+2 wait for the
-                        // epilogue of tile i, the ring filled up and drained in bursts, and a 5-stage ring cannot
-                        // cover the HBM latency of bursts (256 queries: 2.5 us per tile for 1.3 us of MMAs).
-                        // (2) score > threshold  <=>  sign of fma(-float(acc), row scale, threshold').  Survivors
-                        // are ~8e-4 of the scores, so the test runs on the MAXIMUM of 8 accumulators against the
-                        // smallest of their 8 thresholds first: the integer maximum is 4 instructions per 8 scores
-                        // (VIMNMX3), the float test 3 per group, against I2F + FFMA + SHF per score.
-                        // float_ru(max) >= float_rn(acc), min threshold <= threshold, row scale >= 0 and the single
-                        // rounding of the fma make the group test a superset of the per-score test (monotone);
-                        // `!(t > 0)` also passes -0 and NaN on.  A group that passes (every fourth) re-tests its
-                        // scores exactly as before, after an integer pre-compare against a conservative bound.
-                        static_assert(kColsPerWarp % 8 == 0 && kColsPerWarp <= 64, "groups of 8 columns, in registers");
-                        uint32_t r[kColsPerWarp];
-#pragma unroll
-                        for (int c = 0; c < kColsPerWarp; c += Cfg::kChunk)
-                            tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + col_first + c,
-                                                 reinterpret_cast<uint32_t(&)[Cfg::kChunk]>(r[c]));
-                        tmem_ld_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[buf]);
-                        released = true;
-                        // group tests, branch-free: bit g of `trig` = group g may hold a survivor of this row
-                        unsigned trig = 0;
-#pragma unroll
-                        for (int g = 0; g < kColsPerWarp / 8; ++g) {
-                            const int b = 8 * g;
-                            int m = __vimax3_s32((int)r[b], (int)r[b + 1], (int)r[b + 2]);
-                            const int m2 = __vimax3_s32((int)r[b + 3], (int)r[b + 4], (int)r[b + 5]);
-                            m = __vimax3_s32(m, (int)r[b + 6], (int)r[b + 7]);
-                            m = max(m, m2);
-                            const float tp = __fmaf_rn(-__int2float_ru(m), rs, thrmin_s[(col_first >> 3) + g]);
-                            trig |= (tp > 0.f) ? 0u : (1u << g);
-                        }
-                        if (!live) trig = 0;
-                        // the rare group that passed: its 8 accumulators move to a common set of registers (ONE copy
-                        // of the code below for all groups -- unrolled per group, with the survivor path inline, the
-                        // kernel was 6 760 instructions and spent two thirds of its time in instruction-cache misses)
-                        while (trig) {
-                            const int g = __ffs(trig) - 1;
-                            trig &= trig - 1;
-                            uint32_t v[8];
-                            switch (g) {
-#define GF_PICK(G)                                                      \
-    case G:                                                             \
-        if constexpr (8 * G < kColsPerWarp) {                           \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = r[(8 * G + j) % kColsPerWarp]; \
-        }                                                               \
-        break;
-                                GF_PICK(0) GF_PICK(1) GF_PICK(2) GF_PICK(3) GF_PICK(4) GF_PICK(5) GF_PICK(6)
-                                default:
-                                    if constexpr (56 < kColsPerWarp) {
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) v[j] = r[(56 + j) % kColsPerWarp];
-                                    }
-                                    break;
-#undef GF_PICK
+                        // int8 COLLECT.  score > threshold  <=>  sign of fma(-float(acc), row scale, threshold').
+                        // One such test per score (I2F + FFMA + SHF, and a 32-way select chain per survivor) made
+                        // the epilogue the bound of the 128 / 256-query passes and held the accumulator set for
+                        // ~2 500 cycles per tile: the MMAs of tile i+2 waited for it, the ring filled and drained in
+                        // bursts, and a 5-stage ring cannot cover the HBM latency of bursts (256 queries: 2.5 us per
+                        // tile for 1.3 us of MMAs).  Survivors are ~8e-4 of the scores, so the test runs on the MAXIMUM
+                        // of 8 accumulators against the smallest of their 8 thresholds first: the integer maximum is 4
+                        // instructions per 8 scores (VIMNMX3), the float test 3 per group.  float_ru(max) >=
+                        // float_rn(acc), min threshold <= threshold, row scale >= 0 and the single rounding of the fma
+                        // make the group test a superset of the per-score test (monotone); `!(t > 0)` also passes -0
+                        // and NaN on.  A group that passes (every fourth) re-tests its 8 scores exactly as before.
+                        // The accumulator set is released as soon as the LAST chunk of columns is in registers.
+                        // (All 64 columns of a warp in registers at once released it earlier still, but at the 96
+                        // registers an 18-warp CTA may have the row-scale prefetch was spilled the moment it was
+                        // issued -- a store waiting for the load it was meant to hide.)
+                        static_assert(Cfg::kChunk % 8 == 0 && Cfg::kChunk <= 32, "groups of 8 columns");
+#pragma unroll 1
+                        for (int c0 = col_first; c0 < col_first + kColsPerWarp; c0 += Cfg::kChunk) {
+                            uint32_t r[Cfg::kChunk];
+                            tmem_ld<Cfg::kChunk>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + c0, r);
+                            tmem_ld_wait();
+                            if (c0 + Cfg::kChunk >= col_first + kColsPerWarp) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&tempty[buf]);
+                                released = true;
                             }
-                            const int cg = col_first + 8 * g;
-                            const float4 tha = *reinterpret_cast<const float4 *>(thr_s + cg);
-                            const float4 thb = *reinterpret_cast<const float4 *>(thr_s + cg + 4);
-                            const float th[8] = {tha.x, tha.y, tha.z, tha.w, thb.x, thb.y, thb.z, thb.w};
-                            unsigned pass = 0;  // column j of the group -> bit 7 - j
+                            // group tests, branch-free: bit g of `trig` = group g may hold a survivor of this row
+                            unsigned trig = 0;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                pass = __funnelshift_l(__float_as_uint(__fmaf_rn(-__int2float_rn((int)v[j]), rs, th[j])),
-                                                       pass, 1);
-                            while (pass) {
-                                const int bit = __ffs(pass) - 1;
-                                pass &= pass - 1;
-                                const int j = 7 - bit;
-                                uint32_t acc = v[0];
+                            for (int g = 0; g < Cfg::kChunk / 8; ++g) {
+                                const int b = 8 * g;
+                                int m = __vimax3_s32((int)r[b], (int)r[b + 1], (int)r[b + 2]);
+                                const int m2 = __vimax3_s32((int)r[b + 3], (int)r[b + 4], (int)r[b + 5]);
+                                m = __vimax3_s32(m, (int)r[b + 6], (int)r[b + 7]);
+                                m = max(m, m2);
+                                const float tp = __fmaf_rn(-__int2float_ru(m), rs, thrmin_s[(c0 >> 3) + g]);
+                                trig |= (tp > 0.f) ? 0u : (1u << g);
+                            }
+                            if (!live) trig = 0;
+                            // the rare group that passed: its 8 accumulators move to a common set of registers (ONE
+                            // copy of the code below for all groups -- unrolled per group, with the survivor path
+                            // inline, the kernel was 6 760 instructions and spent two thirds of its time in
+                            // instruction-cache misses)
+                            while (trig) {
+                                const int g = __ffs(trig) - 1;
+                                trig &= trig - 1;
+                                uint32_t v[8];
+                                if (g == 0 || Cfg::kChunk == 8) {
 #pragma unroll
-                                for (int jj = 1; jj < 8; ++jj)
-                                    if (jj == j) acc = v[jj];
-                                stage_raw(__int2float_rn((int)acc) * rs, cg + j);
+                                    for (int j = 0; j < 8; ++j) v[j] = r[j];
+                                } else if (g == 1 || Cfg::kChunk == 16) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = r[(8 + j) % Cfg::kChunk];
+                                } else if (g == 2) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = r[(16 + j) % Cfg::kChunk];
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = r[(24 + j) % Cfg::kChunk];
+                                }
+                                const int cg = c0 + 8 * g;
+                                const float4 tha = *reinterpret_cast<const float4 *>(thr_s + cg);
+                                const float4 thb = *reinterpret_cast<const float4 *>(thr_s + cg + 4);
+                                const float th[8] = {tha.x, tha.y, tha.z, tha.w, thb.x, thb.y, thb.z, thb.w};
+                                unsigned pass = 0;  // column j of the group -> bit 7 - j
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    pass = __funnelshift_l(
+                                        __float_as_uint(__fmaf_rn(-__int2float_rn((int)v[j]), rs, th[j])), pass, 1);
+                                while (pass) {
+                                    const int bit = __ffs(pass) - 1;
+                                    pass &= pass - 1;
+                                    const int j = 7 - bit;
+                                    uint32_t acc = v[0];
+#pragma unroll
+                                    for (int jj = 1; jj < 8; ++jj)
+                                        if (jj == j) acc = v[jj];
+                                    stage_raw(__int2float_rn((int)acc) * rs, cg + j);
+                                }
                             }
                         }
                         continue;  // (TM == 1: the tile is done)
