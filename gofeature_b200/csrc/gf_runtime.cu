@@ -836,6 +836,7 @@ bool Set::find_implicit(const std::string &id, int *pos, int *row) const
 // First block (Set.Blocks order) holding the id, last row inside it (set.go:167-170, block.go:140-144).
 bool Set::find(const std::string &id, int *pos, int *row) const
 {
+    loc_sync();
     if (has_dups) {
         for (size_t p = 0; p < blocks.size(); ++p) {
             int r = blocks[p]->find_last(id);
@@ -1102,6 +1103,7 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
     if (n == 0) return GF_OK;
     if (is_multi()) return multi_add(n, values, ids_);
     std::lock_guard<std::mutex> mg(mut_mu);
+    loc_sync();
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;  // DestroySet won
     if (precision != 4) return add_plain(n, values, ids_);
     int rc = ctx->bind();
@@ -1145,6 +1147,7 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
             std::vector<int> rows;
         };
         std::vector<Placed> placed;
+        loc_sync();  // (the previous chunk's ids: (B) reads has_dups and may move a block's ids into the locator)
         {
             ExclusiveGuard g(lock);  // (B)
             rc = quiesce(ctx);
@@ -1201,10 +1204,20 @@ int Set::add(int64_t n, const uint8_t *values, const std::vector<std::string> &i
             GF_CUDA(cudaStreamSynchronize(ctx->mut_stream), GF_ERR_WRITE_CUDA_BUFFER);
         }
         const auto t_c = std::chrono::steady_clock::now();
-        if (!has_dups) loc.reserve(loc.size() + (size_t)cn);
-        int64_t k = c0;  // (C) rows were placed in request order: the caller's own strings name them
-        for (const Placed &p : placed)
-            for (int row : p.rows) note_id(ids_[(size_t)k++], p.bp, row);
+        // (C) the locator learns the ids -- from the blocks' own copies, on a helper thread for anything but a
+        // small request: the caller gets its Add back (and stages the next one) meanwhile.  Searches never read the
+        // locator; every mutation, Read and DestroySet joins the job first (loc_sync).
+        auto learn = [this](const std::vector<Placed> &pl, size_t rows_) {
+            if (!has_dups) loc.reserve(loc.size() + rows_);
+            for (const Placed &p : pl)
+                for (int row : p.rows) note_id(blocks[(size_t)p.bp]->id_at(row), p.bp, row);
+        };
+        if (cn >= 512) {
+            std::lock_guard<std::mutex> jg(loc_job_mu);
+            loc_job = std::async(std::launch::async, [learn, pl = std::move(placed), cn]() { learn(pl, (size_t)cn); });
+        } else {
+            learn(placed, (size_t)cn);
+        }
         const auto t_d = std::chrono::steady_clock::now();
         auto ns = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
             return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count();
@@ -1286,6 +1299,7 @@ int Set::add_synthetic(int64_t n, const gf::SynthSpec &seed, int64_t first_ordin
     if (n == 0) return GF_OK;
     if (is_multi()) return multi_add_synthetic(n, seed, first_ordinal, normalize, prefix);
     std::lock_guard<std::mutex> mg(mut_mu);
+    loc_sync();
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1382,6 +1396,7 @@ int Set::remove(const std::vector<std::string> &ids_, std::vector<uint8_t> &foun
     if (ids_.empty()) return GF_OK;
     if (is_multi()) return multi_remove(ids_, found);
     std::lock_guard<std::mutex> mg(mut_mu);
+    loc_sync();
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     // (A) no set lock: which rows?  set.go:163-193 walks the blocks and block.go:136-147 scans every IDs[]; the
     // locator answers the same question (first block holding the id, last row in it) in O(1) per id, and searches
@@ -1430,6 +1445,7 @@ int Set::update(int64_t n, const uint8_t *values, const std::vector<std::string>
     if (n == 0) return GF_OK;
     if (is_multi()) return multi_update(n, values, ids_, found);
     std::lock_guard<std::mutex> mg(mut_mu);
+    loc_sync();
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1455,6 +1471,7 @@ int Set::read(const std::vector<std::string> &ids_, uint8_t *out, std::vector<ui
     found.assign(ids_.size(), 0);
     if (is_multi()) return multi_read(ids_, out, found);
     std::lock_guard<std::mutex> mg(mut_mu);  // (the id locator is only stable between mutations)
+    loc_sync();
     SharedGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = ctx->bind();
@@ -1482,6 +1499,7 @@ int Set::compact(int64_t *reclaimed)
     if (precision != 4) return GF_ERR_UNSUPPORTED;
     if (is_multi()) return multi_compact(reclaimed);
     std::lock_guard<std::mutex> mg(mut_mu);
+    loc_sync();
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);
@@ -1595,6 +1613,7 @@ int Set::destroy()
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     if (is_multi()) return multi_destroy();
     std::lock_guard<std::mutex> mg(mut_mu);
+    loc_sync();
     ExclusiveGuard g(lock);
     if (destroyed) return GF_ERR_FEATURE_SET_NOT_FOUND;
     int rc = quiesce(ctx);

@@ -12,6 +12,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <future>
 #include <unordered_map>
 #include <vector>
 
@@ -335,6 +336,15 @@ struct gf_set {
     std::vector<ImplicitRange> implicit_ranges;     // sorted by first; ids "<implicit_prefix>%011d"
     std::string implicit_prefix;
     bool has_dups = false;
+    // Add's last phase -- the locator learns the new ids -- runs on a helper thread while the caller returns (and stages
+    // its next Add); everything that reads or writes the locator, the blocks' id tables or `has_dups` joins it first
+    mutable std::mutex loc_job_mu;
+    mutable std::future<void> loc_job;
+    void loc_sync() const
+    {
+        std::lock_guard<std::mutex> g(loc_job_mu);
+        if (loc_job.valid()) loc_job.get();
+    }
     bool find(const std::string &id, int *pos, int *row) const;
     bool find_implicit(const std::string &id, int *pos, int *row) const;
     void note_id(const std::string &id, int pos, int row);
