@@ -1042,8 +1042,7 @@ __device__ __forceinline__ float exact_dot(const float *__restrict__ x, const fl
 __global__ void __launch_bounds__(256)
     rescore_kernel(const Segment *__restrict__ segs, const uint32_t *__restrict__ seg_slot_base, int nseg, int dims,
                    const unsigned int *__restrict__ d_cnt, const float *__restrict__ queries, int kp,
-                   const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact,
-                   const unsigned int *__restrict__ d_need)
+                   const unsigned long long *__restrict__ d_sel, unsigned long long *__restrict__ d_exact)
 {
     pdl_wait();
     pdl_launch_dependents();
@@ -1051,7 +1050,6 @@ __global__ void __launch_bounds__(256)
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int qi = blockIdx.y;
     if (w >= kp) return;
-    if (d_need != nullptr && (unsigned)w >= d_need[qi]) return;  // beyond what this query's certificate needs
     if (d_cnt != nullptr && (unsigned)w >= d_cnt[qi]) return;  // unsorted candidate buffer: only cnt entries are valid
     const unsigned long long key = d_sel[(size_t)qi * kp + w];
     if (key == 0ull) {
@@ -1216,7 +1214,7 @@ __device__ __forceinline__ void fixup_list(const FixupPlan &fix)
 
 // per query: sort the re-scored keys, emit the best K, and certify: the K-th exact score must beat
 // everything a row outside the re-scored set could reach (its approx ceiling + the TF32 error bound).
-//   all == 0: d_exact [q][kp] holds the best kp candidates by approx score (select_kernel)
+//   all == 0: d_exact [q][kp] holds the best kp candidates by approx score, d_sel their approximate keys
 //   all == 1: d_exact [q][kp = cap] holds ALL min(cnt, cap) collected candidates
 __global__ void __launch_bounds__(256)
     finalize_kernel(const unsigned long long *__restrict__ d_exact, const unsigned long long *__restrict__ d_sel,
@@ -1224,8 +1222,7 @@ __global__ void __launch_bounds__(256)
                     int all, int K, long long rows_total, const float *__restrict__ qnorm2,
                     const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
                     const float *__restrict__ qres2, const unsigned int *__restrict__ maxres2_bits,
-                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags, const FixupPlan fix,
-                    const unsigned int *__restrict__ d_need)
+                    unsigned long long *__restrict__ d_out, unsigned int *__restrict__ d_flags, const FixupPlan fix)
 {
     __shared__ unsigned long long buf[kGemmCandCap];
     __shared__ int s_cnt;
@@ -1234,8 +1231,7 @@ __global__ void __launch_bounds__(256)
     const int qi = blockIdx.x;
     const unsigned int n = cnt[qi];
     const int selected = all ? (int)(n < cap ? n : cap) : (int)((unsigned)kp < n ? (unsigned)kp : n);
-    // select_kernel re-scored only the `need` best of the selected candidates (what this query's certificate takes)
-    const int valid = (!all && d_need != nullptr && (int)d_need[qi] < selected) ? (int)d_need[qi] : selected;
+    const int valid = selected;
     unsigned long long mine[kGemmCandCap / 256];
 #pragma unroll
     for (int i = 0; i < kGemmCandCap / 256; ++i) {
@@ -1274,56 +1270,6 @@ __global__ void __launch_bounds__(256)
     }
     fixup_list(fix);
 }
-
-// best kp keys of an unsorted candidate buffer: one CTA per query
-__global__ void __launch_bounds__(256)
-    select_kernel(const unsigned long long *__restrict__ d_cand, const unsigned int *__restrict__ d_cnt,
-                  unsigned int cap, int kp, unsigned long long *__restrict__ d_sel, int K, int kp_min,
-                  const float *__restrict__ qnorm2, const unsigned int *__restrict__ maxnorm2_bits, float err_coeff,
-                  const float *__restrict__ qres2, const unsigned int *__restrict__ maxres2_bits,
-                  unsigned int *__restrict__ d_need)
-{
-    __shared__ unsigned long long buf[kGemmCandCap];
-    __shared__ int s_cnt;
-    pdl_wait();
-    pdl_launch_dependents();
-    const int qi = blockIdx.x;
-    unsigned int n = d_cnt[qi];
-    if (n > cap) n = cap;
-    unsigned long long mine[kGemmCandCap / 256];
-#pragma unroll
-    for (int i = 0; i < kGemmCandCap / 256; ++i) {
-        const unsigned idx = threadIdx.x + 256 * i;
-        mine[i] = idx < n ? d_cand[(size_t)qi * cap + idx] : 0ull;
-    }
-    const int m = block_topk_256(mine, kp, buf, &s_cnt);
-    for (int i = threadIdx.x; i < kp; i += blockDim.x) d_sel[(size_t)qi * kp + i] = buf[i];
-    if (d_need == nullptr) return;
-    // How deep must the exact re-score go for the certificate to hold?  With a = the K-th best APPROXIMATE score and
-    // delta the pass's error bound, every row whose approximate score reaches a - 2.25 delta is re-scored: the K best
-    // exact scores are then >= a - delta, everything left out is < a - 2.25 delta, and finalize_kernel's test
-    // (K-th exact > ceiling + delta) cannot fail -- unless more than kp rows are that close (then it flags).
-    // A fixed depth (K' = 3K + 64) certified uniform data but refused a third of the queries on clustered data,
-    // where a hundred near neighbours sit inside delta of each other.
-    const int have = m < kp ? m : kp;
-    int need = have;
-    if (have > K) {
-        const float delta = cert_delta(qi, qnorm2, maxnorm2_bits, err_coeff, qres2, maxres2_bits);
-        const float cut = key_score(buf[K - 1]) - 2.25f * delta;
-        int cntv = 0;
-        for (int i = threadIdx.x; i < have; i += blockDim.x) cntv += (key_score(buf[i]) >= cut) ? 1 : 0;
-        __shared__ int s_need;
-        if (threadIdx.x == 0) s_need = 0;
-        __syncthreads();
-        if (cntv) atomicAdd(&s_need, cntv);
-        __syncthreads();
-        need = s_need;
-        if (need < kp_min) need = kp_min;
-        if (need > have) need = have;
-    }
-    if (threadIdx.x == 0) d_need[qi] = (unsigned int)need;
-}
-
 
 // ------------------------------------------------------------------ two-pass chain: the fused tail (gf_kernels.h)
 __global__ void __launch_bounds__(256) collect_tail_kernel(const CollectTail a, const FixupPlan fix)
@@ -1968,15 +1914,6 @@ cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, 
     return cudaGetLastError();
 }
 
-cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *d_cnt, unsigned int cap, int q, int kp,
-                          unsigned long long *d_sel, cudaStream_t stream, const SelectNeed &need)
-{
-    if (cap > (unsigned)kGemmCandCap || kp > kGemmCandCap) return cudaErrorInvalidValue;
-    return launch_chain(select_kernel, dim3(q), dim3(256), 0, stream, d_cand, d_cnt, cap, kp, d_sel, need.K, need.kp_min,
-                        need.d_qnorm2, need.d_maxnorm2_bits, need.err_coeff, need.d_qres2, need.d_maxres2_bits,
-                        need.d_need);
-}
-
 cudaError_t collect_tail_launch(const CollectTail &t, const FixupPlan &fix, cudaStream_t stream)
 {
     if (t.cap > (unsigned)kGemmCandCap || t.kp_sel > 1024 || t.K > t.kp_sel || t.K + 32 > 1024 || t.q < 1 ||
@@ -2014,12 +1951,11 @@ cudaError_t grouptop_tail_launch(const GtTail &t, cudaStream_t stream)
 
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
                            const float *d_queries_padded, int kp, const unsigned long long *d_sel,
-                           const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream,
-                           const unsigned int *d_need)
+                           const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream)
 {
     dim3 grid((kp * 32 + 255) / 256, q);
     return launch_chain(rescore_kernel, grid, dim3(256), 0, stream, d_segs, d_seg_slot_base, nseg, dims, d_cnt,
-                        d_queries_padded, kp, d_sel, d_exact, d_need);
+                        d_queries_padded, kp, d_sel, d_exact);
 }
 
 cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned long long *d_sel,
@@ -2027,12 +1963,11 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
                             float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
                             unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
-                            cudaStream_t stream, const unsigned int *d_need)
+                            cudaStream_t stream)
 {
     if (kp > kGemmCandCap || K > kp) return cudaErrorInvalidValue;
     return launch_chain(finalize_kernel, dim3(q), dim3(256), 0, stream, d_exact, d_sel, d_cnt, d_thr, cap, kp, all, K,
-                        rows_total, d_qnorm2, d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags, fix,
-                        d_need);
+                        rows_total, d_qnorm2, d_maxnorm2_bits, err_coeff, d_qres2, d_maxres2_bits, d_out, d_flags, fix);
 }
 
 }  // namespace gf

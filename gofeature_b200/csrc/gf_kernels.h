@@ -154,24 +154,9 @@ cudaError_t rownorm_max_launch(const Segment *d_segs, int nseg, int dims, unsign
                                cudaStream_t stream);
 cudaError_t threshold_launch(const float *d_tilemax, int ntiles, int nq, int q, int m, float *d_thr,
                              unsigned int *d_cnt, cudaStream_t stream);
-// best kp of each query's candidate buffer (unsorted, cnt valid entries) -> d_sel [q][kp] descending
-// ... and, with d_need, how many of them (best first) the exact re-score must cover for the certificate to hold:
-// every candidate whose approximate score reaches (K-th best approximate score) - 2.25 delta, at least kp_min
-struct SelectNeed {
-    int K = 0, kp_min = 0;
-    const float *d_qnorm2 = nullptr;
-    const unsigned int *d_maxnorm2_bits = nullptr;
-    float err_coeff = 0.f;
-    const float *d_qres2 = nullptr;
-    const unsigned int *d_maxres2_bits = nullptr;
-    unsigned int *d_need = nullptr;  // [q] out; null: no depth is computed (everything selected is re-scored)
-};
-cudaError_t select_launch(const unsigned long long *d_cand, const unsigned int *d_cnt, unsigned int cap, int q, int kp,
-                          unsigned long long *d_sel, cudaStream_t stream, const SelectNeed &need = SelectNeed());
 cudaError_t rescore_launch(const Segment *d_segs, const uint32_t *d_seg_slot_base, int nseg, int dims, int q,
                            const float *d_queries_padded, int kp, const unsigned long long *d_sel,
-                           const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream,
-                           const unsigned int *d_need = nullptr);
+                           const unsigned int *d_cnt, unsigned long long *d_exact, cudaStream_t stream);
 constexpr int kFixupMaxQ = 8;  // uncertified queries one device-side fix-up scan pass can take
 // What the LAST finalize launch of a call also does, in the last CTA to finish: flags[0..q_total) (1 =
 // uncertified) -> map[0..n) of their indices, *count = min(n, maxn), those flags cleared; what does not fit
@@ -192,7 +177,7 @@ cudaError_t finalize_launch(const unsigned long long *d_exact, const unsigned lo
                             long long rows_total, const float *d_qnorm2, const unsigned int *d_maxnorm2_bits,
                             float err_coeff, const float *d_qres2, const unsigned int *d_maxres2_bits,
                             unsigned long long *d_out, unsigned int *d_flags, int all, const FixupPlan &fix,
-                            cudaStream_t stream, const unsigned int *d_need = nullptr);
+                            cudaStream_t stream);
 
 // The large-batch (two-pass) chain's tail as ONE kernel, one CTA per query, for all queries of up to
 // kTailBatchPasses candidate passes at once (round 1 / 2a: select -> rescore -> finalize, three launches per pass of
