@@ -184,7 +184,7 @@ struct ListCtl {
     int cnt;                 // keys in the buffer
     int lock;                // 0 free, 1 held
     float tauf;              // score of tau (-inf while tau == 0): the one-compare pre-gate
-    unsigned int gate_img;   // owner-computes lists (scan_tma_kernel): score image of the owner's K-th key (0 while it has fewer)
+    int pad;
 };
 
 __device__ __forceinline__ void list_init(ListCtl *ctl)
@@ -193,7 +193,7 @@ __device__ __forceinline__ void list_init(ListCtl *ctl)
     ctl->cnt = 0;
     ctl->lock = 0;
     ctl->tauf = __int_as_float(0xff800000);  // -inf
-    ctl->gate_img = 0u;
+    ctl->pad = 0;
 }
 
 // bitonic sort (descending) of n (power of two) keys in shared memory by ONE warp
@@ -303,57 +303,6 @@ __device__ __forceinline__ void list_insert(ListCtl *ctl, unsigned long long *bu
         atomicExch(&ctl->lock, 0);
     }
     __syncwarp();
-}
-
-// Owner-computes lists (scan_tma_kernel, K <= 32).  The shared lists above serialise the warps of a CTA behind one lock
-// per query (atomicCAS + back-off + two fences per insert), and a consumer warp that is late releasing its stage stalls
-// the whole bulk-copy ring: measured on 1 M x 512 rows the gate + insert path cost 11 % of the scan's bandwidth at one
-// query and 23 % at eight (6.83 -> 6.11 and 6.69 -> 5.16 TB/s), nearly all of it in the first tiles, where every row
-// still passes and seven warps queue for the same lock.  Here every query's list (32 sorted slots, lane l owns slot l)
-// belongs to ONE consumer warp, which alone reads and writes it -- no lock, no fence; the other warps post their rare
-// candidates to the owner's mailbox (one shared-memory atomic + one store) and go on streaming, the owner drains its
-// mailboxes once per tile.  The gate is the owner's exact K-th key, at most a tile old.
-constexpr int kMailboxCap = 64;
-struct Mailbox {
-    unsigned int tail;  // next index a sender takes (atomicAdd)
-    unsigned int head;  // next index the owner consumes (written by the owner only)
-    unsigned long long slot[kMailboxCap];  // 0 = empty
-};
-
-// owner only: sorted insert of `key` into its 32-slot list; publishes the new K-th score image
-__device__ __forceinline__ void owner_list_insert(unsigned long long *buf, int K, unsigned long long key,
-                                                  unsigned int *gate_img, int lane)
-{
-    const unsigned long long my = buf[lane];
-    const unsigned long long kth = __shfl_sync(0xffffffffu, my, K - 1);
-    if (!(key > kth)) return;  // (warp-uniform)
-    const unsigned p = __popc(__ballot_sync(0xffffffffu, my > key));  // slots holding a better key: the insert position
-    const unsigned long long up = __shfl_up_sync(0xffffffffu, my, 1);
-    const unsigned long long nv = (unsigned)lane < p ? my : ((unsigned)lane == p ? key : up);
-    if ((unsigned)lane >= p) *(volatile unsigned long long *)&buf[lane] = nv;  // (senders peek at slot K-1)
-    const unsigned long long nk = __shfl_sync(0xffffffffu, nv, K - 1);
-    if (lane == 0 && nk != 0ull) *(volatile unsigned int *)gate_img = (unsigned int)(nk >> 32);
-}
-
-// owner only: consume everything posted so far
-__device__ __forceinline__ void mailbox_drain(Mailbox *mb, unsigned long long *buf, int K, unsigned int *gate_img, int lane)
-{
-    const unsigned int t = *(volatile unsigned int *)&mb->tail;
-    unsigned int h = *(volatile unsigned int *)&mb->head;
-    while (h != t) {
-        unsigned long long key;
-        do {  // (a sender stores right after it took the index: never a long wait)
-            key = *(volatile unsigned long long *)&mb->slot[h % kMailboxCap];
-        } while (key == 0ull);
-        __syncwarp();
-        if (lane == 0) {
-            *(volatile unsigned long long *)&mb->slot[h % kMailboxCap] = 0ull;
-            __threadfence_block();
-            *(volatile unsigned int *)&mb->head = h + 1;
-        }
-        ++h;
-        owner_list_insert(buf, K, key, gate_img, lane);
-    }
 }
 
 // Write the list's best K keys (descending, zero padded) to out[0..K).  One warp, no contention.

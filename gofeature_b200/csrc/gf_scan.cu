@@ -45,7 +45,6 @@ struct ScanArgs {
     int tile_rows;
     int dims;
     int per_segment;
-    int warp_lists;
     const int *q_map;             // optional: query i of this launch is row q_map[i] of `queries`
     const unsigned int *q_count;  // optional: live query count lives on the device (0 -> nothing to do)
     const unsigned long long *upper;
@@ -59,9 +58,6 @@ struct TileMeta {
 
 constexpr int kConsumerWarps = kScanConsumerWarps;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-// threads of the bulk-copy kernel: QG groups of 7 consumer warps + the producer warp
-__host__ __device__ constexpr int scan_threads(int qg) { return (kConsumerWarps * qg + 1) * 32; }
-static_assert(scan_threads(1) == kScanThreads, "one query group: 7 consumer warps + the producer");
 
 __device__ __forceinline__ void tile_range(const ScanArgs &a, uint32_t &first, uint32_t &end, uint32_t &stride,
                                            uint32_t &group)
@@ -91,24 +87,14 @@ __device__ __forceinline__ void offer(ListCtl *ctl, unsigned long long *buf, int
 // --------------------------------------------------------------------------------------
 // Bulk-copy (TMA) pipeline kernel.  D in {128,256,512,1024}; CH = D/128 chunks per lane.
 // --------------------------------------------------------------------------------------
-//
-// QG = query groups.  QT queries in registers cost QT * CH * 4 registers per thread: at QT * CH = 32 (8 queries of
-// 512-d) that is 128 of the 255 a thread can have, the CTA is 8 warps and each scheduler has two warps to hide the
-// FFMA2 / shuffle / shared-memory latencies of a 250-instruction dependent chain per row pair (ncu: issue active
-// 40 %, 5.4 TB/s).  With QG = 2 the same tile is read by two groups of 7 consumer warps, each holding HALF of the
-// queries (QW = QT / QG, 128 registers per thread, 15 warps): the arithmetic per SM is unchanged, twice as many
-// warps interleave on it, and every feature byte still crosses HBM once (shared memory is read twice).
-template <int D, int QT, int QG>
-__global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const ScanArgs a)
+template <int D, int QT>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArgs a)
 {
     constexpr int CH = D / 128;
-    constexpr int QW = QT / QG;                      // queries a consumer warp holds
-    constexpr int kWarpsAll = kConsumerWarps * QG;   // consumer warps of the CTA
     constexpr int TILE_ROWS = kScanTileBytes / (D * 4);
     constexpr int RPW = TILE_ROWS / kConsumerWarps;  // rows per warp per tile
-    constexpr int RB = (RPW >= 2 && QW * CH <= 32) ? 2 : 1;  // rows in flight per warp
+    constexpr int RB = (RPW >= 2 && QT * CH <= 32) ? 2 : 1;  // rows in flight per warp
     static_assert(RPW >= 1 && RPW % RB == 0, "tile split");
-    static_assert(QT % QG == 0 && QW >= 1, "query groups");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int stages = a.stages;
@@ -133,25 +119,18 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kWarpsAll);
+            mbar_init(&empty[s], kConsumerWarps);
         }
         mbar_fence_init();
     }
     if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
-    // locked lists: [query][list_cap]; owner-computes lists: [query][32], then one mailbox per query
-    const int list_words = a.warp_lists ? QT * 32 : QT * a.list_cap;
-    Mailbox *mbox = reinterpret_cast<Mailbox *>(lists + (size_t)QT * 32);
-    unsigned int *done_warps = reinterpret_cast<unsigned int *>(mbox + QT);  // consumer warps that have posted everything
-    for (int i = threadIdx.x; i < list_words; i += blockDim.x) lists[i] = 0ull;
-    if (a.warp_lists)
-        for (int i = threadIdx.x; i < (int)(QT * sizeof(Mailbox) / 8) + 1; i += blockDim.x)
-            reinterpret_cast<unsigned long long *>(mbox)[i] = 0ull;  // (+ the done counter behind the mailboxes)
+    for (int i = threadIdx.x; i < QT * a.list_cap; i += blockDim.x) lists[i] = 0ull;
     __syncthreads();
 
     uint32_t first, end, stride, group;
     tile_range(a, first, end, stride, group);
 
-    if (warp == kWarpsAll) {
+    if (warp == kConsumerWarps) {
         // ===================== producer: one thread feeds the ring =====================
         if (lane == 0 && first < end) {
             const uint64_t policy = l2_policy_evict_first();
@@ -185,49 +164,42 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
     }
 
     // ===================== consumers =====================
-    // warp = qg * kConsumerWarps + rw: row share rw of every tile, queries [qg * QW, qg * QW + QW)
-    const int qg = warp / kConsumerWarps, rw = warp - qg * kConsumerWarps;
-    const int q0 = qg * QW;
-    float4 qreg[QW][CH];
+    float4 qreg[QT][CH];
 #pragma unroll
-    for (int qi = 0; qi < QW; ++qi) {
+    for (int qi = 0; qi < QT; ++qi) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             float v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 int e = 128 * j + 4 * lane + c;
-                const int qsrc = (q0 + qi < q_live && a.q_map != nullptr) ? a.q_map[q0 + qi] : q0 + qi;
-                v[c] = (q0 + qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+                const int qsrc = (qi < q_live && a.q_map != nullptr) ? a.q_map[qi] : qi;
+                v[c] = (qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
             }
             qreg[qi][j] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    // V = RB*QW scores are reduced together; afterwards this lane holds score index vi = b*QW + qi
-    constexpr int V = RB * QW;
+    // V = RB*QT scores are reduced together; afterwards this lane holds score index vi = b*QT + qi
+    constexpr int V = RB * QT;
     constexpr int LOG2V = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : 4;
     constexpr int GROUP = 32 >> LOG2V;  // lanes that end up with the same score
     const int vi = lane >> (5 - LOG2V);
-    const int my_b = vi / QW, my_q = q0 + vi % QW;
+    const int my_b = vi / QT, my_q = vi % QT;
     const bool my_live = my_q < q_live;
 
     const int cap = a.list_cap, K = a.K;
     int s = 0;
     uint32_t ph = 0;
     for (uint32_t t = first; t < end; t += stride) {
-        if (a.warp_lists)  // candidates the other warps posted for the queries this warp owns
-            for (int oq = warp; oq < QT; oq += kWarpsAll)
-                mailbox_drain(&mbox[oq], lists + (size_t)oq * 32, K, &ctl[oq].gate_img, lane);
         mbar_wait(&full[s], ph);
         const uint32_t vrows = meta[s].rows;
         const uint32_t slot0 = meta[s].slot0;
         // one-compare pre-gate, refreshed per tile; a stale (lower) value only lets extra keys through
-        const float tau_l = a.warp_lists ? image_score(*(volatile unsigned int *)&ctl[my_q].gate_img)  // (0 -> NaN: all pass)
-                                         : *(volatile float *)&ctl[my_q].tauf;
+        const float tau_l = *(volatile float *)&ctl[my_q].tauf;
         const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * (kScanTileBytes / 4));
 #pragma unroll
         for (int rb = 0; rb < RPW; rb += RB) {
-            const int r0 = rw * RPW + rb;
+            const int r0 = warp * RPW + rb;
             float4 x[RB][CH];
 #pragma unroll
             for (int b = 0; b < RB; ++b)
@@ -243,7 +215,7 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
 #pragma unroll
             for (int b = 0; b < RB; ++b) {
 #pragma unroll
-                for (int qi = 0; qi < QW; ++qi) {
+                for (int qi = 0; qi < QT; ++qi) {
                     // P[4l..4l+3] as two packed pairs: fma.rn.f32x2 (FFMA2) is two independent IEEE fmas
                     float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -253,7 +225,7 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
                         p23 = __ffma2_rn(make_float2(x[b][j].z, x[b][j].w),
                                          make_float2(qreg[qi][j].z, qreg[qi][j].w), p23);
                     }
-                    tsum[b * QW + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
+                    tsum[b * QT + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
                 }
             }
             const float sc = canonical_reduce_many<V>(tsum, lane);
@@ -265,29 +237,9 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
                 const float ls = __shfl_sync(0xffffffffu, sc, leader);
                 const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lvi * GROUP));
                 bal &= ~gmask;
-                const int lb = lvi / QW, lq = q0 + lvi % QW;
+                const int lb = lvi / QT, lq = lvi % QT;
                 const unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + lq] : ~0ull;
-                if (a.warp_lists) {
-                    const unsigned long long key = make_key(ls, slot0 + r0 + lb);
-                    unsigned long long *lst = lists + (size_t)lq * 32;
-                    // (a peek at the owner's K-th key: it only grows, a stale value lets an extra candidate through)
-                    if (key > *(volatile unsigned long long *)&lst[K - 1] && key < up) {
-                        if (lq % kWarpsAll == warp) {
-                            owner_list_insert(lst, K, key, &ctl[lq].gate_img, lane);
-                        } else {
-                            Mailbox *mb = &mbox[lq];
-                            unsigned int idx = 0;
-                            if (lane == 0) idx = atomicAdd(&mb->tail, 1u);
-                            idx = __shfl_sync(0xffffffffu, idx, 0);
-                            // mailbox full: serve this warp's own mailboxes meanwhile (somebody may be waiting on them)
-                            while (idx - *(volatile unsigned int *)&mb->head >= (unsigned)kMailboxCap)
-                                for (int oq = warp; oq < QT; oq += kWarpsAll)
-                                    mailbox_drain(&mbox[oq], lists + (size_t)oq * 32, K, &ctl[oq].gate_img, lane);
-                            if (lane == 0) *(volatile unsigned long long *)&mb->slot[idx % kMailboxCap] = key;
-                        }
-                    }
-                } else
-                    offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
+                offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
             }
         }
         if (++s == stages) {
@@ -296,33 +248,11 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
         }
     }
 
-    if (a.warp_lists) {
-        // No plain barrier here: a warp that is done keeps serving its mailboxes until EVERY warp has posted its last
-        // candidate -- a sender up to a ring's depth behind could otherwise fill the mailbox of an owner that already
-        // waits at the barrier (rows sorted by score make every row a candidate) and block for ever.
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            atomicAdd(done_warps, 1u);
-        }
-        bool all_done;
-        do {
-            all_done = *(volatile unsigned int *)done_warps >= (unsigned)kWarpsAll;  // (read BEFORE the drain it covers)
-            __threadfence_block();
-            for (int oq = warp; oq < QT; oq += kWarpsAll)
-                mailbox_drain(&mbox[oq], lists + (size_t)oq * 32, K, &ctl[oq].gate_img, lane);
-        } while (!all_done);
-    } else {
-        named_bar_sync(1, kWarpsAll * 32);
-    }
-    for (int qi = warp; qi < q_live && qi < QT; qi += kWarpsAll) {  // (the owner of qi flushes it)
+    named_bar_sync(1, kConsumerThreads);
+    for (int qi = warp; qi < q_live && qi < QT; qi += kConsumerWarps) {
         unsigned long long *out =
             a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
-        if (a.warp_lists) {
-            for (int i = lane; i < K; i += 32) out[i] = lists[(size_t)qi * 32 + i];
-        } else {
-            list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
-        }
+        list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
     }
 }
 
@@ -423,13 +353,10 @@ cudaError_t launch_tma(const ScanPlan &plan, const ScanArgs &args, cudaStream_t 
     if constexpr (QT * D > 4096) {
         return cudaErrorInvalidValue;
     } else {
-        // the register-heaviest shapes (QT * D / 128 = 32: 8 queries of 512-d, 4 of 1024-d) split the queries over
-        // two groups of consumer warps
-        constexpr int QG = (QT * D == 4096 && QT >= 2) ? 2 : 1;
-        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT, QG>, plan.smem_bytes);
+        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT>, plan.smem_bytes);
         if (e != cudaSuccess) return e;
         dim3 grid(plan.grid_x, plan.groups);
-        return launch_chain(scan_tma_kernel<D, QT, QG>, grid, dim3(scan_threads(QG)), plan.smem_bytes, stream, args);
+        return launch_chain(scan_tma_kernel<D, QT>, grid, dim3(kScanThreads), plan.smem_bytes, stream, args);
     }
 }
 
@@ -484,8 +411,6 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
     size_t lists_bytes = (size_t)p.qt * p.list_cap * 8;
     int tr = scan_tile_rows(dims);
     p.tma = aligned16 && tr > 0 && p.qt * dims <= 4096;
-    p.warp_lists = p.tma && K <= 32;
-    if (p.warp_lists) lists_bytes = (size_t)p.qt * (32 * 8 + sizeof(Mailbox)) + 16;
     if (p.tma) {
         p.tile_rows = tr;
         size_t fixed = 1024;
@@ -532,7 +457,6 @@ cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, u
     a.tile_rows = plan.tile_rows;
     a.dims = plan.dims;
     a.per_segment = (plan.groups != 1) ? 1 : 0;
-    a.warp_lists = plan.warp_lists ? 1 : 0;
     a.upper = d_upper;
     a.partial = d_partial;
     if (plan.tma) {
