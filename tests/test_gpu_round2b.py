@@ -7,8 +7,8 @@ for bit):
   one tail group (> 1 024 queries);
 * the int8 COLLECT epilogue's group test (maximum of 8 accumulators against the smallest of 8 thresholds) with rows whose
   scales differ by orders of magnitude, zero rows and negative-only scores;
-* the exact scan's owner-computes candidate lists + mailboxes (K <= 32) on rows SORTED by score, where every row is a
-  candidate until the very end (the case that would fill a mailbox behind a finished owner), for 1 .. 8 queries.
+* the exact scan on rows SORTED by score, where every row is a candidate until the very end (the case that hung the
+  withdrawn owner-computes lists), for 1 .. 8 queries.
 """
 import os
 
@@ -82,7 +82,7 @@ def test_collect_group_test_with_mixed_row_scales(gpu_ctx):
 
 @pytest.mark.parametrize("q", [1, 2, 4, 8])
 @pytest.mark.parametrize("dims", [128, 512])
-def test_scan_mailboxes_on_sorted_rows(gpu_ctx, q, dims):
+def test_scan_on_sorted_rows(gpu_ctx, q, dims):
     n, limit = 60_000, 10
     rows = ol.synth_rows(777, 0, n, dims)
     queries = ol.synth_rows(778, 0, q, dims)
