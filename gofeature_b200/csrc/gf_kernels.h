@@ -32,6 +32,7 @@ struct ScanPlan {
     int groups;        // 1 (set-wide top-K) or nseg (per-block top-K)
     size_t smem_bytes;
     bool tma;          // bulk-copy fast path (dims in {128,256,512,1024}, 16-byte aligned blocks)
+    bool warp_lists;   // bulk-copy path, sorted lists (K <= 128): every query's list is owned by one consumer warp, the others post to its mailbox (gf_device.cuh)
 };
 
 // tile_rows for a given dims on the bulk-copy path (0 = not eligible)

@@ -45,6 +45,7 @@ struct ScanArgs {
     int tile_rows;
     int dims;
     int per_segment;
+    int warp_lists;
     const int *q_map;             // optional: query i of this launch is row q_map[i] of `queries`
     const unsigned int *q_count;  // optional: live query count lives on the device (0 -> nothing to do)
     const unsigned long long *upper;
@@ -58,6 +59,9 @@ struct TileMeta {
 
 constexpr int kConsumerWarps = kScanConsumerWarps;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
+// threads of the bulk-copy kernel: QG groups of 7 consumer warps + the producer warp
+__host__ __device__ constexpr int scan_threads(int qg) { return (kConsumerWarps * qg + 1) * 32; }
+static_assert(scan_threads(1) == kScanThreads, "one query group: 7 consumer warps + the producer");
 
 __device__ __forceinline__ void tile_range(const ScanArgs &a, uint32_t &first, uint32_t &end, uint32_t &stride,
                                            uint32_t &group)
@@ -80,21 +84,35 @@ __device__ __forceinline__ void offer(ListCtl *ctl, unsigned long long *buf, int
                                       uint32_t slot, unsigned long long upper, int lane)
 {
     unsigned long long key = make_key(score, slot);
-    unsigned long long tau = *(volatile unsigned long long *)&ctl->tau;
+    // (one lane reads the gate and broadcasts it: other warps change it meanwhile, and list_insert is warp-collective)
+    unsigned long long tau = 0ull;
+    if (lane == 0) tau = *(volatile unsigned long long *)&ctl->tau;
+    tau = __shfl_sync(0xffffffffu, tau, 0);
     if (key > tau && key < upper) list_insert(ctl, buf, cap, K, key, lane);
 }
 
 // --------------------------------------------------------------------------------------
 // Bulk-copy (TMA) pipeline kernel.  D in {128,256,512,1024}; CH = D/128 chunks per lane.
 // --------------------------------------------------------------------------------------
-template <int D, int QT>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArgs a)
+//
+// QG = query groups.  QT queries in registers cost QT * CH * 4 registers per thread: at QT * CH = 32 (8 queries of
+// 512-d) that is 128 of the 255 a thread can have, the CTA is 8 warps and each scheduler has two warps to hide the
+// FFMA2 / shuffle / shared-memory latencies of a 250-instruction dependent chain per row pair (ncu: issue active
+// 40 %, 5.4 TB/s).  With QG = 2 the same tile is read by two groups of 7 consumer warps, each holding HALF of the
+// queries (QW = QT / QG, 128 registers per thread, 15 warps): the arithmetic per SM is unchanged, twice as many
+// warps interleave on it, and every feature byte still crosses HBM once (shared memory is read twice).
+// WL: owner-computes lists + mailboxes (compile-time: the locked-list build carries none of their code in its loop)
+template <int D, int QT, int QG, bool WL>
+__global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const ScanArgs a)
 {
     constexpr int CH = D / 128;
+    constexpr int QW = QT / QG;                      // queries a consumer warp holds
+    constexpr int kWarpsAll = kConsumerWarps * QG;   // consumer warps of the CTA
     constexpr int TILE_ROWS = kScanTileBytes / (D * 4);
     constexpr int RPW = TILE_ROWS / kConsumerWarps;  // rows per warp per tile
-    constexpr int RB = (RPW >= 2 && QT * CH <= 32) ? 2 : 1;  // rows in flight per warp
+    constexpr int RB = (RPW >= 2 && QW * CH <= 32) ? 2 : 1;  // rows in flight per warp
     static_assert(RPW >= 1 && RPW % RB == 0, "tile split");
+    static_assert(QT % QG == 0 && QW >= 1, "query groups");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int stages = a.stages;
@@ -119,18 +137,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(&empty[s], kWarpsAll);
         }
         mbar_fence_init();
     }
     if (threadIdx.x < QT) list_init(&ctl[threadIdx.x]);
-    for (int i = threadIdx.x; i < QT * a.list_cap; i += blockDim.x) lists[i] = 0ull;
+    // lists: [query][list_cap]; owner-computes mode: one mailbox per query behind them, then the done counter
+    const int list_words = QT * a.list_cap;
+    Mailbox *mbox = reinterpret_cast<Mailbox *>(lists + (size_t)QT * a.list_cap);
+    unsigned int *done_warps = reinterpret_cast<unsigned int *>(mbox + QT);  // consumer warps that have posted everything
+    for (int i = threadIdx.x; i < list_words; i += blockDim.x) lists[i] = 0ull;
+    if (WL)
+        for (int i = threadIdx.x; i < (int)(QT * sizeof(Mailbox) / 8) + 1; i += blockDim.x)
+            reinterpret_cast<unsigned long long *>(mbox)[i] = 0ull;  // (+ the done counter behind the mailboxes)
     __syncthreads();
 
     uint32_t first, end, stride, group;
     tile_range(a, first, end, stride, group);
 
-    if (warp == kConsumerWarps) {
+    if (warp == kWarpsAll) {
         // ===================== producer: one thread feeds the ring =====================
         if (lane == 0 && first < end) {
             const uint64_t policy = l2_policy_evict_first();
@@ -164,34 +189,49 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
     }
 
     // ===================== consumers =====================
-    float4 qreg[QT][CH];
+    // warp = qg * kConsumerWarps + rw: row share rw of every tile, queries [qg * QW, qg * QW + QW)
+    const int qg = warp / kConsumerWarps, rw = warp - qg * kConsumerWarps;
+    const int q0 = qg * QW;
+    float4 qreg[QW][CH];
 #pragma unroll
-    for (int qi = 0; qi < QT; ++qi) {
+    for (int qi = 0; qi < QW; ++qi) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             float v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 int e = 128 * j + 4 * lane + c;
-                const int qsrc = (qi < q_live && a.q_map != nullptr) ? a.q_map[qi] : qi;
-                v[c] = (qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
+                const int qsrc = (q0 + qi < q_live && a.q_map != nullptr) ? a.q_map[q0 + qi] : q0 + qi;
+                v[c] = (q0 + qi < q_live) ? a.queries[(long long)qsrc * a.q_stride + (long long)e * a.l_stride] : 0.0f;
             }
             qreg[qi][j] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    // V = RB*QT scores are reduced together; afterwards this lane holds score index vi = b*QT + qi
-    constexpr int V = RB * QT;
+    // V = RB*QW scores are reduced together; afterwards this lane holds score index vi = b*QW + qi
+    constexpr int V = RB * QW;
     constexpr int LOG2V = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : 4;
     constexpr int GROUP = 32 >> LOG2V;  // lanes that end up with the same score
     const int vi = lane >> (5 - LOG2V);
-    const int my_b = vi / QT, my_q = vi % QT;
+    const int my_b = vi / QW, my_q = q0 + vi % QW;
     const bool my_live = my_q < q_live;
 
     const int cap = a.list_cap, K = a.K;
     int s = 0;
     uint32_t ph = 0;
     for (uint32_t t = first; t < end; t += stride) {
-        mbar_wait(&full[s], ph);
+        if (WL) {
+            // candidates the other warps posted for the queries this warp owns -- also WHILE it waits for the tile: a
+            // sender blocked on one of these mailboxes may not have released its stage yet (tiles of several row pairs
+            // per warp, 128 / 256-d), and the producer, hence this wait, would then depend on it for ever (rows sorted
+            // by score: tests/test_gpu_round2b.py)
+            for (;;) {
+                for (int oq = warp; oq < QT; oq += kWarpsAll)
+                    mailbox_drain(&mbox[oq], &ctl[oq], lists + (size_t)oq * cap, cap, K, lane);
+                if (__all_sync(0xffffffffu, mbar_try_wait(&full[s], ph))) break;
+            }
+        } else {
+            mbar_wait(&full[s], ph);
+        }
         const uint32_t vrows = meta[s].rows;
         const uint32_t slot0 = meta[s].slot0;
         // one-compare pre-gate, refreshed per tile; a stale (lower) value only lets extra keys through
@@ -199,7 +239,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * (kScanTileBytes / 4));
 #pragma unroll
         for (int rb = 0; rb < RPW; rb += RB) {
-            const int r0 = warp * RPW + rb;
+            const int r0 = rw * RPW + rb;
             float4 x[RB][CH];
 #pragma unroll
             for (int b = 0; b < RB; ++b)
@@ -215,7 +255,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
 #pragma unroll
             for (int b = 0; b < RB; ++b) {
 #pragma unroll
-                for (int qi = 0; qi < QT; ++qi) {
+                for (int qi = 0; qi < QW; ++qi) {
                     // P[4l..4l+3] as two packed pairs: fma.rn.f32x2 (FFMA2) is two independent IEEE fmas
                     float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -225,7 +265,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
                         p23 = __ffma2_rn(make_float2(x[b][j].z, x[b][j].w),
                                          make_float2(qreg[qi][j].z, qreg[qi][j].w), p23);
                     }
-                    tsum[b * QT + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
+                    tsum[b * QW + qi] = __fadd_rn(__fadd_rn(p01.x, p01.y), __fadd_rn(p23.x, p23.y));
                 }
             }
             const float sc = canonical_reduce_many<V>(tsum, lane);
@@ -237,9 +277,39 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
                 const float ls = __shfl_sync(0xffffffffu, sc, leader);
                 const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lvi * GROUP));
                 bal &= ~gmask;
-                const int lb = lvi / QT, lq = lvi % QT;
+                const int lb = lvi / QW, lq = q0 + lvi % QW;
                 const unsigned long long up = a.upper ? a.upper[(size_t)group * a.q + lq] : ~0ull;
-                offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
+                if (WL) {
+                    const unsigned long long key = make_key(ls, slot0 + r0 + lb);
+                    unsigned long long *lst = lists + (size_t)lq * cap;
+                    // (a peek at the owner's K-th key: it only grows, a stale value lets an extra candidate through;
+                    // read by one lane and broadcast -- the owner changes it meanwhile, and lanes that disagreed
+                    // would split the warp around the collective code below)
+                    unsigned long long tau0 = 0ull;
+                    if (lane == 0) tau0 = *(volatile unsigned long long *)&ctl[lq].tau;
+                    tau0 = __shfl_sync(0xffffffffu, tau0, 0);
+                    if (key > tau0 && key < up) {
+                        if (lq % kWarpsAll == warp) {
+                            owner_list_insert(&ctl[lq], lst, cap, K, key, lane);
+                        } else {
+                            Mailbox *mb = &mbox[lq];
+                            unsigned int idx = 0;
+                            if (lane == 0) idx = atomicAdd(&mb->tail, 1u);
+                            idx = __shfl_sync(0xffffffffu, idx, 0);
+                            // mailbox full: serve this warp's own mailboxes meanwhile (somebody may be waiting on them)
+                            for (;;) {
+                                unsigned int hd = 0;
+                                if (lane == 0) hd = *(volatile unsigned int *)&mb->head;
+                                hd = __shfl_sync(0xffffffffu, hd, 0);
+                                if (idx - hd < (unsigned)kMailboxCap) break;
+                                for (int oq = warp; oq < QT; oq += kWarpsAll)
+                                    mailbox_drain(&mbox[oq], &ctl[oq], lists + (size_t)oq * cap, cap, K, lane);
+                            }
+                            if (lane == 0) *(volatile unsigned long long *)&mb->slot[idx % kMailboxCap] = key;
+                        }
+                    }
+                } else
+                    offer(&ctl[lq], lists + (size_t)lq * cap, cap, K, ls, slot0 + r0 + lb, up, lane);
             }
         }
         if (++s == stages) {
@@ -248,11 +318,35 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const ScanArg
         }
     }
 
-    named_bar_sync(1, kConsumerThreads);
-    for (int qi = warp; qi < q_live && qi < QT; qi += kConsumerWarps) {
+    if (WL) {
+        // No plain barrier here: a warp that is done keeps serving its mailboxes until EVERY warp has posted its last
+        // candidate -- a sender up to a ring's depth behind could otherwise fill the mailbox of an owner that already
+        // waits at the barrier (rows sorted by score make every row a candidate) and block for ever.
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(done_warps, 1u);
+        }
+        bool all_done;
+        do {
+            unsigned int dn = 0;
+            if (lane == 0) dn = *(volatile unsigned int *)done_warps;  // (read BEFORE the drain it covers)
+            all_done = __shfl_sync(0xffffffffu, dn, 0) >= (unsigned)kWarpsAll;
+            __threadfence_block();
+            for (int oq = warp; oq < QT; oq += kWarpsAll)
+                mailbox_drain(&mbox[oq], &ctl[oq], lists + (size_t)oq * cap, cap, K, lane);
+        } while (!all_done);
+    } else {
+        named_bar_sync(1, kWarpsAll * 32);
+    }
+    for (int qi = warp; qi < q_live && qi < QT; qi += kWarpsAll) {  // (the owner of qi flushes it)
         unsigned long long *out =
             a.partial + (((size_t)group * gridDim.x + blockIdx.x) * (size_t)a.q + (size_t)qi) * (size_t)K;
-        list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
+        if (WL) {
+            for (int i = lane; i < K; i += 32) out[i] = lists[(size_t)qi * cap + i];
+        } else {
+            list_flush(&ctl[qi], lists + (size_t)qi * cap, cap, K, out, lane);
+        }
     }
 }
 
@@ -353,10 +447,25 @@ cudaError_t launch_tma(const ScanPlan &plan, const ScanArgs &args, cudaStream_t 
     if constexpr (QT * D > 4096) {
         return cudaErrorInvalidValue;
     } else {
-        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT>, plan.smem_bytes);
-        if (e != cudaSuccess) return e;
+        // the register-heaviest shapes (QT * D / 128 = 32: 8 queries of 512-d, 4 of 1024-d) split the queries over
+        // two groups of consumer warps -- with the owner-computes lists; the locked lists keep one group (twice the
+        // warps would queue for the same locks)
         dim3 grid(plan.grid_x, plan.groups);
-        return launch_chain(scan_tma_kernel<D, QT>, grid, dim3(kScanThreads), plan.smem_bytes, stream, args);
+        if constexpr (QT * D == 4096 && QT >= 2) {
+            if (plan.warp_lists) {
+                cudaError_t e2 = set_smem_attr(scan_tma_kernel<D, QT, 2, true>, plan.smem_bytes);
+                if (e2 != cudaSuccess) return e2;
+                return launch_chain(scan_tma_kernel<D, QT, 2, true>, grid, dim3(scan_threads(2)), plan.smem_bytes, stream, args);
+            }
+        }
+        if (plan.warp_lists) {
+            cudaError_t e1 = set_smem_attr(scan_tma_kernel<D, QT, 1, true>, plan.smem_bytes);
+            if (e1 != cudaSuccess) return e1;
+            return launch_chain(scan_tma_kernel<D, QT, 1, true>, grid, dim3(scan_threads(1)), plan.smem_bytes, stream, args);
+        }
+        cudaError_t e = set_smem_attr(scan_tma_kernel<D, QT, 1, false>, plan.smem_bytes);
+        if (e != cudaSuccess) return e;
+        return launch_chain(scan_tma_kernel<D, QT, 1, false>, grid, dim3(scan_threads(1)), plan.smem_bytes, stream, args);
     }
 }
 
@@ -411,6 +520,12 @@ cudaError_t scan_make_plan(int device_sms, int dims, int q, int K, uint32_t tota
     size_t lists_bytes = (size_t)p.qt * p.list_cap * 8;
     int tr = scan_tile_rows(dims);
     p.tma = aligned16 && tr > 0 && p.qt * dims <= 4096;
+    // Owner-computes lists for the sorted lists (K <= 128) -- except the consumer-bound shapes (8 queries of 512-d, 4 of
+    // 1024-d) at K <= 16: there inserts are few, and an owner warp that inserts for everybody is the warp the ring waits
+    // for.  Same box, 1 M x 512, ms per pass, locked / owner-computes: 8 queries top-10 0.371 / 0.402, top-32 0.508 /
+    // 0.464, top-100 1.31 / 0.69; 4 queries top-10 0.353 / 0.335; 1 query top-10 0.335 / 0.320, top-100 0.81 / 0.43.
+    p.warp_lists = p.tma && list_is_sorted_mode(K) && !(p.qt * dims == 4096 && p.qt >= 2 && K <= 16);
+    if (p.warp_lists) lists_bytes += (size_t)p.qt * sizeof(Mailbox) + 16;
     if (p.tma) {
         p.tile_rows = tr;
         size_t fixed = 1024;
@@ -457,6 +572,7 @@ cudaError_t scan_launch(const ScanPlan &plan, const Segment *d_segs, int nseg, u
     a.tile_rows = plan.tile_rows;
     a.dims = plan.dims;
     a.per_segment = (plan.groups != 1) ? 1 : 0;
+    a.warp_lists = plan.warp_lists ? 1 : 0;
     a.upper = d_upper;
     a.partial = d_partial;
     if (plan.tma) {

@@ -7,8 +7,10 @@ for bit):
   one tail group (> 1 024 queries);
 * the int8 COLLECT epilogue's group test (maximum of 8 accumulators against the smallest of 8 thresholds) with rows whose
   scales differ by orders of magnitude, zero rows and negative-only scores;
-* the exact scan on rows SORTED by score, where every row is a candidate until the very end (the case that hung the
-  withdrawn owner-computes lists), for 1 .. 8 queries.
+* the exact scan's owner-computes candidate lists + mailboxes on rows SORTED by score, where every row is a candidate
+  until the very end and every mailbox runs full -- the case that deadlocked the first two versions: an
+  owner waiting for a tile whose stage a blocked sender still held, and two owners spinning on each other's unwritten
+  slots -- for 1 .. 8 queries, once per shape and 40 times in a row for the shapes with mutual owners.
 """
 import os
 
@@ -82,7 +84,7 @@ def test_collect_group_test_with_mixed_row_scales(gpu_ctx):
 
 @pytest.mark.parametrize("q", [1, 2, 4, 8])
 @pytest.mark.parametrize("dims", [128, 512])
-def test_scan_on_sorted_rows(gpu_ctx, q, dims):
+def test_scan_on_sorted_rows(gpu_ctx, q, dims, repeats=1):
     n, limit = 60_000, 10
     rows = ol.synth_rows(777, 0, n, dims)
     queries = ol.synth_rows(778, 0, q, dims)
@@ -96,7 +98,13 @@ def test_scan_on_sorted_rows(gpu_ctx, q, dims):
     st.SetSearchPath(1)                              # the fused exact scan
     want = ol.scan_topk(rows, queries, limit, ol.MODE_CANONICAL, THREADS)
     gpu_ctx.ResetStats()
-    got = st.SearchArray(-2.0, limit, queries)
-    assert gpu_ctx.Stats()["scan_launches"] >= 1
-    _check(got, want)
+    for _ in range(repeats):
+        got = st.SearchArray(-2.0, limit, queries)
+        _check(got, want)
+    assert gpu_ctx.Stats()["scan_launches"] >= repeats
     cache.Close()
+
+
+@pytest.mark.parametrize("q,dims", [(2, 128), (4, 128), (8, 128), (4, 256), (2, 512)])
+def test_scan_on_sorted_rows_many_times(gpu_ctx, q, dims):
+    test_scan_on_sorted_rows(gpu_ctx, q, dims, repeats=40)
