@@ -351,6 +351,21 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
         if (RESB) mbar_init(bfull, 1);
         mbar_fence_init();
     }
+    // The feature rows of the first tile do not depend on anything this chain computes: their TMA loads go out NOW --
+    // before the wait for the query preparation, the threshold loads and the barrier below -- and only the query halves
+    // of those stages follow once the queries exist.  (A launch streams for ~80 us; ~4 us of it were start-up.)
+    int pre_stages = 0;
+    if (TM == 1 && threadIdx.x == 0 && g_count > 0 && (a.mode == 0 || a.mode == 4)) {
+        SegCursor c0;
+        uint32_t row0, valid;
+        locate_tile(a, a.tile_first + g_begin * a.tile_stride, c0, row0, valid);
+        const int slab_row0 = (int)c0.slab_row0 + (int)row0;
+        pre_stages = kblocks < Cfg::kStages ? kblocks : Cfg::kStages;
+        for (int kb = 0; kb < pre_stages; ++kb) {
+            mbar_arrive_expect_tx(&full[kb], Cfg::kStageBytes);
+            tma_load_2d(smem + (size_t)kb * Cfg::kStageBytes, &tmA, kb * kBK, slab_row0, &full[kb]);
+        }
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)Cfg::kTmemCols)
@@ -424,12 +439,16 @@ __global__ void __launch_bounds__(gemm_threads(NQ), 1)
                     slab_row[j] = (int)segc.slab_row0 + (int)row0;
                 }
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *sa = smem + (size_t)s * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                    if (itp == 0 && kb < pre_stages) {  // (its feature rows are on their way since the kernel started)
+                        if (!RESB) tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
+                    } else {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
 #pragma unroll
-                    for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
-                    if (!RESB) tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
+                        for (int j = 0; j < TM; ++j) tma_load_2d(sa + j * kABytes, &tmA, kb * kBK, slab_row[j], &full[s]);
+                        if (!RESB) tma_load_2d(sa + TM * kABytes, &tmB, kb * kBK, 0, &full[s]);
+                    }
                     if (++s == Cfg::kStages) {
                         s = 0;
                         ph ^= 1;
