@@ -572,9 +572,15 @@ def run_ours(args, rank, world, local_rank):
             subprocess.call(["make", "-C", tools], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         exe = os.path.join(tools, "gf_demo")
         if os.path.exists(exe):
-            demo = run_tool([exe, "--rows", str(args.rows_per_gpu), "--threads", str(Q), "--rounds", "10000",
-                             "--warm-rounds", str(max(args.warmup, 30)), "--limit", str(K), "--coalesce-us", "100",
-                             "--device", str(local_rank)], 300)
+            # three runs of >= 1 s each, the MEDIAN run reported (all three listed): a batch shape the coalescer forms
+            # for the first time on a workspace records its CUDA graph inside the timed rounds (tens of ms, once)
+            demo_runs = [run_tool([exe, "--rows", str(args.rows_per_gpu), "--threads", str(Q), "--rounds", "10000",
+                                   "--warm-rounds", str(max(args.warmup, 30)), "--limit", str(K), "--coalesce-us", "100",
+                                   "--device", str(local_rank)], 300) for _ in range(3)]
+            ok_runs = sorted((r for r in demo_runs if "qps" in r), key=lambda r: r["qps"])
+            demo = ok_runs[len(ok_runs) // 2] if ok_runs else demo_runs[0]
+            if ok_runs:
+                demo["runs_qps"] = [r["qps"] for r in demo_runs if "qps" in r]
             if not args.quick:
                 # config 5: 10 M rows, 4 searchers, Add / Delete 100 k rows in 10 k chunks meanwhile -- and the same
                 # searchers on the same set without the churn
@@ -675,7 +681,8 @@ def run_ours(args, rank, world, local_rank):
                        "wall_s": demo["wall_ms"] / 1e3, "p50_ms": demo["p50_ms"], "p99_ms": demo["p99_ms"],
                        "call": "%d host threads x gf_set_search(q=1), coalescing 100 us (tools/gf_demo)" % Q,
                        "coalesced_batches": demo["coalesced_batches"], "tensor_passes": demo["tensor_passes"],
-                       "self_check": demo["self_check"]}
+                       "self_check": demo["self_check"], "runs_qps": demo.get("runs_qps"),
+                       "how": "median of three runs of 10 000 rounds (>= 1.2 s each)"}
     elif demo:
         line["e2e_parallel_error"] = demo
     if churn:

@@ -2210,6 +2210,33 @@ struct KeyList {
 };
 
 // a search call waits ~0.2 ms for its stream: poll instead of paying a blocking wait's wake-up
+// The host call's results land in pinned memory: keys (8-byte words, never all ones: the score image of a NaN is 0) and
+// flags (0 / 1).  Both areas are filled with all-ones before the launch and polled until no such word is left -- every
+// word is written exactly once per call by an aligned store, so the answer is complete the moment the last sentinel is
+// gone, a few microseconds before the stream itself reports completion (kernel retirement + the driver's own
+// semaphore).  The stream is still consulted now and then: an error ends the wait, and so does its completion.
+static cudaError_t wait_results(cudaStream_t s, const volatile unsigned long long *keys, size_t nkeys,
+                                const volatile unsigned int *flags, size_t nflags)
+{
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+    size_t ki = 0, fi = 0;  // everything before these is known to be written
+    for (int i = 0;; ++i) {
+        while (fi < nflags && flags[fi] != 0xFFFFFFFFu) ++fi;
+        if (fi == nflags) {
+            while (ki < nkeys && keys[ki] != ~0ull) ++ki;
+            if (ki == nkeys) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                return cudaSuccess;
+            }
+        }
+        if ((i & 63) == 63) {
+            cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaErrorNotReady) return e;
+            if (std::chrono::steady_clock::now() >= deadline) return cudaStreamSynchronize(s);
+        }
+    }
+}
+
 static cudaError_t wait_stream(cudaStream_t s)
 {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
@@ -2257,11 +2284,13 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     ctx->stats.h2d_bytes += qbytes;
     // The kernels read the queries from the pinned staging buffer and the winners come back in ONE copy
     // (keys + flags): three stream operations per call.
+    memset(h_out, 0xFF, out_keys * 8);  // sentinels (wait_results)
+    memset(h_flags, 0xFF, (size_t)q * 4);
     const auto t_b = std::chrono::steady_clock::now();
     rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags, true);
     if (rc) return rc;
     const auto t_c = std::chrono::steady_clock::now();
-    GF_CUDA(wait_stream(ws->stream), GF_ERR_READ_CUDA_BUFFER);
+    GF_CUDA(wait_results(ws->stream, h_out, out_keys, h_flags, (size_t)q), GF_ERR_READ_CUDA_BUFFER);
     const auto t_d = std::chrono::steady_clock::now();
     ctx->stats.host_stage_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_b - t_a).count();
     ctx->stats.host_launch_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_c - t_b).count();
