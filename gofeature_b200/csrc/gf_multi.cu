@@ -56,6 +56,11 @@ struct SharedGuard {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+}  // namespace
+// (gf_runtime.cu) poll the pinned result words instead of the stream
+cudaError_t wait_results(cudaStream_t s, const volatile unsigned long long *keys, size_t nkeys,
+                         const volatile unsigned int *flags, size_t nflags);
+namespace {
 cudaError_t wait_stream(cudaStream_t s)
 {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
@@ -480,6 +485,10 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
         off += (size_t)part_q[i] * dims * 4;
     }
     ctx->stats.h2d_bytes += qbytes * G;  // every device reads the batch over PCIe
+    // sentinels: the root's tail writes every key and flag word exactly once (wait_results, gf_runtime.cu); a device
+    // that timed out leaves 0xFFFFFFFF in a flag, and the wait then ends with the stream itself
+    memset(h_out, 0xFF, (size_t)q * kb * 8);
+    memset(h_flags, 0xFF, (size_t)q * 4);
 
     // per-device scratch: local winners | local flags | device copy of the queries (re-runs) | scan lists at the tail
     std::vector<unsigned long long *> d_loc((size_t)G);
@@ -540,11 +549,12 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
     }
     const auto t_c = std::chrono::steady_clock::now();
     shards[root]->ctx->bind();
-    cudaError_t we = wait_stream(x->ws[root]->stream);
+    cudaError_t we = wait_results(x->ws[root]->stream, h_out, (size_t)q * kb, h_flags, (size_t)q);
     if (we != cudaSuccess) return fail(cuda_fail(we, "multi-device search", GF_ERR_READ_CUDA_BUFFER));
-    for (int d = 0; d < G; ++d) {  // the others finished before the root could: these return at once
+    for (int d = 0; d < G; ++d) {  // the others pushed their winners before the root could fold: a query, rarely a wait
         if (d == root) continue;
-        cudaError_t e = cudaStreamSynchronize(x->ws[d]->stream);
+        cudaError_t e = cudaStreamQuery(x->ws[d]->stream);
+        if (e == cudaErrorNotReady) e = cudaStreamSynchronize(x->ws[d]->stream);
         if (e != cudaSuccess) return fail(cuda_fail(e, "multi-device search", GF_ERR_READ_CUDA_BUFFER));
     }
     const auto t_d = std::chrono::steady_clock::now();

@@ -2215,8 +2215,8 @@ struct KeyList {
 // word is written exactly once per call by an aligned store, so the answer is complete the moment the last sentinel is
 // gone, a few microseconds before the stream itself reports completion (kernel retirement + the driver's own
 // semaphore).  The stream is still consulted now and then: an error ends the wait, and so does its completion.
-static cudaError_t wait_results(cudaStream_t s, const volatile unsigned long long *keys, size_t nkeys,
-                                const volatile unsigned int *flags, size_t nflags)
+cudaError_t wait_results(cudaStream_t s, const volatile unsigned long long *keys, size_t nkeys,
+                         const volatile unsigned int *flags, size_t nflags)
 {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
     size_t ki = 0, fi = 0;  // everything before these is known to be written
