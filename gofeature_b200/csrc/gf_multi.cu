@@ -487,8 +487,11 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
     ctx->stats.h2d_bytes += qbytes * G;  // every device reads the batch over PCIe
     // sentinels: the root's tail writes every key and flag word exactly once (wait_results, gf_runtime.cu); a device
     // that timed out leaves 0xFFFFFFFF in a flag, and the wait then ends with the stream itself
-    memset(h_out, 0xFF, (size_t)q * kb * 8);
-    memset(h_flags, 0xFF, (size_t)q * 4);
+    const bool poll_results = (size_t)q * kb <= 8192;  // (large answers: filling and scanning the area costs more than it saves)
+    if (poll_results) {
+        memset(h_out, 0xFF, (size_t)q * kb * 8);
+        memset(h_flags, 0xFF, (size_t)q * 4);
+    }
 
     // per-device scratch: local winners | local flags | device copy of the queries (re-runs) | scan lists at the tail
     std::vector<unsigned long long *> d_loc((size_t)G);
@@ -549,7 +552,8 @@ int Set::multi_direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *p
     }
     const auto t_c = std::chrono::steady_clock::now();
     shards[root]->ctx->bind();
-    cudaError_t we = wait_results(x->ws[root]->stream, h_out, (size_t)q * kb, h_flags, (size_t)q);
+    cudaError_t we = poll_results ? wait_results(x->ws[root]->stream, h_out, (size_t)q * kb, h_flags, (size_t)q)
+                                  : wait_stream(x->ws[root]->stream);
     if (we != cudaSuccess) return fail(cuda_fail(we, "multi-device search", GF_ERR_READ_CUDA_BUFFER));
     for (int d = 0; d < G; ++d) {  // the others pushed their winners before the root could fold: a query, rarely a wait
         if (d == root) continue;

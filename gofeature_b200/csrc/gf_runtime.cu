@@ -2284,13 +2284,17 @@ int Set::direct_keys(Workspace *ws, int kb, int q, const uint8_t *const *parts, 
     ctx->stats.h2d_bytes += qbytes;
     // The kernels read the queries from the pinned staging buffer and the winners come back in ONE copy
     // (keys + flags): three stream operations per call.
-    memset(h_out, 0xFF, out_keys * 8);  // sentinels (wait_results)
-    memset(h_flags, 0xFF, (size_t)q * 4);
+    const bool poll_results = out_keys <= 8192;  // (large answers: filling and scanning the area costs more than it saves)
+    if (poll_results) {
+        memset(h_out, 0xFF, out_keys * 8);  // sentinels (wait_results)
+        memset(h_flags, 0xFF, (size_t)q * 4);
+    }
     const auto t_b = std::chrono::steady_clock::now();
     rc = topk_device(ws, ws->stream, h_q, q, dims, 1, kb, false, nullptr, h_out, search_path, h_flags, true);
     if (rc) return rc;
     const auto t_c = std::chrono::steady_clock::now();
-    GF_CUDA(wait_results(ws->stream, h_out, out_keys, h_flags, (size_t)q), GF_ERR_READ_CUDA_BUFFER);
+    GF_CUDA(poll_results ? wait_results(ws->stream, h_out, out_keys, h_flags, (size_t)q) : wait_stream(ws->stream),
+            GF_ERR_READ_CUDA_BUFFER);
     const auto t_d = std::chrono::steady_clock::now();
     ctx->stats.host_stage_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_b - t_a).count();
     ctx->stats.host_launch_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_c - t_b).count();
