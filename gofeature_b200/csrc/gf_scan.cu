@@ -59,6 +59,9 @@ struct TileMeta {
 
 constexpr int kConsumerWarps = kScanConsumerWarps;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
+// iterations after which a mailbox / tile wait gives up with a trap (each iteration is >= ~100 ns: many seconds, against
+// waits of microseconds) -- a launch failure the host reports, instead of a GPU that has to be reset
+constexpr unsigned int kSpinLimit = 1u << 26;
 // threads of the bulk-copy kernel: QG groups of 7 consumer warps + the producer warp
 __host__ __device__ constexpr int scan_threads(int qg) { return (kConsumerWarps * qg + 1) * 32; }
 static_assert(scan_threads(1) == kScanThreads, "one query group: 7 consumer warps + the producer");
@@ -224,10 +227,11 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
             // sender blocked on one of these mailboxes may not have released its stage yet (tiles of several row pairs
             // per warp, 128 / 256-d), and the producer, hence this wait, would then depend on it for ever (rows sorted
             // by score: tests/test_gpu_round2b.py)
-            for (;;) {
+            for (unsigned int spins = 0;; ++spins) {
                 for (int oq = warp; oq < QT; oq += kWarpsAll)
                     mailbox_drain(&mbox[oq], &ctl[oq], lists + (size_t)oq * cap, cap, K, lane);
                 if (__all_sync(0xffffffffu, mbar_try_wait(&full[s], ph))) break;
+                if (spins == kSpinLimit) __trap();  // (seconds: a wait that long is a bug -- fail the launch, do not hang the GPU)
             }
         } else {
             mbar_wait(&full[s], ph);
@@ -297,7 +301,8 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
                             if (lane == 0) idx = atomicAdd(&mb->tail, 1u);
                             idx = __shfl_sync(0xffffffffu, idx, 0);
                             // mailbox full: serve this warp's own mailboxes meanwhile (somebody may be waiting on them)
-                            for (;;) {
+                            for (unsigned int spins = 0;; ++spins) {
+                                if (spins == kSpinLimit) __trap();
                                 unsigned int hd = 0;
                                 if (lane == 0) hd = *(volatile unsigned int *)&mb->head;
                                 hd = __shfl_sync(0xffffffffu, hd, 0);
@@ -328,7 +333,9 @@ __global__ void __launch_bounds__(scan_threads(QG), 1) scan_tma_kernel(const Sca
             atomicAdd(done_warps, 1u);
         }
         bool all_done;
+        unsigned int spins = 0;
         do {
+            if (++spins == kSpinLimit) __trap();
             unsigned int dn = 0;
             if (lane == 0) dn = *(volatile unsigned int *)done_warps;  // (read BEFORE the drain it covers)
             all_done = __shfl_sync(0xffffffffu, dn, 0) >= (unsigned)kWarpsAll;
